@@ -1,0 +1,230 @@
+/*
+ * vkhrt_b200.h — C ABI of the B200-native hair ray-tracing hot path.
+ *
+ * This is the drop-in boundary for the ONE data-parallel path of mmzala/vkhrt
+ * that this repository replaces: primary-ray generation -> BVH traversal over
+ * per-segment hair primitives -> ray/segment intersection (Phantom / LSS / DOTS)
+ * -> closest-hit shading.  The reference exposes no FFI of its own (it is one
+ * Windows/Vulkan executable, reference source/main.cpp:3-7); the entry points
+ * below sit at the three seams of the reference where data crosses from the
+ * host into the Vulkan ray-tracing pipeline.  Each declaration cites the
+ * reference interface it replaces (paths relative to the reference root).
+ *
+ * Conventions
+ *   - plain pointers + sizes only; no C++/torch types cross this boundary;
+ *   - every call returns int: 0 = VKHRT_OK, negative = VkhrtStatus error.
+ *     Nothing aborts or throws across the ABI (the reference abort()s on
+ *     Vulkan errors, source/vk_common.cpp:5-15);
+ *   - calls on one scene are not re-entrant (the reference is single-threaded,
+ *     one graphics queue; source/renderer.cpp:83-131);
+ *   - there is NO CPU fallback: without a CUDA device every compute entry
+ *     point returns VKHRT_ERR_NO_DEVICE.
+ */
+#ifndef VKHRT_B200_H
+#define VKHRT_B200_H
+
+#include <stdint.h>
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define VKHRT_ABI_VERSION 1
+
+typedef enum VkhrtStatus {
+    VKHRT_OK = 0,
+    VKHRT_ERR_INVALID_ARGUMENT = -1,
+    VKHRT_ERR_NO_DEVICE = -2,      /* no CUDA device / driver: there is no CPU path      */
+    VKHRT_ERR_CUDA = -3,           /* a CUDA runtime call failed (see vkhrt_last_error)  */
+    VKHRT_ERR_OUT_OF_MEMORY = -4,
+    VKHRT_ERR_NOT_BUILT = -5,      /* render/refit/get_bvh before vkhrt_scene_build      */
+    VKHRT_ERR_BAD_TOPOLOGY = -6,   /* index out of range (reference logs and returns the
+                                      input unchanged, geometry_processor.cpp:606-612)   */
+    VKHRT_ERR_UNSUPPORTED = -7
+} VkhrtStatus;
+
+/* Technique = which ProcessHair* generator of the reference builds the primitives
+ * (include/resources/model/geometry_processor.hpp:4-7; the reference picks one by a
+ * source edit at source/resources/model/model_loader.cpp:334). */
+typedef enum VkhrtTechnique {
+    VKHRT_TECHNIQUE_PHANTOM = 0,   /* ProcessHairCurves: Catmull-Rom->Bezier curves + AABBs, Phantom
+                                      Ray-Hair Intersector (shaders/hair_intersection.rint)          */
+    VKHRT_TECHNIQUE_LSS = 1,       /* ProcessHairLSS: linear swept spheres (renderer.cpp:653-692)    */
+    VKHRT_TECHNIQUE_DOTS = 2       /* ProcessHairDOTS: disjoint orthogonal triangle strips           */
+} VkhrtTechnique;
+
+/* Closest-hit output colour: shaders/shading.glsl:1-11 or shaders/debug.glsl:1-7 (the
+ * reference computes Shade() and then displays the debug colour,
+ * shaders/hair_closest_hit.rchit:21-24). */
+typedef enum VkhrtShadeMode {
+    VKHRT_SHADE = 0,
+    VKHRT_SHADE_DEBUG_PRIMID = 1
+} VkhrtShadeMode;
+
+/* Where the caller's output pointers live. */
+typedef enum VkhrtMemory {
+    VKHRT_MEM_HOST = 0,
+    VKHRT_MEM_DEVICE = 1
+} VkhrtMemory;
+
+#define VKHRT_DEFAULT_RADIUS 0.02f   /* shaders/hair_intersection.rint:18, geometry_processor.cpp:635,681,765 */
+#define VKHRT_DEFAULT_T_MIN 0.001f   /* shaders/ray_gen.rgen:27 */
+#define VKHRT_DEFAULT_T_MAX 10000.0f /* shaders/ray_gen.rgen:28 */
+#define VKHRT_MISS_SEGMENT 0xFFFFFFFFu
+
+/* Scene input = the Assimp line mesh as consumed by GenerateLines
+ * (source/resources/model/geometry_processor.cpp:45-67; produced by ProcessMesh,
+ * source/resources/model/model_loader.cpp:139-206): vertex positions + uint32 index
+ * pairs; consecutive segments of one strand share an identical end/start position. */
+typedef struct VkhrtSceneDesc {
+    const float*    positions_xyz;      /* n_vertices * 3 floats, world space                      */
+    uint32_t        n_vertices;
+    const uint32_t* line_indices;       /* n_segments * 2 vertex indices                           */
+    uint32_t        n_segments;
+    const float*    radius_per_vertex;  /* nullable: n_vertices radii (LSS extension). NULL => `radius` */
+    float           radius;             /* <= 0 => VKHRT_DEFAULT_RADIUS                            */
+    int32_t         technique;          /* VkhrtTechnique                                          */
+    int32_t         device;             /* CUDA device ordinal                                     */
+} VkhrtSceneDesc;
+
+/* Per-frame input = CameraUniformData (include/resources/camera_resource.hpp:7-11) +
+ * the vkCmdTraceRaysKHR(width,height,1) launch (source/renderer.cpp:156-166) + the ray
+ * interval of shaders/ray_gen.rgen:27-28.  Matrices are column-major float[16] exactly
+ * as glm::mat4 is memcpy'd into the UBO (source/resources/camera_resource.cpp:16-22). */
+typedef struct VkhrtFrameDesc {
+    float    view_inverse[16];
+    float    proj_inverse[16];
+    uint32_t width, height;
+    float    t_min, t_max;          /* 0,0 => defaults 0.001 / 10000                               */
+    uint32_t spp;                   /* samples per pixel; 0 => 1. Sample 0 is the pixel centre
+                                       (the reference traces exactly that one, ray_gen.rgen:18)    */
+    int32_t  shade_mode;            /* VkhrtShadeMode                                              */
+    float    miss_rgb[3];           /* constant miss colour (env-map miss.rmiss is out of scope)   */
+    /* sharding (all zero => the whole frame): the frame is cut into tile_size^2-pixel tiles
+     * numbered row-major; this call traces tiles tile_first, tile_first+tile_stride, ...
+     * and writes its outputs COMPACTLY in (tile, pixel-in-tile) order when tile_stride > 1 */
+    uint32_t tile_size;             /* 0 => 64 (must be a multiple of 8)                           */
+    uint32_t tile_first;
+    uint32_t tile_stride;           /* 0 => 1                                                      */
+    int32_t  output_memory;         /* VkhrtMemory of hits_out / rgba8_out                         */
+    void*    stream;                /* cudaStream_t to run on (device outputs only); NULL => the
+                                       scene's own stream                                         */
+} VkhrtFrameDesc;
+
+/* Per-ray hit record (sample 0 of each pixel).  The reference exports only t and a
+ * normal (hitAttributeEXT, shaders/hair_intersection.rint:13,148) and the primitive id
+ * (gl_PrimitiveID); `u` (the converged curve parameter) and `segment` are added here. */
+typedef struct VkhrtHit {
+    float    t;          /* hit distance; miss: +inf                                               */
+    uint32_t segment;    /* input segment id (primitive/4 for DOTS); miss: VKHRT_MISS_SEGMENT      */
+    float    u;          /* curve / segment parameter in [0,1]                                     */
+    float    nx, ny, nz; /* unit shading normal                                                    */
+    uint32_t primitive;  /* gl_PrimitiveID equivalent (curve, LSS or triangle index)               */
+    uint32_t flags;      /* bit0 = hit                                                             */
+} VkhrtHit;
+
+/* One LBVH node: two children with their boxes, 64 bytes, read as 4 x 16-byte loads.
+ * child >> 31 == 1 => leaf; low 31 bits = position in Morton-sorted primitive order
+ * (leaf) or internal-node index.  primK = original primitive id when child K is a leaf. */
+typedef struct VkhrtBvhNode {
+    float lo0[3]; uint32_t child0;
+    float hi0[3]; uint32_t child1;
+    float lo1[3]; uint32_t prim0;
+    float hi1[3]; uint32_t prim1;
+} VkhrtBvhNode;
+
+#define VKHRT_BVH_LEAF 0x80000000u
+#define VKHRT_BVH_EMPTY 0xFFFFFFFFu
+
+/* Host copy-out of the acceleration structure for the bit-exact build check (the
+ * reference's BLAS is opaque driver state, source/bottom_level_acceleration_structure.cpp:34-78). */
+typedef struct VkhrtBvhView {
+    uint32_t      n_primitives;
+    uint32_t      n_nodes;          /* max(n_primitives - 1, 1)                                    */
+    VkhrtBvhNode* nodes;            /* caller-allocated, n_nodes entries (nullable)                */
+    uint32_t*     sorted_prim_ids;  /* caller-allocated, n_primitives entries (nullable)           */
+    uint64_t*     sorted_morton;    /* caller-allocated, n_primitives entries (nullable)           */
+    float         scene_lo[3], scene_hi[3];  /* centroid bounds used for Morton quantisation       */
+} VkhrtBvhView;
+
+/* CUDA-event milliseconds of the last call, per stage. */
+typedef struct VkhrtTiming {
+    float geometry_ms;   /* GenerateLines/Curves/AABBs/DOTS/LSS kernels                            */
+    float morton_ms, sort_ms, hierarchy_ms, refit_ms;
+    float build_total_ms;
+    float raygen_ms, trace_ms, shade_ms, render_total_ms;
+    float h2d_ms, d2h_ms;
+} VkhrtTiming;
+
+/* Per-frame traversal statistics (debug counters; filled only by vkhrt_render_stats). */
+typedef struct VkhrtTraceStats {
+    uint64_t rays;
+    uint64_t nodes_visited;     /* internal 64-byte node records fetched                           */
+    uint64_t prims_tested;      /* leaf primitives handed to the intersector                       */
+    uint64_t hits;
+    uint64_t phantom_iterations;
+} VkhrtTraceStats;
+
+typedef struct VkhrtScene VkhrtScene;
+
+/* ---- library -------------------------------------------------------------------------- */
+int         vkhrt_abi_version(void);
+int         vkhrt_device_count(void);                 /* 0 when no usable CUDA device      */
+const char* vkhrt_error_string(int status);
+const char* vkhrt_last_error(void);                   /* detail text of the last failure   */
+uint64_t    vkhrt_launch_count(void);                 /* kernels launched by this library  */
+
+/* ---- scene = ModelLoader::LoadFromFile + ProcessHair{Curves,LSS,DOTS} + Model upload ---- */
+/* replaces include/resources/model/model_loader.hpp:20, geometry_processor.hpp:4-7,
+ * source/resources/model/model.cpp:52-223.  Input arrays are copied before return. */
+int  vkhrt_scene_create(const VkhrtSceneDesc* desc, VkhrtScene** out_scene);
+/* replaces BottomLevelAccelerationStructure ctor + TopLevelAccelerationStructure ctor
+ * (source/bottom_level_acceleration_structure.cpp:34-78, top_level_...cpp:19-113): blocking. */
+int  vkhrt_scene_build(VkhrtScene* scene);
+/* new vertex positions, same topology: regenerate primitives, keep hierarchy, refit boxes */
+int  vkhrt_scene_refit(VkhrtScene* scene, const float* positions_xyz);
+int  vkhrt_scene_get_bvh(VkhrtScene* scene, VkhrtBvhView* view);
+/* host copy-out of the generated primitive buffers (ModelCreation::curveBuffer /
+ * lssPositionBuffer+lssRadiusBuffer / vertexBuffer; include/resources/model/model.hpp:113-126).
+ * floats per primitive: PHANTOM 12 (4 control points), LSS 8 (p0,r0,p1,r1), DOTS 9 (3 vertices) */
+int  vkhrt_scene_get_primitives(VkhrtScene* scene, float* out, size_t out_floats);
+uint32_t vkhrt_scene_primitive_count(const VkhrtScene* scene);
+void vkhrt_scene_destroy(VkhrtScene* scene);
+
+/* ---- frame = UpdateCameraResource + traceRaysKHR(W,H,1) + image ------------------------ */
+/* replaces source/renderer.cpp:156-166,189-195 and shaders/ray_gen.rgen:16-48.
+ * hits_out: n_local_pixels records (nullable); rgba8_out: n_local_pixels*4 bytes (nullable). */
+int  vkhrt_render(VkhrtScene* scene, const VkhrtFrameDesc* frame, VkhrtHit* hits_out, uint8_t* rgba8_out);
+/* same, and also returns the traversal counters (slower debug kernel variant) */
+int  vkhrt_render_stats(VkhrtScene* scene, const VkhrtFrameDesc* frame, VkhrtHit* hits_out,
+                        uint8_t* rgba8_out, VkhrtTraceStats* stats);
+/* number of pixels (= hit records) a frame/shard produces, incl. padding of partial tiles */
+uint64_t vkhrt_frame_local_pixels(const VkhrtFrameDesc* frame);
+/* compact (tile,pixel-in-tile) shards of all ranks, concatenated rank-major -> row-major image.
+ * device pointers; elem_bytes = 32 (hits) or 4 (rgba8). */
+int  vkhrt_untile(const VkhrtFrameDesc* frame, uint32_t world, const void* gathered, void* row_major,
+                  uint32_t elem_bytes, void* stream);
+int  vkhrt_last_timing(const VkhrtScene* scene, VkhrtTiming* timing);
+
+/* ---- wavefront pieces, individually callable (device pointers) -------------------------- */
+/* ray buffer entry: 32 bytes {ox,oy,oz,tmin, dx,dy,dz,tmax} */
+int  vkhrt_generate_rays(const VkhrtFrameDesc* frame, uint32_t sample, float* rays_out_device, int device);
+int  vkhrt_trace_rays(VkhrtScene* scene, const float* rays_device, uint64_t n_rays, VkhrtHit* hits_out_device, void* stream);
+
+/* ---- host helpers: FlyCamera (source/fly_camera.cpp:25-35) + Renderer::UpdateCameraResource -- */
+/* fov in degrees (vertical); yaw/pitch in degrees as FlyCamera (defaults -90, 0) */
+void vkhrt_camera_matrices(const float position[3], float yaw_deg, float pitch_deg, float fov_deg,
+                           float aspect, float near_plane, float far_plane,
+                           float view_inverse_out[16], float proj_inverse_out[16]);
+
+/* ---- synthetic procedural grooms (hair assets are not available offline) ---------------- */
+typedef enum VkhrtGroomStyle { VKHRT_GROOM_STRAIGHT = 0, VKHRT_GROOM_CURLY = 1 } VkhrtGroomStyle;
+/* writes n_strands*(segs+1) positions and n_strands*segs index pairs; deterministic in seed */
+int  vkhrt_groom_generate(uint32_t n_strands, uint32_t segments_per_strand, int32_t style, uint64_t seed,
+                          float* positions_xyz_out, uint32_t* line_indices_out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VKHRT_B200_H */

@@ -1,0 +1,280 @@
+"""GPU parity tests proper: the CUDA path, called through the C ABI, against the CPU oracle on the
+same seeded inputs.  Bars (BASELINE.json north_star): BVH build bit-exact; segment ids agree on
+>= 99.9 % of rays; relative hit t <= 1e-4; image PSNR >= 45 dB.  Because both sides execute the same
+fp32 operation sequence the tests additionally demand (and get) bit-identical hit records."""
+import numpy as np
+import pytest
+from conftest import default_camera, psnr
+
+pytestmark = pytest.mark.gpu
+
+TECHS = [0, 1, 2]
+TECH_NAMES = {0: "phantom", 1: "lss", 2: "dots"}
+
+
+def compare_hits(hg, ho, min_seg_agree=0.999, t_rel=1e-4):
+    assert hg.shape == ho.shape
+    both = (hg["flags"] & 1).astype(bool) & (ho["flags"] & 1).astype(bool)
+    agree = np.mean(hg["segment"] == ho["segment"])
+    assert agree >= min_seg_agree, f"segment agreement {agree}"
+    same = both & (hg["segment"] == ho["segment"])
+    if same.any():
+        rel = np.abs(hg["t"][same] - ho["t"][same]) / np.abs(ho["t"][same])
+        assert rel.max() <= t_rel, f"max rel t err {rel.max()}"
+    return agree
+
+
+def assert_bit_identical(hg, ho):
+    bad = np.nonzero(hg.view(np.uint8).reshape(-1, 32) != ho.view(np.uint8).reshape(-1, 32))[0]
+    assert bad.size == 0, f"{np.unique(bad).size} hit records differ, first {hg[bad[0]]} vs {ho[bad[0]]}"
+
+
+@pytest.fixture(scope="module")
+def small_groom(V):
+    return V.generate_groom(2000, 16, V.GROOM_CURLY)
+
+
+@pytest.mark.parametrize("tech", TECHS)
+def test_primitives_and_bvh_bit_exact(V, O, small_groom, tech):
+    pos, idx = small_groom
+    with V.Scene(pos, idx, technique=tech) as sc:
+        sc.build()
+        orc = O.OracleScene(pos, idx, technique=tech)
+        assert sc.n_primitives == orc.n_primitives
+        assert np.array_equal(sc.primitives().view(np.uint32), orc.primitives().view(np.uint32))
+        nodes, ids, morton, lohi = sc.bvh()
+        onodes, oids, omorton, olohi = orc.bvh()
+        assert np.array_equal(lohi.view(np.uint32), olohi.view(np.uint32))
+        assert np.array_equal(morton, omorton)
+        assert np.array_equal(ids, oids)
+        assert nodes.tobytes() == onodes.tobytes()
+
+
+@pytest.mark.parametrize("tech", TECHS)
+@pytest.mark.parametrize("mode", [0, 1])
+def test_render_parity_small(V, O, small_groom, tech, mode):
+    pos, idx = small_groom
+    W, H = 320, 200
+    vi, pi = default_camera(V, W, H)
+    with V.Scene(pos, idx, technique=tech) as sc:
+        sc.build()
+        orc = O.OracleScene(pos, idx, technique=tech)
+        fg = V.make_frame(vi, pi, W, H, shade_mode=mode, miss_rgb=(0.1, 0.2, 0.3))
+        fo = O.make_frame(vi, pi, W, H, shade_mode=mode, miss_rgb=(0.1, 0.2, 0.3))
+        hg, ig, _ = sc.render(fg)
+        ho, io, _ = orc.render(fo)
+        assert (ho["flags"] & 1).sum() > 1000
+        compare_hits(hg, ho)
+        assert_bit_identical(hg, ho)
+        assert psnr(ig, io) >= 45.0
+        assert np.array_equal(ig, io)
+
+
+def test_config1_straight_phantom_full_frame(V, O):
+    """BASELINE config[0]: straight groom 10k x 16, 512x512, Phantom, hit buffer only."""
+    pos, idx = V.generate_groom(10000, 16, V.GROOM_STRAIGHT)
+    W = H = 512
+    vi, pi = default_camera(V, W, H)
+    with V.Scene(pos, idx, technique=V.PHANTOM) as sc:
+        sc.build()
+        orc = O.OracleScene(pos, idx, technique=0)
+        hg, _, _ = sc.render(V.make_frame(vi, pi, W, H), rgba=False)
+        ho, _, _ = orc.render(O.make_frame(vi, pi, W, H), rgba=False)
+        assert (ho["flags"] & 1).mean() > 0.05
+        compare_hits(hg, ho)
+        assert_bit_identical(hg, ho)
+
+
+@pytest.mark.parametrize("tech", TECHS)
+def test_spp_and_sample0_hits(V, O, small_groom, tech):
+    pos, idx = small_groom
+    W, H = 160, 96
+    vi, pi = default_camera(V, W, H)
+    with V.Scene(pos, idx, technique=tech) as sc:
+        sc.build()
+        orc = O.OracleScene(pos, idx, technique=tech)
+        hg, ig, _ = sc.render(V.make_frame(vi, pi, W, H, spp=4))
+        ho, io, _ = orc.render(O.make_frame(vi, pi, W, H, spp=4))
+        assert_bit_identical(hg, ho)
+        assert np.array_equal(ig, io)
+        h1, _, _ = sc.render(V.make_frame(vi, pi, W, H, spp=1), rgba=False)
+        assert_bit_identical(h1, hg)   # the hit buffer is sample 0 = pixel centre
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_tile_shards_and_untile(V, O, small_groom, world):
+    import torch
+    pos, idx = small_groom
+    W, H, T = 200, 120, 32   # partial tiles on both axes
+    vi, pi = default_camera(V, W, H)
+    with V.Scene(pos, idx, technique=V.PHANTOM) as sc:
+        sc.build()
+        orc = O.OracleScene(pos, idx, technique=0)
+        full_h, full_i, _ = sc.render(V.make_frame(vi, pi, W, H, tile_size=T))
+        shards_h, shards_i = [], []
+        for r in range(world):
+            fg = V.make_frame(vi, pi, W, H, tile_size=T, tile_first=r, tile_stride=world)
+            fo = O.make_frame(vi, pi, W, H, tile_size=T, tile_first=r, tile_stride=world)
+            hg, ig, _ = sc.render(fg)
+            ho, io, _ = orc.render(fo, n_out=V.frame_local_pixels(fg))
+            assert_bit_identical(hg, ho)
+            assert np.array_equal(ig, io)
+            shards_h.append(hg); shards_i.append(ig)
+        gh = torch.from_numpy(np.concatenate(shards_h).view(np.uint8).reshape(-1, 32)).cuda()
+        gi = torch.from_numpy(np.concatenate(shards_i)).cuda()
+        oh = torch.empty((W * H, 32), dtype=torch.uint8, device="cuda")
+        oi = torch.empty((W * H, 4), dtype=torch.uint8, device="cuda")
+        f = V.make_frame(vi, pi, W, H, tile_size=T)
+        st = torch.cuda.current_stream().cuda_stream
+        V.untile(f, world, gh.data_ptr(), oh.data_ptr(), 32, st)
+        V.untile(f, world, gi.data_ptr(), oi.data_ptr(), 4, st)
+        torch.cuda.synchronize()
+        assert np.array_equal(oh.cpu().numpy().reshape(-1).view(V.HIT_DTYPE).view(np.uint8), full_h.view(np.uint8))
+        assert np.array_equal(oi.cpu().numpy(), full_i)
+
+
+def test_device_outputs_and_wavefront_api(V, O, small_groom):
+    import torch
+    pos, idx = small_groom
+    W, H = 128, 64
+    vi, pi = default_camera(V, W, H)
+    with V.Scene(pos, idx, technique=V.PHANTOM) as sc:
+        sc.build()
+        href, iref, _ = sc.render(V.make_frame(vi, pi, W, H))
+        st = torch.cuda.current_stream().cuda_stream
+        dh = torch.zeros((W * H, 32), dtype=torch.uint8, device="cuda")
+        di = torch.zeros((W * H, 4), dtype=torch.uint8, device="cuda")
+        f = V.make_frame(vi, pi, W, H, output_memory=V.MEM_DEVICE, stream=st)
+        sc.render_into(f, dh.data_ptr(), di.data_ptr())
+        torch.cuda.synchronize()
+        assert np.array_equal(dh.cpu().numpy().reshape(-1), href.view(np.uint8))
+        assert np.array_equal(di.cpu().numpy(), iref)
+        # wavefront: ray buffer from the generator kernel, traced by vkhrt_trace_rays
+        rays = torch.zeros((W * H, 8), dtype=torch.float32, device="cuda")
+        from vkhrt_b200.api import generate_rays
+        generate_rays(f, 0, rays.data_ptr(), 0)
+        torch.cuda.synchronize()
+        o, d = O.raygen(vi, pi, W, H, 5, 7)
+        r = rays[7 * W + 5].cpu().numpy()
+        assert np.array_equal(r[:3], o) and np.array_equal(r[4:7], d)
+        dh2 = torch.zeros_like(dh)
+        sc.trace_rays(rays.data_ptr(), W * H, dh2.data_ptr(), st)
+        torch.cuda.synchronize()
+        assert np.array_equal(dh2.cpu().numpy().reshape(-1), href.view(np.uint8))
+        # oracle on the very same ray buffer
+        ho = O.OracleScene(pos, idx, technique=0).trace_rays(rays.cpu().numpy())
+        assert np.array_equal(ho.view(np.uint8), href.view(np.uint8))
+
+
+@pytest.mark.parametrize("tech", TECHS)
+def test_refit_equals_rebuild_results(V, O, small_groom, tech):
+    pos, idx = small_groom
+    W, H = 160, 100
+    vi, pi = default_camera(V, W, H)
+    rng = np.random.default_rng(7)
+    strand = rng.normal(0, 0.05, (2000, 1, 3)).astype(np.float32)
+    pos2 = (pos.reshape(2000, 17, 3) + strand * np.linspace(0, 1, 17, dtype=np.float32)[None, :, None]).reshape(-1, 3)
+    with V.Scene(pos, idx, technique=tech) as sc:
+        sc.build()
+        sc.refit(pos2)
+        hg, ig, _ = sc.render(V.make_frame(vi, pi, W, H))
+        orc = O.OracleScene(pos2, idx, technique=tech)
+        ho, io, _ = orc.render(O.make_frame(vi, pi, W, H))
+        # a refitted tree is a different (valid) tree than a rebuilt one: results must still agree
+        compare_hits(hg, ho)
+        assert_bit_identical(hg, ho)
+        assert np.array_equal(sc.primitives().view(np.uint32), orc.primitives().view(np.uint32))
+
+
+def test_edge_cases(V, O):
+    W, H = 64, 48
+    vi, pi = default_camera(V, W, H)
+    # empty scene: every ray misses
+    with V.Scene(np.zeros((0, 3), np.float32), np.zeros((0, 2), np.uint32)) as sc:
+        sc.build()
+        h, img, _ = sc.render(V.make_frame(vi, pi, W, H, miss_rgb=(1.0, 0.5, 0.0)))
+        assert (h["flags"] == 0).all() and np.isinf(h["t"]).all() and (h["segment"] == 0xFFFFFFFF).all()
+        assert (img == np.array([255, 128, 0, 255], np.uint8)).all()
+    # one segment in front of the camera, all techniques; ragged strands (1-, 2-, 5-segment) and a
+    # reversed-index strand (connectivity by position equality, not index order)
+    pos = np.array([[-1, 150, 0], [1, 150, 0],
+                    [-2, 151, 0], [-1, 151.2, 0], [0, 151, 0],
+                    [-3, 149, 1], [-2, 149.1, 1], [-1, 149, 1], [0, 149.1, 1], [1, 149, 1], [2, 149.1, 1],
+                    [3, 152, 0], [2, 152, 0]], np.float32)
+    idx = np.array([[0, 1], [2, 3], [3, 4], [5, 6], [6, 7], [7, 8], [8, 9], [9, 10], [11, 12]], np.uint32)
+    for tech in TECHS:
+        for p, i in ((pos[:2], idx[:1]), (pos, idx)):
+            with V.Scene(p, i, technique=tech) as sc:
+                sc.build()
+                orc = O.OracleScene(p, i, technique=tech)
+                hg, ig, _ = sc.render(V.make_frame(vi, pi, W, H))
+                ho, io, _ = orc.render(O.make_frame(vi, pi, W, H))
+                assert (ho["flags"] & 1).sum() > 0
+                assert_bit_identical(hg, ho)
+                assert np.array_equal(ig, io)
+                n, ids, m, lohi = sc.bvh()
+                on, oids, om, olohi = orc.bvh()
+                assert n.tobytes() == on.tobytes() and np.array_equal(ids, oids)
+    # bad topology is an error, not a crash
+    with pytest.raises(V.VkhrtError):
+        V.Scene(pos[:2], np.array([[0, 5]], np.uint32))
+
+
+def test_lss_per_vertex_radius(V, O, small_groom):
+    pos, idx = small_groom
+    W, H = 200, 120
+    vi, pi = default_camera(V, W, H)
+    taper = np.tile(np.linspace(0.02, 0.005, 17, dtype=np.float32), 2000)
+    with V.Scene(pos, idx, technique=V.LSS, radius_per_vertex=taper) as sc:
+        sc.build()
+        orc = O.OracleScene(pos, idx, technique=1, radius_per_vertex=taper)
+        hg, ig, _ = sc.render(V.make_frame(vi, pi, W, H))
+        ho, io, _ = orc.render(O.make_frame(vi, pi, W, H))
+        assert_bit_identical(hg, ho)
+        assert np.array_equal(ig, io)
+
+
+def test_stats_counters_match_oracle_closely(V, O, small_groom):
+    pos, idx = small_groom
+    W, H = 256, 160
+    vi, pi = default_camera(V, W, H)
+    with V.Scene(pos, idx, technique=V.PHANTOM) as sc:
+        sc.build()
+        _, _, sg = sc.render(V.make_frame(vi, pi, W, H), rgba=False, stats=True)
+        _, _, so = O.OracleScene(pos, idx, technique=0).render(O.make_frame(vi, pi, W, H), rgba=False, stats=True)
+        assert sg["rays"] == so["rays"] == W * H
+        assert sg["hits"] == so["hits"]
+        # postponed candidate tests delay the closest-hit cull a little: allow a few % more visits
+        assert so["nodes_visited"] <= sg["nodes_visited"] <= 1.10 * so["nodes_visited"]
+        assert so["prims_tested"] <= sg["prims_tested"] <= 1.10 * so["prims_tested"]
+
+
+def test_full_size_config2_properties(V, O):
+    """BASELINE config[1] at full size (3.2 M segments, 1080p): size-independent properties +
+    an oracle spot check on a seeded 8192-pixel subset."""
+    pos, idx = V.generate_groom(100000, 32, V.GROOM_CURLY)
+    W, H = 1920, 1080
+    vi, pi = default_camera(V, W, H)
+    with V.Scene(pos, idx, technique=V.PHANTOM) as sc:
+        sc.build()
+        nodes, ids, morton, _ = sc.bvh()
+        n = sc.n_primitives
+        assert n == 3200000 and nodes.shape[0] == n - 1
+        assert np.array_equal(np.sort(ids), np.arange(n, dtype=np.uint32))          # a permutation
+        assert (np.diff(morton.astype(np.int64)) >= 0).all()                            # sortedness
+        leaf0 = nodes["child0"] >> 31 == 1; leaf1 = nodes["child1"] >> 31 == 1
+        assert leaf0.sum() + leaf1.sum() == n                                           # every leaf referenced once
+        leaves = np.concatenate([nodes["child0"][leaf0], nodes["child1"][leaf1]]) & 0x7FFFFFFF
+        assert np.array_equal(np.sort(leaves), np.arange(n, dtype=np.uint32))
+        h1, _, _ = sc.render(V.make_frame(vi, pi, W, H), rgba=False)
+        h2, _, _ = sc.render(V.make_frame(vi, pi, W, H), rgba=False)
+        assert h1.tobytes() == h2.tobytes()                                             # idempotent / deterministic
+        hit = (h1["flags"] & 1).astype(bool)
+        assert 0.05 < hit.mean() < 0.9
+        nrm = np.sqrt(h1["nx"][hit] ** 2 + h1["ny"][hit] ** 2 + h1["nz"][hit] ** 2)
+        assert np.abs(nrm - 1).max() < 1e-5 and (h1["u"][hit] >= 0).all() and (h1["u"][hit] <= 1).all()
+        rng = np.random.default_rng(0x5EED)
+        sub = np.sort(rng.choice(W * H, 8192, replace=False)).astype(np.uint64)
+        orc = O.OracleScene(pos, idx, technique=0)
+        ho, _, _ = orc.render(O.make_frame(vi, pi, W, H), rgba=False, pixel_subset=sub)
+        assert_bit_identical(h1[sub.astype(np.int64)], ho)

@@ -1,0 +1,290 @@
+"""ctypes host binding of include/vkhrt_b200.h.
+
+Mirrors the reference's host surface for the hot path:
+  ModelLoader::LoadFromFile + ProcessHair{Curves,LSS,DOTS}  -> Scene(positions, indices, technique)
+  BottomLevelAccelerationStructure ctor                     -> Scene.build()
+  FlyCamera::ViewMatrix/ProjectionMatrix + UpdateCameraResource -> FlyCamera.matrices()
+  Renderer::Render / vkCmdTraceRaysKHR(W,H,1)               -> Scene.render(frame)
+No compute happens in Python and there is no fallback: a missing library raises ImportError,
+a missing GPU raises VkhrtError(NO_DEVICE) from the first compute call.
+"""
+import ctypes as C
+import os
+import numpy as np
+
+PHANTOM, LSS, DOTS = 0, 1, 2
+SHADE, DEBUG_PRIMID = 0, 1
+MEM_HOST, MEM_DEVICE = 0, 1
+GROOM_STRAIGHT, GROOM_CURLY = 0, 1
+DEFAULT_SEED = 0x5EED0001
+FLOATS_PER_PRIM = {PHANTOM: 12, LSS: 8, DOTS: 9}
+
+HIT_DTYPE = np.dtype([("t", "<f4"), ("segment", "<u4"), ("u", "<f4"), ("nx", "<f4"), ("ny", "<f4"),
+                      ("nz", "<f4"), ("primitive", "<u4"), ("flags", "<u4")])
+NODE_DTYPE = np.dtype([("lo0", "<f4", 3), ("child0", "<u4"), ("hi0", "<f4", 3), ("child1", "<u4"),
+                       ("lo1", "<f4", 3), ("prim0", "<u4"), ("hi1", "<f4", 3), ("prim1", "<u4")])
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB_PATH = os.path.join(_HERE, "_lib", "libvkhrt_b200.so")
+
+
+class VkhrtError(RuntimeError):
+    def __init__(self, status, where):
+        self.status = int(status)
+        L = lib()
+        msg = L.vkhrt_error_string(self.status).decode()
+        detail = L.vkhrt_last_error().decode()
+        super().__init__(f"{where}: {msg} ({self.status}){': ' + detail if detail else ''}")
+
+
+class SceneDesc(C.Structure):
+    _fields_ = [("positions_xyz", C.c_void_p), ("n_vertices", C.c_uint32), ("line_indices", C.c_void_p),
+                ("n_segments", C.c_uint32), ("radius_per_vertex", C.c_void_p), ("radius", C.c_float),
+                ("technique", C.c_int32), ("device", C.c_int32)]
+
+
+class FrameDesc(C.Structure):
+    _fields_ = [("view_inverse", C.c_float * 16), ("proj_inverse", C.c_float * 16),
+                ("width", C.c_uint32), ("height", C.c_uint32), ("t_min", C.c_float), ("t_max", C.c_float),
+                ("spp", C.c_uint32), ("shade_mode", C.c_int32), ("miss_rgb", C.c_float * 3),
+                ("tile_size", C.c_uint32), ("tile_first", C.c_uint32), ("tile_stride", C.c_uint32),
+                ("output_memory", C.c_int32), ("stream", C.c_void_p)]
+
+
+class BvhView(C.Structure):
+    _fields_ = [("n_primitives", C.c_uint32), ("n_nodes", C.c_uint32), ("nodes", C.c_void_p),
+                ("sorted_prim_ids", C.c_void_p), ("sorted_morton", C.c_void_p),
+                ("scene_lo", C.c_float * 3), ("scene_hi", C.c_float * 3)]
+
+
+class Timing(C.Structure):
+    _fields_ = [(k, C.c_float) for k in ("geometry_ms", "morton_ms", "sort_ms", "hierarchy_ms", "refit_ms",
+                                         "build_total_ms", "raygen_ms", "trace_ms", "shade_ms",
+                                         "render_total_ms", "h2d_ms", "d2h_ms")]
+
+    def as_dict(self):
+        return {k: float(getattr(self, k)) for k, _ in self._fields_}
+
+
+class TraceStats(C.Structure):
+    _fields_ = [("rays", C.c_uint64), ("nodes_visited", C.c_uint64), ("prims_tested", C.c_uint64),
+                ("hits", C.c_uint64), ("phantom_iterations", C.c_uint64)]
+
+    def as_dict(self):
+        return {k: int(getattr(self, k)) for k, _ in self._fields_}
+
+
+# every symbol include/vkhrt_b200.h declares (tests check the library exports all of them)
+ABI_SYMBOLS = [
+    "vkhrt_abi_version", "vkhrt_device_count", "vkhrt_error_string", "vkhrt_last_error", "vkhrt_launch_count",
+    "vkhrt_scene_create", "vkhrt_scene_build", "vkhrt_scene_refit", "vkhrt_scene_get_bvh",
+    "vkhrt_scene_get_primitives", "vkhrt_scene_primitive_count", "vkhrt_scene_destroy",
+    "vkhrt_render", "vkhrt_render_stats", "vkhrt_frame_local_pixels", "vkhrt_untile", "vkhrt_last_timing",
+    "vkhrt_generate_rays", "vkhrt_trace_rays", "vkhrt_camera_matrices", "vkhrt_groom_generate",
+]
+
+_lib = None
+
+
+def library_path():
+    return _LIB_PATH
+
+
+def lib():
+    """Load the CUDA library. There is deliberately no fallback."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(_LIB_PATH):
+        raise ImportError(f"{_LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                          "(make -C vkhrt_b200/csrc). vkhrt_b200 has no CPU fallback.")
+    L = C.CDLL(_LIB_PATH)
+    L.vkhrt_abi_version.restype = C.c_int
+    L.vkhrt_device_count.restype = C.c_int
+    L.vkhrt_error_string.restype = C.c_char_p
+    L.vkhrt_error_string.argtypes = [C.c_int]
+    L.vkhrt_last_error.restype = C.c_char_p
+    L.vkhrt_launch_count.restype = C.c_uint64
+    L.vkhrt_scene_create.argtypes = [C.POINTER(SceneDesc), C.POINTER(C.c_void_p)]
+    L.vkhrt_scene_build.argtypes = [C.c_void_p]
+    L.vkhrt_scene_refit.argtypes = [C.c_void_p, C.c_void_p]
+    L.vkhrt_scene_get_bvh.argtypes = [C.c_void_p, C.POINTER(BvhView)]
+    L.vkhrt_scene_get_primitives.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t]
+    L.vkhrt_scene_primitive_count.restype = C.c_uint32
+    L.vkhrt_scene_primitive_count.argtypes = [C.c_void_p]
+    L.vkhrt_scene_destroy.argtypes = [C.c_void_p]
+    L.vkhrt_scene_destroy.restype = None
+    L.vkhrt_render.argtypes = [C.c_void_p, C.POINTER(FrameDesc), C.c_void_p, C.c_void_p]
+    L.vkhrt_render_stats.argtypes = [C.c_void_p, C.POINTER(FrameDesc), C.c_void_p, C.c_void_p, C.POINTER(TraceStats)]
+    L.vkhrt_frame_local_pixels.restype = C.c_uint64
+    L.vkhrt_frame_local_pixels.argtypes = [C.POINTER(FrameDesc)]
+    L.vkhrt_untile.argtypes = [C.POINTER(FrameDesc), C.c_uint32, C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p]
+    L.vkhrt_last_timing.argtypes = [C.c_void_p, C.POINTER(Timing)]
+    L.vkhrt_generate_rays.argtypes = [C.POINTER(FrameDesc), C.c_uint32, C.c_void_p, C.c_int]
+    L.vkhrt_trace_rays.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p]
+    L.vkhrt_camera_matrices.restype = None
+    L.vkhrt_camera_matrices.argtypes = [C.POINTER(C.c_float), C.c_float, C.c_float, C.c_float, C.c_float, C.c_float,
+                                        C.c_float, C.POINTER(C.c_float), C.POINTER(C.c_float)]
+    L.vkhrt_groom_generate.argtypes = [C.c_uint32, C.c_uint32, C.c_int32, C.c_uint64, C.c_void_p, C.c_void_p]
+    if L.vkhrt_abi_version() != 1:
+        raise ImportError("libvkhrt_b200.so ABI version mismatch")
+    _lib = L
+    return L
+
+
+def _check(rc, where):
+    if rc != 0:
+        raise VkhrtError(rc, where)
+
+
+def device_count():
+    return int(lib().vkhrt_device_count())
+
+
+def launch_count():
+    return int(lib().vkhrt_launch_count())
+
+
+def camera_matrices(position=(0.0, 150.0, 20.0), yaw=-90.0, pitch=0.0, fov=60.0, aspect=16.0 / 9.0, near=0.1, far=1000.0):
+    """(view_inverse, proj_inverse) as float32[16] column-major; defaults = reference application.cpp:65-73."""
+    pos = (C.c_float * 3)(*[float(x) for x in position])
+    vi = (C.c_float * 16)()
+    pi = (C.c_float * 16)()
+    lib().vkhrt_camera_matrices(pos, yaw, pitch, fov, aspect, near, far, vi, pi)
+    return np.array(list(vi), np.float32), np.array(list(pi), np.float32)
+
+
+class FlyCamera:
+    """Host mirror of the reference FlyCamera (source/fly_camera.cpp) without the input handling."""
+
+    def __init__(self, position=(0.0, 150.0, 20.0), fov=60.0, aspect=16.0 / 9.0, near=0.1, far=1000.0, yaw=-90.0, pitch=0.0):
+        self.position, self.fov, self.aspect, self.near, self.far, self.yaw, self.pitch = position, fov, aspect, near, far, yaw, pitch
+
+    def matrices(self):
+        return camera_matrices(self.position, self.yaw, self.pitch, self.fov, self.aspect, self.near, self.far)
+
+
+def generate_groom(n_strands, segments, style=GROOM_CURLY, seed=DEFAULT_SEED):
+    """Seeded synthetic groom -> (positions float32[n,3], line indices uint32[m,2]) in the Assimp line-mesh shape."""
+    pos = np.empty((n_strands * (segments + 1), 3), np.float32)
+    idx = np.empty((n_strands * segments, 2), np.uint32)
+    _check(lib().vkhrt_groom_generate(n_strands, segments, style, seed, pos.ctypes.data, idx.ctypes.data), "vkhrt_groom_generate")
+    return pos, idx
+
+
+def make_frame(view_inv, proj_inv, width, height, spp=1, shade_mode=SHADE, miss_rgb=(0.0, 0.0, 0.0), tile_size=0,
+               tile_first=0, tile_stride=0, t_min=0.0, t_max=0.0, output_memory=MEM_HOST, stream=None):
+    f = FrameDesc()
+    f.view_inverse[:] = [float(x) for x in np.asarray(view_inv, np.float32).reshape(16)]
+    f.proj_inverse[:] = [float(x) for x in np.asarray(proj_inv, np.float32).reshape(16)]
+    f.width, f.height, f.spp, f.shade_mode = int(width), int(height), int(spp), int(shade_mode)
+    f.t_min, f.t_max = t_min, t_max
+    f.miss_rgb[:] = [float(x) for x in miss_rgb]
+    f.tile_size, f.tile_first, f.tile_stride = tile_size, tile_first, tile_stride
+    f.output_memory = output_memory
+    f.stream = stream
+    return f
+
+
+def frame_local_pixels(frame):
+    return int(lib().vkhrt_frame_local_pixels(C.byref(frame)))
+
+
+def untile(frame, world, gathered_ptr, out_ptr, elem_bytes, stream=None):
+    _check(lib().vkhrt_untile(C.byref(frame), world, gathered_ptr, out_ptr, elem_bytes, stream), "vkhrt_untile")
+
+
+class Scene:
+    """One groom on one GPU: primitives + LBVH resident in HBM."""
+
+    def __init__(self, positions, indices, technique=PHANTOM, radius=0.02, radius_per_vertex=None, device=0):
+        self._h = None
+        pos = np.ascontiguousarray(positions, np.float32).reshape(-1, 3)
+        idx = np.ascontiguousarray(indices, np.uint32).reshape(-1, 2)
+        rpv = None if radius_per_vertex is None else np.ascontiguousarray(radius_per_vertex, np.float32)
+        if rpv is not None and rpv.shape[0] != pos.shape[0]:
+            raise ValueError("radius_per_vertex must have one entry per vertex")
+        d = SceneDesc(pos.ctypes.data if pos.size else None, pos.shape[0], idx.ctypes.data if idx.size else None, idx.shape[0],
+                      rpv.ctypes.data if rpv is not None else None, float(radius), int(technique), int(device))
+        h = C.c_void_p()
+        _check(lib().vkhrt_scene_create(C.byref(d), C.byref(h)), "vkhrt_scene_create")
+        self._h = h
+        self.technique = int(technique)
+        self.n_segments = idx.shape[0]
+
+    def close(self):
+        if getattr(self, "_h", None):
+            lib().vkhrt_scene_destroy(self._h)
+            self._h = None
+
+    __del__ = close
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    @property
+    def n_primitives(self):
+        return int(lib().vkhrt_scene_primitive_count(self._h))
+
+    def build(self):
+        _check(lib().vkhrt_scene_build(self._h), "vkhrt_scene_build")
+        return self
+
+    def refit(self, positions):
+        pos = np.ascontiguousarray(positions, np.float32)
+        _check(lib().vkhrt_scene_refit(self._h, pos.ctypes.data), "vkhrt_scene_refit")
+
+    def bvh(self):
+        v = BvhView()
+        _check(lib().vkhrt_scene_get_bvh(self._h, C.byref(v)), "vkhrt_scene_get_bvh")
+        nodes = np.zeros(v.n_nodes, NODE_DTYPE)
+        ids = np.zeros(v.n_primitives, np.uint32)
+        morton = np.zeros(v.n_primitives, np.uint64)
+        v.nodes, v.sorted_prim_ids, v.sorted_morton = nodes.ctypes.data, ids.ctypes.data, morton.ctypes.data
+        _check(lib().vkhrt_scene_get_bvh(self._h, C.byref(v)), "vkhrt_scene_get_bvh")
+        lohi = np.array(list(v.scene_lo) + list(v.scene_hi), np.float32)
+        return nodes, ids, morton, lohi
+
+    def primitives(self):
+        out = np.empty((self.n_primitives, FLOATS_PER_PRIM[self.technique]), np.float32)
+        _check(lib().vkhrt_scene_get_primitives(self._h, out.ctypes.data, out.size), "vkhrt_scene_get_primitives")
+        return out
+
+    def render(self, frame, hits=True, rgba=True, stats=False):
+        """Host-buffer render (the e2e path): returns (hits, rgba[, stats]) as numpy arrays."""
+        n = frame_local_pixels(frame)
+        frame.output_memory = MEM_HOST
+        h = np.zeros(n, HIT_DTYPE) if hits else None
+        img = np.zeros((n, 4), np.uint8) if rgba else None
+        hp = h.ctypes.data if hits else None
+        ip = img.ctypes.data if rgba else None
+        if stats:
+            st = TraceStats()
+            _check(lib().vkhrt_render_stats(self._h, C.byref(frame), hp, ip, C.byref(st)), "vkhrt_render_stats")
+            return h, img, st.as_dict()
+        _check(lib().vkhrt_render(self._h, C.byref(frame), hp, ip), "vkhrt_render")
+        return h, img, None
+
+    def render_into(self, frame, hits_ptr=None, rgba_ptr=None):
+        """Raw-pointer render (host or device pointers per frame.output_memory)."""
+        _check(lib().vkhrt_render(self._h, C.byref(frame), hits_ptr, rgba_ptr), "vkhrt_render")
+
+    def render_stats_into(self, frame, hits_ptr=None, rgba_ptr=None):
+        st = TraceStats()
+        _check(lib().vkhrt_render_stats(self._h, C.byref(frame), hits_ptr, rgba_ptr, C.byref(st)), "vkhrt_render_stats")
+        return st.as_dict()
+
+    def trace_rays(self, rays_ptr, n_rays, hits_ptr, stream=None):
+        _check(lib().vkhrt_trace_rays(self._h, rays_ptr, n_rays, hits_ptr, stream), "vkhrt_trace_rays")
+
+    def timing(self):
+        t = Timing()
+        _check(lib().vkhrt_last_timing(self._h, C.byref(t)), "vkhrt_last_timing")
+        return t.as_dict()
+
+
+def generate_rays(frame, sample, rays_ptr, device=0):
+    _check(lib().vkhrt_generate_rays(C.byref(frame), sample, rays_ptr, device), "vkhrt_generate_rays")

@@ -1,0 +1,247 @@
+// api.cu — the extern "C" boundary declared in include/vkhrt_b200.h.
+// No CPU fallback lives here: every compute entry point needs a CUDA device.
+#include "scene.h"
+#include <atomic>
+#include <cstring>
+#include <cmath>
+#include <mutex>
+#include <new>
+
+namespace vkhrt {
+
+static thread_local std::string g_last_error;
+static std::atomic<uint64_t> g_launches{0};
+
+void set_last_error(const std::string& s) { g_last_error = s; }
+void count_launch(uint64_t n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+
+static int check_device(int device)
+{
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n == 0) {
+        cudaGetLastError();
+        set_last_error("no CUDA device available (this library has no CPU path)");
+        return VKHRT_ERR_NO_DEVICE;
+    }
+    if (device < 0 || device >= n) { set_last_error("device ordinal out of range"); return VKHRT_ERR_INVALID_ARGUMENT; }
+    return VKHRT_OK;
+}
+
+__global__ void validate_indices_kernel(const uint32_t* idx, uint32_t n, uint32_t n_vertices, uint32_t* bad)
+{
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n && idx[i] >= n_vertices) atomicAdd(bad, 1u);
+}
+
+static void free_scene(DeviceScene* sc)
+{
+    if (!sc) return;
+    cudaSetDevice(sc->device);
+    cudaFree(sc->d_positions); cudaFree(sc->d_indices); cudaFree(sc->d_radius_pv);
+    cudaFree(sc->d_nodes); cudaFree(sc->d_sorted_ids); cudaFree(sc->d_sorted_morton);
+    cudaFree(sc->d_parent_internal); cudaFree(sc->d_parent_leaf); cudaFree(sc->d_refit_flags);
+    cudaFree(sc->d_primA); cudaFree(sc->d_primB);
+    cudaFree(sc->d_counters); cudaFree(sc->d_hits_scratch); cudaFree(sc->d_accum); cudaFree(sc->d_rgba_scratch);
+    if (sc->h_pinned) cudaFreeHost(sc->h_pinned);
+    for (auto& e : sc->ev) if (e) cudaEventDestroy(e);
+    if (sc->stream) cudaStreamDestroy(sc->stream);
+    if (sc->copy_stream) cudaStreamDestroy(sc->copy_stream);
+    delete sc;
+}
+
+}  // namespace vkhrt
+
+using namespace vkhrt;
+
+struct VkhrtScene { DeviceScene s; };   // opaque handle == DeviceScene
+
+extern "C" {
+
+int vkhrt_abi_version(void) { return VKHRT_ABI_VERSION; }
+
+int vkhrt_device_count(void)
+{
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+
+const char* vkhrt_error_string(int status)
+{
+    switch (status) {
+    case VKHRT_OK: return "ok";
+    case VKHRT_ERR_INVALID_ARGUMENT: return "invalid argument";
+    case VKHRT_ERR_NO_DEVICE: return "no CUDA device (there is no CPU path)";
+    case VKHRT_ERR_CUDA: return "CUDA runtime error";
+    case VKHRT_ERR_OUT_OF_MEMORY: return "out of device memory";
+    case VKHRT_ERR_NOT_BUILT: return "scene not built";
+    case VKHRT_ERR_BAD_TOPOLOGY: return "line index out of range";
+    case VKHRT_ERR_UNSUPPORTED: return "unsupported";
+    default: return "unknown status";
+    }
+}
+
+const char* vkhrt_last_error(void) { return g_last_error.c_str(); }
+uint64_t vkhrt_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
+
+int vkhrt_scene_create(const VkhrtSceneDesc* desc, VkhrtScene** out_scene)
+{
+    if (!desc || !out_scene) { set_last_error("null argument"); return VKHRT_ERR_INVALID_ARGUMENT; }
+    *out_scene = nullptr;
+    if (desc->technique < VKHRT_TECHNIQUE_PHANTOM || desc->technique > VKHRT_TECHNIQUE_DOTS) { set_last_error("unknown technique"); return VKHRT_ERR_INVALID_ARGUMENT; }
+    if ((desc->n_vertices && !desc->positions_xyz) || (desc->n_segments && !desc->line_indices)) { set_last_error("null geometry array"); return VKHRT_ERR_INVALID_ARGUMENT; }
+    const uint64_t n_prims = desc->technique == VKHRT_TECHNIQUE_DOTS ? (uint64_t)desc->n_segments * 4 : desc->n_segments;
+    if (n_prims >= 0x7FFFFFFFull) { set_last_error("too many primitives for 31-bit references"); return VKHRT_ERR_UNSUPPORTED; }
+    int rc = check_device(desc->device);
+    if (rc) return rc;
+    VK_CUDA(cudaSetDevice(desc->device));
+
+    DeviceScene* sc = new (std::nothrow) DeviceScene();
+    if (!sc) return VKHRT_ERR_OUT_OF_MEMORY;
+    sc->device = desc->device;
+    sc->technique = desc->technique;
+    sc->radius = desc->radius > 0.0f ? desc->radius : VKHRT_DEFAULT_RADIUS;
+    sc->n_vertices = desc->n_vertices;
+    sc->n_segments = desc->n_segments;
+    sc->n_prims = (uint32_t)n_prims;
+#define VK_TRY(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { set_last_error(std::string(#call) + ": " + cudaGetErrorString(e_)); free_scene(sc); return e_ == cudaErrorMemoryAllocation ? VKHRT_ERR_OUT_OF_MEMORY : VKHRT_ERR_CUDA; } } while (0)
+    cudaDeviceProp prop;
+    VK_TRY(cudaGetDeviceProperties(&prop, sc->device));
+    sc->sm_count = prop.multiProcessorCount;
+    VK_TRY(cudaStreamCreateWithFlags(&sc->stream, cudaStreamNonBlocking));
+    VK_TRY(cudaStreamCreateWithFlags(&sc->copy_stream, cudaStreamNonBlocking));
+    for (auto& e : sc->ev) VK_TRY(cudaEventCreate(&e));
+    VK_TRY(cudaMalloc(&sc->d_counters, 8 * sizeof(unsigned long long)));
+    VK_TRY(cudaMemsetAsync(sc->d_counters, 0, 8 * sizeof(unsigned long long), sc->stream));
+    VK_TRY(cudaMalloc(&sc->d_positions, std::max<size_t>(1, (size_t)sc->n_vertices * 3) * sizeof(float)));
+    VK_TRY(cudaMalloc(&sc->d_indices, std::max<size_t>(1, (size_t)sc->n_segments * 2) * sizeof(uint32_t)));
+    if (sc->n_vertices) VK_TRY(cudaMemcpyAsync(sc->d_positions, desc->positions_xyz, (size_t)sc->n_vertices * 12, cudaMemcpyHostToDevice, sc->stream));
+    if (sc->n_segments) VK_TRY(cudaMemcpyAsync(sc->d_indices, desc->line_indices, (size_t)sc->n_segments * 8, cudaMemcpyHostToDevice, sc->stream));
+    if (desc->radius_per_vertex && sc->n_vertices) {
+        VK_TRY(cudaMalloc(&sc->d_radius_pv, (size_t)sc->n_vertices * sizeof(float)));
+        VK_TRY(cudaMemcpyAsync(sc->d_radius_pv, desc->radius_per_vertex, (size_t)sc->n_vertices * 4, cudaMemcpyHostToDevice, sc->stream));
+    }
+    // topology check (the reference logs and bails on malformed input, geometry_processor.cpp:606-612)
+    if (sc->n_segments) {
+        uint32_t* d_bad = reinterpret_cast<uint32_t*>(sc->d_counters + 7);
+        uint32_t n_idx = sc->n_segments * 2;
+        validate_indices_kernel<<<(n_idx + 255) / 256, 256, 0, sc->stream>>>(sc->d_indices, n_idx, sc->n_vertices, d_bad);
+        count_launch();
+        uint32_t bad = 0;
+        VK_TRY(cudaMemcpyAsync(&bad, d_bad, 4, cudaMemcpyDeviceToHost, sc->stream));
+        VK_TRY(cudaStreamSynchronize(sc->stream));
+        if (bad) { set_last_error("line index out of range"); free_scene(sc); return VKHRT_ERR_BAD_TOPOLOGY; }
+        VK_TRY(cudaMemsetAsync(sc->d_counters, 0, 8 * sizeof(unsigned long long), sc->stream));
+    }
+    VK_TRY(cudaStreamSynchronize(sc->stream));   // inputs are copied before return
+#undef VK_TRY
+    *out_scene = reinterpret_cast<VkhrtScene*>(sc);
+    return VKHRT_OK;
+}
+
+int vkhrt_scene_build(VkhrtScene* scene)
+{
+    if (!scene) { set_last_error("null scene"); return VKHRT_ERR_INVALID_ARGUMENT; }
+    return build_scene(scene->s, false);
+}
+
+int vkhrt_scene_refit(VkhrtScene* scene, const float* positions_xyz)
+{
+    if (!scene || !positions_xyz) { set_last_error("null argument"); return VKHRT_ERR_INVALID_ARGUMENT; }
+    DeviceScene& sc = scene->s;
+    if (!sc.built) { set_last_error("refit before build"); return VKHRT_ERR_NOT_BUILT; }
+    VK_CUDA(cudaSetDevice(sc.device));
+    if (sc.n_vertices) VK_CUDA(cudaMemcpyAsync(sc.d_positions, positions_xyz, (size_t)sc.n_vertices * 12, cudaMemcpyHostToDevice, sc.stream));
+    return build_scene(sc, true);
+}
+
+int vkhrt_scene_get_bvh(VkhrtScene* scene, VkhrtBvhView* view)
+{
+    if (!scene || !view) { set_last_error("null argument"); return VKHRT_ERR_INVALID_ARGUMENT; }
+    DeviceScene& sc = scene->s;
+    if (!sc.built) { set_last_error("get_bvh before build"); return VKHRT_ERR_NOT_BUILT; }
+    VK_CUDA(cudaSetDevice(sc.device));
+    view->n_primitives = sc.n_prims;
+    view->n_nodes = sc.n_nodes;
+    for (int k = 0; k < 3; ++k) { view->scene_lo[k] = sc.scene_lo[k]; view->scene_hi[k] = sc.scene_hi[k]; }
+    if (sc.n_prims == 0) return VKHRT_OK;
+    if (view->nodes) VK_CUDA(cudaMemcpy(view->nodes, sc.d_nodes, (size_t)sc.n_nodes * 64, cudaMemcpyDeviceToHost));
+    if (view->sorted_prim_ids) VK_CUDA(cudaMemcpy(view->sorted_prim_ids, sc.d_sorted_ids, (size_t)sc.n_prims * 4, cudaMemcpyDeviceToHost));
+    if (view->sorted_morton) VK_CUDA(cudaMemcpy(view->sorted_morton, sc.d_sorted_morton, (size_t)sc.n_prims * 8, cudaMemcpyDeviceToHost));
+    return VKHRT_OK;
+}
+
+int vkhrt_scene_get_primitives(VkhrtScene* scene, float* out, size_t out_floats)
+{
+    if (!scene || !out) { set_last_error("null argument"); return VKHRT_ERR_INVALID_ARGUMENT; }
+    return export_primitives(scene->s, out, out_floats);
+}
+
+uint32_t vkhrt_scene_primitive_count(const VkhrtScene* scene) { return scene ? scene->s.n_prims : 0; }
+
+void vkhrt_scene_destroy(VkhrtScene* scene)
+{
+    if (scene) free_scene(reinterpret_cast<DeviceScene*>(scene));
+}
+
+int vkhrt_render(VkhrtScene* scene, const VkhrtFrameDesc* frame, VkhrtHit* hits_out, uint8_t* rgba8_out)
+{
+    if (!scene || !frame) { set_last_error("null argument"); return VKHRT_ERR_INVALID_ARGUMENT; }
+    if (!scene->s.built) { set_last_error("render before build"); return VKHRT_ERR_NOT_BUILT; }
+    return render_frame(scene->s, *frame, hits_out, rgba8_out, nullptr);
+}
+
+int vkhrt_render_stats(VkhrtScene* scene, const VkhrtFrameDesc* frame, VkhrtHit* hits_out, uint8_t* rgba8_out, VkhrtTraceStats* stats)
+{
+    if (!scene || !frame || !stats) { set_last_error("null argument"); return VKHRT_ERR_INVALID_ARGUMENT; }
+    if (!scene->s.built) { set_last_error("render before build"); return VKHRT_ERR_NOT_BUILT; }
+    return render_frame(scene->s, *frame, hits_out, rgba8_out, stats);
+}
+
+uint64_t vkhrt_frame_local_pixels(const VkhrtFrameDesc* frame) { return frame ? frame_local_pixels(*frame) : 0; }
+
+int vkhrt_untile(const VkhrtFrameDesc* frame, uint32_t world, const void* gathered, void* row_major, uint32_t elem_bytes, void* stream)
+{
+    if (!frame || !gathered || !row_major) { set_last_error("null argument"); return VKHRT_ERR_INVALID_ARGUMENT; }
+    return untile_buffer(*frame, world, gathered, row_major, elem_bytes, (cudaStream_t)stream);
+}
+
+int vkhrt_last_timing(const VkhrtScene* scene, VkhrtTiming* timing)
+{
+    if (!scene || !timing) { set_last_error("null argument"); return VKHRT_ERR_INVALID_ARGUMENT; }
+    const DeviceScene& sc = scene->s;
+    cudaSetDevice(sc.device);
+    *timing = sc.timing;
+    // frame stages: events 6..11 (recorded by render_frame; zero if no frame has been rendered yet)
+    if (cudaEventSynchronize(sc.ev[11]) == cudaSuccess) {
+        float ms = 0;
+        if (cudaEventElapsedTime(&ms, sc.ev[7], sc.ev[8]) == cudaSuccess) timing->trace_ms = ms;
+        if (cudaEventElapsedTime(&ms, sc.ev[8], sc.ev[9]) == cudaSuccess) timing->shade_ms = ms;
+        if (cudaEventElapsedTime(&ms, sc.ev[6], sc.ev[10]) == cudaSuccess) timing->render_total_ms = ms;
+        if (cudaEventElapsedTime(&ms, sc.ev[10], sc.ev[11]) == cudaSuccess) timing->d2h_ms = ms;
+    }
+    cudaGetLastError();
+    return VKHRT_OK;
+}
+
+int vkhrt_generate_rays(const VkhrtFrameDesc* frame, uint32_t sample, float* rays_out_device, int device)
+{
+    if (!frame || !rays_out_device) { set_last_error("null argument"); return VKHRT_ERR_INVALID_ARGUMENT; }
+    int rc = check_device(device);
+    if (rc) return rc;
+    VK_CUDA(cudaSetDevice(device));
+    rc = generate_ray_buffer(*frame, sample, rays_out_device, (cudaStream_t)frame->stream);
+    if (rc) return rc;
+    if (!frame->stream) VK_CUDA(cudaDeviceSynchronize());
+    return VKHRT_OK;
+}
+
+int vkhrt_trace_rays(VkhrtScene* scene, const float* rays_device, uint64_t n_rays, VkhrtHit* hits_out_device, void* stream)
+{
+    if (!scene || (n_rays && (!rays_device || !hits_out_device))) { set_last_error("null argument"); return VKHRT_ERR_INVALID_ARGUMENT; }
+    if (!scene->s.built) { set_last_error("trace before build"); return VKHRT_ERR_NOT_BUILT; }
+    return trace_ray_buffer(scene->s, rays_device, n_rays, hits_out_device, (cudaStream_t)stream);
+}
+
+}  // extern "C"

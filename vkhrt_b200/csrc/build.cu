@@ -1,0 +1,616 @@
+// build.cu — primitive generation + deterministic LBVH build, all on the device.
+//
+// Replaces (reference paths):
+//   source/resources/model/geometry_processor.cpp:45-67   GenerateLines
+//   ...:123-156 GenerateCurves, :422-436 GenerateAABBs, :201-271 DOTS, :273-298 LSS
+//   source/bottom_level_acceleration_structure.cpp:34-78 (driver BLAS build) -> LBVH:
+//     centroid bounds -> 63-bit Morton keys -> hand-written LSD radix sort (no CUB) ->
+//     Karras hierarchy -> fused "materialise primitives in sorted order + bottom-up refit".
+//
+// Compiled with -fmad=false: generated control points / boxes are bit-identical to the CPU oracle.
+#include "scene.h"
+#include "hair_math.cuh"
+#include <vector>
+
+namespace vkhrt {
+
+// ------------------------------------------------------------------------------------------------
+// primitive generation (one thread = one primitive), shared by the centroid pass and the
+// materialise pass so that nothing but the final sorted arrays is ever stored.
+// ------------------------------------------------------------------------------------------------
+struct MeshIn {
+    const float* pos;
+    const uint32_t* idx;
+    const float* rpv;
+    uint32_t n_segments;
+    float radius;
+};
+
+VK_DEV float3 load_pos(const MeshIn& m, uint32_t v) { return f3(m.pos[3 * v], m.pos[3 * v + 1], m.pos[3 * v + 2]); }
+VK_DEV bool same_point(float3 a, float3 b) { return a.x == b.x && a.y == b.y && a.z == b.z; }   // glm::vec3 ==
+
+struct Aabb { float3 lo, hi; };
+
+// GenerateCurves (geometry_processor.cpp:123-156), tension 1, for segment i
+VK_DEV Bezier gen_curve(const MeshIn& m, uint32_t i)
+{
+    float3 s = load_pos(m, m.idx[2 * i]), e = load_pos(m, m.idx[2 * i + 1]);
+    float3 p0 = s, p3 = e;
+    if (i > 0) {
+        float3 pe = load_pos(m, m.idx[2 * (i - 1) + 1]);
+        if (same_point(pe, s)) p0 = load_pos(m, m.idx[2 * (i - 1)]);
+    }
+    if (i + 1 < m.n_segments) {
+        float3 ns = load_pos(m, m.idx[2 * (i + 1)]);
+        if (same_point(e, ns)) p3 = load_pos(m, m.idx[2 * (i + 1) + 1]);
+    }
+    const float k = 1.0f / 6.0f;
+    Bezier c;
+    c.p0 = s;
+    c.p1 = s + (e - p0) * k;
+    c.p2 = e - (p3 - s) * k;
+    c.p3 = e;
+    return c;
+}
+// GenerateAABBs (geometry_processor.cpp:422-436)
+VK_DEV Aabb curve_box(const Bezier& c, float r)
+{
+    Aabb b;
+    b.lo.x = fminf(fminf(c.p0.x, c.p3.x), fminf(c.p1.x, c.p2.x)) - r;
+    b.lo.y = fminf(fminf(c.p0.y, c.p3.y), fminf(c.p1.y, c.p2.y)) - r;
+    b.lo.z = fminf(fminf(c.p0.z, c.p3.z), fminf(c.p1.z, c.p2.z)) - r;
+    b.hi.x = fmaxf(fmaxf(c.p0.x, c.p3.x), fmaxf(c.p1.x, c.p2.x)) + r;
+    b.hi.y = fmaxf(fmaxf(c.p0.y, c.p3.y), fmaxf(c.p1.y, c.p2.y)) + r;
+    b.hi.z = fmaxf(fmaxf(c.p0.z, c.p3.z), fmaxf(c.p1.z, c.p2.z)) + r;
+    return b;
+}
+
+// GenerateLinearSweptSpheres (geometry_processor.cpp:273-298) + per-vertex radius extension
+struct LssPrim { float3 p0, p1; float r0, r1; };
+VK_DEV LssPrim gen_lss(const MeshIn& m, uint32_t i)
+{
+    uint32_t a = m.idx[2 * i], b = m.idx[2 * i + 1];
+    LssPrim s;
+    s.p0 = load_pos(m, a);
+    s.p1 = load_pos(m, b);
+    s.r0 = fmaxf(m.rpv ? m.rpv[a] : m.radius, 0.001f);
+    s.r1 = fmaxf(m.rpv ? m.rpv[b] : m.radius, 0.001f);
+    return s;
+}
+VK_DEV Aabb lss_box(const LssPrim& s)
+{
+    Aabb b;
+    b.lo = f3(fminf(s.p0.x - s.r0, s.p1.x - s.r1), fminf(s.p0.y - s.r0, s.p1.y - s.r1), fminf(s.p0.z - s.r0, s.p1.z - s.r1));
+    b.hi = f3(fmaxf(s.p0.x + s.r0, s.p1.x + s.r1), fmaxf(s.p0.y + s.r0, s.p1.y + s.r1), fmaxf(s.p0.z + s.r0, s.p1.z + s.r1));
+    return b;
+}
+
+// GenerateDisjointOrthogonalTriangleStrips (geometry_processor.cpp:201-271): triangle `prim` = 4*segment + 2*face + k
+struct TriPrim { float3 v0, v1, v2; };
+VK_DEV float3 perp_stark(float3 u)
+{
+    float ax = fabsf(u.x), ay = fabsf(u.y), az = fabsf(u.z);
+    uint32_t uyx = (ax - ay) < 0.0f ? 1u : 0u;
+    uint32_t uzx = (ax - az) < 0.0f ? 1u : 0u;
+    uint32_t uzy = (ay - az) < 0.0f ? 1u : 0u;
+    uint32_t xm = uyx & uzx;
+    uint32_t ym = (1u ^ xm) & uzy;
+    uint32_t zm = 1u ^ (xm | ym);
+    return normalize3(cross3(u, f3((float)xm, (float)ym, (float)zm)));
+}
+VK_DEV TriPrim gen_tri(const MeshIn& m, uint32_t prim)
+{
+    uint32_t seg = prim >> 2, face = (prim >> 1) & 1u, k = prim & 1u;
+    float3 s = load_pos(m, m.idx[2 * seg]), e = load_pos(m, m.idx[2 * seg + 1]);
+    float3 fwd = normalize3(e - s);
+    float3 sv = perp_stark(fwd);
+    float3 v = face ? cross3(fwd, sv) : sv;
+    float3 off = v * m.radius;
+    TriPrim t;
+    if (k == 0) { t.v0 = s + off; t.v1 = e - off; t.v2 = e + off; }
+    else        { t.v0 = s + off; t.v1 = s - off; t.v2 = e - off; }
+    return t;
+}
+VK_DEV Aabb tri_box(const TriPrim& t)
+{
+    Aabb b;
+    b.lo = f3(fminf(fminf(t.v0.x, t.v1.x), t.v2.x), fminf(fminf(t.v0.y, t.v1.y), t.v2.y), fminf(fminf(t.v0.z, t.v1.z), t.v2.z));
+    b.hi = f3(fmaxf(fmaxf(t.v0.x, t.v1.x), t.v2.x), fmaxf(fmaxf(t.v0.y, t.v1.y), t.v2.y), fmaxf(fmaxf(t.v0.z, t.v1.z), t.v2.z));
+    return b;
+}
+
+template <int TECH>
+VK_DEV Aabb prim_box(const MeshIn& m, uint32_t prim)
+{
+    if (TECH == VKHRT_TECHNIQUE_PHANTOM) return curve_box(gen_curve(m, prim), m.radius);
+    if (TECH == VKHRT_TECHNIQUE_LSS) return lss_box(gen_lss(m, prim));
+    return tri_box(gen_tri(m, prim));
+}
+
+// order-preserving float <-> uint for atomicMin/Max
+VK_DEV uint32_t f2ord(float f) { uint32_t b = __float_as_uint(f); return (b & 0x80000000u) ? ~b : (b | 0x80000000u); }
+static inline float ord2f_host(uint32_t o) { uint32_t b = (o & 0x80000000u) ? (o & 0x7FFFFFFFu) : ~o; float f; memcpy(&f, &b, 4); return f; }
+
+// pass 1a: centroids + their bounds
+template <int TECH>
+__global__ void __launch_bounds__(256) centroid_kernel(MeshIn m, uint32_t n_prims, float4* __restrict__ centroids, uint32_t* __restrict__ bounds /*6*/)
+{
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    const float inf = __int_as_float(0x7f800000);
+    float3 lo = f3(inf, inf, inf), hi = f3(-inf, -inf, -inf);
+    if (i < n_prims) {
+        Aabb b = prim_box<TECH>(m, i);
+        float3 c = (b.lo + b.hi) * 0.5f;
+        centroids[i] = make_float4(c.x, c.y, c.z, 0.0f);
+        lo = c; hi = c;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        lo.x = fminf(lo.x, __shfl_xor_sync(0xffffffffu, lo.x, o)); lo.y = fminf(lo.y, __shfl_xor_sync(0xffffffffu, lo.y, o));
+        lo.z = fminf(lo.z, __shfl_xor_sync(0xffffffffu, lo.z, o)); hi.x = fmaxf(hi.x, __shfl_xor_sync(0xffffffffu, hi.x, o));
+        hi.y = fmaxf(hi.y, __shfl_xor_sync(0xffffffffu, hi.y, o)); hi.z = fmaxf(hi.z, __shfl_xor_sync(0xffffffffu, hi.z, o));
+    }
+    __shared__ float red[8][6];
+    int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+    if (l == 0) { red[w][0] = lo.x; red[w][1] = lo.y; red[w][2] = lo.z; red[w][3] = hi.x; red[w][4] = hi.y; red[w][5] = hi.z; }
+    __syncthreads();
+    if (threadIdx.x < 6) {
+        float v = red[0][threadIdx.x];
+        for (int k = 1; k < 8; ++k) v = threadIdx.x < 3 ? fminf(v, red[k][threadIdx.x]) : fmaxf(v, red[k][threadIdx.x]);
+        if (threadIdx.x < 3) atomicMin(&bounds[threadIdx.x], f2ord(v)); else atomicMax(&bounds[threadIdx.x], f2ord(v));
+    }
+}
+
+// pass 1b: 63-bit Morton keys (21 bits per axis)
+VK_DEV uint64_t spread21(uint32_t v)
+{
+    uint64_t x = v & 0x1FFFFFull;
+    x = (x | (x << 32)) & 0x1F00000000FFFFull;
+    x = (x | (x << 16)) & 0x1F0000FF0000FFull;
+    x = (x | (x << 8)) & 0x100F00F00F00F00Full;
+    x = (x | (x << 4)) & 0x10C30C30C30C30C3ull;
+    x = (x | (x << 2)) & 0x1249249249249249ull;
+    return x;
+}
+VK_DEV uint32_t quantise21(float c, float lo, float scale)
+{
+    float q = (c - lo) * scale;
+    q = fminf(fmaxf(q, 0.0f), 2097151.0f);
+    return (uint32_t)q;
+}
+__global__ void __launch_bounds__(256) morton_kernel(const float4* __restrict__ centroids, uint32_t n, float3 lo, float3 scale,
+                                                     uint64_t* __restrict__ keys, uint32_t* __restrict__ vals)
+{
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    float4 c = centroids[i];
+    uint64_t mx = spread21(quantise21(c.x, lo.x, scale.x));
+    uint64_t my = spread21(quantise21(c.y, lo.y, scale.y));
+    uint64_t mz = spread21(quantise21(c.z, lo.z, scale.z));
+    keys[i] = (mx << 2) | (my << 1) | mz;
+    vals[i] = i;
+}
+
+// ------------------------------------------------------------------------------------------------
+// LSD radix sort, 8-bit digits, stable, 64-bit keys + 32-bit values (hand-written; no CUB/Thrust).
+// Per pass: block histograms -> exclusive scan (digit-major) -> stable scatter with warp-match ranking.
+// ------------------------------------------------------------------------------------------------
+constexpr int RS_BLOCK = 256;
+constexpr int RS_IPT = 8;                       // items per thread
+constexpr int RS_TILE = RS_BLOCK * RS_IPT;      // 2048 keys per block
+constexpr int RS_WARPS = RS_BLOCK / 32;
+
+__global__ void __launch_bounds__(RS_BLOCK) rs_histogram_kernel(const uint64_t* __restrict__ keys, uint32_t n, int shift,
+                                                                uint32_t* __restrict__ hist, uint32_t n_blocks)
+{
+    __shared__ uint32_t sh[256];
+    sh[threadIdx.x] = 0;
+    __syncthreads();
+    uint32_t base = blockIdx.x * RS_TILE;
+#pragma unroll
+    for (int r = 0; r < RS_IPT; ++r) {
+        uint32_t i = base + r * RS_BLOCK + threadIdx.x;
+        if (i < n) atomicAdd(&sh[(uint32_t)(keys[i] >> shift) & 255u], 1u);
+    }
+    __syncthreads();
+    hist[threadIdx.x * n_blocks + blockIdx.x] = sh[threadIdx.x];
+}
+
+__global__ void __launch_bounds__(RS_BLOCK) rs_scatter_kernel(const uint64_t* __restrict__ keys_in, const uint32_t* __restrict__ vals_in,
+                                                              uint64_t* __restrict__ keys_out, uint32_t* __restrict__ vals_out,
+                                                              uint32_t n, int shift, const uint32_t* __restrict__ scanned, uint32_t n_blocks)
+{
+    __shared__ uint32_t warp_cnt[RS_WARPS][256];
+    __shared__ uint32_t base[256];
+    const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    for (int k = threadIdx.x; k < RS_WARPS * 256; k += RS_BLOCK) (&warp_cnt[0][0])[k] = 0;
+    __syncthreads();
+
+    // warp w owns the contiguous range [tile + w*32*IPT, +32*IPT); round r = 32 consecutive keys
+    const uint32_t wbase = blockIdx.x * RS_TILE + w * (32 * RS_IPT);
+    uint64_t key[RS_IPT];
+    uint32_t val[RS_IPT], rank[RS_IPT];
+#pragma unroll
+    for (int r = 0; r < RS_IPT; ++r) {
+        uint32_t i = wbase + r * 32 + lane;
+        bool ok = i < n;
+        key[r] = ok ? keys_in[i] : ~0ull;
+        val[r] = ok ? vals_in[i] : 0u;
+        uint32_t d = ok ? ((uint32_t)(key[r] >> shift) & 255u) : 256u;
+        uint32_t peers = __match_any_sync(0xffffffffu, d);
+        uint32_t pre = ok ? warp_cnt[w][d] : 0u;
+        __syncwarp();
+        if (ok && (peers & ((1u << lane) - 1u)) == 0u) warp_cnt[w][d] = pre + __popc(peers);
+        __syncwarp();
+        rank[r] = pre + __popc(peers & ((1u << lane) - 1u));
+    }
+    __syncthreads();
+    {   // digit d = threadIdx.x: exclusive prefix over the warps of this block
+        uint32_t d = threadIdx.x, run = 0;
+#pragma unroll
+        for (int k = 0; k < RS_WARPS; ++k) { uint32_t c = warp_cnt[k][d]; warp_cnt[k][d] = run; run += c; }
+        base[d] = scanned[d * n_blocks + blockIdx.x];
+    }
+    __syncthreads();
+#pragma unroll
+    for (int r = 0; r < RS_IPT; ++r) {
+        uint32_t i = wbase + r * 32 + lane;
+        if (i < n) {
+            uint32_t d = (uint32_t)(key[r] >> shift) & 255u;
+            uint32_t o = base[d] + warp_cnt[w][d] + rank[r];
+            keys_out[o] = key[r];
+            vals_out[o] = val[r];
+        }
+    }
+}
+
+// exclusive scan of uint32, in place: 2048 elements per block, block totals scanned recursively
+constexpr int SC_BLOCK = 256, SC_IPT = 8, SC_TILE = SC_BLOCK * SC_IPT;
+__global__ void __launch_bounds__(SC_BLOCK) scan_tile_kernel(uint32_t* __restrict__ data, uint32_t n, uint32_t* __restrict__ totals)
+{
+    __shared__ uint32_t wsum[SC_BLOCK / 32];
+    uint32_t base = blockIdx.x * SC_TILE + threadIdx.x * SC_IPT;
+    uint32_t v[SC_IPT], s = 0;
+#pragma unroll
+    for (int k = 0; k < SC_IPT; ++k) { v[k] = (base + k < n) ? data[base + k] : 0u; s += v[k]; }
+    uint32_t inc = s;
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { uint32_t t = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += t; }
+    if (lane == 31) wsum[w] = inc;
+    __syncthreads();
+    if (w == 0) {
+        uint32_t x = lane < SC_BLOCK / 32 ? wsum[lane] : 0u, xi = x;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { uint32_t t = __shfl_up_sync(0xffffffffu, xi, o); if (lane >= o) xi += t; }
+        if (lane < SC_BLOCK / 32) wsum[lane] = xi - x;
+        if (lane == SC_BLOCK / 32 - 1 && totals) totals[blockIdx.x] = xi;
+    }
+    __syncthreads();
+    uint32_t run = wsum[w] + (inc - s);
+#pragma unroll
+    for (int k = 0; k < SC_IPT; ++k) { if (base + k < n) data[base + k] = run; run += v[k]; }
+}
+__global__ void __launch_bounds__(SC_BLOCK) scan_add_kernel(uint32_t* __restrict__ data, uint32_t n, const uint32_t* __restrict__ offsets)
+{
+    uint32_t base = blockIdx.x * SC_TILE + threadIdx.x * SC_IPT;
+    uint32_t off = offsets[blockIdx.x];
+#pragma unroll
+    for (int k = 0; k < SC_IPT; ++k) if (base + k < n) data[base + k] += off;
+}
+
+static int exclusive_scan(uint32_t* d, uint32_t n, uint32_t* tmp, cudaStream_t st)
+{
+    uint32_t nb = (n + SC_TILE - 1) / SC_TILE;
+    if (nb <= 1) {
+        scan_tile_kernel<<<1, SC_BLOCK, 0, st>>>(d, n, nullptr);
+        count_launch();
+        return VKHRT_OK;
+    }
+    scan_tile_kernel<<<nb, SC_BLOCK, 0, st>>>(d, n, tmp);
+    count_launch();
+    int rc = exclusive_scan(tmp, nb, tmp + ((nb + 63) & ~63u), st);
+    if (rc) return rc;
+    scan_add_kernel<<<nb, SC_BLOCK, 0, st>>>(d, n, tmp);
+    count_launch();
+    return VKHRT_OK;
+}
+static size_t scan_tmp_elems(uint32_t n)
+{
+    size_t tot = 0;
+    while (n > SC_TILE) { n = (n + SC_TILE - 1) / SC_TILE; tot += (n + 63) & ~63u; }
+    return tot + 64;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Karras 2012 hierarchy over the sorted keys. Internal node i in [0, n-2], root = 0.
+// delta(i,j) = common-prefix length of the 64-bit keys, ties broken by the sorted position.
+// ------------------------------------------------------------------------------------------------
+VK_DEV int prefix_len(const uint64_t* __restrict__ m, int n, int i, int j)
+{
+    if (j < 0 || j >= n) return -1;
+    uint64_t a = m[i], b = m[j];
+    if (a == b) return 64 + __clz((uint32_t)i ^ (uint32_t)j);
+    return __clzll((long long)(a ^ b));
+}
+
+__global__ void __launch_bounds__(256) karras_kernel(const uint64_t* __restrict__ morton, const uint32_t* __restrict__ sorted_ids, int n,
+                                                     uint32_t* __restrict__ nodes_u32 /* 16 words per node */,
+                                                     uint32_t* __restrict__ parent_internal, uint32_t* __restrict__ parent_leaf)
+{
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n - 1) return;
+    int d = (prefix_len(morton, n, i, i + 1) - prefix_len(morton, n, i, i - 1)) >= 0 ? 1 : -1;
+    int dmin = prefix_len(morton, n, i, i - d);
+    int lmax = 2;
+    while (prefix_len(morton, n, i, i + lmax * d) > dmin) lmax *= 2;
+    int l = 0;
+    for (int t = lmax / 2; t >= 1; t /= 2)
+        if (prefix_len(morton, n, i, i + (l + t) * d) > dmin) l += t;
+    int j = i + l * d;
+    int dnode = prefix_len(morton, n, i, j);
+    int s = 0, t = l;
+    do {
+        t = (t + 1) >> 1;
+        if (prefix_len(morton, n, i, i + (s + t) * d) > dnode) s += t;
+    } while (t > 1);
+    int gamma = i + s * d + min(d, 0);
+    int lo = min(i, j), hi = max(i, j);
+    uint32_t c0, c1, p0 = 0, p1 = 0;
+    if (lo == gamma) { c0 = VKHRT_BVH_LEAF | (uint32_t)gamma; p0 = sorted_ids[gamma]; parent_leaf[gamma] = ((uint32_t)i << 1); }
+    else { c0 = (uint32_t)gamma; parent_internal[gamma] = ((uint32_t)i << 1); }
+    if (hi == gamma + 1) { c1 = VKHRT_BVH_LEAF | (uint32_t)(gamma + 1); p1 = sorted_ids[gamma + 1]; parent_leaf[gamma + 1] = ((uint32_t)i << 1) | 1u; }
+    else { c1 = (uint32_t)(gamma + 1); parent_internal[gamma + 1] = ((uint32_t)i << 1) | 1u; }
+    uint32_t* nd = nodes_u32 + (size_t)i * 16;
+    nd[3] = c0; nd[7] = c1; nd[11] = p0; nd[15] = p1;
+    if (i == 0) parent_internal[0] = 0xFFFFFFFFu;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Materialise primitives at their sorted position and refit boxes bottom-up (one thread per leaf;
+// the second thread to arrive at a node carries the union upward).  min/max are exact, so the
+// boxes do not depend on arrival order.
+// ------------------------------------------------------------------------------------------------
+template <int TECH>
+__global__ void __launch_bounds__(256) materialise_refit_kernel(MeshIn m, uint32_t n_prims, const uint32_t* __restrict__ sorted_ids,
+                                                                float4* __restrict__ primA, float4* __restrict__ primB,
+                                                                float* nodes_f32, const uint32_t* __restrict__ parent_internal,
+                                                                const uint32_t* __restrict__ parent_leaf, uint32_t* flags)
+{
+    uint32_t pos = blockIdx.x * blockDim.x + threadIdx.x;
+    if (pos >= n_prims) return;
+    uint32_t prim = sorted_ids[pos];
+    Aabb box;
+    if (TECH == VKHRT_TECHNIQUE_PHANTOM) {
+        Bezier c = gen_curve(m, prim);
+        box = curve_box(c, m.radius);
+        float rmax = bezier_bound_radius(c, m.radius);
+        primA[2 * (size_t)pos] = make_float4(c.p0.x, c.p0.y, c.p0.z, rmax);
+        primA[2 * (size_t)pos + 1] = make_float4(c.p3.x, c.p3.y, c.p3.z, __uint_as_float(prim));
+        primB[2 * (size_t)pos] = make_float4(c.p1.x, c.p1.y, c.p1.z, 0.0f);
+        primB[2 * (size_t)pos + 1] = make_float4(c.p2.x, c.p2.y, c.p2.z, 0.0f);
+    } else if (TECH == VKHRT_TECHNIQUE_LSS) {
+        LssPrim s = gen_lss(m, prim);
+        box = lss_box(s);
+        primA[2 * (size_t)pos] = make_float4(s.p0.x, s.p0.y, s.p0.z, s.r0);
+        primA[2 * (size_t)pos + 1] = make_float4(s.p1.x, s.p1.y, s.p1.z, s.r1);
+    } else {
+        TriPrim t = gen_tri(m, prim);
+        box = tri_box(t);
+        primA[3 * (size_t)pos] = make_float4(t.v0.x, t.v0.y, t.v0.z, __uint_as_float(prim));
+        primA[3 * (size_t)pos + 1] = make_float4(t.v1.x, t.v1.y, t.v1.z, 0.0f);
+        primA[3 * (size_t)pos + 2] = make_float4(t.v2.x, t.v2.y, t.v2.z, 0.0f);
+    }
+    if (n_prims == 1) {   // single primitive: node 0 holds the same leaf in both slots
+        float* nd = nodes_f32;
+        for (int k = 0; k < 2; ++k) {
+            nd[8 * k + 0] = box.lo.x; nd[8 * k + 1] = box.lo.y; nd[8 * k + 2] = box.lo.z;
+            nd[8 * k + 4] = box.hi.x; nd[8 * k + 5] = box.hi.y; nd[8 * k + 6] = box.hi.z;
+        }
+        return;
+    }
+    uint32_t p = parent_leaf[pos];
+    for (;;) {
+        uint32_t node = p >> 1, slot = p & 1u;
+        volatile float* nd = nodes_f32 + (size_t)node * 16;
+        nd[8 * slot + 0] = box.lo.x; nd[8 * slot + 1] = box.lo.y; nd[8 * slot + 2] = box.lo.z;
+        nd[8 * slot + 4] = box.hi.x; nd[8 * slot + 5] = box.hi.y; nd[8 * slot + 6] = box.hi.z;
+        __threadfence();
+        if (atomicAdd(&flags[node], 1u) == 0u) return;      // first arrival: the sibling will carry on
+        __threadfence();
+        uint32_t o = 1u - slot;
+        box.lo.x = fminf(box.lo.x, nd[8 * o + 0]); box.lo.y = fminf(box.lo.y, nd[8 * o + 1]); box.lo.z = fminf(box.lo.z, nd[8 * o + 2]);
+        box.hi.x = fmaxf(box.hi.x, nd[8 * o + 4]); box.hi.y = fmaxf(box.hi.y, nd[8 * o + 5]); box.hi.z = fmaxf(box.hi.z, nd[8 * o + 6]);
+        if (node == 0) return;
+        p = parent_internal[node];
+    }
+}
+
+// single-primitive scene: node 0 = the same leaf twice
+__global__ void single_node_kernel(uint32_t* nodes_u32, const uint32_t* sorted_ids)
+{
+    nodes_u32[3] = VKHRT_BVH_LEAF | 0u; nodes_u32[7] = VKHRT_BVH_LEAF | 0u;
+    nodes_u32[11] = sorted_ids[0]; nodes_u32[15] = sorted_ids[0];
+}
+
+// primitives in ORIGINAL order for vkhrt_scene_get_primitives (ModelCreation buffers)
+template <int TECH>
+__global__ void __launch_bounds__(256) export_kernel(MeshIn m, uint32_t n_prims, float* __restrict__ out)
+{
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_prims) return;
+    if (TECH == VKHRT_TECHNIQUE_PHANTOM) {
+        Bezier c = gen_curve(m, i);
+        float* o = out + (size_t)i * 12;
+        o[0] = c.p0.x; o[1] = c.p0.y; o[2] = c.p0.z; o[3] = c.p1.x; o[4] = c.p1.y; o[5] = c.p1.z;
+        o[6] = c.p2.x; o[7] = c.p2.y; o[8] = c.p2.z; o[9] = c.p3.x; o[10] = c.p3.y; o[11] = c.p3.z;
+    } else if (TECH == VKHRT_TECHNIQUE_LSS) {
+        LssPrim s = gen_lss(m, i);
+        float* o = out + (size_t)i * 8;
+        o[0] = s.p0.x; o[1] = s.p0.y; o[2] = s.p0.z; o[3] = s.r0; o[4] = s.p1.x; o[5] = s.p1.y; o[6] = s.p1.z; o[7] = s.r1;
+    } else {
+        TriPrim t = gen_tri(m, i);
+        float* o = out + (size_t)i * 9;
+        o[0] = t.v0.x; o[1] = t.v0.y; o[2] = t.v0.z; o[3] = t.v1.x; o[4] = t.v1.y; o[5] = t.v1.z; o[6] = t.v2.x; o[7] = t.v2.y; o[8] = t.v2.z;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// host driver
+// ------------------------------------------------------------------------------------------------
+static inline uint32_t cdiv(uint64_t a, uint32_t b) { return (uint32_t)((a + b - 1) / b); }
+
+template <typename T>
+static int dev_alloc(T** p, size_t n)
+{
+    if (*p) { cudaFree(*p); *p = nullptr; }
+    if (n == 0) n = 1;
+    VK_CUDA(cudaMalloc((void**)p, n * sizeof(T)));
+    return VKHRT_OK;
+}
+
+static float ev_ms(cudaEvent_t a, cudaEvent_t b) { float ms = 0; cudaEventElapsedTime(&ms, a, b); return ms; }
+
+int build_scene(DeviceScene& sc, bool refit_only)
+{
+    VK_CUDA(cudaSetDevice(sc.device));
+    cudaStream_t st = sc.stream;
+    const uint32_t n = sc.n_prims;
+    MeshIn m{sc.d_positions, sc.d_indices, sc.d_radius_pv, sc.n_segments, sc.radius};
+    sc.timing = VkhrtTiming{};
+    if (n == 0) { sc.n_nodes = 0; sc.built = true; return VKHRT_OK; }
+    const int tech = sc.technique;
+    const size_t primA_per = tech == VKHRT_TECHNIQUE_DOTS ? 3 : 2;
+
+    cudaEvent_t* ev = sc.ev;
+    VK_CUDA(cudaEventRecord(ev[0], st));
+    if (!refit_only) {
+        sc.n_nodes = n > 1 ? n - 1 : 1;
+        int rc;
+        if ((rc = dev_alloc(&sc.d_nodes, (size_t)sc.n_nodes * 4))) return rc;
+        if ((rc = dev_alloc(&sc.d_sorted_ids, n))) return rc;
+        if ((rc = dev_alloc(&sc.d_sorted_morton, n))) return rc;
+        if ((rc = dev_alloc(&sc.d_parent_internal, sc.n_nodes))) return rc;
+        if ((rc = dev_alloc(&sc.d_parent_leaf, n))) return rc;
+        if ((rc = dev_alloc(&sc.d_refit_flags, sc.n_nodes))) return rc;
+        if ((rc = dev_alloc(&sc.d_primA, (size_t)n * primA_per))) return rc;
+        if (tech == VKHRT_TECHNIQUE_PHANTOM) { if ((rc = dev_alloc(&sc.d_primB, (size_t)n * 2))) return rc; }
+
+        // scratch for the build
+        float4* d_cent = nullptr; uint32_t* d_bounds = nullptr;
+        uint64_t* d_keys_alt = nullptr; uint32_t* d_vals_alt = nullptr; uint32_t* d_hist = nullptr; uint32_t* d_scan_tmp = nullptr;
+        const uint32_t rs_blocks = cdiv(n, RS_TILE);
+        const uint32_t hist_n = rs_blocks * 256u;
+        auto free_scratch = [&]() {
+            cudaFree(d_cent); cudaFree(d_bounds); cudaFree(d_keys_alt); cudaFree(d_vals_alt); cudaFree(d_hist); cudaFree(d_scan_tmp);
+        };
+#define VK_CUDA_S(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { set_last_error(std::string(#call) + ": " + cudaGetErrorString(e_)); free_scratch(); return e_ == cudaErrorMemoryAllocation ? VKHRT_ERR_OUT_OF_MEMORY : VKHRT_ERR_CUDA; } } while (0)
+        VK_CUDA_S(cudaMalloc(&d_cent, (size_t)n * sizeof(float4)));
+        VK_CUDA_S(cudaMalloc(&d_bounds, 6 * sizeof(uint32_t)));
+        VK_CUDA_S(cudaMalloc(&d_keys_alt, (size_t)n * 8));
+        VK_CUDA_S(cudaMalloc(&d_vals_alt, (size_t)n * 4));
+        VK_CUDA_S(cudaMalloc(&d_hist, (size_t)hist_n * 4));
+        VK_CUDA_S(cudaMalloc(&d_scan_tmp, scan_tmp_elems(hist_n) * 4));
+
+        // 1a centroids + bounds
+        uint32_t init_bounds[6] = {0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0u, 0u, 0u};
+        VK_CUDA_S(cudaMemcpyAsync(d_bounds, init_bounds, sizeof(init_bounds), cudaMemcpyHostToDevice, st));
+        const uint32_t g = cdiv(n, 256);
+        if (tech == VKHRT_TECHNIQUE_PHANTOM) centroid_kernel<VKHRT_TECHNIQUE_PHANTOM><<<g, 256, 0, st>>>(m, n, d_cent, d_bounds);
+        else if (tech == VKHRT_TECHNIQUE_LSS) centroid_kernel<VKHRT_TECHNIQUE_LSS><<<g, 256, 0, st>>>(m, n, d_cent, d_bounds);
+        else centroid_kernel<VKHRT_TECHNIQUE_DOTS><<<g, 256, 0, st>>>(m, n, d_cent, d_bounds);
+        count_launch();
+        VK_CUDA_S(cudaEventRecord(ev[1], st));
+        uint32_t hb[6];
+        VK_CUDA_S(cudaMemcpyAsync(hb, d_bounds, sizeof(hb), cudaMemcpyDeviceToHost, st));
+        VK_CUDA_S(cudaStreamSynchronize(st));
+        float lo[3], hi[3], scale[3];
+        for (int k = 0; k < 3; ++k) {
+            lo[k] = ord2f_host(hb[k]); hi[k] = ord2f_host(hb[3 + k]);
+            float ext = hi[k] - lo[k];
+            scale[k] = ext > 0.0f ? 2097152.0f / ext : 0.0f;
+            sc.scene_lo[k] = lo[k]; sc.scene_hi[k] = hi[k];
+        }
+        // 1b morton keys
+        uint64_t* keys[2] = {sc.d_sorted_morton, d_keys_alt};
+        uint32_t* vals[2] = {sc.d_sorted_ids, d_vals_alt};
+        morton_kernel<<<g, 256, 0, st>>>(d_cent, n, make_float3(lo[0], lo[1], lo[2]), make_float3(scale[0], scale[1], scale[2]), keys[0], vals[0]);
+        count_launch();
+        VK_CUDA_S(cudaEventRecord(ev[2], st));
+        // 2 radix sort: 8 passes over the 63-bit key (even count => result lands back in keys[0]/vals[0])
+        int cur = 0;
+        for (int pass = 0; pass < 8; ++pass) {
+            int shift = pass * 8;
+            rs_histogram_kernel<<<rs_blocks, RS_BLOCK, 0, st>>>(keys[cur], n, shift, d_hist, rs_blocks);
+            count_launch();
+            int rc2 = exclusive_scan(d_hist, hist_n, d_scan_tmp, st);
+            if (rc2) { free_scratch(); return rc2; }
+            rs_scatter_kernel<<<rs_blocks, RS_BLOCK, 0, st>>>(keys[cur], vals[cur], keys[cur ^ 1], vals[cur ^ 1], n, shift, d_hist, rs_blocks);
+            count_launch();
+            cur ^= 1;
+        }
+        VK_CUDA_S(cudaEventRecord(ev[3], st));
+        // 3 hierarchy
+        VK_CUDA_S(cudaMemsetAsync(sc.d_nodes, 0, (size_t)sc.n_nodes * 64, st));
+        if (n > 1) {
+            karras_kernel<<<cdiv(n - 1, 256), 256, 0, st>>>(sc.d_sorted_morton, sc.d_sorted_ids, (int)n, (uint32_t*)sc.d_nodes,
+                                                            sc.d_parent_internal, sc.d_parent_leaf);
+        } else {
+            single_node_kernel<<<1, 1, 0, st>>>((uint32_t*)sc.d_nodes, sc.d_sorted_ids);
+        }
+        count_launch();
+        VK_CUDA_S(cudaEventRecord(ev[4], st));
+        VK_CUDA_S(cudaStreamSynchronize(st));
+        VK_CUDA_S(cudaGetLastError());
+        free_scratch();
+#undef VK_CUDA_S
+    } else {
+        VK_CUDA(cudaEventRecord(ev[1], st)); VK_CUDA(cudaEventRecord(ev[2], st));
+        VK_CUDA(cudaEventRecord(ev[3], st)); VK_CUDA(cudaEventRecord(ev[4], st));
+    }
+    // 4 materialise + refit
+    VK_CUDA(cudaMemsetAsync(sc.d_refit_flags, 0, (size_t)sc.n_nodes * 4, st));
+    const uint32_t g = cdiv(n, 256);
+    if (tech == VKHRT_TECHNIQUE_PHANTOM)
+        materialise_refit_kernel<VKHRT_TECHNIQUE_PHANTOM><<<g, 256, 0, st>>>(m, n, sc.d_sorted_ids, sc.d_primA, sc.d_primB, (float*)sc.d_nodes, sc.d_parent_internal, sc.d_parent_leaf, sc.d_refit_flags);
+    else if (tech == VKHRT_TECHNIQUE_LSS)
+        materialise_refit_kernel<VKHRT_TECHNIQUE_LSS><<<g, 256, 0, st>>>(m, n, sc.d_sorted_ids, sc.d_primA, sc.d_primB, (float*)sc.d_nodes, sc.d_parent_internal, sc.d_parent_leaf, sc.d_refit_flags);
+    else
+        materialise_refit_kernel<VKHRT_TECHNIQUE_DOTS><<<g, 256, 0, st>>>(m, n, sc.d_sorted_ids, sc.d_primA, sc.d_primB, (float*)sc.d_nodes, sc.d_parent_internal, sc.d_parent_leaf, sc.d_refit_flags);
+    count_launch();
+    VK_CUDA(cudaEventRecord(ev[5], st));
+    VK_CUDA(cudaStreamSynchronize(st));
+    VK_CUDA(cudaGetLastError());
+    sc.timing.geometry_ms = ev_ms(ev[0], ev[1]);
+    sc.timing.morton_ms = ev_ms(ev[1], ev[2]);
+    sc.timing.sort_ms = ev_ms(ev[2], ev[3]);
+    sc.timing.hierarchy_ms = ev_ms(ev[3], ev[4]);
+    sc.timing.refit_ms = ev_ms(ev[4], ev[5]);
+    sc.timing.build_total_ms = ev_ms(ev[0], ev[5]);
+    sc.built = true;
+    return VKHRT_OK;
+}
+
+int export_primitives(DeviceScene& sc, float* host_out, size_t out_floats)
+{
+    VK_CUDA(cudaSetDevice(sc.device));
+    const uint32_t n = sc.n_prims;
+    const size_t per = sc.technique == VKHRT_TECHNIQUE_PHANTOM ? 12 : (sc.technique == VKHRT_TECHNIQUE_LSS ? 8 : 9);
+    if (out_floats < (size_t)n * per) { set_last_error("export_primitives: output too small"); return VKHRT_ERR_INVALID_ARGUMENT; }
+    if (n == 0) return VKHRT_OK;
+    MeshIn m{sc.d_positions, sc.d_indices, sc.d_radius_pv, sc.n_segments, sc.radius};
+    float* d_out = nullptr;
+    VK_CUDA(cudaMalloc(&d_out, (size_t)n * per * 4));
+    const uint32_t g = cdiv(n, 256);
+    if (sc.technique == VKHRT_TECHNIQUE_PHANTOM) export_kernel<VKHRT_TECHNIQUE_PHANTOM><<<g, 256, 0, sc.stream>>>(m, n, d_out);
+    else if (sc.technique == VKHRT_TECHNIQUE_LSS) export_kernel<VKHRT_TECHNIQUE_LSS><<<g, 256, 0, sc.stream>>>(m, n, d_out);
+    else export_kernel<VKHRT_TECHNIQUE_DOTS><<<g, 256, 0, sc.stream>>>(m, n, d_out);
+    count_launch();
+    cudaError_t e = cudaMemcpyAsync(host_out, d_out, (size_t)n * per * 4, cudaMemcpyDeviceToHost, sc.stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(sc.stream);
+    cudaFree(d_out);
+    if (e != cudaSuccess) { set_last_error(std::string("export_primitives: ") + cudaGetErrorString(e)); return VKHRT_ERR_CUDA; }
+    return VKHRT_OK;
+}
+
+}  // namespace vkhrt

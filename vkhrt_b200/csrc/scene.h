@@ -1,0 +1,78 @@
+// scene.h — internal (not part of the ABI): device-resident scene + launch helpers.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <string>
+#include "../../include/vkhrt_b200.h"
+
+namespace vkhrt {
+
+// Device buffers of one scene.  Everything is sized for 32-bit primitive indices (< 2^31).
+struct DeviceScene {
+    int device = 0;
+    int technique = 0;
+    float radius = VKHRT_DEFAULT_RADIUS;
+    uint32_t n_vertices = 0, n_segments = 0, n_prims = 0, n_nodes = 0;
+    bool built = false;
+
+    // input (Assimp-shaped line mesh)
+    float* d_positions = nullptr;      // n_vertices * 3
+    uint32_t* d_indices = nullptr;     // n_segments * 2
+    float* d_radius_pv = nullptr;      // n_vertices or null
+
+    // acceleration structure
+    float4* d_nodes = nullptr;         // n_nodes * 4 float4 (VkhrtBvhNode)
+    uint32_t* d_sorted_ids = nullptr;  // n_prims: original primitive id at each Morton-sorted position
+    uint64_t* d_sorted_morton = nullptr;
+    uint32_t* d_parent_internal = nullptr;  // n_nodes: (parent << 1) | slot
+    uint32_t* d_parent_leaf = nullptr;      // n_prims
+    uint32_t* d_refit_flags = nullptr;      // n_nodes
+    float scene_lo[3] = {0, 0, 0}, scene_hi[3] = {0, 0, 0};
+
+    // primitives in Morton-sorted order
+    //   PHANTOM: primA[2p] = {B0.xyz, rmax}, primA[2p+1] = {B3.xyz, bits(prim id)}; primB[2p] = {B1.xyz,0}, primB[2p+1] = {B2.xyz,0}
+    //   LSS:     primA[2p] = {p0.xyz, r0},   primA[2p+1] = {p1.xyz, r1}
+    //   DOTS:    primA[3p] = {v0.xyz, bits(prim id)}, primA[3p+1] = {v1.xyz,0}, primA[3p+2] = {v2.xyz,0}
+    float4* d_primA = nullptr;
+    float4* d_primB = nullptr;
+
+    // per-frame scratch (grown on demand)
+    unsigned long long* d_counters = nullptr;   // [0] work counter, [1..5] stats
+    VkhrtHit* d_hits_scratch = nullptr; size_t hits_scratch_n = 0;
+    float4* d_accum = nullptr; size_t accum_n = 0;
+    uint8_t* d_rgba_scratch = nullptr; size_t rgba_scratch_n = 0;
+    void* h_pinned = nullptr; size_t h_pinned_bytes = 0;   // staging for host outputs
+
+    cudaStream_t stream = nullptr;
+    cudaStream_t copy_stream = nullptr;
+    cudaEvent_t ev[16] = {};
+    VkhrtTiming timing = {};
+    int sm_count = 148;
+};
+
+void set_last_error(const std::string& s);
+void count_launch(uint64_t n = 1);
+
+#define VK_CUDA(call)                                                                              \
+    do {                                                                                           \
+        cudaError_t e_ = (call);                                                                   \
+        if (e_ != cudaSuccess) {                                                                   \
+            ::vkhrt::set_last_error(std::string(#call) + ": " + cudaGetErrorString(e_));           \
+            return e_ == cudaErrorMemoryAllocation ? VKHRT_ERR_OUT_OF_MEMORY : VKHRT_ERR_CUDA;     \
+        }                                                                                          \
+    } while (0)
+
+// build.cu
+int build_scene(DeviceScene& sc, bool refit_only);
+int export_primitives(DeviceScene& sc, float* host_out, size_t out_floats);
+
+// trace.cu
+struct FrameParams;
+int render_frame(DeviceScene& sc, const VkhrtFrameDesc& f, VkhrtHit* hits_out, uint8_t* rgba_out, VkhrtTraceStats* stats);
+int trace_ray_buffer(DeviceScene& sc, const float* rays_dev, uint64_t n, VkhrtHit* hits_dev, cudaStream_t stream);
+int generate_ray_buffer(const VkhrtFrameDesc& f, uint32_t sample, float* rays_dev, cudaStream_t stream);
+int untile_buffer(const VkhrtFrameDesc& f, uint32_t world, const void* gathered, void* row_major, uint32_t elem_bytes,
+                  cudaStream_t stream);
+uint64_t frame_local_pixels(const VkhrtFrameDesc& f);
+
+}  // namespace vkhrt

@@ -1,0 +1,562 @@
+// trace.cu — wavefront ray generator, persistent-thread BVH traversal with the Phantom / LSS / DOTS
+// intersectors, and the closest-hit shading kernel.
+//
+// Replaces (reference paths): shaders/ray_gen.rgen:16-48 (ray generation + traceRayEXT + imageStore),
+// the driver/RT-core traversal behind vkCmdTraceRaysKHR (source/renderer.cpp:156-166),
+// shaders/hair_intersection.rint:132-150 (candidate test + reportIntersectionEXT),
+// shaders/hair_closest_hit.rchit:15-25 and triangle_closest_hit.rchit:43-85 (hit attributes, colour).
+//
+// Compiled with -fmad=false (see hair_math.cuh): hit records are bit-identical to the CPU oracle.
+#include "scene.h"
+#include "hair_math.cuh"
+#include <algorithm>
+#include <cmath>
+
+namespace vkhrt {
+
+constexpr int TR_BLOCK = 128;          // 4 warps per CTA
+constexpr int TR_STACK = 24;           // per-lane shared-memory short stack entries (8 B each)
+constexpr int TR_SPILL = 80;           // per-lane local-memory overflow (Karras depth <= 64 + 32)
+constexpr uint32_t REF_NONE = 0x7FFFFFFFu;
+constexpr uint32_t NO_PENDING = 0xFFFFFFFFu;
+constexpr uint32_t PRIM_NONE = 0xFFFFFFFFu;
+constexpr uint32_t FLAG_HIT = 1u, FLAG_PADDING = 2u;
+
+struct TraceParams {
+    const float4* nodes;
+    const float4* primA;
+    const float4* primB;
+    const uint32_t* sorted_ids;
+    uint32_t n_prims;
+    float radius;
+    // fused ray generation
+    Camera cam;
+    uint32_t W, H;
+    float sx, sy, tmin, tmax;
+    uint32_t T, tiles_x, n_tiles, tile_first, tile_stride, compact;
+    // wavefront mode
+    const float4* rays;
+    unsigned long long n_slots;
+    VkhrtHit* hits;
+    unsigned long long* counters;   // [0] next slot, [1] nodes, [2] prims, [3] hits, [4] iterations, [5] rays
+    uint32_t refill_threshold;
+};
+
+// slot (processing order: tiles, inside a tile 8x4-pixel blocks so one warp = one coherent packet)
+// -> pixel and output index
+struct PixelRef { uint32_t px, py; unsigned long long out; bool valid; };
+VK_DEV PixelRef slot_to_pixel(const TraceParams& p, unsigned long long slot)
+{
+    const uint32_t tt = p.T * p.T;
+    uint32_t tl = (uint32_t)(slot / tt), r = (uint32_t)(slot % tt);
+    uint32_t blk = r >> 5, ln = r & 31u;
+    uint32_t bpr = p.T >> 3;
+    uint32_t x = (blk % bpr) * 8u + (ln & 7u), y = (blk / bpr) * 4u + (ln >> 3);
+    uint32_t tile = p.tile_first + tl * p.tile_stride;
+    PixelRef q;
+    q.px = (tile % p.tiles_x) * p.T + x;
+    q.py = (tile / p.tiles_x) * p.T + y;
+    q.valid = tile < p.n_tiles && q.px < p.W && q.py < p.H;
+    q.out = p.compact ? ((unsigned long long)tl * tt + (unsigned long long)y * p.T + x) : ((unsigned long long)q.py * p.W + q.px);
+    return q;
+}
+
+VK_DEV void store_hit(VkhrtHit* hits, unsigned long long i, float t, uint32_t seg, float u, float3 n, uint32_t prim, uint32_t flags)
+{
+    float4* h = reinterpret_cast<float4*>(hits + i);
+    h[0] = make_float4(t, __uint_as_float(seg), u, n.x);
+    h[1] = make_float4(n.y, n.z, __uint_as_float(prim), __uint_as_float(flags));
+}
+
+VK_DEV bool slab_test(float3 lo, float3 hi, float3 o, float3 id, float tmin, float tcur, float* tnear)
+{
+    float tx0 = (lo.x - o.x) * id.x, tx1 = (hi.x - o.x) * id.x;
+    float ty0 = (lo.y - o.y) * id.y, ty1 = (hi.y - o.y) * id.y;
+    float tz0 = (lo.z - o.z) * id.z, tz1 = (hi.z - o.z) * id.z;
+    float tn = fmaxf(fmaxf(fminf(tx0, tx1), fminf(ty0, ty1)), fmaxf(fminf(tz0, tz1), tmin));
+    float tf = fminf(fminf(fmaxf(tx0, tx1), fmaxf(ty0, ty1)), fminf(fmaxf(tz0, tz1), tcur));
+    *tnear = tn;
+    return tn <= tf;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Persistent-thread traversal.  One warp = one packet of 32 rays pulled from a global counter;
+// idle lanes are refilled by ballot when the live-lane count drops to the threshold.
+// Per lane: nearest-first BVH2 descent, 64-byte nodes fetched as 4 x LDG.128, short stack of
+// (ref, tnear) pairs in shared memory (culled against the current closest hit when popped).
+// Phantom candidates are filtered by the bounding-cylinder test at leaf discovery and the expensive
+// cone march is postponed until every live lane of the warp holds a candidate (or has finished),
+// so the 2..16-iteration loop runs with as many lanes as possible.
+// ------------------------------------------------------------------------------------------------
+template <int TECH, bool STATS, bool WAVEFRONT>
+__global__ void __launch_bounds__(TR_BLOCK) trace_kernel(const TraceParams p)
+{
+    __shared__ uint2 s_stack[TR_STACK][TR_BLOCK];
+    uint2 spill[TR_SPILL];
+    const unsigned FULL = 0xffffffffu;
+    const int tid = threadIdx.x, lane = tid & 31;
+
+    bool alive = false, exhausted = false;
+    float3 o = f3(0, 0, 0), d = f3(0, 0, 1), id = f3(0, 0, 0);
+    float tmin = 0.0f, tcur = 0.0f, best_u = 0.0f;
+    uint32_t best_prim = PRIM_NONE, best_pos = 0;
+    RayFrame fr;
+    fr.e1 = fr.e2 = fr.e3 = f3(0, 0, 0);
+    unsigned long long out_idx = 0;
+    int sp = 0;
+    uint32_t cur = REF_NONE, pending = NO_PENDING;
+    uint32_t st_nodes = 0, st_prims = 0, st_iters = 0, st_hits = 0, st_rays = 0;
+
+    auto push = [&](uint32_t ref, float tn) {
+        uint2 e = make_uint2(ref, __float_as_uint(tn));
+        if (sp < TR_STACK) s_stack[sp][tid] = e; else spill[sp - TR_STACK] = e;
+        ++sp;
+    };
+    auto pop = [&]() -> uint32_t {
+        while (sp > 0) {
+            --sp;
+            uint2 e = sp < TR_STACK ? s_stack[sp][tid] : spill[sp - TR_STACK];
+            if (__uint_as_float(e.y) <= tcur) return e.x;
+        }
+        return REF_NONE;
+    };
+
+    for (;;) {
+        // ---------------- refill idle lanes ----------------
+        unsigned alive_mask = __ballot_sync(FULL, alive);
+        if (!exhausted && (unsigned)__popc(alive_mask) <= p.refill_threshold) {
+            unsigned idle = ~alive_mask;
+            unsigned long long base = 0;
+            if (lane == 0) base = atomicAdd(p.counters, (unsigned long long)__popc(idle));
+            base = __shfl_sync(FULL, base, 0);
+            if (base >= p.n_slots) exhausted = true;
+            if (!alive) {
+                unsigned long long slot = base + (unsigned)__popc(idle & ((1u << lane) - 1u));
+                if (slot < p.n_slots) {
+                    bool valid = true;
+                    if (WAVEFRONT) {
+                        float4 r0 = __ldg(p.rays + 2 * slot), r1 = __ldg(p.rays + 2 * slot + 1);
+                        o = f3(r0.x, r0.y, r0.z); tmin = r0.w; d = f3(r1.x, r1.y, r1.z); tcur = r1.w;
+                        out_idx = slot;
+                    } else {
+                        PixelRef q = slot_to_pixel(p, slot);
+                        valid = q.valid;
+                        out_idx = q.out;
+                        if (valid) {
+                            primary_ray(p.cam, p.W, p.H, q.px, q.py, p.sx, p.sy, &o, &d);
+                            tmin = p.tmin; tcur = p.tmax;
+                        } else if (p.compact && p.hits) {
+                            store_hit(p.hits, out_idx, __int_as_float(0x7f800000), VKHRT_MISS_SEGMENT, 0.0f, f3(0, 0, 0), PRIM_NONE, FLAG_PADDING);
+                        }
+                    }
+                    if (valid) {
+                        id = f3(1.0f / d.x, 1.0f / d.y, 1.0f / d.z);
+                        if (TECH == VKHRT_TECHNIQUE_PHANTOM) fr = make_ray_frame(d);
+                        best_prim = PRIM_NONE; best_pos = 0; best_u = 0.0f;
+                        sp = 0; pending = NO_PENDING;
+                        cur = p.n_prims ? 0u : REF_NONE;
+                        alive = true;
+                        if (STATS) st_rays++;
+                    }
+                }
+            }
+            alive_mask = __ballot_sync(FULL, alive);
+        }
+        if (alive_mask == 0u) {
+            if (exhausted) break;
+            continue;
+        }
+
+        // ---------------- traversal phase ----------------
+        for (;;) {
+            bool searching = alive && pending == NO_PENDING && cur != REF_NONE;
+            if (!__any_sync(FULL, searching)) break;
+            bool is_leaf = (cur & VKHRT_BVH_LEAF) != 0u;
+            if (alive && cur != REF_NONE && !(is_leaf && pending != NO_PENDING)) {
+                if (!is_leaf) {
+                    const float4* nd = p.nodes + 4 * (size_t)cur;
+                    const float4 n0 = __ldg(nd), n1 = __ldg(nd + 1), n2 = __ldg(nd + 2), n3 = __ldg(nd + 3);
+                    if (STATS) st_nodes++;
+                    float tn0, tn1;
+                    bool h0 = slab_test(xyz(n0), xyz(n1), o, id, tmin, tcur, &tn0);
+                    bool h1 = slab_test(xyz(n2), xyz(n3), o, id, tmin, tcur, &tn1);
+                    uint32_t c0 = __float_as_uint(n0.w), c1 = __float_as_uint(n1.w);
+                    if (h0 && h1) {
+                        if (tn1 < tn0) { push(c0, tn0); cur = c1; }
+                        else { push(c1, tn1); cur = c0; }
+                    } else if (h0) cur = c0;
+                    else if (h1) cur = c1;
+                    else cur = pop();
+                } else {
+                    const uint32_t pos = cur & 0x7FFFFFFFu;
+                    if (STATS) st_prims++;
+                    if (TECH == VKHRT_TECHNIQUE_PHANTOM) {
+                        // Prhi early-out (hair_intersection.rint:20-33) with the precomputed rmax
+                        const float4 a0 = __ldg(p.primA + 2 * (size_t)pos), a1 = __ldg(p.primA + 2 * (size_t)pos + 1);
+                        if (ray_hits_cylinder(o, d, xyz(a0), xyz(a1), a0.w)) pending = pos;
+                    } else if (TECH == VKHRT_TECHNIQUE_LSS) {
+                        const float4 a0 = __ldg(p.primA + 2 * (size_t)pos), a1 = __ldg(p.primA + 2 * (size_t)pos + 1);
+                        float t, u;
+                        if (lss_intersect<false>(o, d, xyz(a0), a0.w, xyz(a1), a1.w, &t, &u, nullptr) && t >= tmin && t <= tcur) {
+                            uint32_t prim = __ldg(p.sorted_ids + pos);
+                            if (t < tcur || prim < best_prim) { tcur = t; best_prim = prim; best_pos = pos; best_u = u; }
+                        }
+                    } else {
+                        const float4 a0 = __ldg(p.primA + 3 * (size_t)pos), a1 = __ldg(p.primA + 3 * (size_t)pos + 1),
+                                     a2 = __ldg(p.primA + 3 * (size_t)pos + 2);
+                        uint32_t prim = __float_as_uint(a0.w);
+                        float t, u;
+                        if (tri_intersect(o, d, xyz(a0), xyz(a1), xyz(a2), prim & 1u, &t, &u) && t >= tmin &&
+                            (t < tcur || (t == tcur && prim < best_prim))) {
+                            tcur = t; best_prim = prim; best_pos = pos; best_u = u;
+                        }
+                    }
+                    cur = pop();
+                }
+            }
+        }
+
+        // ---------------- intersect phase: postponed Phantom cone march ----------------
+        if (TECH == VKHRT_TECHNIQUE_PHANTOM) {
+            if (alive && pending != NO_PENDING) {
+                const uint32_t pos = pending;
+                pending = NO_PENDING;
+                const float4 a0 = __ldg(p.primA + 2 * (size_t)pos), a1 = __ldg(p.primA + 2 * (size_t)pos + 1);
+                const float4 b0 = __ldg(p.primB + 2 * (size_t)pos), b1 = __ldg(p.primB + 2 * (size_t)pos + 1);
+                Bezier w;
+                w.p0 = xyz(a0); w.p1 = xyz(b0); w.p2 = xyz(b1); w.p3 = xyz(a1);
+                const uint32_t prim = __float_as_uint(a1.w);
+                float u = 0.0f;
+                float t = phantom_march<STATS>(fr, o, w, p.radius, &u, &st_iters);
+                // hair_intersection.rint:146-148 + the [tMin, tCurrent] interval of reportIntersectionEXT;
+                // exact ties go to the smaller primitive id
+                if (t > 0.0f && t >= tmin && (t < tcur || (t == tcur && prim < best_prim))) {
+                    tcur = t; best_prim = prim; best_pos = pos; best_u = u;
+                }
+            }
+            __syncwarp();
+        }
+
+        // ---------------- retire finished rays: closest-hit attributes ----------------
+        if (alive && cur == REF_NONE && pending == NO_PENDING) {
+            alive = false;
+            if (best_prim != PRIM_NONE) {
+                float3 n;
+                uint32_t seg = best_prim;
+                if (TECH == VKHRT_TECHNIQUE_PHANTOM) {
+                    // hair_intersection.rint:74-76 from the committed (t, u)
+                    const float4 a0 = __ldg(p.primA + 2 * (size_t)best_pos), a1 = __ldg(p.primA + 2 * (size_t)best_pos + 1);
+                    const float4 b0 = __ldg(p.primB + 2 * (size_t)best_pos), b1 = __ldg(p.primB + 2 * (size_t)best_pos + 1);
+                    Bezier w;
+                    w.p0 = xyz(a0); w.p1 = xyz(b0); w.p2 = xyz(b1); w.p3 = xyz(a1);
+                    float3 hp = o + tcur * d;
+                    n = normalize3(hp - bezier_point(w, best_u));
+                } else if (TECH == VKHRT_TECHNIQUE_LSS) {
+                    const float4 a0 = __ldg(p.primA + 2 * (size_t)best_pos), a1 = __ldg(p.primA + 2 * (size_t)best_pos + 1);
+                    float t, u;
+                    lss_intersect<true>(o, d, xyz(a0), a0.w, xyz(a1), a1.w, &t, &u, &n);
+                } else {
+                    const float4 a0 = __ldg(p.primA + 3 * (size_t)best_pos), a1 = __ldg(p.primA + 3 * (size_t)best_pos + 1),
+                                 a2 = __ldg(p.primA + 3 * (size_t)best_pos + 2);
+                    n = tri_normal(d, xyz(a0), xyz(a1), xyz(a2));
+                    seg = best_prim >> 2;
+                }
+                if (p.hits) store_hit(p.hits, out_idx, tcur, seg, best_u, n, best_prim, FLAG_HIT);
+                if (STATS) st_hits++;
+            } else if (p.hits) {
+                store_hit(p.hits, out_idx, __int_as_float(0x7f800000), VKHRT_MISS_SEGMENT, 0.0f, f3(0, 0, 0), PRIM_NONE, 0u);
+            }
+        }
+    }
+
+    if (STATS) {
+#pragma unroll
+        for (int k = 16; k > 0; k >>= 1) {
+            st_nodes += __shfl_xor_sync(FULL, st_nodes, k); st_prims += __shfl_xor_sync(FULL, st_prims, k);
+            st_iters += __shfl_xor_sync(FULL, st_iters, k); st_hits += __shfl_xor_sync(FULL, st_hits, k);
+            st_rays += __shfl_xor_sync(FULL, st_rays, k);
+        }
+        if (lane == 0) {
+            atomicAdd(p.counters + 1, (unsigned long long)st_nodes); atomicAdd(p.counters + 2, (unsigned long long)st_prims);
+            atomicAdd(p.counters + 3, (unsigned long long)st_hits); atomicAdd(p.counters + 4, (unsigned long long)st_iters);
+            atomicAdd(p.counters + 5, (unsigned long long)st_rays);
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// wavefront ray generator: one 32-byte record per ray {o, tmin, d, tmax}, in slot order
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) raygen_kernel(const TraceParams p, float4* __restrict__ rays)
+{
+    unsigned long long slot = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (slot >= p.n_slots) return;
+    PixelRef q = slot_to_pixel(p, slot);
+    float3 o = f3(0, 0, 0), d = f3(0, 0, 1);
+    float tmin = p.tmin, tmax = p.tmax;
+    if (!q.valid && !p.compact) return;   // row-major layout has no slot for padding pixels
+    if (q.valid) primary_ray(p.cam, p.W, p.H, q.px, q.py, p.sx, p.sy, &o, &d);
+    else tmax = -1.0f;    // empty interval: padding pixels never hit
+    rays[2 * q.out] = make_float4(o.x, o.y, o.z, tmin);
+    rays[2 * q.out + 1] = make_float4(d.x, d.y, d.z, tmax);
+}
+
+// ------------------------------------------------------------------------------------------------
+// closest-hit colour (shading.glsl / debug.glsl) + imageStore to 8-bit UNORM; spp accumulation in fp32
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) shade_kernel(const VkhrtHit* __restrict__ hits, unsigned long long n, int mode, float3 miss,
+                                                    float4* __restrict__ accum, uchar4* __restrict__ rgba, uint32_t sample, uint32_t spp)
+{
+    unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float4* h = reinterpret_cast<const float4*>(hits + i);
+    const float4 h0 = h[0], h1 = h[1];
+    const uint32_t flags = __float_as_uint(h1.w);
+    if (flags & FLAG_PADDING) {
+        if (rgba && sample + 1 == spp) rgba[i] = make_uchar4(0, 0, 0, 0);
+        return;
+    }
+    float3 c;
+    if (flags & FLAG_HIT) c = mode == VKHRT_SHADE_DEBUG_PRIMID ? debug_palette(__float_as_uint(h1.z)) : shade_normal(f3(h0.w, h1.x, h1.y));
+    else c = miss;
+    if (spp > 1) {
+        float4 a = sample == 0 ? make_float4(0, 0, 0, 0) : accum[i];
+        a.x += c.x; a.y += c.y; a.z += c.z;
+        if (sample + 1 < spp) { accum[i] = a; return; }
+        float fs = (float)spp;
+        c = f3(a.x / fs, a.y / fs, a.z / fs);
+    }
+    if (rgba) rgba[i] = make_uchar4((unsigned char)to_unorm8(c.x), (unsigned char)to_unorm8(c.y), (unsigned char)to_unorm8(c.z), 255);
+}
+
+// gathered compact shards (rank-major) -> row-major image; elem = 4 or 32 bytes
+struct alignas(16) Elem32 { uint4 a, b; };
+template <typename E>
+__global__ void __launch_bounds__(256) untile_kernel(const E* __restrict__ src, E* __restrict__ dst, uint32_t W, uint32_t H, uint32_t T,
+                                                     uint32_t tiles_x, uint32_t world, unsigned long long shard_elems)
+{
+    unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (unsigned long long)W * H) return;
+    uint32_t px = (uint32_t)(i % W), py = (uint32_t)(i / W);
+    uint32_t tile = (py / T) * tiles_x + px / T;
+    uint32_t rank = tile % world, tl = tile / world;
+    dst[i] = src[rank * shard_elems + (unsigned long long)tl * T * T + (unsigned long long)(py % T) * T + (px % T)];
+}
+
+// ------------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------------
+struct Resolved {
+    uint32_t W, H, spp, T, tiles_x, tiles_y, n_tiles, tile_first, tile_stride, n_local_tiles;
+    bool compact;
+    float tmin, tmax;
+    unsigned long long n_slots, n_out;
+};
+static bool resolve(const VkhrtFrameDesc& f, Resolved& r)
+{
+    r.W = f.width; r.H = f.height;
+    if (r.W == 0 || r.H == 0) return false;
+    r.spp = f.spp ? f.spp : 1;
+    r.T = f.tile_size ? f.tile_size : 64;
+    if (r.T % 8 != 0 || r.T > 1024) return false;
+    r.tile_stride = f.tile_stride ? f.tile_stride : 1;
+    r.tile_first = f.tile_first;
+    if (r.tile_first >= r.tile_stride) return false;
+    r.tiles_x = (r.W + r.T - 1) / r.T; r.tiles_y = (r.H + r.T - 1) / r.T;
+    r.n_tiles = r.tiles_x * r.tiles_y;
+    r.compact = r.tile_stride > 1;
+    r.n_local_tiles = (r.n_tiles + r.tile_stride - 1) / r.tile_stride;
+    r.n_slots = (unsigned long long)r.n_local_tiles * r.T * r.T;
+    r.n_out = r.compact ? r.n_slots : (unsigned long long)r.W * r.H;
+    bool def = f.t_min == 0.0f && f.t_max == 0.0f;
+    r.tmin = def ? VKHRT_DEFAULT_T_MIN : f.t_min;
+    r.tmax = def ? VKHRT_DEFAULT_T_MAX : f.t_max;
+    return true;
+}
+
+uint64_t frame_local_pixels(const VkhrtFrameDesc& f)
+{
+    Resolved r;
+    if (!resolve(f, r)) return 0;
+    return r.n_out;
+}
+
+static void sample_offset(uint32_t s, float* sx, float* sy)
+{
+    if (s == 0) { *sx = 0.5f; *sy = 0.5f; return; }
+    const double a1 = 0.7548776662466927, a2 = 0.5698402909980532;   // R2 sequence
+    double x = 0.5 + a1 * (double)s, y = 0.5 + a2 * (double)s;
+    *sx = (float)(x - std::floor(x)); *sy = (float)(y - std::floor(y));
+}
+
+static void fill_params(const DeviceScene& sc, const VkhrtFrameDesc& f, const Resolved& r, TraceParams& p)
+{
+    p.nodes = sc.d_nodes; p.primA = sc.d_primA; p.primB = sc.d_primB; p.sorted_ids = sc.d_sorted_ids;
+    p.n_prims = sc.n_prims; p.radius = sc.radius;
+    memcpy(p.cam.vi, f.view_inverse, sizeof(p.cam.vi)); memcpy(p.cam.pi, f.proj_inverse, sizeof(p.cam.pi));
+    p.W = r.W; p.H = r.H; p.sx = 0.5f; p.sy = 0.5f; p.tmin = r.tmin; p.tmax = r.tmax;
+    p.T = r.T; p.tiles_x = r.tiles_x; p.n_tiles = r.n_tiles; p.tile_first = r.tile_first; p.tile_stride = r.tile_stride; p.compact = r.compact ? 1u : 0u;
+    p.rays = nullptr; p.n_slots = r.n_slots; p.hits = nullptr; p.counters = sc.d_counters; p.refill_threshold = 0;
+}
+
+static int g_refill_threshold = -1;
+static int g_blocks_per_sm = -1;
+static int env_int(const char* name, int def) { const char* v = getenv(name); return v ? atoi(v) : def; }
+
+template <int TECH, bool STATS, bool WAVEFRONT>
+static int launch_trace_t(const DeviceScene& sc, TraceParams& p, cudaStream_t st)
+{
+    int per_sm = 0;
+    VK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, trace_kernel<TECH, STATS, WAVEFRONT>, TR_BLOCK, 0));
+    if (per_sm < 1) per_sm = 1;
+    if (g_blocks_per_sm < 0) g_blocks_per_sm = env_int("VKHRT_BLOCKS_PER_SM", 0);
+    if (g_blocks_per_sm > 0) per_sm = std::min(per_sm, g_blocks_per_sm);
+    if (g_refill_threshold < 0) g_refill_threshold = env_int("VKHRT_REFILL_THRESHOLD", 0);
+    p.refill_threshold = (uint32_t)g_refill_threshold;
+    unsigned long long want = (p.n_slots + TR_BLOCK - 1) / TR_BLOCK;
+    unsigned grid = (unsigned)std::min<unsigned long long>((unsigned long long)sc.sm_count * per_sm, std::max<unsigned long long>(want, 1ull));
+    trace_kernel<TECH, STATS, WAVEFRONT><<<grid, TR_BLOCK, 0, st>>>(p);
+    count_launch();
+    return VKHRT_OK;
+}
+template <bool STATS, bool WAVEFRONT>
+static int launch_trace(const DeviceScene& sc, TraceParams& p, cudaStream_t st)
+{
+    switch (sc.technique) {
+    case VKHRT_TECHNIQUE_PHANTOM: return launch_trace_t<VKHRT_TECHNIQUE_PHANTOM, STATS, WAVEFRONT>(sc, p, st);
+    case VKHRT_TECHNIQUE_LSS: return launch_trace_t<VKHRT_TECHNIQUE_LSS, STATS, WAVEFRONT>(sc, p, st);
+    default: return launch_trace_t<VKHRT_TECHNIQUE_DOTS, STATS, WAVEFRONT>(sc, p, st);
+    }
+}
+
+template <typename T>
+static int grow(T** p, size_t* have, size_t want)
+{
+    if (*have >= want) return VKHRT_OK;
+    if (*p) cudaFree(*p);
+    *p = nullptr; *have = 0;
+    VK_CUDA(cudaMalloc((void**)p, want * sizeof(T)));
+    *have = want;
+    return VKHRT_OK;
+}
+
+int render_frame(DeviceScene& sc, const VkhrtFrameDesc& f, VkhrtHit* hits_out, uint8_t* rgba_out, VkhrtTraceStats* stats)
+{
+    VK_CUDA(cudaSetDevice(sc.device));
+    Resolved r;
+    if (!resolve(f, r)) { set_last_error("vkhrt_render: bad frame description (size, tile_size multiple of 8, tile_first < tile_stride)"); return VKHRT_ERR_INVALID_ARGUMENT; }
+    const bool host_out = f.output_memory == VKHRT_MEM_HOST;
+    cudaStream_t st = (!host_out && f.stream) ? (cudaStream_t)f.stream : sc.stream;
+    int rc;
+
+    // device-side destinations: sample-0 hit records go to the caller's buffer when it is device memory,
+    // otherwise to scratch[0, n_out); samples >= 1 (only traced when an image is wanted) use scratch[n_out, 2 n_out)
+    const bool want_rgba = rgba_out != nullptr;
+    const bool want_hits = hits_out != nullptr;
+    const bool multi = r.spp > 1 && want_rgba;
+    const bool direct_hits = !host_out && want_hits;
+    VkhrtHit* d_hits0 = nullptr;
+    VkhrtHit* d_hits_other = nullptr;
+    uint8_t* d_rgba = nullptr;
+    if ((want_hits || want_rgba) && (!direct_hits || multi)) {
+        if ((rc = grow(&sc.d_hits_scratch, &sc.hits_scratch_n, (size_t)r.n_out * (multi ? 2 : 1)))) return rc;
+    }
+    if (want_hits || want_rgba) d_hits0 = direct_hits ? hits_out : sc.d_hits_scratch;
+    if (multi) d_hits_other = sc.d_hits_scratch + r.n_out;
+    if (want_rgba) {
+        if (host_out) { if ((rc = grow(&sc.d_rgba_scratch, &sc.rgba_scratch_n, (size_t)r.n_out * 4))) return rc; d_rgba = sc.d_rgba_scratch; }
+        else d_rgba = rgba_out;
+        if (multi) { if ((rc = grow(&sc.d_accum, &sc.accum_n, (size_t)r.n_out))) return rc; }
+    }
+
+    TraceParams p;
+    fill_params(sc, f, r, p);
+    const float3 miss = make_float3(f.miss_rgb[0], f.miss_rgb[1], f.miss_rgb[2]);
+    cudaEvent_t* ev = sc.ev;
+    VK_CUDA(cudaEventRecord(ev[6], st));
+    if (stats) VK_CUDA(cudaMemsetAsync(sc.d_counters, 0, 8 * sizeof(unsigned long long), st));
+    const uint32_t n_samples = (want_rgba || stats) ? r.spp : 1;    // hits only => sample 0 is all that is observable
+    for (uint32_t s = 0; s < n_samples; ++s) {
+        sample_offset(s, &p.sx, &p.sy);
+        p.hits = s == 0 ? d_hits0 : d_hits_other;
+        VK_CUDA(cudaMemsetAsync(sc.d_counters, 0, sizeof(unsigned long long), st));
+        if (s == 0) VK_CUDA(cudaEventRecord(ev[7], st));
+        rc = stats ? launch_trace<true, false>(sc, p, st) : launch_trace<false, false>(sc, p, st);
+        if (rc) return rc;
+        if (s == 0) VK_CUDA(cudaEventRecord(ev[8], st));
+        if (want_rgba) {
+            shade_kernel<<<(unsigned)((r.n_out + 255) / 256), 256, 0, st>>>(p.hits, r.n_out, f.shade_mode, miss, sc.d_accum, (uchar4*)d_rgba, s, r.spp);
+            count_launch();
+        }
+        if (s == 0) VK_CUDA(cudaEventRecord(ev[9], st));
+    }
+    VK_CUDA(cudaEventRecord(ev[10], st));
+    if (host_out) {
+        if (want_hits) VK_CUDA(cudaMemcpyAsync(hits_out, d_hits0, (size_t)r.n_out * sizeof(VkhrtHit), cudaMemcpyDeviceToHost, st));
+        if (want_rgba) VK_CUDA(cudaMemcpyAsync(rgba_out, d_rgba, (size_t)r.n_out * 4, cudaMemcpyDeviceToHost, st));
+    }
+    VK_CUDA(cudaEventRecord(ev[11], st));
+    if (stats) {
+        unsigned long long c[8];
+        VK_CUDA(cudaMemcpyAsync(c, sc.d_counters, sizeof(c), cudaMemcpyDeviceToHost, st));
+        VK_CUDA(cudaStreamSynchronize(st));
+        stats->nodes_visited = c[1]; stats->prims_tested = c[2]; stats->hits = c[3]; stats->phantom_iterations = c[4]; stats->rays = c[5];
+    }
+    if (host_out) VK_CUDA(cudaStreamSynchronize(st));
+    VK_CUDA(cudaGetLastError());
+    return VKHRT_OK;
+}
+
+int trace_ray_buffer(DeviceScene& sc, const float* rays_dev, uint64_t n, VkhrtHit* hits_dev, cudaStream_t stream)
+{
+    VK_CUDA(cudaSetDevice(sc.device));
+    cudaStream_t st = stream ? stream : sc.stream;
+    TraceParams p;
+    memset(&p, 0, sizeof(p));
+    p.nodes = sc.d_nodes; p.primA = sc.d_primA; p.primB = sc.d_primB; p.sorted_ids = sc.d_sorted_ids;
+    p.n_prims = sc.n_prims; p.radius = sc.radius;
+    p.rays = reinterpret_cast<const float4*>(rays_dev); p.n_slots = n; p.hits = hits_dev; p.counters = sc.d_counters;
+    p.T = 8; p.tiles_x = 1; p.tile_stride = 1;
+    if (n == 0) return VKHRT_OK;
+    VK_CUDA(cudaMemsetAsync(sc.d_counters, 0, sizeof(unsigned long long), st));
+    int rc = launch_trace<false, true>(sc, p, st);
+    if (rc) return rc;
+    if (!stream) VK_CUDA(cudaStreamSynchronize(st));
+    VK_CUDA(cudaGetLastError());
+    return VKHRT_OK;
+}
+
+int generate_ray_buffer(const VkhrtFrameDesc& f, uint32_t sample, float* rays_dev, cudaStream_t stream)
+{
+    Resolved r;
+    if (!resolve(f, r)) { set_last_error("vkhrt_generate_rays: bad frame description"); return VKHRT_ERR_INVALID_ARGUMENT; }
+    TraceParams p;
+    memset(&p, 0, sizeof(p));
+    DeviceScene dummy;
+    fill_params(dummy, f, r, p);
+    sample_offset(sample, &p.sx, &p.sy);
+    // padding slots of the non-compact layout have no output position: generate exactly the n_out records
+    raygen_kernel<<<(unsigned)((p.n_slots + 255) / 256), 256, 0, stream>>>(p, reinterpret_cast<float4*>(rays_dev));
+    count_launch();
+    VK_CUDA(cudaGetLastError());
+    return VKHRT_OK;
+}
+
+int untile_buffer(const VkhrtFrameDesc& f, uint32_t world, const void* gathered, void* row_major, uint32_t elem_bytes, cudaStream_t stream)
+{
+    VkhrtFrameDesc g = f;
+    g.tile_first = 0; g.tile_stride = world;
+    Resolved r;
+    if (!resolve(g, r) || world == 0) { set_last_error("vkhrt_untile: bad frame description"); return VKHRT_ERR_INVALID_ARGUMENT; }
+    unsigned long long shard = (unsigned long long)r.n_local_tiles * r.T * r.T;
+    if (world == 1) shard = (unsigned long long)r.n_tiles * r.T * r.T;
+    unsigned grid = (unsigned)(((unsigned long long)r.W * r.H + 255) / 256);
+    if (elem_bytes == 4) untile_kernel<uint32_t><<<grid, 256, 0, stream>>>((const uint32_t*)gathered, (uint32_t*)row_major, r.W, r.H, r.T, r.tiles_x, world, shard);
+    else if (elem_bytes == 32) untile_kernel<Elem32><<<grid, 256, 0, stream>>>((const Elem32*)gathered, (Elem32*)row_major, r.W, r.H, r.T, r.tiles_x, world, shard);
+    else { set_last_error("vkhrt_untile: elem_bytes must be 4 or 32"); return VKHRT_ERR_INVALID_ARGUMENT; }
+    count_launch();
+    VK_CUDA(cudaGetLastError());
+    return VKHRT_OK;
+}
+
+}  // namespace vkhrt
