@@ -202,11 +202,12 @@ def test_edge_cases(V, O):
                     [-3, 149, 1], [-2, 149.1, 1], [-1, 149, 1], [0, 149.1, 1], [1, 149, 1], [2, 149.1, 1],
                     [3, 152, 0], [2, 152, 0]], np.float32)
     idx = np.array([[0, 1], [2, 3], [3, 4], [5, 6], [6, 7], [7, 8], [8, 9], [9, 10], [11, 12]], np.uint32)
+    vi, pi = V.camera_matrices(position=(0.0, 150.5, 4.0), aspect=float(np.float32(W) / np.float32(H)))   # close-up: hairs are > 1 px wide
     for tech in TECHS:
         for p, i in ((pos[:2], idx[:1]), (pos, idx)):
-            with V.Scene(p, i, technique=tech) as sc:
+            with V.Scene(p, i, technique=tech, radius=0.1) as sc:   # non-default radius, > 1 px wide
                 sc.build()
-                orc = O.OracleScene(p, i, technique=tech)
+                orc = O.OracleScene(p, i, technique=tech, radius=0.1)
                 hg, ig, _ = sc.render(V.make_frame(vi, pi, W, H))
                 ho, io, _ = orc.render(O.make_frame(vi, pi, W, H))
                 assert (ho["flags"] & 1).sum() > 0
