@@ -289,6 +289,8 @@ def main():
     if world > 1:
         dist.all_reduce(agg)
     rays_c, nodes_c, prims_c, hits_c, iters_c = [float(x) for x in agg.tolist()]
+    sched = {k: {"steps": int(s_), "lanes_per_step": (l_ / s_ if s_ else 0.0)}
+             for k, s_, l_ in zip(("node", "leaf", "march", "refill"), stats["sched_steps"], stats["sched_lanes"])}
 
     if rank == 0:
         peak, peak_src = peaks()
@@ -318,7 +320,7 @@ def main():
                          "peak_source": peak_src,
                          "bytes_per_ray": b_ray, "n_int_per_ray": n_int, "n_prim_per_ray": n_prim,
                          "phantom_iterations_per_ray": iters_c / rays_c, "hit_fraction": hits_c / rays_c,
-                         "kernel_ms": frame_timing["trace_ms"],
+                         "kernel_ms": frame_timing["trace_ms"], "warp_scheduler_rank0": sched,
                          "note": "B_ray = 64*N_int + P*N_prim + W from the GPU kernel's own debug counters (L2-resident upper levels "
                                  "make this exceed DRAM traffic; see DESIGN.md §6)"},
         }

@@ -164,6 +164,10 @@ typedef struct VkhrtTraceStats {
     uint64_t prims_tested;      /* leaf primitives handed to the intersector                       */
     uint64_t hits;
     uint64_t phantom_iterations;
+    /* warp scheduler: steps executed per state {node, leaf, march, refill} and the lanes active in them
+     * (lanes / (32 * steps) = SIMD occupancy of that state) */
+    uint64_t sched_steps[4];
+    uint64_t sched_lanes[4];
 } VkhrtTraceStats;
 
 typedef struct VkhrtScene VkhrtScene;

@@ -28,10 +28,14 @@ class FrameDesc(C.Structure):
 
 class TraceStats(C.Structure):
     _fields_ = [("rays", C.c_uint64), ("nodes_visited", C.c_uint64), ("prims_tested", C.c_uint64),
-                ("hits", C.c_uint64), ("phantom_iterations", C.c_uint64)]
+                ("hits", C.c_uint64), ("phantom_iterations", C.c_uint64),
+                ("sched_steps", C.c_uint64 * 4), ("sched_lanes", C.c_uint64 * 4)]
 
     def as_dict(self):
-        return {k: int(getattr(self, k)) for k, _ in self._fields_}
+        d = {k: int(getattr(self, k)) for k, _ in self._fields_[:5]}
+        d["sched_steps"] = [int(x) for x in self.sched_steps]
+        d["sched_lanes"] = [int(x) for x in self.sched_lanes]
+        return d
 
 
 def build(force=False):

@@ -112,8 +112,8 @@ int vkhrt_scene_create(const VkhrtSceneDesc* desc, VkhrtScene** out_scene)
     VK_TRY(cudaStreamCreateWithFlags(&sc->stream, cudaStreamNonBlocking));
     VK_TRY(cudaStreamCreateWithFlags(&sc->copy_stream, cudaStreamNonBlocking));
     for (auto& e : sc->ev) VK_TRY(cudaEventCreate(&e));
-    VK_TRY(cudaMalloc(&sc->d_counters, 8 * sizeof(unsigned long long)));
-    VK_TRY(cudaMemsetAsync(sc->d_counters, 0, 8 * sizeof(unsigned long long), sc->stream));
+    VK_TRY(cudaMalloc(&sc->d_counters, 16 * sizeof(unsigned long long)));
+    VK_TRY(cudaMemsetAsync(sc->d_counters, 0, 16 * sizeof(unsigned long long), sc->stream));
     VK_TRY(cudaMalloc(&sc->d_positions, std::max<size_t>(1, (size_t)sc->n_vertices * 3) * sizeof(float)));
     VK_TRY(cudaMalloc(&sc->d_indices, std::max<size_t>(1, (size_t)sc->n_segments * 2) * sizeof(uint32_t)));
     if (sc->n_vertices) VK_TRY(cudaMemcpyAsync(sc->d_positions, desc->positions_xyz, (size_t)sc->n_vertices * 12, cudaMemcpyHostToDevice, sc->stream));
@@ -132,7 +132,7 @@ int vkhrt_scene_create(const VkhrtSceneDesc* desc, VkhrtScene** out_scene)
         VK_TRY(cudaMemcpyAsync(&bad, d_bad, 4, cudaMemcpyDeviceToHost, sc->stream));
         VK_TRY(cudaStreamSynchronize(sc->stream));
         if (bad) { set_last_error("line index out of range"); free_scene(sc); return VKHRT_ERR_BAD_TOPOLOGY; }
-        VK_TRY(cudaMemsetAsync(sc->d_counters, 0, 8 * sizeof(unsigned long long), sc->stream));
+        VK_TRY(cudaMemsetAsync(sc->d_counters, 0, 16 * sizeof(unsigned long long), sc->stream));
     }
     VK_TRY(cudaStreamSynchronize(sc->stream));   // inputs are copied before return
 #undef VK_TRY

@@ -4,10 +4,16 @@
 //   shaders/curve.glsl:9-47, cylinder.glsl:8-46, ray.glsl:13-33, cone.glsl:21-62,
 //   hair_intersection.rint:15-150, ray_gen.rgen:16-48, shading.glsl:1-11, debug.glsl:1-7.
 //
-// Floating-point contract: this translation unit is compiled with -fmad=false and
-// the default -prec-div=true -prec-sqrt=true, so every fp32 operation below is one IEEE
-// round-to-nearest operation in exactly the order written.  Results are therefore a pure
-// function of (ray, primitive) and do not depend on traversal order.
+// Floating-point contract: compiled with -fmad=false and the default -prec-div=true
+// -prec-sqrt=true, so every fp32 operation below is ONE IEEE round-to-nearest operation in exactly
+// the order written, and the only fused multiply-adds are the explicit fmaf() calls.
+//   * shader-side math (everything that follows a .glsl/.rint/.rgen/.rchit file, plus the LSS /
+//     triangle / slab tests defined by this project) is written with explicit fmaf() where an
+//     FMA-contracting GLSL compiler fuses a*b + c  -> fdot3 / fcross3 / fnormalize3 / fmadd3;
+//   * host-side math (geometry_processor.cpp restatements used by build.cu) is unfused
+//     -> dot3 / cross3 / normalize3.
+// The CPU oracle follows the same contract, so results are a pure function of (ray, primitive),
+// bit-identical on both sides, and do not depend on traversal order.
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -32,6 +38,18 @@ VK_DEV float3 normalize3(float3 a)
     return a * inv;
 }
 VK_DEV float3 xyz(float4 v) { return f3(v.x, v.y, v.z); }
+// fused (shader-side) helpers
+VK_DEV float fdot3(float3 a, float3 b) { return fmaf(a.z, b.z, fmaf(a.y, b.y, a.x * b.x)); }
+VK_DEV float3 fcross3(float3 a, float3 b)
+{
+    return f3(fmaf(a.y, b.z, -(a.z * b.y)), fmaf(a.z, b.x, -(a.x * b.z)), fmaf(a.x, b.y, -(a.y * b.x)));
+}
+VK_DEV float3 fnormalize3(float3 a)
+{
+    float inv = 1.0f / sqrtf(fdot3(a, a));
+    return a * inv;
+}
+VK_DEV float3 fmadd3(float s, float3 a, float3 b) { return f3(fmaf(s, a.x, b.x), fmaf(s, a.y, b.y), fmaf(s, a.z, b.z)); }   // s*a + b
 
 // ---- cubic Bezier in Bernstein form: shaders/curve.glsl:9-31 ---------------------------------
 struct Bezier { float3 p0, p1, p2, p3; };
@@ -45,17 +63,17 @@ VK_DEV float3 bezier_point(const Bezier& c, float t)
     float w3 = tt * t;
     float w1 = (3.0f * uu) * t;
     float w2 = (3.0f * u) * tt;
-    return ((w0 * c.p0 + w1 * c.p1) + w2 * c.p2) + w3 * c.p3;
+    return fmadd3(w3, c.p3, fmadd3(w2, c.p2, fmadd3(w1, c.p1, w0 * c.p0)));
 }
 
 VK_DEV float3 bezier_axis(const Bezier& c, float t)
 {
     float u = 1.0f - t;
     float w0 = (-3.0f * u) * u;
-    float w1 = 3.0f * ((((3.0f * t) * t) - (4.0f * t)) + 1.0f);
-    float w2 = (3.0f * (2.0f - (3.0f * t))) * t;
+    float w1 = 3.0f * (fmaf(3.0f * t, t, -(4.0f * t)) + 1.0f);
+    float w2 = (3.0f * fmaf(-3.0f, t, 2.0f)) * t;
     float w3 = (3.0f * t) * t;
-    return ((w0 * c.p0 + w1 * c.p1) + w2 * c.p2) + w3 * c.p3;
+    return fmadd3(w3, c.p3, fmadd3(w2, c.p2, fmadd3(w1, c.p1, w0 * c.p0)));
 }
 
 // rmax of Prhi (hair_intersection.rint:21-22): chord distance of B(0.5) + radius.  A function of the
@@ -63,10 +81,59 @@ VK_DEV float3 bezier_axis(const Bezier& c, float t)
 VK_DEV float bezier_bound_radius(const Bezier& c, float radius)
 {
     float3 m = bezier_point(c, 0.5f);
-    float3 x = cross3(m - c.p0, m - c.p3);
+    float3 x = fcross3(m - c.p0, m - c.p3);
     float3 ch = c.p3 - c.p0;
-    float r = sqrtf(dot3(x, x)) / sqrtf(dot3(ch, ch));
+    float r = sqrtf(fdot3(x, x)) / sqrtf(fdot3(ch, ch));
     return r + radius;
+}
+
+// ---- conservative candidate filter (NOT in the reference; result-neutral by construction) -----
+// Prhi reports a hit only from a REAL cone intersection with |dt| < 5e-5 (hair_intersection.rint:67).
+// In ray-centric coordinates the hit point h = (0,0,c.z+s) then satisfies |h - B(t)|^2 = r^2 + dt^2 |B'(t)|^2
+// (cone.glsl:21-62 with slant 0), so the ray passes within r*(1 + 1e-6) of the curve point B(t), t in [0,1].
+// Every B(t) lies within `dev` of one of the two half-chords [B(0),B(1/2)], [B(1/2),B(1)] (convex-hull
+// property of the de Casteljau halves), and projecting onto the plane orthogonal to the ray cannot increase
+// distances.  Hence: if the ray's projection (the origin of the ray-centric xy-plane) is farther than
+// r + dev (+ rounding slack) from BOTH projected half-chords, the march cannot report anything and is
+// skipped.  bezier_half_chord_deviation() is evaluated once per curve by the build kernel.
+VK_DEV float point_segment_distance(float3 p, float3 a, float3 b)
+{
+    float3 e = b - a, q = p - a;
+    float ee = fdot3(e, e);
+    float t = fminf(fmaxf(fdot3(q, e), 0.0f), ee);
+    float s = ee > 0.0f ? t / ee : 0.0f;
+    float3 r = q - s * e;
+    return sqrtf(fdot3(r, r));
+}
+VK_DEV float bezier_half_chord_deviation(const Bezier& c)
+{
+    float3 q01 = 0.5f * (c.p0 + c.p1), q12 = 0.5f * (c.p1 + c.p2), q23 = 0.5f * (c.p2 + c.p3);
+    float3 r0 = 0.5f * (q01 + q12), r1 = 0.5f * (q12 + q23);
+    float3 m = 0.5f * (r0 + r1);
+    float dv = fmaxf(fmaxf(point_segment_distance(q01, c.p0, m), point_segment_distance(r0, c.p0, m)),
+                     fmaxf(point_segment_distance(r1, m, c.p3), point_segment_distance(q23, m, c.p3)));
+    return dv * 1.001f + 1e-7f;      // inflated: the bound must stay conservative under fp32 rounding
+}
+// squared distance from the origin to the 2-D segment [a, b]
+VK_DEV float origin_segment_dist2(float ax, float ay, float bx, float by)
+{
+    float ex = bx - ax, ey = by - ay;
+    float ee = fmaf(ex, ex, ey * ey);
+    float t = fminf(fmaxf(-fmaf(ax, ex, ay * ey), 0.0f), ee);
+    float s = ee > 0.0f ? t / ee : 0.0f;
+    float px = fmaf(s, ex, ax), py = fmaf(s, ey, ay);
+    return fmaf(px, px, py * py);
+}
+// c = curve in ray-centric coordinates.  true => the march may report a hit (NaNs never reject).
+VK_DEV bool half_chords_near_ray(const Bezier& c, float radius, float dev)
+{
+    float mx = 0.125f * ((c.p0.x + c.p3.x) + 3.0f * (c.p1.x + c.p2.x));
+    float my = 0.125f * ((c.p0.y + c.p3.y) + 3.0f * (c.p1.y + c.p2.y));
+    float bound = (radius + dev) * 1.001f + 4e-6f * (fabsf(c.p0.z) + fabsf(c.p3.z)) + 1e-6f;
+    float b2 = bound * bound;
+    float d0 = origin_segment_dist2(c.p0.x, c.p0.y, mx, my);
+    float d1 = origin_segment_dist2(mx, my, c.p3.x, c.p3.y);
+    return !(d0 > b2 && d1 > b2);
 }
 
 // ---- shaders/cylinder.glsl:8-46 (boolean, no t>0 test, assumes |d| = 1) ------------------------
@@ -74,20 +141,20 @@ VK_DEV bool ray_hits_cylinder(float3 o, float3 d, float3 a, float3 b, float radi
 {
     float3 ba = b - a;
     float3 oc = o - a;
-    float baba = dot3(ba, ba);
-    float bard = dot3(ba, d);
-    float baoc = dot3(ba, oc);
-    float k2 = baba - bard * bard;
-    float k1 = baba * dot3(oc, d) - baoc * bard;
-    float k0 = (baba * dot3(oc, oc) - baoc * baoc) - (radius * radius) * baba;
-    float h = k1 * k1 - k2 * k0;
+    float baba = fdot3(ba, ba);
+    float bard = fdot3(ba, d);
+    float baoc = fdot3(ba, oc);
+    float k2 = fmaf(-bard, bard, baba);
+    float k1 = fmaf(baba, fdot3(oc, d), -(baoc * bard));
+    float k0 = fmaf(-(radius * radius), baba, fmaf(baba, fdot3(oc, oc), -(baoc * baoc)));
+    float h = fmaf(k1, k1, -(k2 * k0));
     if (h < 0.0f) return false;
     h = sqrtf(h);
     float t = (-k1 - h) / k2;
-    float y = baoc + t * bard;
+    float y = fmaf(t, bard, baoc);
     if (y > 0.0f && y < baba) return true;
     t = ((y < 0.0f ? 0.0f : baba) - baoc) / bard;
-    return fabsf(k1 + k2 * t) < h;
+    return fabsf(fmaf(k2, t, k1)) < h;
 }
 
 // ---- ray-centric frame: shaders/ray.glsl:13-33 --------------------------------------------------
@@ -97,17 +164,17 @@ struct RayFrame { float3 e1, e2, e3; };
 VK_DEV RayFrame make_ray_frame(float3 d)
 {
     RayFrame f;
-    f.e3 = normalize3(d);
+    f.e3 = fnormalize3(d);
     float3 w = f.e3;
-    f.e2 = fabsf(w.x) > fabsf(w.y) ? normalize3(f3(-w.z, 0.0f, w.x)) : normalize3(f3(0.0f, w.z, -w.y));
-    f.e1 = cross3(f.e2, w);
+    f.e2 = fabsf(w.x) > fabsf(w.y) ? fnormalize3(f3(-w.z, 0.0f, w.x)) : fnormalize3(f3(0.0f, w.z, -w.y));
+    f.e1 = fcross3(f.e2, w);
     return f;
 }
 // inverse of the rigid matrix [e1 e2 e3 o] applied to a point (curve.glsl:33-42 + ray.glsl:32)
 VK_DEV float3 into_frame(const RayFrame& f, float3 o, float3 p)
 {
     float3 q = p - o;
-    return f3(dot3(f.e1, q), dot3(f.e2, q), dot3(f.e3, q));
+    return f3(fdot3(f.e1, q), fdot3(f.e2, q), fdot3(f.e3, q));
 }
 
 // ---- shaders/cone.glsl:21-62, specialised to what Prhi reads (s, dt, real/phantom) --------------
@@ -117,80 +184,88 @@ VK_DEV ConeStep cone_step(float3 c, float radius, float3 ax, float slant)
 {
     float r2 = radius * radius;
     float drr = radius * slant;
-    float ddd = ax.x * ax.x + ax.y * ax.y;
-    float dp = c.x * c.x + c.y * c.y;
-    float cdd = c.x * ax.x + c.y * ax.y;
-    float cxd = c.x * ax.y - c.y * ax.x;
+    float ddd = fmaf(ax.y, ax.y, ax.x * ax.x);
+    float dp = fmaf(c.y, c.y, c.x * c.x);
+    float cdd = fmaf(c.y, ax.y, c.x * ax.x);
+    float cxd = fmaf(c.x, ax.y, -(c.y * ax.x));
     float qc = ddd;
     float qb = ax.z * (drr - cdd);
     float cdz2 = ax.z * ax.z;
     ddd += cdz2;
-    float qa = (((2.0f * drr) * cdd + cxd * cxd) - ddd * r2) + dp * cdz2;
-    float det = qb * qb - qa * qc;
+    float qa = fmaf(dp, cdz2, fmaf(-ddd, r2, fmaf(2.0f * drr, cdd, cxd * cxd)));
+    float det = fmaf(qb, qb, -(qa * qc));
     ConeStep r;
     r.real = det > 0.0f;
     r.s = (qb - (r.real ? sqrtf(det) : 0.0f)) / qc;
-    r.dt = (r.s * ax.z - cdd) / ddd;
+    r.dt = fmaf(r.s, ax.z, -cdd) / ddd;
     return r;
 }
 
 // ---- Phantom Ray-Hair Intersector: hair_intersection.rint:35-130 (after the cylinder early-out) --
-// Returns the reported distance (0 => nothing reported) and the converged curve parameter.
-// `iters` counts cone evaluations (debug statistics only).
-// The loop leaves a side early only when the march has reached an exact fp32 fixed point
-// (t + dt == t on the plain-step branch): every later iteration would then recompute the very
-// same state, so the result is unchanged (proof in DESIGN.md §4.3).
-template <bool kCountIters>
-VK_DEV float phantom_march(const RayFrame& fr, float3 o, const Bezier& world, float radius, float* u_out, uint32_t* iters)
+// The reference's two nested loops (2 sides x <= 8 cone iterations) are unrolled into a resumable
+// state machine so that the traversal kernel can run ONE cone iteration per scheduling step with
+// whatever lanes currently hold a candidate (trace.cu).  march_begin = :38-44, march_step = one
+// pass through the loop body :56-115 plus the side switch :118-126.
+struct MarchState {
+    Bezier c;            // curve in ray-centric coordinates (TransformCurve, curve.glsl:33-42)
+    float t, told, dt1, dt2;
+    float t_start;
+    uint32_t it;         // bits 0..3: iteration i of this side; bit 4: side
+};
+enum MarchResult { MARCH_CONTINUE = 0, MARCH_HIT = 1, MARCH_NOTHING = 2 };
+
+VK_DEV void march_begin(MarchState& m, const RayFrame& fr, float3 o, const Bezier& world)
 {
-    Bezier c;
-    c.p0 = into_frame(fr, o, world.p0);
-    c.p1 = into_frame(fr, o, world.p1);
-    c.p2 = into_frame(fr, o, world.p2);
-    c.p3 = into_frame(fr, o, world.p3);
+    m.c.p0 = into_frame(fr, o, world.p0);
+    m.c.p1 = into_frame(fr, o, world.p1);
+    m.c.p2 = into_frame(fr, o, world.p2);
+    m.c.p3 = into_frame(fr, o, world.p3);
+    float3 chord = m.c.p3 - m.c.p0;
+    float cz = chord.z * (1.0f / sqrtf(fdot3(chord, chord)));   // z of normalize(chord) == dot(., (0,0,1))
+    m.t_start = cz > 0.0f ? 0.0f : 1.0f;
+    m.t = m.t_start;
+    m.told = m.dt1 = m.dt2 = 0.0f;
+    m.it = 0u;
+}
 
-    float3 chord = c.p3 - c.p0;
-    float cz = chord.z * (1.0f / sqrtf(dot3(chord, chord)));   // z of normalize(chord); dot with (0,0,1)
-    float t_start = cz > 0.0f ? 0.0f : 1.0f;
-    float result = 0.0f;
-
-#pragma unroll 1
-    for (int side = 0; side < 2; ++side) {
-        float t = t_start;
-        float told = 0.0f, dt1 = 0.0f, dt2 = 0.0f;
-#pragma unroll 1
-        for (uint32_t i = 0; i < 8u; ++i) {
-            if (kCountIters) (*iters)++;
-            float3 centre = bezier_point(c, t);
-            float3 axis = bezier_axis(c, t);
-            ConeStep cs = cone_step(centre, radius, axis, 0.0f);
-            if (cs.real && fabsf(cs.dt) < 5e-5f) {
-                result = cs.s + centre.z;
-                *u_out = t;
-                break;
-            }
-            float dt = cs.dt;
-            dt = 0.5f < dt ? 0.5f : dt;      // GLSL min(dt, 0.5)
-            dt = dt < -0.5f ? -0.5f : dt;    // GLSL max(dt, -0.5)
-            dt1 = dt2;
-            dt2 = dt;
-            float tn;
-            bool plain = !(dt1 * dt2 < 0.0f);
-            if (!plain) {
-                tn = ((i & 3u) == 0u) ? 0.5f * (told + t) : (dt2 * told - dt1 * t) / (dt2 - dt1);
-            } else {
-                tn = t + dt;
-            }
-            told = t;
-            bool fixed_point = plain && (tn == t);
-            t = tn;
-            if (t < 0.0f || t > 1.0f) break;
-            if (fixed_point) break;
-        }
-        if (result > 0.0f) break;
-        t_start = 1.0f - t_start;
+// One cone iteration.  On MARCH_HIT *t_hit is `result` (may be <= 0: hair_intersection.rint:146 is applied
+// by the caller) and *u_hit the converged curve parameter.
+// A side is also left when the march has reached an exact fp32 fixed point (t + dt == t on the plain-step
+// branch): every later iteration of that side would recompute the very same state, so the outcome is
+// unchanged.
+VK_DEV int march_step(MarchState& m, float radius, float* t_hit, float* u_hit)
+{
+    const uint32_t i = m.it & 15u;
+    float3 centre = bezier_point(m.c, m.t);
+    float3 axis = bezier_axis(m.c, m.t);
+    ConeStep cs = cone_step(centre, radius, axis, 0.0f);
+    if (cs.real && fabsf(cs.dt) < 5e-5f) {
+        *t_hit = cs.s + centre.z;
+        *u_hit = m.t;
+        if (*t_hit > 0.0f || (m.it & 16u)) return MARCH_HIT;     // :119 `if (result > 0.0) break;`
+        // converged behind the origin on the first side: the reference keeps looking from the other end
+    } else {
+        float dt = cs.dt;
+        dt = 0.5f < dt ? 0.5f : dt;      // GLSL min(dt, 0.5)
+        dt = dt < -0.5f ? -0.5f : dt;    // GLSL max(dt, -0.5)
+        m.dt1 = m.dt2;
+        m.dt2 = dt;
+        float tn;
+        const bool plain = !(m.dt1 * m.dt2 < 0.0f);
+        if (!plain) tn = (i & 3u) == 0u ? 0.5f * (m.told + m.t) : fmaf(m.dt2, m.told, -(m.dt1 * m.t)) / (m.dt2 - m.dt1);
+        else tn = m.t + dt;
+        m.told = m.t;
+        const bool fixed_point = plain && tn == m.t;
+        m.t = tn;
+        if (!(tn < 0.0f || tn > 1.0f) && !fixed_point && i < 7u) { m.it++; return MARCH_CONTINUE; }
     }
-    return result;
+    // this side is over without a positive result
+    if (m.it & 16u) return MARCH_NOTHING;
+    m.t_start = 1.0f - m.t_start;
+    m.t = m.t_start;
+    m.told = m.dt1 = m.dt2 = 0.0f;
+    m.it = 16u;
+    return MARCH_CONTINUE;
 }
 
 // ---- LSS: ray vs linear swept sphere (defined by this project; RT hardware in the reference) -----
@@ -203,32 +278,33 @@ VK_DEV bool lss_intersect(float3 o, float3 d, float3 p0, float r0, float3 p1, fl
 {
     float3 ba = p1 - p0;
     float3 oa0 = o - p0;
-    float dd = dot3(d, d);
-    float t0 = (0.0f - dot3(d, oa0)) / dd;
-    float3 oa = oa0 + t0 * d;
-    float m0 = dot3(ba, ba), m1 = dot3(ba, oa), m2 = dot3(ba, d), m3 = dot3(d, oa), m5 = dot3(oa, oa);
+    float dd = fdot3(d, d);
+    float t0 = (0.0f - fdot3(d, oa0)) / dd;
+    float3 oa = fmadd3(t0, d, oa0);
+    float m0 = fdot3(ba, ba), m1 = fdot3(ba, oa), m2 = fdot3(ba, d), m3 = fdot3(d, oa), m5 = fdot3(oa, oa);
     float rr = r0 - r1;
-    float d2 = m0 - rr * rr;
+    float d2 = fmaf(-rr, rr, m0);
+    float q0 = fmaf(-r0, r0, m5);
     float bt = 0.0f, bu = 0.0f;
     bool found = false;
     if (d2 > 0.0f) {
-        float a1 = m1 - r0 * rr;
-        float k2 = d2 * dd - m2 * m2;
-        float k1 = d2 * m3 - m2 * a1;
-        float k0 = d2 * (m5 - r0 * r0) - a1 * a1;
-        float h = k1 * k1 - k2 * k0;
+        float a1 = fmaf(-r0, rr, m1);
+        float k2 = fmaf(d2, dd, -(m2 * m2));
+        float k1 = fmaf(d2, m3, -(m2 * a1));
+        float k0 = fmaf(d2, q0, -(a1 * a1));
+        float h = fmaf(k1, k1, -(k2 * k0));
         if (h >= 0.0f) {
             float t = (-k1 - sqrtf(h)) / k2;
-            float y = a1 + t * m2;
+            float y = fmaf(t, m2, a1);
             if (y > 0.0f && y < d2) { bt = t; bu = y / d2; found = true; }
         }
     }
     if (!found) {
-        float h1 = m3 * m3 - dd * (m5 - r0 * r0);
+        float h1 = fmaf(m3, m3, -(dd * q0));
         if (h1 > 0.0f) { bt = (-m3 - sqrtf(h1)) / dd; bu = 0.0f; found = true; }
         float3 ob = oa - ba;
-        float m6 = dot3(d, ob), m7 = dot3(ob, ob);
-        float h2 = m6 * m6 - dd * (m7 - r1 * r1);
+        float m6 = fdot3(d, ob), m7 = fdot3(ob, ob);
+        float h2 = fmaf(m6, m6, -(dd * fmaf(-r1, r1, m7)));
         if (h2 > 0.0f) {
             float t = (-m6 - sqrtf(h2)) / dd;
             if (!found || t < bt) { bt = t; bu = 1.0f; found = true; }
@@ -236,7 +312,7 @@ VK_DEV bool lss_intersect(float3 o, float3 d, float3 p0, float r0, float3 p1, fl
     }
     *t_out = bt + t0;
     *u_out = bu;
-    if (kNormal) *n_out = normalize3((oa + bt * d) - bu * ba);
+    if (kNormal) *n_out = fnormalize3(fmadd3(-bu, ba, fmadd3(bt, d, oa)));
     return found;
 }
 
@@ -244,24 +320,24 @@ VK_DEV bool lss_intersect(float3 o, float3 d, float3 p0, float r0, float3 p1, fl
 VK_DEV bool tri_intersect(float3 o, float3 d, float3 v0, float3 v1, float3 v2, uint32_t parity, float* t_out, float* u_out)
 {
     float3 e1 = v1 - v0, e2 = v2 - v0;
-    float3 p = cross3(d, e2);
-    float det = dot3(e1, p);
+    float3 p = fcross3(d, e2);
+    float det = fdot3(e1, p);
     if (det == 0.0f || det != det) return false;
     float inv = 1.0f / det;
     float3 tv = o - v0;
-    float b1 = dot3(tv, p) * inv;
+    float b1 = fdot3(tv, p) * inv;
     if (!(b1 >= 0.0f && b1 <= 1.0f)) return false;
-    float3 q = cross3(tv, e1);
-    float b2 = dot3(d, q) * inv;
+    float3 q = fcross3(tv, e1);
+    float b2 = fdot3(d, q) * inv;
     if (!(b2 >= 0.0f && b1 + b2 <= 1.0f)) return false;
-    *t_out = dot3(e2, q) * inv;
+    *t_out = fdot3(e2, q) * inv;
     *u_out = parity ? b2 : (b1 + b2);
     return true;
 }
 VK_DEV float3 tri_normal(float3 d, float3 v0, float3 v1, float3 v2)
 {
-    float3 n = normalize3(cross3(v1 - v0, v2 - v0));
-    if (dot3(n, d) > 0.0f) n = f3(-n.x, -n.y, -n.z);
+    float3 n = fnormalize3(fcross3(v1 - v0, v2 - v0));
+    if (fdot3(n, d) > 0.0f) n = f3(-n.x, -n.y, -n.z);
     return n;
 }
 
@@ -273,23 +349,43 @@ VK_DEV void primary_ray(const Camera& cam, uint32_t W, uint32_t H, uint32_t px, 
 {
     float pcx = (float)px + sx, pcy = (float)py + sy;
     float u = pcx / (float)W, v = pcy / (float)H;
-    float dx = u * 2.0f - 1.0f, dy = v * 2.0f - 1.0f;
+    float dx = fmaf(u, 2.0f, -1.0f), dy = fmaf(v, 2.0f, -1.0f);
     *o = f3(cam.vi[12], cam.vi[13], cam.vi[14]);
     float3 tg;
-    tg.x = ((cam.pi[0] * dx + cam.pi[4] * dy) + cam.pi[8]) + cam.pi[12];
-    tg.y = ((cam.pi[1] * dx + cam.pi[5] * dy) + cam.pi[9]) + cam.pi[13];
-    tg.z = ((cam.pi[2] * dx + cam.pi[6] * dy) + cam.pi[10]) + cam.pi[14];
-    float3 nd = normalize3(tg);
-    d->x = (cam.vi[0] * nd.x + cam.vi[4] * nd.y) + cam.vi[8] * nd.z;
-    d->y = (cam.vi[1] * nd.x + cam.vi[5] * nd.y) + cam.vi[9] * nd.z;
-    d->z = (cam.vi[2] * nd.x + cam.vi[6] * nd.y) + cam.vi[10] * nd.z;
+    tg.x = (fmaf(cam.pi[4], dy, cam.pi[0] * dx) + cam.pi[8]) + cam.pi[12];
+    tg.y = (fmaf(cam.pi[5], dy, cam.pi[1] * dx) + cam.pi[9]) + cam.pi[13];
+    tg.z = (fmaf(cam.pi[6], dy, cam.pi[2] * dx) + cam.pi[10]) + cam.pi[14];
+    float3 nd = fnormalize3(tg);
+    d->x = fmaf(cam.vi[8], nd.z, fmaf(cam.vi[4], nd.y, cam.vi[0] * nd.x));
+    d->y = fmaf(cam.vi[9], nd.z, fmaf(cam.vi[5], nd.y, cam.vi[1] * nd.x));
+    d->z = fmaf(cam.vi[10], nd.z, fmaf(cam.vi[6], nd.y, cam.vi[2] * nd.x));
+}
+
+// ---- ray/box slab test in the fused form t = fma(plane, 1/d, -(o/d)) ------------------------------
+// A zero direction component would make o*(1/d) infinite and the fused slab NaN: |1/d| is clamped to 1e20,
+// for which the slab degenerates to the exact "is o inside [lo,hi]" test.
+VK_DEV float safe_rcp(float d)
+{
+    float r = 1.0f / d;
+    if (!(fabsf(r) <= 1e20f)) r = (d < 0.0f || (d == 0.0f && signbit(d))) ? -1e20f : 1e20f;
+    return r;
+}
+VK_DEV bool slab_test(float3 lo, float3 hi, float3 id, float3 noid, float tmin, float tcur, float* tnear)
+{
+    float tx0 = fmaf(lo.x, id.x, noid.x), tx1 = fmaf(hi.x, id.x, noid.x);
+    float ty0 = fmaf(lo.y, id.y, noid.y), ty1 = fmaf(hi.y, id.y, noid.y);
+    float tz0 = fmaf(lo.z, id.z, noid.z), tz1 = fmaf(hi.z, id.z, noid.z);
+    float tn = fmaxf(fmaxf(fminf(tx0, tx1), fminf(ty0, ty1)), fmaxf(fminf(tz0, tz1), tmin));
+    float tf = fminf(fminf(fmaxf(tx0, tx1), fmaxf(ty0, ty1)), fminf(fmaxf(tz0, tz1), tcur));
+    *tnear = tn;
+    return tn <= tf;
 }
 
 // ---- closest-hit colour: shaders/shading.glsl:1-11, debug.glsl:1-7 --------------------------------
 VK_DEV float3 shade_normal(float3 n)
 {
-    float k = fabsf((n.x * 0.0f + n.y * -1.0f) + n.z * 0.0f);
-    return f3(k * 0.4f + 0.3f, k * 0.2f + 0.3f, k * 0.1f + 0.3f);
+    float k = fabsf(fdot3(n, f3(0.0f, -1.0f, 0.0f)));
+    return f3(fmaf(k, 0.4f, 0.3f), fmaf(k, 0.2f, 0.3f), fmaf(k, 0.1f, 0.3f));
 }
 VK_DEV float3 debug_palette(uint32_t prim)
 {

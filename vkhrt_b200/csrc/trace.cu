@@ -18,7 +18,6 @@ constexpr int TR_BLOCK = 128;          // 4 warps per CTA
 constexpr int TR_STACK = 24;           // per-lane shared-memory short stack entries (8 B each)
 constexpr int TR_SPILL = 80;           // per-lane local-memory overflow (Karras depth <= 64 + 32)
 constexpr uint32_t REF_NONE = 0x7FFFFFFFu;
-constexpr uint32_t NO_PENDING = 0xFFFFFFFFu;
 constexpr uint32_t PRIM_NONE = 0xFFFFFFFFu;
 constexpr uint32_t FLAG_HIT = 1u, FLAG_PADDING = 2u;
 
@@ -36,19 +35,20 @@ struct TraceParams {
     uint32_t T, tiles_x, n_tiles, tile_first, tile_stride, compact;
     // wavefront mode
     const float4* rays;
-    unsigned long long n_slots;
+    uint32_t n_slots;
     VkhrtHit* hits;
-    unsigned long long* counters;   // [0] next slot, [1] nodes, [2] prims, [3] hits, [4] iterations, [5] rays
-    uint32_t refill_threshold;
+    unsigned long long* counters;   // [0] next slot, [1] nodes, [2] prims, [3] hits, [4] iterations, [5] rays, [8..11] steps, [12..15] lanes
+    uint32_t refill_threshold;      // lanes waiting for a new ray that trigger a refill step
+    uint32_t w_node, w_leaf, w_march;   // scheduler weights (fixed point, 16 = 1.0)
 };
 
 // slot (processing order: tiles, inside a tile 8x4-pixel blocks so one warp = one coherent packet)
 // -> pixel and output index
-struct PixelRef { uint32_t px, py; unsigned long long out; bool valid; };
-VK_DEV PixelRef slot_to_pixel(const TraceParams& p, unsigned long long slot)
+struct PixelRef { uint32_t px, py; uint32_t out; bool valid; };
+VK_DEV PixelRef slot_to_pixel(const TraceParams& p, uint32_t slot)
 {
     const uint32_t tt = p.T * p.T;
-    uint32_t tl = (uint32_t)(slot / tt), r = (uint32_t)(slot % tt);
+    uint32_t tl = slot / tt, r = slot % tt;
     uint32_t blk = r >> 5, ln = r & 31u;
     uint32_t bpr = p.T >> 3;
     uint32_t x = (blk % bpr) * 8u + (ln & 7u), y = (blk / bpr) * 4u + (ln >> 3);
@@ -57,37 +57,37 @@ VK_DEV PixelRef slot_to_pixel(const TraceParams& p, unsigned long long slot)
     q.px = (tile % p.tiles_x) * p.T + x;
     q.py = (tile / p.tiles_x) * p.T + y;
     q.valid = tile < p.n_tiles && q.px < p.W && q.py < p.H;
-    q.out = p.compact ? ((unsigned long long)tl * tt + (unsigned long long)y * p.T + x) : ((unsigned long long)q.py * p.W + q.px);
+    q.out = p.compact ? (tl * tt + y * p.T + x) : (q.py * p.W + q.px);
     return q;
 }
 
-VK_DEV void store_hit(VkhrtHit* hits, unsigned long long i, float t, uint32_t seg, float u, float3 n, uint32_t prim, uint32_t flags)
+VK_DEV void store_hit(VkhrtHit* hits, size_t i, float t, uint32_t seg, float u, float3 n, uint32_t prim, uint32_t flags)
 {
     float4* h = reinterpret_cast<float4*>(hits + i);
     h[0] = make_float4(t, __uint_as_float(seg), u, n.x);
     h[1] = make_float4(n.y, n.z, __uint_as_float(prim), __uint_as_float(flags));
 }
 
-VK_DEV bool slab_test(float3 lo, float3 hi, float3 o, float3 id, float tmin, float tcur, float* tnear)
-{
-    float tx0 = (lo.x - o.x) * id.x, tx1 = (hi.x - o.x) * id.x;
-    float ty0 = (lo.y - o.y) * id.y, ty1 = (hi.y - o.y) * id.y;
-    float tz0 = (lo.z - o.z) * id.z, tz1 = (hi.z - o.z) * id.z;
-    float tn = fmaxf(fmaxf(fminf(tx0, tx1), fminf(ty0, ty1)), fmaxf(fminf(tz0, tz1), tmin));
-    float tf = fminf(fminf(fmaxf(tx0, tx1), fmaxf(ty0, ty1)), fminf(fmaxf(tz0, tz1), tcur));
-    *tnear = tn;
-    return tn <= tf;
-}
+// ------------------------------------------------------------------------------------------------
+// Persistent-thread traversal with a per-warp majority-state scheduler.
+//
+// One warp owns 32 ray slots; every lane is in exactly one state:
+//   NODE   holds an internal BVH2 node: 64-byte record as 4 x LDG.128, two fused slab tests,
+//          nearest-first descent, the far child goes to a short stack in shared memory;
+//   LEAF   holds a leaf: Phantom -> the Prhi bounding-cylinder early-out (and, on a pass, the change
+//          to ray-centric coordinates); LSS / DOTS -> the full primitive test;
+//   MARCH  (Phantom) holds a candidate curve: ONE cone iteration of the 2 x <=8 root finder;
+//   REFILL ray finished (or lane empty): write the hit record, pull the next slot from the global
+//          counter (warp-aggregated atomic) and generate its primary ray;
+//   DONE   no rays left.
+// Each scheduling step ballots the four live states and executes the code of the most populated one
+// (weighted), staying in it while it keeps >= 3/4 of its lanes.  A ray's own sequence of node visits
+// and candidate tests is exactly the CPU oracle's (nothing is speculated or postponed past a cull),
+// so the hit records AND the traversal counters are identical; only the interleaving across lanes is
+// scheduled for SIMD occupancy.  Justification by ncu counters: DESIGN.md §6.
+// ------------------------------------------------------------------------------------------------
+enum : uint32_t { ST_NODE = 0, ST_POP = 1, ST_LEAF = 2, ST_MARCH = 3, ST_REFILL = 4, ST_DONE = 5 };   // NODE|POP are scheduled together
 
-// ------------------------------------------------------------------------------------------------
-// Persistent-thread traversal.  One warp = one packet of 32 rays pulled from a global counter;
-// idle lanes are refilled by ballot when the live-lane count drops to the threshold.
-// Per lane: nearest-first BVH2 descent, 64-byte nodes fetched as 4 x LDG.128, short stack of
-// (ref, tnear) pairs in shared memory (culled against the current closest hit when popped).
-// Phantom candidates are filtered by the bounding-cylinder test at leaf discovery and the expensive
-// cone march is postponed until every live lane of the warp holds a candidate (or has finished),
-// so the 2..16-iteration loop runs with as many lanes as possible.
-// ------------------------------------------------------------------------------------------------
 template <int TECH, bool STATS, bool WAVEFRONT>
 __global__ void __launch_bounds__(TR_BLOCK) trace_kernel(const TraceParams p)
 {
@@ -95,51 +95,179 @@ __global__ void __launch_bounds__(TR_BLOCK) trace_kernel(const TraceParams p)
     uint2 spill[TR_SPILL];
     const unsigned FULL = 0xffffffffu;
     const int tid = threadIdx.x, lane = tid & 31;
+    constexpr bool PH = TECH == VKHRT_TECHNIQUE_PHANTOM;
 
-    bool alive = false, exhausted = false;
-    float3 o = f3(0, 0, 0), d = f3(0, 0, 1), id = f3(0, 0, 0);
+    uint32_t state = ST_REFILL;
+    bool have_ray = false;           // REFILL: a finished ray is waiting for its hit record to be written
+    float3 o = f3(0, 0, 0), d = f3(0, 0, 1), id = f3(0, 0, 0), noid = f3(0, 0, 0);
     float tmin = 0.0f, tcur = 0.0f, best_u = 0.0f;
     uint32_t best_prim = PRIM_NONE, best_pos = 0;
     RayFrame fr;
     fr.e1 = fr.e2 = fr.e3 = f3(0, 0, 0);
-    unsigned long long out_idx = 0;
+    MarchState ms;
+    ms.c.p0 = ms.c.p1 = ms.c.p2 = ms.c.p3 = f3(0, 0, 0);
+    ms.t = ms.told = ms.dt1 = ms.dt2 = ms.t_start = 0.0f; ms.it = 0u;
+    uint32_t out_idx = 0, mpos = 0;
     int sp = 0;
-    uint32_t cur = REF_NONE, pending = NO_PENDING;
+    uint32_t cur = REF_NONE;
     uint32_t st_nodes = 0, st_prims = 0, st_iters = 0, st_hits = 0, st_rays = 0;
+    uint32_t sc_steps[4] = {0, 0, 0, 0}, sc_lanes[4] = {0, 0, 0, 0};   // lane 0 only (STATS)
 
     auto push = [&](uint32_t ref, float tn) {
         uint2 e = make_uint2(ref, __float_as_uint(tn));
         if (sp < TR_STACK) s_stack[sp][tid] = e; else spill[sp - TR_STACK] = e;
         ++sp;
     };
-    auto pop = [&]() -> uint32_t {
-        while (sp > 0) {
-            --sp;
-            uint2 e = sp < TR_STACK ? s_stack[sp][tid] : spill[sp - TR_STACK];
-            if (__uint_as_float(e.y) <= tcur) return e.x;
-        }
-        return REF_NONE;
+    // ONE stack entry per call (the cull loop runs across scheduling steps, in parallel over lanes):
+    // entries whose box entry distance lies beyond the current closest hit are dropped
+    auto pop_one = [&]() {
+        if (sp == 0) { state = ST_REFILL; return; }
+        --sp;
+        const uint2 e = sp < TR_STACK ? s_stack[sp][tid] : spill[sp - TR_STACK];
+        if (__uint_as_float(e.y) <= tcur) { cur = e.x; state = (e.x & VKHRT_BVH_LEAF) ? ST_LEAF : ST_NODE; }
+    };
+    // reportIntersectionEXT interval [tMin, tCurrent] + deterministic tie rule (smaller primitive id)
+    auto commit = [&](float t, float u, uint32_t prim, uint32_t pos) {
+        if (t >= tmin && (t < tcur || (t == tcur && prim < best_prim))) { tcur = t; best_prim = prim; best_pos = pos; best_u = u; }
     };
 
     for (;;) {
-        // ---------------- refill idle lanes ----------------
-        unsigned alive_mask = __ballot_sync(FULL, alive);
-        if (!exhausted && (unsigned)__popc(alive_mask) <= p.refill_threshold) {
-            unsigned idle = ~alive_mask;
+        // ---------------- scheduler ----------------
+        const unsigned mN = __ballot_sync(FULL, state <= ST_POP);
+        const unsigned mL = __ballot_sync(FULL, state == ST_LEAF);
+        const unsigned mM = PH ? __ballot_sync(FULL, state == ST_MARCH) : 0u;
+        const unsigned mR = __ballot_sync(FULL, state == ST_REFILL);
+        const uint32_t nN = __popc(mN), nL = __popc(mL), nM = __popc(mM), nR = __popc(mR);
+        if ((mN | mL | mM | mR) == 0u) break;
+        uint32_t pick;
+        if (nR > 0u && (nR >= p.refill_threshold || (mN | mL | mM) == 0u)) pick = ST_REFILL;
+        else {
+            const uint32_t sN = nN * p.w_node, sL = nL * p.w_leaf, sM = nM * p.w_march;
+            pick = (sN >= sL && sN >= sM) ? ST_NODE : (sM >= sL ? ST_MARCH : ST_LEAF);
+        }
+
+        if (pick == ST_NODE) {
+            // ---------------- internal nodes ----------------
+            uint32_t n0 = nN, n1;
+            do {
+                if (STATS) { sc_steps[0]++; sc_lanes[0] += __popc(__ballot_sync(FULL, state <= ST_POP)); }
+                if (state == ST_POP) pop_one();
+                if (state == ST_NODE) {
+                    const float4* nd = p.nodes + 4 * (size_t)cur;
+                    const float4 q0 = __ldg(nd), q1 = __ldg(nd + 1), q2 = __ldg(nd + 2), q3 = __ldg(nd + 3);
+                    if (STATS) st_nodes++;
+                    float tn0, tn1;
+                    const bool h0 = slab_test(xyz(q0), xyz(q1), id, noid, tmin, tcur, &tn0);
+                    const bool h1 = slab_test(xyz(q2), xyz(q3), id, noid, tmin, tcur, &tn1);
+                    const uint32_t c0 = __float_as_uint(q0.w), c1 = __float_as_uint(q1.w);
+                    // nearest-first: descend into the nearer hit child, the other one (if hit) goes to the stack
+                    const bool both = h0 && h1;
+                    const bool second = both ? (tn1 < tn0) : h1;
+                    const uint32_t near_ref = second ? c1 : c0, far_ref = second ? c0 : c1;
+                    if (both) push(far_ref, second ? tn0 : tn1);
+                    if (h0 || h1) { cur = near_ref; if (near_ref & VKHRT_BVH_LEAF) state = ST_LEAF; }
+                    else state = ST_POP;
+                }
+                n1 = __popc(__ballot_sync(FULL, state <= ST_POP));
+            } while (n1 * 4u >= n0 * 3u && n1 > 0u);
+        } else if (pick == ST_LEAF) {
+            // ---------------- leaves ----------------
+            if (STATS) { sc_steps[1]++; sc_lanes[1] += nL; }
+            if (state == ST_LEAF) {
+                const uint32_t pos = cur & 0x7FFFFFFFu;
+                if (STATS) st_prims++;
+                if (PH) {
+                    // Prhi early-out (hair_intersection.rint:20-33) with the precomputed rmax
+                    const float4 a0 = __ldg(p.primA + 2 * (size_t)pos), a1 = __ldg(p.primA + 2 * (size_t)pos + 1);
+                    if (ray_hits_cylinder(o, d, xyz(a0), xyz(a1), a0.w)) {
+                        const float4 b0 = __ldg(p.primB + 2 * (size_t)pos), b1 = __ldg(p.primB + 2 * (size_t)pos + 1);
+                        Bezier w;
+                        w.p0 = xyz(a0); w.p1 = xyz(b0); w.p2 = xyz(b1); w.p3 = xyz(a1);
+                        march_begin(ms, fr, o, w);
+                        mpos = pos;
+                        // conservative filter (hair_math.cuh): skip marches that cannot report a hit
+                        state = half_chords_near_ray(ms.c, p.radius, b0.w) ? ST_MARCH : ST_POP;
+                    } else state = ST_POP;
+                } else if (TECH == VKHRT_TECHNIQUE_LSS) {
+                    const float4 a0 = __ldg(p.primA + 2 * (size_t)pos), a1 = __ldg(p.primA + 2 * (size_t)pos + 1);
+                    float t, u;
+                    if (lss_intersect<false>(o, d, xyz(a0), a0.w, xyz(a1), a1.w, &t, &u, nullptr)) commit(t, u, __ldg(p.sorted_ids + pos), pos);
+                    state = ST_POP;
+                } else {
+                    const float4 a0 = __ldg(p.primA + 3 * (size_t)pos), a1 = __ldg(p.primA + 3 * (size_t)pos + 1),
+                                 a2 = __ldg(p.primA + 3 * (size_t)pos + 2);
+                    const uint32_t prim = __float_as_uint(a0.w);
+                    float t, u;
+                    if (tri_intersect(o, d, xyz(a0), xyz(a1), xyz(a2), prim & 1u, &t, &u)) commit(t, u, prim, pos);
+                    state = ST_POP;
+                }
+            }
+        } else if (PH && pick == ST_MARCH) {
+            // ---------------- Phantom cone iterations ----------------
+            uint32_t n0 = nM, n1;
+            do {
+                if (STATS) { sc_steps[2]++; sc_lanes[2] += __popc(__ballot_sync(FULL, state == ST_MARCH)); }
+                if (state == ST_MARCH) {
+                    if (STATS) st_iters++;
+                    float t = 0.0f, u = 0.0f;
+                    const int r = march_step(ms, p.radius, &t, &u);
+                    if (r != MARCH_CONTINUE) {
+                        // hair_intersection.rint:146-148: report only tHit > 0
+                        if (r == MARCH_HIT && t > 0.0f) commit(t, u, __float_as_uint(__ldg(p.primA + 2 * (size_t)mpos + 1).w), mpos);
+                        state = ST_POP;
+                    }
+                }
+                n1 = __popc(__ballot_sync(FULL, state == ST_MARCH));
+            } while (n1 * 4u >= n0 * 3u && n1 > 0u);
+        } else {
+            // ---------------- retire finished rays, refill ----------------
+            const bool want = state == ST_REFILL;
+            if (STATS) { sc_steps[3]++; sc_lanes[3] += nR; }
+            if (want && have_ray) {
+                have_ray = false;
+                if (best_prim != PRIM_NONE) {
+                    float3 n;
+                    uint32_t seg = best_prim;
+                    if (PH) {
+                        // hair_intersection.rint:74-76 from the committed (t, u)
+                        const float4 a0 = __ldg(p.primA + 2 * (size_t)best_pos), a1 = __ldg(p.primA + 2 * (size_t)best_pos + 1);
+                        const float4 b0 = __ldg(p.primB + 2 * (size_t)best_pos), b1 = __ldg(p.primB + 2 * (size_t)best_pos + 1);
+                        Bezier w;
+                        w.p0 = xyz(a0); w.p1 = xyz(b0); w.p2 = xyz(b1); w.p3 = xyz(a1);
+                        n = fnormalize3(fmadd3(tcur, d, o) - bezier_point(w, best_u));
+                    } else if (TECH == VKHRT_TECHNIQUE_LSS) {
+                        const float4 a0 = __ldg(p.primA + 2 * (size_t)best_pos), a1 = __ldg(p.primA + 2 * (size_t)best_pos + 1);
+                        float t, u;
+                        lss_intersect<true>(o, d, xyz(a0), a0.w, xyz(a1), a1.w, &t, &u, &n);
+                    } else {
+                        const float4 a0 = __ldg(p.primA + 3 * (size_t)best_pos), a1 = __ldg(p.primA + 3 * (size_t)best_pos + 1),
+                                     a2 = __ldg(p.primA + 3 * (size_t)best_pos + 2);
+                        n = tri_normal(d, xyz(a0), xyz(a1), xyz(a2));
+                        seg = best_prim >> 2;
+                    }
+                    if (p.hits) store_hit(p.hits, out_idx, tcur, seg, best_u, n, best_prim, FLAG_HIT);
+                    if (STATS) st_hits++;
+                } else if (p.hits) {
+                    store_hit(p.hits, out_idx, __int_as_float(0x7f800000), VKHRT_MISS_SEGMENT, 0.0f, f3(0, 0, 0), PRIM_NONE, 0u);
+                }
+            }
+            // warp-aggregated fetch of the next slots
+            const unsigned idle = __ballot_sync(FULL, want);
             unsigned long long base = 0;
             if (lane == 0) base = atomicAdd(p.counters, (unsigned long long)__popc(idle));
             base = __shfl_sync(FULL, base, 0);
-            if (base >= p.n_slots) exhausted = true;
-            if (!alive) {
-                unsigned long long slot = base + (unsigned)__popc(idle & ((1u << lane) - 1u));
-                if (slot < p.n_slots) {
+            if (want) {
+                const unsigned long long slot64 = base + (unsigned)__popc(idle & ((1u << lane) - 1u));
+                if (slot64 >= (unsigned long long)p.n_slots) state = ST_DONE;
+                else {
+                    const uint32_t slot = (uint32_t)slot64;
                     bool valid = true;
                     if (WAVEFRONT) {
-                        float4 r0 = __ldg(p.rays + 2 * slot), r1 = __ldg(p.rays + 2 * slot + 1);
+                        const float4 r0 = __ldg(p.rays + 2 * (size_t)slot), r1 = __ldg(p.rays + 2 * (size_t)slot + 1);
                         o = f3(r0.x, r0.y, r0.z); tmin = r0.w; d = f3(r1.x, r1.y, r1.z); tcur = r1.w;
                         out_idx = slot;
                     } else {
-                        PixelRef q = slot_to_pixel(p, slot);
+                        const PixelRef q = slot_to_pixel(p, slot);
                         valid = q.valid;
                         out_idx = q.out;
                         if (valid) {
@@ -150,121 +278,16 @@ __global__ void __launch_bounds__(TR_BLOCK) trace_kernel(const TraceParams p)
                         }
                     }
                     if (valid) {
-                        id = f3(1.0f / d.x, 1.0f / d.y, 1.0f / d.z);
-                        if (TECH == VKHRT_TECHNIQUE_PHANTOM) fr = make_ray_frame(d);
+                        id = f3(safe_rcp(d.x), safe_rcp(d.y), safe_rcp(d.z));
+                        noid = f3(-(o.x * id.x), -(o.y * id.y), -(o.z * id.z));
+                        if (PH) fr = make_ray_frame(d);
                         best_prim = PRIM_NONE; best_pos = 0; best_u = 0.0f;
-                        sp = 0; pending = NO_PENDING;
-                        cur = p.n_prims ? 0u : REF_NONE;
-                        alive = true;
+                        sp = 0;
+                        have_ray = true;
                         if (STATS) st_rays++;
+                        if (p.n_prims) { cur = 0u; state = ST_NODE; }   // else: stays in REFILL and retires as a miss
                     }
                 }
-            }
-            alive_mask = __ballot_sync(FULL, alive);
-        }
-        if (alive_mask == 0u) {
-            if (exhausted) break;
-            continue;
-        }
-
-        // ---------------- traversal phase ----------------
-        for (;;) {
-            bool searching = alive && pending == NO_PENDING && cur != REF_NONE;
-            if (!__any_sync(FULL, searching)) break;
-            bool is_leaf = (cur & VKHRT_BVH_LEAF) != 0u;
-            if (alive && cur != REF_NONE && !(is_leaf && pending != NO_PENDING)) {
-                if (!is_leaf) {
-                    const float4* nd = p.nodes + 4 * (size_t)cur;
-                    const float4 n0 = __ldg(nd), n1 = __ldg(nd + 1), n2 = __ldg(nd + 2), n3 = __ldg(nd + 3);
-                    if (STATS) st_nodes++;
-                    float tn0, tn1;
-                    bool h0 = slab_test(xyz(n0), xyz(n1), o, id, tmin, tcur, &tn0);
-                    bool h1 = slab_test(xyz(n2), xyz(n3), o, id, tmin, tcur, &tn1);
-                    uint32_t c0 = __float_as_uint(n0.w), c1 = __float_as_uint(n1.w);
-                    if (h0 && h1) {
-                        if (tn1 < tn0) { push(c0, tn0); cur = c1; }
-                        else { push(c1, tn1); cur = c0; }
-                    } else if (h0) cur = c0;
-                    else if (h1) cur = c1;
-                    else cur = pop();
-                } else {
-                    const uint32_t pos = cur & 0x7FFFFFFFu;
-                    if (STATS) st_prims++;
-                    if (TECH == VKHRT_TECHNIQUE_PHANTOM) {
-                        // Prhi early-out (hair_intersection.rint:20-33) with the precomputed rmax
-                        const float4 a0 = __ldg(p.primA + 2 * (size_t)pos), a1 = __ldg(p.primA + 2 * (size_t)pos + 1);
-                        if (ray_hits_cylinder(o, d, xyz(a0), xyz(a1), a0.w)) pending = pos;
-                    } else if (TECH == VKHRT_TECHNIQUE_LSS) {
-                        const float4 a0 = __ldg(p.primA + 2 * (size_t)pos), a1 = __ldg(p.primA + 2 * (size_t)pos + 1);
-                        float t, u;
-                        if (lss_intersect<false>(o, d, xyz(a0), a0.w, xyz(a1), a1.w, &t, &u, nullptr) && t >= tmin && t <= tcur) {
-                            uint32_t prim = __ldg(p.sorted_ids + pos);
-                            if (t < tcur || prim < best_prim) { tcur = t; best_prim = prim; best_pos = pos; best_u = u; }
-                        }
-                    } else {
-                        const float4 a0 = __ldg(p.primA + 3 * (size_t)pos), a1 = __ldg(p.primA + 3 * (size_t)pos + 1),
-                                     a2 = __ldg(p.primA + 3 * (size_t)pos + 2);
-                        uint32_t prim = __float_as_uint(a0.w);
-                        float t, u;
-                        if (tri_intersect(o, d, xyz(a0), xyz(a1), xyz(a2), prim & 1u, &t, &u) && t >= tmin &&
-                            (t < tcur || (t == tcur && prim < best_prim))) {
-                            tcur = t; best_prim = prim; best_pos = pos; best_u = u;
-                        }
-                    }
-                    cur = pop();
-                }
-            }
-        }
-
-        // ---------------- intersect phase: postponed Phantom cone march ----------------
-        if (TECH == VKHRT_TECHNIQUE_PHANTOM) {
-            if (alive && pending != NO_PENDING) {
-                const uint32_t pos = pending;
-                pending = NO_PENDING;
-                const float4 a0 = __ldg(p.primA + 2 * (size_t)pos), a1 = __ldg(p.primA + 2 * (size_t)pos + 1);
-                const float4 b0 = __ldg(p.primB + 2 * (size_t)pos), b1 = __ldg(p.primB + 2 * (size_t)pos + 1);
-                Bezier w;
-                w.p0 = xyz(a0); w.p1 = xyz(b0); w.p2 = xyz(b1); w.p3 = xyz(a1);
-                const uint32_t prim = __float_as_uint(a1.w);
-                float u = 0.0f;
-                float t = phantom_march<STATS>(fr, o, w, p.radius, &u, &st_iters);
-                // hair_intersection.rint:146-148 + the [tMin, tCurrent] interval of reportIntersectionEXT;
-                // exact ties go to the smaller primitive id
-                if (t > 0.0f && t >= tmin && (t < tcur || (t == tcur && prim < best_prim))) {
-                    tcur = t; best_prim = prim; best_pos = pos; best_u = u;
-                }
-            }
-            __syncwarp();
-        }
-
-        // ---------------- retire finished rays: closest-hit attributes ----------------
-        if (alive && cur == REF_NONE && pending == NO_PENDING) {
-            alive = false;
-            if (best_prim != PRIM_NONE) {
-                float3 n;
-                uint32_t seg = best_prim;
-                if (TECH == VKHRT_TECHNIQUE_PHANTOM) {
-                    // hair_intersection.rint:74-76 from the committed (t, u)
-                    const float4 a0 = __ldg(p.primA + 2 * (size_t)best_pos), a1 = __ldg(p.primA + 2 * (size_t)best_pos + 1);
-                    const float4 b0 = __ldg(p.primB + 2 * (size_t)best_pos), b1 = __ldg(p.primB + 2 * (size_t)best_pos + 1);
-                    Bezier w;
-                    w.p0 = xyz(a0); w.p1 = xyz(b0); w.p2 = xyz(b1); w.p3 = xyz(a1);
-                    float3 hp = o + tcur * d;
-                    n = normalize3(hp - bezier_point(w, best_u));
-                } else if (TECH == VKHRT_TECHNIQUE_LSS) {
-                    const float4 a0 = __ldg(p.primA + 2 * (size_t)best_pos), a1 = __ldg(p.primA + 2 * (size_t)best_pos + 1);
-                    float t, u;
-                    lss_intersect<true>(o, d, xyz(a0), a0.w, xyz(a1), a1.w, &t, &u, &n);
-                } else {
-                    const float4 a0 = __ldg(p.primA + 3 * (size_t)best_pos), a1 = __ldg(p.primA + 3 * (size_t)best_pos + 1),
-                                 a2 = __ldg(p.primA + 3 * (size_t)best_pos + 2);
-                    n = tri_normal(d, xyz(a0), xyz(a1), xyz(a2));
-                    seg = best_prim >> 2;
-                }
-                if (p.hits) store_hit(p.hits, out_idx, tcur, seg, best_u, n, best_prim, FLAG_HIT);
-                if (STATS) st_hits++;
-            } else if (p.hits) {
-                store_hit(p.hits, out_idx, __int_as_float(0x7f800000), VKHRT_MISS_SEGMENT, 0.0f, f3(0, 0, 0), PRIM_NONE, 0u);
             }
         }
     }
@@ -280,6 +303,7 @@ __global__ void __launch_bounds__(TR_BLOCK) trace_kernel(const TraceParams p)
             atomicAdd(p.counters + 1, (unsigned long long)st_nodes); atomicAdd(p.counters + 2, (unsigned long long)st_prims);
             atomicAdd(p.counters + 3, (unsigned long long)st_hits); atomicAdd(p.counters + 4, (unsigned long long)st_iters);
             atomicAdd(p.counters + 5, (unsigned long long)st_rays);
+            for (int k = 0; k < 4; ++k) { atomicAdd(p.counters + 8 + k, (unsigned long long)sc_steps[k]); atomicAdd(p.counters + 12 + k, (unsigned long long)sc_lanes[k]); }
         }
     }
 }
@@ -289,16 +313,16 @@ __global__ void __launch_bounds__(TR_BLOCK) trace_kernel(const TraceParams p)
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) raygen_kernel(const TraceParams p, float4* __restrict__ rays)
 {
-    unsigned long long slot = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (slot >= p.n_slots) return;
-    PixelRef q = slot_to_pixel(p, slot);
+    unsigned long long slot64 = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (slot64 >= p.n_slots) return;
+    PixelRef q = slot_to_pixel(p, (uint32_t)slot64);
     float3 o = f3(0, 0, 0), d = f3(0, 0, 1);
     float tmin = p.tmin, tmax = p.tmax;
     if (!q.valid && !p.compact) return;   // row-major layout has no slot for padding pixels
     if (q.valid) primary_ray(p.cam, p.W, p.H, q.px, q.py, p.sx, p.sy, &o, &d);
     else tmax = -1.0f;    // empty interval: padding pixels never hit
-    rays[2 * q.out] = make_float4(o.x, o.y, o.z, tmin);
-    rays[2 * q.out + 1] = make_float4(d.x, d.y, d.z, tmax);
+    rays[2 * (size_t)q.out] = make_float4(o.x, o.y, o.z, tmin);
+    rays[2 * (size_t)q.out + 1] = make_float4(d.x, d.y, d.z, tmax);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -368,6 +392,7 @@ static bool resolve(const VkhrtFrameDesc& f, Resolved& r)
     r.n_local_tiles = (r.n_tiles + r.tile_stride - 1) / r.tile_stride;
     r.n_slots = (unsigned long long)r.n_local_tiles * r.T * r.T;
     r.n_out = r.compact ? r.n_slots : (unsigned long long)r.W * r.H;
+    if (r.n_slots >= 0xFFFFFFFFull || (unsigned long long)r.W * r.H >= 0xFFFFFFFFull) return false;   // 32-bit slot / pixel indices
     bool def = f.t_min == 0.0f && f.t_max == 0.0f;
     r.tmin = def ? VKHRT_DEFAULT_T_MIN : f.t_min;
     r.tmax = def ? VKHRT_DEFAULT_T_MAX : f.t_max;
@@ -396,12 +421,24 @@ static void fill_params(const DeviceScene& sc, const VkhrtFrameDesc& f, const Re
     memcpy(p.cam.vi, f.view_inverse, sizeof(p.cam.vi)); memcpy(p.cam.pi, f.proj_inverse, sizeof(p.cam.pi));
     p.W = r.W; p.H = r.H; p.sx = 0.5f; p.sy = 0.5f; p.tmin = r.tmin; p.tmax = r.tmax;
     p.T = r.T; p.tiles_x = r.tiles_x; p.n_tiles = r.n_tiles; p.tile_first = r.tile_first; p.tile_stride = r.tile_stride; p.compact = r.compact ? 1u : 0u;
-    p.rays = nullptr; p.n_slots = r.n_slots; p.hits = nullptr; p.counters = sc.d_counters; p.refill_threshold = 0;
+    p.rays = nullptr; p.n_slots = (uint32_t)r.n_slots; p.hits = nullptr; p.counters = sc.d_counters;
 }
 
-static int g_refill_threshold = -1;
-static int g_blocks_per_sm = -1;
+// scheduler tunables (defaults from the sweep in profiles/; overridable for experiments)
+static int g_refill_threshold = -1, g_blocks_per_sm = -1, g_w_node = -1, g_w_leaf = -1, g_w_march = -1;
 static int env_int(const char* name, int def) { const char* v = getenv(name); return v ? atoi(v) : def; }
+static void tunables(TraceParams& p)
+{
+    if (g_refill_threshold < 0) {
+        g_refill_threshold = env_int("VKHRT_REFILL_THRESHOLD", 8);
+        g_blocks_per_sm = env_int("VKHRT_BLOCKS_PER_SM", 0);
+        g_w_node = env_int("VKHRT_W_NODE", 16);
+        g_w_leaf = env_int("VKHRT_W_LEAF", 32);
+        g_w_march = env_int("VKHRT_W_MARCH", 32);
+    }
+    p.refill_threshold = (uint32_t)std::max(1, g_refill_threshold);
+    p.w_node = (uint32_t)g_w_node; p.w_leaf = (uint32_t)g_w_leaf; p.w_march = (uint32_t)g_w_march;
+}
 
 template <int TECH, bool STATS, bool WAVEFRONT>
 static int launch_trace_t(const DeviceScene& sc, TraceParams& p, cudaStream_t st)
@@ -409,11 +446,9 @@ static int launch_trace_t(const DeviceScene& sc, TraceParams& p, cudaStream_t st
     int per_sm = 0;
     VK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, trace_kernel<TECH, STATS, WAVEFRONT>, TR_BLOCK, 0));
     if (per_sm < 1) per_sm = 1;
-    if (g_blocks_per_sm < 0) g_blocks_per_sm = env_int("VKHRT_BLOCKS_PER_SM", 0);
+    tunables(p);
     if (g_blocks_per_sm > 0) per_sm = std::min(per_sm, g_blocks_per_sm);
-    if (g_refill_threshold < 0) g_refill_threshold = env_int("VKHRT_REFILL_THRESHOLD", 0);
-    p.refill_threshold = (uint32_t)g_refill_threshold;
-    unsigned long long want = (p.n_slots + TR_BLOCK - 1) / TR_BLOCK;
+    unsigned long long want = ((unsigned long long)p.n_slots + TR_BLOCK - 1) / TR_BLOCK;
     unsigned grid = (unsigned)std::min<unsigned long long>((unsigned long long)sc.sm_count * per_sm, std::max<unsigned long long>(want, 1ull));
     trace_kernel<TECH, STATS, WAVEFRONT><<<grid, TR_BLOCK, 0, st>>>(p);
     count_launch();
@@ -474,7 +509,7 @@ int render_frame(DeviceScene& sc, const VkhrtFrameDesc& f, VkhrtHit* hits_out, u
     const float3 miss = make_float3(f.miss_rgb[0], f.miss_rgb[1], f.miss_rgb[2]);
     cudaEvent_t* ev = sc.ev;
     VK_CUDA(cudaEventRecord(ev[6], st));
-    if (stats) VK_CUDA(cudaMemsetAsync(sc.d_counters, 0, 8 * sizeof(unsigned long long), st));
+    if (stats) VK_CUDA(cudaMemsetAsync(sc.d_counters, 0, 16 * sizeof(unsigned long long), st));
     const uint32_t n_samples = (want_rgba || stats) ? r.spp : 1;    // hits only => sample 0 is all that is observable
     for (uint32_t s = 0; s < n_samples; ++s) {
         sample_offset(s, &p.sx, &p.sy);
@@ -497,10 +532,11 @@ int render_frame(DeviceScene& sc, const VkhrtFrameDesc& f, VkhrtHit* hits_out, u
     }
     VK_CUDA(cudaEventRecord(ev[11], st));
     if (stats) {
-        unsigned long long c[8];
+        unsigned long long c[16];
         VK_CUDA(cudaMemcpyAsync(c, sc.d_counters, sizeof(c), cudaMemcpyDeviceToHost, st));
         VK_CUDA(cudaStreamSynchronize(st));
         stats->nodes_visited = c[1]; stats->prims_tested = c[2]; stats->hits = c[3]; stats->phantom_iterations = c[4]; stats->rays = c[5];
+        for (int k = 0; k < 4; ++k) { stats->sched_steps[k] = c[8 + k]; stats->sched_lanes[k] = c[12 + k]; }
     }
     if (host_out) VK_CUDA(cudaStreamSynchronize(st));
     VK_CUDA(cudaGetLastError());
@@ -515,12 +551,18 @@ int trace_ray_buffer(DeviceScene& sc, const float* rays_dev, uint64_t n, VkhrtHi
     memset(&p, 0, sizeof(p));
     p.nodes = sc.d_nodes; p.primA = sc.d_primA; p.primB = sc.d_primB; p.sorted_ids = sc.d_sorted_ids;
     p.n_prims = sc.n_prims; p.radius = sc.radius;
-    p.rays = reinterpret_cast<const float4*>(rays_dev); p.n_slots = n; p.hits = hits_dev; p.counters = sc.d_counters;
+    p.counters = sc.d_counters;
     p.T = 8; p.tiles_x = 1; p.tile_stride = 1;
-    if (n == 0) return VKHRT_OK;
-    VK_CUDA(cudaMemsetAsync(sc.d_counters, 0, sizeof(unsigned long long), st));
-    int rc = launch_trace<false, true>(sc, p, st);
-    if (rc) return rc;
+    // 32-bit slot indices inside the kernel: long ray buffers go in chunks of 2^30 rays
+    const uint64_t chunk = 1ull << 30;
+    for (uint64_t first = 0; first < n; first += chunk) {
+        p.rays = reinterpret_cast<const float4*>(rays_dev) + 2 * first;
+        p.hits = hits_dev + first;
+        p.n_slots = (uint32_t)std::min<uint64_t>(chunk, n - first);
+        VK_CUDA(cudaMemsetAsync(sc.d_counters, 0, sizeof(unsigned long long), st));
+        int rc = launch_trace<false, true>(sc, p, st);
+        if (rc) return rc;
+    }
     if (!stream) VK_CUDA(cudaStreamSynchronize(st));
     VK_CUDA(cudaGetLastError());
     return VKHRT_OK;
