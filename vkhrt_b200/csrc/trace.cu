@@ -15,6 +15,7 @@
 namespace vkhrt {
 
 constexpr int TR_BLOCK = 128;          // 4 warps per CTA
+constexpr int TR_MIN_BLOCKS = 6;       // CTAs per SM the register allocation is held to
 constexpr int TR_STACK = 24;           // per-lane shared-memory short stack entries (8 B each)
 constexpr int TR_SPILL = 80;           // per-lane local-memory overflow (Karras depth <= 64 + 32)
 constexpr uint32_t REF_NONE = 0x7FFFFFFFu;
@@ -88,8 +89,8 @@ VK_DEV void store_hit(VkhrtHit* hits, size_t i, float t, uint32_t seg, float u, 
 // ------------------------------------------------------------------------------------------------
 enum : uint32_t { ST_NODE = 0, ST_POP = 1, ST_LEAF = 2, ST_MARCH = 3, ST_REFILL = 4, ST_DONE = 5 };   // NODE|POP are scheduled together
 
-template <int TECH, bool STATS, bool WAVEFRONT>
-__global__ void __launch_bounds__(TR_BLOCK) trace_kernel(const TraceParams p)
+template <int TECH, bool STATS, bool WAVEFRONT, int MINB>
+__global__ void __launch_bounds__(TR_BLOCK, MINB) trace_kernel(const TraceParams p)
 {
     __shared__ uint2 s_stack[TR_STACK][TR_BLOCK];
     uint2 spill[TR_SPILL];
@@ -102,8 +103,6 @@ __global__ void __launch_bounds__(TR_BLOCK) trace_kernel(const TraceParams p)
     float3 o = f3(0, 0, 0), d = f3(0, 0, 1), id = f3(0, 0, 0), noid = f3(0, 0, 0);
     float tmin = 0.0f, tcur = 0.0f, best_u = 0.0f;
     uint32_t best_prim = PRIM_NONE, best_pos = 0;
-    RayFrame fr;
-    fr.e1 = fr.e2 = fr.e3 = f3(0, 0, 0);
     MarchState ms;
     ms.c.p0 = ms.c.p1 = ms.c.p2 = ms.c.p3 = f3(0, 0, 0);
     ms.t = ms.told = ms.dt1 = ms.dt2 = ms.t_start = 0.0f; ms.it = 0u;
@@ -183,7 +182,9 @@ __global__ void __launch_bounds__(TR_BLOCK) trace_kernel(const TraceParams p)
                         const float4 b0 = __ldg(p.primB + 2 * (size_t)pos), b1 = __ldg(p.primB + 2 * (size_t)pos + 1);
                         Bezier w;
                         w.p0 = xyz(a0); w.p1 = xyz(b0); w.p2 = xyz(b1); w.p3 = xyz(a1);
-                        march_begin(ms, fr, o, w);
+                        // the ray-centric frame depends on the ray only; rebuilding it per candidate that survives the
+                        // cylinder test (~2 per ray) is cheaper than keeping 9 registers alive through the node loop
+                        march_begin(ms, make_ray_frame(d), o, w);
                         mpos = pos;
                         // conservative filter (hair_math.cuh): skip marches that cannot report a hit
                         state = half_chords_near_ray(ms.c, p.radius, b0.w) ? ST_MARCH : ST_POP;
@@ -280,7 +281,6 @@ __global__ void __launch_bounds__(TR_BLOCK) trace_kernel(const TraceParams p)
                     if (valid) {
                         id = f3(safe_rcp(d.x), safe_rcp(d.y), safe_rcp(d.z));
                         noid = f3(-(o.x * id.x), -(o.y * id.y), -(o.z * id.z));
-                        if (PH) fr = make_ray_frame(d);
                         best_prim = PRIM_NONE; best_pos = 0; best_u = 0.0f;
                         sp = 0;
                         have_ray = true;
@@ -425,12 +425,13 @@ static void fill_params(const DeviceScene& sc, const VkhrtFrameDesc& f, const Re
 }
 
 // scheduler tunables (defaults from the sweep in profiles/; overridable for experiments)
-static int g_refill_threshold = -1, g_blocks_per_sm = -1, g_w_node = -1, g_w_leaf = -1, g_w_march = -1;
+static int g_refill_threshold = -1, g_blocks_per_sm = -1, g_w_node = -1, g_w_leaf = -1, g_w_march = -1, g_min_blocks = -1;
 static int env_int(const char* name, int def) { const char* v = getenv(name); return v ? atoi(v) : def; }
 static void tunables(TraceParams& p)
 {
     if (g_refill_threshold < 0) {
-        g_refill_threshold = env_int("VKHRT_REFILL_THRESHOLD", 8);
+        g_refill_threshold = env_int("VKHRT_REFILL_THRESHOLD", 16);
+        g_min_blocks = env_int("VKHRT_MIN_BLOCKS", TR_MIN_BLOCKS);
         g_blocks_per_sm = env_int("VKHRT_BLOCKS_PER_SM", 0);
         g_w_node = env_int("VKHRT_W_NODE", 16);
         g_w_leaf = env_int("VKHRT_W_LEAF", 32);
@@ -440,27 +441,31 @@ static void tunables(TraceParams& p)
     p.w_node = (uint32_t)g_w_node; p.w_leaf = (uint32_t)g_w_leaf; p.w_march = (uint32_t)g_w_march;
 }
 
-template <int TECH, bool STATS, bool WAVEFRONT>
+template <int TECH, bool STATS, bool WAVEFRONT, int MINB>
 static int launch_trace_t(const DeviceScene& sc, TraceParams& p, cudaStream_t st)
 {
     int per_sm = 0;
-    VK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, trace_kernel<TECH, STATS, WAVEFRONT>, TR_BLOCK, 0));
+    VK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, trace_kernel<TECH, STATS, WAVEFRONT, MINB>, TR_BLOCK, 0));
     if (per_sm < 1) per_sm = 1;
     tunables(p);
     if (g_blocks_per_sm > 0) per_sm = std::min(per_sm, g_blocks_per_sm);
     unsigned long long want = ((unsigned long long)p.n_slots + TR_BLOCK - 1) / TR_BLOCK;
     unsigned grid = (unsigned)std::min<unsigned long long>((unsigned long long)sc.sm_count * per_sm, std::max<unsigned long long>(want, 1ull));
-    trace_kernel<TECH, STATS, WAVEFRONT><<<grid, TR_BLOCK, 0, st>>>(p);
+    trace_kernel<TECH, STATS, WAVEFRONT, MINB><<<grid, TR_BLOCK, 0, st>>>(p);
     count_launch();
     return VKHRT_OK;
 }
 template <bool STATS, bool WAVEFRONT>
 static int launch_trace(const DeviceScene& sc, TraceParams& p, cudaStream_t st)
 {
+    tunables(p);
     switch (sc.technique) {
-    case VKHRT_TECHNIQUE_PHANTOM: return launch_trace_t<VKHRT_TECHNIQUE_PHANTOM, STATS, WAVEFRONT>(sc, p, st);
-    case VKHRT_TECHNIQUE_LSS: return launch_trace_t<VKHRT_TECHNIQUE_LSS, STATS, WAVEFRONT>(sc, p, st);
-    default: return launch_trace_t<VKHRT_TECHNIQUE_DOTS, STATS, WAVEFRONT>(sc, p, st);
+    case VKHRT_TECHNIQUE_PHANTOM:
+        if (!STATS && !WAVEFRONT && g_min_blocks == 7) return launch_trace_t<VKHRT_TECHNIQUE_PHANTOM, false, false, 7>(sc, p, st);
+        if (!STATS && !WAVEFRONT && g_min_blocks == 8) return launch_trace_t<VKHRT_TECHNIQUE_PHANTOM, false, false, 8>(sc, p, st);
+        return launch_trace_t<VKHRT_TECHNIQUE_PHANTOM, STATS, WAVEFRONT, TR_MIN_BLOCKS>(sc, p, st);
+    case VKHRT_TECHNIQUE_LSS: return launch_trace_t<VKHRT_TECHNIQUE_LSS, STATS, WAVEFRONT, TR_MIN_BLOCKS>(sc, p, st);
+    default: return launch_trace_t<VKHRT_TECHNIQUE_DOTS, STATS, WAVEFRONT, TR_MIN_BLOCKS>(sc, p, st);
     }
 }
 
