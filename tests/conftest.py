@@ -19,7 +19,8 @@ def _built():
     from oracle import oracle as O
     O.build()
     lib = os.path.join(ROOT, "vkhrt_b200", "_lib", "libvkhrt_b200.so")
-    if not os.path.exists(lib):
+    exe = os.path.join(ROOT, "vkhrt_b200", "_lib", "vkhrt_headless")
+    if not os.path.exists(lib) or not os.path.exists(exe):
         subprocess.check_call(["make", "-s", "-C", os.path.join(ROOT, "vkhrt_b200", "csrc")])
     yield
 

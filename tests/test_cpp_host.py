@@ -1,0 +1,90 @@
+"""The C++ host layer (vkhrt_b200/host/): header-only mirror of ModelLoader / Model / FlyCamera / Renderer over the
+C ABI, and the headless executable that stands in for the reference's `main`."""
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+EXE = os.path.join(ROOT, "vkhrt_b200", "_lib", "vkhrt_headless")
+
+LOADER_PROBE = r"""
+#include "vkhrt_host.hpp"
+#include <cstdio>
+using namespace vkhrt_host;
+int main(int argc, char** argv) {
+    ModelCreation m;
+    if (!ModelLoader::LoadModel(argv[1], m)) { std::puts("FAIL"); return 1; }
+    std::printf("%zu %zu\n", m.vertexBuffer.size(), m.indexBuffer.size() / 2);
+    for (size_t i = 0; i < m.indexBuffer.size(); ++i) std::printf("%u ", m.indexBuffer[i]);
+    std::printf("\n%g %g %g\n", m.vertexBuffer.back().x, m.vertexBuffer.back().y, m.vertexBuffer.back().z);
+    ModelCreation c = ProcessHairCurves(m), d = ProcessHairDOTS(m), l = ProcessHairLSS(m);
+    std::printf("%d %d %d\n", (int)c.technique, (int)d.technique, (int)l.technique);
+    (void)argc; return 0;
+}
+"""
+
+
+@pytest.fixture(scope="module")
+def probe(tmp_path_factory, V):
+    d = tmp_path_factory.mktemp("probe")
+    src = d / "probe.cpp"
+    src.write_text(LOADER_PROBE)
+    exe = d / "probe"
+    lib_dir = os.path.dirname(V.library_path())
+    subprocess.check_call(["/usr/bin/g++", "-std=c++17", "-Wall", "-Wextra", "-Werror", "-I", os.path.join(ROOT, "vkhrt_b200", "host"), str(src), "-o", str(exe),
+                           "-L", lib_dir, "-lvkhrt_b200", f"-Wl,-rpath,{lib_dir}"])
+    return str(exe)
+
+
+def test_obj_polyline_loader_and_process_functions(probe, tmp_path):
+    obj = tmp_path / "strands.obj"
+    obj.write_text("# two strands\nv 0 0 0\nv 1 0 0\nv 2 1 0\nv 5 5 5\nv 6 5 5\nl 1 2 3\nl -2 -1\n")
+    out = subprocess.run([probe, str(obj)], capture_output=True, text=True).stdout.split("\n")
+    assert out[0] == "5 3"
+    assert out[1].split() == ["0", "1", "1", "2", "3", "4"]         # joints repeat the vertex index (GenerateCurves connectivity)
+    assert out[2] == "6 5 5"
+    assert out[3] == "0 2 1"                                        # ProcessHairCurves / DOTS / LSS select the technique
+    assert subprocess.run([probe, str(tmp_path / "missing.obj")], capture_output=True, text=True).stdout.strip() == "FAIL"
+    bad = tmp_path / "bad.obj"
+    bad.write_text("v 0 0 0\nl 1 7\n")
+    assert subprocess.run([probe, str(bad)], capture_output=True, text=True).stdout.strip() == "FAIL"
+
+
+def test_synthetic_uri_matches_the_abi_generator(probe, V):
+    out = subprocess.run([probe, "synthetic:curly:50:4"], capture_output=True, text=True).stdout.split("\n")
+    assert out[0] == "250 200"
+    pos, idx = V.generate_groom(50, 4, V.GROOM_CURLY)
+    assert [int(x) for x in out[1].split()] == idx.reshape(-1).tolist()
+    assert np.allclose([float(x) for x in out[2].split()], pos[-1], rtol=1e-5)
+
+
+def test_headless_cli_without_gpu(V):
+    assert os.path.exists(EXE)
+    r = subprocess.run([EXE, "--help"], capture_output=True, text=True)
+    assert r.returncode == 0 and "usage" in r.stdout
+    if V.device_count() == 0:
+        r = subprocess.run([EXE, "--model", "synthetic:curly:10:4"], capture_output=True, text=True)
+        assert r.returncode == 3 and "no CPU path" in r.stderr       # loud failure, no fallback
+    r = subprocess.run([EXE, "--model", "/nonexistent.obj"], capture_output=True, text=True)
+    assert r.returncode == 1 and "[MODEL LOADING]" in r.stderr
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("tech,name", [(0, "phantom"), (1, "lss"), (2, "dots")])
+def test_headless_matches_python_binding_and_oracle(V, O, tmp_path, tech, name):
+    W, H = 192, 108
+    hits_path, ppm = tmp_path / "hits.bin", tmp_path / "out.ppm"
+    r = subprocess.run([EXE, "--model", "synthetic:curly:3000:16", "--technique", name, "--size", f"{W}x{H}", "--frames", "2",
+                        "--hits", str(hits_path), "--ppm", str(ppm)], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    hits = np.fromfile(hits_path, dtype=V.HIT_DTYPE)
+    pos, idx = V.generate_groom(3000, 16, V.GROOM_CURLY)
+    vi, pi = V.camera_matrices(aspect=float(np.float32(W) / np.float32(H)))
+    ho, io, _ = O.OracleScene(pos, idx, technique=tech).render(O.make_frame(vi, pi, W, H))
+    assert hits.tobytes() == ho.tobytes()
+    raw = open(ppm, "rb").read()
+    header = f"P6\n{W} {H}\n255\n".encode()
+    assert raw.startswith(header)
+    assert np.array_equal(np.frombuffer(raw[len(header):], np.uint8).reshape(-1, 3), io[:, :3])

@@ -1,0 +1,85 @@
+// vkhrt_headless — the reference's `main` (source/main.cpp:3-7 -> Application -> Renderer::Render loop,
+// source/application.cpp:101-129) without the window: load or synthesise a groom, build, render N frames,
+// write the image and the hit buffer, print per-stage device timings.
+//
+//   vkhrt_headless --model synthetic:curly:100000:32 --technique phantom --size 1920x1080
+//                  [--spp 1] [--debug-primid] [--frames 10] [--ppm out.ppm] [--hits out.bin] [--device 0]
+//
+// Host code only: every number comes from libvkhrt_b200.so; without a CUDA device it exits with the ABI's error.
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+
+#include "vkhrt_host.hpp"
+
+using namespace vkhrt_host;
+
+static void usage()
+{
+    std::puts("usage: vkhrt_headless --model <file.obj | synthetic:<straight|curly>:<strands>:<segments>[:seed]>\n"
+              "                      [--technique phantom|lss|dots] [--size WxH] [--spp N] [--debug-primid]\n"
+              "                      [--frames N] [--ppm out.ppm] [--hits out.bin] [--device D]");
+}
+
+int main(int argc, char** argv)
+{
+    std::string model = "synthetic:curly:10000:16", ppm, hits_path, technique = "lss";
+    RendererInitInfo info;
+    int frames = 1, device = 0;
+    for (int i = 1; i < argc; ++i) {
+        const std::string a = argv[i];
+        auto next = [&]() -> const char* { if (i + 1 >= argc) { usage(); std::exit(2); } return argv[++i]; };
+        if (a == "--help" || a == "-h") { usage(); return 0; }
+        else if (a == "--model") model = next();
+        else if (a == "--technique") technique = next();
+        else if (a == "--size") { if (std::sscanf(next(), "%ux%u", &info.width, &info.height) != 2) { usage(); return 2; } }
+        else if (a == "--spp") info.spp = (uint32_t)std::atoi(next());
+        else if (a == "--debug-primid") info.shadeMode = VKHRT_SHADE_DEBUG_PRIMID;
+        else if (a == "--frames") frames = std::atoi(next());
+        else if (a == "--ppm") ppm = next();
+        else if (a == "--hits") hits_path = next();
+        else if (a == "--device") device = std::atoi(next());
+        else { std::fprintf(stderr, "unknown argument %s\n", a.c_str()); usage(); return 2; }
+    }
+    const VkhrtTechnique tech = technique == "phantom" ? VKHRT_TECHNIQUE_PHANTOM : (technique == "dots" ? VKHRT_TECHNIQUE_DOTS : VKHRT_TECHNIQUE_LSS);
+    try {
+        ModelLoader loader(device);
+        auto t0 = std::chrono::steady_clock::now();
+        std::shared_ptr<Model> m = loader.LoadFromFile(model, tech);
+        if (!m) return 1;
+        const VkhrtTiming bt = m->Timing();
+        std::printf("[MODEL LOADING] %s: %u primitives (%s), load+build %.1f ms wall, device build %.2f ms (sort %.2f, hierarchy %.2f, refit %.2f)\n",
+                    model.c_str(), m->PrimitiveCount(), technique.c_str(),
+                    std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count(), bt.build_total_ms, bt.sort_ms,
+                    bt.hierarchy_ms, bt.refit_ms);
+        FlyCameraCreation cc;
+        cc.aspectRatio = (float)info.width / (float)info.height;
+        auto camera = std::make_shared<FlyCamera>(cc);
+        Renderer renderer(info, camera);
+        renderer.AddModel(m);
+        for (int f = 0; f < frames; ++f) {
+            auto f0 = std::chrono::steady_clock::now();
+            renderer.Render();
+            const VkhrtTiming t = m->Timing();
+            const double wall = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - f0).count();
+            std::printf("frame %d: %.3f ms wall, trace %.3f ms, shade %.3f ms, d2h %.3f ms  (%.1f Mrays/s device)\n", f, wall, t.trace_ms, t.shade_ms,
+                        t.d2h_ms, (double)info.width * info.height / (t.trace_ms * 1e3));
+        }
+        size_t n_hit = 0;
+        for (const VkhrtHit& h : renderer.GetHits()) n_hit += h.flags & 1u;
+        std::printf("hits: %zu of %zu rays\n", n_hit, renderer.GetHits().size());
+        if (!ppm.empty() && !renderer.WritePPM(ppm)) { std::fprintf(stderr, "[FILE] cannot write %s\n", ppm.c_str()); return 1; }
+        if (!hits_path.empty()) {
+            std::FILE* fp = std::fopen(hits_path.c_str(), "wb");
+            if (!fp) { std::fprintf(stderr, "[FILE] cannot write %s\n", hits_path.c_str()); return 1; }
+            std::fwrite(renderer.GetHits().data(), sizeof(VkhrtHit), renderer.GetHits().size(), fp);
+            std::fclose(fp);
+        }
+    } catch (const VkhrtError& e) {
+        std::fprintf(stderr, "[VKHRT] %s\n", e.what());
+        return 3;
+    }
+    return 0;
+}
