@@ -166,7 +166,7 @@ def run_reference(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
@@ -205,31 +205,19 @@ def main():
     build_timing = scene.timing()
 
     # a non-default stream: the ABI treats a NULL stream handle as "use the scene's own stream"
+    from vkhrt_b200.multi import ShardedRenderer
     stream = torch.cuda.Stream(device=dev)
     torch.cuda.set_stream(stream)
     T = 64
-    fd = V.make_frame(vi, pi, W, H, spp=spp, tile_size=T, tile_first=rank, tile_stride=world,
-                      output_memory=V.MEM_DEVICE, stream=stream.cuda_stream)
-    n_local = V.frame_local_pixels(fd)
-    d_hits = torch.empty((n_local, 32), dtype=torch.uint8, device=dev)
-    d_rgba = torch.empty((n_local, 4), dtype=torch.uint8, device=dev) if want_rgba else None
-    if world > 1:
-        g_hits = torch.empty((world * n_local, 32), dtype=torch.uint8, device=dev)
-        o_hits = torch.empty((W * H, 32), dtype=torch.uint8, device=dev)
-        f_full = V.make_frame(vi, pi, W, H, tile_size=T)
-        if want_rgba:
-            g_rgba = torch.empty((world * n_local, 4), dtype=torch.uint8, device=dev)
-            o_rgba = torch.empty((W * H, 4), dtype=torch.uint8, device=dev)
+    sharded = ShardedRenderer(scene, W, H, tile=T, spp=spp, want_rgba=want_rgba, device=dev)
+    fd = sharded.make_frame(vi, pi, stream.cuda_stream)
+    n_local = sharded.layout.shard_pixels
+    d_hits = sharded.d_hits
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)   # > 126 MB L2
 
     def step_device():
-        scene.render_into(fd, d_hits.data_ptr(), d_rgba.data_ptr() if want_rgba else None)
-        if world > 1:
-            dist.all_gather_into_tensor(g_hits, d_hits)
-            V.untile(f_full, world, g_hits.data_ptr(), o_hits.data_ptr(), 32, stream.cuda_stream)
-            if want_rgba:
-                dist.all_gather_into_tensor(g_rgba, d_rgba)
-                V.untile(f_full, world, g_rgba.data_ptr(), o_rgba.data_ptr(), 4, stream.cuda_stream)
+        # trace this rank's tiles; N > 1: NCCL all_gather of the compact shards + untile (vkhrt_b200/multi.py)
+        sharded.render(fd, stream.cuda_stream)
 
     def barrier():
         if world > 1:

@@ -286,3 +286,24 @@ def test_full_size_config2_properties(V, O):
         orc = O.OracleScene(pos, idx, technique=0)
         ho, _, _ = orc.render(O.make_frame(vi, pi, W, H), rgba=False, pixel_subset=sub)
         assert_bit_identical(h1[sub.astype(np.int64)], ho)
+
+
+@pytest.mark.parametrize("tech", TECHS)
+def test_pinned_host_buffers_zero_copy_path(V, small_groom, tech):
+    """vkhrt_render with a PINNED host hit buffer: the kernel stores the records straight into host memory
+    (no device->host copy).  Must equal the pageable-buffer path bit for bit, with and without an image."""
+    import torch
+    pos, idx = small_groom
+    W, H = 200, 120
+    vi, pi = default_camera(V, W, H)
+    with V.Scene(pos, idx, technique=tech) as sc:
+        sc.build()
+        href, iref, _ = sc.render(V.make_frame(vi, pi, W, H, spp=2))
+        for want_rgba in (False, True):
+            hh = torch.zeros((W * H, 32), dtype=torch.uint8).pin_memory()
+            hi = torch.zeros((W * H, 4), dtype=torch.uint8).pin_memory()
+            f = V.make_frame(vi, pi, W, H, spp=2, output_memory=V.MEM_HOST)
+            sc.render_into(f, hh.data_ptr(), hi.data_ptr() if want_rgba else None)      # blocks until complete
+            assert np.array_equal(hh.numpy().reshape(-1), href.view(np.uint8))
+            if want_rgba:
+                assert np.array_equal(hi.numpy(), iref)

@@ -36,8 +36,9 @@ struct TraceParams {
     uint32_t T, tiles_x, n_tiles, tile_first, tile_stride, compact;
     // wavefront mode
     const float4* rays;
-    uint32_t n_slots;
+    uint32_t slot_begin, n_slots;   // this launch traces slots [slot_begin, n_slots)
     VkhrtHit* hits;
+    VkhrtHit* hits_mirror;          // optional second destination (pinned host memory), same indexing
     unsigned long long* counters;   // [0] next slot, [1] nodes, [2] prims, [3] hits, [4] iterations, [5] rays, [8..11] steps, [12..15] lanes
     uint32_t refill_threshold;      // lanes waiting for a new ray that trigger a refill step
     uint32_t w_node, w_leaf, w_march;   // scheduler weights (fixed point, 16 = 1.0)
@@ -62,11 +63,12 @@ VK_DEV PixelRef slot_to_pixel(const TraceParams& p, uint32_t slot)
     return q;
 }
 
-VK_DEV void store_hit(VkhrtHit* hits, size_t i, float t, uint32_t seg, float u, float3 n, uint32_t prim, uint32_t flags)
+VK_DEV void store_hit(const TraceParams& p, size_t i, float t, uint32_t seg, float u, float3 n, uint32_t prim, uint32_t flags)
 {
-    float4* h = reinterpret_cast<float4*>(hits + i);
-    h[0] = make_float4(t, __uint_as_float(seg), u, n.x);
-    h[1] = make_float4(n.y, n.z, __uint_as_float(prim), __uint_as_float(flags));
+    const float4 a = make_float4(t, __uint_as_float(seg), u, n.x);
+    const float4 b = make_float4(n.y, n.z, __uint_as_float(prim), __uint_as_float(flags));
+    if (p.hits) { float4* h = reinterpret_cast<float4*>(p.hits + i); h[0] = a; h[1] = b; }
+    if (p.hits_mirror) { float4* h = reinterpret_cast<float4*>(p.hits_mirror + i); h[0] = a; h[1] = b; }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -246,10 +248,10 @@ __global__ void __launch_bounds__(TR_BLOCK, MINB) trace_kernel(const TraceParams
                         n = tri_normal(d, xyz(a0), xyz(a1), xyz(a2));
                         seg = best_prim >> 2;
                     }
-                    if (p.hits) store_hit(p.hits, out_idx, tcur, seg, best_u, n, best_prim, FLAG_HIT);
+                    store_hit(p, out_idx, tcur, seg, best_u, n, best_prim, FLAG_HIT);
                     if (STATS) st_hits++;
-                } else if (p.hits) {
-                    store_hit(p.hits, out_idx, __int_as_float(0x7f800000), VKHRT_MISS_SEGMENT, 0.0f, f3(0, 0, 0), PRIM_NONE, 0u);
+                } else {
+                    store_hit(p, out_idx, __int_as_float(0x7f800000), VKHRT_MISS_SEGMENT, 0.0f, f3(0, 0, 0), PRIM_NONE, 0u);
                 }
             }
             // warp-aggregated fetch of the next slots
@@ -258,7 +260,7 @@ __global__ void __launch_bounds__(TR_BLOCK, MINB) trace_kernel(const TraceParams
             if (lane == 0) base = atomicAdd(p.counters, (unsigned long long)__popc(idle));
             base = __shfl_sync(FULL, base, 0);
             if (want) {
-                const unsigned long long slot64 = base + (unsigned)__popc(idle & ((1u << lane) - 1u));
+                const unsigned long long slot64 = p.slot_begin + base + (unsigned)__popc(idle & ((1u << lane) - 1u));
                 if (slot64 >= (unsigned long long)p.n_slots) state = ST_DONE;
                 else {
                     const uint32_t slot = (uint32_t)slot64;
@@ -274,8 +276,8 @@ __global__ void __launch_bounds__(TR_BLOCK, MINB) trace_kernel(const TraceParams
                         if (valid) {
                             primary_ray(p.cam, p.W, p.H, q.px, q.py, p.sx, p.sy, &o, &d);
                             tmin = p.tmin; tcur = p.tmax;
-                        } else if (p.compact && p.hits) {
-                            store_hit(p.hits, out_idx, __int_as_float(0x7f800000), VKHRT_MISS_SEGMENT, 0.0f, f3(0, 0, 0), PRIM_NONE, FLAG_PADDING);
+                        } else if (p.compact) {
+                            store_hit(p, out_idx, __int_as_float(0x7f800000), VKHRT_MISS_SEGMENT, 0.0f, f3(0, 0, 0), PRIM_NONE, FLAG_PADDING);
                         }
                     }
                     if (valid) {
@@ -421,7 +423,7 @@ static void fill_params(const DeviceScene& sc, const VkhrtFrameDesc& f, const Re
     memcpy(p.cam.vi, f.view_inverse, sizeof(p.cam.vi)); memcpy(p.cam.pi, f.proj_inverse, sizeof(p.cam.pi));
     p.W = r.W; p.H = r.H; p.sx = 0.5f; p.sy = 0.5f; p.tmin = r.tmin; p.tmax = r.tmax;
     p.T = r.T; p.tiles_x = r.tiles_x; p.n_tiles = r.n_tiles; p.tile_first = r.tile_first; p.tile_stride = r.tile_stride; p.compact = r.compact ? 1u : 0u;
-    p.rays = nullptr; p.n_slots = (uint32_t)r.n_slots; p.hits = nullptr; p.counters = sc.d_counters;
+    p.rays = nullptr; p.slot_begin = 0; p.n_slots = (uint32_t)r.n_slots; p.hits = nullptr; p.hits_mirror = nullptr; p.counters = sc.d_counters;
 }
 
 // scheduler tunables (defaults from the sweep in profiles/; overridable for experiments)
@@ -449,7 +451,7 @@ static int launch_trace_t(const DeviceScene& sc, TraceParams& p, cudaStream_t st
     if (per_sm < 1) per_sm = 1;
     tunables(p);
     if (g_blocks_per_sm > 0) per_sm = std::min(per_sm, g_blocks_per_sm);
-    unsigned long long want = ((unsigned long long)p.n_slots + TR_BLOCK - 1) / TR_BLOCK;
+    unsigned long long want = ((unsigned long long)(p.n_slots - p.slot_begin) + TR_BLOCK - 1) / TR_BLOCK;
     unsigned grid = (unsigned)std::min<unsigned long long>((unsigned long long)sc.sm_count * per_sm, std::max<unsigned long long>(want, 1ull));
     trace_kernel<TECH, STATS, WAVEFRONT, MINB><<<grid, TR_BLOCK, 0, st>>>(p);
     count_launch();
@@ -495,13 +497,25 @@ int render_frame(DeviceScene& sc, const VkhrtFrameDesc& f, VkhrtHit* hits_out, u
     const bool want_hits = hits_out != nullptr;
     const bool multi = r.spp > 1 && want_rgba;
     const bool direct_hits = !host_out && want_hits;
+    bool direct_to_host = false;
     VkhrtHit* d_hits0 = nullptr;
     VkhrtHit* d_hits_other = nullptr;
     uint8_t* d_rgba = nullptr;
-    if ((want_hits || want_rgba) && (!direct_hits || multi)) {
+    // Host hit buffer in pinned (page-locked) memory: the traversal kernel stores each record straight into it over
+    // PCIe (posted 16-byte writes, fully overlapped with the traversal) instead of a device->host copy after the
+    // kernel.  When an image is wanted too, the records are also kept in HBM for the shading kernel.
+    VkhrtHit* h_hits_mapped = nullptr;
+    if (host_out && want_hits && !stats && env_int("VKHRT_ZERO_COPY", 1)) {
+        cudaPointerAttributes at;
+        if (cudaPointerGetAttributes(&at, hits_out) == cudaSuccess && at.type == cudaMemoryTypeHost && at.devicePointer)
+            h_hits_mapped = static_cast<VkhrtHit*>(at.devicePointer);
+        cudaGetLastError();
+    }
+    if ((want_hits || want_rgba) && (!direct_hits || multi) && !(h_hits_mapped && !want_rgba)) {
         if ((rc = grow(&sc.d_hits_scratch, &sc.hits_scratch_n, (size_t)r.n_out * (multi ? 2 : 1)))) return rc;
     }
     if (want_hits || want_rgba) d_hits0 = direct_hits ? hits_out : sc.d_hits_scratch;
+    if (h_hits_mapped && !want_rgba) { d_hits0 = h_hits_mapped; h_hits_mapped = nullptr; direct_to_host = true; }   // single destination
     if (multi) d_hits_other = sc.d_hits_scratch + r.n_out;
     if (want_rgba) {
         if (host_out) { if ((rc = grow(&sc.d_rgba_scratch, &sc.rgba_scratch_n, (size_t)r.n_out * 4))) return rc; d_rgba = sc.d_rgba_scratch; }
@@ -516,9 +530,11 @@ int render_frame(DeviceScene& sc, const VkhrtFrameDesc& f, VkhrtHit* hits_out, u
     VK_CUDA(cudaEventRecord(ev[6], st));
     if (stats) VK_CUDA(cudaMemsetAsync(sc.d_counters, 0, 16 * sizeof(unsigned long long), st));
     const uint32_t n_samples = (want_rgba || stats) ? r.spp : 1;    // hits only => sample 0 is all that is observable
+
     for (uint32_t s = 0; s < n_samples; ++s) {
         sample_offset(s, &p.sx, &p.sy);
         p.hits = s == 0 ? d_hits0 : d_hits_other;
+        p.hits_mirror = s == 0 ? h_hits_mapped : nullptr;
         VK_CUDA(cudaMemsetAsync(sc.d_counters, 0, sizeof(unsigned long long), st));
         if (s == 0) VK_CUDA(cudaEventRecord(ev[7], st));
         rc = stats ? launch_trace<true, false>(sc, p, st) : launch_trace<false, false>(sc, p, st);
@@ -532,7 +548,7 @@ int render_frame(DeviceScene& sc, const VkhrtFrameDesc& f, VkhrtHit* hits_out, u
     }
     VK_CUDA(cudaEventRecord(ev[10], st));
     if (host_out) {
-        if (want_hits) VK_CUDA(cudaMemcpyAsync(hits_out, d_hits0, (size_t)r.n_out * sizeof(VkhrtHit), cudaMemcpyDeviceToHost, st));
+        if (want_hits && !h_hits_mapped && !direct_to_host) VK_CUDA(cudaMemcpyAsync(hits_out, d_hits0, (size_t)r.n_out * sizeof(VkhrtHit), cudaMemcpyDeviceToHost, st));
         if (want_rgba) VK_CUDA(cudaMemcpyAsync(rgba_out, d_rgba, (size_t)r.n_out * 4, cudaMemcpyDeviceToHost, st));
     }
     VK_CUDA(cudaEventRecord(ev[11], st));
@@ -557,6 +573,7 @@ int trace_ray_buffer(DeviceScene& sc, const float* rays_dev, uint64_t n, VkhrtHi
     p.nodes = sc.d_nodes; p.primA = sc.d_primA; p.primB = sc.d_primB; p.sorted_ids = sc.d_sorted_ids;
     p.n_prims = sc.n_prims; p.radius = sc.radius;
     p.counters = sc.d_counters;
+    p.slot_begin = 0; p.hits_mirror = nullptr;
     p.T = 8; p.tiles_x = 1; p.tile_stride = 1;
     // 32-bit slot indices inside the kernel: long ray buffers go in chunks of 2^30 rays
     const uint64_t chunk = 1ull << 30;
