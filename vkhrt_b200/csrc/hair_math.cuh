@@ -91,11 +91,12 @@ VK_DEV float bezier_bound_radius(const Bezier& c, float radius)
 // Prhi reports a hit only from a REAL cone intersection with |dt| < 5e-5 (hair_intersection.rint:67).
 // In ray-centric coordinates the hit point h = (0,0,c.z+s) then satisfies |h - B(t)|^2 = r^2 + dt^2 |B'(t)|^2
 // (cone.glsl:21-62 with slant 0), so the ray passes within r*(1 + 1e-6) of the curve point B(t), t in [0,1].
-// Every B(t) lies within `dev` of one of the two half-chords [B(0),B(1/2)], [B(1/2),B(1)] (convex-hull
-// property of the de Casteljau halves), and projecting onto the plane orthogonal to the ray cannot increase
+// Every B(t) lies within `dev` of one of the sub-chords [B(k/4),B((k+1)/4)] (convex-hull property of the
+// de Casteljau pieces), and projecting onto the plane orthogonal to the ray cannot increase
 // distances.  Hence: if the ray's projection (the origin of the ray-centric xy-plane) is farther than
-// r + dev (+ rounding slack) from BOTH projected half-chords, the march cannot report anything and is
-// skipped.  bezier_half_chord_deviation() is evaluated once per curve by the build kernel.
+// r + dev (+ rounding slack) from ALL four projected quarter-chords, the march cannot report anything and
+// is skipped.  bezier_quarter_chord_deviation() (= sagitta/16 of the whole curve) is evaluated once per curve
+// by the build kernel.
 VK_DEV float point_segment_distance(float3 p, float3 a, float3 b)
 {
     float3 e = b - a, q = p - a;
@@ -105,35 +106,55 @@ VK_DEV float point_segment_distance(float3 p, float3 a, float3 b)
     float3 r = q - s * e;
     return sqrtf(fdot3(r, r));
 }
-VK_DEV float bezier_half_chord_deviation(const Bezier& c)
+// de Casteljau split of a cubic at t = 1/2
+VK_DEV void bezier_split(const Bezier& c, Bezier& l, Bezier& r)
 {
     float3 q01 = 0.5f * (c.p0 + c.p1), q12 = 0.5f * (c.p1 + c.p2), q23 = 0.5f * (c.p2 + c.p3);
     float3 r0 = 0.5f * (q01 + q12), r1 = 0.5f * (q12 + q23);
     float3 m = 0.5f * (r0 + r1);
-    float dv = fmaxf(fmaxf(point_segment_distance(q01, c.p0, m), point_segment_distance(r0, c.p0, m)),
-                     fmaxf(point_segment_distance(r1, m, c.p3), point_segment_distance(q23, m, c.p3)));
-    return dv * 1.001f + 1e-7f;      // inflated: the bound must stay conservative under fp32 rounding
+    l.p0 = c.p0; l.p1 = q01; l.p2 = r0; l.p3 = m;
+    r.p0 = m; r.p1 = r1; r.p2 = q23; r.p3 = c.p3;
 }
-// squared distance from the origin to the 2-D segment [a, b]
-VK_DEV float origin_segment_dist2(float ax, float ay, float bx, float by)
+VK_DEV float bezier_chord_deviation(const Bezier& c)      // max distance of the curve from its chord SEGMENT (hull bound)
+{
+    return fmaxf(point_segment_distance(c.p1, c.p0, c.p3), point_segment_distance(c.p2, c.p0, c.p3));
+}
+// max deviation of the four quarter-curves from their chords [B(k/4), B((k+1)/4)], inflated
+VK_DEV float bezier_quarter_chord_deviation(const Bezier& c)
+{
+    Bezier l, r, a, b;
+    bezier_split(c, l, r);
+    bezier_split(l, a, b);
+    float dv = fmaxf(bezier_chord_deviation(a), bezier_chord_deviation(b));
+    bezier_split(r, a, b);
+    dv = fmaxf(dv, fmaxf(bezier_chord_deviation(a), bezier_chord_deviation(b)));
+    return dv * 1.001f + 1e-7f;      // the bound must stay conservative under fp32 rounding
+}
+// is the origin farther than sqrt(b2) from the 2-D segment [a, b]?  Division-free: compares d^2 * |e|^2 with b2 * |e|^2.
+// Any NaN makes the comparison false (= "not farther").
+VK_DEV bool origin_farther_than(float ax, float ay, float bx, float by, float b2)
 {
     float ex = bx - ax, ey = by - ay;
     float ee = fmaf(ex, ex, ey * ey);
-    float t = fminf(fmaxf(-fmaf(ax, ex, ay * ey), 0.0f), ee);
-    float s = ee > 0.0f ? t / ee : 0.0f;
-    float px = fmaf(s, ex, ax), py = fmaf(s, ey, ay);
-    return fmaf(px, px, py * py);
+    float aa = fmaf(ax, ax, ay * ay), bb = fmaf(bx, bx, by * by);
+    float t = -fmaf(ax, ex, ay * ey);                       // projection parameter * ee
+    float num = t <= 0.0f ? aa * ee : (t >= ee ? bb * ee : fmaf(aa, ee, -(t * t)));
+    return num > b2 * ee * 1.0001f;                         // rounding slack on the products
 }
 // c = curve in ray-centric coordinates.  true => the march may report a hit (NaNs never reject).
-VK_DEV bool half_chords_near_ray(const Bezier& c, float radius, float dev)
+VK_DEV bool quarter_chords_near_ray(const Bezier& c, float radius, float dev)
 {
-    float mx = 0.125f * ((c.p0.x + c.p3.x) + 3.0f * (c.p1.x + c.p2.x));
-    float my = 0.125f * ((c.p0.y + c.p3.y) + 3.0f * (c.p1.y + c.p2.y));
+    // B(1/4), B(1/2), B(3/4) projected on the xy-plane
+    float x1 = (1.0f / 64.0f) * (fmaf(27.0f, c.p0.x + c.p1.x, c.p3.x) + 9.0f * c.p2.x);
+    float y1 = (1.0f / 64.0f) * (fmaf(27.0f, c.p0.y + c.p1.y, c.p3.y) + 9.0f * c.p2.y);
+    float x2 = 0.125f * ((c.p0.x + c.p3.x) + 3.0f * (c.p1.x + c.p2.x));
+    float y2 = 0.125f * ((c.p0.y + c.p3.y) + 3.0f * (c.p1.y + c.p2.y));
+    float x3 = (1.0f / 64.0f) * (fmaf(27.0f, c.p2.x + c.p3.x, c.p0.x) + 9.0f * c.p1.x);
+    float y3 = (1.0f / 64.0f) * (fmaf(27.0f, c.p2.y + c.p3.y, c.p0.y) + 9.0f * c.p1.y);
     float bound = (radius + dev) * 1.001f + 4e-6f * (fabsf(c.p0.z) + fabsf(c.p3.z)) + 1e-6f;
     float b2 = bound * bound;
-    float d0 = origin_segment_dist2(c.p0.x, c.p0.y, mx, my);
-    float d1 = origin_segment_dist2(mx, my, c.p3.x, c.p3.y);
-    return !(d0 > b2 && d1 > b2);
+    return !(origin_farther_than(c.p0.x, c.p0.y, x1, y1, b2) && origin_farther_than(x1, y1, x2, y2, b2) &&
+             origin_farther_than(x2, y2, x3, y3, b2) && origin_farther_than(x3, y3, c.p3.x, c.p3.y, b2));
 }
 
 // ---- shaders/cylinder.glsl:8-46 (boolean, no t>0 test, assumes |d| = 1) ------------------------

@@ -30,7 +30,7 @@ struct DeviceScene {
     float scene_lo[3] = {0, 0, 0}, scene_hi[3] = {0, 0, 0};
 
     // primitives in Morton-sorted order
-    //   PHANTOM: primA[2p] = {B0.xyz, rmax}, primA[2p+1] = {B3.xyz, bits(prim id)}; primB[2p] = {B1.xyz, half-chord deviation}, primB[2p+1] = {B2.xyz,0}
+    //   PHANTOM: primA[2p] = {B0.xyz, rmax}, primA[2p+1] = {B3.xyz, bits(prim id)}; primB[2p] = {B1.xyz, quarter-chord deviation}, primB[2p+1] = {B2.xyz,0}
     //   LSS:     primA[2p] = {p0.xyz, r0},   primA[2p+1] = {p1.xyz, r1}
     //   DOTS:    primA[3p] = {v0.xyz, bits(prim id)}, primA[3p+1] = {v1.xyz,0}, primA[3p+2] = {v2.xyz,0}
     float4* d_primA = nullptr;

@@ -189,7 +189,7 @@ __global__ void __launch_bounds__(TR_BLOCK, MINB) trace_kernel(const TraceParams
                         march_begin(ms, make_ray_frame(d), o, w);
                         mpos = pos;
                         // conservative filter (hair_math.cuh): skip marches that cannot report a hit
-                        state = half_chords_near_ray(ms.c, p.radius, b0.w) ? ST_MARCH : ST_POP;
+                        state = quarter_chords_near_ray(ms.c, p.radius, b0.w) ? ST_MARCH : ST_POP;
                     } else state = ST_POP;
                 } else if (TECH == VKHRT_TECHNIQUE_LSS) {
                     const float4 a0 = __ldg(p.primA + 2 * (size_t)pos), a1 = __ldg(p.primA + 2 * (size_t)pos + 1);

@@ -70,6 +70,7 @@ class ShardedRenderer:
         n = self.layout.shard_pixels
         self.d_hits = torch.empty((n, 32), dtype=torch.uint8, device=self.device)
         self.d_rgba = torch.empty((n, 4), dtype=torch.uint8, device=self.device) if want_rgba else None
+        self.o_rgba = None
         if self.world > 1:
             self.g_hits = torch.empty((self.world * n, 32), dtype=torch.uint8, device=self.device)
             self.o_hits = torch.empty((width * height, 32), dtype=torch.uint8, device=self.device)
