@@ -33,6 +33,8 @@ WORKLOADS = {
     "c3": (100000, 32, "curly", 1920, 1080, "lss", 8, True),
     "c4": (1000000, 16, "curly", 1920, 1080, "dots", 1, False),
     "c5": (1000000, 64, "curly", 3840, 2160, "phantom", 64, True),
+    # not a BASELINE config: C2's groom at 4K, to separate kernel throughput from launch ramp/tail effects
+    "c2_4k": (100000, 32, "curly", 3840, 2160, "phantom", 1, False),
 }
 PRIM_BYTES = {"phantom": 48, "lss": 32, "dots": 36}   # P in B_ray = 64 N_int + P N_prim + W
 
@@ -49,7 +51,7 @@ def workload_desc(name, n, w, h):
     s, g, style, _, _, tech, spp, rgba = WORKLOADS[name]
     return (f"{name}: synthetic {style} groom {s} strands x {g} segments ({s * g} segs), {tech} intersector, "
             f"{w}x{h} primary rays x {spp} spp, {'hit buffer + RGBA8' if rgba else 'hit buffer only'}"
-            + (f", 64x64 tiles round-robin over {n} GPUs, NCCL all_gather" if n > 1 else ""))
+            + (f", 64x64 tiles round-robin over {n} GPUs" if n > 1 else ""))
 
 
 def peaks():
@@ -121,11 +123,19 @@ def oracle_sample(name, n_rays, seed=0x5EED):
     return orc, frame, sub, build_s
 
 
+def host_threads():
+    """All host threads this process may use (torchrun exports OMP_NUM_THREADS=1: ask the affinity mask instead)."""
+    try:
+        return len(os.sched_getaffinity(0))
+    except AttributeError:
+        return os.cpu_count() or 1
+
+
 def time_oracle(orc, frame, sub, reps):
     times, stats = [], None
     for _ in range(reps):
         t0 = time.time()
-        _, _, stats = orc.render(frame, hits=True, rgba=False, pixel_subset=sub, stats=True)
+        _, _, stats = orc.render(frame, hits=True, rgba=False, pixel_subset=sub, stats=True, n_threads=host_threads())
         times.append(time.time() - t0)
     return times, stats
 
@@ -148,7 +158,7 @@ def run_reference(args):
     times, stats = time_oracle(orc, frame, sub, args.steps)
     total = time.time() - t0
     mrays = len(sub) * args.steps / total / 1e6
-    cores = O.max_threads()
+    cores = host_threads()
     sample = f"{len(sub)} stratified pixels of the {w}x{h} frame per step (1 spp)"
     print(json.dumps({
         "impl": "reference", "metric": "Mrays/s primary-ray hair hits", "value": mrays, "unit": "Mrays/s",
@@ -172,6 +182,8 @@ def main():
     ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="target CPU-baseline duration")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--gather", default="peer", choices=["peer", "gather"],
+                    help="N > 1: 'peer' = kernels store straight into the gathering rank's frame buffer over NVLink; 'gather' = NCCL all_gather + untile")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
     if args.impl == "reference":
@@ -209,10 +221,9 @@ def main():
     stream = torch.cuda.Stream(device=dev)
     torch.cuda.set_stream(stream)
     T = 64
-    sharded = ShardedRenderer(scene, W, H, tile=T, spp=spp, want_rgba=want_rgba, device=dev)
+    sharded = ShardedRenderer(scene, W, H, tile=T, spp=spp, want_rgba=want_rgba, device=dev, mode=args.gather)
     fd = sharded.make_frame(vi, pi, stream.cuda_stream)
     n_local = sharded.layout.shard_pixels
-    d_hits = sharded.d_hits
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)   # > 126 MB L2
 
     def step_device():
@@ -270,7 +281,9 @@ def main():
     frame_timing = scene.timing()
 
     # ---------------- algorithmic bytes per ray (GPU debug counters on the same frame) ----------------
-    stats = scene.render_stats_into(fd, d_hits.data_ptr(), None)
+    d_hits = torch.empty((n_local, 32), dtype=torch.uint8, device=dev)
+    fs = V.make_frame(vi, pi, W, H, spp=spp, output_memory=V.MEM_DEVICE, stream=stream.cuda_stream, **sharded.layout.frame_kwargs(rank))
+    stats = scene.render_stats_into(fs, d_hits.data_ptr(), None)
     torch.cuda.synchronize()
     agg = torch.tensor([stats["rays"], stats["nodes_visited"], stats["prims_tested"], stats["hits"], stats["phantom_iterations"]],
                        dtype=torch.float64, device=dev)
@@ -297,7 +310,9 @@ def main():
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": workload_desc(name, world, W, H), "rays_per_step": rays_per_step, "rays_per_gpu_per_step": rays_per_step // world,
                        "l2": "256 MB flush between timed frames; scene (nodes+primitives) is %.0f MB" % (scene.n_primitives * 128 / 1e6),
-                       "seed": hex(V.DEFAULT_SEED), "build_ms": build_timing["build_total_ms"]},
+                       "seed": hex(V.DEFAULT_SEED), "build_ms": build_timing["build_total_ms"],
+                       "frame_assembly": {"single": "one GPU", "peer": "traversal kernels store hit records straight into rank 0's frame buffer over NVLink (CUDA IPC peer mapping), 4-byte NCCL all_reduce as completion signal",
+                                          "gather": "NCCL all_gather of compact shards + untile kernel"}[sharded.mode]},
             "e2e": {"value": e2e_value, "unit": "Mrays/s", "h2d_bytes_per_step": 128 + 64,
                     "d2h_bytes_per_step": int(n_local * 32 + (n_local * 4 if want_rgba else 0)),
                     "note": "vkhrt_render with host buffers: camera in (kernel parameters), hit records out to pinned host memory; wall clock"},
@@ -312,7 +327,7 @@ def main():
                          "note": "B_ray = 64*N_int + P*N_prim + W from the GPU kernel's own debug counters (L2-resident upper levels "
                                  "make this exceed DRAM traffic; see DESIGN.md §6)"},
         }
-        if not args.no_cpu_baseline:
+        if not args.no_cpu_baseline and world == 1:      # the CPU leg runs at N=1 only
             from oracle import oracle as O
             n0 = 262144
             orc, frame, sub, _ = oracle_sample(name, n0)
@@ -321,7 +336,7 @@ def main():
             reps = int(max(1, min(256, args.cpu_seconds / max(t1[0], 1e-3))))
             tt, ost = time_oracle(orc, frame, sub, reps)
             cpu_mrays = len(sub) * reps / sum(tt) / 1e6
-            line["cpu_baseline"] = {"value": cpu_mrays, "unit": "Mrays/s", "cores": O.max_threads(), "kind": "port",
+            line["cpu_baseline"] = {"value": cpu_mrays, "unit": "Mrays/s", "cores": host_threads(), "kind": "port",
                                     "sample": f"{reps} x {len(sub)} stratified pixels of the N=1 {bw}x{bh} frame ({sum(tt):.1f} s of CPU work)",
                                     "n_int_per_ray": ost["nodes_visited"] / ost["rays"], "n_prim_per_ray": ost["prims_tested"] / ost["rays"]}
         print(json.dumps(line))

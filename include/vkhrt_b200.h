@@ -107,6 +107,11 @@ typedef struct VkhrtFrameDesc {
     uint32_t tile_size;             /* 0 => 64 (must be a multiple of 8)                           */
     uint32_t tile_first;
     uint32_t tile_stride;           /* 0 => 1                                                      */
+    uint32_t row_major_output;      /* with tile_stride > 1: 1 => outputs are FULL-FRAME buffers and every pixel
+                                       is written at its row-major position (only the tiles of this shard are
+                                       touched).  All shards can then share one frame buffer, e.g. the gathering
+                                       GPU's, mapped into every rank over NVLink (vkhrt_shared_buffer_*): the
+                                       traversal kernel's stores ARE the gather.  Device output memory only.   */
     int32_t  output_memory;         /* VkhrtMemory of hits_out / rgba8_out                         */
     void*    stream;                /* cudaStream_t to run on (device outputs only); NULL => the
                                        scene's own stream                                         */
@@ -210,6 +215,17 @@ uint64_t vkhrt_frame_local_pixels(const VkhrtFrameDesc* frame);
 int  vkhrt_untile(const VkhrtFrameDesc* frame, uint32_t world, const void* gathered, void* row_major,
                   uint32_t elem_bytes, void* stream);
 int  vkhrt_last_timing(const VkhrtScene* scene, VkhrtTiming* timing);
+
+/* ---- device buffers shareable between the per-GPU processes of one box (CUDA IPC over NVLink/PCIe) ---- */
+/* create: plain device allocation on `device` + a 64-byte handle another process can open.
+ * open:   map the exporter's allocation into this process (peer access is enabled on first use);
+ *         the returned pointer is valid as hits_out / rgba8_out of vkhrt_render with VKHRT_MEM_DEVICE.
+ * The reference is single-GPU (one graphics queue, source/vulkan_context.cpp:287-288): nothing replaces these. */
+#define VKHRT_IPC_HANDLE_BYTES 64
+int  vkhrt_shared_buffer_create(int device, size_t bytes, void** dev_ptr_out, uint8_t handle_out[VKHRT_IPC_HANDLE_BYTES]);
+int  vkhrt_shared_buffer_open(int device, const uint8_t handle[VKHRT_IPC_HANDLE_BYTES], void** dev_ptr_out);
+int  vkhrt_shared_buffer_close(int device, void* opened_ptr);
+int  vkhrt_shared_buffer_destroy(int device, void* created_ptr);
 
 /* ---- wavefront pieces, individually callable (device pointers) -------------------------- */
 /* ray buffer entry: 32 bytes {ox,oy,oz,tmin, dx,dy,dz,tmax} */

@@ -23,7 +23,7 @@ class FrameDesc(C.Structure):
                 ("width", C.c_uint32), ("height", C.c_uint32), ("t_min", C.c_float), ("t_max", C.c_float),
                 ("spp", C.c_uint32), ("shade_mode", C.c_int32), ("miss_rgb", C.c_float * 3),
                 ("tile_size", C.c_uint32), ("tile_first", C.c_uint32), ("tile_stride", C.c_uint32),
-                ("output_memory", C.c_int32), ("stream", C.c_void_p)]
+                ("row_major_output", C.c_uint32), ("output_memory", C.c_int32), ("stream", C.c_void_p)]
 
 
 class TraceStats(C.Structure):
@@ -98,7 +98,7 @@ def max_threads():
 
 
 def make_frame(view_inv, proj_inv, width, height, spp=1, shade_mode=0, miss_rgb=(0.0, 0.0, 0.0),
-               tile_size=0, tile_first=0, tile_stride=0, t_min=0.0, t_max=0.0):
+               tile_size=0, tile_first=0, tile_stride=0, t_min=0.0, t_max=0.0, row_major_output=0):
     f = FrameDesc()
     f.view_inverse[:] = [float(x) for x in np.asarray(view_inv, np.float32).reshape(16)]
     f.proj_inverse[:] = [float(x) for x in np.asarray(proj_inv, np.float32).reshape(16)]
@@ -106,6 +106,7 @@ def make_frame(view_inv, proj_inv, width, height, spp=1, shade_mode=0, miss_rgb=
     f.t_min, f.t_max = t_min, t_max
     f.miss_rgb[:] = list(miss_rgb)
     f.tile_size, f.tile_first, f.tile_stride = tile_size, tile_first, tile_stride
+    f.row_major_output = row_major_output
     return f
 
 
@@ -182,7 +183,7 @@ class OracleScene:
 def local_pixels(frame):
     T = frame.tile_size or 64
     stride = frame.tile_stride or 1
-    if stride <= 1:
+    if stride <= 1 or frame.row_major_output:
         return frame.width * frame.height
     tx, ty = (frame.width + T - 1) // T, (frame.height + T - 1) // T
     nt = tx * ty

@@ -307,3 +307,46 @@ def test_pinned_host_buffers_zero_copy_path(V, small_groom, tech):
             assert np.array_equal(hh.numpy().reshape(-1), href.view(np.uint8))
             if want_rgba:
                 assert np.array_equal(hi.numpy(), iref)
+
+
+@pytest.mark.parametrize("tech,spp", [(0, 1), (1, 3), (2, 1)])
+def test_row_major_shards_share_one_frame_buffer(V, O, small_groom, tech, spp):
+    """tile_stride > 1 with row_major_output: every shard writes only its own pixels at their row-major position of a
+    full-frame buffer (the layout the multi-GPU 'peer' mode uses over NVLink).  All shards into ONE buffer == full frame."""
+    import torch
+    pos, idx = small_groom
+    W, H, T, world = 200, 120, 32, 3
+    vi, pi = default_camera(V, W, H)
+    with V.Scene(pos, idx, technique=tech) as sc:
+        sc.build()
+        full_h, full_i, _ = sc.render(V.make_frame(vi, pi, W, H, spp=spp, tile_size=T))
+        shared = V.SharedBuffer.create(W * H * 32)                       # an IPC-exportable device buffer
+        try:
+            di = torch.full((W * H, 4), 7, dtype=torch.uint8, device="cuda")
+            st = torch.cuda.current_stream().cuda_stream
+            for r in range(world):
+                f = V.make_frame(vi, pi, W, H, spp=spp, tile_size=T, tile_first=r, tile_stride=world, row_major_output=1,
+                                 output_memory=V.MEM_DEVICE, stream=st)
+                assert V.frame_local_pixels(f) == W * H
+                sc.render_into(f, shared.ptr, di.data_ptr())
+                torch.cuda.synchronize()
+                if r == 0:      # only this shard's tiles have been written so far
+                    assert (di.cpu().numpy() == 7).all(axis=1).sum() > W * H // 2
+            from vkhrt_b200.multi import _DeviceView
+            dh = torch.as_tensor(_DeviceView(shared.ptr, (W * H, 32)), device="cuda")
+            assert np.array_equal(dh.cpu().numpy().reshape(-1), full_h.view(np.uint8))
+            assert np.array_equal(di.cpu().numpy(), full_i)
+        finally:
+            shared.close()
+        # the oracle implements the same layout
+        orc = O.OracleScene(pos, idx, technique=tech)
+        acc = np.zeros(W * H, V.HIT_DTYPE)
+        for r in range(world):
+            fo = O.make_frame(vi, pi, W, H, spp=spp, tile_size=T, tile_first=r, tile_stride=world, row_major_output=1)
+            ho, _, _ = orc.render(fo, rgba=False)
+            own = (ho["flags"] != 0) | (ho["t"] != 0)
+            acc[own] = ho[own]
+        assert acc.tobytes() == full_h.tobytes()
+        # host output memory cannot be shared between shards
+        with pytest.raises(V.VkhrtError):
+            sc.render(V.make_frame(vi, pi, W, H, tile_size=T, tile_first=0, tile_stride=2, row_major_output=1))

@@ -48,7 +48,7 @@ class FrameDesc(C.Structure):
                 ("width", C.c_uint32), ("height", C.c_uint32), ("t_min", C.c_float), ("t_max", C.c_float),
                 ("spp", C.c_uint32), ("shade_mode", C.c_int32), ("miss_rgb", C.c_float * 3),
                 ("tile_size", C.c_uint32), ("tile_first", C.c_uint32), ("tile_stride", C.c_uint32),
-                ("output_memory", C.c_int32), ("stream", C.c_void_p)]
+                ("row_major_output", C.c_uint32), ("output_memory", C.c_int32), ("stream", C.c_void_p)]
 
 
 class BvhView(C.Structure):
@@ -85,6 +85,7 @@ ABI_SYMBOLS = [
     "vkhrt_scene_get_primitives", "vkhrt_scene_primitive_count", "vkhrt_scene_destroy",
     "vkhrt_render", "vkhrt_render_stats", "vkhrt_frame_local_pixels", "vkhrt_untile", "vkhrt_last_timing",
     "vkhrt_generate_rays", "vkhrt_trace_rays", "vkhrt_camera_matrices", "vkhrt_groom_generate",
+    "vkhrt_shared_buffer_create", "vkhrt_shared_buffer_open", "vkhrt_shared_buffer_close", "vkhrt_shared_buffer_destroy",
 ]
 
 _lib = None
@@ -130,6 +131,10 @@ def lib():
     L.vkhrt_camera_matrices.argtypes = [C.POINTER(C.c_float), C.c_float, C.c_float, C.c_float, C.c_float, C.c_float,
                                         C.c_float, C.POINTER(C.c_float), C.POINTER(C.c_float)]
     L.vkhrt_groom_generate.argtypes = [C.c_uint32, C.c_uint32, C.c_int32, C.c_uint64, C.c_void_p, C.c_void_p]
+    L.vkhrt_shared_buffer_create.argtypes = [C.c_int, C.c_size_t, C.POINTER(C.c_void_p), C.c_char_p]
+    L.vkhrt_shared_buffer_open.argtypes = [C.c_int, C.c_char_p, C.POINTER(C.c_void_p)]
+    L.vkhrt_shared_buffer_close.argtypes = [C.c_int, C.c_void_p]
+    L.vkhrt_shared_buffer_destroy.argtypes = [C.c_int, C.c_void_p]
     if L.vkhrt_abi_version() != 1:
         raise ImportError("libvkhrt_b200.so ABI version mismatch")
     _lib = L
@@ -177,7 +182,7 @@ def generate_groom(n_strands, segments, style=GROOM_CURLY, seed=DEFAULT_SEED):
 
 
 def make_frame(view_inv, proj_inv, width, height, spp=1, shade_mode=SHADE, miss_rgb=(0.0, 0.0, 0.0), tile_size=0,
-               tile_first=0, tile_stride=0, t_min=0.0, t_max=0.0, output_memory=MEM_HOST, stream=None):
+               tile_first=0, tile_stride=0, t_min=0.0, t_max=0.0, output_memory=MEM_HOST, stream=None, row_major_output=0):
     f = FrameDesc()
     f.view_inverse[:] = [float(x) for x in np.asarray(view_inv, np.float32).reshape(16)]
     f.proj_inverse[:] = [float(x) for x in np.asarray(proj_inv, np.float32).reshape(16)]
@@ -187,6 +192,7 @@ def make_frame(view_inv, proj_inv, width, height, spp=1, shade_mode=SHADE, miss_
     f.tile_size, f.tile_first, f.tile_stride = tile_size, tile_first, tile_stride
     f.output_memory = output_memory
     f.stream = stream
+    f.row_major_output = row_major_output
     return f
 
 
@@ -288,6 +294,35 @@ class Scene:
         t = Timing()
         _check(lib().vkhrt_last_timing(self._h, C.byref(t)), "vkhrt_last_timing")
         return t.as_dict()
+
+
+class SharedBuffer:
+    """A device buffer that the per-GPU processes of one box can all address (CUDA IPC; peer stores go over NVLink).
+    The creator owns it: `SharedBuffer.create(bytes, device)` -> `.handle` (64 bytes) -> `SharedBuffer.open(handle, device)`."""
+
+    def __init__(self, ptr, handle, device, owner):
+        self.ptr, self.handle, self.device, self.owner = ptr, handle, device, owner
+
+    @classmethod
+    def create(cls, nbytes, device=0):
+        ptr = C.c_void_p()
+        handle = C.create_string_buffer(64)
+        _check(lib().vkhrt_shared_buffer_create(device, nbytes, C.byref(ptr), handle), "vkhrt_shared_buffer_create")
+        return cls(ptr.value, handle.raw, device, True)
+
+    @classmethod
+    def open(cls, handle, device=0):
+        ptr = C.c_void_p()
+        _check(lib().vkhrt_shared_buffer_open(device, bytes(handle), C.byref(ptr)), "vkhrt_shared_buffer_open")
+        return cls(ptr.value, bytes(handle), device, False)
+
+    def close(self):
+        if self.ptr:
+            if self.owner:
+                lib().vkhrt_shared_buffer_destroy(self.device, self.ptr)
+            else:
+                lib().vkhrt_shared_buffer_close(self.device, self.ptr)
+            self.ptr = None
 
 
 def generate_rays(frame, sample, rays_ptr, device=0):

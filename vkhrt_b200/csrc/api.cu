@@ -225,6 +225,53 @@ int vkhrt_last_timing(const VkhrtScene* scene, VkhrtTiming* timing)
     return VKHRT_OK;
 }
 
+int vkhrt_shared_buffer_create(int device, size_t bytes, void** dev_ptr_out, uint8_t handle_out[VKHRT_IPC_HANDLE_BYTES])
+{
+    static_assert(sizeof(cudaIpcMemHandle_t) == VKHRT_IPC_HANDLE_BYTES, "IPC handle size");
+    if (!dev_ptr_out || !handle_out || bytes == 0) { set_last_error("null argument"); return VKHRT_ERR_INVALID_ARGUMENT; }
+    int rc = check_device(device);
+    if (rc) return rc;
+    VK_CUDA(cudaSetDevice(device));
+    void* ptr = nullptr;
+    VK_CUDA(cudaMalloc(&ptr, bytes));
+    cudaIpcMemHandle_t h;
+    cudaError_t e = cudaIpcGetMemHandle(&h, ptr);
+    if (e != cudaSuccess) { cudaFree(ptr); set_last_error(std::string("cudaIpcGetMemHandle: ") + cudaGetErrorString(e)); return VKHRT_ERR_CUDA; }
+    memcpy(handle_out, &h, sizeof(h));
+    *dev_ptr_out = ptr;
+    return VKHRT_OK;
+}
+
+int vkhrt_shared_buffer_open(int device, const uint8_t handle[VKHRT_IPC_HANDLE_BYTES], void** dev_ptr_out)
+{
+    if (!handle || !dev_ptr_out) { set_last_error("null argument"); return VKHRT_ERR_INVALID_ARGUMENT; }
+    int rc = check_device(device);
+    if (rc) return rc;
+    VK_CUDA(cudaSetDevice(device));
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle, sizeof(h));
+    void* ptr = nullptr;
+    VK_CUDA(cudaIpcOpenMemHandle(&ptr, h, cudaIpcMemLazyEnablePeerAccess));
+    *dev_ptr_out = ptr;
+    return VKHRT_OK;
+}
+
+int vkhrt_shared_buffer_close(int device, void* opened_ptr)
+{
+    if (!opened_ptr) return VKHRT_OK;
+    VK_CUDA(cudaSetDevice(device));
+    VK_CUDA(cudaIpcCloseMemHandle(opened_ptr));
+    return VKHRT_OK;
+}
+
+int vkhrt_shared_buffer_destroy(int device, void* created_ptr)
+{
+    if (!created_ptr) return VKHRT_OK;
+    VK_CUDA(cudaSetDevice(device));
+    VK_CUDA(cudaFree(created_ptr));
+    return VKHRT_OK;
+}
+
 int vkhrt_generate_rays(const VkhrtFrameDesc* frame, uint32_t sample, float* rays_out_device, int device)
 {
     if (!frame || !rays_out_device) { set_last_error("null argument"); return VKHRT_ERR_INVALID_ARGUMENT; }

@@ -330,18 +330,22 @@ __global__ void __launch_bounds__(256) raygen_kernel(const TraceParams p, float4
 // ------------------------------------------------------------------------------------------------
 // closest-hit colour (shading.glsl / debug.glsl) + imageStore to 8-bit UNORM; spp accumulation in fp32
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) shade_kernel(const VkhrtHit* __restrict__ hits, unsigned long long n, int mode, float3 miss,
+// One thread per ray slot of this shard (same slot -> pixel map as the traversal kernel), so that a shard only
+// ever touches the pixels it owns whatever the output layout is.
+__global__ void __launch_bounds__(256) shade_kernel(const TraceParams p, const VkhrtHit* __restrict__ hits, int mode, float3 miss,
                                                     float4* __restrict__ accum, uchar4* __restrict__ rgba, uint32_t sample, uint32_t spp)
 {
-    unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
+    const unsigned long long slot64 = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (slot64 >= p.n_slots) return;
+    const PixelRef q = slot_to_pixel(p, (uint32_t)slot64);
+    const size_t i = q.out;
+    if (!q.valid) {                                         // padding pixel of a partial tile
+        if (p.compact && rgba && sample + 1 == spp) rgba[i] = make_uchar4(0, 0, 0, 0);
+        return;
+    }
     const float4* h = reinterpret_cast<const float4*>(hits + i);
     const float4 h0 = h[0], h1 = h[1];
     const uint32_t flags = __float_as_uint(h1.w);
-    if (flags & FLAG_PADDING) {
-        if (rgba && sample + 1 == spp) rgba[i] = make_uchar4(0, 0, 0, 0);
-        return;
-    }
     float3 c;
     if (flags & FLAG_HIT) c = mode == VKHRT_SHADE_DEBUG_PRIMID ? debug_palette(__float_as_uint(h1.z)) : shade_normal(f3(h0.w, h1.x, h1.y));
     else c = miss;
@@ -390,7 +394,7 @@ static bool resolve(const VkhrtFrameDesc& f, Resolved& r)
     if (r.tile_first >= r.tile_stride) return false;
     r.tiles_x = (r.W + r.T - 1) / r.T; r.tiles_y = (r.H + r.T - 1) / r.T;
     r.n_tiles = r.tiles_x * r.tiles_y;
-    r.compact = r.tile_stride > 1;
+    r.compact = r.tile_stride > 1 && !f.row_major_output;
     r.n_local_tiles = (r.n_tiles + r.tile_stride - 1) / r.tile_stride;
     r.n_slots = (unsigned long long)r.n_local_tiles * r.T * r.T;
     r.n_out = r.compact ? r.n_slots : (unsigned long long)r.W * r.H;
@@ -488,6 +492,10 @@ int render_frame(DeviceScene& sc, const VkhrtFrameDesc& f, VkhrtHit* hits_out, u
     Resolved r;
     if (!resolve(f, r)) { set_last_error("vkhrt_render: bad frame description (size, tile_size multiple of 8, tile_first < tile_stride)"); return VKHRT_ERR_INVALID_ARGUMENT; }
     const bool host_out = f.output_memory == VKHRT_MEM_HOST;
+    if (host_out && r.tile_stride > 1 && f.row_major_output) {
+        set_last_error("vkhrt_render: row_major_output with tile_stride > 1 writes into a frame buffer shared by all shards and needs device output memory");
+        return VKHRT_ERR_INVALID_ARGUMENT;
+    }
     cudaStream_t st = (!host_out && f.stream) ? (cudaStream_t)f.stream : sc.stream;
     int rc;
 
@@ -541,7 +549,7 @@ int render_frame(DeviceScene& sc, const VkhrtFrameDesc& f, VkhrtHit* hits_out, u
         if (rc) return rc;
         if (s == 0) VK_CUDA(cudaEventRecord(ev[8], st));
         if (want_rgba) {
-            shade_kernel<<<(unsigned)((r.n_out + 255) / 256), 256, 0, st>>>(p.hits, r.n_out, f.shade_mode, miss, sc.d_accum, (uchar4*)d_rgba, s, r.spp);
+            shade_kernel<<<(unsigned)((r.n_slots + 255) / 256), 256, 0, st>>>(p, p.hits, f.shade_mode, miss, sc.d_accum, (uchar4*)d_rgba, s, r.spp);
             count_launch();
         }
         if (s == 0) VK_CUDA(cudaEventRecord(ev[9], st));
