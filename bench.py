@@ -36,7 +36,10 @@ WORKLOADS = {
     # not a BASELINE config: C2's groom at 4K, to separate kernel throughput from launch ramp/tail effects
     "c2_4k": (100000, 32, "curly", 3840, 2160, "phantom", 1, False),
 }
-PRIM_BYTES = {"phantom": 48, "lss": 32, "dots": 36}   # P in B_ray = 64 N_int + P N_prim + W
+# P in B_ray = 64 N_int + P N_prim + W.  DOTS: a leaf is one 64-byte strip record holding the 4 triangles of
+# a segment, so P = 16 bytes per triangle of a fetched strip (a triangle-per-leaf tree would read 36 B each)
+PRIM_BYTES = {"phantom": 48, "lss": 32, "dots": 16}
+LEAF_RECORD_BYTES = {"phantom": 64, "lss": 32, "dots": 64}
 
 
 def frame_size(base_w, base_h, n):
@@ -310,7 +313,7 @@ def main():
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": total_ms / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": workload_desc(name, world, W, H), "rays_per_step": rays_per_step, "rays_per_gpu_per_step": rays_per_step // world,
-                       "l2": "256 MB flush between timed frames; scene (nodes+primitives) is %.0f MB" % (scene.n_primitives * 128 / 1e6),
+                       "l2": "256 MB flush between timed frames; scene (nodes+primitives) is %.0f MB" % (s * g * (64 + LEAF_RECORD_BYTES[tech]) / 1e6),
                        "seed": hex(V.DEFAULT_SEED), "build_ms": build_timing["build_total_ms"],
                        "frame_assembly": {"single": "one GPU", "peer": "traversal kernels store hit records straight into rank 0's frame buffer over NVLink (CUDA IPC peer mapping), 4-byte NCCL all_reduce as completion signal",
                                           "gather": "NCCL all_gather of compact shards + untile kernel"}[sharded.mode]},

@@ -130,8 +130,10 @@ typedef struct VkhrtHit {
 } VkhrtHit;
 
 /* One LBVH node: two children with their boxes, 64 bytes, read as 4 x 16-byte loads.
- * child >> 31 == 1 => leaf; low 31 bits = position in Morton-sorted primitive order
- * (leaf) or internal-node index.  primK = original primitive id when child K is a leaf. */
+ * child >> 31 == 1 => leaf; low 31 bits = position in Morton-sorted leaf order
+ * (leaf) or internal-node index.  primK = original leaf id when child K is a leaf.
+ * A leaf is one primitive (PHANTOM curve, LSS) or, for DOTS, one STRIP = the 4 triangles
+ * 4*segment .. 4*segment+3 of a segment (their boxes all but coincide); leaf id = segment id. */
 typedef struct VkhrtBvhNode {
     float lo0[3]; uint32_t child0;
     float hi0[3]; uint32_t child1;
@@ -145,10 +147,10 @@ typedef struct VkhrtBvhNode {
 /* Host copy-out of the acceleration structure for the bit-exact build check (the
  * reference's BLAS is opaque driver state, source/bottom_level_acceleration_structure.cpp:34-78). */
 typedef struct VkhrtBvhView {
-    uint32_t      n_primitives;
+    uint32_t      n_primitives;     /* number of BVH leaves (= segments; see VkhrtBvhNode)         */
     uint32_t      n_nodes;          /* max(n_primitives - 1, 1)                                    */
     VkhrtBvhNode* nodes;            /* caller-allocated, n_nodes entries (nullable)                */
-    uint32_t*     sorted_prim_ids;  /* caller-allocated, n_primitives entries (nullable)           */
+    uint32_t*     sorted_prim_ids;  /* caller-allocated, n_primitives entries (nullable): leaf ids */
     uint64_t*     sorted_morton;    /* caller-allocated, n_primitives entries (nullable)           */
     float         scene_lo[3], scene_hi[3];  /* centroid bounds used for Morton quantisation       */
 } VkhrtBvhView;
@@ -166,7 +168,7 @@ typedef struct VkhrtTiming {
 typedef struct VkhrtTraceStats {
     uint64_t rays;
     uint64_t nodes_visited;     /* internal 64-byte node records fetched                           */
-    uint64_t prims_tested;      /* leaf primitives handed to the intersector                       */
+    uint64_t prims_tested;      /* primitives of the leaves reached (DOTS: 4 per strip fetched)    */
     uint64_t hits;
     uint64_t phantom_iterations;
     /* warp scheduler: steps executed per state {node, leaf, march, refill} and the lanes active in them

@@ -62,6 +62,8 @@ def lib():
         L.orc_scene_destroy.argtypes = [C.c_void_p]
         L.orc_scene_primitive_count.restype = C.c_uint32
         L.orc_scene_primitive_count.argtypes = [C.c_void_p]
+        L.orc_scene_leaf_count.restype = C.c_uint32
+        L.orc_scene_leaf_count.argtypes = [C.c_void_p]
         L.orc_scene_node_count.restype = C.c_uint32
         L.orc_scene_node_count.argtypes = [C.c_void_p]
         L.orc_scene_get_primitives.argtypes = [C.c_void_p, C.c_void_p]
@@ -137,18 +139,24 @@ class OracleScene:
     def n_primitives(self):
         return int(lib().orc_scene_primitive_count(self._h))
 
+    @property
+    def n_leaves(self):
+        """BVH leaves: one per primitive (PHANTOM, LSS) or one per 4-triangle strip (DOTS)."""
+        return int(lib().orc_scene_leaf_count(self._h))
+
     def primitives(self):
         out = np.empty((self.n_primitives, FLOATS_PER_PRIM[self.technique]), np.float32)
         lib().orc_scene_get_primitives(self._h, out.ctypes.data)
         return out
 
     def aabbs(self):
-        out = np.empty((self.n_primitives, 6), np.float32)
+        """leaf boxes (lo, hi), one per BVH leaf"""
+        out = np.empty((self.n_leaves, 6), np.float32)
         lib().orc_scene_get_aabbs(self._h, out.ctypes.data)
         return out
 
     def bvh(self):
-        n = self.n_primitives
+        n = self.n_leaves
         nodes = np.zeros(int(lib().orc_scene_node_count(self._h)), NODE_DTYPE)
         ids = np.zeros(n, np.uint32)
         morton = np.zeros(n, np.uint64)

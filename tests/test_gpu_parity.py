@@ -350,3 +350,37 @@ def test_row_major_shards_share_one_frame_buffer(V, O, small_groom, tech, spp):
         # host output memory cannot be shared between shards
         with pytest.raises(V.VkhrtError):
             sc.render(V.make_frame(vi, pi, W, H, tile_size=T, tile_first=0, tile_stride=2, row_major_output=1))
+
+
+@pytest.mark.parametrize("cam,radius,fov", [((0.0, 150.0, 20.0), 0.02, 60.0), ((0.0, 150.0, 400.0), 0.02, 4.0),
+                                            ((3.0, 158.5, 1.0), 0.005, 90.0), ((900.0, 150.0, 0.0), 0.1, 2.0)])
+def test_dots_strip_reject_is_result_neutral(V, O, small_groom, cam, radius, fov):
+    """DOTS leaves are 4-triangle strips and the kernel rejects a strip when the ray passes farther than r (inflated) from
+    the segment axis before running the 4 triangle tests.  The oracle has no such filter: bit-identical hit records from
+    near, far, grazing and inside-the-groom cameras (and from scaled, non-unit wavefront directions) show it never
+    removes a hit."""
+    import torch
+    pos, idx = small_groom
+    W, H = 192, 128
+    yaw = 180.0 if cam[0] > 100 else -90.0
+    vi, pi = V.camera_matrices(position=cam, yaw=yaw, fov=fov, aspect=float(np.float32(W) / np.float32(H)))
+    with V.Scene(pos, idx, technique=V.DOTS, radius=radius) as sc:
+        sc.build()
+        orc = O.OracleScene(pos, idx, technique=2, radius=radius)
+        hg, ig, _ = sc.render(V.make_frame(vi, pi, W, H))
+        ho, io, _ = orc.render(O.make_frame(vi, pi, W, H))
+        assert (ho["flags"] & 1).sum() > 200
+        assert_bit_identical(hg, ho)
+        assert np.array_equal(ig, io)
+        # wavefront rays with directions scaled by 0.25 .. 4 (the reject must not assume |d| = 1)
+        from vkhrt_b200.api import generate_rays
+        st = torch.cuda.current_stream().cuda_stream
+        rays = torch.zeros((W * H, 8), dtype=torch.float32, device="cuda")
+        generate_rays(V.make_frame(vi, pi, W, H, output_memory=V.MEM_DEVICE, stream=st), 0, rays.data_ptr(), 0)
+        scale = torch.tensor([0.25, 1.0, 4.0, 0.5], device="cuda")[torch.arange(W * H, device="cuda") % 4]
+        rays[:, 4:7] *= scale[:, None]
+        dh = torch.zeros((W * H, 32), dtype=torch.uint8, device="cuda")
+        sc.trace_rays(rays.data_ptr(), W * H, dh.data_ptr(), st)
+        torch.cuda.synchronize()
+        ho2 = orc.trace_rays(rays.cpu().numpy())
+        assert np.array_equal(dh.cpu().numpy().reshape(-1), ho2.view(np.uint8).reshape(-1))

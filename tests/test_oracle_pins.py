@@ -289,8 +289,12 @@ def test_lbvh_invariants(O, V, tech):
     pos, idx = V.generate_groom(300, 12, V.GROOM_CURLY)
     sc = O.OracleScene(pos, idx, technique=tech)
     nodes, ids, morton, lohi = sc.bvh()
-    n = sc.n_primitives
+    n = sc.n_leaves
+    assert n == idx.shape[0] and sc.n_primitives == n * (4 if tech == 2 else 1)   # DOTS: one leaf per 4-triangle strip
     boxes = sc.aabbs()
+    if tech == 2:   # strip box = union of its 4 triangle boxes
+        tr = sc.primitives().reshape(n, 12, 3)
+        assert np.array_equal(boxes[:, :3], tr.min(axis=1)) and np.array_equal(boxes[:, 3:], tr.max(axis=1))
     assert nodes.shape[0] == n - 1
     assert np.array_equal(np.sort(ids), np.arange(n, dtype=np.uint32))
     assert (np.diff(morton.astype(np.int64)) >= 0).all()

@@ -92,7 +92,7 @@ int vkhrt_scene_create(const VkhrtSceneDesc* desc, VkhrtScene** out_scene)
     if (desc->technique < VKHRT_TECHNIQUE_PHANTOM || desc->technique > VKHRT_TECHNIQUE_DOTS) { set_last_error("unknown technique"); return VKHRT_ERR_INVALID_ARGUMENT; }
     if ((desc->n_vertices && !desc->positions_xyz) || (desc->n_segments && !desc->line_indices)) { set_last_error("null geometry array"); return VKHRT_ERR_INVALID_ARGUMENT; }
     const uint64_t n_prims = desc->technique == VKHRT_TECHNIQUE_DOTS ? (uint64_t)desc->n_segments * 4 : desc->n_segments;
-    if (n_prims >= 0x7FFFFFFFull) { set_last_error("too many primitives for 31-bit references"); return VKHRT_ERR_UNSUPPORTED; }
+    if (n_prims >= 0xFFFFFFFFull || desc->n_segments >= 0x7FFFFFFFu) { set_last_error("too many primitives for 31-bit references"); return VKHRT_ERR_UNSUPPORTED; }
     int rc = check_device(desc->device);
     if (rc) return rc;
     VK_CUDA(cudaSetDevice(desc->device));
@@ -105,6 +105,7 @@ int vkhrt_scene_create(const VkhrtSceneDesc* desc, VkhrtScene** out_scene)
     sc->n_vertices = desc->n_vertices;
     sc->n_segments = desc->n_segments;
     sc->n_prims = (uint32_t)n_prims;
+    sc->n_leaves = desc->n_segments;
 #define VK_TRY(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { set_last_error(std::string(#call) + ": " + cudaGetErrorString(e_)); free_scene(sc); return e_ == cudaErrorMemoryAllocation ? VKHRT_ERR_OUT_OF_MEMORY : VKHRT_ERR_CUDA; } } while (0)
     cudaDeviceProp prop;
     VK_TRY(cudaGetDeviceProperties(&prop, sc->device));
@@ -162,13 +163,13 @@ int vkhrt_scene_get_bvh(VkhrtScene* scene, VkhrtBvhView* view)
     DeviceScene& sc = scene->s;
     if (!sc.built) { set_last_error("get_bvh before build"); return VKHRT_ERR_NOT_BUILT; }
     VK_CUDA(cudaSetDevice(sc.device));
-    view->n_primitives = sc.n_prims;
+    view->n_primitives = sc.n_leaves;
     view->n_nodes = sc.n_nodes;
     for (int k = 0; k < 3; ++k) { view->scene_lo[k] = sc.scene_lo[k]; view->scene_hi[k] = sc.scene_hi[k]; }
-    if (sc.n_prims == 0) return VKHRT_OK;
+    if (sc.n_leaves == 0) return VKHRT_OK;
     if (view->nodes) VK_CUDA(cudaMemcpy(view->nodes, sc.d_nodes, (size_t)sc.n_nodes * 64, cudaMemcpyDeviceToHost));
-    if (view->sorted_prim_ids) VK_CUDA(cudaMemcpy(view->sorted_prim_ids, sc.d_sorted_ids, (size_t)sc.n_prims * 4, cudaMemcpyDeviceToHost));
-    if (view->sorted_morton) VK_CUDA(cudaMemcpy(view->sorted_morton, sc.d_sorted_morton, (size_t)sc.n_prims * 8, cudaMemcpyDeviceToHost));
+    if (view->sorted_prim_ids) VK_CUDA(cudaMemcpy(view->sorted_prim_ids, sc.d_sorted_ids, (size_t)sc.n_leaves * 4, cudaMemcpyDeviceToHost));
+    if (view->sorted_morton) VK_CUDA(cudaMemcpy(view->sorted_morton, sc.d_sorted_morton, (size_t)sc.n_leaves * 8, cudaMemcpyDeviceToHost));
     return VKHRT_OK;
 }
 

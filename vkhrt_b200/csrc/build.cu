@@ -119,12 +119,20 @@ VK_DEV Aabb tri_box(const TriPrim& t)
     return b;
 }
 
+// box of BVH leaf `leaf`: the primitive's own box, or (DOTS) the union over the 4 triangles of strip `leaf`
 template <int TECH>
-VK_DEV Aabb prim_box(const MeshIn& m, uint32_t prim)
+VK_DEV Aabb leaf_box(const MeshIn& m, uint32_t leaf)
 {
-    if (TECH == VKHRT_TECHNIQUE_PHANTOM) return curve_box(gen_curve(m, prim), m.radius);
-    if (TECH == VKHRT_TECHNIQUE_LSS) return lss_box(gen_lss(m, prim));
-    return tri_box(gen_tri(m, prim));
+    if (TECH == VKHRT_TECHNIQUE_PHANTOM) return curve_box(gen_curve(m, leaf), m.radius);
+    if (TECH == VKHRT_TECHNIQUE_LSS) return lss_box(gen_lss(m, leaf));
+    Aabb b = tri_box(gen_tri(m, 4u * leaf));
+#pragma unroll
+    for (uint32_t k = 1; k < 4; ++k) {
+        Aabb c = tri_box(gen_tri(m, 4u * leaf + k));
+        b.lo = f3(fminf(b.lo.x, c.lo.x), fminf(b.lo.y, c.lo.y), fminf(b.lo.z, c.lo.z));
+        b.hi = f3(fmaxf(b.hi.x, c.hi.x), fmaxf(b.hi.y, c.hi.y), fmaxf(b.hi.z, c.hi.z));
+    }
+    return b;
 }
 
 // order-preserving float <-> uint for atomicMin/Max
@@ -139,7 +147,7 @@ __global__ void __launch_bounds__(256) centroid_kernel(MeshIn m, uint32_t n_prim
     const float inf = __int_as_float(0x7f800000);
     float3 lo = f3(inf, inf, inf), hi = f3(-inf, -inf, -inf);
     if (i < n_prims) {
-        Aabb b = prim_box<TECH>(m, i);
+        Aabb b = leaf_box<TECH>(m, i);
         float3 c = (b.lo + b.hi) * 0.5f;
         centroids[i] = make_float4(c.x, c.y, c.z, 0.0f);
         lo = c; hi = c;
@@ -395,11 +403,17 @@ __global__ void __launch_bounds__(256) materialise_refit_kernel(MeshIn m, uint32
         primA[2 * (size_t)pos] = make_float4(s.p0.x, s.p0.y, s.p0.z, s.r0);
         primA[2 * (size_t)pos + 1] = make_float4(s.p1.x, s.p1.y, s.p1.z, s.r1);
     } else {
-        TriPrim t = gen_tri(m, prim);
-        box = tri_box(t);
-        primA[3 * (size_t)pos] = make_float4(t.v0.x, t.v0.y, t.v0.z, __uint_as_float(prim));
-        primA[3 * (size_t)pos + 1] = make_float4(t.v1.x, t.v1.y, t.v1.z, 0.0f);
-        primA[3 * (size_t)pos + 2] = make_float4(t.v2.x, t.v2.y, t.v2.z, 0.0f);
+        // strip record: the traversal kernel rebuilds the 12 vertices as start/end -+ offset with the very same
+        // single fp32 add/sub gen_tri() performs, so they are bit-identical to the generator's
+        box = leaf_box<TECH>(m, prim);
+        float3 s = load_pos(m, m.idx[2 * prim]), e = load_pos(m, m.idx[2 * prim + 1]);
+        float3 fwd = normalize3(e - s);
+        float3 sv = perp_stark(fwd);
+        float3 off0 = sv * m.radius, off1 = cross3(fwd, sv) * m.radius;
+        primA[4 * (size_t)pos] = make_float4(s.x, s.y, s.z, __uint_as_float(prim));
+        primA[4 * (size_t)pos + 1] = make_float4(e.x, e.y, e.z, 0.0f);
+        primA[4 * (size_t)pos + 2] = make_float4(off0.x, off0.y, off0.z, 0.0f);
+        primA[4 * (size_t)pos + 3] = make_float4(off1.x, off1.y, off1.z, 0.0f);
     }
     if (n_prims == 1) {   // single primitive: node 0 holds the same leaf in both slots
         float* nd = nodes_f32;
@@ -475,12 +489,12 @@ int build_scene(DeviceScene& sc, bool refit_only)
 {
     VK_CUDA(cudaSetDevice(sc.device));
     cudaStream_t st = sc.stream;
-    const uint32_t n = sc.n_prims;
+    const uint32_t n = sc.n_leaves;
     MeshIn m{sc.d_positions, sc.d_indices, sc.d_radius_pv, sc.n_segments, sc.radius};
     sc.timing = VkhrtTiming{};
     if (n == 0) { sc.n_nodes = 0; sc.built = true; return VKHRT_OK; }
     const int tech = sc.technique;
-    const size_t primA_per = tech == VKHRT_TECHNIQUE_DOTS ? 3 : 2;
+    const size_t primA_per = tech == VKHRT_TECHNIQUE_DOTS ? 4 : 2;
 
     cudaEvent_t* ev = sc.ev;
     VK_CUDA(cudaEventRecord(ev[0], st));

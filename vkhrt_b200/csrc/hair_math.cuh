@@ -362,6 +362,32 @@ VK_DEV float3 tri_normal(float3 d, float3 v0, float3 v1, float3 v2)
     return n;
 }
 
+// ---- DOTS strip: the 4 triangles of one segment, rebuilt from the 64-byte strip record --------------
+// GenerateDisjointOrthogonalTriangleStrips (geometry_processor.cpp:221-271): face f in {0,1}, offset off_f = v_f * r,
+//   triangle 2f   = (start+off, end-off, end+off)      triangle 2f+1 = (start+off, start-off, end-off)
+// each vertex is ONE fp32 add/sub of the stored operands, exactly what the generator computes.
+VK_DEV void strip_triangle(float3 s, float3 e, float3 off, uint32_t k, float3* v0, float3* v1, float3* v2)
+{
+    *v0 = s + off;
+    if (k == 0u) { *v1 = e - off; *v2 = e + off; }
+    else         { *v1 = s - off; *v2 = e - off; }
+}
+// Conservative strip reject (NOT in the reference; result-neutral by construction).  Every point of the four
+// triangles is (a point of the segment) + c * off_f with |c| <= 1 and |off_f| = r, so a ray that hits any of them
+// passes within r of the segment's axis LINE: |(start - o) . n| <= r |n| with n = d x (end - start).
+// The bound is inflated by 1 % plus a rounding allowance that grows with the distance of the strip from the ray origin
+// (fp32 barycentrics of a sliver seen from afar accept points slightly outside the triangle).  Parallel ray / NaN: never rejects.
+VK_DEV bool ray_near_strip_axis(float3 o, float3 d, float3 s, float3 e, float radius)
+{
+    float3 a = e - s, so = s - o;
+    float3 n = fcross3(d, a);
+    float lhs = fabsf(fdot3(so, n));
+    float nn = sqrtf(fdot3(n, n));
+    float slack = 1e-5f * ((fabsf(so.x) + fabsf(so.y) + fabsf(so.z)) * (fabsf(a.x) + fabsf(a.y) + fabsf(a.z)));
+    float rhs = fmaf(radius * 1.01f, nn, slack);
+    return !(lhs > rhs);
+}
+
 // ---- primary ray: shaders/ray_gen.rgen:16-24 ------------------------------------------------------
 struct Camera { float vi[16]; float pi[16]; };   // CameraUniformData, column-major
 

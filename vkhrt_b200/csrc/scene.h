@@ -13,6 +13,8 @@ struct DeviceScene {
     int technique = 0;
     float radius = VKHRT_DEFAULT_RADIUS;
     uint32_t n_vertices = 0, n_segments = 0, n_prims = 0, n_nodes = 0;
+    // BVH leaves: one per primitive (PHANTOM, LSS); DOTS: one per STRIP = the 4 triangles of a segment
+    uint32_t n_leaves = 0;
     bool built = false;
 
     // input (Assimp-shaped line mesh)
@@ -22,17 +24,18 @@ struct DeviceScene {
 
     // acceleration structure
     float4* d_nodes = nullptr;         // n_nodes * 4 float4 (VkhrtBvhNode)
-    uint32_t* d_sorted_ids = nullptr;  // n_prims: original primitive id at each Morton-sorted position
+    uint32_t* d_sorted_ids = nullptr;  // n_leaves: original leaf id (segment) at each Morton-sorted position
     uint64_t* d_sorted_morton = nullptr;
     uint32_t* d_parent_internal = nullptr;  // n_nodes: (parent << 1) | slot
-    uint32_t* d_parent_leaf = nullptr;      // n_prims
+    uint32_t* d_parent_leaf = nullptr;      // n_leaves
     uint32_t* d_refit_flags = nullptr;      // n_nodes
     float scene_lo[3] = {0, 0, 0}, scene_hi[3] = {0, 0, 0};
 
     // primitives in Morton-sorted order
     //   PHANTOM: primA[2p] = {B0.xyz, rmax}, primA[2p+1] = {B3.xyz, bits(prim id)}; primB[2p] = {B1.xyz, quarter-chord deviation}, primB[2p+1] = {B2.xyz,0}
     //   LSS:     primA[2p] = {p0.xyz, r0},   primA[2p+1] = {p1.xyz, r1}
-    //   DOTS:    primA[3p] = {v0.xyz, bits(prim id)}, primA[3p+1] = {v1.xyz,0}, primA[3p+2] = {v2.xyz,0}
+    //   DOTS:    one 64-byte strip record per segment: primA[4p] = {start.xyz, bits(segment id)}, primA[4p+1] = {end.xyz, 0},
+    //            primA[4p+2] = {v0*r, 0}, primA[4p+3] = {v1*r, 0}; the 12 strip vertices are start/end -+ these offsets
     float4* d_primA = nullptr;
     float4* d_primB = nullptr;
 

@@ -197,11 +197,21 @@ __global__ void __launch_bounds__(TR_BLOCK, MINB) trace_kernel(const TraceParams
                     if (lss_intersect<false>(o, d, xyz(a0), a0.w, xyz(a1), a1.w, &t, &u, nullptr)) commit(t, u, __ldg(p.sorted_ids + pos), pos);
                     state = ST_POP;
                 } else {
-                    const float4 a0 = __ldg(p.primA + 3 * (size_t)pos), a1 = __ldg(p.primA + 3 * (size_t)pos + 1),
-                                 a2 = __ldg(p.primA + 3 * (size_t)pos + 2);
-                    const uint32_t prim = __float_as_uint(a0.w);
-                    float t, u;
-                    if (tri_intersect(o, d, xyz(a0), xyz(a1), xyz(a2), prim & 1u, &t, &u)) commit(t, u, prim, pos);
+                    // one strip = the 4 triangles of a segment (64-byte record); the cheap axis-distance reject first
+                    const float4* rec = p.primA + 4 * (size_t)pos;
+                    const float4 a0 = __ldg(rec), a1 = __ldg(rec + 1);
+                    if (STATS) st_prims += 3;
+                    if (ray_near_strip_axis(o, d, xyz(a0), xyz(a1), p.radius)) {
+                        const float4 a2 = __ldg(rec + 2), a3 = __ldg(rec + 3);
+                        const uint32_t prim0 = __float_as_uint(a0.w) << 2;
+#pragma unroll 1
+                        for (uint32_t k = 0; k < 4u; ++k) {
+                            float3 v0, v1, v2;
+                            strip_triangle(xyz(a0), xyz(a1), (k & 2u) ? xyz(a3) : xyz(a2), k & 1u, &v0, &v1, &v2);
+                            float t, u;
+                            if (tri_intersect(o, d, v0, v1, v2, k & 1u, &t, &u)) commit(t, u, prim0 + k, pos);
+                        }
+                    }
                     state = ST_POP;
                 }
             }
@@ -243,9 +253,11 @@ __global__ void __launch_bounds__(TR_BLOCK, MINB) trace_kernel(const TraceParams
                         float t, u;
                         lss_intersect<true>(o, d, xyz(a0), a0.w, xyz(a1), a1.w, &t, &u, &n);
                     } else {
-                        const float4 a0 = __ldg(p.primA + 3 * (size_t)best_pos), a1 = __ldg(p.primA + 3 * (size_t)best_pos + 1),
-                                     a2 = __ldg(p.primA + 3 * (size_t)best_pos + 2);
-                        n = tri_normal(d, xyz(a0), xyz(a1), xyz(a2));
+                        const float4* rec = p.primA + 4 * (size_t)best_pos;
+                        const float4 a0 = __ldg(rec), a1 = __ldg(rec + 1), a2 = __ldg(rec + ((best_prim & 2u) ? 3 : 2));
+                        float3 v0, v1, v2;
+                        strip_triangle(xyz(a0), xyz(a1), xyz(a2), best_prim & 1u, &v0, &v1, &v2);
+                        n = tri_normal(d, v0, v1, v2);
                         seg = best_prim >> 2;
                     }
                     store_hit(p, out_idx, tcur, seg, best_u, n, best_prim, FLAG_HIT);
@@ -423,7 +435,7 @@ static void sample_offset(uint32_t s, float* sx, float* sy)
 static void fill_params(const DeviceScene& sc, const VkhrtFrameDesc& f, const Resolved& r, TraceParams& p)
 {
     p.nodes = sc.d_nodes; p.primA = sc.d_primA; p.primB = sc.d_primB; p.sorted_ids = sc.d_sorted_ids;
-    p.n_prims = sc.n_prims; p.radius = sc.radius;
+    p.n_prims = sc.n_leaves; p.radius = sc.radius;
     memcpy(p.cam.vi, f.view_inverse, sizeof(p.cam.vi)); memcpy(p.cam.pi, f.proj_inverse, sizeof(p.cam.pi));
     p.W = r.W; p.H = r.H; p.sx = 0.5f; p.sy = 0.5f; p.tmin = r.tmin; p.tmax = r.tmax;
     p.T = r.T; p.tiles_x = r.tiles_x; p.n_tiles = r.n_tiles; p.tile_first = r.tile_first; p.tile_stride = r.tile_stride; p.compact = r.compact ? 1u : 0u;
@@ -579,7 +591,7 @@ int trace_ray_buffer(DeviceScene& sc, const float* rays_dev, uint64_t n, VkhrtHi
     TraceParams p;
     memset(&p, 0, sizeof(p));
     p.nodes = sc.d_nodes; p.primA = sc.d_primA; p.primB = sc.d_primB; p.sorted_ids = sc.d_sorted_ids;
-    p.n_prims = sc.n_prims; p.radius = sc.radius;
+    p.n_prims = sc.n_leaves; p.radius = sc.radius;
     p.counters = sc.d_counters;
     p.slot_begin = 0; p.hits_mirror = nullptr;
     p.T = 8; p.tiles_x = 1; p.tile_stride = 1;
