@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define VKHRT_ABI_VERSION 1
+#define VKHRT_ABI_VERSION 2
 
 typedef enum VkhrtStatus {
     VKHRT_OK = 0,
@@ -115,7 +115,19 @@ typedef struct VkhrtFrameDesc {
     int32_t  output_memory;         /* VkhrtMemory of hits_out / rgba8_out                         */
     void*    stream;                /* cudaStream_t to run on (device outputs only); NULL => the
                                        scene's own stream                                         */
+    /* secondary rays (not in the reference, whose closest-hit shaders never trace,
+     * shaders/hair_closest_hit.rchit:15-25).  ao_samples > 0: every primary hit spawns ao_samples
+     * ambient-occlusion rays (cosine-weighted about the shading normal, terminate-on-first-hit,
+     * through the same traversal kernel) and the pixel colour is multiplied by the unoccluded
+     * fraction.  Only the image is affected; hit records stay the primary hits. */
+    uint32_t ao_samples;
+    float    ao_distance;           /* <= 0 => VKHRT_DEFAULT_AO_DISTANCE                           */
+    float    ao_bias;               /* origin offset along the normal; <= 0 => 0.25 * radius       */
+    uint32_t reserved0;
 } VkhrtFrameDesc;
+
+#define VKHRT_DEFAULT_AO_DISTANCE 2.0f
+#define VKHRT_AO_T_MIN 1e-4f
 
 /* Per-ray hit record (sample 0 of each pixel).  The reference exports only t and a
  * normal (hitAttributeEXT, shaders/hair_intersection.rint:13,148) and the primitive id
@@ -162,6 +174,7 @@ typedef struct VkhrtTiming {
     float build_total_ms;
     float raygen_ms, trace_ms, shade_ms, render_total_ms;
     float h2d_ms, d2h_ms;
+    float ao_ms;         /* ambient-occlusion passes of sample 0 (0 when ao_samples == 0)          */
 } VkhrtTiming;
 
 /* Per-frame traversal statistics (debug counters; filled only by vkhrt_render_stats). */
@@ -233,6 +246,9 @@ int  vkhrt_shared_buffer_destroy(int device, void* created_ptr);
 /* ray buffer entry: 32 bytes {ox,oy,oz,tmin, dx,dy,dz,tmax} */
 int  vkhrt_generate_rays(const VkhrtFrameDesc* frame, uint32_t sample, float* rays_out_device, int device);
 int  vkhrt_trace_rays(VkhrtScene* scene, const float* rays_device, uint64_t n_rays, VkhrtHit* hits_out_device, void* stream);
+/* same with gl_RayFlagsTerminateOnFirstHitEXT semantics (shadow / occlusion rays): the record is the FIRST accepted hit
+ * in traversal order (deterministic: the order is the oracle's), not the closest one; flags bit0 = occluded */
+int  vkhrt_trace_rays_any_hit(VkhrtScene* scene, const float* rays_device, uint64_t n_rays, VkhrtHit* hits_out_device, void* stream);
 
 /* ---- host helpers: FlyCamera (source/fly_camera.cpp:25-35) + Renderer::UpdateCameraResource -- */
 /* fov in degrees (vertical); yaw/pitch in degrees as FlyCamera (defaults -90, 0) */

@@ -23,7 +23,8 @@ class FrameDesc(C.Structure):
                 ("width", C.c_uint32), ("height", C.c_uint32), ("t_min", C.c_float), ("t_max", C.c_float),
                 ("spp", C.c_uint32), ("shade_mode", C.c_int32), ("miss_rgb", C.c_float * 3),
                 ("tile_size", C.c_uint32), ("tile_first", C.c_uint32), ("tile_stride", C.c_uint32),
-                ("row_major_output", C.c_uint32), ("output_memory", C.c_int32), ("stream", C.c_void_p)]
+                ("row_major_output", C.c_uint32), ("output_memory", C.c_int32), ("stream", C.c_void_p),
+                ("ao_samples", C.c_uint32), ("ao_distance", C.c_float), ("ao_bias", C.c_float), ("reserved0", C.c_uint32)]
 
 
 class TraceStats(C.Structure):
@@ -72,7 +73,8 @@ def lib():
         L.orc_render.restype = C.c_int
         L.orc_render.argtypes = [C.c_void_p, C.POINTER(FrameDesc), C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64,
                                  C.c_int, C.POINTER(TraceStats), C.c_int]
-        L.orc_trace_rays.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, C.c_int, C.c_int]
+        L.orc_trace_rays.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, C.c_int, C.c_int, C.c_int]
+        L.orc_ao_direction.argtypes = [fp, C.c_uint32, C.c_uint32, C.c_uint32, fp]
         L.orc_prhi.restype = C.c_int
         L.orc_prhi.argtypes = [fp, fp, fp, C.c_float, fp, fp, fp]
         L.orc_ray_cylinder.restype = C.c_int
@@ -100,8 +102,10 @@ def max_threads():
 
 
 def make_frame(view_inv, proj_inv, width, height, spp=1, shade_mode=0, miss_rgb=(0.0, 0.0, 0.0),
-               tile_size=0, tile_first=0, tile_stride=0, t_min=0.0, t_max=0.0, row_major_output=0):
+               tile_size=0, tile_first=0, tile_stride=0, t_min=0.0, t_max=0.0, row_major_output=0,
+               ao_samples=0, ao_distance=0.0, ao_bias=0.0):
     f = FrameDesc()
+    f.ao_samples, f.ao_distance, f.ao_bias = int(ao_samples), float(ao_distance), float(ao_bias)
     f.view_inverse[:] = [float(x) for x in np.asarray(view_inv, np.float32).reshape(16)]
     f.proj_inverse[:] = [float(x) for x in np.asarray(proj_inv, np.float32).reshape(16)]
     f.width, f.height, f.spp, f.shade_mode = width, height, spp, shade_mode
@@ -181,10 +185,11 @@ class OracleScene:
         assert rc == 0
         return h, img, (st.as_dict() if stats else None)
 
-    def trace_rays(self, rays, brute=False, n_threads=0):
+    def trace_rays(self, rays, brute=False, n_threads=0, any_hit=False):
+        """any_hit: terminate on the first accepted hit in traversal order (shadow / occlusion rays)"""
         rays = np.ascontiguousarray(rays, np.float32).reshape(-1, 8)
         h = np.zeros(rays.shape[0], HIT_DTYPE)
-        lib().orc_trace_rays(self._h, rays.ctypes.data, rays.shape[0], h.ctypes.data, int(brute), int(n_threads))
+        lib().orc_trace_rays(self._h, rays.ctypes.data, rays.shape[0], h.ctypes.data, int(brute), int(n_threads), int(any_hit))
         return h
 
 
@@ -242,6 +247,12 @@ def curve_point(curve, t):
 def curve_axis(curve, t):
     a = _f(np.asarray(curve).reshape(12)); o = (C.c_float * 3)()
     lib().orc_curve_axis(a[1], t, o)
+    return np.array(list(o), np.float32)
+
+
+def ao_direction(n, pixel, sample, index):
+    a = _f(n); o = (C.c_float * 3)()
+    lib().orc_ao_direction(a[1], pixel, sample, index, o)
     return np.array(list(o), np.float32)
 
 

@@ -59,6 +59,7 @@ int main(void){
         sizeof(VkhrtBvhView), sizeof(VkhrtTiming), sizeof(VkhrtTraceStats));
  printf("%zu %zu %zu %zu %zu %zu\n", offsetof(VkhrtFrameDesc, proj_inverse), offsetof(VkhrtFrameDesc, width), offsetof(VkhrtFrameDesc, spp),
         offsetof(VkhrtFrameDesc, miss_rgb), offsetof(VkhrtFrameDesc, tile_size), offsetof(VkhrtFrameDesc, stream));
+ printf("%zu %zu\n", offsetof(VkhrtFrameDesc, ao_samples), offsetof(VkhrtFrameDesc, ao_bias));
  printf("%zu %zu %zu\n", offsetof(VkhrtSceneDesc, line_indices), offsetof(VkhrtSceneDesc, radius), offsetof(VkhrtSceneDesc, device));
  return 0; }
 """
@@ -71,8 +72,11 @@ int main(void){
     assert sizes == [C.sizeof(api.SceneDesc), C.sizeof(api.FrameDesc), 32, 64, C.sizeof(api.BvhView), C.sizeof(api.Timing), C.sizeof(api.TraceStats)]
     F = api.FrameDesc
     assert [int(x) for x in out[1].split()] == [F.proj_inverse.offset, F.width.offset, F.spp.offset, F.miss_rgb.offset, F.tile_size.offset, F.stream.offset]
+    assert [int(x) for x in out[2].split()] == [F.ao_samples.offset, F.ao_bias.offset]
     S = api.SceneDesc
-    assert [int(x) for x in out[2].split()] == [S.line_indices.offset, S.radius.offset, S.device.offset]
+    assert [int(x) for x in out[3].split()] == [S.line_indices.offset, S.radius.offset, S.device.offset]
+    from oracle import oracle as O
+    assert C.sizeof(O.FrameDesc) == C.sizeof(F) and O.FrameDesc.ao_samples.offset == F.ao_samples.offset
 
 
 def test_header_is_plain_c(V):
@@ -82,7 +86,7 @@ def test_header_is_plain_c(V):
 
 def test_error_strings_and_versions(V):
     L = V.lib()
-    assert L.vkhrt_abi_version() == 1
+    assert L.vkhrt_abi_version() == 2
     assert L.vkhrt_error_string(0) == b"ok"
     for code in range(-7, 0):
         assert L.vkhrt_error_string(code) not in (b"ok", b"unknown status")

@@ -384,3 +384,81 @@ def test_dots_strip_reject_is_result_neutral(V, O, small_groom, cam, radius, fov
         torch.cuda.synchronize()
         ho2 = orc.trace_rays(rays.cpu().numpy())
         assert np.array_equal(dh.cpu().numpy().reshape(-1), ho2.view(np.uint8).reshape(-1))
+
+
+# ---------------------------------------------------------------- secondary rays: AO + any-hit
+@pytest.mark.parametrize("tech", TECHS)
+@pytest.mark.parametrize("spp,ao", [(1, 3), (2, 2)])
+def test_ambient_occlusion_parity(V, O, small_groom, tech, spp, ao):
+    """ao_samples > 0: AO rays are spawned from the primary hit records inside the traversal kernel's refill step and traced
+    terminate-on-first-hit.  Image, hit records and all traversal counters equal the oracle's."""
+    pos, idx = small_groom
+    W, H = 192, 120
+    vi, pi = default_camera(V, W, H)
+    kw = dict(spp=spp, ao_samples=ao, ao_distance=1.5, miss_rgb=(0.1, 0.2, 0.3))
+    with V.Scene(pos, idx, technique=tech) as sc:
+        sc.build()
+        orc = O.OracleScene(pos, idx, technique=tech)
+        hg, ig, sg = sc.render(V.make_frame(vi, pi, W, H, **kw), stats=True)
+        ho, io, so = orc.render(O.make_frame(vi, pi, W, H, **kw), stats=True)
+        assert_bit_identical(hg, ho)
+        assert np.array_equal(ig, io)
+        for k in ("rays", "hits", "nodes_visited", "prims_tested"):
+            assert sg[k] == so[k], k
+        _, i0, _ = sc.render(V.make_frame(vi, pi, W, H, spp=spp, miss_rgb=(0.1, 0.2, 0.3)))
+        hit = (hg["flags"] & 1).astype(bool)
+        assert (ig[hit, :3] <= i0[hit, :3]).all() and (ig[hit, :3] < i0[hit, :3]).mean() > 0.2    # AO darkens, and visibly so
+        h2, i2, _ = sc.render(V.make_frame(vi, pi, W, H, **kw))                                    # non-stats kernels
+        assert h2.tobytes() == hg.tobytes() and np.array_equal(i2, ig)
+
+
+def test_ambient_occlusion_device_outputs_and_shards(V, O, small_groom):
+    """Device output memory + AO: hit records are kept in local HBM for the AO passes and mirrored to the caller's buffer
+    (which is rank 0's frame buffer in the multi-GPU peer mode); sharded row-major frames assemble to the full frame."""
+    import torch
+    pos, idx = small_groom
+    W, H, T, world = 200, 120, 32, 2
+    vi, pi = default_camera(V, W, H)
+    with V.Scene(pos, idx, technique=V.PHANTOM) as sc:
+        sc.build()
+        full_h, full_i, _ = sc.render(V.make_frame(vi, pi, W, H, tile_size=T, ao_samples=2))
+        st = torch.cuda.current_stream().cuda_stream
+        dh = torch.zeros((W * H, 32), dtype=torch.uint8, device="cuda")
+        di = torch.zeros((W * H, 4), dtype=torch.uint8, device="cuda")
+        for r in range(world):
+            f = V.make_frame(vi, pi, W, H, tile_size=T, tile_first=r, tile_stride=world, row_major_output=1, ao_samples=2,
+                             output_memory=V.MEM_DEVICE, stream=st)
+            sc.render_into(f, dh.data_ptr(), di.data_ptr())
+        torch.cuda.synchronize()
+        assert np.array_equal(dh.cpu().numpy().reshape(-1), full_h.view(np.uint8))
+        assert np.array_equal(di.cpu().numpy(), full_i)
+        orc = O.OracleScene(pos, idx, technique=0)
+        ho, io, _ = orc.render(O.make_frame(vi, pi, W, H, ao_samples=2))
+        assert full_h.tobytes() == ho.tobytes() and np.array_equal(full_i, io)
+
+
+@pytest.mark.parametrize("tech", TECHS)
+def test_any_hit_wavefront_rays(V, O, small_groom, tech):
+    """vkhrt_trace_rays_any_hit (terminate on first hit): the accepted hit is the first one in traversal order, which is the
+    oracle's order, so even these order-dependent records are bit-identical."""
+    import torch
+    pos, idx = small_groom
+    rng = np.random.default_rng(11)
+    n = 20000
+    o = (rng.normal(0, 1, (n, 3)) * 6 + (0, 152, 0)).astype(np.float32)
+    tgt = pos[rng.integers(0, pos.shape[0], n)] + rng.normal(0, 0.03, (n, 3))
+    d = tgt - o
+    d = (d / np.linalg.norm(d, axis=1, keepdims=True)).astype(np.float32)
+    rays = np.concatenate([o, np.full((n, 1), 1e-3, np.float32), d, rng.uniform(2, 30, (n, 1)).astype(np.float32)], axis=1)
+    with V.Scene(pos, idx, technique=tech) as sc:
+        sc.build()
+        orc = O.OracleScene(pos, idx, technique=tech)
+        dr = torch.from_numpy(rays).cuda()
+        dh = torch.zeros((n, 32), dtype=torch.uint8, device="cuda")
+        st = torch.cuda.current_stream().cuda_stream
+        for any_hit in (False, True):
+            sc.trace_rays(dr.data_ptr(), n, dh.data_ptr(), st, any_hit=any_hit)
+            torch.cuda.synchronize()
+            ho = orc.trace_rays(rays, any_hit=any_hit)
+            assert (ho["flags"] & 1).sum() > 2000
+            assert np.array_equal(dh.cpu().numpy().reshape(-1), ho.view(np.uint8).reshape(-1)), f"any_hit={any_hit}"

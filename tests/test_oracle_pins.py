@@ -365,3 +365,62 @@ def test_spp_mean_and_unorm8(O, V):
     miss = (h1["flags"] & 1) == 0
     assert (i1[miss] == np.array([51, 102, 153, 255], np.uint8)).all()    # round(c*255)
     assert (i4[:, 3] == 255).all() and not np.array_equal(i1, i4)
+
+
+# ---------------------------------------------------------------- secondary rays: AO + any-hit
+def test_ao_directions_are_unit_cosine_weighted_and_deterministic(O):
+    n = np.array([0.0, 0.6, 0.8], np.float32)
+    d = np.array([O.ao_direction(n, pix, 0, k) for pix in range(400) for k in range(8)], np.float64)
+    assert np.abs(np.linalg.norm(d, axis=1) - 1).max() < 1e-6
+    c = d @ n.astype(np.float64)
+    assert (c >= -1e-6).all()                       # hemisphere about n
+    assert abs(c.mean() - 2.0 / 3.0) < 0.02         # cosine-weighted: E[cos] = 2/3
+    t1 = np.array([1.0, 0.0, 0.0]); t2 = np.cross(n, t1)
+    assert abs((d @ t1).mean()) < 0.03 and abs((d @ t2).mean()) < 0.03      # no tangential bias
+    assert np.array_equal(O.ao_direction(n, 17, 3, 5), O.ao_direction(n, 17, 3, 5))
+    assert not np.array_equal(O.ao_direction(n, 17, 3, 5), O.ao_direction(n, 17, 3, 6))
+    assert not np.array_equal(O.ao_direction(n, 17, 3, 5), O.ao_direction(n, 18, 3, 5))
+
+
+@pytest.mark.parametrize("tech", [0, 1, 2])
+def test_any_hit_rays_agree_with_closest_hit_on_occlusion(O, V, tech):
+    """Terminate-on-first-hit returns SOME accepted hit: it exists iff the closest-hit search finds one, it lies in the
+    ray interval, and it is never closer than the closest hit."""
+    pos, idx = V.generate_groom(200, 8, V.GROOM_CURLY)
+    sc = O.OracleScene(pos, idx, technique=tech)
+    rng = np.random.default_rng(7)
+    n = 3000
+    o = (rng.normal(0, 1, (n, 3)) * 6 + (0, 152, 0)).astype(np.float32)
+    tgt = pos[rng.integers(0, pos.shape[0], n)] + rng.normal(0, 0.03, (n, 3))
+    d = tgt - o
+    d = (d / np.linalg.norm(d, axis=1, keepdims=True)).astype(np.float32)
+    rays = np.concatenate([o, np.full((n, 1), 1e-3, np.float32), d, rng.uniform(2, 30, (n, 1)).astype(np.float32)], axis=1)
+    hc = sc.trace_rays(rays)
+    ha = sc.trace_rays(rays, any_hit=True)
+    occ_c, occ_a = (hc["flags"] & 1).astype(bool), (ha["flags"] & 1).astype(bool)
+    assert occ_c.sum() > 300 and (~occ_c).sum() > 50
+    assert np.array_equal(occ_c, occ_a)
+    assert (ha["t"][occ_a] >= hc["t"][occ_a]).all() and (ha["t"][occ_a] <= rays[occ_a, 7]).all()
+    assert (ha["t"][occ_a] == hc["t"][occ_a]).mean() > 0.5      # nearest-first order usually finds the closest one first
+
+
+def test_ao_image_is_the_base_image_times_visibility(O, V):
+    pos, idx = V.generate_groom(400, 12, V.GROOM_CURLY)
+    sc = O.OracleScene(pos, idx, technique=1)
+    W, H = 64, 48
+    vi, pi = V.camera_matrices(aspect=W / H)
+    h0, i0, s0 = sc.render(O.make_frame(vi, pi, W, H, miss_rgb=(0.1, 0.2, 0.3)), stats=True)
+    h1, i1, s1 = sc.render(O.make_frame(vi, pi, W, H, miss_rgb=(0.1, 0.2, 0.3), ao_samples=4), stats=True)
+    assert h0.tobytes() == h1.tobytes()                              # hit records stay the primary hits
+    hit = (h0["flags"] & 1).astype(bool)
+    assert hit.sum() > 200
+    assert np.array_equal(i0[~hit], i1[~hit])                        # miss pixels untouched
+    assert (i1[hit, :3] <= i0[hit, :3]).all() and (i1[hit, :3] < i0[hit, :3]).any() and (i1[:, 3] == i0[:, 3]).all()
+    assert s1["rays"] == s0["rays"] + 4 * hit.sum()
+    # every AO pixel value is one of the 5 possible visibilities times the base colour
+    base = np.float32(0.3) + np.abs(h0["ny"][hit])[:, None] * np.float32([0.4, 0.2, 0.1])
+    levels = np.stack([np.clip(base * np.float32(1 - k / 4), 0, 1) * 255 + 0.5 for k in range(5)]).astype(np.uint8)   # [5, n, 3]
+    assert (levels == i1[hit, :3][None]).all(axis=2).any(axis=0).all()
+    # ao_distance -> 0: nothing is occluded
+    _, i2, _ = sc.render(O.make_frame(vi, pi, W, H, miss_rgb=(0.1, 0.2, 0.3), ao_samples=4, ao_distance=1e-3))
+    assert np.array_equal(i2, i0)

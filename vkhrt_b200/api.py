@@ -48,7 +48,8 @@ class FrameDesc(C.Structure):
                 ("width", C.c_uint32), ("height", C.c_uint32), ("t_min", C.c_float), ("t_max", C.c_float),
                 ("spp", C.c_uint32), ("shade_mode", C.c_int32), ("miss_rgb", C.c_float * 3),
                 ("tile_size", C.c_uint32), ("tile_first", C.c_uint32), ("tile_stride", C.c_uint32),
-                ("row_major_output", C.c_uint32), ("output_memory", C.c_int32), ("stream", C.c_void_p)]
+                ("row_major_output", C.c_uint32), ("output_memory", C.c_int32), ("stream", C.c_void_p),
+                ("ao_samples", C.c_uint32), ("ao_distance", C.c_float), ("ao_bias", C.c_float), ("reserved0", C.c_uint32)]
 
 
 class BvhView(C.Structure):
@@ -60,7 +61,7 @@ class BvhView(C.Structure):
 class Timing(C.Structure):
     _fields_ = [(k, C.c_float) for k in ("geometry_ms", "morton_ms", "sort_ms", "hierarchy_ms", "refit_ms",
                                          "build_total_ms", "raygen_ms", "trace_ms", "shade_ms",
-                                         "render_total_ms", "h2d_ms", "d2h_ms")]
+                                         "render_total_ms", "h2d_ms", "d2h_ms", "ao_ms")]
 
     def as_dict(self):
         return {k: float(getattr(self, k)) for k, _ in self._fields_}
@@ -84,7 +85,7 @@ ABI_SYMBOLS = [
     "vkhrt_scene_create", "vkhrt_scene_build", "vkhrt_scene_refit", "vkhrt_scene_get_bvh",
     "vkhrt_scene_get_primitives", "vkhrt_scene_primitive_count", "vkhrt_scene_destroy",
     "vkhrt_render", "vkhrt_render_stats", "vkhrt_frame_local_pixels", "vkhrt_untile", "vkhrt_last_timing",
-    "vkhrt_generate_rays", "vkhrt_trace_rays", "vkhrt_camera_matrices", "vkhrt_groom_generate",
+    "vkhrt_generate_rays", "vkhrt_trace_rays", "vkhrt_trace_rays_any_hit", "vkhrt_camera_matrices", "vkhrt_groom_generate",
     "vkhrt_shared_buffer_create", "vkhrt_shared_buffer_open", "vkhrt_shared_buffer_close", "vkhrt_shared_buffer_destroy",
 ]
 
@@ -127,6 +128,7 @@ def lib():
     L.vkhrt_last_timing.argtypes = [C.c_void_p, C.POINTER(Timing)]
     L.vkhrt_generate_rays.argtypes = [C.POINTER(FrameDesc), C.c_uint32, C.c_void_p, C.c_int]
     L.vkhrt_trace_rays.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p]
+    L.vkhrt_trace_rays_any_hit.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p]
     L.vkhrt_camera_matrices.restype = None
     L.vkhrt_camera_matrices.argtypes = [C.POINTER(C.c_float), C.c_float, C.c_float, C.c_float, C.c_float, C.c_float,
                                         C.c_float, C.POINTER(C.c_float), C.POINTER(C.c_float)]
@@ -135,7 +137,7 @@ def lib():
     L.vkhrt_shared_buffer_open.argtypes = [C.c_int, C.c_char_p, C.POINTER(C.c_void_p)]
     L.vkhrt_shared_buffer_close.argtypes = [C.c_int, C.c_void_p]
     L.vkhrt_shared_buffer_destroy.argtypes = [C.c_int, C.c_void_p]
-    if L.vkhrt_abi_version() != 1:
+    if L.vkhrt_abi_version() != 2:
         raise ImportError("libvkhrt_b200.so ABI version mismatch")
     _lib = L
     return L
@@ -182,8 +184,10 @@ def generate_groom(n_strands, segments, style=GROOM_CURLY, seed=DEFAULT_SEED):
 
 
 def make_frame(view_inv, proj_inv, width, height, spp=1, shade_mode=SHADE, miss_rgb=(0.0, 0.0, 0.0), tile_size=0,
-               tile_first=0, tile_stride=0, t_min=0.0, t_max=0.0, output_memory=MEM_HOST, stream=None, row_major_output=0):
+               tile_first=0, tile_stride=0, t_min=0.0, t_max=0.0, output_memory=MEM_HOST, stream=None, row_major_output=0,
+               ao_samples=0, ao_distance=0.0, ao_bias=0.0):
     f = FrameDesc()
+    f.ao_samples, f.ao_distance, f.ao_bias = int(ao_samples), float(ao_distance), float(ao_bias)
     f.view_inverse[:] = [float(x) for x in np.asarray(view_inv, np.float32).reshape(16)]
     f.proj_inverse[:] = [float(x) for x in np.asarray(proj_inv, np.float32).reshape(16)]
     f.width, f.height, f.spp, f.shade_mode = int(width), int(height), int(spp), int(shade_mode)
@@ -287,8 +291,12 @@ class Scene:
         _check(lib().vkhrt_render_stats(self._h, C.byref(frame), hits_ptr, rgba_ptr, C.byref(st)), "vkhrt_render_stats")
         return st.as_dict()
 
-    def trace_rays(self, rays_ptr, n_rays, hits_ptr, stream=None):
-        _check(lib().vkhrt_trace_rays(self._h, rays_ptr, n_rays, hits_ptr, stream), "vkhrt_trace_rays")
+    def trace_rays(self, rays_ptr, n_rays, hits_ptr, stream=None, any_hit=False):
+        """Wavefront trace of a device ray buffer; any_hit = terminate on the first accepted hit (occlusion rays)."""
+        if any_hit:
+            _check(lib().vkhrt_trace_rays_any_hit(self._h, rays_ptr, n_rays, hits_ptr, stream), "vkhrt_trace_rays_any_hit")
+        else:
+            _check(lib().vkhrt_trace_rays(self._h, rays_ptr, n_rays, hits_ptr, stream), "vkhrt_trace_rays")
 
     def timing(self):
         t = Timing()

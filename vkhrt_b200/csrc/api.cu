@@ -42,7 +42,7 @@ static void free_scene(DeviceScene* sc)
     cudaFree(sc->d_nodes); cudaFree(sc->d_sorted_ids); cudaFree(sc->d_sorted_morton);
     cudaFree(sc->d_parent_internal); cudaFree(sc->d_parent_leaf); cudaFree(sc->d_refit_flags);
     cudaFree(sc->d_primA); cudaFree(sc->d_primB);
-    cudaFree(sc->d_counters); cudaFree(sc->d_hits_scratch); cudaFree(sc->d_accum); cudaFree(sc->d_rgba_scratch);
+    cudaFree(sc->d_counters); cudaFree(sc->d_hits_scratch); cudaFree(sc->d_accum); cudaFree(sc->d_rgba_scratch); cudaFree(sc->d_occluded);
     if (sc->h_pinned) cudaFreeHost(sc->h_pinned);
     for (auto& e : sc->ev) if (e) cudaEventDestroy(e);
     if (sc->stream) cudaStreamDestroy(sc->stream);
@@ -218,7 +218,8 @@ int vkhrt_last_timing(const VkhrtScene* scene, VkhrtTiming* timing)
     if (cudaEventSynchronize(sc.ev[11]) == cudaSuccess) {
         float ms = 0;
         if (cudaEventElapsedTime(&ms, sc.ev[7], sc.ev[8]) == cudaSuccess) timing->trace_ms = ms;
-        if (cudaEventElapsedTime(&ms, sc.ev[8], sc.ev[9]) == cudaSuccess) timing->shade_ms = ms;
+        if (cudaEventElapsedTime(&ms, sc.ev[8], sc.ev[12]) == cudaSuccess) timing->ao_ms = ms;
+        if (cudaEventElapsedTime(&ms, sc.ev[12], sc.ev[9]) == cudaSuccess) timing->shade_ms = ms;
         if (cudaEventElapsedTime(&ms, sc.ev[6], sc.ev[10]) == cudaSuccess) timing->render_total_ms = ms;
         if (cudaEventElapsedTime(&ms, sc.ev[10], sc.ev[11]) == cudaSuccess) timing->d2h_ms = ms;
     }
@@ -289,7 +290,14 @@ int vkhrt_trace_rays(VkhrtScene* scene, const float* rays_device, uint64_t n_ray
 {
     if (!scene || (n_rays && (!rays_device || !hits_out_device))) { set_last_error("null argument"); return VKHRT_ERR_INVALID_ARGUMENT; }
     if (!scene->s.built) { set_last_error("trace before build"); return VKHRT_ERR_NOT_BUILT; }
-    return trace_ray_buffer(scene->s, rays_device, n_rays, hits_out_device, (cudaStream_t)stream);
+    return trace_ray_buffer(scene->s, rays_device, n_rays, hits_out_device, false, (cudaStream_t)stream);
+}
+
+int vkhrt_trace_rays_any_hit(VkhrtScene* scene, const float* rays_device, uint64_t n_rays, VkhrtHit* hits_out_device, void* stream)
+{
+    if (!scene || (n_rays && (!rays_device || !hits_out_device))) { set_last_error("null argument"); return VKHRT_ERR_INVALID_ARGUMENT; }
+    if (!scene->s.built) { set_last_error("trace before build"); return VKHRT_ERR_NOT_BUILT; }
+    return trace_ray_buffer(scene->s, rays_device, n_rays, hits_out_device, true, (cudaStream_t)stream);
 }
 
 }  // extern "C"

@@ -408,6 +408,35 @@ VK_DEV void primary_ray(const Camera& cam, uint32_t W, uint32_t H, uint32_t px, 
     d->z = fmaf(cam.vi[10], nd.z, fmaf(cam.vi[6], nd.y, cam.vi[2] * nd.x));
 }
 
+// ---- ambient-occlusion rays (NOT in the reference: the SURVEY.md §8(f) "secondary rays" row) ------
+// One AO ray per (pixel, spp sample, ao index): origin = hit point pushed `bias` along the shading normal,
+// direction = normalize(n + s) with s uniform on the unit sphere (cosine-weighted about n).  s comes from
+// Marsaglia's 1972 rejection construction driven by an integer hash, so the whole thing needs only + * sqrt and is
+// bit-identical on the CPU oracle and here (no sin/cos).
+VK_DEV uint32_t hash32(uint32_t h)
+{
+    h ^= h >> 16; h *= 0x7feb352du; h ^= h >> 15; h *= 0x846ca68bu; h ^= h >> 16;
+    return h;
+}
+VK_DEV float hash_unit(uint32_t h) { return (float)(h >> 8) * (1.0f / 16777216.0f); }   // [0,1), exact
+VK_DEV float3 ao_direction(float3 n, uint32_t pixel, uint32_t sample, uint32_t index)
+{
+    uint32_t seed = hash32(pixel * 0x9E3779B1u + sample * 0x85EBCA77u + index * 0xC2B2AE3Du + 0x27D4EB2Fu);
+    float x1 = 0.0f, x2 = 0.0f, S = 2.0f;
+    for (uint32_t j = 0; j < 8u && !(S < 1.0f); ++j) {
+        uint32_t a = hash32(seed + j * 0x9E3779B9u), b = hash32(a ^ 0x68E31DA4u);
+        x1 = fmaf(2.0f, hash_unit(a), -1.0f);
+        x2 = fmaf(2.0f, hash_unit(b), -1.0f);
+        S = fmaf(x1, x1, x2 * x2);
+    }
+    if (!(S < 1.0f)) { x1 = 0.0f; x2 = 0.0f; S = 0.0f; }     // 8 rejections in a row (p ~ 4e-6): the pole
+    float q = 2.0f * sqrtf(1.0f - S);
+    float3 v = f3(fmaf(x1, q, n.x), fmaf(x2, q, n.y), fmaf(-2.0f, S, 1.0f) + n.z);
+    float l2 = fdot3(v, v);
+    if (!(l2 > 1e-8f)) return n;                             // s = -n
+    return v * (1.0f / sqrtf(l2));
+}
+
 // ---- ray/box slab test in the fused form t = fma(plane, 1/d, -(o/d)) ------------------------------
 // A zero direction component would make o*(1/d) infinite and the fused slab NaN: |1/d| is clamped to 1e20,
 // for which the slab degenerates to the exact "is o inside [lo,hi]" test.

@@ -43,6 +43,7 @@ struct DeviceScene {
     unsigned long long* d_counters = nullptr;   // [0] work counter, [1..5] stats
     VkhrtHit* d_hits_scratch = nullptr; size_t hits_scratch_n = 0;
     float4* d_accum = nullptr; size_t accum_n = 0;
+    uint32_t* d_occluded = nullptr; size_t occluded_n = 0;   // per pixel: occluded AO rays of the current sample
     uint8_t* d_rgba_scratch = nullptr; size_t rgba_scratch_n = 0;
     void* h_pinned = nullptr; size_t h_pinned_bytes = 0;   // staging for host outputs
 
@@ -72,7 +73,7 @@ int export_primitives(DeviceScene& sc, float* host_out, size_t out_floats);
 // trace.cu
 struct FrameParams;
 int render_frame(DeviceScene& sc, const VkhrtFrameDesc& f, VkhrtHit* hits_out, uint8_t* rgba_out, VkhrtTraceStats* stats);
-int trace_ray_buffer(DeviceScene& sc, const float* rays_dev, uint64_t n, VkhrtHit* hits_dev, cudaStream_t stream);
+int trace_ray_buffer(DeviceScene& sc, const float* rays_dev, uint64_t n, VkhrtHit* hits_dev, bool any_hit, cudaStream_t stream);
 int generate_ray_buffer(const VkhrtFrameDesc& f, uint32_t sample, float* rays_dev, cudaStream_t stream);
 int untile_buffer(const VkhrtFrameDesc& f, uint32_t world, const void* gathered, void* row_major, uint32_t elem_bytes,
                   cudaStream_t stream);

@@ -34,6 +34,11 @@ struct TraceParams {
     uint32_t W, H;
     float sx, sy, tmin, tmax;
     uint32_t T, tiles_x, n_tiles, tile_first, tile_stride, compact;
+    // ambient-occlusion mode (SRC_AO): rays are generated from the primary hit records
+    const VkhrtHit* ao_hits;        // indexed like `hits`
+    uint32_t* ao_occluded;          // per pixel: += 1 for every occluded AO ray (zeroed by the host before the passes)
+    uint32_t ao_index, ao_sample;   // which AO ray of the pixel / which spp sample (seeds of the direction hash)
+    float ao_distance, ao_bias;
     // wavefront mode
     const float4* rays;
     uint32_t slot_begin, n_slots;   // this launch traces slots [slot_begin, n_slots)
@@ -90,10 +95,16 @@ VK_DEV void store_hit(const TraceParams& p, size_t i, float t, uint32_t seg, flo
 // scheduled for SIMD occupancy.  Justification by ncu counters: DESIGN.md §6.
 // ------------------------------------------------------------------------------------------------
 enum : uint32_t { ST_NODE = 0, ST_POP = 1, ST_LEAF = 2, ST_MARCH = 3, ST_REFILL = 4, ST_DONE = 5 };   // NODE|POP are scheduled together
+// where a lane's next ray comes from
+enum : int { SRC_PRIMARY = 0,   // generated from the camera (ray_gen.rgen), fused into the refill step
+             SRC_BUFFER = 1,    // wavefront ray buffer
+             SRC_AO = 2 };      // ambient-occlusion ray spawned from the pixel's primary hit record
 
-template <int TECH, bool STATS, bool WAVEFRONT, int MINB>
+// ANYHIT: gl_RayFlagsTerminateOnFirstHitEXT — the ray retires on its first accepted hit (shadow / occlusion rays).
+template <int TECH, bool STATS, int SRC, bool ANYHIT, int MINB>
 __global__ void __launch_bounds__(TR_BLOCK, MINB) trace_kernel(const TraceParams p)
 {
+    constexpr bool WAVEFRONT = SRC == SRC_BUFFER;
     __shared__ uint2 s_stack[TR_STACK][TR_BLOCK];
     uint2 spill[TR_SPILL];
     const unsigned FULL = 0xffffffffu;
@@ -195,7 +206,7 @@ __global__ void __launch_bounds__(TR_BLOCK, MINB) trace_kernel(const TraceParams
                     const float4 a0 = __ldg(p.primA + 2 * (size_t)pos), a1 = __ldg(p.primA + 2 * (size_t)pos + 1);
                     float t, u;
                     if (lss_intersect<false>(o, d, xyz(a0), a0.w, xyz(a1), a1.w, &t, &u, nullptr)) commit(t, u, __ldg(p.sorted_ids + pos), pos);
-                    state = ST_POP;
+                    state = (ANYHIT && best_prim != PRIM_NONE) ? ST_REFILL : ST_POP;
                 } else {
                     // one strip = the 4 triangles of a segment (64-byte record); the cheap axis-distance reject first
                     const float4* rec = p.primA + 4 * (size_t)pos;
@@ -210,9 +221,10 @@ __global__ void __launch_bounds__(TR_BLOCK, MINB) trace_kernel(const TraceParams
                             strip_triangle(xyz(a0), xyz(a1), (k & 2u) ? xyz(a3) : xyz(a2), k & 1u, &v0, &v1, &v2);
                             float t, u;
                             if (tri_intersect(o, d, v0, v1, v2, k & 1u, &t, &u)) commit(t, u, prim0 + k, pos);
+                            if (ANYHIT && best_prim != PRIM_NONE) break;
                         }
                     }
-                    state = ST_POP;
+                    state = (ANYHIT && best_prim != PRIM_NONE) ? ST_REFILL : ST_POP;
                 }
             }
         } else if (PH && pick == ST_MARCH) {
@@ -227,7 +239,7 @@ __global__ void __launch_bounds__(TR_BLOCK, MINB) trace_kernel(const TraceParams
                     if (r != MARCH_CONTINUE) {
                         // hair_intersection.rint:146-148: report only tHit > 0
                         if (r == MARCH_HIT && t > 0.0f) commit(t, u, __float_as_uint(__ldg(p.primA + 2 * (size_t)mpos + 1).w), mpos);
-                        state = ST_POP;
+                        state = (ANYHIT && best_prim != PRIM_NONE) ? ST_REFILL : ST_POP;
                     }
                 }
                 n1 = __popc(__ballot_sync(FULL, state == ST_MARCH));
@@ -238,7 +250,10 @@ __global__ void __launch_bounds__(TR_BLOCK, MINB) trace_kernel(const TraceParams
             if (STATS) { sc_steps[3]++; sc_lanes[3] += nR; }
             if (want && have_ray) {
                 have_ray = false;
-                if (best_prim != PRIM_NONE) {
+                if (SRC == SRC_AO) {
+                    // one owner per pixel and pass: a plain read-modify-write is enough
+                    if (best_prim != PRIM_NONE) { p.ao_occluded[out_idx] += 1u; if (STATS) st_hits++; }
+                } else if (best_prim != PRIM_NONE) {
                     float3 n;
                     uint32_t seg = best_prim;
                     if (PH) {
@@ -281,6 +296,23 @@ __global__ void __launch_bounds__(TR_BLOCK, MINB) trace_kernel(const TraceParams
                         const float4 r0 = __ldg(p.rays + 2 * (size_t)slot), r1 = __ldg(p.rays + 2 * (size_t)slot + 1);
                         o = f3(r0.x, r0.y, r0.z); tmin = r0.w; d = f3(r1.x, r1.y, r1.z); tcur = r1.w;
                         out_idx = slot;
+                    } else if (SRC == SRC_AO) {
+                        const PixelRef q = slot_to_pixel(p, slot);
+                        valid = q.valid;
+                        out_idx = q.out;
+                        if (valid) {
+                            const float4* h = reinterpret_cast<const float4*>(p.ao_hits + q.out);
+                            const float4 h0 = __ldg(h), h1 = __ldg(h + 1);
+                            valid = (__float_as_uint(h1.w) & FLAG_HIT) != 0u;     // a miss pixel spawns nothing
+                            if (valid) {
+                                float3 po, pd;
+                                primary_ray(p.cam, p.W, p.H, q.px, q.py, p.sx, p.sy, &po, &pd);
+                                const float3 n = f3(h0.w, h1.x, h1.y);
+                                o = fmadd3(p.ao_bias, n, fmadd3(h0.x, pd, po));
+                                d = ao_direction(n, q.py * p.W + q.px, p.ao_sample, p.ao_index);
+                                tmin = VKHRT_AO_T_MIN; tcur = p.ao_distance;
+                            }
+                        }
                     } else {
                         const PixelRef q = slot_to_pixel(p, slot);
                         valid = q.valid;
@@ -345,7 +377,8 @@ __global__ void __launch_bounds__(256) raygen_kernel(const TraceParams p, float4
 // One thread per ray slot of this shard (same slot -> pixel map as the traversal kernel), so that a shard only
 // ever touches the pixels it owns whatever the output layout is.
 __global__ void __launch_bounds__(256) shade_kernel(const TraceParams p, const VkhrtHit* __restrict__ hits, int mode, float3 miss,
-                                                    float4* __restrict__ accum, uchar4* __restrict__ rgba, uint32_t sample, uint32_t spp)
+                                                    float4* __restrict__ accum, uchar4* __restrict__ rgba, uint32_t sample, uint32_t spp,
+                                                    const uint32_t* __restrict__ occluded, uint32_t ao_samples)
 {
     const unsigned long long slot64 = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (slot64 >= p.n_slots) return;
@@ -359,8 +392,10 @@ __global__ void __launch_bounds__(256) shade_kernel(const TraceParams p, const V
     const float4 h0 = h[0], h1 = h[1];
     const uint32_t flags = __float_as_uint(h1.w);
     float3 c;
-    if (flags & FLAG_HIT) c = mode == VKHRT_SHADE_DEBUG_PRIMID ? debug_palette(__float_as_uint(h1.z)) : shade_normal(f3(h0.w, h1.x, h1.y));
-    else c = miss;
+    if (flags & FLAG_HIT) {
+        c = mode == VKHRT_SHADE_DEBUG_PRIMID ? debug_palette(__float_as_uint(h1.z)) : shade_normal(f3(h0.w, h1.x, h1.y));
+        if (ao_samples) c = c * (1.0f - (float)occluded[i] / (float)ao_samples);    // unoccluded fraction of the AO rays
+    } else c = miss;
     if (spp > 1) {
         float4 a = sample == 0 ? make_float4(0, 0, 0, 0) : accum[i];
         a.x += c.x; a.y += c.y; a.z += c.z;
@@ -440,6 +475,7 @@ static void fill_params(const DeviceScene& sc, const VkhrtFrameDesc& f, const Re
     p.W = r.W; p.H = r.H; p.sx = 0.5f; p.sy = 0.5f; p.tmin = r.tmin; p.tmax = r.tmax;
     p.T = r.T; p.tiles_x = r.tiles_x; p.n_tiles = r.n_tiles; p.tile_first = r.tile_first; p.tile_stride = r.tile_stride; p.compact = r.compact ? 1u : 0u;
     p.rays = nullptr; p.slot_begin = 0; p.n_slots = (uint32_t)r.n_slots; p.hits = nullptr; p.hits_mirror = nullptr; p.counters = sc.d_counters;
+    p.ao_hits = nullptr; p.ao_occluded = nullptr; p.ao_index = p.ao_sample = 0u; p.ao_distance = 0.0f; p.ao_bias = 0.0f;
 }
 
 // scheduler tunables (defaults from the sweep in profiles/; overridable for experiments)
@@ -459,31 +495,31 @@ static void tunables(TraceParams& p)
     p.w_node = (uint32_t)g_w_node; p.w_leaf = (uint32_t)g_w_leaf; p.w_march = (uint32_t)g_w_march;
 }
 
-template <int TECH, bool STATS, bool WAVEFRONT, int MINB>
+template <int TECH, bool STATS, int SRC, bool ANYHIT, int MINB>
 static int launch_trace_t(const DeviceScene& sc, TraceParams& p, cudaStream_t st)
 {
     int per_sm = 0;
-    VK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, trace_kernel<TECH, STATS, WAVEFRONT, MINB>, TR_BLOCK, 0));
+    VK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, trace_kernel<TECH, STATS, SRC, ANYHIT, MINB>, TR_BLOCK, 0));
     if (per_sm < 1) per_sm = 1;
     tunables(p);
     if (g_blocks_per_sm > 0) per_sm = std::min(per_sm, g_blocks_per_sm);
     unsigned long long want = ((unsigned long long)(p.n_slots - p.slot_begin) + TR_BLOCK - 1) / TR_BLOCK;
     unsigned grid = (unsigned)std::min<unsigned long long>((unsigned long long)sc.sm_count * per_sm, std::max<unsigned long long>(want, 1ull));
-    trace_kernel<TECH, STATS, WAVEFRONT, MINB><<<grid, TR_BLOCK, 0, st>>>(p);
+    trace_kernel<TECH, STATS, SRC, ANYHIT, MINB><<<grid, TR_BLOCK, 0, st>>>(p);
     count_launch();
     return VKHRT_OK;
 }
-template <bool STATS, bool WAVEFRONT>
+template <bool STATS, int SRC, bool ANYHIT>
 static int launch_trace(const DeviceScene& sc, TraceParams& p, cudaStream_t st)
 {
     tunables(p);
     switch (sc.technique) {
     case VKHRT_TECHNIQUE_PHANTOM:
-        if (!STATS && !WAVEFRONT && g_min_blocks == 7) return launch_trace_t<VKHRT_TECHNIQUE_PHANTOM, false, false, 7>(sc, p, st);
-        if (!STATS && !WAVEFRONT && g_min_blocks == 8) return launch_trace_t<VKHRT_TECHNIQUE_PHANTOM, false, false, 8>(sc, p, st);
-        return launch_trace_t<VKHRT_TECHNIQUE_PHANTOM, STATS, WAVEFRONT, TR_MIN_BLOCKS>(sc, p, st);
-    case VKHRT_TECHNIQUE_LSS: return launch_trace_t<VKHRT_TECHNIQUE_LSS, STATS, WAVEFRONT, TR_MIN_BLOCKS>(sc, p, st);
-    default: return launch_trace_t<VKHRT_TECHNIQUE_DOTS, STATS, WAVEFRONT, TR_MIN_BLOCKS>(sc, p, st);
+        if (!STATS && SRC == SRC_PRIMARY && g_min_blocks == 7) return launch_trace_t<VKHRT_TECHNIQUE_PHANTOM, false, SRC_PRIMARY, false, 7>(sc, p, st);
+        if (!STATS && SRC == SRC_PRIMARY && g_min_blocks == 8) return launch_trace_t<VKHRT_TECHNIQUE_PHANTOM, false, SRC_PRIMARY, false, 8>(sc, p, st);
+        return launch_trace_t<VKHRT_TECHNIQUE_PHANTOM, STATS, SRC, ANYHIT, TR_MIN_BLOCKS>(sc, p, st);
+    case VKHRT_TECHNIQUE_LSS: return launch_trace_t<VKHRT_TECHNIQUE_LSS, STATS, SRC, ANYHIT, TR_MIN_BLOCKS>(sc, p, st);
+    default: return launch_trace_t<VKHRT_TECHNIQUE_DOTS, STATS, SRC, ANYHIT, TR_MIN_BLOCKS>(sc, p, st);
     }
 }
 
@@ -516,7 +552,11 @@ int render_frame(DeviceScene& sc, const VkhrtFrameDesc& f, VkhrtHit* hits_out, u
     const bool want_rgba = rgba_out != nullptr;
     const bool want_hits = hits_out != nullptr;
     const bool multi = r.spp > 1 && want_rgba;
-    const bool direct_hits = !host_out && want_hits;
+    const uint32_t ao = want_rgba ? f.ao_samples : 0u;     // AO only changes the image
+    // with AO the passes re-read the primary hit records: keep them in this GPU's HBM and mirror them to the caller's
+    // buffer (which may be a peer GPU's frame buffer, row_major_output) instead of reading them back over NVLink
+    const bool direct_hits = !host_out && want_hits && ao == 0u;
+    VkhrtHit* d_hits_mirror = (!host_out && want_hits && ao != 0u) ? hits_out : nullptr;
     bool direct_to_host = false;
     VkhrtHit* d_hits0 = nullptr;
     VkhrtHit* d_hits_other = nullptr;
@@ -541,6 +581,7 @@ int render_frame(DeviceScene& sc, const VkhrtFrameDesc& f, VkhrtHit* hits_out, u
         if (host_out) { if ((rc = grow(&sc.d_rgba_scratch, &sc.rgba_scratch_n, (size_t)r.n_out * 4))) return rc; d_rgba = sc.d_rgba_scratch; }
         else d_rgba = rgba_out;
         if (multi) { if ((rc = grow(&sc.d_accum, &sc.accum_n, (size_t)r.n_out))) return rc; }
+        if (ao) { if ((rc = grow(&sc.d_occluded, &sc.occluded_n, (size_t)r.n_out))) return rc; }
     }
 
     TraceParams p;
@@ -554,14 +595,32 @@ int render_frame(DeviceScene& sc, const VkhrtFrameDesc& f, VkhrtHit* hits_out, u
     for (uint32_t s = 0; s < n_samples; ++s) {
         sample_offset(s, &p.sx, &p.sy);
         p.hits = s == 0 ? d_hits0 : d_hits_other;
-        p.hits_mirror = s == 0 ? h_hits_mapped : nullptr;
+        p.hits_mirror = s == 0 ? (h_hits_mapped ? h_hits_mapped : d_hits_mirror) : nullptr;
         VK_CUDA(cudaMemsetAsync(sc.d_counters, 0, sizeof(unsigned long long), st));
         if (s == 0) VK_CUDA(cudaEventRecord(ev[7], st));
-        rc = stats ? launch_trace<true, false>(sc, p, st) : launch_trace<false, false>(sc, p, st);
+        rc = stats ? launch_trace<true, SRC_PRIMARY, false>(sc, p, st) : launch_trace<false, SRC_PRIMARY, false>(sc, p, st);
         if (rc) return rc;
         if (s == 0) VK_CUDA(cudaEventRecord(ev[8], st));
+        if (ao) {
+            // secondary rays: ao passes of one occlusion ray per hit pixel, spawned from the hit records inside the
+            // traversal kernel's refill step (no ray buffer), terminate-on-first-hit
+            VK_CUDA(cudaMemsetAsync(sc.d_occluded, 0, (size_t)r.n_out * sizeof(uint32_t), st));
+            TraceParams q = p;
+            q.ao_hits = p.hits; q.ao_occluded = sc.d_occluded; q.ao_sample = s;
+            q.ao_distance = f.ao_distance > 0.0f ? f.ao_distance : VKHRT_DEFAULT_AO_DISTANCE;
+            q.ao_bias = f.ao_bias > 0.0f ? f.ao_bias : 0.25f * sc.radius;
+            q.hits = nullptr; q.hits_mirror = nullptr;
+            for (uint32_t a = 0; a < ao; ++a) {
+                q.ao_index = a;
+                VK_CUDA(cudaMemsetAsync(sc.d_counters, 0, sizeof(unsigned long long), st));
+                rc = stats ? launch_trace<true, SRC_AO, true>(sc, q, st) : launch_trace<false, SRC_AO, true>(sc, q, st);
+                if (rc) return rc;
+            }
+        }
+        if (s == 0) VK_CUDA(cudaEventRecord(ev[12], st));
         if (want_rgba) {
-            shade_kernel<<<(unsigned)((r.n_slots + 255) / 256), 256, 0, st>>>(p, p.hits, f.shade_mode, miss, sc.d_accum, (uchar4*)d_rgba, s, r.spp);
+            shade_kernel<<<(unsigned)((r.n_slots + 255) / 256), 256, 0, st>>>(p, p.hits, f.shade_mode, miss, sc.d_accum, (uchar4*)d_rgba, s, r.spp,
+                                                                              sc.d_occluded, ao);
             count_launch();
         }
         if (s == 0) VK_CUDA(cudaEventRecord(ev[9], st));
@@ -584,7 +643,7 @@ int render_frame(DeviceScene& sc, const VkhrtFrameDesc& f, VkhrtHit* hits_out, u
     return VKHRT_OK;
 }
 
-int trace_ray_buffer(DeviceScene& sc, const float* rays_dev, uint64_t n, VkhrtHit* hits_dev, cudaStream_t stream)
+int trace_ray_buffer(DeviceScene& sc, const float* rays_dev, uint64_t n, VkhrtHit* hits_dev, bool any_hit, cudaStream_t stream)
 {
     VK_CUDA(cudaSetDevice(sc.device));
     cudaStream_t st = stream ? stream : sc.stream;
@@ -602,7 +661,7 @@ int trace_ray_buffer(DeviceScene& sc, const float* rays_dev, uint64_t n, VkhrtHi
         p.hits = hits_dev + first;
         p.n_slots = (uint32_t)std::min<uint64_t>(chunk, n - first);
         VK_CUDA(cudaMemsetAsync(sc.d_counters, 0, sizeof(unsigned long long), st));
-        int rc = launch_trace<false, true>(sc, p, st);
+        int rc = any_hit ? launch_trace<false, SRC_BUFFER, true>(sc, p, st) : launch_trace<false, SRC_BUFFER, false>(sc, p, st);
         if (rc) return rc;
     }
     if (!stream) VK_CUDA(cudaStreamSynchronize(st));
