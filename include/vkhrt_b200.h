@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define VKHRT_ABI_VERSION 2
+#define VKHRT_ABI_VERSION 3
 
 typedef enum VkhrtStatus {
     VKHRT_OK = 0,
@@ -41,7 +41,9 @@ typedef enum VkhrtStatus {
     VKHRT_ERR_NOT_BUILT = -5,      /* render/refit/get_bvh before vkhrt_scene_build      */
     VKHRT_ERR_BAD_TOPOLOGY = -6,   /* index out of range (reference logs and returns the
                                       input unchanged, geometry_processor.cpp:606-612)   */
-    VKHRT_ERR_UNSUPPORTED = -7
+    VKHRT_ERR_UNSUPPORTED = -7,
+    VKHRT_ERR_IO = -8              /* asset / image file could not be read, parsed or written (the reference logs
+                                      and returns nullptr, source/resources/model/model_loader.cpp:280-284)      */
 } VkhrtStatus;
 
 /* Technique = which ProcessHair* generator of the reference builds the primitives
@@ -61,6 +63,14 @@ typedef enum VkhrtShadeMode {
     VKHRT_SHADE = 0,
     VKHRT_SHADE_DEBUG_PRIMID = 1
 } VkhrtShadeMode;
+
+/* Colour of a ray that hits nothing.  ENVIRONMENT = shaders/miss.rmiss:17-38: equirectangular lookup of
+ * normalize(-rayDirection) in the scene's environment map (linear filter, repeat addressing, the sampler defaults of
+ * include/resources/gpu_resources.hpp:46-50), then 1 - exp(-c) and gamma 1/2.2. */
+typedef enum VkhrtMissMode {
+    VKHRT_MISS_CONSTANT = 0,
+    VKHRT_MISS_ENVIRONMENT = 1
+} VkhrtMissMode;
 
 /* Where the caller's output pointers live. */
 typedef enum VkhrtMemory {
@@ -100,7 +110,7 @@ typedef struct VkhrtFrameDesc {
     uint32_t spp;                   /* samples per pixel; 0 => 1. Sample 0 is the pixel centre
                                        (the reference traces exactly that one, ray_gen.rgen:18)    */
     int32_t  shade_mode;            /* VkhrtShadeMode                                              */
-    float    miss_rgb[3];           /* constant miss colour (env-map miss.rmiss is out of scope)   */
+    float    miss_rgb[3];           /* constant miss colour (miss_mode == VKHRT_MISS_CONSTANT)     */
     /* sharding (all zero => the whole frame): the frame is cut into tile_size^2-pixel tiles
      * numbered row-major; this call traces tiles tile_first, tile_first+tile_stride, ...
      * and writes its outputs COMPACTLY in (tile, pixel-in-tile) order when tile_stride > 1 */
@@ -123,7 +133,7 @@ typedef struct VkhrtFrameDesc {
     uint32_t ao_samples;
     float    ao_distance;           /* <= 0 => VKHRT_DEFAULT_AO_DISTANCE                           */
     float    ao_bias;               /* origin offset along the normal; <= 0 => 0.25 * radius       */
-    uint32_t reserved0;
+    int32_t  miss_mode;             /* VkhrtMissMode; ENVIRONMENT needs vkhrt_scene_set_environment */
 } VkhrtFrameDesc;
 
 #define VKHRT_DEFAULT_AO_DISTANCE 2.0f
@@ -249,6 +259,47 @@ int  vkhrt_trace_rays(VkhrtScene* scene, const float* rays_device, uint64_t n_ra
 /* same with gl_RayFlagsTerminateOnFirstHitEXT semantics (shadow / occlusion rays): the record is the FIRST accepted hit
  * in traversal order (deterministic: the order is the oracle's), not the closest one; flags bit0 = occluded */
 int  vkhrt_trace_rays_any_hit(VkhrtScene* scene, const float* rays_device, uint64_t n_rays, VkhrtHit* hits_out_device, void* stream);
+
+/* ---- environment map: Renderer ctor, source/renderer.cpp:45-56 (RGBA32F image, sampled by shaders/miss.rmiss) ---- */
+/* rgba32f: width*height texels, row 0 first, HOST memory (copied to the scene's GPU before return).
+ * NULL / 0x0 removes the map.  Frames select it with miss_mode = VKHRT_MISS_ENVIRONMENT. */
+int  vkhrt_scene_set_environment(VkhrtScene* scene, const float* rgba32f, uint32_t width, uint32_t height);
+
+/* ---- strand level of detail on the device, before the build ------------------------------
+ * The reference defines but never calls MergeLines / SplitLines / MergeCurvesFast
+ * (source/resources/model/geometry_processor.cpp:69-104, 106-121, 158-197).  Applied in this order to the scene's
+ * line list: `line_split_passes` x SplitLines, `line_merge_passes` x MergeLines, then (PHANTOM only, after
+ * GenerateCurves) `curve_merge_passes` x MergeCurvesFast.  Must be called before vkhrt_scene_build; afterwards
+ * segment ids count the processed lines / curves, and vkhrt_scene_refit is refused (the input vertices are gone).
+ * Like the reference, MergeLines / MergeCurvesFast drop the last element of an odd-sized list. */
+int  vkhrt_scene_apply_lod(VkhrtScene* scene, uint32_t line_split_passes, uint32_t line_merge_passes, uint32_t curve_merge_passes);
+/* number of line segments after LOD (= BVH leaves) and a host copy of them: n_segments * 6 floats {start.xyz, end.xyz} */
+uint32_t vkhrt_scene_segment_count(const VkhrtScene* scene);
+int  vkhrt_scene_get_lines(VkhrtScene* scene, float* out, size_t out_floats);
+
+/* ---- asset ingest and image output (host; no GPU needed): SURVEY.md §8(f) rows 3, 4 --------------------------------
+ * Replaces ModelLoader::LoadFromFile + ProcessMesh for line primitives (source/resources/model/model_loader.cpp:139-206,
+ * 274-291; Assimp is not vendored) and LoadFloatImageFromFile (source/resources/file_io.cpp:22-37, stbi_loadf). */
+typedef struct VkhrtLineAsset {
+    float*    positions_xyz;      /* n_vertices * 3, malloc'd by the loader                          */
+    uint32_t  n_vertices;
+    uint32_t* line_indices;       /* n_segments * 2                                                  */
+    uint32_t  n_segments;
+    float*    radius_per_vertex;  /* NULL unless the file carries a thickness array (.hair): thickness / 2 */
+    uint32_t  n_strands;
+} VkhrtLineAsset;
+/* by extension: .obj (`v` + `l` polyline records), .hair (Cem Yuksel HAIR format) */
+int  vkhrt_asset_load_lines(const char* path, VkhrtLineAsset* out);
+int  vkhrt_asset_save_lines(const char* path, const VkhrtLineAsset* in);
+void vkhrt_asset_free(VkhrtLineAsset* asset);
+/* Radiance .hdr (RGBE, flat or RLE scanlines) -> RGBA32F exactly as stbi_loadf(path, &w, &h, &n, 4); free with vkhrt_image_free */
+int  vkhrt_image_load_hdr(const char* path, float** rgba_out, uint32_t* width_out, uint32_t* height_out);
+int  vkhrt_image_save_hdr(const char* path, const float* rgba, uint32_t width, uint32_t height);
+void vkhrt_image_free(float* rgba);
+/* the frame the reference presents to its swap chain (source/renderer.cpp:222-231) as an 8-bit RGBA PNG */
+int  vkhrt_image_save_png(const char* path, const uint8_t* rgba8, uint32_t width, uint32_t height);
+/* procedural equirectangular sky, RGBA32F (the reference's .hdr asset is not in its repository) */
+void vkhrt_environment_generate(uint32_t width, uint32_t height, float* rgba_out);
 
 /* ---- host helpers: FlyCamera (source/fly_camera.cpp:25-35) + Renderer::UpdateCameraResource -- */
 /* fov in degrees (vertical); yaw/pitch in degrees as FlyCamera (defaults -90, 0) */

@@ -24,7 +24,7 @@ class FrameDesc(C.Structure):
                 ("spp", C.c_uint32), ("shade_mode", C.c_int32), ("miss_rgb", C.c_float * 3),
                 ("tile_size", C.c_uint32), ("tile_first", C.c_uint32), ("tile_stride", C.c_uint32),
                 ("row_major_output", C.c_uint32), ("output_memory", C.c_int32), ("stream", C.c_void_p),
-                ("ao_samples", C.c_uint32), ("ao_distance", C.c_float), ("ao_bias", C.c_float), ("reserved0", C.c_uint32)]
+                ("ao_samples", C.c_uint32), ("ao_distance", C.c_float), ("ao_bias", C.c_float), ("miss_mode", C.c_int32)]
 
 
 class TraceStats(C.Structure):
@@ -60,6 +60,13 @@ def lib():
         fp = C.POINTER(C.c_float)
         L.orc_scene_create.restype = C.c_void_p
         L.orc_scene_create.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32, C.c_void_p, C.c_float, C.c_int]
+        L.orc_scene_create_lod.restype = C.c_void_p
+        L.orc_scene_create_lod.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32, C.c_void_p, C.c_float, C.c_int, C.c_void_p]
+        L.orc_scene_set_environment.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32]
+        L.orc_scene_line_count.restype = C.c_uint32
+        L.orc_scene_line_count.argtypes = [C.c_void_p]
+        L.orc_scene_get_lines.argtypes = [C.c_void_p, C.c_void_p]
+        L.orc_environment_miss.argtypes = [C.c_void_p, fp, fp]
         L.orc_scene_destroy.argtypes = [C.c_void_p]
         L.orc_scene_primitive_count.restype = C.c_uint32
         L.orc_scene_primitive_count.argtypes = [C.c_void_p]
@@ -103,9 +110,10 @@ def max_threads():
 
 def make_frame(view_inv, proj_inv, width, height, spp=1, shade_mode=0, miss_rgb=(0.0, 0.0, 0.0),
                tile_size=0, tile_first=0, tile_stride=0, t_min=0.0, t_max=0.0, row_major_output=0,
-               ao_samples=0, ao_distance=0.0, ao_bias=0.0):
+               ao_samples=0, ao_distance=0.0, ao_bias=0.0, miss_mode=0):
     f = FrameDesc()
     f.ao_samples, f.ao_distance, f.ao_bias = int(ao_samples), float(ao_distance), float(ao_bias)
+    f.miss_mode = int(miss_mode)
     f.view_inverse[:] = [float(x) for x in np.asarray(view_inv, np.float32).reshape(16)]
     f.proj_inverse[:] = [float(x) for x in np.asarray(proj_inv, np.float32).reshape(16)]
     f.width, f.height, f.spp, f.shade_mode = width, height, spp, shade_mode
@@ -117,7 +125,8 @@ def make_frame(view_inv, proj_inv, width, height, spp=1, shade_mode=0, miss_rgb=
 
 
 class OracleScene:
-    def __init__(self, positions, indices, technique=0, radius=0.02, radius_per_vertex=None):
+    def __init__(self, positions, indices, technique=0, radius=0.02, radius_per_vertex=None, lod=None):
+        """lod = (line_split_passes, line_merge_passes, curve_merge_passes), as vkhrt_scene_apply_lod"""
         self.positions = np.ascontiguousarray(positions, np.float32).reshape(-1, 3)
         self.indices = np.ascontiguousarray(indices, np.uint32).reshape(-1, 2)
         self.technique = int(technique)
@@ -126,11 +135,32 @@ class OracleScene:
             rpv = np.ascontiguousarray(radius_per_vertex, np.float32)
             assert rpv.shape[0] == self.positions.shape[0]
         self._rpv = rpv
-        self._h = lib().orc_scene_create(self.positions.ctypes.data, self.positions.shape[0], self.indices.ctypes.data,
-                                         self.indices.shape[0], rpv.ctypes.data if rpv is not None else None,
-                                         float(radius), self.technique)
+        lod3 = np.asarray(lod if lod is not None else (0, 0, 0), np.uint32)
+        self._h = lib().orc_scene_create_lod(self.positions.ctypes.data, self.positions.shape[0], self.indices.ctypes.data,
+                                             self.indices.shape[0], rpv.ctypes.data if rpv is not None else None,
+                                             float(radius), self.technique, lod3.ctypes.data)
         if not self._h:
             raise ValueError("oracle: bad topology")
+
+    def set_environment(self, rgba):
+        """RGBA32F equirectangular map [h, w, 4] (None removes it); frames select it with miss_mode=1"""
+        if rgba is None:
+            lib().orc_scene_set_environment(self._h, None, 0, 0)
+            return
+        e = np.ascontiguousarray(rgba, np.float32)
+        assert e.ndim == 3 and e.shape[2] == 4
+        lib().orc_scene_set_environment(self._h, e.ctypes.data, e.shape[1], e.shape[0])
+
+    def environment_miss(self, d):
+        a = _f(d); o = (C.c_float * 3)()
+        lib().orc_environment_miss(self._h, a[1], o)
+        return np.array(list(o), np.float32)
+
+    def lines(self):
+        """the line list the primitives were generated from (after LOD): [n, 6] = start.xyz, end.xyz"""
+        out = np.empty((int(lib().orc_scene_line_count(self._h)), 6), np.float32)
+        lib().orc_scene_get_lines(self._h, out.ctypes.data)
+        return out
 
     def close(self):
         if getattr(self, "_h", None):

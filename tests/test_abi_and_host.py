@@ -86,9 +86,9 @@ def test_header_is_plain_c(V):
 
 def test_error_strings_and_versions(V):
     L = V.lib()
-    assert L.vkhrt_abi_version() == 2
+    assert L.vkhrt_abi_version() == 3
     assert L.vkhrt_error_string(0) == b"ok"
-    for code in range(-7, 0):
+    for code in range(-8, 0):
         assert L.vkhrt_error_string(code) not in (b"ok", b"unknown status")
     assert L.vkhrt_error_string(-99) == b"unknown status"
 

@@ -1,0 +1,319 @@
+"""asset ingest (OBJ / HAIR line assets, Radiance .hdr), PNG output, strand LOD
+(MergeLines / SplitLines / MergeCurvesFast) and the environment-map miss shader.
+
+CPU part: host code of the product (no GPU needed) and the oracle restatements against hand-derived answers.
+GPU part: the device passes against the oracle — bit-identical lines / curves / BVH / hit records; the environment
+colour within 1 LSB of the 8-bit image (asin / atan / exp / pow are library functions on both sides)."""
+import os
+import struct
+import zlib
+
+import numpy as np
+import pytest
+
+from conftest import default_camera, has_gpu
+
+gpu = pytest.mark.gpu
+
+
+# ---------------------------------------------------------------------------------- asset ingest (host, CPU)
+def test_obj_polylines_negative_indices_comments(V, tmp_path):
+    p = tmp_path / "a.obj"
+    p.write_text("# two strands\nv 0 0 0\nv 1 0 0\nv 2 1 0 # inline comment\n l 1 2 3\nv 5 5 5\nv 6 5 5\nl -2 -1\nvn 0 1 0\nf 1 2 3\nl 4/1 5/2\n")
+    pos, idx, rpv, strands = V.load_lines(str(p))
+    assert rpv is None and strands == 3
+    assert pos.tolist() == [[0, 0, 0], [1, 0, 0], [2, 1, 0], [5, 5, 5], [6, 5, 5]]
+    assert idx.tolist() == [[0, 1], [1, 2], [3, 4], [3, 4]]       # `l 1 2 3` -> two 2-index faces, like Assimp
+
+
+def test_obj_errors(V, tmp_path):
+    p = tmp_path / "bad.obj"
+    p.write_text("v 0 0 0\nl 1 2\n")
+    with pytest.raises(V.VkhrtError) as e:
+        V.load_lines(str(p))
+    assert e.value.status == -6                                    # BAD_TOPOLOGY
+    with pytest.raises(V.VkhrtError) as e:
+        V.load_lines(str(tmp_path / "missing.obj"))
+    assert e.value.status == -8                                    # IO
+    q = tmp_path / "x.abc"
+    q.write_text("")
+    with pytest.raises(V.VkhrtError) as e:
+        V.load_lines(str(q))
+    assert e.value.status == -7                                    # UNSUPPORTED
+
+
+@pytest.mark.parametrize("ext", ["obj", "hair"])
+def test_line_asset_round_trip_is_exact(V, tmp_path, ext):
+    pos, idx = V.generate_groom(37, 5, V.GROOM_CURLY)
+    path = str(tmp_path / f"g.{ext}")
+    V.save_lines(path, pos, idx)
+    p2, i2, rpv, strands = V.load_lines(path)
+    assert strands == 37 and rpv is None
+    assert p2.tobytes() == pos.tobytes() and np.array_equal(i2, idx)     # %.9g text round-trips fp32 exactly
+
+
+def test_hair_file_layout_and_thickness(V, tmp_path):
+    # Cem Yuksel HAIR: 128-byte header, u16 segments per strand, points, thickness (diameter -> radius/2)
+    pts = np.arange(21, dtype=np.float32).reshape(7, 3)
+    segs = np.array([2, 3], np.uint16)                             # 3 + 4 points
+    thick = np.linspace(0.04, 0.01, 7).astype(np.float32)
+    hdr = b"HAIR" + struct.pack("<IIII", 2, 7, 1 | 2 | 4, 0) + struct.pack("<ff3f", 0.04, 0.0, 1, 1, 1) + b"\0" * 88
+    assert len(hdr) == 128
+    path = tmp_path / "h.hair"
+    path.write_bytes(hdr + segs.tobytes() + pts.tobytes() + thick.tobytes())
+    pos, idx, rpv, strands = V.load_lines(str(path))
+    assert strands == 2 and np.array_equal(pos, pts)
+    assert idx.tolist() == [[0, 1], [1, 2], [3, 4], [4, 5], [5, 6]]
+    assert np.array_equal(rpv, thick * np.float32(0.5))
+    # default segment count, no segments array
+    hdr2 = b"HAIR" + struct.pack("<IIII", 2, 6, 2, 2) + struct.pack("<ff3f", 0.04, 0.0, 1, 1, 1) + b"\0" * 88
+    path.write_bytes(hdr2 + pts[:6].tobytes())
+    pos, idx, rpv, strands = V.load_lines(str(path))
+    assert rpv is None and idx.tolist() == [[0, 1], [1, 2], [3, 4], [4, 5]]
+    # writer: thickness round trip
+    V.save_lines(str(path), pts, [[0, 1], [1, 2], [3, 4], [4, 5], [5, 6]], radius_per_vertex=thick)
+    _, i3, r3, s3 = V.load_lines(str(path))
+    assert s3 == 2 and len(i3) == 5 and np.array_equal(r3, thick)
+    path.write_bytes(hdr[:100])
+    with pytest.raises(V.VkhrtError):
+        V.load_lines(str(path))
+
+
+def _rgbe_decode(b):
+    """numpy restatement of stb_image's stbi__hdr_convert (req_comp 4)"""
+    b = b.astype(np.int32)
+    f = np.ldexp(np.float32(1.0), b[..., 3] - 136).astype(np.float32)
+    out = np.zeros(b.shape[:-1] + (4,), np.float32)
+    out[..., :3] = b[..., :3].astype(np.float32) * f[..., None]
+    out[b[..., 3] == 0, :3] = 0
+    out[..., 3] = 1
+    return out
+
+
+def test_hdr_flat_and_rle_scanlines(V, tmp_path):
+    rng = np.random.default_rng(3)
+    W, H = 40, 6
+    rgbe = rng.integers(0, 256, (H, W, 4), dtype=np.uint8)
+    rgbe[0, 0] = (5, 6, 7, 0)                                      # zero exponent -> black
+    rgbe[:, 0, 0] = 9                                              # keep flat rows from looking like the RLE marker
+    want = _rgbe_decode(rgbe)
+    head = b"#?RADIANCE\n# comment\nFORMAT=32-bit_rle_rgbe\nEXPOSURE=1.0\n\n-Y %d +X %d\n" % (H, W)
+    flat = tmp_path / "flat.hdr"
+    flat.write_bytes(head + rgbe.tobytes())
+    assert np.array_equal(V.load_hdr(str(flat)), want)
+    # new-style RLE: per scanline 2 2 hi lo, then each component as runs / literals
+    body = b""
+    for y in range(H):
+        body += bytes([2, 2, W >> 8, W & 255])
+        for c in range(4):
+            row = rgbe[y, :, c]
+            if c == 1:
+                row = np.full(W, row[0], np.uint8); rgbe[y, :, 1] = row          # one long run
+                body += bytes([128 + W, int(row[0])]) if W <= 127 else b""
+            else:
+                for x in range(0, W, 16):
+                    chunk = row[x:x + 16]
+                    body += bytes([len(chunk)]) + chunk.tobytes()
+    rle = tmp_path / "rle.hdr"
+    rle.write_bytes(head + body)
+    assert np.array_equal(V.load_hdr(str(rle)), _rgbe_decode(rgbe))
+    # writer -> reader: RGBE quantisation only (<= 1/128 relative on the largest channel)
+    env = V.generate_environment(64, 32)
+    out = tmp_path / "env.hdr"
+    V.save_hdr(str(out), env)
+    back = V.load_hdr(str(out))
+    assert back.shape == env.shape and (back[..., 3] == 1).all()
+    mx = env[..., :3].max(axis=-1, keepdims=True)
+    assert (np.abs(back[..., :3] - env[..., :3]) <= mx / 100.0 + 1e-6).all()
+    (tmp_path / "bad.hdr").write_bytes(b"P6\n")
+    with pytest.raises(V.VkhrtError):
+        V.load_hdr(str(tmp_path / "bad.hdr"))
+
+
+def test_png_writer_decodes_with_zlib(V, tmp_path):
+    rng = np.random.default_rng(4)
+    for (W, H) in ((7, 5), (300, 90)):                             # second one spans several 64 KiB stored blocks
+        img = rng.integers(0, 256, (H, W, 4), dtype=np.uint8)
+        path = tmp_path / "o.png"
+        V.save_png(str(path), img, W, H)
+        data = path.read_bytes()
+        assert data[:8] == b"\x89PNG\r\n\x1a\n"
+        pos, chunks = 8, []
+        while pos < len(data):
+            n, = struct.unpack(">I", data[pos:pos + 4]); typ = data[pos + 4:pos + 8]; body = data[pos + 8:pos + 8 + n]
+            crc, = struct.unpack(">I", data[pos + 8 + n:pos + 12 + n])
+            assert zlib.crc32(typ + body) == crc
+            chunks.append((typ, body)); pos += 12 + n
+        assert [c[0] for c in chunks] == [b"IHDR", b"IDAT", b"IEND"]
+        assert struct.unpack(">IIBBBBB", chunks[0][1]) == (W, H, 8, 6, 0, 0, 0)
+        raw = np.frombuffer(zlib.decompress(chunks[1][1]), np.uint8).reshape(H, 1 + 4 * W)     # checks the adler32 too
+        assert (raw[:, 0] == 0).all() and np.array_equal(raw[:, 1:].reshape(H, W, 4), img)
+
+
+# ---------------------------------------------------------------------------------- LOD restatements (oracle, CPU)
+def _two_strands():
+    # strand A: 5 segments (6 vertices), strand B: 2 segments; B is not connected to A
+    a = np.array([[0, 0, 0], [1, 0, 0], [2, 1, 0], [3, 1, 1], [4, 2, 1], [5, 2, 2]], np.float32)
+    b = np.array([[10, 0, 0], [10, 1, 0], [10, 2, 1]], np.float32)
+    pos = np.concatenate([a, b])
+    idx = np.array([[0, 1], [1, 2], [2, 3], [3, 4], [4, 5], [6, 7], [7, 8]], np.uint32)
+    return pos, idx
+
+
+def test_oracle_merge_and_split_lines_by_hand(O):
+    pos, idx = _two_strands()
+    base = O.OracleScene(pos, idx).lines()
+    assert base.shape == (7, 6)
+    # MergeLines (geometry_processor.cpp:69-104): pairs (0,1) (2,3) merge, pair (4,5) is not connected -> kept, line 6 dropped (odd)
+    m = O.OracleScene(pos, idx, lod=(0, 1, 0)).lines()
+    want = np.array([[0, 0, 0, 2, 1, 0], [2, 1, 0, 4, 2, 1], [4, 2, 1, 5, 2, 2], [10, 0, 0, 10, 1, 0]], np.float32)
+    assert np.array_equal(m, want)
+    # SplitLines (:106-121): midpoint (s + e) * 0.5
+    s = O.OracleScene(pos, idx, lod=(1, 0, 0)).lines()
+    assert s.shape == (14, 6)
+    assert np.array_equal(s[0], [0, 0, 0, 0.5, 0, 0]) and np.array_equal(s[1], [0.5, 0, 0, 1, 0, 0])
+    assert np.array_equal(s[0::2, :3], base[:, :3]) and np.array_equal(s[1::2, 3:], base[:, 3:]) and np.array_equal(s[0::2, 3:], s[1::2, :3])
+    # split then merge gives the original lines back (exactly: the midpoints are dropped again)
+    sm = O.OracleScene(pos, idx, lod=(1, 1, 0)).lines()
+    assert np.array_equal(sm, base)
+
+
+def test_oracle_merge_curves_fast_by_hand(O):
+    pos, idx = _two_strands()
+    c = O.OracleScene(pos, idx).primitives().reshape(-1, 4, 3)
+    m = O.OracleScene(pos, idx, lod=(0, 0, 1)).primitives().reshape(-1, 4, 3)
+    assert m.shape[0] == 4                                          # (0,1) (2,3) merged, (4,5) kept as two, curve 6 dropped
+    mid = (c[0, 2] + c[1, 1]) * np.float32(0.5)                      # geometry_processor.cpp:190-192
+    assert np.array_equal(m[0, 0], c[0, 0]) and np.array_equal(m[0, 3], c[1, 3])
+    assert np.array_equal(m[0, 1], (c[0, 1] + mid) * np.float32(0.5)) and np.array_equal(m[0, 2], (mid + c[1, 2]) * np.float32(0.5))
+    assert np.array_equal(m[2], c[4]) and np.array_equal(m[3], c[5])
+    with pytest.raises(ValueError):
+        O.OracleScene(pos, idx, technique=1, lod=(0, 0, 1))          # curve merge needs curves
+
+
+def test_oracle_environment_lookup_by_hand(O, V):
+    pos, idx = _two_strands()
+    sc = O.OracleScene(pos, idx)
+    env = np.zeros((4, 8, 4), np.float32)
+    env[..., 3] = 1
+    env[0, :, 0] = 2.0                                              # top row red = what a ray pointing up sees (dir = -d looks down: v -> 0)
+    env[3, :, 2] = 1.0                                              # bottom row blue
+    sc.set_environment(env)
+    tone = lambda x: (1.0 - np.exp(-x)) ** (1.0 / 2.2)              # miss.rmiss:34-35
+    # straight up: dir.y = -1 -> v = 0 exactly -> texel row -0.5: repeat addressing blends row 0 with row 3 half and half
+    up = sc.environment_miss([0, 1, 0])
+    assert abs(up[0] - tone(1.0)) < 1e-6 and up[1] == 0 and abs(up[2] - tone(0.5)) < 1e-6
+    # centre of row 0: v = 0.125 -> elevation of dir = -0.375 pi
+    c, s_ = np.cos(0.375 * np.pi), np.sin(0.375 * np.pi)
+    r0 = sc.environment_miss([0, s_, -c])
+    assert abs(r0[0] - tone(2.0)) < 1e-4 and r0[1] == 0 and r0[2] < 0.01
+    r3 = sc.environment_miss([0, -s_, -c])
+    assert abs(r3[2] - tone(1.0)) < 1e-4 and r3[0] < 0.01
+    # horizontal ray: v = 0.5 -> halfway between rows 1 and 2 (both black)
+    assert np.array_equal(sc.environment_miss([0, 0, -1]), [0, 0, 0])
+    # u: dir = -d; theta = atan(dir.x, -dir.z): d = (0,0,-1) -> dir = (0,0,1) -> theta = atan2(0,-1) = pi -> u = 1 (wraps to texel column 0/7 seam)
+    env2 = np.zeros((2, 8, 4), np.float32); env2[:, 0, 1] = 1.0; env2[:, 7, 1] = 1.0
+    sc.set_environment(env2)
+    assert abs(sc.environment_miss([0, 0, -1])[1] - tone(1.0)) < 1e-6    # repeat addressing across the seam
+    assert sc.environment_miss([0, 0, 1])[1] == 0                      # u = 0.5 -> columns 3/4
+
+
+# ---------------------------------------------------------------------------------- device passes vs oracle (GPU)
+@gpu
+@pytest.mark.parametrize("tech", [0, 1, 2])
+@pytest.mark.parametrize("lod", [(1, 0, 0), (0, 1, 0), (2, 1, 0), (0, 3, 0), (1, 2, 0)])
+def test_gpu_line_lod_matches_oracle(V, O, tech, lod):
+    pos, idx = V.generate_groom(301, 7, V.GROOM_CURLY)               # 7 segments: odd strands exercise the unconnected-pair branch
+    rpv = None
+    if tech == 1:
+        rpv = np.linspace(0.03, 0.005, pos.shape[0]).astype(np.float32)
+    with V.Scene(pos, idx, technique=tech, radius_per_vertex=rpv) as sc:
+        sc.apply_lod(*lod)
+        orc = O.OracleScene(pos, idx, technique=tech, radius_per_vertex=rpv, lod=lod)
+        assert sc.n_segments == orc.lines().shape[0]
+        assert sc.lines().tobytes() == orc.lines().tobytes()
+        sc.build()
+        assert sc.primitives().tobytes() == orc.primitives().tobytes()
+        gn, gi, gm, _ = sc.bvh(); on, oi, om, _ = orc.bvh()
+        assert gn.tobytes() == on.tobytes() and np.array_equal(gi, oi) and np.array_equal(gm, om)
+        W, H = 160, 96
+        vi, pi = default_camera(V, W, H)
+        hg, ig, _ = sc.render(V.make_frame(vi, pi, W, H))
+        ho, io, _ = orc.render(O.make_frame(vi, pi, W, H))
+        assert hg.tobytes() == ho.tobytes() and np.array_equal(ig, io)
+        assert (hg["flags"] & 1).sum() > 50
+        with pytest.raises(V.VkhrtError) as e:
+            sc.refit(pos)
+        assert e.value.status == -7
+
+
+@gpu
+@pytest.mark.parametrize("lod", [(0, 0, 1), (0, 0, 2), (1, 0, 1), (0, 1, 2)])
+def test_gpu_curve_merge_matches_oracle(V, O, lod):
+    pos, idx = V.generate_groom(257, 9, V.GROOM_CURLY)
+    with V.Scene(pos, idx) as sc:
+        sc.apply_lod(*lod)
+        orc = O.OracleScene(pos, idx, lod=lod)
+        assert sc.n_primitives == orc.n_primitives
+        assert sc.lines().tobytes() == orc.lines().tobytes()
+        sc.build()
+        assert sc.primitives().tobytes() == orc.primitives().tobytes()
+        gn, gi, _, _ = sc.bvh(); on, oi, _, _ = orc.bvh()
+        assert gn.tobytes() == on.tobytes() and np.array_equal(gi, oi)
+        W, H = 160, 96
+        vi, pi = default_camera(V, W, H)
+        hg, _, _ = sc.render(V.make_frame(vi, pi, W, H), rgba=False)
+        ho, _, _ = orc.render(O.make_frame(vi, pi, W, H), rgba=False)
+        assert hg.tobytes() == ho.tobytes()
+
+
+@gpu
+def test_gpu_lod_argument_errors(V):
+    pos, idx = V.generate_groom(8, 4, V.GROOM_STRAIGHT)
+    with V.Scene(pos, idx, technique=V.LSS) as sc:
+        with pytest.raises(V.VkhrtError) as e:
+            sc.apply_lod(0, 0, 1)
+        assert e.value.status == -7
+        sc.apply_lod(0, 0, 0)                                        # no-op
+        sc.build()
+        sc.refit(pos)                                                # still allowed
+        with pytest.raises(V.VkhrtError) as e:
+            sc.apply_lod(1, 0, 0)
+        assert e.value.status == -1                                  # after build
+    with V.Scene(pos[:0], idx[:0]) as sc:                           # empty scene through the passes
+        sc.apply_lod(1, 1, 1)
+        assert sc.n_segments == 0
+        sc.build()
+
+
+@gpu
+@pytest.mark.parametrize("spp", [1, 3])
+def test_gpu_environment_miss_within_one_lsb(V, O, spp):
+    pos, idx = V.generate_groom(2000, 12, V.GROOM_CURLY)
+    env = V.generate_environment(256, 128)
+    W, H = 320, 200
+    vi, pi = V.camera_matrices(position=(0.0, 152.0, 26.0), pitch=8.0, aspect=float(np.float32(W) / np.float32(H)))
+    with V.Scene(pos, idx) as sc:
+        sc.build()
+        with pytest.raises(V.VkhrtError) as e:
+            sc.render(V.make_frame(vi, pi, W, H, miss_mode=V.MISS_ENVIRONMENT))
+        assert e.value.status == -1                                  # no environment set
+        sc.set_environment(env)
+        hg, ig, _ = sc.render(V.make_frame(vi, pi, W, H, spp=spp, miss_mode=V.MISS_ENVIRONMENT))
+        orc = O.OracleScene(pos, idx)
+        orc.set_environment(env)
+        ho, io, _ = orc.render(O.make_frame(vi, pi, W, H, spp=spp, miss_mode=1))
+        assert hg.tobytes() == ho.tobytes()                          # hit records are untouched by the miss shader
+        miss = (hg["flags"] & 1) == 0
+        assert 0.2 < miss.mean() < 0.95
+        d = np.abs(ig.astype(np.int32) - io.astype(np.int32))
+        assert d.max() <= 1 and (d[miss] != 0).mean() < 0.01         # library transcendentals: 1 LSB, rarely
+        if spp == 1:
+            assert np.array_equal(ig[~miss], io[~miss])
+        assert len(np.unique(ig[miss][:, :3], axis=0)) > 50          # a real gradient, not a constant
+        # constant mode still works with a map installed
+        _, ic, _ = sc.render(V.make_frame(vi, pi, W, H, miss_rgb=(0.25, 0.5, 0.75)))
+        assert (ic[miss][:, :3] == np.array([64, 128, 191], np.uint8)).all()
+        sc.set_environment(None)
+        with pytest.raises(V.VkhrtError):
+            sc.render(V.make_frame(vi, pi, W, H, miss_mode=V.MISS_ENVIRONMENT))

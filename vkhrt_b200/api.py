@@ -15,6 +15,7 @@ import numpy as np
 PHANTOM, LSS, DOTS = 0, 1, 2
 SHADE, DEBUG_PRIMID = 0, 1
 MEM_HOST, MEM_DEVICE = 0, 1
+MISS_CONSTANT, MISS_ENVIRONMENT = 0, 1
 GROOM_STRAIGHT, GROOM_CURLY = 0, 1
 DEFAULT_SEED = 0x5EED0001
 FLOATS_PER_PRIM = {PHANTOM: 12, LSS: 8, DOTS: 9}
@@ -49,7 +50,12 @@ class FrameDesc(C.Structure):
                 ("spp", C.c_uint32), ("shade_mode", C.c_int32), ("miss_rgb", C.c_float * 3),
                 ("tile_size", C.c_uint32), ("tile_first", C.c_uint32), ("tile_stride", C.c_uint32),
                 ("row_major_output", C.c_uint32), ("output_memory", C.c_int32), ("stream", C.c_void_p),
-                ("ao_samples", C.c_uint32), ("ao_distance", C.c_float), ("ao_bias", C.c_float), ("reserved0", C.c_uint32)]
+                ("ao_samples", C.c_uint32), ("ao_distance", C.c_float), ("ao_bias", C.c_float), ("miss_mode", C.c_int32)]
+
+
+class LineAsset(C.Structure):
+    _fields_ = [("positions_xyz", C.c_void_p), ("n_vertices", C.c_uint32), ("line_indices", C.c_void_p),
+                ("n_segments", C.c_uint32), ("radius_per_vertex", C.c_void_p), ("n_strands", C.c_uint32)]
 
 
 class BvhView(C.Structure):
@@ -87,6 +93,9 @@ ABI_SYMBOLS = [
     "vkhrt_render", "vkhrt_render_stats", "vkhrt_frame_local_pixels", "vkhrt_untile", "vkhrt_last_timing",
     "vkhrt_generate_rays", "vkhrt_trace_rays", "vkhrt_trace_rays_any_hit", "vkhrt_camera_matrices", "vkhrt_groom_generate",
     "vkhrt_shared_buffer_create", "vkhrt_shared_buffer_open", "vkhrt_shared_buffer_close", "vkhrt_shared_buffer_destroy",
+    "vkhrt_scene_set_environment", "vkhrt_scene_apply_lod", "vkhrt_scene_segment_count", "vkhrt_scene_get_lines",
+    "vkhrt_asset_load_lines", "vkhrt_asset_save_lines", "vkhrt_asset_free", "vkhrt_image_load_hdr", "vkhrt_image_save_hdr",
+    "vkhrt_image_free", "vkhrt_image_save_png", "vkhrt_environment_generate",
 ]
 
 _lib = None
@@ -137,7 +146,23 @@ def lib():
     L.vkhrt_shared_buffer_open.argtypes = [C.c_int, C.c_char_p, C.POINTER(C.c_void_p)]
     L.vkhrt_shared_buffer_close.argtypes = [C.c_int, C.c_void_p]
     L.vkhrt_shared_buffer_destroy.argtypes = [C.c_int, C.c_void_p]
-    if L.vkhrt_abi_version() != 2:
+    L.vkhrt_scene_set_environment.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32]
+    L.vkhrt_scene_apply_lod.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32]
+    L.vkhrt_scene_segment_count.restype = C.c_uint32
+    L.vkhrt_scene_segment_count.argtypes = [C.c_void_p]
+    L.vkhrt_scene_get_lines.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t]
+    L.vkhrt_asset_load_lines.argtypes = [C.c_char_p, C.POINTER(LineAsset)]
+    L.vkhrt_asset_save_lines.argtypes = [C.c_char_p, C.POINTER(LineAsset)]
+    L.vkhrt_asset_free.argtypes = [C.POINTER(LineAsset)]
+    L.vkhrt_asset_free.restype = None
+    L.vkhrt_image_load_hdr.argtypes = [C.c_char_p, C.POINTER(C.c_void_p), C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)]
+    L.vkhrt_image_save_hdr.argtypes = [C.c_char_p, C.c_void_p, C.c_uint32, C.c_uint32]
+    L.vkhrt_image_free.argtypes = [C.c_void_p]
+    L.vkhrt_image_free.restype = None
+    L.vkhrt_image_save_png.argtypes = [C.c_char_p, C.c_void_p, C.c_uint32, C.c_uint32]
+    L.vkhrt_environment_generate.argtypes = [C.c_uint32, C.c_uint32, C.c_void_p]
+    L.vkhrt_environment_generate.restype = None
+    if L.vkhrt_abi_version() != 3:
         raise ImportError("libvkhrt_b200.so ABI version mismatch")
     _lib = L
     return L
@@ -185,9 +210,10 @@ def generate_groom(n_strands, segments, style=GROOM_CURLY, seed=DEFAULT_SEED):
 
 def make_frame(view_inv, proj_inv, width, height, spp=1, shade_mode=SHADE, miss_rgb=(0.0, 0.0, 0.0), tile_size=0,
                tile_first=0, tile_stride=0, t_min=0.0, t_max=0.0, output_memory=MEM_HOST, stream=None, row_major_output=0,
-               ao_samples=0, ao_distance=0.0, ao_bias=0.0):
+               ao_samples=0, ao_distance=0.0, ao_bias=0.0, miss_mode=MISS_CONSTANT):
     f = FrameDesc()
     f.ao_samples, f.ao_distance, f.ao_bias = int(ao_samples), float(ao_distance), float(ao_bias)
+    f.miss_mode = int(miss_mode)
     f.view_inverse[:] = [float(x) for x in np.asarray(view_inv, np.float32).reshape(16)]
     f.proj_inverse[:] = [float(x) for x in np.asarray(proj_inv, np.float32).reshape(16)]
     f.width, f.height, f.spp, f.shade_mode = int(width), int(height), int(spp), int(shade_mode)
@@ -198,6 +224,57 @@ def make_frame(view_inv, proj_inv, width, height, spp=1, shade_mode=SHADE, miss_
     f.stream = stream
     f.row_major_output = row_major_output
     return f
+
+
+def load_lines(path):
+    """ModelLoader::LoadFromFile for line assets (.obj `l` records, .hair): -> (positions [n,3], indices [m,2], radius_per_vertex | None, n_strands)"""
+    a = LineAsset()
+    _check(lib().vkhrt_asset_load_lines(os.fsencode(path), C.byref(a)), "vkhrt_asset_load_lines")
+    try:
+        pos = np.ctypeslib.as_array(C.cast(a.positions_xyz, C.POINTER(C.c_float)), (a.n_vertices, 3)).copy() if a.n_vertices else np.zeros((0, 3), np.float32)
+        idx = np.ctypeslib.as_array(C.cast(a.line_indices, C.POINTER(C.c_uint32)), (a.n_segments, 2)).copy() if a.n_segments else np.zeros((0, 2), np.uint32)
+        rpv = None
+        if a.radius_per_vertex and a.n_vertices:
+            rpv = np.ctypeslib.as_array(C.cast(a.radius_per_vertex, C.POINTER(C.c_float)), (a.n_vertices,)).copy()
+        return pos, idx, rpv, int(a.n_strands)
+    finally:
+        lib().vkhrt_asset_free(C.byref(a))
+
+
+def save_lines(path, positions, indices, radius_per_vertex=None):
+    pos = np.ascontiguousarray(positions, np.float32).reshape(-1, 3)
+    idx = np.ascontiguousarray(indices, np.uint32).reshape(-1, 2)
+    rpv = None if radius_per_vertex is None else np.ascontiguousarray(radius_per_vertex, np.float32)
+    a = LineAsset(pos.ctypes.data if pos.size else None, pos.shape[0], idx.ctypes.data if idx.size else None, idx.shape[0],
+                  rpv.ctypes.data if rpv is not None else None, 0)
+    _check(lib().vkhrt_asset_save_lines(os.fsencode(path), C.byref(a)), "vkhrt_asset_save_lines")
+
+
+def load_hdr(path):
+    """LoadFloatImageFromFile (stbi_loadf, 4 channels): Radiance .hdr -> float32 [h, w, 4]"""
+    p = C.c_void_p(); w = C.c_uint32(); h = C.c_uint32()
+    _check(lib().vkhrt_image_load_hdr(os.fsencode(path), C.byref(p), C.byref(w), C.byref(h)), "vkhrt_image_load_hdr")
+    try:
+        return np.ctypeslib.as_array(C.cast(p, C.POINTER(C.c_float)), (h.value, w.value, 4)).copy()
+    finally:
+        lib().vkhrt_image_free(p)
+
+
+def save_hdr(path, rgba):
+    e = np.ascontiguousarray(rgba, np.float32)
+    _check(lib().vkhrt_image_save_hdr(os.fsencode(path), e.ctypes.data, e.shape[1], e.shape[0]), "vkhrt_image_save_hdr")
+
+
+def save_png(path, rgba8, width, height):
+    img = np.ascontiguousarray(rgba8, np.uint8).reshape(height, width, 4)
+    _check(lib().vkhrt_image_save_png(os.fsencode(path), img.ctypes.data, width, height), "vkhrt_image_save_png")
+
+
+def generate_environment(width=512, height=256):
+    """procedural equirectangular sky, float32 [h, w, 4] (the reference's .hdr asset is not in its repository)"""
+    out = np.empty((height, width, 4), np.float32)
+    lib().vkhrt_environment_generate(width, height, out.ctypes.data)
+    return out
 
 
 def frame_local_pixels(frame):
@@ -242,6 +319,28 @@ class Scene:
     @property
     def n_primitives(self):
         return int(lib().vkhrt_scene_primitive_count(self._h))
+
+    def apply_lod(self, line_split_passes=0, line_merge_passes=0, curve_merge_passes=0):
+        """SplitLines / MergeLines / MergeCurvesFast on the device, before build()"""
+        _check(lib().vkhrt_scene_apply_lod(self._h, line_split_passes, line_merge_passes, curve_merge_passes), "vkhrt_scene_apply_lod")
+        self.n_segments = int(lib().vkhrt_scene_segment_count(self._h))
+        return self
+
+    def lines(self):
+        out = np.empty((int(lib().vkhrt_scene_segment_count(self._h)), 6), np.float32)
+        _check(lib().vkhrt_scene_get_lines(self._h, out.ctypes.data, out.size), "vkhrt_scene_get_lines")
+        return out
+
+    def set_environment(self, rgba):
+        """RGBA32F equirectangular map [h, w, 4] for miss_mode=MISS_ENVIRONMENT (None removes it)"""
+        if rgba is None:
+            _check(lib().vkhrt_scene_set_environment(self._h, None, 0, 0), "vkhrt_scene_set_environment")
+            return self
+        e = np.ascontiguousarray(rgba, np.float32)
+        if e.ndim != 3 or e.shape[2] != 4:
+            raise ValueError("environment map must be [h, w, 4] float32")
+        _check(lib().vkhrt_scene_set_environment(self._h, e.ctypes.data, e.shape[1], e.shape[0]), "vkhrt_scene_set_environment")
+        return self
 
     def build(self):
         _check(lib().vkhrt_scene_build(self._h), "vkhrt_scene_build")

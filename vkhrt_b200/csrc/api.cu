@@ -38,7 +38,7 @@ static void free_scene(DeviceScene* sc)
 {
     if (!sc) return;
     cudaSetDevice(sc->device);
-    cudaFree(sc->d_positions); cudaFree(sc->d_indices); cudaFree(sc->d_radius_pv);
+    cudaFree(sc->d_positions); cudaFree(sc->d_indices); cudaFree(sc->d_radius_pv); cudaFree(sc->d_curves); cudaFree(sc->d_env);
     cudaFree(sc->d_nodes); cudaFree(sc->d_sorted_ids); cudaFree(sc->d_sorted_morton);
     cudaFree(sc->d_parent_internal); cudaFree(sc->d_parent_leaf); cudaFree(sc->d_refit_flags);
     cudaFree(sc->d_primA); cudaFree(sc->d_primB);
@@ -78,6 +78,7 @@ const char* vkhrt_error_string(int status)
     case VKHRT_ERR_NOT_BUILT: return "scene not built";
     case VKHRT_ERR_BAD_TOPOLOGY: return "line index out of range";
     case VKHRT_ERR_UNSUPPORTED: return "unsupported";
+    case VKHRT_ERR_IO: return "asset or image file could not be read, parsed or written";
     default: return "unknown status";
     }
 }
@@ -152,6 +153,7 @@ int vkhrt_scene_refit(VkhrtScene* scene, const float* positions_xyz)
     if (!scene || !positions_xyz) { set_last_error("null argument"); return VKHRT_ERR_INVALID_ARGUMENT; }
     DeviceScene& sc = scene->s;
     if (!sc.built) { set_last_error("refit before build"); return VKHRT_ERR_NOT_BUILT; }
+    if (sc.lod_applied) { set_last_error("refit after vkhrt_scene_apply_lod: the caller's vertex list no longer describes the scene"); return VKHRT_ERR_UNSUPPORTED; }
     VK_CUDA(cudaSetDevice(sc.device));
     if (sc.n_vertices) VK_CUDA(cudaMemcpyAsync(sc.d_positions, positions_xyz, (size_t)sc.n_vertices * 12, cudaMemcpyHostToDevice, sc.stream));
     return build_scene(sc, true);
@@ -180,6 +182,35 @@ int vkhrt_scene_get_primitives(VkhrtScene* scene, float* out, size_t out_floats)
 }
 
 uint32_t vkhrt_scene_primitive_count(const VkhrtScene* scene) { return scene ? scene->s.n_prims : 0; }
+uint32_t vkhrt_scene_segment_count(const VkhrtScene* scene) { return scene ? scene->s.n_segments : 0; }
+
+int vkhrt_scene_apply_lod(VkhrtScene* scene, uint32_t line_split_passes, uint32_t line_merge_passes, uint32_t curve_merge_passes)
+{
+    if (!scene) { set_last_error("null scene"); return VKHRT_ERR_INVALID_ARGUMENT; }
+    return apply_lod(scene->s, line_split_passes, line_merge_passes, curve_merge_passes);
+}
+
+int vkhrt_scene_get_lines(VkhrtScene* scene, float* out, size_t out_floats)
+{
+    if (!scene || !out) { set_last_error("null argument"); return VKHRT_ERR_INVALID_ARGUMENT; }
+    return export_lines(scene->s, out, out_floats);
+}
+
+int vkhrt_scene_set_environment(VkhrtScene* scene, const float* rgba32f, uint32_t width, uint32_t height)
+{
+    if (!scene) { set_last_error("null scene"); return VKHRT_ERR_INVALID_ARGUMENT; }
+    DeviceScene& sc = scene->s;
+    VK_CUDA(cudaSetDevice(sc.device));
+    VK_CUDA(cudaStreamSynchronize(sc.stream));
+    cudaFree(sc.d_env); sc.d_env = nullptr; sc.env_w = sc.env_h = 0;
+    if (!rgba32f || !width || !height) return VKHRT_OK;
+    if (width > 32768u || height > 32768u) { set_last_error("environment map larger than 32768 texels on a side"); return VKHRT_ERR_UNSUPPORTED; }
+    const size_t bytes = (size_t)width * height * sizeof(float4);
+    VK_CUDA(cudaMalloc(&sc.d_env, bytes));
+    VK_CUDA(cudaMemcpy(sc.d_env, rgba32f, bytes, cudaMemcpyHostToDevice));
+    sc.env_w = width; sc.env_h = height;
+    return VKHRT_OK;
+}
 
 void vkhrt_scene_destroy(VkhrtScene* scene)
 {

@@ -24,6 +24,7 @@ struct MeshIn {
     const float* rpv;
     uint32_t n_segments;
     float radius;
+    const float* curves;    // nullable: explicit curve list (12 floats each) left by MergeCurvesFast; replaces GenerateCurves
 };
 
 VK_DEV float3 load_pos(const MeshIn& m, uint32_t v) { return f3(m.pos[3 * v], m.pos[3 * v + 1], m.pos[3 * v + 2]); }
@@ -34,6 +35,12 @@ struct Aabb { float3 lo, hi; };
 // GenerateCurves (geometry_processor.cpp:123-156), tension 1, for segment i
 VK_DEV Bezier gen_curve(const MeshIn& m, uint32_t i)
 {
+    if (m.curves) {
+        const float* c = m.curves + 12 * (size_t)i;
+        Bezier b;
+        b.p0 = f3(c[0], c[1], c[2]); b.p1 = f3(c[3], c[4], c[5]); b.p2 = f3(c[6], c[7], c[8]); b.p3 = f3(c[9], c[10], c[11]);
+        return b;
+    }
     float3 s = load_pos(m, m.idx[2 * i]), e = load_pos(m, m.idx[2 * i + 1]);
     float3 p0 = s, p3 = e;
     if (i > 0) {
@@ -490,7 +497,7 @@ int build_scene(DeviceScene& sc, bool refit_only)
     VK_CUDA(cudaSetDevice(sc.device));
     cudaStream_t st = sc.stream;
     const uint32_t n = sc.n_leaves;
-    MeshIn m{sc.d_positions, sc.d_indices, sc.d_radius_pv, sc.n_segments, sc.radius};
+    MeshIn m{sc.d_positions, sc.d_indices, sc.d_radius_pv, sc.n_segments, sc.radius, sc.d_curves};
     sc.timing = VkhrtTiming{};
     if (n == 0) { sc.n_nodes = 0; sc.built = true; return VKHRT_OK; }
     const int tech = sc.technique;
@@ -612,7 +619,7 @@ int export_primitives(DeviceScene& sc, float* host_out, size_t out_floats)
     const size_t per = sc.technique == VKHRT_TECHNIQUE_PHANTOM ? 12 : (sc.technique == VKHRT_TECHNIQUE_LSS ? 8 : 9);
     if (out_floats < (size_t)n * per) { set_last_error("export_primitives: output too small"); return VKHRT_ERR_INVALID_ARGUMENT; }
     if (n == 0) return VKHRT_OK;
-    MeshIn m{sc.d_positions, sc.d_indices, sc.d_radius_pv, sc.n_segments, sc.radius};
+    MeshIn m{sc.d_positions, sc.d_indices, sc.d_radius_pv, sc.n_segments, sc.radius, sc.d_curves};
     float* d_out = nullptr;
     VK_CUDA(cudaMalloc(&d_out, (size_t)n * per * 4));
     const uint32_t g = cdiv(n, 256);
@@ -624,6 +631,246 @@ int export_primitives(DeviceScene& sc, float* host_out, size_t out_floats)
     if (e == cudaSuccess) e = cudaStreamSynchronize(sc.stream);
     cudaFree(d_out);
     if (e != cudaSuccess) { set_last_error(std::string("export_primitives: ") + cudaGetErrorString(e)); return VKHRT_ERR_CUDA; }
+    return VKHRT_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Strand level of detail: MergeLines / SplitLines / MergeCurvesFast of
+// source/resources/model/geometry_processor.cpp:69-104, 106-121, 158-197 as device passes over the line list.
+// A line is two float4 {start.xyz, r0} {end.xyz, r1} (the per-vertex radius rides along: outer radii survive a merge,
+// a split midpoint gets the mean).  The merges are stream compactions: pair i = elements (2i, 2i+1) emits one element
+// if the two are connected (exact float compare of end/start, glm::vec3 ==) and both otherwise; like the reference,
+// the last element of an odd-sized list is dropped.  Output offsets come from the block scan of the radix sort.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) lines_from_mesh_kernel(MeshIn m, uint32_t n, float4* __restrict__ lines)
+{
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    uint32_t a = m.idx[2 * i], b = m.idx[2 * i + 1];
+    float3 s = load_pos(m, a), e = load_pos(m, b);
+    lines[2 * (size_t)i] = make_float4(s.x, s.y, s.z, m.rpv ? m.rpv[a] : m.radius);
+    lines[2 * (size_t)i + 1] = make_float4(e.x, e.y, e.z, m.rpv ? m.rpv[b] : m.radius);
+}
+__global__ void __launch_bounds__(256) lines_to_mesh_kernel(const float4* __restrict__ lines, uint32_t n, float* __restrict__ pos,
+                                                            uint32_t* __restrict__ idx, float* __restrict__ rpv)
+{
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    float4 s = lines[2 * (size_t)i], e = lines[2 * (size_t)i + 1];
+    float* p = pos + 6 * (size_t)i;
+    p[0] = s.x; p[1] = s.y; p[2] = s.z; p[3] = e.x; p[4] = e.y; p[5] = e.z;
+    idx[2 * (size_t)i] = 2 * i; idx[2 * (size_t)i + 1] = 2 * i + 1;
+    if (rpv) { rpv[2 * (size_t)i] = s.w; rpv[2 * (size_t)i + 1] = e.w; }
+}
+// SplitLines: middlePoint = (start + end) * 0.5f
+__global__ void __launch_bounds__(256) split_lines_kernel(const float4* __restrict__ in, uint32_t n, float4* __restrict__ out)
+{
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    float4 s = in[2 * (size_t)i], e = in[2 * (size_t)i + 1];
+    float4 mid = make_float4((s.x + e.x) * 0.5f, (s.y + e.y) * 0.5f, (s.z + e.z) * 0.5f, (s.w + e.w) * 0.5f);
+    float4* o = out + 4 * (size_t)i;
+    o[0] = s; o[1] = mid; o[2] = mid; o[3] = e;
+}
+VK_DEV bool same_xyz(float4 a, float4 b) { return a.x == b.x && a.y == b.y && a.z == b.z; }
+// MergeLines, pass 1: how many lines pair i emits (slot n_pairs = 0 so that the exclusive scan ends with the total)
+__global__ void __launch_bounds__(256) merge_lines_count_kernel(const float4* __restrict__ in, uint32_t n_pairs, uint32_t* __restrict__ counts)
+{
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i > n_pairs) return;
+    counts[i] = i == n_pairs ? 0u : (same_xyz(in[4 * (size_t)i + 1], in[4 * (size_t)i + 2]) ? 1u : 2u);
+}
+__global__ void __launch_bounds__(256) merge_lines_scatter_kernel(const float4* __restrict__ in, uint32_t n_pairs, const uint32_t* __restrict__ offsets,
+                                                                  float4* __restrict__ out)
+{
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_pairs) return;
+    const float4* a = in + 4 * (size_t)i;
+    float4* o = out + 2 * (size_t)offsets[i];
+    if (same_xyz(a[1], a[2])) { o[0] = a[0]; o[1] = a[3]; }
+    else { o[0] = a[0]; o[1] = a[1]; o[2] = a[2]; o[3] = a[3]; }
+}
+// GenerateCurves into an explicit array (input of MergeCurvesFast)
+__global__ void __launch_bounds__(256) curves_materialise_kernel(MeshIn m, uint32_t n, float* __restrict__ curves)
+{
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    Bezier c = gen_curve(m, i);
+    float* o = curves + 12 * (size_t)i;
+    o[0] = c.p0.x; o[1] = c.p0.y; o[2] = c.p0.z; o[3] = c.p1.x; o[4] = c.p1.y; o[5] = c.p1.z;
+    o[6] = c.p2.x; o[7] = c.p2.y; o[8] = c.p2.z; o[9] = c.p3.x; o[10] = c.p3.y; o[11] = c.p3.z;
+}
+VK_DEV bool curves_connected(const float* a, const float* b) { return a[9] == b[0] && a[10] == b[1] && a[11] == b[2]; }
+__global__ void __launch_bounds__(256) merge_curves_count_kernel(const float* __restrict__ in, uint32_t n_pairs, uint32_t* __restrict__ counts)
+{
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i > n_pairs) return;
+    counts[i] = i == n_pairs ? 0u : (curves_connected(in + 24 * (size_t)i, in + 24 * (size_t)i + 12) ? 1u : 2u);
+}
+// MergeCurvesFast: middlePoint = (a.cp2 + b.cp1) * 0.5; cp1 = (a.cp1 + middlePoint) * 0.5; cp2 = (middlePoint + b.cp2) * 0.5
+__global__ void __launch_bounds__(256) merge_curves_scatter_kernel(const float* __restrict__ in, uint32_t n_pairs, const uint32_t* __restrict__ offsets,
+                                                                   float* __restrict__ out)
+{
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_pairs) return;
+    const float* a = in + 24 * (size_t)i;
+    const float* b = a + 12;
+    float* o = out + 12 * (size_t)offsets[i];
+    if (curves_connected(a, b)) {
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            float mid = (a[6 + k] + b[3 + k]) * 0.5f;
+            o[k] = a[k];
+            o[3 + k] = (a[3 + k] + mid) * 0.5f;
+            o[6 + k] = (mid + b[6 + k]) * 0.5f;
+            o[9 + k] = b[9 + k];
+        }
+    } else {
+        for (int k = 0; k < 24; ++k) o[k] = a[k];
+    }
+}
+__global__ void __launch_bounds__(256) lines_from_curves_kernel(const float* __restrict__ curves, uint32_t n, float radius, float4* __restrict__ lines)
+{
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float* c = curves + 12 * (size_t)i;
+    lines[2 * (size_t)i] = make_float4(c[0], c[1], c[2], radius);
+    lines[2 * (size_t)i + 1] = make_float4(c[9], c[10], c[11], radius);
+}
+__global__ void __launch_bounds__(256) export_lines_kernel(MeshIn m, uint32_t n, float* __restrict__ out)
+{
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    float3 s = load_pos(m, m.idx[2 * i]), e = load_pos(m, m.idx[2 * i + 1]);
+    float* o = out + 6 * (size_t)i;
+    o[0] = s.x; o[1] = s.y; o[2] = s.z; o[3] = e.x; o[4] = e.y; o[5] = e.z;
+}
+
+// one compaction pass: counts -> exclusive scan -> total (read back) -> scatter.  `elem_floats` = 8 (line) or 12 (curve)
+template <typename T>
+static int compact_pairs(void (*count_k)(const T*, uint32_t, uint32_t*), void (*scatter_k)(const T*, uint32_t, const uint32_t*, T*),
+                         const T* in, uint32_t n, T** out, uint32_t* n_out, size_t elem_bytes, cudaStream_t st)
+{
+    const uint32_t n_pairs = n / 2;
+    *out = nullptr; *n_out = 0;
+    uint32_t* d_cnt = nullptr; uint32_t* d_tmp = nullptr;
+    VK_CUDA(cudaMalloc(&d_cnt, ((size_t)n_pairs + 1) * 4));
+    cudaError_t e = cudaMalloc(&d_tmp, scan_tmp_elems(n_pairs + 1) * 4);
+    if (e != cudaSuccess) { cudaFree(d_cnt); set_last_error("lod: out of device memory"); return VKHRT_ERR_OUT_OF_MEMORY; }
+    count_k<<<cdiv((uint64_t)n_pairs + 1, 256), 256, 0, st>>>(in, n_pairs, d_cnt);
+    count_launch();
+    int rc = exclusive_scan(d_cnt, n_pairs + 1, d_tmp, st);
+    uint32_t total = 0;
+    if (!rc) {
+        e = cudaMemcpyAsync(&total, d_cnt + n_pairs, 4, cudaMemcpyDeviceToHost, st);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+        if (e != cudaSuccess) { set_last_error(std::string("lod: ") + cudaGetErrorString(e)); rc = VKHRT_ERR_CUDA; }
+    }
+    if (!rc) {
+        e = cudaMalloc((void**)out, std::max<size_t>(1, (size_t)total) * elem_bytes);
+        if (e != cudaSuccess) { set_last_error("lod: out of device memory"); rc = VKHRT_ERR_OUT_OF_MEMORY; }
+    }
+    if (!rc && n_pairs) {
+        scatter_k<<<cdiv(n_pairs, 256), 256, 0, st>>>(in, n_pairs, d_cnt, *out);
+        count_launch();
+        e = cudaStreamSynchronize(st);
+        if (e != cudaSuccess) { set_last_error(std::string("lod: ") + cudaGetErrorString(e)); rc = VKHRT_ERR_CUDA; }
+    }
+    cudaFree(d_cnt); cudaFree(d_tmp);
+    if (rc) { cudaFree(*out); *out = nullptr; return rc; }
+    *n_out = total;
+    return VKHRT_OK;
+}
+
+int apply_lod(DeviceScene& sc, uint32_t split_passes, uint32_t merge_passes, uint32_t curve_merge_passes)
+{
+    VK_CUDA(cudaSetDevice(sc.device));
+    if (sc.built) { set_last_error("vkhrt_scene_apply_lod must be called before vkhrt_scene_build"); return VKHRT_ERR_INVALID_ARGUMENT; }
+    if (curve_merge_passes && sc.technique != VKHRT_TECHNIQUE_PHANTOM) { set_last_error("curve_merge_passes needs the PHANTOM technique (curves)"); return VKHRT_ERR_UNSUPPORTED; }
+    if (!split_passes && !merge_passes && !curve_merge_passes) return VKHRT_OK;
+    if (split_passes > 30 || ((uint64_t)sc.n_segments << split_passes) * (sc.technique == VKHRT_TECHNIQUE_DOTS ? 4 : 1) >= 0x3FFFFFFFull) {
+        set_last_error("lod: too many segments after splitting"); return VKHRT_ERR_UNSUPPORTED;
+    }
+    cudaStream_t st = sc.stream;
+    MeshIn m{sc.d_positions, sc.d_indices, sc.d_radius_pv, sc.n_segments, sc.radius, sc.d_curves};
+    uint32_t n = sc.n_segments;
+    float4* lines = nullptr;
+    VK_CUDA(cudaMalloc(&lines, std::max<size_t>(1, (size_t)n * 2) * sizeof(float4)));
+#define VK_LOD(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { set_last_error(std::string(#call) + ": " + cudaGetErrorString(e_)); cudaFree(lines); return e_ == cudaErrorMemoryAllocation ? VKHRT_ERR_OUT_OF_MEMORY : VKHRT_ERR_CUDA; } } while (0)
+    if (n) { lines_from_mesh_kernel<<<cdiv(n, 256), 256, 0, st>>>(m, n, lines); count_launch(); }
+    for (uint32_t k = 0; k < split_passes; ++k) {
+        float4* out = nullptr;
+        VK_LOD(cudaMalloc(&out, std::max<size_t>(1, (size_t)n * 4) * sizeof(float4)));
+        if (n) { split_lines_kernel<<<cdiv(n, 256), 256, 0, st>>>(lines, n, out); count_launch(); }
+        VK_LOD(cudaStreamSynchronize(st));
+        cudaFree(lines); lines = out; n *= 2;
+    }
+    for (uint32_t k = 0; k < merge_passes; ++k) {
+        float4* out = nullptr; uint32_t n_out = 0;
+        int rc = compact_pairs<float4>(merge_lines_count_kernel, merge_lines_scatter_kernel, lines, n, &out, &n_out, 2 * sizeof(float4), st);
+        if (rc) { cudaFree(lines); return rc; }
+        cudaFree(lines); lines = out; n = n_out;
+    }
+    // back to the indexed shape the generators consume (2 vertices per line), optionally through the curve merge
+    float* curves = nullptr;
+    if (curve_merge_passes) {
+        float* pos = nullptr; uint32_t* idx = nullptr;
+        VK_LOD(cudaMalloc(&pos, std::max<size_t>(1, (size_t)n * 6) * 4));
+        cudaError_t e = cudaMalloc(&idx, std::max<size_t>(1, (size_t)n * 2) * 4);
+        if (e == cudaSuccess) e = cudaMalloc(&curves, std::max<size_t>(1, (size_t)n * 12) * 4);
+        if (e != cudaSuccess) { cudaFree(pos); cudaFree(idx); cudaFree(lines); set_last_error("lod: out of device memory"); return VKHRT_ERR_OUT_OF_MEMORY; }
+        if (n) {
+            lines_to_mesh_kernel<<<cdiv(n, 256), 256, 0, st>>>(lines, n, pos, idx, nullptr);
+            MeshIn lm{pos, idx, nullptr, n, sc.radius, nullptr};
+            curves_materialise_kernel<<<cdiv(n, 256), 256, 0, st>>>(lm, n, curves);
+            count_launch(2);
+        }
+        e = cudaStreamSynchronize(st);
+        cudaFree(pos); cudaFree(idx);
+        if (e != cudaSuccess) { cudaFree(curves); cudaFree(lines); set_last_error(std::string("lod: ") + cudaGetErrorString(e)); return VKHRT_ERR_CUDA; }
+        for (uint32_t k = 0; k < curve_merge_passes; ++k) {
+            float* out = nullptr; uint32_t n_out = 0;
+            int rc = compact_pairs<float>(merge_curves_count_kernel, merge_curves_scatter_kernel, curves, n, &out, &n_out, 12 * sizeof(float), st);
+            if (rc) { cudaFree(curves); cudaFree(lines); return rc; }
+            cudaFree(curves); curves = out; n = n_out;
+        }
+        cudaFree(lines); lines = nullptr;
+        e = cudaMalloc(&lines, std::max<size_t>(1, (size_t)n * 2) * sizeof(float4));
+        if (e != cudaSuccess) { cudaFree(curves); set_last_error("lod: out of device memory"); return VKHRT_ERR_OUT_OF_MEMORY; }
+        if (n) { lines_from_curves_kernel<<<cdiv(n, 256), 256, 0, st>>>(curves, n, sc.radius, lines); count_launch(); }
+    }
+    float* pos = nullptr; uint32_t* idx = nullptr; float* rpv = nullptr;
+    cudaError_t e = cudaMalloc(&pos, std::max<size_t>(1, (size_t)n * 6) * 4);
+    if (e == cudaSuccess) e = cudaMalloc(&idx, std::max<size_t>(1, (size_t)n * 2) * 4);
+    if (e == cudaSuccess && sc.d_radius_pv && !curve_merge_passes) e = cudaMalloc(&rpv, std::max<size_t>(1, (size_t)n * 2) * 4);
+    if (e == cudaSuccess && n) { lines_to_mesh_kernel<<<cdiv(n, 256), 256, 0, st>>>(lines, n, pos, idx, rpv); count_launch(); }
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    cudaFree(lines);
+    if (e != cudaSuccess) { cudaFree(pos); cudaFree(idx); cudaFree(rpv); cudaFree(curves); set_last_error(std::string("lod: ") + cudaGetErrorString(e)); return e == cudaErrorMemoryAllocation ? VKHRT_ERR_OUT_OF_MEMORY : VKHRT_ERR_CUDA; }
+#undef VK_LOD
+    cudaFree(sc.d_positions); cudaFree(sc.d_indices); cudaFree(sc.d_radius_pv); cudaFree(sc.d_curves);
+    sc.d_positions = pos; sc.d_indices = idx; sc.d_radius_pv = rpv; sc.d_curves = curves;
+    sc.n_vertices = 2 * n; sc.n_segments = n; sc.n_leaves = n;
+    sc.n_prims = sc.technique == VKHRT_TECHNIQUE_DOTS ? 4 * n : n;
+    sc.lod_applied = true;
+    return VKHRT_OK;
+}
+
+int export_lines(DeviceScene& sc, float* host_out, size_t out_floats)
+{
+    VK_CUDA(cudaSetDevice(sc.device));
+    const uint32_t n = sc.n_segments;
+    if (out_floats < (size_t)n * 6) { set_last_error("export_lines: output too small"); return VKHRT_ERR_INVALID_ARGUMENT; }
+    if (n == 0) return VKHRT_OK;
+    MeshIn m{sc.d_positions, sc.d_indices, sc.d_radius_pv, sc.n_segments, sc.radius, nullptr};
+    float* d_out = nullptr;
+    VK_CUDA(cudaMalloc(&d_out, (size_t)n * 24));
+    export_lines_kernel<<<cdiv(n, 256), 256, 0, sc.stream>>>(m, n, d_out);
+    count_launch();
+    cudaError_t e = cudaMemcpyAsync(host_out, d_out, (size_t)n * 24, cudaMemcpyDeviceToHost, sc.stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(sc.stream);
+    cudaFree(d_out);
+    if (e != cudaSuccess) { set_last_error(std::string("export_lines: ") + cudaGetErrorString(e)); return VKHRT_ERR_CUDA; }
     return VKHRT_OK;
 }
 

@@ -471,6 +471,41 @@ VK_DEV float3 debug_palette(uint32_t prim)
     const float g[6] = {0.0f, 0.2f, 0.4f, 0.6f, 0.8f, 1.0f};
     return f3(r[i], g[i], 0.3f);
 }
+
+// ---- miss colour: shaders/miss.rmiss:17-38 ----------------------------------------------------------
+// Equirectangular lookup of normalize(-rayDirection) with a linear, repeat-addressed sampler (gpu_resources.hpp:46-50:
+// texel coordinate u*W - 0.5, fp32 weights), then 1 - exp(-c * exposure) and gamma 1/2.2.  asinf/atan2f/expf/powf are the
+// CUDA math library's (<= 2-4 ulp), so this is the one colour that is compared with the oracle to 1 LSB of the 8-bit
+// image rather than bit for bit.
+VK_DEV int wrap_texel(int i, int n) { int m = i % n; return m < 0 ? m + n : m; }
+VK_DEV float3 environment_miss(const float4* __restrict__ env, uint32_t env_w, uint32_t env_h, float3 ray_d)
+{
+    const float3 dir = fnormalize3(f3(-ray_d.x, -ray_d.y, -ray_d.z));
+    const float gy = fminf(fmaxf(dir.y, -1.0f), 1.0f);
+    const float gamma = asinf(gy);
+    const float theta = atan2f(dir.x, -dir.z);
+    const float u = fmaf(theta * 0.3183098861837f, 0.5f, 0.5f);
+    const float v = gamma * 0.3183098861837f + 0.5f;
+    const int W = (int)env_w, H = (int)env_h;
+    const float x = fmaf(u, (float)W, -0.5f), y = fmaf(v, (float)H, -0.5f);
+    const float x0 = floorf(x), y0 = floorf(y);
+    const float fx = x - x0, fy = y - y0;
+    const int i0 = wrap_texel((int)x0, W), i1 = wrap_texel((int)x0 + 1, W), j0 = wrap_texel((int)y0, H), j1 = wrap_texel((int)y0 + 1, H);
+    const float4 t00 = __ldg(env + (size_t)j0 * W + i0), t10 = __ldg(env + (size_t)j0 * W + i1);
+    const float4 t01 = __ldg(env + (size_t)j1 * W + i0), t11 = __ldg(env + (size_t)j1 * W + i1);
+    const float a[3] = {t00.x, t00.y, t00.z}, b[3] = {t10.x, t10.y, t10.z}, c[3] = {t01.x, t01.y, t01.z}, e[3] = {t11.x, t11.y, t11.z};
+    float out[3];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        const float top = fmaf(fx, b[k] - a[k], a[k]);
+        const float bot = fmaf(fx, e[k] - c[k], c[k]);
+        float r = fmaf(fy, bot - top, top);
+        r = 1.0f - expf(-(r * 1.0f));
+        out[k] = powf(r, 1.0f / 2.2f);
+    }
+    return f3(out[0], out[1], out[2]);
+}
+
 VK_DEV uint32_t to_unorm8(float c)
 {
     c = fminf(fmaxf(c, 0.0f), 1.0f);

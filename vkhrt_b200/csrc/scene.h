@@ -21,6 +21,12 @@ struct DeviceScene {
     float* d_positions = nullptr;      // n_vertices * 3
     uint32_t* d_indices = nullptr;     // n_segments * 2
     float* d_radius_pv = nullptr;      // n_vertices or null
+    float* d_curves = nullptr;         // null unless vkhrt_scene_apply_lod merged curves: n_segments * 12 floats, replaces GenerateCurves
+    bool lod_applied = false;          // the vertex list was rewritten by the LOD passes: refit with caller positions is refused
+
+    // environment map (RGBA32F, miss.rmiss)
+    float4* d_env = nullptr;
+    uint32_t env_w = 0, env_h = 0;
 
     // acceleration structure
     float4* d_nodes = nullptr;         // n_nodes * 4 float4 (VkhrtBvhNode)
@@ -69,6 +75,8 @@ void count_launch(uint64_t n = 1);
 // build.cu
 int build_scene(DeviceScene& sc, bool refit_only);
 int export_primitives(DeviceScene& sc, float* host_out, size_t out_floats);
+int apply_lod(DeviceScene& sc, uint32_t split_passes, uint32_t merge_passes, uint32_t curve_merge_passes);
+int export_lines(DeviceScene& sc, float* host_out, size_t out_floats);
 
 // trace.cu
 struct FrameParams;

@@ -378,7 +378,8 @@ __global__ void __launch_bounds__(256) raygen_kernel(const TraceParams p, float4
 // ever touches the pixels it owns whatever the output layout is.
 __global__ void __launch_bounds__(256) shade_kernel(const TraceParams p, const VkhrtHit* __restrict__ hits, int mode, float3 miss,
                                                     float4* __restrict__ accum, uchar4* __restrict__ rgba, uint32_t sample, uint32_t spp,
-                                                    const uint32_t* __restrict__ occluded, uint32_t ao_samples)
+                                                    const uint32_t* __restrict__ occluded, uint32_t ao_samples,
+                                                    const float4* __restrict__ env, uint32_t env_w, uint32_t env_h)
 {
     const unsigned long long slot64 = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (slot64 >= p.n_slots) return;
@@ -395,6 +396,11 @@ __global__ void __launch_bounds__(256) shade_kernel(const TraceParams p, const V
     if (flags & FLAG_HIT) {
         c = mode == VKHRT_SHADE_DEBUG_PRIMID ? debug_palette(__float_as_uint(h1.z)) : shade_normal(f3(h0.w, h1.x, h1.y));
         if (ao_samples) c = c * (1.0f - (float)occluded[i] / (float)ao_samples);    // unoccluded fraction of the AO rays
+    } else if (env) {
+        // miss.rmiss: the colour depends on the ray of THIS sample, regenerated here (ray_gen.rgen:16-24)
+        float3 ro, rd;
+        primary_ray(p.cam, p.W, p.H, q.px, q.py, p.sx, p.sy, &ro, &rd);
+        c = environment_miss(env, env_w, env_h, rd);
     } else c = miss;
     if (spp > 1) {
         float4 a = sample == 0 ? make_float4(0, 0, 0, 0) : accum[i];
@@ -539,6 +545,8 @@ int render_frame(DeviceScene& sc, const VkhrtFrameDesc& f, VkhrtHit* hits_out, u
     VK_CUDA(cudaSetDevice(sc.device));
     Resolved r;
     if (!resolve(f, r)) { set_last_error("vkhrt_render: bad frame description (size, tile_size multiple of 8, tile_first < tile_stride)"); return VKHRT_ERR_INVALID_ARGUMENT; }
+    if (f.miss_mode == VKHRT_MISS_ENVIRONMENT && !sc.d_env) { set_last_error("vkhrt_render: miss_mode ENVIRONMENT without vkhrt_scene_set_environment"); return VKHRT_ERR_INVALID_ARGUMENT; }
+    if (f.miss_mode != VKHRT_MISS_CONSTANT && f.miss_mode != VKHRT_MISS_ENVIRONMENT) { set_last_error("vkhrt_render: unknown miss_mode"); return VKHRT_ERR_INVALID_ARGUMENT; }
     const bool host_out = f.output_memory == VKHRT_MEM_HOST;
     if (host_out && r.tile_stride > 1 && f.row_major_output) {
         set_last_error("vkhrt_render: row_major_output with tile_stride > 1 writes into a frame buffer shared by all shards and needs device output memory");
@@ -619,8 +627,9 @@ int render_frame(DeviceScene& sc, const VkhrtFrameDesc& f, VkhrtHit* hits_out, u
         }
         if (s == 0) VK_CUDA(cudaEventRecord(ev[12], st));
         if (want_rgba) {
+            const bool env = f.miss_mode == VKHRT_MISS_ENVIRONMENT && sc.d_env;
             shade_kernel<<<(unsigned)((r.n_slots + 255) / 256), 256, 0, st>>>(p, p.hits, f.shade_mode, miss, sc.d_accum, (uchar4*)d_rgba, s, r.spp,
-                                                                              sc.d_occluded, ao);
+                                                                              sc.d_occluded, ao, env ? sc.d_env : nullptr, sc.env_w, sc.env_h);
             count_launch();
         }
         if (s == 0) VK_CUDA(cudaEventRecord(ev[9], st));
