@@ -88,3 +88,29 @@ def test_headless_matches_python_binding_and_oracle(V, O, tmp_path, tech, name):
     header = f"P6\n{W} {H}\n255\n".encode()
     assert raw.startswith(header)
     assert np.array_equal(np.frombuffer(raw[len(header):], np.uint8).reshape(-1, 3), io[:, :3])
+
+
+@pytest.mark.gpu
+def test_headless_hair_asset_lod_environment_png(V, O, tmp_path):
+    """the widened host path end to end: .hair asset -> LOD passes -> build -> environment miss shader -> PNG"""
+    import struct
+    import zlib
+    W, H = 160, 96
+    pos, idx = V.generate_groom(1500, 8, V.GROOM_CURLY)
+    asset, png, hits_path = tmp_path / "groom.hair", tmp_path / "out.png", tmp_path / "hits.bin"
+    V.save_lines(str(asset), pos, idx)
+    r = subprocess.run([EXE, "--model", str(asset), "--technique", "phantom", "--size", f"{W}x{H}", "--lod", "1,0,1", "--env", "procedural",
+                        "--png", str(png), "--hits", str(hits_path)], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    orc = O.OracleScene(pos, idx, lod=(1, 0, 1))
+    env = np.empty((512, 1024, 4), np.float32)
+    V.lib().vkhrt_environment_generate(1024, 512, env.ctypes.data)
+    orc.set_environment(env)
+    vi, pi = V.camera_matrices(aspect=float(np.float32(W) / np.float32(H)))
+    ho, io, _ = orc.render(O.make_frame(vi, pi, W, H, miss_mode=1))
+    assert np.fromfile(hits_path, dtype=V.HIT_DTYPE).tobytes() == ho.tobytes()
+    data = png.read_bytes()
+    n, = struct.unpack(">I", data[33:37])
+    assert data[37:41] == b"IDAT"
+    raw = np.frombuffer(zlib.decompress(data[41:41 + n]), np.uint8).reshape(H, 1 + 4 * W)[:, 1:].reshape(-1, 4)
+    assert np.abs(raw.astype(np.int32) - io.astype(np.int32)).max() <= 1

@@ -3,7 +3,8 @@
 // write the image and the hit buffer, print per-stage device timings.
 //
 //   vkhrt_headless --model synthetic:curly:100000:32 --technique phantom --size 1920x1080
-//                  [--spp 1] [--debug-primid] [--frames 10] [--ppm out.ppm] [--hits out.bin] [--device 0]
+//                  [--spp 1] [--debug-primid] [--frames 10] [--ppm out.ppm] [--png out.png] [--hits out.bin] [--device 0]
+//                  [--env procedural|sky.hdr] [--ao N] [--lod split,merge,curve_merge]
 //
 // Host code only: every number comes from libvkhrt_b200.so; without a CUDA device it exits with the ABI's error.
 #include <chrono>
@@ -18,14 +19,16 @@ using namespace vkhrt_host;
 
 static void usage()
 {
-    std::puts("usage: vkhrt_headless --model <file.obj | synthetic:<straight|curly>:<strands>:<segments>[:seed]>\n"
+    std::puts("usage: vkhrt_headless --model <file.obj | file.hair | synthetic:<straight|curly>:<strands>:<segments>[:seed]>\n"
               "                      [--technique phantom|lss|dots] [--size WxH] [--spp N] [--debug-primid]\n"
-              "                      [--frames N] [--ppm out.ppm] [--hits out.bin] [--device D]");
+              "                      [--frames N] [--ppm out.ppm] [--png out.png] [--hits out.bin] [--device D]\n"
+              "                      [--env procedural|file.hdr] [--ao N] [--lod split,merge,curve_merge]");
 }
 
 int main(int argc, char** argv)
 {
-    std::string model = "synthetic:curly:10000:16", ppm, hits_path, technique = "lss";
+    std::string model = "synthetic:curly:10000:16", ppm, png, hits_path, technique = "lss";
+    unsigned lod[3] = {0, 0, 0};
     RendererInitInfo info;
     int frames = 1, device = 0;
     for (int i = 1; i < argc; ++i) {
@@ -39,6 +42,10 @@ int main(int argc, char** argv)
         else if (a == "--debug-primid") info.shadeMode = VKHRT_SHADE_DEBUG_PRIMID;
         else if (a == "--frames") frames = std::atoi(next());
         else if (a == "--ppm") ppm = next();
+        else if (a == "--png") png = next();
+        else if (a == "--env") info.environmentMap = next();
+        else if (a == "--ao") info.aoSamples = (uint32_t)std::atoi(next());
+        else if (a == "--lod") { if (std::sscanf(next(), "%u,%u,%u", &lod[0], &lod[1], &lod[2]) != 3) { usage(); return 2; } }
         else if (a == "--hits") hits_path = next();
         else if (a == "--device") device = std::atoi(next());
         else { std::fprintf(stderr, "unknown argument %s\n", a.c_str()); usage(); return 2; }
@@ -47,7 +54,7 @@ int main(int argc, char** argv)
     try {
         ModelLoader loader(device);
         auto t0 = std::chrono::steady_clock::now();
-        std::shared_ptr<Model> m = loader.LoadFromFile(model, tech);
+        std::shared_ptr<Model> m = loader.LoadFromFile(model, tech, lod[0], lod[1], lod[2]);
         if (!m) return 1;
         const VkhrtTiming bt = m->Timing();
         std::printf("[MODEL LOADING] %s: %u primitives (%s), load+build %.1f ms wall, device build %.2f ms (sort %.2f, hierarchy %.2f, refit %.2f)\n",
@@ -71,6 +78,7 @@ int main(int argc, char** argv)
         for (const VkhrtHit& h : renderer.GetHits()) n_hit += h.flags & 1u;
         std::printf("hits: %zu of %zu rays\n", n_hit, renderer.GetHits().size());
         if (!ppm.empty() && !renderer.WritePPM(ppm)) { std::fprintf(stderr, "[FILE] cannot write %s\n", ppm.c_str()); return 1; }
+        if (!png.empty() && !renderer.WritePNG(png)) { std::fprintf(stderr, "[FILE] cannot write %s\n", png.c_str()); return 1; }
         if (!hits_path.empty()) {
             std::FILE* fp = std::fopen(hits_path.c_str(), "wb");
             if (!fp) { std::fprintf(stderr, "[FILE] cannot write %s\n", hits_path.c_str()); return 1; }

@@ -8,9 +8,11 @@
 //   FlyCameraCreation / FlyCamera                 include/fly_camera.hpp:7-52, source/fly_camera.cpp:25-35
 //   Renderer::Render / GetModels                  include/renderer.hpp:27-31, source/renderer.cpp:83-166,189-195
 // Differences, by design: no window, swap chain, ImGui or Vulkan objects; the technique is a run-time
-// field instead of a source edit (model_loader.cpp:334); asset import is a minimal OBJ polyline reader
-// (Assimp is not available offline) that yields the same "positions + index pairs" line mesh
-// ProcessMesh produces (model_loader.cpp:139-206), plus a `synthetic:` URI for the seeded grooms.
+// field instead of a source edit (model_loader.cpp:334); asset import goes through the ABI's line-asset readers
+// (vkhrt_asset_load_lines: OBJ polylines and Cem Yuksel HAIR files; Assimp is not available offline), which yield the
+// same "positions + index pairs" line mesh ProcessMesh produces (model_loader.cpp:139-206), plus a `synthetic:` URI
+// for the seeded grooms.  The environment map of Renderer's constructor (renderer.cpp:45-56) is a Radiance .hdr file
+// or the procedural sky; the unused LOD helpers of geometry_processor.cpp:69-197 are ModelCreation fields.
 // Error behaviour follows the reference: asset failures log and return nullptr (model_loader.cpp:280-284);
 // device failures are fatal there (abort, vk_common.cpp:5-15) and throw VkhrtError here.
 // This layer holds no compute: every number comes from libvkhrt_b200.so (CUDA); there is no CPU path.
@@ -49,6 +51,9 @@ struct ModelCreation {
     float radius = VKHRT_DEFAULT_RADIUS;
     VkhrtTechnique technique = VKHRT_TECHNIQUE_LSS;   // the reference's own default when the LSS extension exists
     std::string sceneName {};
+    // strand level of detail, run on the device before the build (vkhrt_scene_apply_lod):
+    // SplitLines / MergeLines / MergeCurvesFast of geometry_processor.cpp:69-197
+    uint32_t lineSplitPasses = 0, lineMergePasses = 0, curveMergePasses = 0;
 };
 
 // geometry_processor.hpp:4-7 — in the reference these run the generators on the host; here they only
@@ -72,7 +77,8 @@ public:
         d.technique = creation.technique;
         d.device = device;
         Check(vkhrt_scene_create(&d, &_scene), "vkhrt_scene_create");
-        int rc = vkhrt_scene_build(_scene);
+        int rc = vkhrt_scene_apply_lod(_scene, creation.lineSplitPasses, creation.lineMergePasses, creation.curveMergePasses);
+        if (rc == VKHRT_OK) rc = vkhrt_scene_build(_scene);
         if (rc != VKHRT_OK) { vkhrt_scene_destroy(_scene); _scene = nullptr; throw VkhrtError(rc, "vkhrt_scene_build"); }
     }
     ~Model() { if (_scene) vkhrt_scene_destroy(_scene); }
@@ -93,13 +99,15 @@ private:
 class ModelLoader {
 public:
     explicit ModelLoader(int device = 0) : _device(device) {}
-    // path: an OBJ file with `v x y z` and `l i j k ...` polyline records (1-based, negative = relative), or
+    // path: a line asset (.obj with `v` / `l i j k ...` polyline records, or a Cem Yuksel .hair file), or
     // "synthetic:<straight|curly>:<strands>:<segments>[:<seed>]".  Returns nullptr on failure like the reference.
-    [[nodiscard]] std::shared_ptr<Model> LoadFromFile(std::string_view path, VkhrtTechnique technique = VKHRT_TECHNIQUE_LSS)
+    [[nodiscard]] std::shared_ptr<Model> LoadFromFile(std::string_view path, VkhrtTechnique technique = VKHRT_TECHNIQUE_LSS,
+                                                      uint32_t lineSplitPasses = 0, uint32_t lineMergePasses = 0, uint32_t curveMergePasses = 0)
     {
         ModelCreation creation;
         if (!LoadModel(path, creation)) { std::fprintf(stderr, "[MODEL LOADING] Failed to load %.*s\n", (int)path.size(), path.data()); return nullptr; }
         creation.technique = technique;
+        creation.lineSplitPasses = lineSplitPasses; creation.lineMergePasses = lineMergePasses; creation.curveMergePasses = curveMergePasses;
         return ProcessModel(creation);
     }
     [[nodiscard]] static bool LoadModel(std::string_view path, ModelCreation& out)
@@ -120,25 +128,13 @@ public:
             out.indexBuffer.resize((size_t)strands * segs * 2);
             return vkhrt_groom_generate((uint32_t)strands, (uint32_t)segs, style, seed, &out.vertexBuffer[0].x, out.indexBuffer.data()) == VKHRT_OK;
         }
-        std::ifstream in(p);
-        if (!in) return false;
-        for (std::string line; std::getline(in, line);) {
-            std::stringstream ls(line);
-            std::string tag;
-            ls >> tag;
-            if (tag == "v") { vec3 v; ls >> v.x >> v.y >> v.z; if (!ls) return false; out.vertexBuffer.push_back(v); }
-            else if (tag == "l") {
-                long prev = 0; bool have = false;
-                for (std::string tok; ls >> tok;) {
-                    long i = std::atol(tok.c_str());          // "i" or "i/t"
-                    if (i == 0) return false;
-                    long idx = i > 0 ? i - 1 : (long)out.vertexBuffer.size() + i;
-                    if (idx < 0 || idx >= (long)out.vertexBuffer.size()) return false;
-                    if (have) { out.indexBuffer.push_back((uint32_t)prev); out.indexBuffer.push_back((uint32_t)idx); }
-                    prev = idx; have = true;
-                }
-            }
-        }
+        VkhrtLineAsset a {};
+        if (vkhrt_asset_load_lines(p.c_str(), &a) != VKHRT_OK) return false;
+        out.vertexBuffer.resize(a.n_vertices);
+        if (a.n_vertices) std::memcpy(&out.vertexBuffer[0].x, a.positions_xyz, (size_t)a.n_vertices * 12);
+        out.indexBuffer.assign(a.line_indices, a.line_indices + (size_t)a.n_segments * 2);
+        if (a.radius_per_vertex) out.radiusBuffer.assign(a.radius_per_vertex, a.radius_per_vertex + a.n_vertices);
+        vkhrt_asset_free(&a);
         return !out.indexBuffer.empty();
     }
 
@@ -186,12 +182,34 @@ struct RendererInitInfo {                  // stands in for VulkanInitInfo: the 
     VkhrtShadeMode shadeMode = VKHRT_SHADE;
     float missColor[3] = { 0.0f, 0.0f, 0.0f };
     bool wantHits = true, wantImage = true;
+    // environment map sampled by the miss shader (renderer.cpp:45-56, miss.rmiss): "" = constant missColor,
+    // "procedural" = the built-in sky, anything else = a Radiance .hdr file
+    std::string environmentMap {};
+    uint32_t aoSamples = 0;                // ambient-occlusion rays per primary hit (not in the reference)
 };
 
 class Renderer {
 public:
-    Renderer(const RendererInitInfo& initInfo, const std::shared_ptr<FlyCamera>& flyCamera) : _info(initInfo), _flyCamera(flyCamera) {}
-    void AddModel(const std::shared_ptr<Model>& model) { _models.push_back(model); }
+    Renderer(const RendererInitInfo& initInfo, const std::shared_ptr<FlyCamera>& flyCamera) : _info(initInfo), _flyCamera(flyCamera)
+    {
+        // Initialize scene environment map (renderer.cpp:45-56); a failed load logs and leaves the constant colour
+        if (_info.environmentMap == "procedural") {
+            _envW = 1024; _envH = 512;
+            _env.resize((size_t)_envW * _envH * 4);
+            vkhrt_environment_generate(_envW, _envH, _env.data());
+        } else if (!_info.environmentMap.empty()) {
+            float* data = nullptr;
+            if (vkhrt_image_load_hdr(_info.environmentMap.c_str(), &data, &_envW, &_envH) == VKHRT_OK) {
+                _env.assign(data, data + (size_t)_envW * _envH * 4);
+                vkhrt_image_free(data);
+            } else std::fprintf(stderr, "[IMAGE LOADING] Failed to load data for image from path [%s]\n", _info.environmentMap.c_str());
+        }
+    }
+    void AddModel(const std::shared_ptr<Model>& model)
+    {
+        if (!_env.empty()) Check(vkhrt_scene_set_environment(model->Handle(), _env.data(), _envW, _envH), "vkhrt_scene_set_environment");
+        _models.push_back(model);
+    }
     [[nodiscard]] const std::vector<std::shared_ptr<Model>>& GetModels() const { return _models; }
 
     // One frame: UpdateCameraResource + traceRaysKHR(width, height, 1) + read-back, blocking.
@@ -204,6 +222,8 @@ public:
         f.width = _info.width; f.height = _info.height; f.spp = _info.spp; f.shade_mode = _info.shadeMode;
         std::memcpy(f.miss_rgb, _info.missColor, sizeof(f.miss_rgb));
         f.output_memory = VKHRT_MEM_HOST;
+        f.miss_mode = _env.empty() ? VKHRT_MISS_CONSTANT : VKHRT_MISS_ENVIRONMENT;
+        f.ao_samples = _info.aoSamples;
         const size_t n = (size_t)_info.width * _info.height;
         if (_info.wantHits) _hits.resize(n);
         if (_info.wantImage) _image.resize(n * 4);
@@ -222,8 +242,15 @@ public:
         return (bool)out;
     }
 
+    bool WritePNG(const std::string& path) const
+    {
+        return !_image.empty() && vkhrt_image_save_png(path.c_str(), _image.data(), _info.width, _info.height) == VKHRT_OK;
+    }
+
 private:
     RendererInitInfo _info;
+    std::vector<float> _env;
+    uint32_t _envW = 0, _envH = 0;
     std::shared_ptr<FlyCamera> _flyCamera;
     std::vector<std::shared_ptr<Model>> _models;
     std::vector<VkhrtHit> _hits;
