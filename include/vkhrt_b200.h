@@ -185,6 +185,7 @@ typedef struct VkhrtTiming {
     float raygen_ms, trace_ms, shade_ms, render_total_ms;
     float h2d_ms, d2h_ms;
     float ao_ms;         /* ambient-occlusion passes of sample 0 (0 when ao_samples == 0)          */
+    float lod_ms;        /* vkhrt_scene_apply_lod: all passes, incl. the host reads of the compacted sizes */
 } VkhrtTiming;
 
 /* Per-frame traversal statistics (debug counters; filled only by vkhrt_render_stats). */

@@ -67,7 +67,7 @@ class BvhView(C.Structure):
 class Timing(C.Structure):
     _fields_ = [(k, C.c_float) for k in ("geometry_ms", "morton_ms", "sort_ms", "hierarchy_ms", "refit_ms",
                                          "build_total_ms", "raygen_ms", "trace_ms", "shade_ms",
-                                         "render_total_ms", "h2d_ms", "d2h_ms", "ao_ms")]
+                                         "render_total_ms", "h2d_ms", "d2h_ms", "ao_ms", "lod_ms")]
 
     def as_dict(self):
         return {k: float(getattr(self, k)) for k, _ in self._fields_}

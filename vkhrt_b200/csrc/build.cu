@@ -499,6 +499,7 @@ int build_scene(DeviceScene& sc, bool refit_only)
     const uint32_t n = sc.n_leaves;
     MeshIn m{sc.d_positions, sc.d_indices, sc.d_radius_pv, sc.n_segments, sc.radius, sc.d_curves};
     sc.timing = VkhrtTiming{};
+    sc.timing.lod_ms = sc.lod_ms;
     if (n == 0) { sc.n_nodes = 0; sc.built = true; return VKHRT_OK; }
     const int tech = sc.technique;
     const size_t primA_per = tech == VKHRT_TECHNIQUE_DOTS ? 4 : 2;
@@ -794,6 +795,7 @@ int apply_lod(DeviceScene& sc, uint32_t split_passes, uint32_t merge_passes, uin
     cudaStream_t st = sc.stream;
     MeshIn m{sc.d_positions, sc.d_indices, sc.d_radius_pv, sc.n_segments, sc.radius, sc.d_curves};
     uint32_t n = sc.n_segments;
+    VK_CUDA(cudaEventRecord(sc.ev[13], st));
     float4* lines = nullptr;
     VK_CUDA(cudaMalloc(&lines, std::max<size_t>(1, (size_t)n * 2) * sizeof(float4)));
 #define VK_LOD(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { set_last_error(std::string(#call) + ": " + cudaGetErrorString(e_)); cudaFree(lines); return e_ == cudaErrorMemoryAllocation ? VKHRT_ERR_OUT_OF_MEMORY : VKHRT_ERR_CUDA; } } while (0)
@@ -844,6 +846,7 @@ int apply_lod(DeviceScene& sc, uint32_t split_passes, uint32_t merge_passes, uin
     if (e == cudaSuccess) e = cudaMalloc(&idx, std::max<size_t>(1, (size_t)n * 2) * 4);
     if (e == cudaSuccess && sc.d_radius_pv && !curve_merge_passes) e = cudaMalloc(&rpv, std::max<size_t>(1, (size_t)n * 2) * 4);
     if (e == cudaSuccess && n) { lines_to_mesh_kernel<<<cdiv(n, 256), 256, 0, st>>>(lines, n, pos, idx, rpv); count_launch(); }
+    if (e == cudaSuccess) e = cudaEventRecord(sc.ev[14], st);
     if (e == cudaSuccess) e = cudaStreamSynchronize(st);
     cudaFree(lines);
     if (e != cudaSuccess) { cudaFree(pos); cudaFree(idx); cudaFree(rpv); cudaFree(curves); set_last_error(std::string("lod: ") + cudaGetErrorString(e)); return e == cudaErrorMemoryAllocation ? VKHRT_ERR_OUT_OF_MEMORY : VKHRT_ERR_CUDA; }
@@ -853,6 +856,7 @@ int apply_lod(DeviceScene& sc, uint32_t split_passes, uint32_t merge_passes, uin
     sc.n_vertices = 2 * n; sc.n_segments = n; sc.n_leaves = n;
     sc.n_prims = sc.technique == VKHRT_TECHNIQUE_DOTS ? 4 * n : n;
     sc.lod_applied = true;
+    sc.lod_ms = ev_ms(sc.ev[13], sc.ev[14]);
     return VKHRT_OK;
 }
 

@@ -22,6 +22,7 @@ struct DeviceScene {
     uint32_t* d_indices = nullptr;     // n_segments * 2
     float* d_radius_pv = nullptr;      // n_vertices or null
     float* d_curves = nullptr;         // null unless vkhrt_scene_apply_lod merged curves: n_segments * 12 floats, replaces GenerateCurves
+    float lod_ms = 0.0f;
     bool lod_applied = false;          // the vertex list was rewritten by the LOD passes: refit with caller positions is refused
 
     // environment map (RGBA32F, miss.rmiss)
