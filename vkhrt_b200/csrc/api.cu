@@ -42,7 +42,7 @@ static void free_scene(DeviceScene* sc)
     cudaFree(sc->d_nodes); cudaFree(sc->d_sorted_ids); cudaFree(sc->d_sorted_morton);
     cudaFree(sc->d_parent_internal); cudaFree(sc->d_parent_leaf); cudaFree(sc->d_refit_flags);
     cudaFree(sc->d_primA); cudaFree(sc->d_primB);
-    cudaFree(sc->d_counters); cudaFree(sc->d_hits_scratch); cudaFree(sc->d_accum); cudaFree(sc->d_rgba_scratch); cudaFree(sc->d_occluded);
+    cudaFree(sc->d_counters); cudaFree(sc->d_hits_scratch); cudaFree(sc->d_accum); cudaFree(sc->d_rgba_scratch); cudaFree(sc->d_occluded); cudaFree(sc->d_pool_overflow);
     if (sc->h_pinned) cudaFreeHost(sc->h_pinned);
     for (auto& e : sc->ev) if (e) cudaEventDestroy(e);
     if (sc->stream) cudaStreamDestroy(sc->stream);

@@ -50,7 +50,8 @@ struct DeviceScene {
     unsigned long long* d_counters = nullptr;   // [0] work counter, [1..5] stats
     VkhrtHit* d_hits_scratch = nullptr; size_t hits_scratch_n = 0;
     float4* d_accum = nullptr; size_t accum_n = 0;
-    uint32_t* d_occluded = nullptr; size_t occluded_n = 0;   // per pixel: occluded AO rays of the current sample
+    uint32_t* d_occluded = nullptr; size_t occluded_n = 0;
+    uint2* d_pool_overflow = nullptr; size_t pool_overflow_n = 0;   // trace_pool_kernel: stack entries beyond the shared-memory slots   // per pixel: occluded AO rays of the current sample
     uint8_t* d_rgba_scratch = nullptr; size_t rgba_scratch_n = 0;
     void* h_pinned = nullptr; size_t h_pinned_bytes = 0;   // staging for host outputs
 

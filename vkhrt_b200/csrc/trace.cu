@@ -44,9 +44,14 @@ struct TraceParams {
     uint32_t slot_begin, n_slots;   // this launch traces slots [slot_begin, n_slots)
     VkhrtHit* hits;
     VkhrtHit* hits_mirror;          // optional second destination (pinned host memory), same indexing
+    uint32_t hits_aligned32;        // bit 0 / 1: hits / hits_mirror are 32-byte aligned (256-bit record stores)
+    uint32_t host_dest;             // a destination is mapped host memory (zero-copy over PCIe)
     unsigned long long* counters;   // [0] next slot, [1] nodes, [2] prims, [3] hits, [4] iterations, [5] rays, [8..11] steps, [12..15] lanes
     uint32_t refill_threshold;      // lanes waiting for a new ray that trigger a refill step
     uint32_t w_node, w_leaf, w_march;   // scheduler weights (fixed point, 16 = 1.0)
+    // trace_pool_kernel
+    uint2* pool_overflow;           // stack overflow area: [resident warp][slot][PL_OVF]
+    uint32_t pool_node_lanes, pool_batch_lanes, pool_node_min;
 };
 
 // slot (processing order: tiles, inside a tile 8x4-pixel blocks so one warp = one coherent packet)
@@ -68,12 +73,27 @@ VK_DEV PixelRef slot_to_pixel(const TraceParams& p, uint32_t slot)
     return q;
 }
 
+// One 32-byte record = one 256-bit store (STG.E.256, sm_100) when the buffer is 32-byte aligned: a record that goes out to
+// pinned host memory then crosses PCIe as ONE 32-byte write instead of two 16-byte ones.
+VK_DEV void store_record(VkhrtHit* dst, bool aligned32, const float4& a, const float4& b)
+{
+    if (aligned32) {
+        asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(dst), "r"(__float_as_uint(a.x)), "r"(__float_as_uint(a.y)),
+                     "r"(__float_as_uint(a.z)), "r"(__float_as_uint(a.w)), "r"(__float_as_uint(b.x)), "r"(__float_as_uint(b.y)),
+                     "r"(__float_as_uint(b.z)), "r"(__float_as_uint(b.w))
+                     : "memory");
+    } else {
+        float4* h = reinterpret_cast<float4*>(dst);
+        h[0] = a; h[1] = b;
+    }
+}
+template <bool WIDE = true>
 VK_DEV void store_hit(const TraceParams& p, size_t i, float t, uint32_t seg, float u, float3 n, uint32_t prim, uint32_t flags)
 {
     const float4 a = make_float4(t, __uint_as_float(seg), u, n.x);
     const float4 b = make_float4(n.y, n.z, __uint_as_float(prim), __uint_as_float(flags));
-    if (p.hits) { float4* h = reinterpret_cast<float4*>(p.hits + i); h[0] = a; h[1] = b; }
-    if (p.hits_mirror) { float4* h = reinterpret_cast<float4*>(p.hits_mirror + i); h[0] = a; h[1] = b; }
+    if (p.hits) store_record(p.hits + i, WIDE && (p.hits_aligned32 & 1u) != 0u, a, b);
+    if (p.hits_mirror) store_record(p.hits_mirror + i, WIDE && (p.hits_aligned32 & 2u) != 0u, a, b);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -355,6 +375,333 @@ __global__ void __launch_bounds__(TR_BLOCK, MINB) trace_kernel(const TraceParams
 }
 
 // ------------------------------------------------------------------------------------------------
+// Phantom primary rays, closest hit: per-warp RAY POOL.
+//
+// trace_kernel ties a ray to a lane for its whole life, so a lane whose ray waits for a leaf test or a cone iteration is
+// dead weight in every node step (17 of 32 lanes active), and the leaf / march steps run with ~10 / ~9 lanes.  Here a
+// warp owns S ray SLOTS in shared memory (S = 64 = 2 per lane: origin, direction, 1/d, tcur, best hit, stack) and rays
+// move between queues of slot ids instead of waiting inside a lane:
+//   READY  rays that want node steps     -> lanes pull them whenever they are free ("top-up"), traverse until the ray
+//                                           reaches a leaf (-> LEAF) or its stack runs empty (-> DONE)
+//   LEAF   rays standing at a leaf       -> batch of up to 32: the Prhi bounding-cylinder early-out; reject -> READY, pass -> CAND
+//   CAND   rays with a candidate curve   -> set-up batch (ray-centric transform + quarter-chord filter) into the lanes'
+//                                           MARCH registers; reject -> READY.  A lane's march persists across phases and is a
+//                                           different ray from the one the lane traverses; cone iterations run as a phase of
+//                                           their own while enough lanes hold one; a finished march commits into its ray's slot
+//                                           (one outstanding candidate per ray: no race) -> READY
+//   DONE   finished rays                 -> batch: hit records written, slots refilled with new primary rays -> READY
+// Nothing is speculated: a ray's own sequence of node visits and candidate tests is exactly trace_kernel's (and the
+// oracle's), so hit records AND traversal counters are identical; only which lane executes which step changes.
+// Everything is warp-synchronous (queues are per warp), so there is no inter-warp protocol to get wrong.
+// ------------------------------------------------------------------------------------------------
+constexpr int PL_OVF = 96;             // spill entries per slot (Karras depth <= 64 + 32)
+constexpr uint32_t REF_POP = REF_NONE; // slot.cur marker: the ray resumes by popping its stack
+constexpr int PL_MINB = 8;             // CTAs per SM the register allocation is held to
+enum : int { Q_READY = 0, Q_LEAF = 1, Q_CAND = 2, Q_DONE = 3, Q_FREE = 4 };
+
+// 115 bytes per slot.  The origin is the camera position for every primary ray (kernel parameter) and -(o/d) is rebuilt
+// from it when a lane pulls the ray, so a slot stores only d and 1/d; the best hit is (tcur, leaf position, u) — the
+// primitive id lives in the leaf record.
+// PL_S = ray slots per warp; PL_STK = shared-memory stack window per slot (the TOP entries; older ones spill to global);
+// RCP = 1/d is stored in the slot (else rebuilt with three IEEE divisions when a lane pulls the ray)
+template <int PL_S, int PL_STK, bool RCP>
+struct PoolWarp {
+    uint2 stack[PL_STK][PL_S];         // ring: entry k of the stack sits at [k % PL_STK] while it is among the top PL_STK
+    float dir[RCP ? 6 : 3][PL_S];      // d.xyz, 1/d
+    float tcur[PL_S];
+    uint32_t cur[PL_S], best_pos[PL_S];
+    float best_u[PL_S];
+    uint32_t out_idx[PL_S];
+    uint8_t sp[PL_S], spilled[PL_S];   // stack size, and how many of its bottom entries live in the global spill area
+    uint8_t q[5][PL_S];
+};
+
+template <bool STATS, int PL_S, int PL_STK, bool RCP>
+__global__ void __launch_bounds__(TR_BLOCK, PL_MINB) trace_pool_kernel(const TraceParams p)
+{
+    __shared__ PoolWarp<PL_S, PL_STK, RCP> sh_all[TR_BLOCK / 32];
+    const unsigned FULL = 0xffffffffu;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const unsigned lt = (1u << lane) - 1u;
+    PoolWarp<PL_S, PL_STK, RCP>& sh = sh_all[warp];
+    uint2* const ovf_base = p.pool_overflow + ((size_t)(blockIdx.x * (TR_BLOCK / 32) + warp) * PL_S) * PL_OVF;
+    const float3 o = f3(p.cam.vi[12], p.cam.vi[13], p.cam.vi[14]);     // ray_gen.rgen:22: every primary ray starts at the camera
+
+    // the ray this lane traverses
+    bool has = false;
+    uint32_t slot = 0, cur = REF_POP, state = ST_POP;
+    int sp = 0, spilled = 0, rtop = 0;      // rtop = ring position of the next push (= sp mod PL_STK)
+    float3 id = f3(0, 0, 0), noid = f3(0, 0, 0);
+    float tcur = 0.0f;
+    // the candidate this lane marches (a different ray)
+    bool mhave = false;
+    MarchState ms;
+    ms.c.p0 = ms.c.p1 = ms.c.p2 = ms.c.p3 = f3(0, 0, 0);
+    ms.t = ms.told = ms.dt1 = ms.dt2 = ms.t_start = 0.0f; ms.it = 0u;
+    uint32_t m_slot = 0;
+    // queue fills (warp-uniform)
+    uint32_t nR = 0, nL = 0, nC = 0, nD = 0, nF = PL_S;
+    bool exhausted = false;
+    uint32_t st_nodes = 0, st_prims = 0, st_iters = 0, st_hits = 0, st_rays = 0;
+    uint32_t sc_steps[4] = {0, 0, 0, 0}, sc_lanes[4] = {0, 0, 0, 0};
+
+    for (int k = lane; k < PL_S; k += 32) sh.q[Q_FREE][k] = (uint8_t)k;
+    __syncwarp();
+
+    auto enqueue = [&](int qi, uint32_t& n, bool pred, uint32_t s) {
+        const unsigned m = __ballot_sync(FULL, pred);
+        if (pred) sh.q[qi][n + __popc(m & lt)] = (uint8_t)s;
+        n += __popc(m);
+    };
+    // the shared-memory ring holds the top PL_STK entries; when it is full the OLDEST entry moves to the global spill area,
+    // and comes back only when everything above it has been popped
+    constexpr bool POW2 = (PL_STK & (PL_STK - 1)) == 0;
+    auto push = [&](uint32_t ref, float tn) {
+        if (POW2) rtop = sp & (PL_STK - 1);
+        // ring full: its oldest entry sits exactly where the new one goes
+        if (sp - spilled == PL_STK) { ovf_base[(size_t)slot * PL_OVF + spilled] = sh.stack[rtop][slot]; ++spilled; }
+        sh.stack[rtop][slot] = make_uint2(ref, __float_as_uint(tn));
+        ++sp;
+        if (!POW2) rtop = rtop + 1 == PL_STK ? 0 : rtop + 1;
+    };
+    auto pop_one = [&]() {
+        if (sp == 0) { state = ST_DONE; return; }
+        --sp;
+        if (POW2) rtop = sp & (PL_STK - 1);
+        else rtop = rtop == 0 ? PL_STK - 1 : rtop - 1;
+        uint2 e;
+        if (sp < spilled) { --spilled; e = ovf_base[(size_t)slot * PL_OVF + sp]; }
+        else e = sh.stack[rtop][slot];
+        if (__uint_as_float(e.y) <= tcur) { cur = e.x; state = (e.x & VKHRT_BVH_LEAF) ? ST_LEAF : ST_NODE; }
+    };
+
+    for (;;) {
+        // ---------------- top-up: free lanes pull READY rays ----------------
+        {
+            const unsigned idle = __ballot_sync(FULL, !has);
+            if (nR > 0u && idle != 0u) {
+                const uint32_t rank = __popc(idle & lt);
+                if (!has && rank < nR) {
+                    slot = sh.q[Q_READY][nR - 1u - rank];
+                    if (RCP) id = f3(sh.dir[3][slot], sh.dir[4][slot], sh.dir[5][slot]);
+                    else id = f3(safe_rcp(sh.dir[0][slot]), safe_rcp(sh.dir[1][slot]), safe_rcp(sh.dir[2][slot]));
+                    noid = f3(-(o.x * id.x), -(o.y * id.y), -(o.z * id.z));
+                    tcur = sh.tcur[slot]; cur = sh.cur[slot]; sp = (int)sh.sp[slot]; spilled = (int)sh.spilled[slot];
+                    if (!POW2) rtop = sp % PL_STK;
+                    state = cur == REF_POP ? ST_POP : ST_NODE;
+                    has = true;
+                }
+                nR -= min(nR, (uint32_t)__popc(idle));
+                __syncwarp();
+            }
+        }
+        const uint32_t nHave = __popc(__ballot_sync(FULL, has));
+        const uint32_t nM = __popc(__ballot_sync(FULL, mhave));
+        const uint32_t nRet = exhausted ? nD : nD + nF;
+        if ((nHave | nM | nR | nL | nC | nRet) == 0u) break;
+
+        // ---------------- scheduler ----------------
+        enum : int { PH_NODE, PH_LEAF, PH_SETUP, PH_MARCH, PH_RETIRE };
+        int phase;
+        {
+            const uint32_t sS = min(nC, 32u - nM);
+            const uint32_t sR = min(nRet, 32u);
+            uint32_t best = nL; int bp = PH_LEAF;
+            if (sS > best) { best = sS; bp = PH_SETUP; }
+            if (nM > best || (nM == 32u)) { best = nM; bp = PH_MARCH; }
+            if (sR > best) { best = sR; bp = PH_RETIRE; }
+            if (!exhausted && nF >= 32u) phase = PH_RETIRE;                    // fill the pool first
+            else if (nHave >= p.pool_node_lanes) phase = PH_NODE;
+            else if (best >= p.pool_batch_lanes) phase = bp;
+            else if (nHave >= p.pool_node_min) phase = PH_NODE;
+            else if (best > 0u) phase = bp;
+            else phase = PH_NODE;
+        }
+
+        if (phase == PH_NODE) {
+            // ---------------- internal nodes (same step as trace_kernel) ----------------
+            uint32_t n0 = nHave, n1;
+            do {
+                if (STATS) { sc_steps[0]++; sc_lanes[0] += __popc(__ballot_sync(FULL, has && state <= ST_POP)); }
+                if (has) {
+                    if (state == ST_POP) pop_one();
+                    if (state == ST_NODE) {
+                        const float4* nd = p.nodes + 4 * (size_t)cur;
+                        const float4 q0 = __ldg(nd), q1 = __ldg(nd + 1), q2 = __ldg(nd + 2), q3 = __ldg(nd + 3);
+                        if (STATS) st_nodes++;
+                        float tn0, tn1;
+                        const bool h0 = slab_test(xyz(q0), xyz(q1), id, noid, p.tmin, tcur, &tn0);
+                        const bool h1 = slab_test(xyz(q2), xyz(q3), id, noid, p.tmin, tcur, &tn1);
+                        const uint32_t c0 = __float_as_uint(q0.w), c1 = __float_as_uint(q1.w);
+                        const bool both = h0 && h1;
+                        const bool second = both ? (tn1 < tn0) : h1;
+                        const uint32_t near_ref = second ? c1 : c0, far_ref = second ? c0 : c1;
+                        if (both) push(far_ref, second ? tn0 : tn1);
+                        if (h0 || h1) { cur = near_ref; if (near_ref & VKHRT_BVH_LEAF) state = ST_LEAF; }
+                        else state = ST_POP;
+                    }
+                }
+                n1 = __popc(__ballot_sync(FULL, has && state <= ST_POP));
+            } while (n1 * 4u >= n0 * 3u && n1 > 0u);
+            // rays that left the node state go to their queues; the lane is free again
+            const bool to_leaf = has && state == ST_LEAF, to_done = has && state == ST_DONE;
+            if (to_leaf) { sh.cur[slot] = cur; sh.sp[slot] = (uint8_t)sp; sh.spilled[slot] = (uint8_t)spilled; }
+            enqueue(Q_LEAF, nL, to_leaf, slot);
+            enqueue(Q_DONE, nD, to_done, slot);
+            if (to_leaf || to_done) has = false;
+            __syncwarp();
+        } else if (phase == PH_LEAF) {
+            // ---------------- leaves: Prhi early-out (hair_intersection.rint:20-33, rmax precomputed) ----------------
+            const uint32_t n = min(nL, 32u);
+            const bool act = (uint32_t)lane < n;
+            if (STATS) { sc_steps[1]++; sc_lanes[1] += n; }
+            uint32_t s = 0;
+            bool pass = false;
+            if (act) {
+                s = sh.q[Q_LEAF][nL - 1u - lane];
+                const float3 d = f3(sh.dir[0][s], sh.dir[1][s], sh.dir[2][s]);
+                const uint32_t pos = sh.cur[s] & 0x7FFFFFFFu;
+                if (STATS) st_prims++;
+                const float4 a0 = __ldg(p.primA + 2 * (size_t)pos), a1 = __ldg(p.primA + 2 * (size_t)pos + 1);
+                pass = ray_hits_cylinder(o, d, xyz(a0), xyz(a1), a0.w);
+                if (!pass) sh.cur[s] = REF_POP;
+            }
+            nL -= n;
+            __syncwarp();
+            enqueue(Q_CAND, nC, act && pass, s);
+            enqueue(Q_READY, nR, act && !pass, s);
+            __syncwarp();
+        } else if (phase == PH_SETUP) {
+            // ---------------- candidates: ray-centric transform + quarter-chord filter into free MARCH registers ----------------
+            const unsigned midle = __ballot_sync(FULL, !mhave);
+            const uint32_t rank = __popc(midle & lt);
+            const bool take = !mhave && rank < nC;
+            if (STATS) { sc_steps[1]++; sc_lanes[1] += __popc(__ballot_sync(FULL, take)); }
+            bool reject = false;
+            if (take) {
+                m_slot = sh.q[Q_CAND][nC - 1u - rank];
+                const float3 d = f3(sh.dir[0][m_slot], sh.dir[1][m_slot], sh.dir[2][m_slot]);
+                const uint32_t pos = sh.cur[m_slot] & 0x7FFFFFFFu;
+                const float4 a0 = __ldg(p.primA + 2 * (size_t)pos), a1 = __ldg(p.primA + 2 * (size_t)pos + 1);
+                const float4 b0 = __ldg(p.primB + 2 * (size_t)pos), b1 = __ldg(p.primB + 2 * (size_t)pos + 1);
+                Bezier w;
+                w.p0 = xyz(a0); w.p1 = xyz(b0); w.p2 = xyz(b1); w.p3 = xyz(a1);
+                march_begin(ms, make_ray_frame(d), o, w);
+                if (quarter_chords_near_ray(ms.c, p.radius, b0.w)) mhave = true;
+                else { reject = true; sh.cur[m_slot] = REF_POP; }
+            }
+            nC -= min(nC, (uint32_t)__popc(midle));
+            __syncwarp();
+            enqueue(Q_READY, nR, reject, m_slot);
+            __syncwarp();
+        } else if (phase == PH_MARCH) {
+            // ---------------- Phantom cone iterations (hair_intersection.rint:56-126) ----------------
+            uint32_t n0 = nM, n1;
+            do {
+                if (STATS) { sc_steps[2]++; sc_lanes[2] += __popc(__ballot_sync(FULL, mhave)); }
+                bool fin = false;
+                if (mhave) {
+                    if (STATS) st_iters++;
+                    float t = 0.0f, u = 0.0f;
+                    const int r = march_step(ms, p.radius, &t, &u);
+                    if (r != MARCH_CONTINUE) {
+                        mhave = false; fin = true;
+                        const uint32_t pos = sh.cur[m_slot] & 0x7FFFFFFFu;       // the slot still points at the candidate's leaf
+                        // hair_intersection.rint:146-148 (report only tHit > 0), reportIntersectionEXT interval, tie rule of `commit`
+                        if (r == MARCH_HIT && t > 0.0f && t >= p.tmin) {
+                            const float tc = sh.tcur[m_slot];
+                            bool take_it = t < tc;
+                            if (t == tc) {
+                                const uint32_t bpos = sh.best_pos[m_slot];
+                                const uint32_t prim = __float_as_uint(__ldg(p.primA + 2 * (size_t)pos + 1).w);
+                                take_it = bpos == PRIM_NONE || prim < __float_as_uint(__ldg(p.primA + 2 * (size_t)bpos + 1).w);
+                            }
+                            if (take_it) { sh.tcur[m_slot] = t; sh.best_pos[m_slot] = pos; sh.best_u[m_slot] = u; }
+                        }
+                        sh.cur[m_slot] = REF_POP;
+                    }
+                }
+                enqueue(Q_READY, nR, fin, m_slot);
+                n1 = __popc(__ballot_sync(FULL, mhave));
+            } while (n1 * 4u >= n0 * 3u && n1 > 0u);
+            __syncwarp();
+        } else {
+            // ---------------- retire finished rays, refill their slots (and free ones) with new primary rays ----------------
+            const uint32_t n_d = min(nD, 32u);
+            const uint32_t n_f = exhausted ? 0u : min(nF, 32u - n_d);
+            const bool act_d = (uint32_t)lane < n_d, act_f = !act_d && (uint32_t)lane - n_d < n_f;
+            if (STATS) { sc_steps[3]++; sc_lanes[3] += n_d + n_f; }
+            uint32_t s = 0;
+            if (act_d) s = sh.q[Q_DONE][nD - 1u - lane];
+            else if (act_f) s = sh.q[Q_FREE][nF - 1u - ((uint32_t)lane - n_d)];
+            nD -= n_d; nF -= n_f;
+            if (act_d) {
+                const uint32_t pos = sh.best_pos[s], oi = sh.out_idx[s];
+                if (pos != PRIM_NONE) {
+                    // hair_intersection.rint:74-76 from the committed (t, u)
+                    const float t = sh.tcur[s], u = sh.best_u[s];
+                    const float3 d = f3(sh.dir[0][s], sh.dir[1][s], sh.dir[2][s]);
+                    const float4 a0 = __ldg(p.primA + 2 * (size_t)pos), a1 = __ldg(p.primA + 2 * (size_t)pos + 1);
+                    const float4 b0 = __ldg(p.primB + 2 * (size_t)pos), b1 = __ldg(p.primB + 2 * (size_t)pos + 1);
+                    Bezier w;
+                    w.p0 = xyz(a0); w.p1 = xyz(b0); w.p2 = xyz(b1); w.p3 = xyz(a1);
+                    const uint32_t prim = __float_as_uint(a1.w);
+                    const float3 n = fnormalize3(fmadd3(t, d, o) - bezier_point(w, u));
+                    store_hit<false>(p, oi, t, prim, u, n, prim, FLAG_HIT);
+                    if (STATS) st_hits++;
+                } else {
+                    store_hit<false>(p, oi, __int_as_float(0x7f800000), VKHRT_MISS_SEGMENT, 0.0f, f3(0, 0, 0), PRIM_NONE, 0u);
+                }
+            }
+            const bool want = (act_d || act_f) && !exhausted;
+            const unsigned wm = __ballot_sync(FULL, want);
+            unsigned long long base = 0;
+            if (lane == 0 && wm) base = atomicAdd(p.counters, (unsigned long long)__popc(wm));
+            base = __shfl_sync(FULL, base, 0);
+            bool fresh = false;
+            if (want) {
+                const unsigned long long slot64 = p.slot_begin + base + (unsigned)__popc(wm & lt);
+                if (slot64 < (unsigned long long)p.n_slots) {
+                    const PixelRef q = slot_to_pixel(p, (uint32_t)slot64);
+                    if (q.valid) {
+                        float3 ro, d;
+                        primary_ray(p.cam, p.W, p.H, q.px, q.py, p.sx, p.sy, &ro, &d);
+                        sh.dir[0][s] = d.x; sh.dir[1][s] = d.y; sh.dir[2][s] = d.z;
+                        if (RCP) { sh.dir[3][s] = safe_rcp(d.x); sh.dir[4][s] = safe_rcp(d.y); sh.dir[5][s] = safe_rcp(d.z); }
+                        sh.tcur[s] = p.tmax; sh.cur[s] = 0u; sh.sp[s] = 0; sh.spilled[s] = 0;
+                        sh.best_pos[s] = PRIM_NONE; sh.best_u[s] = 0.0f; sh.out_idx[s] = q.out;
+                        fresh = true;
+                        if (STATS) st_rays++;
+                    } else if (p.compact) {
+                        store_hit<false>(p, q.out, __int_as_float(0x7f800000), VKHRT_MISS_SEGMENT, 0.0f, f3(0, 0, 0), PRIM_NONE, FLAG_PADDING);
+                    }
+                }
+            }
+            if (wm && p.slot_begin + base + (unsigned)__popc(wm) >= (unsigned long long)p.n_slots) exhausted = true;
+            __syncwarp();
+            enqueue(Q_READY, nR, fresh, s);
+            enqueue(Q_FREE, nF, (act_d || act_f) && !fresh, s);
+            __syncwarp();
+        }
+    }
+
+    if (STATS) {
+#pragma unroll
+        for (int k = 16; k > 0; k >>= 1) {
+            st_nodes += __shfl_xor_sync(FULL, st_nodes, k); st_prims += __shfl_xor_sync(FULL, st_prims, k);
+            st_iters += __shfl_xor_sync(FULL, st_iters, k); st_hits += __shfl_xor_sync(FULL, st_hits, k);
+            st_rays += __shfl_xor_sync(FULL, st_rays, k);
+        }
+        if (lane == 0) {
+            atomicAdd(p.counters + 1, (unsigned long long)st_nodes); atomicAdd(p.counters + 2, (unsigned long long)st_prims);
+            atomicAdd(p.counters + 3, (unsigned long long)st_hits); atomicAdd(p.counters + 4, (unsigned long long)st_iters);
+            atomicAdd(p.counters + 5, (unsigned long long)st_rays);
+            for (int k = 0; k < 4; ++k) { atomicAdd(p.counters + 8 + k, (unsigned long long)sc_steps[k]); atomicAdd(p.counters + 12 + k, (unsigned long long)sc_lanes[k]); }
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
 // wavefront ray generator: one 32-byte record per ray {o, tmin, d, tmax}, in slot order
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) raygen_kernel(const TraceParams p, float4* __restrict__ rays)
@@ -481,11 +828,13 @@ static void fill_params(const DeviceScene& sc, const VkhrtFrameDesc& f, const Re
     p.W = r.W; p.H = r.H; p.sx = 0.5f; p.sy = 0.5f; p.tmin = r.tmin; p.tmax = r.tmax;
     p.T = r.T; p.tiles_x = r.tiles_x; p.n_tiles = r.n_tiles; p.tile_first = r.tile_first; p.tile_stride = r.tile_stride; p.compact = r.compact ? 1u : 0u;
     p.rays = nullptr; p.slot_begin = 0; p.n_slots = (uint32_t)r.n_slots; p.hits = nullptr; p.hits_mirror = nullptr; p.counters = sc.d_counters;
+    p.host_dest = 0u; p.hits_aligned32 = 0u; p.pool_overflow = nullptr;
     p.ao_hits = nullptr; p.ao_occluded = nullptr; p.ao_index = p.ao_sample = 0u; p.ao_distance = 0.0f; p.ao_bias = 0.0f;
 }
 
 // scheduler tunables (defaults from the sweep in profiles/; overridable for experiments)
 static int g_refill_threshold = -1, g_blocks_per_sm = -1, g_w_node = -1, g_w_leaf = -1, g_w_march = -1, g_min_blocks = -1;
+static int g_pool = 1, g_pool_stats = 1, g_pool_node_lanes = 24, g_pool_batch_lanes = 8, g_pool_node_min = 8;
 static int env_int(const char* name, int def) { const char* v = getenv(name); return v ? atoi(v) : def; }
 static void tunables(TraceParams& p)
 {
@@ -496,13 +845,19 @@ static void tunables(TraceParams& p)
         g_w_node = env_int("VKHRT_W_NODE", 16);
         g_w_leaf = env_int("VKHRT_W_LEAF", 32);
         g_w_march = env_int("VKHRT_W_MARCH", 32);
+        g_pool = env_int("VKHRT_POOL", 1);                       // Phantom primary rays: trace_pool_kernel
+        g_pool_stats = env_int("VKHRT_POOL_STATS", 1);           // scheduler statistics of the pool kernel instead of trace_kernel's
+        g_pool_node_lanes = env_int("VKHRT_POOL_NODE_LANES", 24);
+        g_pool_batch_lanes = env_int("VKHRT_POOL_BATCH_LANES", 8);
+        g_pool_node_min = env_int("VKHRT_POOL_NODE_MIN", 8);
     }
+    p.pool_node_lanes = (uint32_t)g_pool_node_lanes; p.pool_batch_lanes = (uint32_t)g_pool_batch_lanes; p.pool_node_min = (uint32_t)g_pool_node_min;
     p.refill_threshold = (uint32_t)std::max(1, g_refill_threshold);
     p.w_node = (uint32_t)g_w_node; p.w_leaf = (uint32_t)g_w_leaf; p.w_march = (uint32_t)g_w_march;
 }
 
 template <int TECH, bool STATS, int SRC, bool ANYHIT, int MINB>
-static int launch_trace_t(const DeviceScene& sc, TraceParams& p, cudaStream_t st)
+static int launch_trace_t(DeviceScene& sc, TraceParams& p, cudaStream_t st)
 {
     int per_sm = 0;
     VK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, trace_kernel<TECH, STATS, SRC, ANYHIT, MINB>, TR_BLOCK, 0));
@@ -515,12 +870,52 @@ static int launch_trace_t(const DeviceScene& sc, TraceParams& p, cudaStream_t st
     count_launch();
     return VKHRT_OK;
 }
+template <bool STATS, int PL_S, int PL_STK, bool RCP>
+static int launch_pool_t(DeviceScene& sc, TraceParams& p, cudaStream_t st)
+{
+    int per_sm = 0;
+    const int carve = env_int("VKHRT_CARVEOUT", -1);
+    if (carve >= 0) VK_CUDA(cudaFuncSetAttribute(trace_pool_kernel<STATS, PL_S, PL_STK, RCP>, cudaFuncAttributePreferredSharedMemoryCarveout, carve));
+    VK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, trace_pool_kernel<STATS, PL_S, PL_STK, RCP>, TR_BLOCK, 0));
+    if (per_sm < 1) per_sm = 1;
+    if (g_blocks_per_sm > 0) per_sm = std::min(per_sm, g_blocks_per_sm);
+    unsigned long long want = ((unsigned long long)(p.n_slots - p.slot_begin) + TR_BLOCK - 1) / TR_BLOCK;
+    unsigned grid = (unsigned)std::min<unsigned long long>((unsigned long long)sc.sm_count * per_sm, std::max<unsigned long long>(want, 1ull));
+    const size_t ovf = (size_t)grid * (TR_BLOCK / 32) * PL_S * PL_OVF;
+    if (sc.pool_overflow_n < ovf) {
+        if (sc.d_pool_overflow) cudaFree(sc.d_pool_overflow);
+        sc.d_pool_overflow = nullptr; sc.pool_overflow_n = 0;
+        VK_CUDA(cudaMalloc(&sc.d_pool_overflow, ovf * sizeof(uint2)));
+        sc.pool_overflow_n = ovf;
+    }
+    p.pool_overflow = sc.d_pool_overflow;
+    trace_pool_kernel<STATS, PL_S, PL_STK, RCP><<<grid, TR_BLOCK, 0, st>>>(p);
+    count_launch();
+    return VKHRT_OK;
+}
+template <bool STATS>
+static int launch_pool(DeviceScene& sc, TraceParams& p, cudaStream_t st)
+{
+    switch (env_int("VKHRT_POOL_CFG", 0)) {
+    case 1: return launch_pool_t<STATS, 64, 6, true>(sc, p, st);
+    case 2: return launch_pool_t<STATS, 56, 6, true>(sc, p, st);
+    case 3: return launch_pool_t<STATS, 72, 6, false>(sc, p, st);
+    case 4: return launch_pool_t<STATS, 64, 8, false>(sc, p, st);
+    case 5: return launch_pool_t<STATS, 64, 4, true>(sc, p, st);
+    default: return launch_pool_t<STATS, 56, 8, true>(sc, p, st);
+    }
+}
 template <bool STATS, int SRC, bool ANYHIT>
-static int launch_trace(const DeviceScene& sc, TraceParams& p, cudaStream_t st)
+static int launch_trace(DeviceScene& sc, TraceParams& p, cudaStream_t st)
 {
     tunables(p);
+    p.hits_aligned32 = (((uintptr_t)p.hits & 31u) == 0u ? 1u : 0u) | (((uintptr_t)p.hits_mirror & 31u) == 0u ? 2u : 0u);
+    if (env_int("VKHRT_STORE256", 1) == 0) p.hits_aligned32 = 0u;
     switch (sc.technique) {
     case VKHRT_TECHNIQUE_PHANTOM:
+        // records that go straight to pinned host memory keep trace_kernel: its retiring lanes are pixel neighbours, which the
+        // PCIe write path combines better (e2e 997 vs 819 Mrays/s on C2)
+        if (SRC == SRC_PRIMARY && !ANYHIT && g_pool && p.n_prims && (!STATS || g_pool_stats) && !(p.host_dest && env_int("VKHRT_POOL_HOST", 0) == 0)) return launch_pool<STATS>(sc, p, st);
         if (!STATS && SRC == SRC_PRIMARY && g_min_blocks == 7) return launch_trace_t<VKHRT_TECHNIQUE_PHANTOM, false, SRC_PRIMARY, false, 7>(sc, p, st);
         if (!STATS && SRC == SRC_PRIMARY && g_min_blocks == 8) return launch_trace_t<VKHRT_TECHNIQUE_PHANTOM, false, SRC_PRIMARY, false, 8>(sc, p, st);
         return launch_trace_t<VKHRT_TECHNIQUE_PHANTOM, STATS, SRC, ANYHIT, TR_MIN_BLOCKS>(sc, p, st);
@@ -604,6 +999,7 @@ int render_frame(DeviceScene& sc, const VkhrtFrameDesc& f, VkhrtHit* hits_out, u
         sample_offset(s, &p.sx, &p.sy);
         p.hits = s == 0 ? d_hits0 : d_hits_other;
         p.hits_mirror = s == 0 ? (h_hits_mapped ? h_hits_mapped : d_hits_mirror) : nullptr;
+        p.host_dest = (s == 0 && (direct_to_host || h_hits_mapped)) ? 1u : 0u;
         VK_CUDA(cudaMemsetAsync(sc.d_counters, 0, sizeof(unsigned long long), st));
         if (s == 0) VK_CUDA(cudaEventRecord(ev[7], st));
         rc = stats ? launch_trace<true, SRC_PRIMARY, false>(sc, p, st) : launch_trace<false, SRC_PRIMARY, false>(sc, p, st);
