@@ -16,7 +16,7 @@ launches)
   timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/${tag}_launches.csv \
       python bench.py --steps 2 --warmup 3 --no-cpu-baseline > gpurun_out/${tag}_launches.log 2>&1; echo "launches rc=$?" ;;
 prof)
-  timeout 900 ncu --set full --clock-control none --import-source on -k regex:trace_kernel -s 3 -c 1 -f -o gpurun_out/${tag}_prof \
+  timeout 900 ncu --set full --clock-control none --import-source on -k regex:trace_pool_kernel -s 3 -c 1 -f -o gpurun_out/${tag}_prof \
       python bench.py --steps 2 --warmup 3 --no-cpu-baseline > gpurun_out/${tag}_prof.log 2>&1; echo "prof rc=$?" ;;
 esac
 done

@@ -413,7 +413,7 @@ struct PoolWarp {
     float best_u[PL_S];
     uint32_t out_idx[PL_S];
     uint8_t sp[PL_S], spilled[PL_S];   // stack size, and how many of its bottom entries live in the global spill area
-    uint8_t q[5][PL_S];
+    uint8_t q[5][PL_S];                // LIFO stacks of slot ids
 };
 
 template <bool STATS, int PL_S, int PL_STK, bool RCP>
@@ -448,11 +448,15 @@ __global__ void __launch_bounds__(TR_BLOCK, PL_MINB) trace_pool_kernel(const Tra
     for (int k = lane; k < PL_S; k += 32) sh.q[Q_FREE][k] = (uint8_t)k;
     __syncwarp();
 
+    // the queues are LIFO stacks of slot ids: the most recently queued rays are served first, while the nodes and curves they
+    // touched are still in L1 (a FIFO ring measured 4 % slower: 1112 vs 1156 Mrays/s on C2); every queue drains when the warp
+    // runs out of other work, so nothing is left behind
     auto enqueue = [&](int qi, uint32_t& n, bool pred, uint32_t s) {
         const unsigned m = __ballot_sync(FULL, pred);
         if (pred) sh.q[qi][n + __popc(m & lt)] = (uint8_t)s;
         n += __popc(m);
     };
+    auto dequeue = [&](int qi, uint32_t n, uint32_t k) -> uint32_t { return sh.q[qi][n - 1u - k]; };
     // the shared-memory ring holds the top PL_STK entries; when it is full the OLDEST entry moves to the global spill area,
     // and comes back only when everything above it has been popped
     constexpr bool POW2 = (PL_STK & (PL_STK - 1)) == 0;
@@ -475,44 +479,45 @@ __global__ void __launch_bounds__(TR_BLOCK, PL_MINB) trace_pool_kernel(const Tra
         if (__uint_as_float(e.y) <= tcur) { cur = e.x; state = (e.x & VKHRT_BVH_LEAF) ? ST_LEAF : ST_NODE; }
     };
 
-    for (;;) {
-        // ---------------- top-up: free lanes pull READY rays ----------------
-        {
-            const unsigned idle = __ballot_sync(FULL, !has);
-            if (nR > 0u && idle != 0u) {
-                const uint32_t rank = __popc(idle & lt);
-                if (!has && rank < nR) {
-                    slot = sh.q[Q_READY][nR - 1u - rank];
-                    if (RCP) id = f3(sh.dir[3][slot], sh.dir[4][slot], sh.dir[5][slot]);
-                    else id = f3(safe_rcp(sh.dir[0][slot]), safe_rcp(sh.dir[1][slot]), safe_rcp(sh.dir[2][slot]));
-                    noid = f3(-(o.x * id.x), -(o.y * id.y), -(o.z * id.z));
-                    tcur = sh.tcur[slot]; cur = sh.cur[slot]; sp = (int)sh.sp[slot]; spilled = (int)sh.spilled[slot];
-                    if (!POW2) rtop = sp % PL_STK;
-                    state = cur == REF_POP ? ST_POP : ST_NODE;
-                    has = true;
-                }
-                nR -= min(nR, (uint32_t)__popc(idle));
-                __syncwarp();
-            }
+    uint32_t nHave = 0, nM = 0;               // lanes holding a ray / a march (warp-uniform)
+    // free lanes pull READY rays
+    auto top_up = [&]() {
+        if (nR == 0u || nHave == 32u) return;
+        const unsigned idle = __ballot_sync(FULL, !has);
+        const uint32_t rank = __popc(idle & lt);
+        if (!has && rank < nR) {
+            slot = dequeue(Q_READY, nR, rank);
+            if (RCP) id = f3(sh.dir[3][slot], sh.dir[4][slot], sh.dir[5][slot]);
+            else id = f3(safe_rcp(sh.dir[0][slot]), safe_rcp(sh.dir[1][slot]), safe_rcp(sh.dir[2][slot]));
+            noid = f3(-(o.x * id.x), -(o.y * id.y), -(o.z * id.z));
+            tcur = sh.tcur[slot]; cur = sh.cur[slot]; sp = (int)sh.sp[slot]; spilled = (int)sh.spilled[slot];
+            if (!POW2) rtop = sp % PL_STK;
+            state = cur == REF_POP ? ST_POP : ST_NODE;
+            has = true;
         }
-        const uint32_t nHave = __popc(__ballot_sync(FULL, has));
-        const uint32_t nM = __popc(__ballot_sync(FULL, mhave));
+        const uint32_t taken = min(nR, 32u - nHave);
+        nR -= taken; nHave += taken;
+        __syncwarp();
+    };
+
+    for (;;) {
+        top_up();
         const uint32_t nRet = exhausted ? nD : nD + nF;
         if ((nHave | nM | nR | nL | nC | nRet) == 0u) break;
 
         // ---------------- scheduler ----------------
         enum : int { PH_NODE, PH_LEAF, PH_SETUP, PH_MARCH, PH_RETIRE };
         int phase;
-        {
+        if (!exhausted && nF >= 32u) phase = PH_RETIRE;                        // fill the pool first
+        else if (nHave >= p.pool_node_lanes) phase = PH_NODE;
+        else {
             const uint32_t sS = min(nC, 32u - nM);
             const uint32_t sR = min(nRet, 32u);
             uint32_t best = nL; int bp = PH_LEAF;
             if (sS > best) { best = sS; bp = PH_SETUP; }
             if (nM > best || (nM == 32u)) { best = nM; bp = PH_MARCH; }
             if (sR > best) { best = sR; bp = PH_RETIRE; }
-            if (!exhausted && nF >= 32u) phase = PH_RETIRE;                    // fill the pool first
-            else if (nHave >= p.pool_node_lanes) phase = PH_NODE;
-            else if (best >= p.pool_batch_lanes) phase = bp;
+            if (best >= p.pool_batch_lanes) phase = bp;
             else if (nHave >= p.pool_node_min) phase = PH_NODE;
             else if (best > 0u) phase = bp;
             else phase = PH_NODE;
@@ -520,36 +525,41 @@ __global__ void __launch_bounds__(TR_BLOCK, PL_MINB) trace_pool_kernel(const Tra
 
         if (phase == PH_NODE) {
             // ---------------- internal nodes (same step as trace_kernel) ----------------
-            uint32_t n0 = nHave, n1;
+            // stays here, re-filling free lanes from READY, for as long as enough lanes hold a ray
             do {
-                if (STATS) { sc_steps[0]++; sc_lanes[0] += __popc(__ballot_sync(FULL, has && state <= ST_POP)); }
-                if (has) {
-                    if (state == ST_POP) pop_one();
-                    if (state == ST_NODE) {
-                        const float4* nd = p.nodes + 4 * (size_t)cur;
-                        const float4 q0 = __ldg(nd), q1 = __ldg(nd + 1), q2 = __ldg(nd + 2), q3 = __ldg(nd + 3);
-                        if (STATS) st_nodes++;
-                        float tn0, tn1;
-                        const bool h0 = slab_test(xyz(q0), xyz(q1), id, noid, p.tmin, tcur, &tn0);
-                        const bool h1 = slab_test(xyz(q2), xyz(q3), id, noid, p.tmin, tcur, &tn1);
-                        const uint32_t c0 = __float_as_uint(q0.w), c1 = __float_as_uint(q1.w);
-                        const bool both = h0 && h1;
-                        const bool second = both ? (tn1 < tn0) : h1;
-                        const uint32_t near_ref = second ? c1 : c0, far_ref = second ? c0 : c1;
-                        if (both) push(far_ref, second ? tn0 : tn1);
-                        if (h0 || h1) { cur = near_ref; if (near_ref & VKHRT_BVH_LEAF) state = ST_LEAF; }
-                        else state = ST_POP;
+                uint32_t n0 = nHave, n1;
+                do {
+                    if (STATS) { sc_steps[0]++; sc_lanes[0] += __popc(__ballot_sync(FULL, has && state <= ST_POP)); }
+                    if (has) {
+                        if (state == ST_POP) pop_one();
+                        if (state == ST_NODE) {
+                            const float4* nd = p.nodes + 4 * (size_t)cur;
+                            const float4 q0 = __ldg(nd), q1 = __ldg(nd + 1), q2 = __ldg(nd + 2), q3 = __ldg(nd + 3);
+                            if (STATS) st_nodes++;
+                            float tn0, tn1;
+                            const bool h0 = slab_test(xyz(q0), xyz(q1), id, noid, p.tmin, tcur, &tn0);
+                            const bool h1 = slab_test(xyz(q2), xyz(q3), id, noid, p.tmin, tcur, &tn1);
+                            const uint32_t c0 = __float_as_uint(q0.w), c1 = __float_as_uint(q1.w);
+                            const bool both = h0 && h1;
+                            const bool second = both ? (tn1 < tn0) : h1;
+                            const uint32_t near_ref = second ? c1 : c0, far_ref = second ? c0 : c1;
+                            if (both) push(far_ref, second ? tn0 : tn1);
+                            if (h0 || h1) { cur = near_ref; if (near_ref & VKHRT_BVH_LEAF) state = ST_LEAF; }
+                            else state = ST_POP;
+                        }
                     }
-                }
-                n1 = __popc(__ballot_sync(FULL, has && state <= ST_POP));
-            } while (n1 * 4u >= n0 * 3u && n1 > 0u);
-            // rays that left the node state go to their queues; the lane is free again
-            const bool to_leaf = has && state == ST_LEAF, to_done = has && state == ST_DONE;
-            if (to_leaf) { sh.cur[slot] = cur; sh.sp[slot] = (uint8_t)sp; sh.spilled[slot] = (uint8_t)spilled; }
-            enqueue(Q_LEAF, nL, to_leaf, slot);
-            enqueue(Q_DONE, nD, to_done, slot);
-            if (to_leaf || to_done) has = false;
-            __syncwarp();
+                    n1 = __popc(__ballot_sync(FULL, has && state <= ST_POP));
+                } while (n1 * 4u >= n0 * 3u && n1 > 0u);
+                // rays that left the node state go to their queues; the lane is free again
+                const bool to_leaf = has && state == ST_LEAF, to_done = has && state == ST_DONE;
+                if (to_leaf) { sh.cur[slot] = cur; sh.sp[slot] = (uint8_t)sp; sh.spilled[slot] = (uint8_t)spilled; }
+                enqueue(Q_LEAF, nL, to_leaf, slot);
+                enqueue(Q_DONE, nD, to_done, slot);
+                if (to_leaf || to_done) has = false;
+                nHave = n1;
+                __syncwarp();
+                top_up();
+            } while (nHave >= p.pool_node_lanes);
         } else if (phase == PH_LEAF) {
             // ---------------- leaves: Prhi early-out (hair_intersection.rint:20-33, rmax precomputed) ----------------
             const uint32_t n = min(nL, 32u);
@@ -558,7 +568,7 @@ __global__ void __launch_bounds__(TR_BLOCK, PL_MINB) trace_pool_kernel(const Tra
             uint32_t s = 0;
             bool pass = false;
             if (act) {
-                s = sh.q[Q_LEAF][nL - 1u - lane];
+                s = dequeue(Q_LEAF, nL, (uint32_t)lane);
                 const float3 d = f3(sh.dir[0][s], sh.dir[1][s], sh.dir[2][s]);
                 const uint32_t pos = sh.cur[s] & 0x7FFFFFFFu;
                 if (STATS) st_prims++;
@@ -579,7 +589,7 @@ __global__ void __launch_bounds__(TR_BLOCK, PL_MINB) trace_pool_kernel(const Tra
             if (STATS) { sc_steps[1]++; sc_lanes[1] += __popc(__ballot_sync(FULL, take)); }
             bool reject = false;
             if (take) {
-                m_slot = sh.q[Q_CAND][nC - 1u - rank];
+                m_slot = dequeue(Q_CAND, nC, rank);
                 const float3 d = f3(sh.dir[0][m_slot], sh.dir[1][m_slot], sh.dir[2][m_slot]);
                 const uint32_t pos = sh.cur[m_slot] & 0x7FFFFFFFu;
                 const float4 a0 = __ldg(p.primA + 2 * (size_t)pos), a1 = __ldg(p.primA + 2 * (size_t)pos + 1);
@@ -591,6 +601,7 @@ __global__ void __launch_bounds__(TR_BLOCK, PL_MINB) trace_pool_kernel(const Tra
                 else { reject = true; sh.cur[m_slot] = REF_POP; }
             }
             nC -= min(nC, (uint32_t)__popc(midle));
+            nM = __popc(__ballot_sync(FULL, mhave));
             __syncwarp();
             enqueue(Q_READY, nR, reject, m_slot);
             __syncwarp();
@@ -624,6 +635,7 @@ __global__ void __launch_bounds__(TR_BLOCK, PL_MINB) trace_pool_kernel(const Tra
                 enqueue(Q_READY, nR, fin, m_slot);
                 n1 = __popc(__ballot_sync(FULL, mhave));
             } while (n1 * 4u >= n0 * 3u && n1 > 0u);
+            nM = n1;
             __syncwarp();
         } else {
             // ---------------- retire finished rays, refill their slots (and free ones) with new primary rays ----------------
@@ -632,8 +644,8 @@ __global__ void __launch_bounds__(TR_BLOCK, PL_MINB) trace_pool_kernel(const Tra
             const bool act_d = (uint32_t)lane < n_d, act_f = !act_d && (uint32_t)lane - n_d < n_f;
             if (STATS) { sc_steps[3]++; sc_lanes[3] += n_d + n_f; }
             uint32_t s = 0;
-            if (act_d) s = sh.q[Q_DONE][nD - 1u - lane];
-            else if (act_f) s = sh.q[Q_FREE][nF - 1u - ((uint32_t)lane - n_d)];
+            if (act_d) s = dequeue(Q_DONE, nD, (uint32_t)lane);
+            else if (act_f) s = dequeue(Q_FREE, nF, (uint32_t)lane - n_d);
             nD -= n_d; nF -= n_f;
             if (act_d) {
                 const uint32_t pos = sh.best_pos[s], oi = sh.out_idx[s];
@@ -834,6 +846,7 @@ static void fill_params(const DeviceScene& sc, const VkhrtFrameDesc& f, const Re
 
 // scheduler tunables (defaults from the sweep in profiles/; overridable for experiments)
 static int g_refill_threshold = -1, g_blocks_per_sm = -1, g_w_node = -1, g_w_leaf = -1, g_w_march = -1, g_min_blocks = -1;
+static int g_pool_min_ratio = 3;
 static int g_pool = 1, g_pool_stats = 1, g_pool_node_lanes = 24, g_pool_batch_lanes = 8, g_pool_node_min = 8;
 static int env_int(const char* name, int def) { const char* v = getenv(name); return v ? atoi(v) : def; }
 static void tunables(TraceParams& p)
@@ -847,6 +860,7 @@ static void tunables(TraceParams& p)
         g_w_march = env_int("VKHRT_W_MARCH", 32);
         g_pool = env_int("VKHRT_POOL", 1);                       // Phantom primary rays: trace_pool_kernel
         g_pool_stats = env_int("VKHRT_POOL_STATS", 1);           // scheduler statistics of the pool kernel instead of trace_kernel's
+        g_pool_min_ratio = env_int("VKHRT_POOL_MIN_RATIO", 3);
         g_pool_node_lanes = env_int("VKHRT_POOL_NODE_LANES", 24);
         g_pool_batch_lanes = env_int("VKHRT_POOL_BATCH_LANES", 8);
         g_pool_node_min = env_int("VKHRT_POOL_NODE_MIN", 8);
@@ -915,7 +929,11 @@ static int launch_trace(DeviceScene& sc, TraceParams& p, cudaStream_t st)
     case VKHRT_TECHNIQUE_PHANTOM:
         // records that go straight to pinned host memory keep trace_kernel: its retiring lanes are pixel neighbours, which the
         // PCIe write path combines better (e2e 997 vs 819 Mrays/s on C2)
-        if (SRC == SRC_PRIMARY && !ANYHIT && g_pool && p.n_prims && (!STATS || g_pool_stats) && !(p.host_dest && env_int("VKHRT_POOL_HOST", 0) == 0)) return launch_pool<STATS>(sc, p, st);
+        // ... and small frames too: the pool needs several times its resident capacity (SMs x 32 warps x 56 slots = 265 k rays
+        // on a B200) in rays to reach a steady state; below that it is all ramp-up and drain (C1: 639 vs 801 Mrays/s)
+        if (SRC == SRC_PRIMARY && !ANYHIT && g_pool && p.n_prims && (!STATS || g_pool_stats) && !(p.host_dest && env_int("VKHRT_POOL_HOST", 0) == 0) &&
+            (unsigned long long)(p.n_slots - p.slot_begin) >= (unsigned long long)g_pool_min_ratio * sc.sm_count * 32ull * 56ull)
+            return launch_pool<STATS>(sc, p, st);
         if (!STATS && SRC == SRC_PRIMARY && g_min_blocks == 7) return launch_trace_t<VKHRT_TECHNIQUE_PHANTOM, false, SRC_PRIMARY, false, 7>(sc, p, st);
         if (!STATS && SRC == SRC_PRIMARY && g_min_blocks == 8) return launch_trace_t<VKHRT_TECHNIQUE_PHANTOM, false, SRC_PRIMARY, false, 8>(sc, p, st);
         return launch_trace_t<VKHRT_TECHNIQUE_PHANTOM, STATS, SRC, ANYHIT, TR_MIN_BLOCKS>(sc, p, st);
