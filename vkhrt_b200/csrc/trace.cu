@@ -51,7 +51,7 @@ struct TraceParams {
     uint32_t w_node, w_leaf, w_march;   // scheduler weights (fixed point, 16 = 1.0)
     // trace_pool_kernel
     uint2* pool_overflow;           // stack overflow area: [resident warp][slot][PL_OVF]
-    uint32_t pool_node_lanes, pool_batch_lanes, pool_node_min;
+    uint32_t pool_node_lanes, pool_batch_lanes, pool_node_min, pool_exit_eighths;
 };
 
 // slot (processing order: tiles, inside a tile 8x4-pixel blocks so one warp = one coherent packet)
@@ -549,7 +549,7 @@ __global__ void __launch_bounds__(TR_BLOCK, PL_MINB) trace_pool_kernel(const Tra
                         }
                     }
                     n1 = __popc(__ballot_sync(FULL, has && state <= ST_POP));
-                } while (n1 * 4u >= n0 * 3u && n1 > 0u);
+                } while (n1 * 8u >= n0 * p.pool_exit_eighths && n1 > 0u);
                 // rays that left the node state go to their queues; the lane is free again
                 const bool to_leaf = has && state == ST_LEAF, to_done = has && state == ST_DONE;
                 if (to_leaf) { sh.cur[slot] = cur; sh.sp[slot] = (uint8_t)sp; sh.spilled[slot] = (uint8_t)spilled; }
@@ -865,7 +865,7 @@ static void tunables(TraceParams& p)
         g_pool_batch_lanes = env_int("VKHRT_POOL_BATCH_LANES", 8);
         g_pool_node_min = env_int("VKHRT_POOL_NODE_MIN", 8);
     }
-    p.pool_node_lanes = (uint32_t)g_pool_node_lanes; p.pool_batch_lanes = (uint32_t)g_pool_batch_lanes; p.pool_node_min = (uint32_t)g_pool_node_min;
+    p.pool_node_lanes = (uint32_t)g_pool_node_lanes; p.pool_batch_lanes = (uint32_t)g_pool_batch_lanes; p.pool_node_min = (uint32_t)g_pool_node_min; p.pool_exit_eighths = (uint32_t)env_int("VKHRT_POOL_EXIT", 6);
     p.refill_threshold = (uint32_t)std::max(1, g_refill_threshold);
     p.w_node = (uint32_t)g_w_node; p.w_leaf = (uint32_t)g_w_leaf; p.w_march = (uint32_t)g_w_march;
 }
@@ -910,13 +910,11 @@ static int launch_pool_t(DeviceScene& sc, TraceParams& p, cudaStream_t st)
 template <bool STATS>
 static int launch_pool(DeviceScene& sc, TraceParams& p, cudaStream_t st)
 {
+    // slots per warp x shared-memory stack window: 72 x 4 and 56 x 8 both fit 8 CTAs per SM (profiles/experiments/r01_pool_kernel.txt)
     switch (env_int("VKHRT_POOL_CFG", 0)) {
-    case 1: return launch_pool_t<STATS, 64, 6, true>(sc, p, st);
-    case 2: return launch_pool_t<STATS, 56, 6, true>(sc, p, st);
-    case 3: return launch_pool_t<STATS, 72, 6, false>(sc, p, st);
-    case 4: return launch_pool_t<STATS, 64, 8, false>(sc, p, st);
-    case 5: return launch_pool_t<STATS, 64, 4, true>(sc, p, st);
-    default: return launch_pool_t<STATS, 56, 8, true>(sc, p, st);
+    case 1: return launch_pool_t<STATS, 56, 8, true>(sc, p, st);
+    case 2: return launch_pool_t<STATS, 80, 4, true>(sc, p, st);
+    default: return launch_pool_t<STATS, 72, 4, true>(sc, p, st);
     }
 }
 template <bool STATS, int SRC, bool ANYHIT>
