@@ -462,3 +462,21 @@ def test_any_hit_wavefront_rays(V, O, small_groom, tech):
             ho = orc.trace_rays(rays, any_hit=any_hit)
             assert (ho["flags"] & 1).sum() > 2000
             assert np.array_equal(dh.cpu().numpy().reshape(-1), ho.view(np.uint8).reshape(-1)), f"any_hit={any_hit}"
+
+
+@pytest.mark.parametrize("env", [{"VKHRT_POOL_MIN_RATIO": "0"}, {"VKHRT_POOL_MIN_RATIO": "0", "VKHRT_POOL_CFG": "1"}, {"VKHRT_POOL": "0"}],
+                         ids=["pool-on-every-frame", "pool-56x8", "lane-bound-only"])
+def test_both_traversal_kernels_pass_the_whole_suite(env):
+    """Phantom primary rays have two traversal kernels: the per-warp ray pool (frames >= 3x its resident capacity) and the lane-bound
+    kernel (everything else).  The library reads its switches once per process, so the whole parity file is re-run in a subprocess
+    with the pool forced onto every frame size (tiny, ragged, sharded, empty ...) and with the pool switched off (full-size C2 on
+    the lane-bound kernel)."""
+    import os
+    import subprocess
+    import sys
+    if os.environ.get("VKHRT_NESTED"):
+        pytest.skip("nested run")
+    e = dict(os.environ, VKHRT_NESTED="1", **env)
+    r = subprocess.run([sys.executable, "-m", "pytest", os.path.abspath(__file__), "-m", "gpu", "-x", "-q", "-p", "no:cacheprovider"],
+                       env=e, capture_output=True, text=True, cwd=os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
