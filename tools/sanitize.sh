@@ -12,8 +12,18 @@ for tech in (V.PHANTOM, V.LSS, V.DOTS):
         sc.refit(pos + np.float32(0.01))
         h2, _, _ = sc.render(V.make_frame(vi, pi, 160, 96, tile_size=32, tile_first=1, tile_stride=2))
         print(tech, int((h["flags"] & 1).sum()), int((h2["flags"] & 1).sum()))
+# strand LOD passes, environment miss shader, ambient occlusion
+env = V.generate_environment(64, 32)
+with V.Scene(pos, idx) as sc:
+    sc.apply_lod(1, 1, 1).set_environment(env).build()
+    h, img, _ = sc.render(V.make_frame(vi, pi, 160, 96, miss_mode=V.MISS_ENVIRONMENT, ao_samples=2))
+    print("lod+env+ao", sc.n_segments, int((h["flags"] & 1).sum()), int(img[:, :3].sum()))
 PY
+# VKHRT_POOL_MIN_RATIO=0: the Phantom frames above go through the per-warp ray-pool kernel as well as the lane-bound one
 for tool in memcheck racecheck; do
-  timeout 900 compute-sanitizer --tool $tool --print-limit 5 python san_tmp.py > gpurun_out/sanitizer_$tool.log 2>&1
-  echo "$tool rc=$?"; grep -E "ERROR SUMMARY|RACECHECK SUMMARY|hazard" gpurun_out/sanitizer_$tool.log | tail -3
+  for pool in 3 0; do
+    VKHRT_POOL_MIN_RATIO=$pool timeout 900 compute-sanitizer --tool $tool --print-limit 5 python san_tmp.py > gpurun_out/sanitizer_${tool}_pool$pool.log 2>&1
+    echo "$tool (VKHRT_POOL_MIN_RATIO=$pool) rc=$?"; grep -E "ERROR SUMMARY|RACECHECK SUMMARY|hazard" gpurun_out/sanitizer_${tool}_pool$pool.log | tail -3
+  done
 done
+rm -f san_tmp.py
