@@ -317,3 +317,42 @@ def test_gpu_environment_miss_within_one_lsb(V, O, spp):
         sc.set_environment(None)
         with pytest.raises(V.VkhrtError):
             sc.render(V.make_frame(vi, pi, W, H, miss_mode=V.MISS_ENVIRONMENT))
+
+
+def test_loaders_survive_truncated_and_corrupt_files(V, tmp_path):
+    """every prefix of a valid file and a few hundred random mutations: the readers must return an error or an asset, never crash
+    (the reference logs and returns nullptr on a failed load, model_loader.cpp:280-284)"""
+    rng = np.random.default_rng(11)
+    pos, idx = V.generate_groom(5, 3, V.GROOM_CURLY)
+    good = {}
+    for ext in ("obj", "hair"):
+        p = tmp_path / f"g.{ext}"
+        V.save_lines(str(p), pos, idx, radius_per_vertex=np.full(pos.shape[0], 0.02, np.float32) if ext == "hair" else None)
+        good[ext] = p.read_bytes()
+    hp = tmp_path / "e.hdr"
+    V.save_hdr(str(hp), V.generate_environment(16, 8))
+    good["hdr"] = hp.read_bytes()
+    n_ok = n_err = 0
+    for ext, data in good.items():
+        cases = [data[:k] for k in range(0, len(data), max(1, len(data) // 60))]
+        for _ in range(150):
+            b = bytearray(data)
+            for _ in range(int(rng.integers(1, 6))):
+                b[int(rng.integers(0, len(b)))] = int(rng.integers(0, 256))
+            cases.append(bytes(b))
+        for k, c in enumerate(cases):
+            f = tmp_path / f"fuzz{k}.{ext}"
+            f.write_bytes(c)
+            try:
+                if ext == "hdr":
+                    img = V.load_hdr(str(f))
+                    assert img.ndim == 3 and img.shape[2] == 4
+                else:
+                    p2, i2, r2, _ = V.load_lines(str(f))
+                    assert i2.size == 0 or int(i2.max()) < p2.shape[0]
+                n_ok += 1
+            except V.VkhrtError as e:
+                assert e.status in (-6, -7, -8, -4)
+                n_err += 1
+            f.unlink()
+    assert n_ok > 50 and n_err > 50
