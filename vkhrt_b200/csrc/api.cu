@@ -39,9 +39,7 @@ static void free_scene(DeviceScene* sc)
     if (!sc) return;
     cudaSetDevice(sc->device);
     cudaFree(sc->d_positions); cudaFree(sc->d_indices); cudaFree(sc->d_radius_pv); cudaFree(sc->d_curves); cudaFree(sc->d_env);
-    cudaFree(sc->d_nodes); cudaFree(sc->d_sorted_ids); cudaFree(sc->d_sorted_morton);
-    cudaFree(sc->d_parent_internal); cudaFree(sc->d_parent_leaf); cudaFree(sc->d_refit_flags);
-    cudaFree(sc->d_primA); cudaFree(sc->d_primB);
+    cudaFree(sc->d_arena);       // nodes, sorted ids / keys, parents, refit flags, primA, primB
     cudaFree(sc->d_counters); cudaFree(sc->d_hits_scratch); cudaFree(sc->d_accum); cudaFree(sc->d_rgba_scratch); cudaFree(sc->d_occluded); cudaFree(sc->d_pool_overflow);
     if (sc->h_pinned) cudaFreeHost(sc->h_pinned);
     for (auto& e : sc->ev) if (e) cudaEventDestroy(e);

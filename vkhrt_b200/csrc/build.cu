@@ -193,11 +193,16 @@ VK_DEV uint32_t quantise21(float c, float lo, float scale)
     q = fminf(fmaxf(q, 0.0f), 2097151.0f);
     return (uint32_t)q;
 }
-__global__ void __launch_bounds__(256) morton_kernel(const float4* __restrict__ centroids, uint32_t n, float3 lo, float3 scale,
+VK_DEV float ord2f(uint32_t o) { return __uint_as_float((o & 0x80000000u) ? (o & 0x7FFFFFFFu) : ~o); }
+// the centroid bounds stay on the device (ordered-uint min/max of centroid_kernel): no host round trip in the middle of the build
+__global__ void __launch_bounds__(256) morton_kernel(const float4* __restrict__ centroids, uint32_t n, const uint32_t* __restrict__ bounds,
                                                      uint64_t* __restrict__ keys, uint32_t* __restrict__ vals)
 {
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
+    const float3 lo = f3(ord2f(bounds[0]), ord2f(bounds[1]), ord2f(bounds[2]));
+    const float3 ext = f3(ord2f(bounds[3]) - lo.x, ord2f(bounds[4]) - lo.y, ord2f(bounds[5]) - lo.z);
+    const float3 scale = f3(ext.x > 0.0f ? 2097152.0f / ext.x : 0.0f, ext.y > 0.0f ? 2097152.0f / ext.y : 0.0f, ext.z > 0.0f ? 2097152.0f / ext.z : 0.0f);
     float4 c = centroids[i];
     uint64_t mx = spread21(quantise21(c.x, lo.x, scale.x));
     uint64_t my = spread21(quantise21(c.y, lo.y, scale.y));
@@ -481,15 +486,6 @@ __global__ void __launch_bounds__(256) export_kernel(MeshIn m, uint32_t n_prims,
 // ------------------------------------------------------------------------------------------------
 static inline uint32_t cdiv(uint64_t a, uint32_t b) { return (uint32_t)((a + b - 1) / b); }
 
-template <typename T>
-static int dev_alloc(T** p, size_t n)
-{
-    if (*p) { cudaFree(*p); *p = nullptr; }
-    if (n == 0) n = 1;
-    VK_CUDA(cudaMalloc((void**)p, n * sizeof(T)));
-    return VKHRT_OK;
-}
-
 static float ev_ms(cudaEvent_t a, cudaEvent_t b) { float ms = 0; cudaEventElapsedTime(&ms, a, b); return ms; }
 
 int build_scene(DeviceScene& sc, bool refit_only)
@@ -508,31 +504,34 @@ int build_scene(DeviceScene& sc, bool refit_only)
     VK_CUDA(cudaEventRecord(ev[0], st));
     if (!refit_only) {
         sc.n_nodes = n > 1 ? n - 1 : 1;
-        int rc;
-        if ((rc = dev_alloc(&sc.d_nodes, (size_t)sc.n_nodes * 4))) return rc;
-        if ((rc = dev_alloc(&sc.d_sorted_ids, n))) return rc;
-        if ((rc = dev_alloc(&sc.d_sorted_morton, n))) return rc;
-        if ((rc = dev_alloc(&sc.d_parent_internal, sc.n_nodes))) return rc;
-        if ((rc = dev_alloc(&sc.d_parent_leaf, n))) return rc;
-        if ((rc = dev_alloc(&sc.d_refit_flags, sc.n_nodes))) return rc;
-        if ((rc = dev_alloc(&sc.d_primA, (size_t)n * primA_per))) return rc;
-        if (tech == VKHRT_TECHNIQUE_PHANTOM) { if ((rc = dev_alloc(&sc.d_primB, (size_t)n * 2))) return rc; }
+        // one allocation for everything the scene keeps (a cudaMalloc per array used to cost more than the build's kernels) ...
+        auto up = [](size_t x) { return (x + 255) & ~(size_t)255; };
+        const size_t o_nodes = 0, o_ids = o_nodes + up((size_t)sc.n_nodes * 64), o_morton = o_ids + up((size_t)n * 4), o_pint = o_morton + up((size_t)n * 8),
+                     o_pleaf = o_pint + up((size_t)sc.n_nodes * 4), o_flags = o_pleaf + up((size_t)n * 4), o_primA = o_flags + up((size_t)sc.n_nodes * 4),
+                     o_primB = o_primA + up((size_t)n * primA_per * 16), total = o_primB + (tech == VKHRT_TECHNIQUE_PHANTOM ? up((size_t)n * 32) : 0);
+        if (sc.arena_bytes < total) {
+            if (sc.d_arena) cudaFree(sc.d_arena);
+            sc.d_arena = nullptr; sc.arena_bytes = 0;
+            VK_CUDA(cudaMalloc((void**)&sc.d_arena, total));
+            sc.arena_bytes = total;
+        }
+        sc.d_nodes = (float4*)(sc.d_arena + o_nodes); sc.d_sorted_ids = (uint32_t*)(sc.d_arena + o_ids); sc.d_sorted_morton = (uint64_t*)(sc.d_arena + o_morton);
+        sc.d_parent_internal = (uint32_t*)(sc.d_arena + o_pint); sc.d_parent_leaf = (uint32_t*)(sc.d_arena + o_pleaf);
+        sc.d_refit_flags = (uint32_t*)(sc.d_arena + o_flags); sc.d_primA = (float4*)(sc.d_arena + o_primA);
+        sc.d_primB = tech == VKHRT_TECHNIQUE_PHANTOM ? (float4*)(sc.d_arena + o_primB) : nullptr;
 
-        // scratch for the build
-        float4* d_cent = nullptr; uint32_t* d_bounds = nullptr;
-        uint64_t* d_keys_alt = nullptr; uint32_t* d_vals_alt = nullptr; uint32_t* d_hist = nullptr; uint32_t* d_scan_tmp = nullptr;
+        // ... and one for the build's scratch
         const uint32_t rs_blocks = cdiv(n, RS_TILE);
         const uint32_t hist_n = rs_blocks * 256u;
-        auto free_scratch = [&]() {
-            cudaFree(d_cent); cudaFree(d_bounds); cudaFree(d_keys_alt); cudaFree(d_vals_alt); cudaFree(d_hist); cudaFree(d_scan_tmp);
-        };
+        const size_t s_cent = 0, s_bounds = s_cent + up((size_t)n * 16), s_keys = s_bounds + 256, s_vals = s_keys + up((size_t)n * 8),
+                     s_hist = s_vals + up((size_t)n * 4), s_scan = s_hist + up((size_t)hist_n * 4), s_total = s_scan + up(scan_tmp_elems(hist_n) * 4);
+        unsigned char* d_scratch = nullptr;
+        auto free_scratch = [&]() { cudaFree(d_scratch); };
 #define VK_CUDA_S(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { set_last_error(std::string(#call) + ": " + cudaGetErrorString(e_)); free_scratch(); return e_ == cudaErrorMemoryAllocation ? VKHRT_ERR_OUT_OF_MEMORY : VKHRT_ERR_CUDA; } } while (0)
-        VK_CUDA_S(cudaMalloc(&d_cent, (size_t)n * sizeof(float4)));
-        VK_CUDA_S(cudaMalloc(&d_bounds, 6 * sizeof(uint32_t)));
-        VK_CUDA_S(cudaMalloc(&d_keys_alt, (size_t)n * 8));
-        VK_CUDA_S(cudaMalloc(&d_vals_alt, (size_t)n * 4));
-        VK_CUDA_S(cudaMalloc(&d_hist, (size_t)hist_n * 4));
-        VK_CUDA_S(cudaMalloc(&d_scan_tmp, scan_tmp_elems(hist_n) * 4));
+        VK_CUDA_S(cudaMalloc((void**)&d_scratch, s_total));
+        float4* d_cent = (float4*)(d_scratch + s_cent); uint32_t* d_bounds = (uint32_t*)(d_scratch + s_bounds);
+        uint64_t* d_keys_alt = (uint64_t*)(d_scratch + s_keys); uint32_t* d_vals_alt = (uint32_t*)(d_scratch + s_vals);
+        uint32_t* d_hist = (uint32_t*)(d_scratch + s_hist); uint32_t* d_scan_tmp = (uint32_t*)(d_scratch + s_scan);
 
         // 1a centroids + bounds
         uint32_t init_bounds[6] = {0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0u, 0u, 0u};
@@ -543,20 +542,10 @@ int build_scene(DeviceScene& sc, bool refit_only)
         else centroid_kernel<VKHRT_TECHNIQUE_DOTS><<<g, 256, 0, st>>>(m, n, d_cent, d_bounds);
         count_launch();
         VK_CUDA_S(cudaEventRecord(ev[1], st));
-        uint32_t hb[6];
-        VK_CUDA_S(cudaMemcpyAsync(hb, d_bounds, sizeof(hb), cudaMemcpyDeviceToHost, st));
-        VK_CUDA_S(cudaStreamSynchronize(st));
-        float lo[3], hi[3], scale[3];
-        for (int k = 0; k < 3; ++k) {
-            lo[k] = ord2f_host(hb[k]); hi[k] = ord2f_host(hb[3 + k]);
-            float ext = hi[k] - lo[k];
-            scale[k] = ext > 0.0f ? 2097152.0f / ext : 0.0f;
-            sc.scene_lo[k] = lo[k]; sc.scene_hi[k] = hi[k];
-        }
         // 1b morton keys
         uint64_t* keys[2] = {sc.d_sorted_morton, d_keys_alt};
         uint32_t* vals[2] = {sc.d_sorted_ids, d_vals_alt};
-        morton_kernel<<<g, 256, 0, st>>>(d_cent, n, make_float3(lo[0], lo[1], lo[2]), make_float3(scale[0], scale[1], scale[2]), keys[0], vals[0]);
+        morton_kernel<<<g, 256, 0, st>>>(d_cent, n, d_bounds, keys[0], vals[0]);
         count_launch();
         VK_CUDA_S(cudaEventRecord(ev[2], st));
         // 2 radix sort: 8 passes over the 63-bit key (even count => result lands back in keys[0]/vals[0])
@@ -582,8 +571,11 @@ int build_scene(DeviceScene& sc, bool refit_only)
         }
         count_launch();
         VK_CUDA_S(cudaEventRecord(ev[4], st));
+        uint32_t hb[6];
+        VK_CUDA_S(cudaMemcpyAsync(hb, d_bounds, sizeof(hb), cudaMemcpyDeviceToHost, st));
         VK_CUDA_S(cudaStreamSynchronize(st));
         VK_CUDA_S(cudaGetLastError());
+        for (int k = 0; k < 3; ++k) { sc.scene_lo[k] = ord2f_host(hb[k]); sc.scene_hi[k] = ord2f_host(hb[3 + k]); }
         free_scratch();
 #undef VK_CUDA_S
     } else {
@@ -747,38 +739,22 @@ __global__ void __launch_bounds__(256) export_lines_kernel(MeshIn m, uint32_t n,
     o[0] = s.x; o[1] = s.y; o[2] = s.z; o[3] = e.x; o[4] = e.y; o[5] = e.z;
 }
 
-// one compaction pass: counts -> exclusive scan -> total (read back) -> scatter.  `elem_floats` = 8 (line) or 12 (curve)
+// one compaction pass into a preallocated output (a pair emits at most its two inputs): counts -> exclusive scan -> scatter,
+// then the compacted size is read back (the next pass pairs up exactly that many elements)
 template <typename T>
 static int compact_pairs(void (*count_k)(const T*, uint32_t, uint32_t*), void (*scatter_k)(const T*, uint32_t, const uint32_t*, T*),
-                         const T* in, uint32_t n, T** out, uint32_t* n_out, size_t elem_bytes, cudaStream_t st)
+                         const T* in, uint32_t n, T* out, uint32_t* d_cnt, uint32_t* d_tmp, uint32_t* n_out, cudaStream_t st)
 {
     const uint32_t n_pairs = n / 2;
-    *out = nullptr; *n_out = 0;
-    uint32_t* d_cnt = nullptr; uint32_t* d_tmp = nullptr;
-    VK_CUDA(cudaMalloc(&d_cnt, ((size_t)n_pairs + 1) * 4));
-    cudaError_t e = cudaMalloc(&d_tmp, scan_tmp_elems(n_pairs + 1) * 4);
-    if (e != cudaSuccess) { cudaFree(d_cnt); set_last_error("lod: out of device memory"); return VKHRT_ERR_OUT_OF_MEMORY; }
+    *n_out = 0;
     count_k<<<cdiv((uint64_t)n_pairs + 1, 256), 256, 0, st>>>(in, n_pairs, d_cnt);
     count_launch();
     int rc = exclusive_scan(d_cnt, n_pairs + 1, d_tmp, st);
+    if (rc) return rc;
+    if (n_pairs) { scatter_k<<<cdiv(n_pairs, 256), 256, 0, st>>>(in, n_pairs, d_cnt, out); count_launch(); }
     uint32_t total = 0;
-    if (!rc) {
-        e = cudaMemcpyAsync(&total, d_cnt + n_pairs, 4, cudaMemcpyDeviceToHost, st);
-        if (e == cudaSuccess) e = cudaStreamSynchronize(st);
-        if (e != cudaSuccess) { set_last_error(std::string("lod: ") + cudaGetErrorString(e)); rc = VKHRT_ERR_CUDA; }
-    }
-    if (!rc) {
-        e = cudaMalloc((void**)out, std::max<size_t>(1, (size_t)total) * elem_bytes);
-        if (e != cudaSuccess) { set_last_error("lod: out of device memory"); rc = VKHRT_ERR_OUT_OF_MEMORY; }
-    }
-    if (!rc && n_pairs) {
-        scatter_k<<<cdiv(n_pairs, 256), 256, 0, st>>>(in, n_pairs, d_cnt, *out);
-        count_launch();
-        e = cudaStreamSynchronize(st);
-        if (e != cudaSuccess) { set_last_error(std::string("lod: ") + cudaGetErrorString(e)); rc = VKHRT_ERR_CUDA; }
-    }
-    cudaFree(d_cnt); cudaFree(d_tmp);
-    if (rc) { cudaFree(*out); *out = nullptr; return rc; }
+    VK_CUDA(cudaMemcpyAsync(&total, d_cnt + n_pairs, 4, cudaMemcpyDeviceToHost, st));
+    VK_CUDA(cudaStreamSynchronize(st));
     *n_out = total;
     return VKHRT_OK;
 }
@@ -796,63 +772,69 @@ int apply_lod(DeviceScene& sc, uint32_t split_passes, uint32_t merge_passes, uin
     MeshIn m{sc.d_positions, sc.d_indices, sc.d_radius_pv, sc.n_segments, sc.radius, sc.d_curves};
     uint32_t n = sc.n_segments;
     VK_CUDA(cudaEventRecord(sc.ev[13], st));
-    float4* lines = nullptr;
-    VK_CUDA(cudaMalloc(&lines, std::max<size_t>(1, (size_t)n * 2) * sizeof(float4)));
-#define VK_LOD(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { set_last_error(std::string(#call) + ": " + cudaGetErrorString(e_)); cudaFree(lines); return e_ == cudaErrorMemoryAllocation ? VKHRT_ERR_OUT_OF_MEMORY : VKHRT_ERR_CUDA; } } while (0)
+
+    // ONE scratch allocation for all passes: two ping-pong line buffers of the largest line count, the same for curves, the
+    // temporary indexed mesh GenerateCurves reads, pair counts and the scan's block totals
+    const size_t N = std::max<size_t>(1, (size_t)n << split_passes);
+    auto up = [](size_t x) { return (x + 255) & ~(size_t)255; };
+    const size_t o_l0 = 0, o_l1 = o_l0 + up(N * 32), o_c0 = o_l1 + up(N * 32), o_c1 = o_c0 + (curve_merge_passes ? up(N * 48) : 0),
+                 o_pos = o_c1 + (curve_merge_passes ? up(N * 48) : 0), o_idx = o_pos + (curve_merge_passes ? up(N * 24) : 0),
+                 o_cnt = o_idx + (curve_merge_passes ? up(N * 8) : 0), o_tmp = o_cnt + up((N / 2 + 1) * 4),
+                 total_bytes = o_tmp + up(scan_tmp_elems((uint32_t)(N / 2 + 1)) * 4);
+    unsigned char* arena = nullptr;
+    VK_CUDA(cudaMalloc((void**)&arena, total_bytes));
+    float4* lines = (float4*)(arena + o_l0); float4* lines_alt = (float4*)(arena + o_l1);
+    float* curves = (float*)(arena + o_c0); float* curves_alt = (float*)(arena + o_c1);
+    uint32_t* d_cnt = (uint32_t*)(arena + o_cnt); uint32_t* d_tmp = (uint32_t*)(arena + o_tmp);
+    float* pos = nullptr; uint32_t* idx = nullptr; float* rpv = nullptr; float* curves_out = nullptr;
+    auto bail = [&](int code, const char* what, cudaError_t e) {
+        set_last_error(std::string("lod: ") + what + (e != cudaSuccess ? std::string(": ") + cudaGetErrorString(e) : std::string()));
+        cudaFree(arena); cudaFree(pos); cudaFree(idx); cudaFree(rpv); cudaFree(curves_out);
+        return code;
+    };
     if (n) { lines_from_mesh_kernel<<<cdiv(n, 256), 256, 0, st>>>(m, n, lines); count_launch(); }
     for (uint32_t k = 0; k < split_passes; ++k) {
-        float4* out = nullptr;
-        VK_LOD(cudaMalloc(&out, std::max<size_t>(1, (size_t)n * 4) * sizeof(float4)));
-        if (n) { split_lines_kernel<<<cdiv(n, 256), 256, 0, st>>>(lines, n, out); count_launch(); }
-        VK_LOD(cudaStreamSynchronize(st));
-        cudaFree(lines); lines = out; n *= 2;
+        if (n) { split_lines_kernel<<<cdiv(n, 256), 256, 0, st>>>(lines, n, lines_alt); count_launch(); }
+        std::swap(lines, lines_alt); n *= 2;
     }
     for (uint32_t k = 0; k < merge_passes; ++k) {
-        float4* out = nullptr; uint32_t n_out = 0;
-        int rc = compact_pairs<float4>(merge_lines_count_kernel, merge_lines_scatter_kernel, lines, n, &out, &n_out, 2 * sizeof(float4), st);
-        if (rc) { cudaFree(lines); return rc; }
-        cudaFree(lines); lines = out; n = n_out;
+        uint32_t n_out = 0;
+        int rc = compact_pairs<float4>(merge_lines_count_kernel, merge_lines_scatter_kernel, lines, n, lines_alt, d_cnt, d_tmp, &n_out, st);
+        if (rc) { cudaFree(arena); return rc; }
+        std::swap(lines, lines_alt); n = n_out;
     }
-    // back to the indexed shape the generators consume (2 vertices per line), optionally through the curve merge
-    float* curves = nullptr;
+    // optionally through the curve merge: GenerateCurves over a temporary indexed mesh, MergeCurvesFast passes, lines = curve ends
     if (curve_merge_passes) {
-        float* pos = nullptr; uint32_t* idx = nullptr;
-        VK_LOD(cudaMalloc(&pos, std::max<size_t>(1, (size_t)n * 6) * 4));
-        cudaError_t e = cudaMalloc(&idx, std::max<size_t>(1, (size_t)n * 2) * 4);
-        if (e == cudaSuccess) e = cudaMalloc(&curves, std::max<size_t>(1, (size_t)n * 12) * 4);
-        if (e != cudaSuccess) { cudaFree(pos); cudaFree(idx); cudaFree(lines); set_last_error("lod: out of device memory"); return VKHRT_ERR_OUT_OF_MEMORY; }
+        float* tpos = (float*)(arena + o_pos); uint32_t* tidx = (uint32_t*)(arena + o_idx);
         if (n) {
-            lines_to_mesh_kernel<<<cdiv(n, 256), 256, 0, st>>>(lines, n, pos, idx, nullptr);
-            MeshIn lm{pos, idx, nullptr, n, sc.radius, nullptr};
+            lines_to_mesh_kernel<<<cdiv(n, 256), 256, 0, st>>>(lines, n, tpos, tidx, nullptr);
+            MeshIn lm{tpos, tidx, nullptr, n, sc.radius, nullptr};
             curves_materialise_kernel<<<cdiv(n, 256), 256, 0, st>>>(lm, n, curves);
             count_launch(2);
         }
-        e = cudaStreamSynchronize(st);
-        cudaFree(pos); cudaFree(idx);
-        if (e != cudaSuccess) { cudaFree(curves); cudaFree(lines); set_last_error(std::string("lod: ") + cudaGetErrorString(e)); return VKHRT_ERR_CUDA; }
         for (uint32_t k = 0; k < curve_merge_passes; ++k) {
-            float* out = nullptr; uint32_t n_out = 0;
-            int rc = compact_pairs<float>(merge_curves_count_kernel, merge_curves_scatter_kernel, curves, n, &out, &n_out, 12 * sizeof(float), st);
-            if (rc) { cudaFree(curves); cudaFree(lines); return rc; }
-            cudaFree(curves); curves = out; n = n_out;
+            uint32_t n_out = 0;
+            int rc = compact_pairs<float>(merge_curves_count_kernel, merge_curves_scatter_kernel, curves, n, curves_alt, d_cnt, d_tmp, &n_out, st);
+            if (rc) { cudaFree(arena); return rc; }
+            std::swap(curves, curves_alt); n = n_out;
         }
-        cudaFree(lines); lines = nullptr;
-        e = cudaMalloc(&lines, std::max<size_t>(1, (size_t)n * 2) * sizeof(float4));
-        if (e != cudaSuccess) { cudaFree(curves); set_last_error("lod: out of device memory"); return VKHRT_ERR_OUT_OF_MEMORY; }
         if (n) { lines_from_curves_kernel<<<cdiv(n, 256), 256, 0, st>>>(curves, n, sc.radius, lines); count_launch(); }
     }
-    float* pos = nullptr; uint32_t* idx = nullptr; float* rpv = nullptr;
+    // back to the indexed shape the generators consume (2 vertices per line); these arrays stay with the scene
     cudaError_t e = cudaMalloc(&pos, std::max<size_t>(1, (size_t)n * 6) * 4);
     if (e == cudaSuccess) e = cudaMalloc(&idx, std::max<size_t>(1, (size_t)n * 2) * 4);
     if (e == cudaSuccess && sc.d_radius_pv && !curve_merge_passes) e = cudaMalloc(&rpv, std::max<size_t>(1, (size_t)n * 2) * 4);
-    if (e == cudaSuccess && n) { lines_to_mesh_kernel<<<cdiv(n, 256), 256, 0, st>>>(lines, n, pos, idx, rpv); count_launch(); }
+    if (e == cudaSuccess && curve_merge_passes) e = cudaMalloc(&curves_out, std::max<size_t>(1, (size_t)n * 12) * 4);
+    if (e != cudaSuccess) return bail(e == cudaErrorMemoryAllocation ? VKHRT_ERR_OUT_OF_MEMORY : VKHRT_ERR_CUDA, "allocation", e);
+    if (n) { lines_to_mesh_kernel<<<cdiv(n, 256), 256, 0, st>>>(lines, n, pos, idx, rpv); count_launch(); }
+    if (curve_merge_passes && n) e = cudaMemcpyAsync(curves_out, curves, (size_t)n * 48, cudaMemcpyDeviceToDevice, st);
     if (e == cudaSuccess) e = cudaEventRecord(sc.ev[14], st);
     if (e == cudaSuccess) e = cudaStreamSynchronize(st);
-    cudaFree(lines);
-    if (e != cudaSuccess) { cudaFree(pos); cudaFree(idx); cudaFree(rpv); cudaFree(curves); set_last_error(std::string("lod: ") + cudaGetErrorString(e)); return e == cudaErrorMemoryAllocation ? VKHRT_ERR_OUT_OF_MEMORY : VKHRT_ERR_CUDA; }
-#undef VK_LOD
+    if (e == cudaSuccess) e = cudaGetLastError();
+    if (e != cudaSuccess) return bail(VKHRT_ERR_CUDA, "passes", e);
+    cudaFree(arena);
     cudaFree(sc.d_positions); cudaFree(sc.d_indices); cudaFree(sc.d_radius_pv); cudaFree(sc.d_curves);
-    sc.d_positions = pos; sc.d_indices = idx; sc.d_radius_pv = rpv; sc.d_curves = curves;
+    sc.d_positions = pos; sc.d_indices = idx; sc.d_radius_pv = rpv; sc.d_curves = curves_out;
     sc.n_vertices = 2 * n; sc.n_segments = n; sc.n_leaves = n;
     sc.n_prims = sc.technique == VKHRT_TECHNIQUE_DOTS ? 4 * n : n;
     sc.lod_applied = true;

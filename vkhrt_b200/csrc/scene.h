@@ -29,7 +29,8 @@ struct DeviceScene {
     float4* d_env = nullptr;
     uint32_t env_w = 0, env_h = 0;
 
-    // acceleration structure
+    // acceleration structure + sorted primitives: views into ONE allocation (d_arena)
+    unsigned char* d_arena = nullptr; size_t arena_bytes = 0;
     float4* d_nodes = nullptr;         // n_nodes * 4 float4 (VkhrtBvhNode)
     uint32_t* d_sorted_ids = nullptr;  // n_leaves: original leaf id (segment) at each Morton-sorted position
     uint64_t* d_sorted_morton = nullptr;
