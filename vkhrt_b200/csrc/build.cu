@@ -438,15 +438,19 @@ __global__ void __launch_bounds__(256) materialise_refit_kernel(MeshIn m, uint32
     uint32_t p = parent_leaf[pos];
     for (;;) {
         uint32_t node = p >> 1, slot = p & 1u;
-        volatile float* nd = nodes_f32 + (size_t)node * 16;
-        nd[8 * slot + 0] = box.lo.x; nd[8 * slot + 1] = box.lo.y; nd[8 * slot + 2] = box.lo.z;
-        nd[8 * slot + 4] = box.hi.x; nd[8 * slot + 5] = box.hi.y; nd[8 * slot + 6] = box.hi.z;
-        __threadfence();
-        if (atomicAdd(&flags[node], 1u) == 0u) return;      // first arrival: the sibling will carry on
-        __threadfence();
-        uint32_t o = 1u - slot;
-        box.lo.x = fminf(box.lo.x, nd[8 * o + 0]); box.lo.y = fminf(box.lo.y, nd[8 * o + 1]); box.lo.z = fminf(box.lo.z, nd[8 * o + 2]);
-        box.hi.x = fmaxf(box.hi.x, nd[8 * o + 4]); box.hi.y = fmaxf(box.hi.y, nd[8 * o + 5]); box.hi.z = fmaxf(box.hi.z, nd[8 * o + 6]);
+        float* nd = nodes_f32 + (size_t)node * 16 + 8 * slot;
+        // publish my box in the parent's slot (L2 is the coherence point: .cg stores / loads), then ONE acq_rel atomic both
+        // releases it and, for the second arrival, acquires the sibling's
+        __stcg(reinterpret_cast<float2*>(nd), make_float2(box.lo.x, box.lo.y)); __stcg(nd + 2, box.lo.z);
+        __stcg(reinterpret_cast<float2*>(nd + 4), make_float2(box.hi.x, box.hi.y)); __stcg(nd + 6, box.hi.z);
+        uint32_t arrived;
+        asm volatile("atom.acq_rel.gpu.global.add.u32 %0, [%1], 1;" : "=r"(arrived) : "l"(flags + node) : "memory");
+        if (arrived == 0u) return;                           // first arrival: the sibling will carry on
+        const float* sb = nodes_f32 + (size_t)node * 16 + 8 * (1u - slot);
+        const float2 l01 = __ldcg(reinterpret_cast<const float2*>(sb)), h01 = __ldcg(reinterpret_cast<const float2*>(sb + 4));
+        const float lz = __ldcg(sb + 2), hz = __ldcg(sb + 6);
+        box.lo.x = fminf(box.lo.x, l01.x); box.lo.y = fminf(box.lo.y, l01.y); box.lo.z = fminf(box.lo.z, lz);
+        box.hi.x = fmaxf(box.hi.x, h01.x); box.hi.y = fmaxf(box.hi.y, h01.y); box.hi.z = fmaxf(box.hi.z, hz);
         if (node == 0) return;
         p = parent_internal[node];
     }
