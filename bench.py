@@ -316,7 +316,7 @@ def main():
                        "l2": "256 MB flush between timed frames; scene (nodes+primitives) is %.0f MB" % (s * g * (64 + LEAF_RECORD_BYTES[tech]) / 1e6),
                        "seed": hex(V.DEFAULT_SEED), "build_ms": build_timing["build_total_ms"],
                        "traversal_kernel": ("value: trace_pool_kernel (per-warp ray pool) for Phantom frames of >= 3x the pool's resident capacity, else "
-                                            "trace_kernel (lane-bound); e2e: trace_kernel storing records straight into the pinned host buffer"),
+                                            "trace_kernel (lane-bound); e2e: the same kernel delivering complete 128-byte lines of records to the pinned host buffer"),
                        "frame_assembly": {"single": "one GPU", "peer": "traversal kernels store hit records straight into rank 0's frame buffer over NVLink (CUDA IPC peer mapping), 4-byte NCCL all_reduce as completion signal",
                                           "gather": "NCCL all_gather of compact shards + untile kernel"}[sharded.mode]},
             "e2e": {"value": e2e_value, "unit": "Mrays/s", "h2d_bytes_per_step": 128 + 64,

@@ -309,6 +309,27 @@ def test_pinned_host_buffers_zero_copy_path(V, small_groom, tech):
                 assert np.array_equal(hi.numpy(), iref)
 
 
+@pytest.mark.parametrize("W,H,shard", [(201, 121, None), (333, 77, None), (200, 120, (1, 3)), (1920, 1080, None), (1928, 1083, (0, 2))])
+def test_pinned_host_buffer_awkward_sizes_and_line_wise_delivery(V, small_groom, W, H, shard):
+    """Phantom hit records into a pinned buffer for record counts that are not a multiple of 4, compact shards with padding
+    records, and a frame large enough for the pool kernel: there the records reach the host line-wise (a 128-byte line = 4
+    records is copied by four lanes when its last record is written).  The nested runs of this file force that path onto the
+    small frames too.  Must equal the pageable-buffer path bit for bit."""
+    import torch
+    pos, idx = small_groom
+    vi, pi = default_camera(V, W, H)
+    kw = {} if shard is None else dict(tile_size=32, tile_first=shard[0], tile_stride=shard[1])
+    with V.Scene(pos, idx, technique=V.PHANTOM) as sc:
+        sc.build()
+        href, _, _ = sc.render(V.make_frame(vi, pi, W, H, **kw), rgba=False)
+        n = href.shape[0]
+        for rep in range(2):                                   # the per-line counters must be reset between frames
+            hh = torch.full((n, 32), 0xAB, dtype=torch.uint8).pin_memory()
+            sc.render_into(V.make_frame(vi, pi, W, H, output_memory=V.MEM_HOST, **kw), hh.data_ptr(), None)
+            got = hh.numpy().reshape(-1)
+            assert np.array_equal(got, href.view(np.uint8)), f"{int((got != href.view(np.uint8)).sum())} bytes differ (rep {rep})"
+
+
 @pytest.mark.parametrize("tech,spp", [(0, 1), (1, 3), (2, 1)])
 def test_row_major_shards_share_one_frame_buffer(V, O, small_groom, tech, spp):
     """tile_stride > 1 with row_major_output: every shard writes only its own pixels at their row-major position of a

@@ -18,6 +18,13 @@ with V.Scene(pos, idx) as sc:
     sc.apply_lod(1, 1, 1).set_environment(env).build()
     h, img, _ = sc.render(V.make_frame(vi, pi, 160, 96, miss_mode=V.MISS_ENVIRONMENT, ao_samples=2))
     print("lod+env+ao", sc.n_segments, int((h["flags"] & 1).sum()), int(img[:, :3].sum()))
+# hit records into a pinned host buffer (zero-copy stores; with the pool kernel: line-wise delivery), odd record count
+import torch
+with V.Scene(pos, idx) as sc:
+    sc.build()
+    hh = torch.zeros((161 * 97, 32), dtype=torch.uint8).pin_memory()
+    sc.render_into(V.make_frame(vi, pi, 161, 97, output_memory=V.MEM_HOST), hh.data_ptr(), None)
+    print("pinned", int(hh.numpy().view(V.HIT_DTYPE)["flags"].sum()))
 PY
 # VKHRT_POOL_MIN_RATIO=0: the Phantom frames above go through the per-warp ray-pool kernel as well as the lane-bound one
 for tool in memcheck racecheck; do

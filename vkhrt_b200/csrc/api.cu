@@ -40,7 +40,7 @@ static void free_scene(DeviceScene* sc)
     cudaSetDevice(sc->device);
     cudaFree(sc->d_positions); cudaFree(sc->d_indices); cudaFree(sc->d_radius_pv); cudaFree(sc->d_curves); cudaFree(sc->d_env);
     cudaFree(sc->d_arena);       // nodes, sorted ids / keys, parents, refit flags, primA, primB
-    cudaFree(sc->d_counters); cudaFree(sc->d_hits_scratch); cudaFree(sc->d_accum); cudaFree(sc->d_rgba_scratch); cudaFree(sc->d_occluded); cudaFree(sc->d_pool_overflow);
+    cudaFree(sc->d_counters); cudaFree(sc->d_hits_scratch); cudaFree(sc->d_accum); cudaFree(sc->d_rgba_scratch); cudaFree(sc->d_occluded); cudaFree(sc->d_pool_overflow); cudaFree(sc->d_line_cnt);
     if (sc->h_pinned) cudaFreeHost(sc->h_pinned);
     for (auto& e : sc->ev) if (e) cudaEventDestroy(e);
     if (sc->stream) cudaStreamDestroy(sc->stream);

@@ -52,6 +52,8 @@ struct DeviceScene {
     VkhrtHit* d_hits_scratch = nullptr; size_t hits_scratch_n = 0;
     float4* d_accum = nullptr; size_t accum_n = 0;
     uint32_t* d_occluded = nullptr; size_t occluded_n = 0;
+    bool last_trace_was_pool = false;
+    uint32_t* d_line_cnt = nullptr; size_t line_cnt_n = 0;             // line-wise host delivery: records written per 128-byte line
     uint2* d_pool_overflow = nullptr; size_t pool_overflow_n = 0;   // trace_pool_kernel: stack entries beyond the shared-memory slots   // per pixel: occluded AO rays of the current sample
     uint8_t* d_rgba_scratch = nullptr; size_t rgba_scratch_n = 0;
     void* h_pinned = nullptr; size_t h_pinned_bytes = 0;   // staging for host outputs

@@ -46,6 +46,11 @@ struct TraceParams {
     VkhrtHit* hits_mirror;          // optional second destination (pinned host memory), same indexing
     uint32_t hits_aligned32;        // bit 0 / 1: hits / hits_mirror are 32-byte aligned (256-bit record stores)
     uint32_t host_dest;             // a destination is mapped host memory (zero-copy over PCIe)
+    // line-wise host delivery (trace_pool_kernel): records go to HBM (`hits`); whoever completes a 128-byte line (4 records) has
+    // four lanes copy it to the mapped host buffer in ONE store instruction (see tools/micro/pcie_write.cu for why)
+    uint32_t* line_cnt;             // records written per line, zeroed per frame (null = off)
+    VkhrtHit* host_lines;           // mapped pinned host buffer, same indexing as `hits`
+    uint32_t n_out;
     unsigned long long* counters;   // [0] next slot, [1] nodes, [2] prims, [3] hits, [4] iterations, [5] rays, [8..11] steps, [12..15] lanes
     uint32_t refill_threshold;      // lanes waiting for a new ray that trigger a refill step
     uint32_t w_node, w_leaf, w_march;   // scheduler weights (fixed point, 16 = 1.0)
@@ -459,6 +464,38 @@ __global__ void __launch_bounds__(TR_BLOCK, PL_MINB) trace_pool_kernel(const Tra
     auto dequeue = [&](int qi, uint32_t n, uint32_t k) -> uint32_t { return sh.q[qi][n - 1u - k]; };
     // the shared-memory ring holds the top PL_STK entries; when it is full the OLDEST entry moves to the global spill area,
     // and comes back only when everything above it has been popped
+    // Write one hit record per calling lane (`wrote`).  With line-wise host delivery the record goes to HBM, the lane counts it
+    // on its 128-byte line with a releasing atomic, and for every line that just became complete four lanes copy its four
+    // records to the host in one 256-bit store instruction = one 128-byte PCIe write (random 32-byte writes reach 12 GB/s,
+    // whole lines from adjacent lanes 44 GB/s: tools/micro/pcie_write.cu).  Called by all lanes of the warp.
+    auto emit = [&](bool wrote, uint32_t oi, float t, uint32_t seg, float u, float3 n, uint32_t prim, uint32_t flags) {
+        if (!p.line_cnt) { if (wrote) store_hit<false>(p, oi, t, seg, u, n, prim, flags); return; }      // warp-uniform
+        bool completes = false;
+        uint32_t line = 0;
+        if (wrote) {
+            store_hit<false>(p, oi, t, seg, u, n, prim, flags);
+            __threadfence();
+            line = oi >> 2;
+            uint32_t old;
+            asm volatile("atom.acq_rel.gpu.global.add.u32 %0, [%1], 1;" : "=r"(old) : "l"(p.line_cnt + line) : "memory");
+            completes = old + 1u == min(4u, p.n_out - (line << 2));
+        }
+        unsigned m = __ballot_sync(FULL, completes);
+        while (m) {
+            // lane L copies record L % 4 of the (L / 4)-th completed line of this pass (8 lines per pass)
+            const uint32_t src = __fns(m, 0, (lane >> 2) + 1);
+            const uint32_t ln = __shfl_sync(FULL, line, src & 31u);
+            const uint32_t rec = (ln << 2) + ((uint32_t)lane & 3u);
+            if (src != 0xFFFFFFFFu && rec < p.n_out) {
+                uint32_t c;
+                asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(c) : "l"(p.line_cnt + ln) : "memory");
+                const float4* sp4 = reinterpret_cast<const float4*>(p.hits + rec);
+                const float4 x = __ldcg(sp4), y = __ldcg(sp4 + 1);
+                store_record(p.host_lines + rec, true, x, y);
+            }
+            for (int j = 0; j < 8 && m; ++j) m &= m - 1u;
+        }
+    };
     constexpr bool POW2 = (PL_STK & (PL_STK - 1)) == 0;
     auto push = [&](uint32_t ref, float tn) {
         if (POW2) rtop = sp & (PL_STK - 1);
@@ -647,30 +684,36 @@ __global__ void __launch_bounds__(TR_BLOCK, PL_MINB) trace_pool_kernel(const Tra
             if (act_d) s = dequeue(Q_DONE, nD, (uint32_t)lane);
             else if (act_f) s = dequeue(Q_FREE, nF, (uint32_t)lane - n_d);
             nD -= n_d; nF -= n_f;
-            if (act_d) {
-                const uint32_t pos = sh.best_pos[s], oi = sh.out_idx[s];
-                if (pos != PRIM_NONE) {
-                    // hair_intersection.rint:74-76 from the committed (t, u)
-                    const float t = sh.tcur[s], u = sh.best_u[s];
-                    const float3 d = f3(sh.dir[0][s], sh.dir[1][s], sh.dir[2][s]);
-                    const float4 a0 = __ldg(p.primA + 2 * (size_t)pos), a1 = __ldg(p.primA + 2 * (size_t)pos + 1);
-                    const float4 b0 = __ldg(p.primB + 2 * (size_t)pos), b1 = __ldg(p.primB + 2 * (size_t)pos + 1);
-                    Bezier w;
-                    w.p0 = xyz(a0); w.p1 = xyz(b0); w.p2 = xyz(b1); w.p3 = xyz(a1);
-                    const uint32_t prim = __float_as_uint(a1.w);
-                    const float3 n = fnormalize3(fmadd3(t, d, o) - bezier_point(w, u));
-                    store_hit<false>(p, oi, t, prim, u, n, prim, FLAG_HIT);
-                    if (STATS) st_hits++;
-                } else {
-                    store_hit<false>(p, oi, __int_as_float(0x7f800000), VKHRT_MISS_SEGMENT, 0.0f, f3(0, 0, 0), PRIM_NONE, 0u);
+            {
+                float rt = __int_as_float(0x7f800000), ru = 0.0f;
+                float3 rn = f3(0, 0, 0);
+                uint32_t rprim = PRIM_NONE, rseg = VKHRT_MISS_SEGMENT, rflags = 0u, oi = 0u;
+                if (act_d) {
+                    const uint32_t pos = sh.best_pos[s];
+                    oi = sh.out_idx[s];
+                    if (pos != PRIM_NONE) {
+                        // hair_intersection.rint:74-76 from the committed (t, u)
+                        rt = sh.tcur[s]; ru = sh.best_u[s];
+                        const float3 d = f3(sh.dir[0][s], sh.dir[1][s], sh.dir[2][s]);
+                        const float4 a0 = __ldg(p.primA + 2 * (size_t)pos), a1 = __ldg(p.primA + 2 * (size_t)pos + 1);
+                        const float4 b0 = __ldg(p.primB + 2 * (size_t)pos), b1 = __ldg(p.primB + 2 * (size_t)pos + 1);
+                        Bezier w;
+                        w.p0 = xyz(a0); w.p1 = xyz(b0); w.p2 = xyz(b1); w.p3 = xyz(a1);
+                        rprim = rseg = __float_as_uint(a1.w);
+                        rn = fnormalize3(fmadd3(rt, d, o) - bezier_point(w, ru));
+                        rflags = FLAG_HIT;
+                        if (STATS) st_hits++;
+                    }
                 }
+                emit(act_d, oi, rt, rseg, ru, rn, rprim, rflags);
             }
             const bool want = (act_d || act_f) && !exhausted;
             const unsigned wm = __ballot_sync(FULL, want);
             unsigned long long base = 0;
             if (lane == 0 && wm) base = atomicAdd(p.counters, (unsigned long long)__popc(wm));
             base = __shfl_sync(FULL, base, 0);
-            bool fresh = false;
+            bool fresh = false, padded = false;
+            uint32_t pad_idx = 0u;
             if (want) {
                 const unsigned long long slot64 = p.slot_begin + base + (unsigned)__popc(wm & lt);
                 if (slot64 < (unsigned long long)p.n_slots) {
@@ -684,11 +727,10 @@ __global__ void __launch_bounds__(TR_BLOCK, PL_MINB) trace_pool_kernel(const Tra
                         sh.best_pos[s] = PRIM_NONE; sh.best_u[s] = 0.0f; sh.out_idx[s] = q.out;
                         fresh = true;
                         if (STATS) st_rays++;
-                    } else if (p.compact) {
-                        store_hit<false>(p, q.out, __int_as_float(0x7f800000), VKHRT_MISS_SEGMENT, 0.0f, f3(0, 0, 0), PRIM_NONE, FLAG_PADDING);
-                    }
+                    } else if (p.compact) { padded = true; pad_idx = q.out; }
                 }
             }
+            if (p.compact) emit(padded, pad_idx, __int_as_float(0x7f800000), VKHRT_MISS_SEGMENT, 0.0f, f3(0, 0, 0), PRIM_NONE, FLAG_PADDING);
             if (wm && p.slot_begin + base + (unsigned)__popc(wm) >= (unsigned long long)p.n_slots) exhausted = true;
             __syncwarp();
             enqueue(Q_READY, nR, fresh, s);
@@ -840,7 +882,7 @@ static void fill_params(const DeviceScene& sc, const VkhrtFrameDesc& f, const Re
     p.W = r.W; p.H = r.H; p.sx = 0.5f; p.sy = 0.5f; p.tmin = r.tmin; p.tmax = r.tmax;
     p.T = r.T; p.tiles_x = r.tiles_x; p.n_tiles = r.n_tiles; p.tile_first = r.tile_first; p.tile_stride = r.tile_stride; p.compact = r.compact ? 1u : 0u;
     p.rays = nullptr; p.slot_begin = 0; p.n_slots = (uint32_t)r.n_slots; p.hits = nullptr; p.hits_mirror = nullptr; p.counters = sc.d_counters;
-    p.host_dest = 0u; p.hits_aligned32 = 0u; p.pool_overflow = nullptr;
+    p.host_dest = 0u; p.hits_aligned32 = 0u; p.pool_overflow = nullptr; p.line_cnt = nullptr; p.host_lines = nullptr; p.n_out = (uint32_t)r.n_out;
     p.ao_hits = nullptr; p.ao_occluded = nullptr; p.ao_index = p.ao_sample = 0u; p.ao_distance = 0.0f; p.ao_bias = 0.0f;
 }
 
@@ -904,6 +946,7 @@ static int launch_pool_t(DeviceScene& sc, TraceParams& p, cudaStream_t st)
     }
     p.pool_overflow = sc.d_pool_overflow;
     trace_pool_kernel<STATS, PL_S, PL_STK, RCP><<<grid, TR_BLOCK, 0, st>>>(p);
+    sc.last_trace_was_pool = true;
     count_launch();
     return VKHRT_OK;
 }
@@ -921,6 +964,7 @@ template <bool STATS, int SRC, bool ANYHIT>
 static int launch_trace(DeviceScene& sc, TraceParams& p, cudaStream_t st)
 {
     tunables(p);
+    sc.last_trace_was_pool = false;
     p.hits_aligned32 = (((uintptr_t)p.hits & 31u) == 0u ? 1u : 0u) | (((uintptr_t)p.hits_mirror & 31u) == 0u ? 2u : 0u);
     if (env_int("VKHRT_STORE256", 1) == 0) p.hits_aligned32 = 0u;
     switch (sc.technique) {
@@ -994,6 +1038,16 @@ int render_frame(DeviceScene& sc, const VkhrtFrameDesc& f, VkhrtHit* hits_out, u
         if ((rc = grow(&sc.d_hits_scratch, &sc.hits_scratch_n, (size_t)r.n_out * (multi ? 2 : 1)))) return rc;
     }
     if (want_hits || want_rgba) d_hits0 = direct_hits ? hits_out : sc.d_hits_scratch;
+    // Phantom frames large enough for the pool kernel: line-wise delivery (records to HBM, complete 128-byte lines to the host)
+    bool linewise = false;
+    if (h_hits_mapped && !want_rgba && sc.technique == VKHRT_TECHNIQUE_PHANTOM && sc.n_leaves && env_int("VKHRT_POOL", 1) && env_int("VKHRT_LINEWISE", 1) &&
+        (((uintptr_t)h_hits_mapped) & 127u) == 0u && r.n_slots >= (unsigned long long)env_int("VKHRT_POOL_MIN_RATIO", 3) * sc.sm_count * 32ull * 56ull) {
+        if ((rc = grow(&sc.d_hits_scratch, &sc.hits_scratch_n, (size_t)r.n_out))) return rc;
+        if ((rc = grow(&sc.d_line_cnt, &sc.line_cnt_n, (size_t)r.n_out / 4 + 1))) return rc;
+        linewise = true;
+    }
+    VkhrtHit* h_lines = nullptr;
+    if (linewise) { h_lines = h_hits_mapped; d_hits0 = sc.d_hits_scratch; h_hits_mapped = nullptr; }
     if (h_hits_mapped && !want_rgba) { d_hits0 = h_hits_mapped; h_hits_mapped = nullptr; direct_to_host = true; }   // single destination
     if (multi) d_hits_other = sc.d_hits_scratch + r.n_out;
     if (want_rgba) {
@@ -1016,11 +1070,19 @@ int render_frame(DeviceScene& sc, const VkhrtFrameDesc& f, VkhrtHit* hits_out, u
         p.hits = s == 0 ? d_hits0 : d_hits_other;
         p.hits_mirror = s == 0 ? (h_hits_mapped ? h_hits_mapped : d_hits_mirror) : nullptr;
         p.host_dest = (s == 0 && (direct_to_host || h_hits_mapped)) ? 1u : 0u;
+        p.line_cnt = nullptr; p.host_lines = nullptr;
+        if (linewise && s == 0) {
+            p.line_cnt = sc.d_line_cnt; p.host_lines = h_lines;
+            VK_CUDA(cudaMemsetAsync(sc.d_line_cnt, 0, ((size_t)r.n_out / 4 + 1) * sizeof(uint32_t), st));
+        }
         VK_CUDA(cudaMemsetAsync(sc.d_counters, 0, sizeof(unsigned long long), st));
         if (s == 0) VK_CUDA(cudaEventRecord(ev[7], st));
         rc = stats ? launch_trace<true, SRC_PRIMARY, false>(sc, p, st) : launch_trace<false, SRC_PRIMARY, false>(sc, p, st);
         if (rc) return rc;
         if (s == 0) VK_CUDA(cudaEventRecord(ev[8], st));
+        // line-wise delivery is a feature of the pool kernel: if the dispatch picked the lane-bound kernel after all, the records are
+        // in HBM only and go out with a plain copy
+        if (linewise && s == 0 && !sc.last_trace_was_pool) VK_CUDA(cudaMemcpyAsync(hits_out, d_hits0, (size_t)r.n_out * sizeof(VkhrtHit), cudaMemcpyDeviceToHost, st));
         if (ao) {
             // secondary rays: ao passes of one occlusion ray per hit pixel, spawned from the hit records inside the
             // traversal kernel's refill step (no ray buffer), terminate-on-first-hit
@@ -1048,7 +1110,7 @@ int render_frame(DeviceScene& sc, const VkhrtFrameDesc& f, VkhrtHit* hits_out, u
     }
     VK_CUDA(cudaEventRecord(ev[10], st));
     if (host_out) {
-        if (want_hits && !h_hits_mapped && !direct_to_host) VK_CUDA(cudaMemcpyAsync(hits_out, d_hits0, (size_t)r.n_out * sizeof(VkhrtHit), cudaMemcpyDeviceToHost, st));
+        if (want_hits && !h_hits_mapped && !direct_to_host && !linewise) VK_CUDA(cudaMemcpyAsync(hits_out, d_hits0, (size_t)r.n_out * sizeof(VkhrtHit), cudaMemcpyDeviceToHost, st));
         if (want_rgba) VK_CUDA(cudaMemcpyAsync(rgba_out, d_rgba, (size_t)r.n_out * 4, cudaMemcpyDeviceToHost, st));
     }
     VK_CUDA(cudaEventRecord(ev[11], st));
