@@ -50,7 +50,7 @@ struct TraceParams {
     // four lanes copy it to the mapped host buffer in ONE store instruction (see tools/micro/pcie_write.cu for why)
     uint32_t* line_cnt;             // records written per line, zeroed per frame (null = off)
     VkhrtHit* host_lines;           // mapped pinned host buffer, same indexing as `hits`
-    uint32_t n_out;
+    uint32_t n_out, line_shift;     // a line = 1 << line_shift records (2: 128 bytes)
     unsigned long long* counters;   // [0] next slot, [1] nodes, [2] prims, [3] hits, [4] iterations, [5] rays, [8..11] steps, [12..15] lanes
     uint32_t refill_threshold;      // lanes waiting for a new ray that trigger a refill step
     uint32_t w_node, w_leaf, w_march;   // scheduler weights (fixed point, 16 = 1.0)
@@ -475,17 +475,17 @@ __global__ void __launch_bounds__(TR_BLOCK, PL_MINB) trace_pool_kernel(const Tra
         if (wrote) {
             store_hit<false>(p, oi, t, seg, u, n, prim, flags);
             __threadfence();
-            line = oi >> 2;
+            line = oi >> p.line_shift;
             uint32_t old;
             asm volatile("atom.acq_rel.gpu.global.add.u32 %0, [%1], 1;" : "=r"(old) : "l"(p.line_cnt + line) : "memory");
-            completes = old + 1u == min(4u, p.n_out - (line << 2));
+            completes = old + 1u == min(1u << p.line_shift, p.n_out - (line << p.line_shift));
         }
         unsigned m = __ballot_sync(FULL, completes);
         while (m) {
-            // lane L copies record L % 4 of the (L / 4)-th completed line of this pass (8 lines per pass)
-            const uint32_t src = __fns(m, 0, (lane >> 2) + 1);
+            // with r = 1 << line_shift records per line: lane L copies record L % r of the (L / r)-th completed line of this pass
+            const uint32_t src = __fns(m, 0, (lane >> p.line_shift) + 1);
             const uint32_t ln = __shfl_sync(FULL, line, src & 31u);
-            const uint32_t rec = (ln << 2) + ((uint32_t)lane & 3u);
+            const uint32_t rec = (ln << p.line_shift) + ((uint32_t)lane & ((1u << p.line_shift) - 1u));
             if (src != 0xFFFFFFFFu && rec < p.n_out) {
                 uint32_t c;
                 asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(c) : "l"(p.line_cnt + ln) : "memory");
@@ -493,7 +493,7 @@ __global__ void __launch_bounds__(TR_BLOCK, PL_MINB) trace_pool_kernel(const Tra
                 const float4 x = __ldcg(sp4), y = __ldcg(sp4 + 1);
                 store_record(p.host_lines + rec, true, x, y);
             }
-            for (int j = 0; j < 8 && m; ++j) m &= m - 1u;
+            for (uint32_t j = 0; j < (32u >> p.line_shift) && m; ++j) m &= m - 1u;
         }
     };
     constexpr bool POW2 = (PL_STK & (PL_STK - 1)) == 0;
@@ -882,7 +882,7 @@ static void fill_params(const DeviceScene& sc, const VkhrtFrameDesc& f, const Re
     p.W = r.W; p.H = r.H; p.sx = 0.5f; p.sy = 0.5f; p.tmin = r.tmin; p.tmax = r.tmax;
     p.T = r.T; p.tiles_x = r.tiles_x; p.n_tiles = r.n_tiles; p.tile_first = r.tile_first; p.tile_stride = r.tile_stride; p.compact = r.compact ? 1u : 0u;
     p.rays = nullptr; p.slot_begin = 0; p.n_slots = (uint32_t)r.n_slots; p.hits = nullptr; p.hits_mirror = nullptr; p.counters = sc.d_counters;
-    p.host_dest = 0u; p.hits_aligned32 = 0u; p.pool_overflow = nullptr; p.line_cnt = nullptr; p.host_lines = nullptr; p.n_out = (uint32_t)r.n_out;
+    p.host_dest = 0u; p.hits_aligned32 = 0u; p.pool_overflow = nullptr; p.line_cnt = nullptr; p.host_lines = nullptr; p.n_out = (uint32_t)r.n_out; p.line_shift = 2u;
     p.ao_hits = nullptr; p.ao_occluded = nullptr; p.ao_index = p.ao_sample = 0u; p.ao_distance = 0.0f; p.ao_bias = 0.0f;
 }
 
@@ -1040,10 +1040,12 @@ int render_frame(DeviceScene& sc, const VkhrtFrameDesc& f, VkhrtHit* hits_out, u
     if (want_hits || want_rgba) d_hits0 = direct_hits ? hits_out : sc.d_hits_scratch;
     // Phantom frames large enough for the pool kernel: line-wise delivery (records to HBM, complete 128-byte lines to the host)
     bool linewise = false;
+    // 128-byte lines (4 records) measured best: e2e 996 (64 B) / 1077 (128 B) / 1068 (256 B) / 1034 (512 B) Mrays/s on C2
+    const uint32_t line_shift = (uint32_t)std::min(5, std::max(1, env_int("VKHRT_LINE_SHIFT", 2)));
     if (h_hits_mapped && !want_rgba && sc.technique == VKHRT_TECHNIQUE_PHANTOM && sc.n_leaves && env_int("VKHRT_POOL", 1) && env_int("VKHRT_LINEWISE", 1) &&
-        (((uintptr_t)h_hits_mapped) & 127u) == 0u && r.n_slots >= (unsigned long long)env_int("VKHRT_POOL_MIN_RATIO", 3) * sc.sm_count * 32ull * 56ull) {
+        (((uintptr_t)h_hits_mapped) & ((32u << line_shift) - 1u)) == 0u && r.n_slots >= (unsigned long long)env_int("VKHRT_POOL_MIN_RATIO", 3) * sc.sm_count * 32ull * 56ull) {
         if ((rc = grow(&sc.d_hits_scratch, &sc.hits_scratch_n, (size_t)r.n_out))) return rc;
-        if ((rc = grow(&sc.d_line_cnt, &sc.line_cnt_n, (size_t)r.n_out / 4 + 1))) return rc;
+        if ((rc = grow(&sc.d_line_cnt, &sc.line_cnt_n, (size_t)r.n_out / 2 + 1))) return rc;      // enough for the smallest line (2 records)
         linewise = true;
     }
     VkhrtHit* h_lines = nullptr;
@@ -1072,8 +1074,8 @@ int render_frame(DeviceScene& sc, const VkhrtFrameDesc& f, VkhrtHit* hits_out, u
         p.host_dest = (s == 0 && (direct_to_host || h_hits_mapped)) ? 1u : 0u;
         p.line_cnt = nullptr; p.host_lines = nullptr;
         if (linewise && s == 0) {
-            p.line_cnt = sc.d_line_cnt; p.host_lines = h_lines;
-            VK_CUDA(cudaMemsetAsync(sc.d_line_cnt, 0, ((size_t)r.n_out / 4 + 1) * sizeof(uint32_t), st));
+            p.line_cnt = sc.d_line_cnt; p.host_lines = h_lines; p.line_shift = line_shift;
+            VK_CUDA(cudaMemsetAsync(sc.d_line_cnt, 0, (((size_t)r.n_out >> p.line_shift) + 1) * sizeof(uint32_t), st));
         }
         VK_CUDA(cudaMemsetAsync(sc.d_counters, 0, sizeof(unsigned long long), st));
         if (s == 0) VK_CUDA(cudaEventRecord(ev[7], st));
