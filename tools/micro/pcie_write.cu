@@ -1,3 +1,4 @@
+// build: nvcc -gencode arch=compute_100a,code=sm_100a -O2 tools/micro/pcie_write.cu -o tools/micro/pcie_write   (results: profiles/experiments/r01_pool_kernel.txt)
 // micro-benchmark: SM-driven writes to pinned host memory, 32-byte records at scattered positions
 //   mode 0: one 32 B record per thread, random record positions            (what a retiring ray does)
 //   mode 1: one 32 B record per thread, consecutive threads = consecutive records (fully coalesced)
