@@ -174,3 +174,68 @@ def analytic_cylinder(ro, rd, p0, p1, r):
     if t > 0 and 0 < y < baba:
         return t, y / baba
     return None
+
+
+# ---- shaders/miss.rmiss:17-38, in float64 (an analytic check of the fp32 oracle, not a bit-level one) --------------
+def miss_shader(env, ray_d):
+    """env: [h, w, 4] float32 equirectangular map; sampler = linear, repeat (gpu_resources.hpp:46-50)"""
+    d = -np.asarray(ray_d, np.float64)
+    d = d / np.sqrt((d * d).sum())                                   # :27 normalize(-gl_WorldRayDirectionEXT)
+    gamma = np.arcsin(np.clip(d[1], -1.0, 1.0))                      # :19
+    theta = np.arctan2(d[0], -d[2])                                  # :20
+    u = theta * 0.3183098861837 * 0.5 + 0.5                          # :22
+    v = gamma * 0.3183098861837 + 0.5
+    h, w = env.shape[:2]
+    x, y = u * w - 0.5, v * h - 0.5                                  # Vulkan unnormalised texel coordinates
+    x0, y0 = int(np.floor(x)), int(np.floor(y))
+    fx, fy = x - x0, y - y0
+    e = env.astype(np.float64)
+    t = lambda i, j: e[j % h, i % w, :3]
+    c = (1 - fy) * ((1 - fx) * t(x0, y0) + fx * t(x0 + 1, y0)) + fy * ((1 - fx) * t(x0, y0 + 1) + fx * t(x0 + 1, y0 + 1))
+    c = 1.0 - np.exp(-c * 1.0)                                       # :34 exposure 1
+    return c ** (1.0 / 2.2)                                          # :35
+
+
+# ---- geometry_processor.cpp:69-121, 158-197, transcribed statement by statement over Python lists ----------------
+def merge_lines(lines):
+    """lines: list of (start, end) float32 triples"""
+    new = []
+    wanted = len(lines) // 2                                         # :73
+    for i in range(wanted):                                          # :76
+        old = i * 2
+        l1 = lines[old]
+        if old + 1 == len(lines):                                    # :82 (never true inside this loop)
+            new.append(l1)
+            break
+        l2 = lines[old + 1]
+        if not np.array_equal(l1[1], l2[0]):                         # :91 glm::vec3 !=
+            new.append(l1); new.append(l2)
+            continue
+        new.append((l1[0], l2[1]))                                   # :98-100
+    return new
+
+
+def split_lines(lines):
+    new = []
+    for s, e in lines:                                               # :113
+        mid = ((s + e) * F(0.5)).astype(F)                           # :115
+        new.append((s, mid)); new.append((mid, e))
+    return new
+
+
+def merge_curves_fast(curves):
+    """curves: list of [start, cp1, cp2, end] float32 triples"""
+    new = []
+    wanted = len(curves) // 2
+    for i in range(wanted):
+        c1 = curves[2 * i]
+        if 2 * i + 1 == len(curves):
+            new.append(c1)
+            break
+        c2 = curves[2 * i + 1]
+        if not np.array_equal(c1[3], c2[0]):                         # :180
+            new.append(c1); new.append(c2)
+            continue
+        mid = ((c1[2] + c2[1]) * F(0.5)).astype(F)                   # :190
+        new.append([c1[0], ((c1[1] + mid) * F(0.5)).astype(F), ((mid + c2[2]) * F(0.5)).astype(F), c2[3]])   # :187-192
+    return new

@@ -356,3 +356,39 @@ def test_loaders_survive_truncated_and_corrupt_files(V, tmp_path):
                 n_err += 1
             f.unlink()
     assert n_ok > 50 and n_err > 50
+
+
+def test_oracle_lod_and_miss_shader_against_the_second_transcription(O, V):
+    """tests/glsl_transcription.py restates MergeLines / SplitLines / MergeCurvesFast over Python lists and miss.rmiss in float64,
+    independently of oracle/vkhrt_oracle.cpp: random ragged polylines (unconnected pairs, odd counts) and random directions"""
+    import glsl_transcription as G
+    rng = np.random.default_rng(21)
+    for trial in range(6):
+        # ragged strands of 1..6 segments, some strands start where the previous one ended (connected across strands on purpose)
+        pos, idx, base = [], [], 0
+        for s in range(int(rng.integers(3, 9))):
+            k = int(rng.integers(1, 7))
+            p = rng.normal(size=(k + 1, 3)).astype(np.float32)
+            if pos and rng.random() < 0.3:
+                p[0] = pos[-1]
+            pos.extend(p); idx.extend([[base + j, base + j + 1] for j in range(k)]); base += k + 1
+        pos = np.array(pos, np.float32); idx = np.array(idx, np.uint32)
+        lines = [(pos[a], pos[b]) for a, b in idx]
+        flat = lambda ls: np.array([np.concatenate(l) for l in ls], np.float32).reshape(-1, 6)
+        for lod, fn in (((0, 1, 0), lambda l: G.merge_lines(l)), ((1, 0, 0), lambda l: G.split_lines(l)),
+                        ((1, 2, 0), lambda l: G.merge_lines(G.merge_lines(G.split_lines(l)))), ((0, 2, 0), lambda l: G.merge_lines(G.merge_lines(l)))):
+            assert np.array_equal(O.OracleScene(pos, idx, lod=lod).lines(), flat(fn(lines))), (trial, lod)
+        curves = [list(c) for c in O.OracleScene(pos, idx).primitives().reshape(-1, 4, 3)]
+        for passes in (1, 2):
+            want = curves
+            for _ in range(passes):
+                want = G.merge_curves_fast(want)
+            got = O.OracleScene(pos, idx, lod=(0, 0, passes)).primitives().reshape(-1, 4, 3)
+            assert np.array_equal(got, np.array(want, np.float32).reshape(-1, 4, 3)), (trial, passes)
+    env = V.generate_environment(64, 32)
+    sc = O.OracleScene(pos, idx)
+    sc.set_environment(env)
+    for _ in range(300):
+        d = rng.normal(size=3)
+        d /= np.linalg.norm(d)
+        assert np.abs(sc.environment_miss(d.astype(np.float32)) - G.miss_shader(env, d)).max() < 2e-4
