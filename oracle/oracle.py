@@ -76,6 +76,9 @@ def lib():
         L.orc_scene_node_count.argtypes = [C.c_void_p]
         L.orc_scene_get_primitives.argtypes = [C.c_void_p, C.c_void_p]
         L.orc_scene_get_aabbs.argtypes = [C.c_void_p, C.c_void_p]
+        L.orc_curve_aabb.argtypes = [fp, C.c_float, fp]
+        L.orc_scene_leaf_split.restype = C.c_uint32
+        L.orc_scene_leaf_split.argtypes = [C.c_void_p]
         L.orc_scene_get_bvh.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
         L.orc_render.restype = C.c_int
         L.orc_render.argtypes = [C.c_void_p, C.POINTER(FrameDesc), C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64,
@@ -175,8 +178,12 @@ class OracleScene:
 
     @property
     def n_leaves(self):
-        """BVH leaves: one per primitive (PHANTOM, LSS) or one per 4-triangle strip (DOTS)."""
+        """BVH leaves: leaf_split pieces per group (group = PHANTOM curve, LSS, or the 4-triangle DOTS strip of a segment)."""
         return int(lib().orc_scene_leaf_count(self._h))
+
+    @property
+    def leaf_split(self):
+        return int(lib().orc_scene_leaf_split(self._h))
 
     def primitives(self):
         out = np.empty((self.n_primitives, FLOATS_PER_PRIM[self.technique]), np.float32)
@@ -266,6 +273,13 @@ def raygen(view_inv, proj_inv, W, H, px, py, sample=0):
     o = (C.c_float * 3)(); d = (C.c_float * 3)()
     lib().orc_raygen(a[0][1], a[1][1], W, H, px, py, sample, o, d)
     return np.array(list(o), np.float32), np.array(list(d), np.float32)
+
+
+def curve_aabb(curve, radius=0.02):
+    """GenerateAABBs for one curve (lo.xyz, hi.xyz)"""
+    a = _f(np.asarray(curve).reshape(12)); o = (C.c_float * 6)()
+    lib().orc_curve_aabb(a[1], radius, o)
+    return np.array(list(o), np.float32)
 
 
 def curve_point(curve, t):

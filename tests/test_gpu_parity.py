@@ -266,8 +266,9 @@ def test_full_size_config2_properties(V, O):
     with V.Scene(pos, idx, technique=V.PHANTOM) as sc:
         sc.build()
         nodes, ids, morton, _ = sc.bvh()
-        n = sc.n_primitives
-        assert n == 3200000 and nodes.shape[0] == n - 1
+        assert sc.n_primitives == 3200000
+        n = ids.shape[0]                                                                # BVH leaves = 2 pieces per curve
+        assert n == 2 * 3200000 and nodes.shape[0] == n - 1
         assert np.array_equal(np.sort(ids), np.arange(n, dtype=np.uint32))          # a permutation
         assert (np.diff(morton.astype(np.int64)) >= 0).all()                            # sortedness
         leaf0 = nodes["child0"] >> 31 == 1; leaf1 = nodes["child1"] >> 31 == 1

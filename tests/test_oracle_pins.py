@@ -200,9 +200,19 @@ def test_generate_aabbs(O):
     idx = np.array([[0, 1], [1, 2]], np.uint32)
     sc = O.OracleScene(pos, idx)
     c = sc.primitives().reshape(2, 4, 3)
-    b = sc.aabbs()
     r = np.float32(0.02)
+    b = np.array([O.curve_aabb(c[i], r) for i in range(2)])                      # GenerateAABBs, geometry_processor.cpp:422-436
     assert np.array_equal(b[:, :3], c.min(axis=1) - r) and np.array_equal(b[:, 3:], c.max(axis=1) + r)
+    # the BVH leaves are K piece boxes per curve (VKHRT_LEAF_SPLIT_PHANTOM): each inside the reference box (plus a few ulps),
+    # and together they hold every point within r of the curve
+    K = sc.leaf_split
+    lb = sc.aabbs().reshape(2, K, 6)
+    assert K == 2 and (lb[:, :, :3] >= b[:, None, :3] - 1e-5).all() and (lb[:, :, 3:] <= b[:, None, 3:] + 1e-5).all()
+    for i in range(2):
+        for t in np.linspace(0, 1, 101):
+            pt = O.curve_point(c[i], np.float32(t))
+            k = min(K - 1, int(t * K))
+            assert (pt - r >= lb[i, k, :3] - 1e-6).all() and (pt + r <= lb[i, k, 3:] + 1e-6).all()
 
 
 def test_dots_geometry(O, V):
@@ -290,11 +300,16 @@ def test_lbvh_invariants(O, V, tech):
     sc = O.OracleScene(pos, idx, technique=tech)
     nodes, ids, morton, lohi = sc.bvh()
     n = sc.n_leaves
-    assert n == idx.shape[0] and sc.n_primitives == n * (4 if tech == 2 else 1)   # DOTS: one leaf per 4-triangle strip
+    K = sc.leaf_split                                                             # leaf pieces per group: 2 / 1 / 4
+    assert K == (2, 1, 4)[tech] and n == idx.shape[0] * K and sc.n_primitives == idx.shape[0] * (4 if tech == 2 else 1)
     boxes = sc.aabbs()
-    if tech == 2:   # strip box = union of its 4 triangle boxes
-        tr = sc.primitives().reshape(n, 12, 3)
-        assert np.array_equal(boxes[:, :3], tr.min(axis=1)) and np.array_equal(boxes[:, 3:], tr.max(axis=1))
+    if tech == 2:   # the K piece boxes of a strip: together they hold its 12 vertices, and none sticks out of the strip's own box
+        tr = sc.primitives().reshape(idx.shape[0], 12, 3)
+        pb = boxes.reshape(idx.shape[0], K, 6)
+        assert (pb[:, :, :3].min(axis=1) <= tr.min(axis=1)).all() and (pb[:, :, 3:].max(axis=1) >= tr.max(axis=1)).all()
+        assert (pb[:, :, :3] >= tr.min(axis=1)[:, None] - 2e-4).all() and (pb[:, :, 3:] <= tr.max(axis=1)[:, None] + 2e-4).all()
+        vol = np.prod(pb[:, :, 3:] - pb[:, :, :3], axis=2).sum(axis=1) / np.prod(tr.max(axis=1) - tr.min(axis=1), axis=1)
+        assert np.median(vol) < 0.5                                               # the point of the split: much less empty space
     assert nodes.shape[0] == n - 1
     assert np.array_equal(np.sort(ids), np.arange(n, dtype=np.uint32))
     assert (np.diff(morton.astype(np.int64)) >= 0).all()

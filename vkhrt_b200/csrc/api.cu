@@ -91,7 +91,7 @@ int vkhrt_scene_create(const VkhrtSceneDesc* desc, VkhrtScene** out_scene)
     if (desc->technique < VKHRT_TECHNIQUE_PHANTOM || desc->technique > VKHRT_TECHNIQUE_DOTS) { set_last_error("unknown technique"); return VKHRT_ERR_INVALID_ARGUMENT; }
     if ((desc->n_vertices && !desc->positions_xyz) || (desc->n_segments && !desc->line_indices)) { set_last_error("null geometry array"); return VKHRT_ERR_INVALID_ARGUMENT; }
     const uint64_t n_prims = desc->technique == VKHRT_TECHNIQUE_DOTS ? (uint64_t)desc->n_segments * 4 : desc->n_segments;
-    if (n_prims >= 0xFFFFFFFFull || desc->n_segments >= 0x7FFFFFFFu) { set_last_error("too many primitives for 31-bit references"); return VKHRT_ERR_UNSUPPORTED; }
+    if (n_prims >= 0xFFFFFFFFull || (uint64_t)desc->n_segments * leaf_split_of(desc->technique) >= 0x7FFFFFFFull) { set_last_error("too many primitives for 31-bit references"); return VKHRT_ERR_UNSUPPORTED; }
     int rc = check_device(desc->device);
     if (rc) return rc;
     VK_CUDA(cudaSetDevice(desc->device));
@@ -104,7 +104,7 @@ int vkhrt_scene_create(const VkhrtSceneDesc* desc, VkhrtScene** out_scene)
     sc->n_vertices = desc->n_vertices;
     sc->n_segments = desc->n_segments;
     sc->n_prims = (uint32_t)n_prims;
-    sc->n_leaves = desc->n_segments;
+    sc->n_leaves = desc->n_segments * leaf_split_of(desc->technique);
 #define VK_TRY(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { set_last_error(std::string(#call) + ": " + cudaGetErrorString(e_)); free_scene(sc); return e_ == cudaErrorMemoryAllocation ? VKHRT_ERR_OUT_OF_MEMORY : VKHRT_ERR_CUDA; } } while (0)
     cudaDeviceProp prop;
     VK_TRY(cudaGetDeviceProperties(&prop, sc->device));

@@ -126,16 +126,73 @@ VK_DEV Aabb tri_box(const TriPrim& t)
     return b;
 }
 
-// box of BVH leaf `leaf`: the primitive's own box, or (DOTS) the union over the 4 triangles of strip `leaf`
+// ---- leaf pieces (VKHRT_LEAF_SPLIT_*, include/vkhrt_b200.h): leaf = group * K + piece ----------------------------------
+// Rounding guard of a piece box: the piece's corner points are recomputed in fp32 (midpoints, s + (e-s)*a), so the box is
+// padded by a few ulps of its largest coordinate.  The same statement order is in the oracle (piece_guard).
+VK_DEV float piece_guard(const Aabb& b)
+{
+    float m = fmaxf(fmaxf(fmaxf(fabsf(b.lo.x), fabsf(b.lo.y)), fabsf(b.lo.z)), fmaxf(fmaxf(fabsf(b.hi.x), fabsf(b.hi.y)), fabsf(b.hi.z)));
+    return m * 8e-7f + 1e-7f;
+}
+VK_DEV void grow_box(Aabb& b, float3 p)
+{
+    b.lo = f3(fminf(b.lo.x, p.x), fminf(b.lo.y, p.y), fminf(b.lo.z, p.z));
+    b.hi = f3(fmaxf(b.hi.x, p.x), fmaxf(b.hi.y, p.y), fmaxf(b.hi.z, p.z));
+}
+VK_DEV Aabb pad_box(Aabb b, float pad)
+{
+    b.lo = f3(b.lo.x - pad, b.lo.y - pad, b.lo.z - pad);
+    b.hi = f3(b.hi.x + pad, b.hi.y + pad, b.hi.z + pad);
+    return b;
+}
+// piece `piece` of K = 2^levels equal parameter ranges of a cubic Bezier: repeated de Casteljau halving, control hull + radius
+template <int K>
+VK_DEV Aabb curve_piece_box(Bezier c, uint32_t piece, float r)
+{
+    if (K == 1) return curve_box(c, r);
+#pragma unroll
+    for (int half = K >> 1; half >= 1; half >>= 1) {
+        float3 q01 = (c.p0 + c.p1) * 0.5f, q12 = (c.p1 + c.p2) * 0.5f, q23 = (c.p2 + c.p3) * 0.5f;
+        float3 r0 = (q01 + q12) * 0.5f, r1 = (q12 + q23) * 0.5f;
+        float3 mid = (r0 + r1) * 0.5f;
+        if (piece & (uint32_t)half) { c.p0 = mid; c.p1 = r1; c.p2 = q23; }
+        else { c.p1 = q01; c.p2 = r0; c.p3 = mid; }
+    }
+    Aabb b; b.lo = c.p0; b.hi = c.p0;
+    grow_box(b, c.p1); grow_box(b, c.p2); grow_box(b, c.p3);
+    return pad_box(b, r + piece_guard(b));
+}
+// piece `piece` of K equal parts of a DOTS strip: the two crossed quads between s + (e-s)*a and s + (e-s)*b
+template <int K>
+VK_DEV Aabb strip_piece_box(const MeshIn& m, uint32_t seg, uint32_t piece)
+{
+    float3 s = load_pos(m, m.idx[2 * seg]), e = load_pos(m, m.idx[2 * seg + 1]);
+    float3 fwd = normalize3(e - s);
+    float3 sv = perp_stark(fwd);
+    float3 off0 = sv * m.radius, off1 = cross3(fwd, sv) * m.radius;
+    float a = (float)piece / (float)K, bb = (float)(piece + 1u) / (float)K;
+    float3 se = e - s;
+    float3 A = s + se * a, B = s + se * bb;
+    Aabb b; b.lo = A + off0; b.hi = b.lo;
+    grow_box(b, A - off0); grow_box(b, A + off1); grow_box(b, A - off1);
+    grow_box(b, B + off0); grow_box(b, B - off0); grow_box(b, B + off1); grow_box(b, B - off1);
+    return pad_box(b, piece_guard(b));
+}
+template <int TECH> struct LeafSplit { static constexpr uint32_t K = TECH == VKHRT_TECHNIQUE_PHANTOM ? VKHRT_LEAF_SPLIT_PHANTOM : (TECH == VKHRT_TECHNIQUE_LSS ? VKHRT_LEAF_SPLIT_LSS : VKHRT_LEAF_SPLIT_DOTS); };
+
+// box of BVH leaf `leaf` = piece (leaf % K) of group (leaf / K)
 template <int TECH>
 VK_DEV Aabb leaf_box(const MeshIn& m, uint32_t leaf)
 {
-    if (TECH == VKHRT_TECHNIQUE_PHANTOM) return curve_box(gen_curve(m, leaf), m.radius);
-    if (TECH == VKHRT_TECHNIQUE_LSS) return lss_box(gen_lss(m, leaf));
-    Aabb b = tri_box(gen_tri(m, 4u * leaf));
+    constexpr uint32_t K = LeafSplit<TECH>::K;
+    const uint32_t group = leaf / K, piece = leaf % K;
+    if (TECH == VKHRT_TECHNIQUE_PHANTOM) return curve_piece_box<(int)K>(gen_curve(m, group), piece, m.radius);
+    if (TECH == VKHRT_TECHNIQUE_LSS) return lss_box(gen_lss(m, group));        // K = 1
+    if (K > 1) return strip_piece_box<(int)K>(m, group, piece);
+    Aabb b = tri_box(gen_tri(m, 4u * group));
 #pragma unroll
     for (uint32_t k = 1; k < 4; ++k) {
-        Aabb c = tri_box(gen_tri(m, 4u * leaf + k));
+        Aabb c = tri_box(gen_tri(m, 4u * group + k));
         b.lo = f3(fminf(b.lo.x, c.lo.x), fminf(b.lo.y, c.lo.y), fminf(b.lo.z, c.lo.z));
         b.hi = f3(fmaxf(b.hi.x, c.hi.x), fmaxf(b.hi.y, c.hi.y), fmaxf(b.hi.z, c.hi.z));
     }
@@ -399,11 +456,13 @@ __global__ void __launch_bounds__(256) materialise_refit_kernel(MeshIn m, uint32
 {
     uint32_t pos = blockIdx.x * blockDim.x + threadIdx.x;
     if (pos >= n_prims) return;
-    uint32_t prim = sorted_ids[pos];
+    // the leaf's record is its GROUP's (a curve / LSS / strip reached through any of its pieces is tested whole); its box is the piece's
+    const uint32_t leaf = sorted_ids[pos];
+    const uint32_t prim = leaf / LeafSplit<TECH>::K;
     Aabb box;
     if (TECH == VKHRT_TECHNIQUE_PHANTOM) {
         Bezier c = gen_curve(m, prim);
-        box = curve_box(c, m.radius);
+        box = curve_piece_box<(int)LeafSplit<TECH>::K>(c, leaf % LeafSplit<TECH>::K, m.radius);
         float rmax = bezier_bound_radius(c, m.radius);
         primA[2 * (size_t)pos] = make_float4(c.p0.x, c.p0.y, c.p0.z, rmax);
         primA[2 * (size_t)pos + 1] = make_float4(c.p3.x, c.p3.y, c.p3.z, __uint_as_float(prim));
@@ -417,7 +476,7 @@ __global__ void __launch_bounds__(256) materialise_refit_kernel(MeshIn m, uint32
     } else {
         // strip record: the traversal kernel rebuilds the 12 vertices as start/end -+ offset with the very same
         // single fp32 add/sub gen_tri() performs, so they are bit-identical to the generator's
-        box = leaf_box<TECH>(m, prim);
+        box = leaf_box<TECH>(m, leaf);
         float3 s = load_pos(m, m.idx[2 * prim]), e = load_pos(m, m.idx[2 * prim + 1]);
         float3 fwd = normalize3(e - s);
         float3 sv = perp_stark(fwd);
@@ -839,7 +898,7 @@ int apply_lod(DeviceScene& sc, uint32_t split_passes, uint32_t merge_passes, uin
     cudaFree(arena);
     cudaFree(sc.d_positions); cudaFree(sc.d_indices); cudaFree(sc.d_radius_pv); cudaFree(sc.d_curves);
     sc.d_positions = pos; sc.d_indices = idx; sc.d_radius_pv = rpv; sc.d_curves = curves_out;
-    sc.n_vertices = 2 * n; sc.n_segments = n; sc.n_leaves = n;
+    sc.n_vertices = 2 * n; sc.n_segments = n; sc.n_leaves = n * leaf_split_of(sc.technique);
     sc.n_prims = sc.technique == VKHRT_TECHNIQUE_DOTS ? 4 * n : n;
     sc.lod_applied = true;
     sc.lod_ms = ev_ms(sc.ev[13], sc.ev[14]);

@@ -13,7 +13,7 @@ struct DeviceScene {
     int technique = 0;
     float radius = VKHRT_DEFAULT_RADIUS;
     uint32_t n_vertices = 0, n_segments = 0, n_prims = 0, n_nodes = 0;
-    // BVH leaves: one per primitive (PHANTOM, LSS); DOTS: one per STRIP = the 4 triangles of a segment
+    // BVH leaves: VKHRT_LEAF_SPLIT_* pieces per group (PHANTOM curve, LSS, DOTS strip = the 4 triangles of a segment)
     uint32_t n_leaves = 0;
     bool built = false;
 
@@ -76,6 +76,11 @@ void count_launch(uint64_t n = 1);
             return e_ == cudaErrorMemoryAllocation ? VKHRT_ERR_OUT_OF_MEMORY : VKHRT_ERR_CUDA;     \
         }                                                                                          \
     } while (0)
+
+inline uint32_t leaf_split_of(int technique)
+{
+    return technique == VKHRT_TECHNIQUE_PHANTOM ? VKHRT_LEAF_SPLIT_PHANTOM : (technique == VKHRT_TECHNIQUE_LSS ? VKHRT_LEAF_SPLIT_LSS : VKHRT_LEAF_SPLIT_DOTS);
+}
 
 // build.cu
 int build_scene(DeviceScene& sc, bool refit_only);
