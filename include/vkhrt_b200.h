@@ -169,7 +169,7 @@ typedef struct VkhrtBvhNode {
  * tested as before (a group reached through two of its leaves is simply tested twice: closest-hit selection is idempotent).
  * C2: 57.6 -> 52.1 node visits and 5.9 -> 3.9 curve tests per ray; a 4 M-segment DOTS groom: 93 -> 52 and 15.2 -> 4.3 strips. */
 #define VKHRT_LEAF_SPLIT_PHANTOM 2
-#define VKHRT_LEAF_SPLIT_LSS 1
+#define VKHRT_LEAF_SPLIT_LSS 2
 #define VKHRT_LEAF_SPLIT_DOTS 4
 
 #define VKHRT_BVH_LEAF 0x80000000u

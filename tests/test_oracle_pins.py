@@ -300,8 +300,8 @@ def test_lbvh_invariants(O, V, tech):
     sc = O.OracleScene(pos, idx, technique=tech)
     nodes, ids, morton, lohi = sc.bvh()
     n = sc.n_leaves
-    K = sc.leaf_split                                                             # leaf pieces per group: 2 / 1 / 4
-    assert K == (2, 1, 4)[tech] and n == idx.shape[0] * K and sc.n_primitives == idx.shape[0] * (4 if tech == 2 else 1)
+    K = sc.leaf_split                                                             # leaf pieces per group: 2 / 2 / 4
+    assert K == (2, 2, 4)[tech] and n == idx.shape[0] * K and sc.n_primitives == idx.shape[0] * (4 if tech == 2 else 1)
     boxes = sc.aabbs()
     if tech == 2:   # the K piece boxes of a strip: together they hold its 12 vertices, and none sticks out of the strip's own box
         tr = sc.primitives().reshape(idx.shape[0], 12, 3)

@@ -178,6 +178,20 @@ VK_DEV Aabb strip_piece_box(const MeshIn& m, uint32_t seg, uint32_t piece)
     grow_box(b, B + off0); grow_box(b, B - off0); grow_box(b, B + off1); grow_box(b, B - off1);
     return pad_box(b, piece_guard(b));
 }
+// piece `piece` of K equal parts of a linear swept sphere: the two end spheres of the part (radius is linear along the segment)
+template <int K>
+VK_DEV Aabb lss_piece_box(const LssPrim& s, uint32_t piece)
+{
+    if (K == 1) return lss_box(s);
+    float a = (float)piece / (float)K, bb = (float)(piece + 1u) / (float)K;
+    float3 se = s.p1 - s.p0;
+    float dr = s.r1 - s.r0;
+    LssPrim q;
+    q.p0 = s.p0 + se * a; q.p1 = s.p0 + se * bb;
+    q.r0 = s.r0 + dr * a; q.r1 = s.r0 + dr * bb;
+    Aabb b = lss_box(q);
+    return pad_box(b, piece_guard(b));
+}
 template <int TECH> struct LeafSplit { static constexpr uint32_t K = TECH == VKHRT_TECHNIQUE_PHANTOM ? VKHRT_LEAF_SPLIT_PHANTOM : (TECH == VKHRT_TECHNIQUE_LSS ? VKHRT_LEAF_SPLIT_LSS : VKHRT_LEAF_SPLIT_DOTS); };
 
 // box of BVH leaf `leaf` = piece (leaf % K) of group (leaf / K)
@@ -187,7 +201,7 @@ VK_DEV Aabb leaf_box(const MeshIn& m, uint32_t leaf)
     constexpr uint32_t K = LeafSplit<TECH>::K;
     const uint32_t group = leaf / K, piece = leaf % K;
     if (TECH == VKHRT_TECHNIQUE_PHANTOM) return curve_piece_box<(int)K>(gen_curve(m, group), piece, m.radius);
-    if (TECH == VKHRT_TECHNIQUE_LSS) return lss_box(gen_lss(m, group));        // K = 1
+    if (TECH == VKHRT_TECHNIQUE_LSS) return lss_piece_box<(int)K>(gen_lss(m, group), piece);
     if (K > 1) return strip_piece_box<(int)K>(m, group, piece);
     Aabb b = tri_box(gen_tri(m, 4u * group));
 #pragma unroll
@@ -470,7 +484,7 @@ __global__ void __launch_bounds__(256) materialise_refit_kernel(MeshIn m, uint32
         primB[2 * (size_t)pos + 1] = make_float4(c.p2.x, c.p2.y, c.p2.z, 0.0f);
     } else if (TECH == VKHRT_TECHNIQUE_LSS) {
         LssPrim s = gen_lss(m, prim);
-        box = lss_box(s);
+        box = lss_piece_box<(int)LeafSplit<TECH>::K>(s, leaf % LeafSplit<TECH>::K);
         primA[2 * (size_t)pos] = make_float4(s.p0.x, s.p0.y, s.p0.z, s.r0);
         primA[2 * (size_t)pos + 1] = make_float4(s.p1.x, s.p1.y, s.p1.z, s.r1);
     } else {

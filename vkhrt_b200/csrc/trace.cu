@@ -230,7 +230,7 @@ __global__ void __launch_bounds__(TR_BLOCK, MINB) trace_kernel(const TraceParams
                 } else if (TECH == VKHRT_TECHNIQUE_LSS) {
                     const float4 a0 = __ldg(p.primA + 2 * (size_t)pos), a1 = __ldg(p.primA + 2 * (size_t)pos + 1);
                     float t, u;
-                    if (lss_intersect<false>(o, d, xyz(a0), a0.w, xyz(a1), a1.w, &t, &u, nullptr)) commit(t, u, __ldg(p.sorted_ids + pos), pos);
+                    if (lss_intersect<false>(o, d, xyz(a0), a0.w, xyz(a1), a1.w, &t, &u, nullptr)) commit(t, u, __ldg(p.sorted_ids + pos) / VKHRT_LEAF_SPLIT_LSS, pos);
                     state = (ANYHIT && best_prim != PRIM_NONE) ? ST_REFILL : ST_POP;
                 } else {
                     // one strip = the 4 triangles of a segment (64-byte record); the cheap axis-distance reject first
