@@ -407,12 +407,12 @@ enum : int { Q_READY = 0, Q_LEAF = 1, Q_CAND = 2, Q_DONE = 3, Q_FREE = 4 };
 // 115 bytes per slot.  The origin is the camera position for every primary ray (kernel parameter) and -(o/d) is rebuilt
 // from it when a lane pulls the ray, so a slot stores only d and 1/d; the best hit is (tcur, leaf position, u) — the
 // primitive id lives in the leaf record.
-// PL_S = ray slots per warp; PL_STK = shared-memory stack window per slot (the TOP entries; older ones spill to global);
-// RCP = 1/d is stored in the slot (else rebuilt with three IEEE divisions when a lane pulls the ray)
-template <int PL_S, int PL_STK, bool RCP>
+// PL_S = ray slots per warp; PL_STK = shared-memory stack window per slot (a power of two: the TOP entries; older ones spill to global)
+template <int PL_S, int PL_STK>
 struct PoolWarp {
+    static_assert((PL_STK & (PL_STK - 1)) == 0, "the stack window is indexed with a mask");
     uint2 stack[PL_STK][PL_S];         // ring: entry k of the stack sits at [k % PL_STK] while it is among the top PL_STK
-    float dir[RCP ? 6 : 3][PL_S];      // d.xyz, 1/d
+    float dir[6][PL_S];                // d.xyz, 1/d (rebuilding 1/d on every pull instead: -4 %)
     float tcur[PL_S];
     uint32_t cur[PL_S], best_pos[PL_S];
     float best_u[PL_S];
@@ -421,21 +421,21 @@ struct PoolWarp {
     uint8_t q[5][PL_S];                // LIFO stacks of slot ids
 };
 
-template <bool STATS, int PL_S, int PL_STK, bool RCP>
+template <bool STATS, int PL_S, int PL_STK>
 __global__ void __launch_bounds__(TR_BLOCK, PL_MINB) trace_pool_kernel(const TraceParams p)
 {
-    __shared__ PoolWarp<PL_S, PL_STK, RCP> sh_all[TR_BLOCK / 32];
+    __shared__ PoolWarp<PL_S, PL_STK> sh_all[TR_BLOCK / 32];
     const unsigned FULL = 0xffffffffu;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const unsigned lt = (1u << lane) - 1u;
-    PoolWarp<PL_S, PL_STK, RCP>& sh = sh_all[warp];
+    PoolWarp<PL_S, PL_STK>& sh = sh_all[warp];
     uint2* const ovf_base = p.pool_overflow + ((size_t)(blockIdx.x * (TR_BLOCK / 32) + warp) * PL_S) * PL_OVF;
     const float3 o = f3(p.cam.vi[12], p.cam.vi[13], p.cam.vi[14]);     // ray_gen.rgen:22: every primary ray starts at the camera
 
     // the ray this lane traverses
     bool has = false;
     uint32_t slot = 0, cur = REF_POP, state = ST_POP;
-    int sp = 0, spilled = 0, rtop = 0;      // rtop = ring position of the next push (= sp mod PL_STK)
+    int sp = 0, spilled = 0;
     float3 id = f3(0, 0, 0), noid = f3(0, 0, 0);
     float tcur = 0.0f;
     // the candidate this lane marches (a different ray)
@@ -496,20 +496,17 @@ __global__ void __launch_bounds__(TR_BLOCK, PL_MINB) trace_pool_kernel(const Tra
             for (uint32_t j = 0; j < (32u >> p.line_shift) && m; ++j) m &= m - 1u;
         }
     };
-    constexpr bool POW2 = (PL_STK & (PL_STK - 1)) == 0;
     auto push = [&](uint32_t ref, float tn) {
-        if (POW2) rtop = sp & (PL_STK - 1);
+        const int rtop = sp & (PL_STK - 1);
         // ring full: its oldest entry sits exactly where the new one goes
         if (sp - spilled == PL_STK) { ovf_base[(size_t)slot * PL_OVF + spilled] = sh.stack[rtop][slot]; ++spilled; }
         sh.stack[rtop][slot] = make_uint2(ref, __float_as_uint(tn));
         ++sp;
-        if (!POW2) rtop = rtop + 1 == PL_STK ? 0 : rtop + 1;
     };
     auto pop_one = [&]() {
         if (sp == 0) { state = ST_DONE; return; }
         --sp;
-        if (POW2) rtop = sp & (PL_STK - 1);
-        else rtop = rtop == 0 ? PL_STK - 1 : rtop - 1;
+        const int rtop = sp & (PL_STK - 1);
         uint2 e;
         if (sp < spilled) { --spilled; e = ovf_base[(size_t)slot * PL_OVF + sp]; }
         else e = sh.stack[rtop][slot];
@@ -524,11 +521,9 @@ __global__ void __launch_bounds__(TR_BLOCK, PL_MINB) trace_pool_kernel(const Tra
         const uint32_t rank = __popc(idle & lt);
         if (!has && rank < nR) {
             slot = dequeue(Q_READY, nR, rank);
-            if (RCP) id = f3(sh.dir[3][slot], sh.dir[4][slot], sh.dir[5][slot]);
-            else id = f3(safe_rcp(sh.dir[0][slot]), safe_rcp(sh.dir[1][slot]), safe_rcp(sh.dir[2][slot]));
+            id = f3(sh.dir[3][slot], sh.dir[4][slot], sh.dir[5][slot]);
             noid = f3(-(o.x * id.x), -(o.y * id.y), -(o.z * id.z));
             tcur = sh.tcur[slot]; cur = sh.cur[slot]; sp = (int)sh.sp[slot]; spilled = (int)sh.spilled[slot];
-            if (!POW2) rtop = sp % PL_STK;
             state = cur == REF_POP ? ST_POP : ST_NODE;
             has = true;
         }
@@ -722,7 +717,7 @@ __global__ void __launch_bounds__(TR_BLOCK, PL_MINB) trace_pool_kernel(const Tra
                         float3 ro, d;
                         primary_ray(p.cam, p.W, p.H, q.px, q.py, p.sx, p.sy, &ro, &d);
                         sh.dir[0][s] = d.x; sh.dir[1][s] = d.y; sh.dir[2][s] = d.z;
-                        if (RCP) { sh.dir[3][s] = safe_rcp(d.x); sh.dir[4][s] = safe_rcp(d.y); sh.dir[5][s] = safe_rcp(d.z); }
+                        sh.dir[3][s] = safe_rcp(d.x); sh.dir[4][s] = safe_rcp(d.y); sh.dir[5][s] = safe_rcp(d.z);
                         sh.tcur[s] = p.tmax; sh.cur[s] = 0u; sh.sp[s] = 0; sh.spilled[s] = 0;
                         sh.best_pos[s] = PRIM_NONE; sh.best_u[s] = 0.0f; sh.out_idx[s] = q.out;
                         fresh = true;
@@ -926,13 +921,13 @@ static int launch_trace_t(DeviceScene& sc, TraceParams& p, cudaStream_t st)
     count_launch();
     return VKHRT_OK;
 }
-template <bool STATS, int PL_S, int PL_STK, bool RCP>
+template <bool STATS, int PL_S, int PL_STK>
 static int launch_pool_t(DeviceScene& sc, TraceParams& p, cudaStream_t st)
 {
     int per_sm = 0;
     const int carve = env_int("VKHRT_CARVEOUT", -1);
-    if (carve >= 0) VK_CUDA(cudaFuncSetAttribute(trace_pool_kernel<STATS, PL_S, PL_STK, RCP>, cudaFuncAttributePreferredSharedMemoryCarveout, carve));
-    VK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, trace_pool_kernel<STATS, PL_S, PL_STK, RCP>, TR_BLOCK, 0));
+    if (carve >= 0) VK_CUDA(cudaFuncSetAttribute(trace_pool_kernel<STATS, PL_S, PL_STK>, cudaFuncAttributePreferredSharedMemoryCarveout, carve));
+    VK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, trace_pool_kernel<STATS, PL_S, PL_STK>, TR_BLOCK, 0));
     if (per_sm < 1) per_sm = 1;
     if (g_blocks_per_sm > 0) per_sm = std::min(per_sm, g_blocks_per_sm);
     unsigned long long want = ((unsigned long long)(p.n_slots - p.slot_begin) + TR_BLOCK - 1) / TR_BLOCK;
@@ -945,7 +940,7 @@ static int launch_pool_t(DeviceScene& sc, TraceParams& p, cudaStream_t st)
         sc.pool_overflow_n = ovf;
     }
     p.pool_overflow = sc.d_pool_overflow;
-    trace_pool_kernel<STATS, PL_S, PL_STK, RCP><<<grid, TR_BLOCK, 0, st>>>(p);
+    trace_pool_kernel<STATS, PL_S, PL_STK><<<grid, TR_BLOCK, 0, st>>>(p);
     sc.last_trace_was_pool = true;
     count_launch();
     return VKHRT_OK;
@@ -955,9 +950,8 @@ static int launch_pool(DeviceScene& sc, TraceParams& p, cudaStream_t st)
 {
     // slots per warp x shared-memory stack window: 72 x 4 and 56 x 8 both fit 8 CTAs per SM (profiles/experiments/r01_pool_kernel.txt)
     switch (env_int("VKHRT_POOL_CFG", 0)) {
-    case 1: return launch_pool_t<STATS, 56, 8, true>(sc, p, st);
-    case 2: return launch_pool_t<STATS, 80, 4, true>(sc, p, st);
-    default: return launch_pool_t<STATS, 72, 4, true>(sc, p, st);
+    case 1: return launch_pool_t<STATS, 56, 8>(sc, p, st);
+    default: return launch_pool_t<STATS, 72, 4>(sc, p, st);
     }
 }
 template <bool STATS, int SRC, bool ANYHIT>
