@@ -168,9 +168,28 @@ typedef struct VkhrtBvhNode {
  * its own (leaf id = group * K + piece) whose box bounds only that piece; the leaf still refers to the whole group, which is
  * tested as before (a group reached through two of its leaves is simply tested twice: closest-hit selection is idempotent).
  * C2: 57.6 -> 52.1 node visits and 5.9 -> 3.9 curve tests per ray; a 4 M-segment DOTS groom: 93 -> 52 and 15.2 -> 4.3 strips. */
+#ifndef VKHRT_LEAF_SPLIT_PHANTOM          /* overridable only for experiment builds (tools/variants); the oracle follows the same macros */
 #define VKHRT_LEAF_SPLIT_PHANTOM 2
+#endif
+#ifndef VKHRT_LEAF_SPLIT_LSS
 #define VKHRT_LEAF_SPLIT_LSS 2
+#endif
+#ifndef VKHRT_LEAF_SPLIT_DOTS
 #define VKHRT_LEAF_SPLIT_DOTS 4
+#endif
+
+/* One-entry mailbox per ray: the group a ray tested LAST is not tested again when the next leaf the ray reaches is another
+ * piece of that same group (consecutive pieces of a curve / strip are what a ray along the strand meets).  Result-neutral:
+ * the repeated test would return the same (t, u) and closest-hit selection is idempotent; only the traversal counters change
+ * (a skipped leaf is not counted as a primitive test).  Part of the traversal definition, so the oracle applies it too.
+ * PHANTOM only: there a repeated test is a repeated march (C2, per ray: 3.86 -> 3.70 curve tests and 16.2 -> 15.4 cone iterations
+ * with 2 pieces per curve, 3.28 -> 2.75 and 17.7 -> 14.5 with 4).  LSS has no mailbox (its group id is not in the leaf record and
+ * the test is cheaper than the extra fetch), DOTS neither (strip pieces are rarely met back to back: 4.28 -> 4.18 strips). */
+#ifndef VKHRT_MAILBOX_PHANTOM
+#define VKHRT_MAILBOX_PHANTOM 1
+#endif
+#define VKHRT_MAILBOX_LSS 0
+#define VKHRT_MAILBOX_DOTS 0
 
 #define VKHRT_BVH_LEAF 0x80000000u
 #define VKHRT_BVH_EMPTY 0xFFFFFFFFu

@@ -207,7 +207,7 @@ def test_generate_aabbs(O):
     # and together they hold every point within r of the curve
     K = sc.leaf_split
     lb = sc.aabbs().reshape(2, K, 6)
-    assert K == 2 and (lb[:, :, :3] >= b[:, None, :3] - 1e-5).all() and (lb[:, :, 3:] <= b[:, None, 3:] + 1e-5).all()
+    assert K in (2, 4) and (lb[:, :, :3] >= b[:, None, :3] - 1e-5).all() and (lb[:, :, 3:] <= b[:, None, 3:] + 1e-5).all()
     for i in range(2):
         for t in np.linspace(0, 1, 101):
             pt = O.curve_point(c[i], np.float32(t))
@@ -300,8 +300,8 @@ def test_lbvh_invariants(O, V, tech):
     sc = O.OracleScene(pos, idx, technique=tech)
     nodes, ids, morton, lohi = sc.bvh()
     n = sc.n_leaves
-    K = sc.leaf_split                                                             # leaf pieces per group: 2 / 2 / 4
-    assert K == (2, 2, 4)[tech] and n == idx.shape[0] * K and sc.n_primitives == idx.shape[0] * (4 if tech == 2 else 1)
+    K = sc.leaf_split                                                             # leaf pieces per group: 2 or 4 / 2 / 4
+    assert K in ((2, 4), (2,), (4,))[tech] and n == idx.shape[0] * K and sc.n_primitives == idx.shape[0] * (4 if tech == 2 else 1)
     boxes = sc.aabbs()
     if tech == 2:   # the K piece boxes of a strip: together they hold its 12 vertices, and none sticks out of the strip's own box
         tr = sc.primitives().reshape(idx.shape[0], 12, 3)
@@ -349,6 +349,32 @@ def test_bvh_search_equals_brute_force(O, V, tech):
     h2, i2, _ = sc.render(f, brute=True)
     assert (h1["flags"] & 1).sum() > 50
     assert h1.tobytes() == h2.tobytes() and np.array_equal(i1, i2)
+
+
+def test_mailbox_is_result_neutral(O, V, monkeypatch):
+    """VKHRT_MAILBOX_PHANTOM (include/vkhrt_b200.h): skipping the curve a ray tested last changes no hit record and no node
+    visit, only the number of curve tests and cone iterations.  ORC_MAILBOX / ORC_LEAF_SPLIT are the oracle's study overrides."""
+    pos, idx = V.generate_groom(400, 12, V.GROOM_CURLY)
+    W, H = 128, 96
+    vi, pi = V.camera_matrices(aspect=W / H)
+    f = O.make_frame(vi, pi, W, H)
+    res = {}
+    for K in (1, 2, 4):
+        for mb in (0, 1):
+            monkeypatch.setenv("ORC_LEAF_SPLIT", str(K))
+            monkeypatch.setenv("ORC_MAILBOX", str(mb))
+            sc = O.OracleScene(pos, idx, technique=0, radius=0.05)
+            assert sc.leaf_split == K
+            h, img, st = sc.render(f, stats=True)
+            res[K, mb] = (h.tobytes(), img.tobytes(), st)
+    monkeypatch.delenv("ORC_LEAF_SPLIT"); monkeypatch.delenv("ORC_MAILBOX")
+    ref = res[1, 0]
+    assert res[1, 1][2]["prims_tested"] == ref[2]["prims_tested"]            # one leaf per curve: a ray never meets a curve twice
+    for (K, mb), (hb, ib, st) in res.items():
+        assert hb == ref[0] and ib == ref[1], (K, mb)
+        assert st["nodes_visited"] == res[K, 0][2]["nodes_visited"]
+        assert st["prims_tested"] <= res[K, 0][2]["prims_tested"] and st["phantom_iterations"] <= res[K, 0][2]["phantom_iterations"]
+    assert res[4, 1][2]["prims_tested"] < res[4, 0][2]["prims_tested"]        # ... and with pieces it does skip something
 
 
 def test_oracle_edge_cases(O, V):

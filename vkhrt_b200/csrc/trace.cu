@@ -141,6 +141,7 @@ __global__ void __launch_bounds__(TR_BLOCK, MINB) trace_kernel(const TraceParams
     float3 o = f3(0, 0, 0), d = f3(0, 0, 1), id = f3(0, 0, 0), noid = f3(0, 0, 0);
     float tmin = 0.0f, tcur = 0.0f, best_u = 0.0f;
     uint32_t best_prim = PRIM_NONE, best_pos = 0;
+    uint32_t last_group = PRIM_NONE;     // one-entry mailbox (VKHRT_MAILBOX_PHANTOM): the curve this ray tested last
     MarchState ms;
     ms.c.p0 = ms.c.p1 = ms.c.p2 = ms.c.p3 = f3(0, 0, 0);
     ms.t = ms.told = ms.dt1 = ms.dt2 = ms.t_start = 0.0f; ms.it = 0u;
@@ -212,11 +213,14 @@ __global__ void __launch_bounds__(TR_BLOCK, MINB) trace_kernel(const TraceParams
             if (STATS) { sc_steps[1]++; sc_lanes[1] += nL; }
             if (state == ST_LEAF) {
                 const uint32_t pos = cur & 0x7FFFFFFFu;
-                if (STATS) st_prims++;
                 if (PH) {
                     // Prhi early-out (hair_intersection.rint:20-33) with the precomputed rmax
                     const float4 a0 = __ldg(p.primA + 2 * (size_t)pos), a1 = __ldg(p.primA + 2 * (size_t)pos + 1);
-                    if (ray_hits_cylinder(o, d, xyz(a0), xyz(a1), a0.w)) {
+                    // mailbox: another piece of the curve tested last gives the same answer; skipped and not counted
+                    const bool again = VKHRT_MAILBOX_PHANTOM && __float_as_uint(a1.w) == last_group;
+                    if (VKHRT_MAILBOX_PHANTOM) last_group = __float_as_uint(a1.w);
+                    if (STATS && !again) st_prims++;
+                    if (!again && ray_hits_cylinder(o, d, xyz(a0), xyz(a1), a0.w)) {
                         const float4 b0 = __ldg(p.primB + 2 * (size_t)pos), b1 = __ldg(p.primB + 2 * (size_t)pos + 1);
                         Bezier w;
                         w.p0 = xyz(a0); w.p1 = xyz(b0); w.p2 = xyz(b1); w.p3 = xyz(a1);
@@ -230,13 +234,14 @@ __global__ void __launch_bounds__(TR_BLOCK, MINB) trace_kernel(const TraceParams
                 } else if (TECH == VKHRT_TECHNIQUE_LSS) {
                     const float4 a0 = __ldg(p.primA + 2 * (size_t)pos), a1 = __ldg(p.primA + 2 * (size_t)pos + 1);
                     float t, u;
+                    if (STATS) st_prims++;
                     if (lss_intersect<false>(o, d, xyz(a0), a0.w, xyz(a1), a1.w, &t, &u, nullptr)) commit(t, u, __ldg(p.sorted_ids + pos) / VKHRT_LEAF_SPLIT_LSS, pos);
                     state = (ANYHIT && best_prim != PRIM_NONE) ? ST_REFILL : ST_POP;
                 } else {
                     // one strip = the 4 triangles of a segment (64-byte record); the cheap axis-distance reject first
                     const float4* rec = p.primA + 4 * (size_t)pos;
                     const float4 a0 = __ldg(rec), a1 = __ldg(rec + 1);
-                    if (STATS) st_prims += 3;
+                    if (STATS) st_prims += 4;
                     if (ray_near_strip_axis(o, d, xyz(a0), xyz(a1), p.radius)) {
                         const float4 a2 = __ldg(rec + 2), a3 = __ldg(rec + 3);
                         const uint32_t prim0 = __float_as_uint(a0.w) << 2;
@@ -353,6 +358,7 @@ __global__ void __launch_bounds__(TR_BLOCK, MINB) trace_kernel(const TraceParams
                         id = f3(safe_rcp(d.x), safe_rcp(d.y), safe_rcp(d.z));
                         noid = f3(-(o.x * id.x), -(o.y * id.y), -(o.z * id.z));
                         best_prim = PRIM_NONE; best_pos = 0; best_u = 0.0f;
+                        last_group = PRIM_NONE;
                         sp = 0;
                         have_ray = true;
                         if (STATS) st_rays++;
@@ -415,6 +421,7 @@ struct PoolWarp {
     float dir[6][PL_S];                // d.xyz, 1/d (rebuilding 1/d on every pull instead: -4 %)
     float tcur[PL_S];
     uint32_t cur[PL_S], best_pos[PL_S];
+    uint32_t last_group[VKHRT_MAILBOX_PHANTOM ? PL_S : 1];   // one-entry mailbox (VKHRT_MAILBOX_PHANTOM): the curve the ray tested last
     float best_u[PL_S];
     uint32_t out_idx[PL_S];
     uint8_t sp[PL_S], spilled[PL_S];   // stack size, and how many of its bottom entries live in the global spill area
@@ -603,9 +610,12 @@ __global__ void __launch_bounds__(TR_BLOCK, PL_MINB) trace_pool_kernel(const Tra
                 s = dequeue(Q_LEAF, nL, (uint32_t)lane);
                 const float3 d = f3(sh.dir[0][s], sh.dir[1][s], sh.dir[2][s]);
                 const uint32_t pos = sh.cur[s] & 0x7FFFFFFFu;
-                if (STATS) st_prims++;
                 const float4 a0 = __ldg(p.primA + 2 * (size_t)pos), a1 = __ldg(p.primA + 2 * (size_t)pos + 1);
-                pass = ray_hits_cylinder(o, d, xyz(a0), xyz(a1), a0.w);
+                // mailbox: another piece of the curve tested last gives the same answer; skipped and not counted
+                const bool again = VKHRT_MAILBOX_PHANTOM && __float_as_uint(a1.w) == sh.last_group[s];
+                if (VKHRT_MAILBOX_PHANTOM) sh.last_group[s] = __float_as_uint(a1.w);
+                if (STATS && !again) st_prims++;
+                pass = !again && ray_hits_cylinder(o, d, xyz(a0), xyz(a1), a0.w);
                 if (!pass) sh.cur[s] = REF_POP;
             }
             nL -= n;
@@ -720,6 +730,7 @@ __global__ void __launch_bounds__(TR_BLOCK, PL_MINB) trace_pool_kernel(const Tra
                         sh.dir[3][s] = safe_rcp(d.x); sh.dir[4][s] = safe_rcp(d.y); sh.dir[5][s] = safe_rcp(d.z);
                         sh.tcur[s] = p.tmax; sh.cur[s] = 0u; sh.sp[s] = 0; sh.spilled[s] = 0;
                         sh.best_pos[s] = PRIM_NONE; sh.best_u[s] = 0.0f; sh.out_idx[s] = q.out;
+                        if (VKHRT_MAILBOX_PHANTOM) sh.last_group[s] = PRIM_NONE;
                         fresh = true;
                         if (STATS) st_rays++;
                     } else if (p.compact) { padded = true; pad_idx = q.out; }
