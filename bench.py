@@ -218,6 +218,7 @@ def main():
     scene = V.Scene(pos, idx, technique=tech_id, device=local_rank)
     scene.build()
     build_timing = scene.timing()
+    n_leaves = scene.n_leaves
 
     # a non-default stream: the ABI treats a NULL stream handle as "use the scene's own stream"
     from vkhrt_b200.multi import ShardedRenderer
@@ -313,7 +314,7 @@ def main():
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": total_ms / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": workload_desc(name, world, W, H), "rays_per_step": rays_per_step, "rays_per_gpu_per_step": rays_per_step // world,
-                       "l2": "256 MB flush between timed frames; scene (nodes+primitives) is %.0f MB" % (s * g * (64 + LEAF_RECORD_BYTES[tech]) / 1e6),
+                       "l2": "256 MB flush between timed frames; scene is %.0f MB (%d BVH leaves: a 64-byte node and a %d-byte primitive record each)" % (n_leaves * (64 + LEAF_RECORD_BYTES[tech]) / 1e6, n_leaves, LEAF_RECORD_BYTES[tech]),
                        "seed": hex(V.DEFAULT_SEED), "build_ms": build_timing["build_total_ms"],
                        "traversal_kernel": ("value: trace_pool_kernel (per-warp ray pool) for Phantom frames of >= 3x the pool's resident capacity, else "
                                             "trace_kernel (lane-bound); e2e: the same kernel delivering complete 128-byte lines of records to the pinned host buffer"),

@@ -268,7 +268,7 @@ def test_full_size_config2_properties(V, O):
         nodes, ids, morton, _ = sc.bvh()
         assert sc.n_primitives == 3200000
         n = ids.shape[0]                                                                # BVH leaves = 2 pieces per curve
-        assert n == 2 * 3200000 and nodes.shape[0] == n - 1
+        assert n == 2 * 3200000 and nodes.shape[0] == n - 1 and sc.n_leaves == n
         assert np.array_equal(np.sort(ids), np.arange(n, dtype=np.uint32))          # a permutation
         assert (np.diff(morton.astype(np.int64)) >= 0).all()                            # sortedness
         leaf0 = nodes["child0"] >> 31 == 1; leaf1 = nodes["child1"] >> 31 == 1

@@ -320,6 +320,13 @@ class Scene:
     def n_primitives(self):
         return int(lib().vkhrt_scene_primitive_count(self._h))
 
+    @property
+    def n_leaves(self):
+        """BVH leaves = primitive groups x VKHRT_LEAF_SPLIT_* pieces (include/vkhrt_b200.h); read from the built scene"""
+        v = BvhView()
+        _check(lib().vkhrt_scene_get_bvh(self._h, C.byref(v)), "vkhrt_scene_get_bvh")
+        return int(v.n_primitives)
+
     def apply_lod(self, line_split_passes=0, line_merge_passes=0, curve_merge_passes=0):
         """SplitLines / MergeLines / MergeCurvesFast on the device, before build()"""
         _check(lib().vkhrt_scene_apply_lod(self._h, line_split_passes, line_merge_passes, curve_merge_passes), "vkhrt_scene_apply_lod")
