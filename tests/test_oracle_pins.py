@@ -377,6 +377,25 @@ def test_mailbox_is_result_neutral(O, V, monkeypatch):
     assert res[4, 1][2]["prims_tested"] < res[4, 0][2]["prims_tested"]        # ... and with pieces it does skip something
 
 
+@pytest.mark.parametrize("tech", [0, 1, 2])
+def test_wide_traversal_study_is_result_neutral(O, V, tech, monkeypatch):
+    """ORC_WIDE=1 (oracle study of a 4-wide walk over the same tree, the next step named in DESIGN.md §8): identical hit records
+    and images, about half the dependent node fetches for about the same number of slab tests."""
+    pos, idx = V.generate_groom(400, 12, V.GROOM_CURLY)
+    W, H = 128, 96
+    vi, pi = V.camera_matrices(aspect=W / H)
+    f = O.make_frame(vi, pi, W, H)
+    h2, i2, s2 = O.OracleScene(pos, idx, technique=tech, radius=0.05).render(f, stats=True)
+    monkeypatch.setenv("ORC_WIDE", "1")
+    h4, i4, s4 = O.OracleScene(pos, idx, technique=tech, radius=0.05).render(f, stats=True)
+    monkeypatch.delenv("ORC_WIDE")
+    assert (h2["flags"] & 1).sum() > 200
+    assert h4.tobytes() == h2.tobytes() and np.array_equal(i4, i2)
+    assert s4["nodes_visited"] < 0.62 * s2["nodes_visited"]
+    assert s4["sched_steps"][0] <= 1.05 * 2 * s2["nodes_visited"]                   # slab tests: 2 per BVH2 visit vs <= 4 per wide visit
+    assert 0 < s4["sched_steps"][1] <= 64                                         # deepest stack
+
+
 def test_oracle_edge_cases(O, V):
     W, H = 32, 24
     vi, pi = V.camera_matrices(aspect=W / H)
