@@ -410,7 +410,7 @@ constexpr uint32_t REF_POP = REF_NONE; // slot.cur marker: the ray resumes by po
 constexpr int PL_MINB = 8;             // CTAs per SM the register allocation is held to
 enum : int { Q_READY = 0, Q_LEAF = 1, Q_CAND = 2, Q_DONE = 3, Q_FREE = 4 };
 
-// 115 bytes per slot.  The origin is the camera position for every primary ray (kernel parameter) and -(o/d) is rebuilt
+// 87 bytes per slot with the default 72 x 4 configuration (119 with an 8-entry stack window).  The origin is the camera position for every primary ray (kernel parameter) and -(o/d) is rebuilt
 // from it when a lane pulls the ray, so a slot stores only d and 1/d; the best hit is (tcur, leaf position, u) — the
 // primitive id lives in the leaf record.
 // PL_S = ray slots per warp; PL_STK = shared-memory stack window per slot (a power of two: the TOP entries; older ones spill to global)
