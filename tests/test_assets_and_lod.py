@@ -319,6 +319,154 @@ def test_gpu_environment_miss_within_one_lsb(V, O, spp):
             sc.render(V.make_frame(vi, pi, W, H, miss_mode=V.MISS_ENVIRONMENT))
 
 
+# ---------------------------------------------------------------- glTF 2.0 line primitives (the format of the reference's own scene)
+def _gltf_doc(bin_len, uri=None, extra=None):
+    """two meshes: mesh 0 = LINES with u16 indices over 4 interleaved (strided) vertices, mesh 1 = LINE_STRIP without indices over 3
+    vertices, a triangle primitive that must be ignored, and a node hierarchy with a matrix, a TRS child and an untransformed root"""
+    doc = {
+        "asset": {"version": "2.0"},
+        "scene": 0,
+        "scenes": [{"nodes": [0, 2]}],
+        "nodes": [
+            {"name": "root", "matrix": [1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0, 10, 20, 30, 1], "children": [1]},
+            {"name": "child", "mesh": 1, "translation": [1, 0, 0], "rotation": [0, 0, 0.7071067811865476, 0.7071067811865476], "scale": [2, 2, 2]},
+            {"name": "plain", "mesh": 0},
+        ],
+        "meshes": [
+            {"primitives": [{"mode": 1, "attributes": {"POSITION": 0}, "indices": 1},
+                            {"mode": 4, "attributes": {"POSITION": 0}, "indices": 1}]},
+            {"primitives": [{"mode": 3, "attributes": {"POSITION": 2}}]},
+        ],
+        "accessors": [
+            {"bufferView": 0, "componentType": 5126, "count": 4, "type": "VEC3"},
+            {"bufferView": 1, "componentType": 5123, "count": 6, "type": "SCALAR"},
+            {"bufferView": 2, "byteOffset": 4, "componentType": 5126, "count": 3, "type": "VEC3"},
+        ],
+        "bufferViews": [
+            {"buffer": 0, "byteOffset": 0, "byteLength": 80, "byteStride": 20},
+            {"buffer": 0, "byteOffset": 80, "byteLength": 12},
+            {"buffer": 0, "byteOffset": 92, "byteLength": 40},
+        ],
+        "buffers": [{"byteLength": bin_len}],
+    }
+    if uri is not None:
+        doc["buffers"][0]["uri"] = uri
+    if extra:
+        doc.update(extra)
+    return doc
+
+
+def _gltf_bin():
+    v0 = np.array([[0, 0, 0], [1, 0, 0], [2, 1, 0], [3, 1, 1]], np.float32)
+    inter = b"".join(v0[i].tobytes() + struct.pack("<ff", 9.0, 9.0) for i in range(4))      # 12 bytes position + 8 bytes of other attributes
+    ind = np.array([0, 1, 1, 2, 2, 3], np.uint16).tobytes()
+    v1 = np.array([[0, 0, 0], [0, 1, 0], [0, 2, 0.5]], np.float32)
+    blob = inter + ind + struct.pack("<f", 123.0) + v1.tobytes()
+    assert len(blob) == 80 + 12 + 40
+    return blob, v0, v1
+
+
+def _gltf_expected(v0, v1):
+    # node "child": world = root(translate 10,20,30) * T(1,0,0) * Rz(90 deg) * S(2): p -> (10 + 1 - 2 y, 20 + 2 x, 30 + 2 z)
+    w1 = np.stack([11.0 - 2.0 * v1[:, 1].astype(np.float64), 20.0 + 2.0 * v1[:, 0].astype(np.float64), 30.0 + 2.0 * v1[:, 2].astype(np.float64)], axis=1)
+    pos = np.concatenate([w1.astype(np.float32), v0])
+    idx = np.array([[0, 1], [1, 2], [3, 4], [4, 5], [5, 6]], np.uint32)
+    return pos, idx
+
+
+@pytest.mark.parametrize("container", ["external", "base64", "glb", "glb-padded"])
+def test_gltf_line_primitives(V, tmp_path, container):
+    import base64
+    import json
+    blob, v0, v1 = _gltf_bin()
+    if container == "external":
+        (tmp_path / "hair data.bin").write_bytes(blob)
+        path = tmp_path / "a.gltf"
+        path.write_text(json.dumps(_gltf_doc(len(blob), "hair%20data.bin")))
+    elif container == "base64":
+        path = tmp_path / "a.gltf"
+        path.write_text(json.dumps(_gltf_doc(len(blob), "data:application/octet-stream;base64," + base64.b64encode(blob).decode()), indent=2))
+    else:
+        js = json.dumps(_gltf_doc(len(blob))).encode()
+        if container == "glb-padded":
+            js += b" "
+        js += b" " * (-len(js) % 4)
+        body = struct.pack("<II", len(js), 0x4E4F534A) + js + struct.pack("<II", len(blob), 0x004E4942) + blob
+        path = tmp_path / "a.glb"
+        path.write_bytes(b"glTF" + struct.pack("<II", 2, 12 + len(body)) + body)
+    pos, idx, rpv, strands = V.load_lines(str(path))
+    epos, eidx = _gltf_expected(v0, v1)
+    assert rpv is None and strands == 2
+    assert np.array_equal(idx, eidx)
+    assert np.array_equal(pos[3:], epos[3:])                       # untransformed node: the file's floats, bit for bit
+    assert np.allclose(pos[:3], epos[:3], rtol=0, atol=2e-6)       # transformed node: double arithmetic rounded once
+    # consecutive segments of a strand share the vertex, which is what GenerateCurves keys on
+    assert idx[0, 1] == idx[1, 0] and idx[2, 1] == idx[3, 0]
+
+
+def test_gltf_loop_no_scene_and_errors(V, tmp_path):
+    import base64
+    import json
+    tri = np.array([[0, 0, 0], [1, 0, 0], [0, 1, 0]], np.float32)
+    uri = "data:application/octet-stream;base64," + base64.b64encode(tri.tobytes()).decode()
+    base = {"asset": {"version": "2.0"}, "meshes": [{"primitives": [{"mode": 2, "attributes": {"POSITION": 0}}]}],
+            "accessors": [{"bufferView": 0, "componentType": 5126, "count": 3, "type": "VEC3"}],
+            "bufferViews": [{"buffer": 0, "byteLength": 36}], "buffers": [{"byteLength": 36, "uri": uri}]}
+    p = tmp_path / "loop.gltf"
+    p.write_text(json.dumps(base))                                  # no nodes at all: meshes as they are
+    pos, idx, _, strands = V.load_lines(str(p))
+    assert np.array_equal(pos, tri) and np.array_equal(idx, [[0, 1], [1, 2], [2, 0]]) and strands == 1
+    # a mesh instanced by two nodes is emitted twice
+    two = dict(base, nodes=[{"mesh": 0}, {"mesh": 0, "translation": [0, 0, 5]}])
+    p.write_text(json.dumps(two))
+    pos, idx, _, _ = V.load_lines(str(p))
+    assert pos.shape == (6, 3) and idx.shape == (6, 2) and np.array_equal(pos[3:], tri + np.float32([0, 0, 5]))
+
+    def expect(doc, status):
+        p.write_text(json.dumps(doc))
+        with pytest.raises(V.VkhrtError) as e:
+            V.load_lines(str(p))
+        assert e.value.status == status, e.value
+    expect(dict(base, extensionsRequired=["KHR_draco_mesh_compression"]), -7)                                          # unsupported
+    expect(dict(base, accessors=[{"bufferView": 0, "componentType": 5126, "count": 4, "type": "VEC3"}]), -8)          # runs past its view
+    expect(dict(base, accessors=[{"bufferView": 0, "componentType": 5126, "count": 3, "type": "VEC3", "sparse": {"count": 1}}]), -7)
+    expect(dict(base, accessors=[{"bufferView": 0, "componentType": 5123, "count": 3, "type": "VEC3"}]), -7)          # positions must be float
+    expect(dict(base, bufferViews=[{"buffer": 0, "byteLength": 360}]), -8)                                            # view past the buffer
+    expect(dict(base, buffers=[{"byteLength": 36, "uri": "missing.bin"}]), -8)
+    expect(dict(base, scenes=[{"nodes": [0]}], nodes=[{"mesh": 0, "children": [0]}]), -8)                                                       # a cycle
+    bad_idx = dict(base, meshes=[{"primitives": [{"mode": 1, "attributes": {"POSITION": 0}, "indices": 1}]}])
+    bad_idx["accessors"] = base["accessors"] + [{"bufferView": 1, "componentType": 5125, "count": 2, "type": "SCALAR"}]
+    bad_idx["bufferViews"] = base["bufferViews"] + [{"buffer": 1, "byteLength": 8}]
+    bad_idx["buffers"] = base["buffers"] + [{"byteLength": 8, "uri": "data:application/octet-stream;base64," + base64.b64encode(struct.pack("<II", 0, 7)).decode()}]
+    expect(bad_idx, -6)                                                                                                # index out of range
+    p.write_text("{ not json")
+    with pytest.raises(V.VkhrtError):
+        V.load_lines(str(p))
+
+
+def test_gltf_groom_renders_like_the_same_lines(V, O, tmp_path):
+    """a groom written as glTF LINES by hand and read back feeds the oracle exactly like the original arrays (CPU only)"""
+    import json
+    pos, idx = V.generate_groom(60, 6, V.GROOM_CURLY)
+    blob = pos.tobytes() + idx.astype(np.uint32).tobytes()
+    (tmp_path / "g.bin").write_bytes(blob)
+    doc = {"asset": {"version": "2.0"}, "scenes": [{"nodes": [0]}], "nodes": [{"mesh": 0}],
+           "meshes": [{"primitives": [{"mode": 1, "attributes": {"POSITION": 0}, "indices": 1}]}],
+           "accessors": [{"bufferView": 0, "componentType": 5126, "count": int(pos.shape[0]), "type": "VEC3"},
+                         {"bufferView": 1, "componentType": 5125, "count": int(idx.size), "type": "SCALAR"}],
+           "bufferViews": [{"buffer": 0, "byteLength": pos.nbytes}, {"buffer": 0, "byteOffset": pos.nbytes, "byteLength": idx.size * 4}],
+           "buffers": [{"byteLength": len(blob), "uri": "g.bin"}]}
+    (tmp_path / "g.gltf").write_text(json.dumps(doc))
+    p2, i2, _, strands = V.load_lines(str(tmp_path / "g.gltf"))
+    assert np.array_equal(p2, pos) and np.array_equal(i2, idx) and strands == 60
+    W, H = 64, 48
+    vi, pi = default_camera(V, W, H)
+    f = O.make_frame(vi, pi, W, H)
+    h1, _, _ = O.OracleScene(pos, idx).render(f)
+    h2, _, _ = O.OracleScene(p2, i2).render(f)
+    assert h1.tobytes() == h2.tobytes() and (h1["flags"] & 1).sum() > 10
+
+
 def test_loaders_survive_truncated_and_corrupt_files(V, tmp_path):
     """every prefix of a valid file and a few hundred random mutations: the readers must return an error or an asset, never crash
     (the reference logs and returns nullptr on a failed load, model_loader.cpp:280-284)"""
@@ -332,6 +480,14 @@ def test_loaders_survive_truncated_and_corrupt_files(V, tmp_path):
     hp = tmp_path / "e.hdr"
     V.save_hdr(str(hp), V.generate_environment(16, 8))
     good["hdr"] = hp.read_bytes()
+    import base64
+    import json
+    blob, _, _ = _gltf_bin()
+    good["gltf"] = json.dumps(_gltf_doc(len(blob), "data:application/octet-stream;base64," + base64.b64encode(blob).decode())).encode()
+    js = json.dumps(_gltf_doc(len(blob))).encode()
+    js += b" " * (-len(js) % 4)
+    body = struct.pack("<II", len(js), 0x4E4F534A) + js + struct.pack("<II", len(blob), 0x004E4942) + blob
+    good["glb"] = b"glTF" + struct.pack("<II", 2, 12 + len(body)) + body
     n_ok = n_err = 0
     for ext, data in good.items():
         cases = [data[:k] for k in range(0, len(data), max(1, len(data) // 60))]

@@ -227,7 +227,7 @@ def make_frame(view_inv, proj_inv, width, height, spp=1, shade_mode=SHADE, miss_
 
 
 def load_lines(path):
-    """ModelLoader::LoadFromFile for line assets (.obj `l` records, .hair): -> (positions [n,3], indices [m,2], radius_per_vertex | None, n_strands)"""
+    """ModelLoader::LoadFromFile for line assets (.gltf / .glb line primitives, .obj `l` records, .hair): -> (positions [n,3], indices [m,2], radius_per_vertex | None, n_strands)"""
     a = LineAsset()
     _check(lib().vkhrt_asset_load_lines(os.fsencode(path), C.byref(a)), "vkhrt_asset_load_lines")
     try:

@@ -21,6 +21,7 @@
 
 namespace vkhrt {
 void set_last_error(const std::string& s);
+int load_gltf(const std::string& path, const std::vector<unsigned char>& data, bool glb, VkhrtLineAsset* out);   // gltf.cpp
 }
 using vkhrt::set_last_error;
 
@@ -361,7 +362,9 @@ int vkhrt_asset_load_lines(const char* path, VkhrtLineAsset* out)
     int rc;
     if (ends_with(p, ".obj")) rc = load_obj(data, out);
     else if (ends_with(p, ".hair")) rc = load_hair(data, out);
-    else return fail(VKHRT_ERR_UNSUPPORTED, "unknown line-asset extension (supported: .obj, .hair)");
+    else if (ends_with(p, ".gltf")) rc = vkhrt::load_gltf(p, data, false, out);
+    else if (ends_with(p, ".glb")) rc = vkhrt::load_gltf(p, data, true, out);
+    else return fail(VKHRT_ERR_UNSUPPORTED, "unknown line-asset extension (supported: .obj, .hair, .gltf, .glb)");
     if (rc == VKHRT_OK && (!out->positions_xyz || !out->line_indices)) { vkhrt_asset_free(out); return fail(VKHRT_ERR_OUT_OF_MEMORY, "out of host memory"); }
     return rc;
 }

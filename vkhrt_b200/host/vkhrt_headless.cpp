@@ -19,7 +19,7 @@ using namespace vkhrt_host;
 
 static void usage()
 {
-    std::puts("usage: vkhrt_headless --model <file.obj | file.hair | synthetic:<straight|curly>:<strands>:<segments>[:seed]>\n"
+    std::puts("usage: vkhrt_headless --model <file.gltf | file.glb | file.obj | file.hair | synthetic:<straight|curly>:<strands>:<segments>[:seed]>\n"
               "                      [--technique phantom|lss|dots] [--size WxH] [--spp N] [--debug-primid]\n"
               "                      [--frames N] [--ppm out.ppm] [--png out.png] [--hits out.bin] [--device D]\n"
               "                      [--env procedural|file.hdr] [--ao N] [--lod split,merge,curve_merge]");

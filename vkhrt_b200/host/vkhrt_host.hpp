@@ -99,7 +99,8 @@ private:
 class ModelLoader {
 public:
     explicit ModelLoader(int device = 0) : _device(device) {}
-    // path: a line asset (.obj with `v` / `l i j k ...` polyline records, or a Cem Yuksel .hair file), or
+    // path: a line asset (.gltf / .glb line primitives — what the reference loads, renderer.cpp:33-37 —, .obj with `v` / `l i j k ...`
+    // polyline records, or a Cem Yuksel .hair file), or
     // "synthetic:<straight|curly>:<strands>:<segments>[:<seed>]".  Returns nullptr on failure like the reference.
     [[nodiscard]] std::shared_ptr<Model> LoadFromFile(std::string_view path, VkhrtTechnique technique = VKHRT_TECHNIQUE_LSS,
                                                       uint32_t lineSplitPasses = 0, uint32_t lineMergePasses = 0, uint32_t curveMergePasses = 0)
