@@ -319,7 +319,7 @@ typedef struct VkhrtLineAsset {
 } VkhrtLineAsset;
 /* by extension: .obj (`v` + `l` polyline records), .hair (Cem Yuksel HAIR format), .gltf / .glb (glTF 2.0 line primitives: modes LINES,
  * LINE_LOOP, LINE_STRIP; external, base64 or GLB buffers; node transforms applied to the positions) — the format of the reference's own
- * scene (source/renderer.cpp:33-37).  Saving: .obj and .hair. */
+ * scene (source/renderer.cpp:33-37).  Saving: .obj, .hair and .glb (one LINES primitive, loadable by Assimp and therefore by the reference). */
 int  vkhrt_asset_load_lines(const char* path, VkhrtLineAsset* out);
 int  vkhrt_asset_save_lines(const char* path, const VkhrtLineAsset* in);
 void vkhrt_asset_free(VkhrtLineAsset* asset);

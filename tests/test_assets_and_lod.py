@@ -42,7 +42,7 @@ def test_obj_errors(V, tmp_path):
     assert e.value.status == -7                                    # UNSUPPORTED
 
 
-@pytest.mark.parametrize("ext", ["obj", "hair"])
+@pytest.mark.parametrize("ext", ["obj", "hair", "glb"])
 def test_line_asset_round_trip_is_exact(V, tmp_path, ext):
     pos, idx = V.generate_groom(37, 5, V.GROOM_CURLY)
     path = str(tmp_path / f"g.{ext}")
@@ -50,6 +50,22 @@ def test_line_asset_round_trip_is_exact(V, tmp_path, ext):
     p2, i2, rpv, strands = V.load_lines(path)
     assert strands == 37 and rpv is None
     assert p2.tobytes() == pos.tobytes() and np.array_equal(i2, idx)     # %.9g text round-trips fp32 exactly
+    if ext == "glb":
+        # the container a glTF importer (Assimp in the reference) expects: header, 4-byte aligned JSON + BIN chunks, POSITION min / max
+        import json
+        raw = open(path, "rb").read()
+        magic, version, total = struct.unpack("<4sII", raw[:12])
+        jlen, jtype = struct.unpack("<II", raw[12:20])
+        assert magic == b"glTF" and version == 2 and total == len(raw) and jtype == 0x4E4F534A and jlen % 4 == 0
+        doc = json.loads(raw[20:20 + jlen])
+        blen, btype = struct.unpack("<II", raw[20 + jlen:28 + jlen])
+        assert btype == 0x004E4942 and blen == pos.nbytes + idx.nbytes == doc["buffers"][0]["byteLength"] and 28 + jlen + blen == total
+        acc = doc["accessors"][0]
+        assert doc["meshes"][0]["primitives"][0]["mode"] == 1 and acc["count"] == pos.shape[0]
+        assert np.array_equal(np.float32(acc["min"]), pos.min(axis=0)) and np.array_equal(np.float32(acc["max"]), pos.max(axis=0))
+        V.save_lines(path, np.zeros((0, 3), np.float32), np.zeros((0, 2), np.uint32))       # an empty asset is still a valid file
+        p3, i3, _, _ = V.load_lines(path)
+        assert p3.shape == (0, 3) and i3.shape == (0, 2)
 
 
 def test_hair_file_layout_and_thickness(V, tmp_path):

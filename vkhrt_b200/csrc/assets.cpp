@@ -22,6 +22,7 @@
 namespace vkhrt {
 void set_last_error(const std::string& s);
 int load_gltf(const std::string& path, const std::vector<unsigned char>& data, bool glb, VkhrtLineAsset* out);   // gltf.cpp
+int save_glb(const char* path, const VkhrtLineAsset* in);
 }
 using vkhrt::set_last_error;
 
@@ -377,7 +378,8 @@ int vkhrt_asset_save_lines(const char* path, const VkhrtLineAsset* in)
     std::string p(path);
     if (ends_with(p, ".obj")) return save_obj(path, in);
     if (ends_with(p, ".hair")) return save_hair(path, in);
-    return fail(VKHRT_ERR_UNSUPPORTED, "unknown line-asset extension (supported: .obj, .hair)");
+    if (ends_with(p, ".glb")) return vkhrt::save_glb(path, in);
+    return fail(VKHRT_ERR_UNSUPPORTED, "unknown line-asset extension (supported: .obj, .hair, .glb)");
 }
 
 void vkhrt_asset_free(VkhrtLineAsset* a)

@@ -31,6 +31,7 @@
 namespace vkhrt {
 void set_last_error(const std::string& s);
 int load_gltf(const std::string& path, const std::vector<unsigned char>& data, bool glb, VkhrtLineAsset* out);
+int save_glb(const char* path, const VkhrtLineAsset* in);
 }
 
 namespace {
@@ -459,6 +460,55 @@ int load_gltf(const std::string& path, const std::vector<unsigned char>& data, b
     out->line_indices = dup_array(b.idx);
     out->radius_per_vertex = nullptr;
     return VKHRT_OK;
+}
+
+// Writer: one .glb with one mesh, one LINES primitive (float positions, u32 index pairs), one untransformed node — loadable by
+// Assimp (i.e. by the reference) and by load_gltf above, which returns the very same arrays.
+int save_glb(const char* path, const VkhrtLineAsset* in)
+{
+    const size_t pos_bytes = (size_t)in->n_vertices * 12, idx_bytes = (size_t)in->n_segments * 8;
+    float lo[3] = {0, 0, 0}, hi[3] = {0, 0, 0};
+    for (uint32_t i = 0; i < in->n_vertices; ++i)
+        for (int k = 0; k < 3; ++k) {
+            const float v = in->positions_xyz[3 * (size_t)i + k];
+            if (i == 0 || v < lo[k]) lo[k] = v;
+            if (i == 0 || v > hi[k]) hi[k] = v;
+        }
+    char js[1024];
+    int n;
+    if (in->n_vertices && in->n_segments)
+        n = std::snprintf(js, sizeof(js),
+            "{\"asset\":{\"version\":\"2.0\",\"generator\":\"vkhrt_b200\"},\"scene\":0,\"scenes\":[{\"nodes\":[0]}],\"nodes\":[{\"mesh\":0}],"
+            "\"meshes\":[{\"primitives\":[{\"mode\":1,\"attributes\":{\"POSITION\":0},\"indices\":1}]}],"
+            "\"accessors\":[{\"bufferView\":0,\"componentType\":5126,\"count\":%u,\"type\":\"VEC3\",\"min\":[%.9g,%.9g,%.9g],\"max\":[%.9g,%.9g,%.9g]},"
+            "{\"bufferView\":1,\"componentType\":5125,\"count\":%zu,\"type\":\"SCALAR\"}],"
+            "\"bufferViews\":[{\"buffer\":0,\"byteOffset\":0,\"byteLength\":%zu,\"target\":34962},{\"buffer\":0,\"byteOffset\":%zu,\"byteLength\":%zu,\"target\":34963}],"
+            "\"buffers\":[{\"byteLength\":%zu}]}",
+            in->n_vertices, (double)lo[0], (double)lo[1], (double)lo[2], (double)hi[0], (double)hi[1], (double)hi[2], (size_t)in->n_segments * 2,
+            pos_bytes, pos_bytes, idx_bytes, pos_bytes + idx_bytes);
+    else
+        n = std::snprintf(js, sizeof(js), "{\"asset\":{\"version\":\"2.0\",\"generator\":\"vkhrt_b200\"},\"scenes\":[{\"nodes\":[]}]}");
+    if (n <= 0 || (size_t)n >= sizeof(js)) return fail(VKHRT_ERR_IO, "glb: header formatting failed");
+    std::string json(js, (size_t)n);
+    while (json.size() % 4) json.push_back(' ');
+    const size_t bin_bytes = (in->n_vertices && in->n_segments) ? pos_bytes + idx_bytes : 0;       // both are multiples of 4
+    const size_t total = 12 + 8 + json.size() + (bin_bytes ? 8 + bin_bytes : 0);
+    if (total > 0xFFFFFFFFull) return fail(VKHRT_ERR_UNSUPPORTED, "glb: asset larger than 4 GiB");
+    FILE* f = std::fopen(path, "wb");
+    if (!f) return fail(VKHRT_ERR_IO, std::string("cannot write ") + path);
+    bool ok = true;
+    auto put32 = [&](uint32_t v) { ok = ok && std::fwrite(&v, 4, 1, f) == 1; };
+    ok = std::fwrite("glTF", 1, 4, f) == 4;
+    put32(2u); put32((uint32_t)total);
+    put32((uint32_t)json.size()); put32(0x4E4F534Au);
+    ok = ok && std::fwrite(json.data(), 1, json.size(), f) == json.size();
+    if (bin_bytes) {
+        put32((uint32_t)bin_bytes); put32(0x004E4942u);
+        ok = ok && std::fwrite(in->positions_xyz, 1, pos_bytes, f) == pos_bytes;
+        ok = ok && std::fwrite(in->line_indices, 1, idx_bytes, f) == idx_bytes;
+    }
+    ok = (std::fclose(f) == 0) && ok;
+    return ok ? VKHRT_OK : fail(VKHRT_ERR_IO, std::string("short write to ") + path);
 }
 
 }  // namespace vkhrt
