@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define VKHRT_ABI_VERSION 3
+#define VKHRT_ABI_VERSION 4
 
 typedef enum VkhrtStatus {
     VKHRT_OK = 0,
@@ -268,6 +268,15 @@ uint64_t vkhrt_frame_local_pixels(const VkhrtFrameDesc* frame);
  * device pointers; elem_bytes = 32 (hits) or 4 (rgba8). */
 int  vkhrt_untile(const VkhrtFrameDesc* frame, uint32_t world, const void* gathered, void* row_major,
                   uint32_t elem_bytes, void* stream);
+/* the same re-ordering on HOST buffers (plain loops, no device needed) */
+int  vkhrt_untile_host(const VkhrtFrameDesc* frame, uint32_t world, const void* gathered, void* row_major, uint32_t elem_bytes);
+/* One frame on several GPUs from ONE process (the shape of the reference's single executable).  scenes[r] is the
+ * same geometry built on device r (deterministic build => identical BVHs; several scenes may also share a device).  The frame is cut
+ * into tile_size^2 tiles dealt round-robin (scene r traces tiles r, r + n, ...; no exchange step), one host thread
+ * per scene drives vkhrt_render on its shard, and the shards are re-ordered into the caller's row-major HOST buffers.  `frame` must
+ * describe the whole frame (tile_stride <= 1) with output_memory = VKHRT_MEM_HOST; results are identical to vkhrt_render's.
+ * The per-process path used by bench.py (one process per GPU, NVLink peer stores) is vkhrt_b200/multi.py. */
+int  vkhrt_render_multi(VkhrtScene* const* scenes, uint32_t n_scenes, const VkhrtFrameDesc* frame, VkhrtHit* hits_out, uint8_t* rgba8_out);
 int  vkhrt_last_timing(const VkhrtScene* scene, VkhrtTiming* timing);
 
 /* ---- device buffers shareable between the per-GPU processes of one box (CUDA IPC over NVLink/PCIe) ---- */

@@ -86,7 +86,7 @@ def test_header_is_plain_c(V):
 
 def test_error_strings_and_versions(V):
     L = V.lib()
-    assert L.vkhrt_abi_version() == 3
+    assert L.vkhrt_abi_version() == 4
     assert L.vkhrt_error_string(0) == b"ok"
     for code in range(-8, 0):
         assert L.vkhrt_error_string(code) not in (b"ok", b"unknown status")
@@ -134,6 +134,29 @@ def test_frame_local_pixels_and_tile_layout(V):
         if world > 1:
             gi = lay.gather_index()
             assert gi.shape[0] == W * H and np.unique(gi).shape[0] == W * H and gi.max() < world * lay.shard_pixels
+
+
+def test_untile_host_equals_the_numpy_mirror(V):
+    """vkhrt_untile_host (what vkhrt_render_multi assembles the frame with) against TileSharding.untile_host, on random shards"""
+    from vkhrt_b200.multi import TileSharding
+    rng = np.random.default_rng(3)
+    for (W, H, T, world) in ((200, 120, 32, 3), (333, 77, 64, 2), (64, 64, 64, 4), (130, 70, 8, 5), (50, 40, 64, 1)):
+        lay = TileSharding(W, H, world, T)
+        f = V.make_frame(np.eye(4), np.eye(4), W, H, tile_size=T)
+        n = world * lay.shard_pixels
+        hits = np.frombuffer(rng.integers(0, 256, n * 32, dtype=np.uint8).tobytes(), V.HIT_DTYPE).copy()
+        rgba = rng.integers(0, 256, (n, 4), dtype=np.uint8)
+        assert V.untile_host(f, world, hits).tobytes() == lay.untile_host(hits).tobytes()
+        assert np.array_equal(V.untile_host(f, world, rgba), lay.untile_host(rgba))
+    L = V.lib()
+    assert L.vkhrt_untile_host(None, 2, None, None, 4) == -1
+    buf = np.zeros(64 * 64 * 2, np.uint8)
+    f = V.make_frame(np.eye(4), np.eye(4), 64, 64)
+    assert L.vkhrt_untile_host(C.byref(f), 2, buf.ctypes.data, buf.ctypes.data, 7) == -1           # element size
+    # render_multi validates before it touches a device
+    assert L.vkhrt_render_multi(None, 2, C.byref(f), None, None) == -1
+    arr = (C.c_void_p * 2)(None, None)
+    assert L.vkhrt_render_multi(arr, 0, C.byref(f), None, None) == -1 and L.vkhrt_render_multi(arr, 2, C.byref(f), None, None) == -1
 
 
 # ---------------------------------------------------------------- FlyCamera (source/fly_camera.cpp:25-35)

@@ -486,6 +486,37 @@ def test_any_hit_wavefront_rays(V, O, small_groom, tech):
             assert np.array_equal(dh.cpu().numpy().reshape(-1), ho.view(np.uint8).reshape(-1)), f"any_hit={any_hit}"
 
 
+@pytest.mark.gpu
+@pytest.mark.parametrize("tech", TECHS)
+def test_render_multi_from_one_process(V, small_groom, tech):
+    """vkhrt_render_multi: several scene handles (one per device; here also several on one device), tiles dealt round-robin,
+    one host thread per handle, host re-ordering: the frame must equal vkhrt_render's, bit for bit"""
+    pos, idx = small_groom
+    W, H = 333, 201                                    # partial tiles on both edges
+    vi, pi = default_camera(V, W, H)
+    ndev = V.device_count()
+    with V.Scene(pos, idx, technique=tech) as ref:
+        ref.build()
+        h0, i0, _ = ref.render(V.make_frame(vi, pi, W, H, spp=2, miss_rgb=(0.1, 0.2, 0.3)))
+    for n in (1, 2, 3):
+        scenes = [V.Scene(pos, idx, technique=tech, device=r % ndev).build() for r in range(n)]
+        try:
+            for tile in (0, 32):
+                h, img = V.render_multi(scenes, V.make_frame(vi, pi, W, H, spp=2, miss_rgb=(0.1, 0.2, 0.3), tile_size=tile))
+                assert h.tobytes() == h0.tobytes() and np.array_equal(img, i0), (n, tile)
+            h, img = V.render_multi(scenes, V.make_frame(vi, pi, W, H), rgba=False)
+            assert img is None and h.tobytes() == h0.tobytes()
+        finally:
+            for sc in scenes:
+                sc.close()
+    with V.Scene(pos, idx, technique=tech) as sc:
+        sc.build()
+        with pytest.raises(V.VkhrtError):
+            V.render_multi([sc, sc], V.make_frame(vi, pi, W, H))                      # one handle twice
+        with pytest.raises(V.VkhrtError):
+            V.render_multi([sc], V.make_frame(vi, pi, W, H, tile_first=1, tile_stride=2))   # the frame must be whole
+
+
 @pytest.mark.parametrize("env", [{"VKHRT_POOL_MIN_RATIO": "0"}, {"VKHRT_POOL_MIN_RATIO": "0", "VKHRT_POOL_CFG": "1"}, {"VKHRT_POOL": "0"}],
                          ids=["pool-on-every-frame", "pool-56x8", "lane-bound-only"])
 def test_both_traversal_kernels_pass_the_whole_suite(env):

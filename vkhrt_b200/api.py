@@ -90,7 +90,7 @@ ABI_SYMBOLS = [
     "vkhrt_abi_version", "vkhrt_device_count", "vkhrt_error_string", "vkhrt_last_error", "vkhrt_launch_count",
     "vkhrt_scene_create", "vkhrt_scene_build", "vkhrt_scene_refit", "vkhrt_scene_get_bvh",
     "vkhrt_scene_get_primitives", "vkhrt_scene_primitive_count", "vkhrt_scene_destroy",
-    "vkhrt_render", "vkhrt_render_stats", "vkhrt_frame_local_pixels", "vkhrt_untile", "vkhrt_last_timing",
+    "vkhrt_render", "vkhrt_render_stats", "vkhrt_frame_local_pixels", "vkhrt_untile", "vkhrt_untile_host", "vkhrt_render_multi", "vkhrt_last_timing",
     "vkhrt_generate_rays", "vkhrt_trace_rays", "vkhrt_trace_rays_any_hit", "vkhrt_camera_matrices", "vkhrt_groom_generate",
     "vkhrt_shared_buffer_create", "vkhrt_shared_buffer_open", "vkhrt_shared_buffer_close", "vkhrt_shared_buffer_destroy",
     "vkhrt_scene_set_environment", "vkhrt_scene_apply_lod", "vkhrt_scene_segment_count", "vkhrt_scene_get_lines",
@@ -134,6 +134,8 @@ def lib():
     L.vkhrt_frame_local_pixels.restype = C.c_uint64
     L.vkhrt_frame_local_pixels.argtypes = [C.POINTER(FrameDesc)]
     L.vkhrt_untile.argtypes = [C.POINTER(FrameDesc), C.c_uint32, C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p]
+    L.vkhrt_untile_host.argtypes = [C.POINTER(FrameDesc), C.c_uint32, C.c_void_p, C.c_void_p, C.c_uint32]
+    L.vkhrt_render_multi.argtypes = [C.POINTER(C.c_void_p), C.c_uint32, C.POINTER(FrameDesc), C.c_void_p, C.c_void_p]
     L.vkhrt_last_timing.argtypes = [C.c_void_p, C.POINTER(Timing)]
     L.vkhrt_generate_rays.argtypes = [C.POINTER(FrameDesc), C.c_uint32, C.c_void_p, C.c_int]
     L.vkhrt_trace_rays.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p]
@@ -162,7 +164,7 @@ def lib():
     L.vkhrt_image_save_png.argtypes = [C.c_char_p, C.c_void_p, C.c_uint32, C.c_uint32]
     L.vkhrt_environment_generate.argtypes = [C.c_uint32, C.c_uint32, C.c_void_p]
     L.vkhrt_environment_generate.restype = None
-    if L.vkhrt_abi_version() != 3:
+    if L.vkhrt_abi_version() != 4:
         raise ImportError("libvkhrt_b200.so ABI version mismatch")
     _lib = L
     return L
@@ -283,6 +285,33 @@ def frame_local_pixels(frame):
 
 def untile(frame, world, gathered_ptr, out_ptr, elem_bytes, stream=None):
     _check(lib().vkhrt_untile(C.byref(frame), world, gathered_ptr, out_ptr, elem_bytes, stream), "vkhrt_untile")
+
+
+def untile_host(frame, world, gathered):
+    """vkhrt_untile_host: compact shards concatenated rank-major -> row-major.  gathered: HIT_DTYPE[world * shard] or uint8[world * shard, 4]"""
+    g = np.ascontiguousarray(gathered)
+    n = frame.width * frame.height
+    if g.dtype == HIT_DTYPE:
+        out, elem = np.zeros(n, HIT_DTYPE), 32
+    elif g.dtype == np.uint8 and g.ndim == 2 and g.shape[1] == 4:
+        out, elem = np.zeros((n, 4), np.uint8), 4
+    else:
+        raise ValueError("untile_host: HIT_DTYPE records or [n, 4] uint8 pixels")
+    _check(lib().vkhrt_untile_host(C.byref(frame), world, g.ctypes.data, out.ctypes.data, elem), "vkhrt_untile_host")
+    return out
+
+
+def render_multi(scenes, frame, hits=True, rgba=True):
+    """vkhrt_render_multi: one frame on several GPUs from this process (scenes[r] = the same groom built on device r) ->
+    (hits[H*W], rgba[H*W, 4]) in row-major order, identical to Scene.render of the whole frame"""
+    frame.output_memory = MEM_HOST
+    n = frame.width * frame.height
+    h = np.zeros(n, HIT_DTYPE) if hits else None
+    img = np.zeros((n, 4), np.uint8) if rgba else None
+    arr = (C.c_void_p * len(scenes))(*[sc._h for sc in scenes])
+    _check(lib().vkhrt_render_multi(arr, len(scenes), C.byref(frame), h.ctypes.data if hits else None, img.ctypes.data if rgba else None),
+           "vkhrt_render_multi")
+    return h, img
 
 
 class Scene:

@@ -6,6 +6,8 @@
 #include <cmath>
 #include <mutex>
 #include <new>
+#include <thread>
+#include <vector>
 
 namespace vkhrt {
 
@@ -235,6 +237,86 @@ int vkhrt_untile(const VkhrtFrameDesc* frame, uint32_t world, const void* gather
 {
     if (!frame || !gathered || !row_major) { set_last_error("null argument"); return VKHRT_ERR_INVALID_ARGUMENT; }
     return untile_buffer(*frame, world, gathered, row_major, elem_bytes, (cudaStream_t)stream);
+}
+
+// compact (tile, pixel-in-tile) shards concatenated rank-major -> row-major, on the host (same index arithmetic as untile_kernel)
+static int untile_host(const VkhrtFrameDesc& f, uint32_t world, const unsigned char* const* shards, unsigned char* row_major, uint32_t elem_bytes)
+{
+    const uint32_t T = f.tile_size ? f.tile_size : 64;
+    if (world == 0 || f.width == 0 || f.height == 0 || T % 8) { set_last_error("untile: bad frame description"); return VKHRT_ERR_INVALID_ARGUMENT; }
+    if (elem_bytes != 4 && elem_bytes != 32) { set_last_error("untile: elem_bytes must be 4 or 32"); return VKHRT_ERR_INVALID_ARGUMENT; }
+    const uint32_t tiles_x = (f.width + T - 1) / T;
+    for (uint32_t py = 0; py < f.height; ++py)
+        for (uint32_t px = 0; px < f.width; ++px) {
+            const uint64_t tile = (uint64_t)(py / T) * tiles_x + px / T;
+            const uint64_t local = (tile / world) * T * T + (uint64_t)(py % T) * T + px % T;
+            std::memcpy(row_major + ((uint64_t)py * f.width + px) * elem_bytes, shards[tile % world] + local * elem_bytes, elem_bytes);
+        }
+    return VKHRT_OK;
+}
+
+int vkhrt_untile_host(const VkhrtFrameDesc* frame, uint32_t world, const void* gathered, void* row_major, uint32_t elem_bytes)
+{
+    if (!frame || !gathered || !row_major || world == 0) { set_last_error("null argument"); return VKHRT_ERR_INVALID_ARGUMENT; }
+    VkhrtFrameDesc shard = *frame;
+    shard.tile_first = 0; shard.tile_stride = world; shard.row_major_output = 0;
+    const uint64_t per_shard = world > 1 ? frame_local_pixels(shard) : (uint64_t)frame->width * frame->height;
+    if (world == 1) { std::memcpy(row_major, gathered, (size_t)(per_shard * elem_bytes)); return (elem_bytes == 4 || elem_bytes == 32) ? VKHRT_OK : VKHRT_ERR_INVALID_ARGUMENT; }
+    std::vector<const unsigned char*> shards(world);
+    for (uint32_t r = 0; r < world; ++r) shards[r] = (const unsigned char*)gathered + (uint64_t)r * per_shard * elem_bytes;
+    return untile_host(*frame, world, shards.data(), (unsigned char*)row_major, elem_bytes);
+}
+
+int vkhrt_render_multi(VkhrtScene* const* scenes, uint32_t n_scenes, const VkhrtFrameDesc* frame, VkhrtHit* hits_out, uint8_t* rgba8_out)
+{
+    if (!scenes || n_scenes == 0 || !frame) { set_last_error("null argument"); return VKHRT_ERR_INVALID_ARGUMENT; }
+    for (uint32_t r = 0; r < n_scenes; ++r) {
+        if (!scenes[r]) { set_last_error("null scene"); return VKHRT_ERR_INVALID_ARGUMENT; }
+        if (!scenes[r]->s.built) { set_last_error("render before build"); return VKHRT_ERR_NOT_BUILT; }
+        for (uint32_t q = 0; q < r; ++q) if (scenes[q] == scenes[r]) { set_last_error("vkhrt_render_multi: the same scene handle twice (calls on one scene are not re-entrant)"); return VKHRT_ERR_INVALID_ARGUMENT; }
+    }
+    if (frame->tile_stride > 1 || frame->tile_first != 0 || frame->row_major_output) { set_last_error("vkhrt_render_multi: the frame must describe the whole image"); return VKHRT_ERR_INVALID_ARGUMENT; }
+    if (frame->output_memory != VKHRT_MEM_HOST) { set_last_error("vkhrt_render_multi: host output buffers only"); return VKHRT_ERR_INVALID_ARGUMENT; }
+    if (n_scenes == 1) return vkhrt_render(scenes[0], frame, hits_out, rgba8_out);
+    VkhrtFrameDesc base = *frame;
+    base.stream = nullptr;
+    if (base.tile_size == 0) base.tile_size = 64;
+    base.tile_stride = n_scenes;
+    const uint64_t per_shard = frame_local_pixels(base);
+    if (per_shard == 0) { set_last_error("vkhrt_render_multi: bad frame description"); return VKHRT_ERR_INVALID_ARGUMENT; }
+    std::vector<std::vector<unsigned char>> sh_hits(n_scenes), sh_rgba(n_scenes);
+    try {
+        for (uint32_t r = 0; r < n_scenes; ++r) {
+            if (hits_out) sh_hits[r].resize((size_t)per_shard * sizeof(VkhrtHit));
+            if (rgba8_out) sh_rgba[r].resize((size_t)per_shard * 4);
+        }
+    } catch (const std::bad_alloc&) { set_last_error("out of host memory"); return VKHRT_ERR_OUT_OF_MEMORY; }
+    init_tunables();                       // the environment switches are read once, before the worker threads launch anything
+    std::vector<int> rc(n_scenes, VKHRT_OK);
+    std::vector<std::string> err(n_scenes);
+    std::vector<std::thread> workers;
+    for (uint32_t r = 0; r < n_scenes; ++r)
+        workers.emplace_back([&, r]() {
+            VkhrtFrameDesc f = base;
+            f.tile_first = r;
+            rc[r] = vkhrt_render(scenes[r], &f, hits_out ? (VkhrtHit*)sh_hits[r].data() : nullptr, rgba8_out ? sh_rgba[r].data() : nullptr);
+            if (rc[r] != VKHRT_OK) err[r] = vkhrt_last_error();       // the error text is per thread: carry it to the caller's
+        });
+    for (std::thread& w : workers) w.join();
+    for (uint32_t r = 0; r < n_scenes; ++r)
+        if (rc[r] != VKHRT_OK) { set_last_error("shard " + std::to_string(r) + ": " + err[r]); return rc[r]; }
+    std::vector<const unsigned char*> ptr(n_scenes);
+    if (hits_out) {
+        for (uint32_t r = 0; r < n_scenes; ++r) ptr[r] = sh_hits[r].data();
+        int u = untile_host(*frame, n_scenes, ptr.data(), (unsigned char*)hits_out, (uint32_t)sizeof(VkhrtHit));
+        if (u) return u;
+    }
+    if (rgba8_out) {
+        for (uint32_t r = 0; r < n_scenes; ++r) ptr[r] = sh_rgba[r].data();
+        int u = untile_host(*frame, n_scenes, ptr.data(), rgba8_out, 4u);
+        if (u) return u;
+    }
+    return VKHRT_OK;
 }
 
 int vkhrt_last_timing(const VkhrtScene* scene, VkhrtTiming* timing)

@@ -96,5 +96,6 @@ int generate_ray_buffer(const VkhrtFrameDesc& f, uint32_t sample, float* rays_de
 int untile_buffer(const VkhrtFrameDesc& f, uint32_t world, const void* gathered, void* row_major, uint32_t elem_bytes,
                   cudaStream_t stream);
 uint64_t frame_local_pixels(const VkhrtFrameDesc& f);
+void init_tunables();   // reads the environment switches once (call before launching from several host threads)
 
 }  // namespace vkhrt

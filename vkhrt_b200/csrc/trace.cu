@@ -918,6 +918,8 @@ static void tunables(TraceParams& p)
     p.w_node = (uint32_t)g_w_node; p.w_leaf = (uint32_t)g_w_leaf; p.w_march = (uint32_t)g_w_march;
 }
 
+void init_tunables() { TraceParams p{}; tunables(p); }
+
 template <int TECH, bool STATS, int SRC, bool ANYHIT, int MINB>
 static int launch_trace_t(DeviceScene& sc, TraceParams& p, cudaStream_t st)
 {
