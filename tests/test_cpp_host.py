@@ -52,6 +52,17 @@ def test_obj_polyline_loader_and_process_functions(probe, tmp_path):
     assert subprocess.run([probe, str(bad)], capture_output=True, text=True).stdout.strip() == "FAIL"
 
 
+def test_gltf_binary_through_the_cpp_loader(probe, V, tmp_path):
+    """ModelLoader::LoadModel on a .glb (the reference loads glTF hair files, source/renderer.cpp:33-37): same arrays as the .obj path"""
+    pos = np.float32([[0, 0, 0], [1, 0, 0], [2, 1, 0], [5, 5, 5], [6, 5, 5]])
+    idx = np.uint32([[0, 1], [1, 2], [3, 4]])
+    V.save_lines(str(tmp_path / "strands.glb"), pos, idx)
+    out = subprocess.run([probe, str(tmp_path / "strands.glb")], capture_output=True, text=True).stdout.split("\n")
+    assert out[0] == "5 3" and out[1].split() == ["0", "1", "1", "2", "3", "4"] and out[2] == "6 5 5"
+    (tmp_path / "cut.glb").write_bytes((tmp_path / "strands.glb").read_bytes()[:60])
+    assert subprocess.run([probe, str(tmp_path / "cut.glb")], capture_output=True, text=True).stdout.strip() == "FAIL"
+
+
 def test_synthetic_uri_matches_the_abi_generator(probe, V):
     out = subprocess.run([probe, "synthetic:curly:50:4"], capture_output=True, text=True).stdout.split("\n")
     assert out[0] == "250 200"
