@@ -1,6 +1,7 @@
 // api.cu — the extern "C" boundary declared in include/vkhrt_b200.h.
 // No CPU fallback lives here: every compute entry point needs a CUDA device.
 #include "scene.h"
+#include <algorithm>
 #include <atomic>
 #include <cstring>
 #include <cmath>
@@ -246,11 +247,13 @@ static int untile_host(const VkhrtFrameDesc& f, uint32_t world, const unsigned c
     if (world == 0 || f.width == 0 || f.height == 0 || T % 8) { set_last_error("untile: bad frame description"); return VKHRT_ERR_INVALID_ARGUMENT; }
     if (elem_bytes != 4 && elem_bytes != 32) { set_last_error("untile: elem_bytes must be 4 or 32"); return VKHRT_ERR_INVALID_ARGUMENT; }
     const uint32_t tiles_x = (f.width + T - 1) / T;
+    // a tile row is contiguous on both sides: one copy per (image row, tile column)
     for (uint32_t py = 0; py < f.height; ++py)
-        for (uint32_t px = 0; px < f.width; ++px) {
-            const uint64_t tile = (uint64_t)(py / T) * tiles_x + px / T;
-            const uint64_t local = (tile / world) * T * T + (uint64_t)(py % T) * T + px % T;
-            std::memcpy(row_major + ((uint64_t)py * f.width + px) * elem_bytes, shards[tile % world] + local * elem_bytes, elem_bytes);
+        for (uint32_t tx = 0; tx < tiles_x; ++tx) {
+            const uint32_t px = tx * T, npx = std::min(T, f.width - px);
+            const uint64_t tile = (uint64_t)(py / T) * tiles_x + tx;
+            const uint64_t local = (tile / world) * T * T + (uint64_t)(py % T) * T;
+            std::memcpy(row_major + ((uint64_t)py * f.width + px) * elem_bytes, shards[tile % world] + local * elem_bytes, (size_t)npx * elem_bytes);
         }
     return VKHRT_OK;
 }
