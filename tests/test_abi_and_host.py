@@ -153,6 +153,7 @@ def test_untile_host_equals_the_numpy_mirror(V):
     buf = np.zeros(64 * 64 * 2, np.uint8)
     f = V.make_frame(np.eye(4), np.eye(4), 64, 64)
     assert L.vkhrt_untile_host(C.byref(f), 2, buf.ctypes.data, buf.ctypes.data, 7) == -1           # element size
+    assert L.vkhrt_untile_host(C.byref(f), 1, buf.ctypes.data, buf.ctypes.data, 7) == -1
     # render_multi validates before it touches a device
     assert L.vkhrt_render_multi(None, 2, C.byref(f), None, None) == -1
     arr = (C.c_void_p * 2)(None, None)

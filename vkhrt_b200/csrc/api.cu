@@ -261,10 +261,11 @@ static int untile_host(const VkhrtFrameDesc& f, uint32_t world, const unsigned c
 int vkhrt_untile_host(const VkhrtFrameDesc* frame, uint32_t world, const void* gathered, void* row_major, uint32_t elem_bytes)
 {
     if (!frame || !gathered || !row_major || world == 0) { set_last_error("null argument"); return VKHRT_ERR_INVALID_ARGUMENT; }
+    if (elem_bytes != 4 && elem_bytes != 32) { set_last_error("untile: elem_bytes must be 4 or 32"); return VKHRT_ERR_INVALID_ARGUMENT; }
     VkhrtFrameDesc shard = *frame;
     shard.tile_first = 0; shard.tile_stride = world; shard.row_major_output = 0;
     const uint64_t per_shard = world > 1 ? frame_local_pixels(shard) : (uint64_t)frame->width * frame->height;
-    if (world == 1) { std::memcpy(row_major, gathered, (size_t)(per_shard * elem_bytes)); return (elem_bytes == 4 || elem_bytes == 32) ? VKHRT_OK : VKHRT_ERR_INVALID_ARGUMENT; }
+    if (world == 1) { std::memcpy(row_major, gathered, (size_t)(per_shard * elem_bytes)); return VKHRT_OK; }
     std::vector<const unsigned char*> shards(world);
     for (uint32_t r = 0; r < world; ++r) shards[r] = (const unsigned char*)gathered + (uint64_t)r * per_shard * elem_bytes;
     return untile_host(*frame, world, shards.data(), (unsigned char*)row_major, elem_bytes);
