@@ -455,6 +455,9 @@ def test_gltf_loop_no_scene_and_errors(V, tmp_path):
     bad_idx["bufferViews"] = base["bufferViews"] + [{"buffer": 1, "byteLength": 8}]
     bad_idx["buffers"] = base["buffers"] + [{"byteLength": 8, "uri": "data:application/octet-stream;base64," + base64.b64encode(struct.pack("<II", 0, 7)).decode()}]
     expect(bad_idx, -6)                                                                                                # index out of range
+    # a hierarchy that is a DAG (every node lists the next one twice) would expand to 2^24 mesh instances: cut off, not expanded
+    bomb = dict(base, scenes=[{"nodes": [0]}], nodes=[{"children": [i + 1, i + 1]} for i in range(24)] + [{"mesh": 0}])
+    expect(bomb, -8)
     p.write_text("{ not json")
     with pytest.raises(V.VkhrtError):
         V.load_lines(str(p))

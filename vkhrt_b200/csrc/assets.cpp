@@ -16,6 +16,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <exception>
 #include <string>
 #include <vector>
 
@@ -361,11 +362,16 @@ int vkhrt_asset_load_lines(const char* path, VkhrtLineAsset* out)
     if (!read_file(path, data)) return fail(VKHRT_ERR_IO, std::string("cannot read ") + path);
     std::string p(path);
     int rc;
-    if (ends_with(p, ".obj")) rc = load_obj(data, out);
-    else if (ends_with(p, ".hair")) rc = load_hair(data, out);
-    else if (ends_with(p, ".gltf")) rc = vkhrt::load_gltf(p, data, false, out);
-    else if (ends_with(p, ".glb")) rc = vkhrt::load_gltf(p, data, true, out);
-    else return fail(VKHRT_ERR_UNSUPPORTED, "unknown line-asset extension (supported: .obj, .hair, .gltf, .glb)");
+    try {
+        if (ends_with(p, ".obj")) rc = load_obj(data, out);
+        else if (ends_with(p, ".hair")) rc = load_hair(data, out);
+        else if (ends_with(p, ".gltf")) rc = vkhrt::load_gltf(p, data, false, out);
+        else if (ends_with(p, ".glb")) rc = vkhrt::load_gltf(p, data, true, out);
+        else return fail(VKHRT_ERR_UNSUPPORTED, "unknown line-asset extension (supported: .obj, .hair, .gltf, .glb)");
+    } catch (const std::exception& e) {          // nothing may unwind across the C boundary (a hostile file can ask for any amount of memory)
+        vkhrt_asset_free(out);
+        return fail(VKHRT_ERR_OUT_OF_MEMORY, std::string("asset too large for host memory: ") + e.what());
+    }
     if (rc == VKHRT_OK && (!out->positions_xyz || !out->line_indices)) { vkhrt_asset_free(out); return fail(VKHRT_ERR_OUT_OF_MEMORY, "out of host memory"); }
     return rc;
 }
