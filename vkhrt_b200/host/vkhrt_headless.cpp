@@ -21,7 +21,7 @@ static void usage()
 {
     std::puts("usage: vkhrt_headless --model <file.gltf | file.glb | file.obj | file.hair | synthetic:<straight|curly>:<strands>:<segments>[:seed]>\n"
               "                      [--technique phantom|lss|dots] [--size WxH] [--spp N] [--debug-primid]\n"
-              "                      [--frames N] [--ppm out.ppm] [--png out.png] [--hits out.bin] [--device D]\n"
+              "                      [--frames N] [--ppm out.ppm] [--png out.png] [--hits out.bin] [--device D] [--gpus N]\n"
               "                      [--env procedural|file.hdr] [--ao N] [--lod split,merge,curve_merge]");
 }
 
@@ -30,7 +30,7 @@ int main(int argc, char** argv)
     std::string model = "synthetic:curly:10000:16", ppm, png, hits_path, technique = "lss";
     unsigned lod[3] = {0, 0, 0};
     RendererInitInfo info;
-    int frames = 1, device = 0;
+    int frames = 1, device = 0, gpus = 1;
     for (int i = 1; i < argc; ++i) {
         const std::string a = argv[i];
         auto next = [&]() -> const char* { if (i + 1 >= argc) { usage(); std::exit(2); } return argv[++i]; };
@@ -48,6 +48,7 @@ int main(int argc, char** argv)
         else if (a == "--lod") { if (std::sscanf(next(), "%u,%u,%u", &lod[0], &lod[1], &lod[2]) != 3) { usage(); return 2; } }
         else if (a == "--hits") hits_path = next();
         else if (a == "--device") device = std::atoi(next());
+        else if (a == "--gpus") gpus = std::atoi(next());            // devices device .. device+N-1 share every frame (one process, vkhrt_render_multi)
         else { std::fprintf(stderr, "unknown argument %s\n", a.c_str()); usage(); return 2; }
     }
     const VkhrtTechnique tech = technique == "phantom" ? VKHRT_TECHNIQUE_PHANTOM : (technique == "dots" ? VKHRT_TECHNIQUE_DOTS : VKHRT_TECHNIQUE_LSS);
@@ -66,6 +67,11 @@ int main(int argc, char** argv)
         auto camera = std::make_shared<FlyCamera>(cc);
         Renderer renderer(info, camera);
         renderer.AddModel(m);
+        for (int g = 1; g < gpus; ++g) {
+            std::shared_ptr<Model> r = ModelLoader(device + g).LoadFromFile(model, tech, lod[0], lod[1], lod[2]);
+            if (!r) return 1;
+            renderer.AddReplica(r);
+        }
         for (int f = 0; f < frames; ++f) {
             auto f0 = std::chrono::steady_clock::now();
             renderer.Render();

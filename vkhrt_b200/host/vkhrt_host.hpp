@@ -212,6 +212,13 @@ public:
         _models.push_back(model);
     }
     [[nodiscard]] const std::vector<std::shared_ptr<Model>>& GetModels() const { return _models; }
+    // The same groom built on another GPU (ModelLoader(device).LoadFromFile of the same asset; the build is deterministic, so the
+    // replicas are identical).  With replicas, Render() shards the frame over all of them from this one process (vkhrt_render_multi).
+    void AddReplica(const std::shared_ptr<Model>& model)
+    {
+        if (!_env.empty()) Check(vkhrt_scene_set_environment(model->Handle(), _env.data(), _envW, _envH), "vkhrt_scene_set_environment");
+        _replicas.push_back(model);
+    }
 
     // One frame: UpdateCameraResource + traceRaysKHR(width, height, 1) + read-back, blocking.
     // (The reference TLAS holds several BLAS; this path renders one groom per Renderer, the first model.)
@@ -228,7 +235,14 @@ public:
         const size_t n = (size_t)_info.width * _info.height;
         if (_info.wantHits) _hits.resize(n);
         if (_info.wantImage) _image.resize(n * 4);
-        Check(vkhrt_render(_models[0]->Handle(), &f, _info.wantHits ? _hits.data() : nullptr, _info.wantImage ? _image.data() : nullptr), "vkhrt_render");
+        if (_replicas.empty()) {
+            Check(vkhrt_render(_models[0]->Handle(), &f, _info.wantHits ? _hits.data() : nullptr, _info.wantImage ? _image.data() : nullptr), "vkhrt_render");
+        } else {
+            std::vector<VkhrtScene*> handles { _models[0]->Handle() };
+            for (const auto& r : _replicas) handles.push_back(r->Handle());
+            Check(vkhrt_render_multi(handles.data(), (uint32_t)handles.size(), &f, _info.wantHits ? _hits.data() : nullptr, _info.wantImage ? _image.data() : nullptr),
+                  "vkhrt_render_multi");
+        }
     }
     [[nodiscard]] const std::vector<VkhrtHit>& GetHits() const { return _hits; }
     [[nodiscard]] const std::vector<uint8_t>& GetImage() const { return _image; }     // RGBA8, row-major, row 0 = top
@@ -254,6 +268,7 @@ private:
     uint32_t _envW = 0, _envH = 0;
     std::shared_ptr<FlyCamera> _flyCamera;
     std::vector<std::shared_ptr<Model>> _models;
+    std::vector<std::shared_ptr<Model>> _replicas;
     std::vector<VkhrtHit> _hits;
     std::vector<uint8_t> _image;
 };
