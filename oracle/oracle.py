@@ -98,6 +98,10 @@ def lib():
         L.orc_curve_axis.argtypes = [fp, C.c_float, fp]
         L.orc_shade.argtypes = [fp, C.c_uint32, C.c_int, fp]
         L.orc_max_threads.restype = C.c_int
+        L.orc_groom_generate.restype = C.c_int
+        L.orc_groom_generate.argtypes = [C.c_uint32, C.c_uint32, C.c_int, C.c_uint64, C.c_void_p, C.c_void_p]
+        L.orc_camera_matrices.restype = None
+        L.orc_camera_matrices.argtypes = [fp, C.c_float, C.c_float, C.c_float, C.c_float, C.c_float, C.c_float, fp, fp]
         _lib = L
     return _lib
 
@@ -105,6 +109,30 @@ def lib():
 def _f(a):
     a = np.ascontiguousarray(a, dtype=np.float32)
     return a, a.ctypes.data_as(C.POINTER(C.c_float))
+
+
+GROOM_STRAIGHT, GROOM_CURLY = 0, 1
+DEFAULT_SEED = 0x5EED0001
+
+
+def generate_groom(n_strands, segments, style=GROOM_CURLY, seed=DEFAULT_SEED):
+    """The checker's own seeded groom; bit-identical to the product's vkhrt_groom_generate
+    (tests/test_oracle_pins.py::test_oracle_inputs_equal_the_products)."""
+    pos = np.empty((n_strands * (segments + 1), 3), np.float32)
+    idx = np.empty((n_strands * segments, 2), np.uint32)
+    rc = lib().orc_groom_generate(n_strands, segments, style, seed, pos.ctypes.data, idx.ctypes.data)
+    if rc != 0:
+        raise ValueError("orc_groom_generate: bad arguments")
+    return pos, idx
+
+
+def camera_matrices(position=(0.0, 150.0, 20.0), yaw=-90.0, pitch=0.0, fov=60.0, aspect=16.0 / 9.0, near=0.1, far=1000.0):
+    """(view_inverse, proj_inverse) float32[16] column-major; defaults = reference application.cpp:65-73."""
+    pos = (C.c_float * 3)(*[float(x) for x in position])
+    vi = (C.c_float * 16)()
+    pi = (C.c_float * 16)()
+    lib().orc_camera_matrices(pos, yaw, pitch, fov, aspect, near, far, vi, pi)
+    return np.array(list(vi), np.float32), np.array(list(pi), np.float32)
 
 
 def max_threads():

@@ -13,6 +13,21 @@ def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box)")
 
 
+def pytest_collection_modifyitems(config, items):
+    """`gpu` tests skip (not fail) on a machine without a CUDA device, so a plain `pytest` run is green there."""
+    try:
+        import vkhrt_b200
+        n_dev = vkhrt_b200.device_count()
+    except Exception:
+        n_dev = 0
+    if n_dev > 0:
+        return
+    skip = pytest.mark.skip(reason="no CUDA device (vkhrt_b200 has no CPU path)")
+    for item in items:
+        if "gpu" in item.keywords:
+            item.add_marker(skip)
+
+
 @pytest.fixture(scope="session", autouse=True)
 def _built():
     """Build the product library and the oracle if they are missing (the GPU box gets them prebuilt)."""

@@ -484,3 +484,36 @@ def test_ao_image_is_the_base_image_times_visibility(O, V):
     # ao_distance -> 0: nothing is occluded
     _, i2, _ = sc.render(O.make_frame(vi, pi, W, H, miss_rgb=(0.1, 0.2, 0.3), ao_samples=4, ao_distance=1e-3))
     assert np.array_equal(i2, i0)
+
+
+def test_oracle_inputs_equal_the_products(V, O):
+    """The checker generates its own grooms and cameras (so bench.py --impl reference never loads the product library);
+    they must be the product's, bit for bit (one seeded generator shared by oracle and GPU)."""
+    for style in (V.GROOM_STRAIGHT, V.GROOM_CURLY):
+        for n, segs in ((1, 1), (7, 3), (1000, 16), (5000, 32)):
+            a, b = V.generate_groom(n, segs, style), O.generate_groom(n, segs, style)
+            assert a[0].tobytes() == b[0].tobytes() and a[1].tobytes() == b[1].tobytes()
+        a, b = V.generate_groom(100, 8, style, seed=12345), O.generate_groom(100, 8, style, seed=12345)
+        assert a[0].tobytes() == b[0].tobytes()
+    for kw in (dict(), dict(aspect=1.0), dict(aspect=float(np.float32(3840) / np.float32(2160))),
+               dict(position=(1.0, 140.0, 30.0), yaw=-80.0, pitch=10.0, fov=45.0, aspect=1.5, near=0.5, far=500.0)):
+        a, b = V.camera_matrices(**kw), O.camera_matrices(**kw)
+        assert a[0].tobytes() == b[0].tobytes() and a[1].tobytes() == b[1].tobytes(), kw
+
+
+def test_oracle_build_is_thread_count_independent(O):
+    """The oracle's LBVH build is OpenMP-parallel for the at-size scenes; nodes must not depend on the thread count."""
+    import subprocess, sys, os, hashlib
+    code = ("import sys, hashlib; sys.path.insert(0, %r)\n"
+            "from oracle import oracle as O\n"
+            "pos, idx = O.generate_groom(3000, 16, 1)\n"
+            "h = hashlib.sha256()\n"
+            "for t in (0, 1, 2):\n"
+            "    n, i, m, l = O.OracleScene(pos, idx, technique=t).bvh()\n"
+            "    h.update(n.tobytes()); h.update(i.tobytes()); h.update(m.tobytes()); h.update(l.tobytes())\n"
+            "print(h.hexdigest())\n") % os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    outs = set()
+    for nt in ("1", "3", "8"):
+        env = dict(os.environ, OMP_NUM_THREADS=nt)
+        outs.add(subprocess.check_output([sys.executable, "-c", code], env=env).decode().strip())
+    assert len(outs) == 1, outs
