@@ -480,7 +480,7 @@ __global__ void __launch_bounds__(256) materialise_refit_kernel(MeshIn m, uint32
         float rmax = bezier_bound_radius(c, m.radius);
         primA[2 * (size_t)pos] = make_float4(c.p0.x, c.p0.y, c.p0.z, rmax);
         primA[2 * (size_t)pos + 1] = make_float4(c.p3.x, c.p3.y, c.p3.z, __uint_as_float(prim));
-        primB[2 * (size_t)pos] = make_float4(c.p1.x, c.p1.y, c.p1.z, bezier_quarter_chord_deviation(c));
+        primB[2 * (size_t)pos] = make_float4(c.p1.x, c.p1.y, c.p1.z, bezier_quarter_chord_deviation(c) + bezier_convergence_slack(c, m.radius));
         primB[2 * (size_t)pos + 1] = make_float4(c.p2.x, c.p2.y, c.p2.z, 0.0f);
     } else if (TECH == VKHRT_TECHNIQUE_LSS) {
         LssPrim s = gen_lss(m, prim);

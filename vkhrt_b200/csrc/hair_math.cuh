@@ -119,6 +119,16 @@ VK_DEV float bezier_chord_deviation(const Bezier& c)      // max distance of the
 {
     return fmaxf(point_segment_distance(c.p1, c.p0, c.p3), point_segment_distance(c.p2, c.p0, c.p3));
 }
+// An accepted Prhi hit h lies sqrt(r^2 + (dt |B'(t)|)^2) from B(t) with |dt| < 5e-5 (hair_intersection.rint:67), i.e. up to
+// (5e-5 max|B'|)^2 / (2 r) farther than r.  max|B'| <= 3 max|p[i+1] - p[i]| (hull of the derivative's control points).  For hair-like
+// segments (length L < ~900 r) the 0.1 % inflation of the filter's bound covers it; this term makes thin or long segments safe too.
+VK_DEV float bezier_convergence_slack(const Bezier& c, float radius)
+{
+    float3 d0 = c.p1 - c.p0, d1 = c.p2 - c.p1, d2 = c.p3 - c.p2;
+    float l2 = fmaxf(fmaxf(fdot3(d0, d0), fdot3(d1, d1)), fdot3(d2, d2));         // max |p[i+1] - p[i]|^2
+    float x2 = (9.0f * l2) * (5e-5f * 5e-5f);                                      // (5e-5 max|B'|)^2
+    return (x2 / (2.0f * radius)) * 1.01f;
+}
 // max deviation of the four quarter-curves from their chords [B(k/4), B((k+1)/4)], inflated
 VK_DEV float bezier_quarter_chord_deviation(const Bezier& c)
 {

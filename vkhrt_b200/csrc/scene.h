@@ -48,7 +48,8 @@ struct DeviceScene {
     float4* d_primB = nullptr;
 
     // per-frame scratch (grown on demand)
-    unsigned long long* d_counters = nullptr;   // [0] work counter, [1..5] stats
+    unsigned long long* d_counters = nullptr;   // [0], [6] alternating work counters (a launch zeroes the other one), [1..5] stats, [8..15] scheduler
+    bool work_flip = false;
     VkhrtHit* d_hits_scratch = nullptr; size_t hits_scratch_n = 0;
     float4* d_accum = nullptr; size_t accum_n = 0;
     uint32_t* d_occluded = nullptr; size_t occluded_n = 0;

@@ -51,7 +51,11 @@ struct TraceParams {
     uint32_t* line_cnt;             // records written per line, zeroed per frame (null = off)
     VkhrtHit* host_lines;           // mapped pinned host buffer, same indexing as `hits`
     uint32_t n_out, line_shift;     // a line = 1 << line_shift records (2: 128 bytes)
-    unsigned long long* counters;   // [0] next slot, [1] nodes, [2] prims, [3] hits, [4] iterations, [5] rays, [8..11] steps, [12..15] lanes
+    unsigned long long* counters;   // [1] nodes, [2] prims, [3] hits, [4] iterations, [5] rays, [8..11] steps, [12..15] lanes
+    // work counters [0] and [6] alternate between launches: a launch pulls slots from `work` and zeroes `work_next` for the launch
+    // after it (stream-ordered), so no memset sits between the samples of a frame
+    unsigned long long* work;
+    unsigned long long* work_next;
     uint32_t refill_threshold;      // lanes waiting for a new ray that trigger a refill step
     uint32_t w_node, w_leaf, w_march;   // scheduler weights (fixed point, 16 = 1.0)
     // trace_pool_kernel
@@ -131,6 +135,7 @@ __global__ void __launch_bounds__(TR_BLOCK, MINB) trace_kernel(const TraceParams
 {
     constexpr bool WAVEFRONT = SRC == SRC_BUFFER;
     __shared__ uint2 s_stack[TR_STACK][TR_BLOCK];
+    if (blockIdx.x == 0 && threadIdx.x == 0) *p.work_next = 0ull;
     uint2 spill[TR_SPILL];
     const unsigned FULL = 0xffffffffu;
     const int tid = threadIdx.x, lane = tid & 31;
@@ -314,7 +319,7 @@ __global__ void __launch_bounds__(TR_BLOCK, MINB) trace_kernel(const TraceParams
             // warp-aggregated fetch of the next slots
             const unsigned idle = __ballot_sync(FULL, want);
             unsigned long long base = 0;
-            if (lane == 0) base = atomicAdd(p.counters, (unsigned long long)__popc(idle));
+            if (lane == 0) base = atomicAdd(p.work, (unsigned long long)__popc(idle));
             base = __shfl_sync(FULL, base, 0);
             if (want) {
                 const unsigned long long slot64 = p.slot_begin + base + (unsigned)__popc(idle & ((1u << lane) - 1u));
@@ -432,6 +437,7 @@ template <bool STATS, int PL_S, int PL_STK>
 __global__ void __launch_bounds__(TR_BLOCK, PL_MINB) trace_pool_kernel(const TraceParams p)
 {
     __shared__ PoolWarp<PL_S, PL_STK> sh_all[TR_BLOCK / 32];
+    if (blockIdx.x == 0 && threadIdx.x == 0) *p.work_next = 0ull;
     const unsigned FULL = 0xffffffffu;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const unsigned lt = (1u << lane) - 1u;
@@ -715,7 +721,7 @@ __global__ void __launch_bounds__(TR_BLOCK, PL_MINB) trace_pool_kernel(const Tra
             const bool want = (act_d || act_f) && !exhausted;
             const unsigned wm = __ballot_sync(FULL, want);
             unsigned long long base = 0;
-            if (lane == 0 && wm) base = atomicAdd(p.counters, (unsigned long long)__popc(wm));
+            if (lane == 0 && wm) base = atomicAdd(p.work, (unsigned long long)__popc(wm));
             base = __shfl_sync(FULL, base, 0);
             bool fresh = false, padded = false;
             uint32_t pad_idx = 0u;
@@ -729,6 +735,380 @@ __global__ void __launch_bounds__(TR_BLOCK, PL_MINB) trace_pool_kernel(const Tra
                         sh.dir[0][s] = d.x; sh.dir[1][s] = d.y; sh.dir[2][s] = d.z;
                         sh.dir[3][s] = safe_rcp(d.x); sh.dir[4][s] = safe_rcp(d.y); sh.dir[5][s] = safe_rcp(d.z);
                         sh.tcur[s] = p.tmax; sh.cur[s] = 0u; sh.sp[s] = 0; sh.spilled[s] = 0;
+                        sh.best_pos[s] = PRIM_NONE; sh.best_u[s] = 0.0f; sh.out_idx[s] = q.out;
+                        if (VKHRT_MAILBOX_PHANTOM) sh.last_group[s] = PRIM_NONE;
+                        fresh = true;
+                        if (STATS) st_rays++;
+                    } else if (p.compact) { padded = true; pad_idx = q.out; }
+                }
+            }
+            if (p.compact) emit(padded, pad_idx, __int_as_float(0x7f800000), VKHRT_MISS_SEGMENT, 0.0f, f3(0, 0, 0), PRIM_NONE, FLAG_PADDING);
+            if (wm && p.slot_begin + base + (unsigned)__popc(wm) >= (unsigned long long)p.n_slots) exhausted = true;
+            __syncwarp();
+            enqueue(Q_READY, nR, fresh, s);
+            enqueue(Q_FREE, nF, (act_d || act_f) && !fresh, s);
+            __syncwarp();
+        }
+    }
+
+    if (STATS) {
+#pragma unroll
+        for (int k = 16; k > 0; k >>= 1) {
+            st_nodes += __shfl_xor_sync(FULL, st_nodes, k); st_prims += __shfl_xor_sync(FULL, st_prims, k);
+            st_iters += __shfl_xor_sync(FULL, st_iters, k); st_hits += __shfl_xor_sync(FULL, st_hits, k);
+            st_rays += __shfl_xor_sync(FULL, st_rays, k);
+        }
+        if (lane == 0) {
+            atomicAdd(p.counters + 1, (unsigned long long)st_nodes); atomicAdd(p.counters + 2, (unsigned long long)st_prims);
+            atomicAdd(p.counters + 3, (unsigned long long)st_hits); atomicAdd(p.counters + 4, (unsigned long long)st_iters);
+            atomicAdd(p.counters + 5, (unsigned long long)st_rays);
+            for (int k = 0; k < 4; ++k) { atomicAdd(p.counters + 8 + k, (unsigned long long)sc_steps[k]); atomicAdd(p.counters + 12 + k, (unsigned long long)sc_lanes[k]); }
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// trace_pool2_kernel: the ray pool with a leaner node step (round 2).  Same queues, same scheduler, same per-ray sequence of
+// node visits and candidate tests as trace_pool_kernel (records AND counters identical); what changed is where the
+// instructions go (ncu source page of round 1: stack push / pop / spill 15.8 % of the warp instructions at 5-7 lanes, loop
+// control and state bookkeeping 8 %):
+//   * a lane's state lives in `cur` alone: internal node index | leaf ref (bit 31) | POP | DONE | IDLE;
+//   * WRITE-THROUGH stack: every push stores the entry both in the slot's shared-memory ring (the top PL_STK entries) and at
+//     its depth in the warp's global spill area ([depth][slot]: lanes of a warp at similar depths share lines, .cg = L2
+//     only).  A push therefore never branches on "ring full"; a pop reads the ring when the entry is still there
+//     (index >= lo) and the spill area otherwise.  `lo` = lowest index whose ring copy is intact;
+//   * a ray whose leaf test / candidate set-up / march is over pops its next stack entry RIGHT THERE, in the batch that
+//     finished it (all lanes of the batch do the same thing), and goes straight back to the LEAF queue when that entry is a
+//     leaf — consecutive leaves of a ray (pieces of neighbouring curves) no longer pass through a node lane in between.
+// ------------------------------------------------------------------------------------------------
+constexpr uint32_t R2_POP = 0x7FFFFFFDu, R2_DONE = 0x7FFFFFFEu, R2_IDLE = 0x7FFFFFFFu;   // cur < R2_POP: internal node
+
+template <int PL_S, int PL_STK>
+struct PoolWarp2 {
+    uint2 stack[PL_STK][PL_S];         // ring: entry k of the stack sits at [k % PL_STK] while index k >= lo
+    float dir[6][PL_S];                // d.xyz, 1/d
+    float tcur[PL_S];
+    uint32_t cur[PL_S], best_pos[PL_S];
+    uint32_t last_group[VKHRT_MAILBOX_PHANTOM ? PL_S : 1];
+    float best_u[PL_S];
+    uint32_t out_idx[PL_S];
+    uint8_t sp[PL_S], lo[PL_S];
+    uint8_t q[5][PL_S];
+    uint2* ovf;                        // this warp's spill area [depth][slot] (kept here: recomputing it from the CTA / warp id in
+                                       // every push costs more than one LDS)
+};
+
+template <bool STATS, int PL_S, int PL_STK>
+__global__ void __launch_bounds__(TR_BLOCK, PL_MINB) trace_pool2_kernel(const TraceParams p)
+{
+    __shared__ PoolWarp2<PL_S, PL_STK> sh_all[TR_BLOCK / 32];
+    if (blockIdx.x == 0 && threadIdx.x == 0) *p.work_next = 0ull;
+    const unsigned FULL = 0xffffffffu;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const unsigned lt = (1u << lane) - 1u;
+    PoolWarp2<PL_S, PL_STK>& sh = sh_all[warp];
+    // spill area of this warp: [depth][slot]
+    if (lane == 0) sh.ovf = p.pool_overflow + (size_t)(blockIdx.x * (TR_BLOCK / 32) + (uint32_t)warp) * (size_t)(PL_S * PL_OVF);
+    const float3 o = f3(p.cam.vi[12], p.cam.vi[13], p.cam.vi[14]);     // ray_gen.rgen:22: every primary ray starts at the camera
+
+    // the ray this lane traverses (cur == R2_IDLE: none)
+    uint32_t slot = 0, cur = R2_IDLE;
+    uint32_t sp = 0, lo = 0;
+    float3 id = f3(0, 0, 0), noid = f3(0, 0, 0);
+    float tcur = 0.0f;
+    // the candidate this lane marches (a different ray)
+    bool mhave = false;
+    MarchState ms;
+    ms.c.p0 = ms.c.p1 = ms.c.p2 = ms.c.p3 = f3(0, 0, 0);
+    ms.t = ms.told = ms.dt1 = ms.dt2 = ms.t_start = 0.0f; ms.it = 0u;
+    uint32_t m_slot = 0;
+    uint32_t nR = 0, nL = 0, nC = 0, nD = 0, nF = PL_S;      // queue fills (warp-uniform)
+    bool exhausted = false;
+    uint32_t st_nodes = 0, st_prims = 0, st_iters = 0, st_hits = 0, st_rays = 0;
+    uint32_t sc_steps[4] = {0, 0, 0, 0}, sc_lanes[4] = {0, 0, 0, 0};
+
+    for (int k = lane; k < PL_S; k += 32) sh.q[Q_FREE][k] = (uint8_t)k;
+    __syncwarp();
+
+    auto enqueue = [&](int qi, uint32_t& n, bool pred, uint32_t s) {
+        const unsigned m = __ballot_sync(FULL, pred);
+        if (pred) sh.q[qi][n + __popc(m & lt)] = (uint8_t)s;
+        n += __popc(m);
+    };
+    auto dequeue = [&](int qi, uint32_t n, uint32_t k) -> uint32_t { return sh.q[qi][n - 1u - k]; };   // LIFO (see trace_pool_kernel)
+    // hit-record delivery: see trace_pool_kernel::emit
+    auto emit = [&](bool wrote, uint32_t oi, float t, uint32_t seg, float u, float3 n, uint32_t prim, uint32_t flags) {
+        if (!p.line_cnt) { if (wrote) store_hit<false>(p, oi, t, seg, u, n, prim, flags); return; }      // warp-uniform
+        bool completes = false;
+        uint32_t line = 0;
+        if (wrote) {
+            store_hit<false>(p, oi, t, seg, u, n, prim, flags);
+            __threadfence();
+            line = oi >> p.line_shift;
+            uint32_t old;
+            asm volatile("atom.acq_rel.gpu.global.add.u32 %0, [%1], 1;" : "=r"(old) : "l"(p.line_cnt + line) : "memory");
+            completes = old + 1u == min(1u << p.line_shift, p.n_out - (line << p.line_shift));
+        }
+        unsigned m = __ballot_sync(FULL, completes);
+        while (m) {
+            const uint32_t src = __fns(m, 0, (lane >> p.line_shift) + 1);
+            const uint32_t ln = __shfl_sync(FULL, line, src & 31u);
+            const uint32_t rec = (ln << p.line_shift) + ((uint32_t)lane & ((1u << p.line_shift) - 1u));
+            if (src != 0xFFFFFFFFu && rec < p.n_out) {
+                uint32_t c;
+                asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(c) : "l"(p.line_cnt + ln) : "memory");
+                const float4* sp4 = reinterpret_cast<const float4*>(p.hits + rec);
+                const float4 x = __ldcg(sp4), y = __ldcg(sp4 + 1);
+                store_record(p.host_lines + rec, true, x, y);
+            }
+            for (uint32_t j = 0; j < (32u >> p.line_shift) && m; ++j) m &= m - 1u;
+        }
+    };
+    // ---- stack of the ray a lane traverses (registers sp, lo) ----
+    auto push = [&](uint2 e) {
+        sh.stack[sp % PL_STK][slot] = e;
+        __stcg(reinterpret_cast<unsigned long long*>(sh.ovf + (sp * PL_S + slot)), ((unsigned long long)e.y << 32) | e.x);
+        lo = max(lo + (PL_STK - 1), sp) - (PL_STK - 1);         // the ring slot written held entry sp - PL_STK
+        ++sp;
+    };
+    // one entry; entries whose box entry distance lies beyond the current closest hit are dropped (cur stays R2_POP: the cull
+    // loop runs across steps, in parallel over lanes)
+    auto pop = [&]() {
+        if (sp == 0) { cur = R2_DONE; return; }
+        --sp;
+        uint2 e;
+        if (sp >= lo) e = sh.stack[sp % PL_STK][slot];
+        else { const unsigned long long v = __ldcg(reinterpret_cast<const unsigned long long*>(sh.ovf + (sp * PL_S + slot))); e = make_uint2((uint32_t)v, (uint32_t)(v >> 32)); lo = sp; }
+        if (__uint_as_float(e.y) <= tcur) cur = e.x;
+    };
+    // the same pop on a PARKED ray (slot state in shared memory), for the batches that finish a leaf / candidate / march:
+    // returns the ray's new `cur` (internal node | leaf | R2_POP when the entry was culled | R2_DONE)
+    auto pop_parked = [&](uint32_t s) -> uint32_t {
+        uint32_t k = sh.sp[s];
+        if (k == 0u) return R2_DONE;
+        --k;
+        const uint32_t l = sh.lo[s];
+        uint2 e;
+        if (k >= l) e = sh.stack[k % PL_STK][s];
+        else { const unsigned long long v = __ldcg(reinterpret_cast<const unsigned long long*>(sh.ovf + (k * PL_S + s))); e = make_uint2((uint32_t)v, (uint32_t)(v >> 32)); sh.lo[s] = (uint8_t)k; }
+        sh.sp[s] = (uint8_t)k;
+        return __uint_as_float(e.y) <= sh.tcur[s] ? e.x : R2_POP;
+    };
+    // a parked ray goes where its `cur` says: leaf -> LEAF, DONE -> DONE, node / POP -> READY
+    auto route = [&](bool pred, uint32_t s, uint32_t c) {
+        if (pred) sh.cur[s] = c;
+        enqueue(Q_LEAF, nL, pred && (int)c < 0, s);
+        enqueue(Q_DONE, nD, pred && c == R2_DONE, s);
+        enqueue(Q_READY, nR, pred && (int)c >= 0 && c != R2_DONE, s);
+    };
+
+    uint32_t nHave = 0, nM = 0;               // lanes holding a ray / a march (warp-uniform)
+    auto top_up = [&]() {
+        if (nR == 0u || nHave == 32u) return;
+        const unsigned idle = __ballot_sync(FULL, cur == R2_IDLE);
+        const uint32_t rank = __popc(idle & lt);
+        if (cur == R2_IDLE && rank < nR) {
+            slot = dequeue(Q_READY, nR, rank);
+            id = f3(sh.dir[3][slot], sh.dir[4][slot], sh.dir[5][slot]);
+            noid = f3(-(o.x * id.x), -(o.y * id.y), -(o.z * id.z));
+            tcur = sh.tcur[slot]; cur = sh.cur[slot]; sp = sh.sp[slot]; lo = sh.lo[slot];
+        }
+        const uint32_t taken = min(nR, 32u - nHave);
+        nR -= taken; nHave += taken;
+        __syncwarp();
+    };
+
+    for (;;) {
+        top_up();
+        const uint32_t nRet = exhausted ? nD : nD + nF;
+        if ((nHave | nM | nR | nL | nC | nRet) == 0u) break;
+
+        // ---------------- scheduler (as trace_pool_kernel) ----------------
+        enum : int { PH_NODE, PH_LEAF, PH_SETUP, PH_MARCH, PH_RETIRE };
+        int phase;
+        if (!exhausted && nF >= 32u) phase = PH_RETIRE;
+        else if (nHave >= p.pool_node_lanes) phase = PH_NODE;
+        else {
+            const uint32_t sS = min(nC, 32u - nM);
+            const uint32_t sR = min(nRet, 32u);
+            uint32_t best = nL; int bp = PH_LEAF;
+            if (sS > best) { best = sS; bp = PH_SETUP; }
+            if (nM > best || (nM == 32u)) { best = nM; bp = PH_MARCH; }
+            if (sR > best) { best = sR; bp = PH_RETIRE; }
+            if (best >= p.pool_batch_lanes) phase = bp;
+            else if (nHave >= p.pool_node_min) phase = PH_NODE;
+            else if (best > 0u) phase = bp;
+            else phase = PH_NODE;
+        }
+
+        if (phase == PH_NODE) {
+            // ---------------- internal nodes ----------------
+            do {
+                const uint32_t thr = max(1u, (nHave * p.pool_exit_eighths + 7u) >> 3);     // leave the loop below this many node lanes
+                uint32_t n1;
+                do {
+                    if (STATS) { sc_steps[0]++; sc_lanes[0] += __popc(__ballot_sync(FULL, cur <= R2_POP)); }
+                    bool both = false;
+                    uint2 far = make_uint2(0u, 0u);
+                    if (cur < R2_POP) {
+                        const float4* nd = p.nodes + 4 * (size_t)cur;
+                        const float4 q0 = __ldg(nd), q1 = __ldg(nd + 1), q2 = __ldg(nd + 2), q3 = __ldg(nd + 3);
+                        if (STATS) st_nodes++;
+                        float tn0, tn1;
+                        const bool h0 = slab_test(xyz(q0), xyz(q1), id, noid, p.tmin, tcur, &tn0);
+                        const bool h1 = slab_test(xyz(q2), xyz(q3), id, noid, p.tmin, tcur, &tn1);
+                        const uint32_t c0 = __float_as_uint(q0.w), c1 = __float_as_uint(q1.w);
+                        both = h0 && h1;
+                        const bool second = both ? (tn1 < tn0) : h1;
+                        far = make_uint2(second ? c0 : c1, __float_as_uint(second ? tn0 : tn1));
+                        cur = (h0 || h1) ? (second ? c1 : c0) : R2_POP;
+                    }
+                    if (both) push(far);
+                    else if (cur == R2_POP) pop();
+                    n1 = __popc(__ballot_sync(FULL, cur <= R2_POP));
+                } while (n1 >= thr);
+                // rays that left the node state go to their queues; the lane is free again
+                const bool to_leaf = (int)cur < 0, to_done = cur == R2_DONE;
+                if (to_leaf) { sh.cur[slot] = cur; sh.sp[slot] = (uint8_t)sp; sh.lo[slot] = (uint8_t)lo; }
+                enqueue(Q_LEAF, nL, to_leaf, slot);
+                enqueue(Q_DONE, nD, to_done, slot);
+                if (to_leaf || to_done) cur = R2_IDLE;
+                nHave = n1;
+                __syncwarp();
+                top_up();
+            } while (nHave >= p.pool_node_lanes);
+        } else if (phase == PH_LEAF) {
+            // ---------------- leaves: Prhi early-out (hair_intersection.rint:20-33, rmax precomputed) ----------------
+            const uint32_t n = min(nL, 32u);
+            const bool act = (uint32_t)lane < n;
+            if (STATS) { sc_steps[1]++; sc_lanes[1] += n; }
+            uint32_t s = 0, next = 0;
+            bool pass = false;
+            if (act) {
+                s = dequeue(Q_LEAF, nL, (uint32_t)lane);
+                const float3 d = f3(sh.dir[0][s], sh.dir[1][s], sh.dir[2][s]);
+                const uint32_t pos = sh.cur[s] & 0x7FFFFFFFu;
+                const float4 a0 = __ldg(p.primA + 2 * (size_t)pos), a1 = __ldg(p.primA + 2 * (size_t)pos + 1);
+                // mailbox: another piece of the curve tested last gives the same answer; skipped and not counted
+                const bool again = VKHRT_MAILBOX_PHANTOM && __float_as_uint(a1.w) == sh.last_group[s];
+                if (VKHRT_MAILBOX_PHANTOM) sh.last_group[s] = __float_as_uint(a1.w);
+                if (STATS && !again) st_prims++;
+                pass = !again && ray_hits_cylinder(o, d, xyz(a0), xyz(a1), a0.w);
+                if (!pass) next = pop_parked(s);
+            }
+            nL -= n;
+            __syncwarp();
+            enqueue(Q_CAND, nC, act && pass, s);
+            route(act && !pass, s, next);
+            __syncwarp();
+        } else if (phase == PH_SETUP) {
+            // ---------------- candidates: ray-centric transform + quarter-chord filter into free MARCH registers ----------------
+            const unsigned midle = __ballot_sync(FULL, !mhave);
+            const uint32_t rank = __popc(midle & lt);
+            const bool take = !mhave && rank < nC;
+            if (STATS) { sc_steps[1]++; sc_lanes[1] += __popc(__ballot_sync(FULL, take)); }
+            bool reject = false;
+            uint32_t next = 0;
+            if (take) {
+                m_slot = dequeue(Q_CAND, nC, rank);
+                const float3 d = f3(sh.dir[0][m_slot], sh.dir[1][m_slot], sh.dir[2][m_slot]);
+                const uint32_t pos = sh.cur[m_slot] & 0x7FFFFFFFu;
+                const float4 a0 = __ldg(p.primA + 2 * (size_t)pos), a1 = __ldg(p.primA + 2 * (size_t)pos + 1);
+                const float4 b0 = __ldg(p.primB + 2 * (size_t)pos), b1 = __ldg(p.primB + 2 * (size_t)pos + 1);
+                Bezier w;
+                w.p0 = xyz(a0); w.p1 = xyz(b0); w.p2 = xyz(b1); w.p3 = xyz(a1);
+                march_begin(ms, make_ray_frame(d), o, w);
+                if (quarter_chords_near_ray(ms.c, p.radius, b0.w)) mhave = true;
+                else { reject = true; next = pop_parked(m_slot); }
+            }
+            nC -= min(nC, (uint32_t)__popc(midle));
+            nM = __popc(__ballot_sync(FULL, mhave));
+            __syncwarp();
+            route(reject, m_slot, next);
+            __syncwarp();
+        } else if (phase == PH_MARCH) {
+            // ---------------- Phantom cone iterations (hair_intersection.rint:56-126) ----------------
+            uint32_t n0 = nM, n1;
+            do {
+                if (STATS) { sc_steps[2]++; sc_lanes[2] += __popc(__ballot_sync(FULL, mhave)); }
+                bool fin = false;
+                uint32_t next = 0;
+                if (mhave) {
+                    if (STATS) st_iters++;
+                    float t = 0.0f, u = 0.0f;
+                    const int r = march_step(ms, p.radius, &t, &u);
+                    if (r != MARCH_CONTINUE) {
+                        mhave = false; fin = true;
+                        const uint32_t pos = sh.cur[m_slot] & 0x7FFFFFFFu;       // the slot still points at the candidate's leaf
+                        // hair_intersection.rint:146-148 (report only tHit > 0), reportIntersectionEXT interval, tie rule of `commit`
+                        if (r == MARCH_HIT && t > 0.0f && t >= p.tmin) {
+                            const float tc = sh.tcur[m_slot];
+                            bool take_it = t < tc;
+                            if (t == tc) {
+                                const uint32_t bpos = sh.best_pos[m_slot];
+                                const uint32_t prim = __float_as_uint(__ldg(p.primA + 2 * (size_t)pos + 1).w);
+                                take_it = bpos == PRIM_NONE || prim < __float_as_uint(__ldg(p.primA + 2 * (size_t)bpos + 1).w);
+                            }
+                            if (take_it) { sh.tcur[m_slot] = t; sh.best_pos[m_slot] = pos; sh.best_u[m_slot] = u; }
+                        }
+                        next = pop_parked(m_slot);          // culls against the hit just committed
+                    }
+                }
+                route(fin, m_slot, next);
+                n1 = __popc(__ballot_sync(FULL, mhave));
+            } while (n1 * 4u >= n0 * 3u && n1 > 0u);
+            nM = n1;
+            __syncwarp();
+        } else {
+            // ---------------- retire finished rays, refill their slots (and free ones) with new primary rays ----------------
+            const uint32_t n_d = min(nD, 32u);
+            const uint32_t n_f = exhausted ? 0u : min(nF, 32u - n_d);
+            const bool act_d = (uint32_t)lane < n_d, act_f = !act_d && (uint32_t)lane - n_d < n_f;
+            if (STATS) { sc_steps[3]++; sc_lanes[3] += n_d + n_f; }
+            uint32_t s = 0;
+            if (act_d) s = dequeue(Q_DONE, nD, (uint32_t)lane);
+            else if (act_f) s = dequeue(Q_FREE, nF, (uint32_t)lane - n_d);
+            nD -= n_d; nF -= n_f;
+            {
+                float rt = __int_as_float(0x7f800000), ru = 0.0f;
+                float3 rn = f3(0, 0, 0);
+                uint32_t rprim = PRIM_NONE, rseg = VKHRT_MISS_SEGMENT, rflags = 0u, oi = 0u;
+                if (act_d) {
+                    const uint32_t pos = sh.best_pos[s];
+                    oi = sh.out_idx[s];
+                    if (pos != PRIM_NONE) {
+                        // hair_intersection.rint:74-76 from the committed (t, u)
+                        rt = sh.tcur[s]; ru = sh.best_u[s];
+                        const float3 d = f3(sh.dir[0][s], sh.dir[1][s], sh.dir[2][s]);
+                        const float4 a0 = __ldg(p.primA + 2 * (size_t)pos), a1 = __ldg(p.primA + 2 * (size_t)pos + 1);
+                        const float4 b0 = __ldg(p.primB + 2 * (size_t)pos), b1 = __ldg(p.primB + 2 * (size_t)pos + 1);
+                        Bezier w;
+                        w.p0 = xyz(a0); w.p1 = xyz(b0); w.p2 = xyz(b1); w.p3 = xyz(a1);
+                        rprim = rseg = __float_as_uint(a1.w);
+                        rn = fnormalize3(fmadd3(rt, d, o) - bezier_point(w, ru));
+                        rflags = FLAG_HIT;
+                        if (STATS) st_hits++;
+                    }
+                }
+                emit(act_d, oi, rt, rseg, ru, rn, rprim, rflags);
+            }
+            const bool want = (act_d || act_f) && !exhausted;
+            const unsigned wm = __ballot_sync(FULL, want);
+            unsigned long long base = 0;
+            if (lane == 0 && wm) base = atomicAdd(p.work, (unsigned long long)__popc(wm));
+            base = __shfl_sync(FULL, base, 0);
+            bool fresh = false, padded = false;
+            uint32_t pad_idx = 0u;
+            if (want) {
+                const unsigned long long slot64 = p.slot_begin + base + (unsigned)__popc(wm & lt);
+                if (slot64 < (unsigned long long)p.n_slots) {
+                    const PixelRef q = slot_to_pixel(p, (uint32_t)slot64);
+                    if (q.valid) {
+                        float3 ro, d;
+                        primary_ray(p.cam, p.W, p.H, q.px, q.py, p.sx, p.sy, &ro, &d);
+                        sh.dir[0][s] = d.x; sh.dir[1][s] = d.y; sh.dir[2][s] = d.z;
+                        sh.dir[3][s] = safe_rcp(d.x); sh.dir[4][s] = safe_rcp(d.y); sh.dir[5][s] = safe_rcp(d.z);
+                        sh.tcur[s] = p.tmax; sh.cur[s] = 0u; sh.sp[s] = 0; sh.lo[s] = 0;
                         sh.best_pos[s] = PRIM_NONE; sh.best_u[s] = 0.0f; sh.out_idx[s] = q.out;
                         if (VKHRT_MAILBOX_PHANTOM) sh.last_group[s] = PRIM_NONE;
                         fresh = true;
@@ -892,42 +1272,83 @@ static void fill_params(const DeviceScene& sc, const VkhrtFrameDesc& f, const Re
     p.ao_hits = nullptr; p.ao_occluded = nullptr; p.ao_index = p.ao_sample = 0u; p.ao_distance = 0.0f; p.ao_bias = 0.0f;
 }
 
-// scheduler tunables (defaults from the sweep in profiles/; overridable for experiments)
-static int g_refill_threshold = -1, g_blocks_per_sm = -1, g_w_node = -1, g_w_leaf = -1, g_w_march = -1, g_min_blocks = -1;
-static int g_pool_min_ratio = 3;
-static int g_pool = 1, g_pool_stats = 1, g_pool_node_lanes = 24, g_pool_batch_lanes = 8, g_pool_node_min = 8;
+// Experiment switches: environment variables read ONCE per process, on first use (thread-safe static
+// initialisation); the defaults are the shipped configuration.
+struct Tunables {
+    int refill_threshold, min_blocks, blocks_per_sm, w_node, w_leaf, w_march;
+    int pool_version;
+    int pool, pool_stats, pool_min_ratio, pool_node_lanes, pool_batch_lanes, pool_node_min, pool_exit, pool_cfg, pool_host, carveout;
+    int store256, zero_copy, linewise, line_shift;
+};
 static int env_int(const char* name, int def) { const char* v = getenv(name); return v ? atoi(v) : def; }
+static const Tunables& tun()
+{
+    static const Tunables t = [] {
+        Tunables x;
+        x.refill_threshold = std::max(1, env_int("VKHRT_REFILL_THRESHOLD", 16));
+        x.min_blocks = env_int("VKHRT_MIN_BLOCKS", TR_MIN_BLOCKS);
+        x.blocks_per_sm = env_int("VKHRT_BLOCKS_PER_SM", 0);
+        x.w_node = env_int("VKHRT_W_NODE", 16);
+        x.w_leaf = env_int("VKHRT_W_LEAF", 32);
+        x.w_march = env_int("VKHRT_W_MARCH", 32);
+        x.pool_version = env_int("VKHRT_POOL_V", 2);             // 1 = round 1's trace_pool_kernel, 2 = trace_pool2_kernel
+        x.pool = env_int("VKHRT_POOL", 1);                       // Phantom primary rays: trace_pool_kernel
+        x.pool_stats = env_int("VKHRT_POOL_STATS", 1);           // scheduler statistics of the pool kernel instead of trace_kernel's
+        x.pool_min_ratio = env_int("VKHRT_POOL_MIN_RATIO", 3);
+        x.pool_node_lanes = env_int("VKHRT_POOL_NODE_LANES", 24);
+        x.pool_batch_lanes = env_int("VKHRT_POOL_BATCH_LANES", 8);
+        x.pool_node_min = env_int("VKHRT_POOL_NODE_MIN", 8);
+        x.pool_exit = env_int("VKHRT_POOL_EXIT", 6);
+        x.pool_cfg = env_int("VKHRT_POOL_CFG", 0);
+        x.pool_host = env_int("VKHRT_POOL_HOST", 0);
+        x.carveout = env_int("VKHRT_CARVEOUT", -1);
+        x.store256 = env_int("VKHRT_STORE256", 1);
+        x.zero_copy = env_int("VKHRT_ZERO_COPY", 1);
+        x.linewise = env_int("VKHRT_LINEWISE", 1);
+        // 128-byte lines (4 records) measured best: e2e 996 (64 B) / 1077 (128 B) / 1068 (256 B) / 1034 (512 B) Mrays/s on C2
+        x.line_shift = std::min(5, std::max(1, env_int("VKHRT_LINE_SHIFT", 2)));
+        return x;
+    }();
+    return t;
+}
 static void tunables(TraceParams& p)
 {
-    if (g_refill_threshold < 0) {
-        g_refill_threshold = env_int("VKHRT_REFILL_THRESHOLD", 16);
-        g_min_blocks = env_int("VKHRT_MIN_BLOCKS", TR_MIN_BLOCKS);
-        g_blocks_per_sm = env_int("VKHRT_BLOCKS_PER_SM", 0);
-        g_w_node = env_int("VKHRT_W_NODE", 16);
-        g_w_leaf = env_int("VKHRT_W_LEAF", 32);
-        g_w_march = env_int("VKHRT_W_MARCH", 32);
-        g_pool = env_int("VKHRT_POOL", 1);                       // Phantom primary rays: trace_pool_kernel
-        g_pool_stats = env_int("VKHRT_POOL_STATS", 1);           // scheduler statistics of the pool kernel instead of trace_kernel's
-        g_pool_min_ratio = env_int("VKHRT_POOL_MIN_RATIO", 3);
-        g_pool_node_lanes = env_int("VKHRT_POOL_NODE_LANES", 24);
-        g_pool_batch_lanes = env_int("VKHRT_POOL_BATCH_LANES", 8);
-        g_pool_node_min = env_int("VKHRT_POOL_NODE_MIN", 8);
-    }
-    p.pool_node_lanes = (uint32_t)g_pool_node_lanes; p.pool_batch_lanes = (uint32_t)g_pool_batch_lanes; p.pool_node_min = (uint32_t)g_pool_node_min; p.pool_exit_eighths = (uint32_t)env_int("VKHRT_POOL_EXIT", 6);
-    p.refill_threshold = (uint32_t)std::max(1, g_refill_threshold);
-    p.w_node = (uint32_t)g_w_node; p.w_leaf = (uint32_t)g_w_leaf; p.w_march = (uint32_t)g_w_march;
+    const Tunables& t = tun();
+    p.pool_node_lanes = (uint32_t)t.pool_node_lanes; p.pool_batch_lanes = (uint32_t)t.pool_batch_lanes; p.pool_node_min = (uint32_t)t.pool_node_min; p.pool_exit_eighths = (uint32_t)t.pool_exit;
+    p.refill_threshold = (uint32_t)t.refill_threshold;
+    p.w_node = (uint32_t)t.w_node; p.w_leaf = (uint32_t)t.w_leaf; p.w_march = (uint32_t)t.w_march;
 }
 
-void init_tunables() { TraceParams p{}; tunables(p); }
+void init_tunables() { (void)tun(); }
+
+// resident CTAs per SM of a kernel: asked once per kernel instantiation and device
+template <typename K>
+static int blocks_per_sm(K kernel, int device)
+{
+    static int cached[64];            // 0 = not asked yet; indexed by device ordinal
+    const int d = device & 63;
+    if (cached[d] == 0) {
+        int per_sm = 0;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, TR_BLOCK, 0) != cudaSuccess) { cudaGetLastError(); per_sm = 1; }
+        cached[d] = std::max(1, per_sm);
+    }
+    return cached[d];
+}
+
+// every traversal launch takes the next of the two alternating work counters (TraceParams::work)
+static void take_work_counter(DeviceScene& sc, TraceParams& p)
+{
+    p.work = sc.d_counters + (sc.work_flip ? 6 : 0);
+    p.work_next = sc.d_counters + (sc.work_flip ? 0 : 6);
+    sc.work_flip = !sc.work_flip;
+}
 
 template <int TECH, bool STATS, int SRC, bool ANYHIT, int MINB>
 static int launch_trace_t(DeviceScene& sc, TraceParams& p, cudaStream_t st)
 {
-    int per_sm = 0;
-    VK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, trace_kernel<TECH, STATS, SRC, ANYHIT, MINB>, TR_BLOCK, 0));
-    if (per_sm < 1) per_sm = 1;
+    int per_sm = blocks_per_sm(trace_kernel<TECH, STATS, SRC, ANYHIT, MINB>, sc.device);
     tunables(p);
-    if (g_blocks_per_sm > 0) per_sm = std::min(per_sm, g_blocks_per_sm);
+    if (tun().blocks_per_sm > 0) per_sm = std::min(per_sm, tun().blocks_per_sm);
     unsigned long long want = ((unsigned long long)(p.n_slots - p.slot_begin) + TR_BLOCK - 1) / TR_BLOCK;
     unsigned grid = (unsigned)std::min<unsigned long long>((unsigned long long)sc.sm_count * per_sm, std::max<unsigned long long>(want, 1ull));
     trace_kernel<TECH, STATS, SRC, ANYHIT, MINB><<<grid, TR_BLOCK, 0, st>>>(p);
@@ -937,12 +1358,10 @@ static int launch_trace_t(DeviceScene& sc, TraceParams& p, cudaStream_t st)
 template <bool STATS, int PL_S, int PL_STK>
 static int launch_pool_t(DeviceScene& sc, TraceParams& p, cudaStream_t st)
 {
-    int per_sm = 0;
-    const int carve = env_int("VKHRT_CARVEOUT", -1);
+    const int carve = tun().carveout;
     if (carve >= 0) VK_CUDA(cudaFuncSetAttribute(trace_pool_kernel<STATS, PL_S, PL_STK>, cudaFuncAttributePreferredSharedMemoryCarveout, carve));
-    VK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, trace_pool_kernel<STATS, PL_S, PL_STK>, TR_BLOCK, 0));
-    if (per_sm < 1) per_sm = 1;
-    if (g_blocks_per_sm > 0) per_sm = std::min(per_sm, g_blocks_per_sm);
+    int per_sm = blocks_per_sm(trace_pool_kernel<STATS, PL_S, PL_STK>, sc.device);
+    if (tun().blocks_per_sm > 0) per_sm = std::min(per_sm, tun().blocks_per_sm);
     unsigned long long want = ((unsigned long long)(p.n_slots - p.slot_begin) + TR_BLOCK - 1) / TR_BLOCK;
     unsigned grid = (unsigned)std::min<unsigned long long>((unsigned long long)sc.sm_count * per_sm, std::max<unsigned long long>(want, 1ull));
     const size_t ovf = (size_t)grid * (TR_BLOCK / 32) * PL_S * PL_OVF;
@@ -958,11 +1377,40 @@ static int launch_pool_t(DeviceScene& sc, TraceParams& p, cudaStream_t st)
     count_launch();
     return VKHRT_OK;
 }
+template <bool STATS, int PL_S, int PL_STK>
+static int launch_pool2_t(DeviceScene& sc, TraceParams& p, cudaStream_t st)
+{
+    const int carve = tun().carveout;
+    if (carve >= 0) VK_CUDA(cudaFuncSetAttribute(trace_pool2_kernel<STATS, PL_S, PL_STK>, cudaFuncAttributePreferredSharedMemoryCarveout, carve));
+    int per_sm = blocks_per_sm(trace_pool2_kernel<STATS, PL_S, PL_STK>, sc.device);
+    if (tun().blocks_per_sm > 0) per_sm = std::min(per_sm, tun().blocks_per_sm);
+    unsigned long long want = ((unsigned long long)(p.n_slots - p.slot_begin) + TR_BLOCK - 1) / TR_BLOCK;
+    unsigned grid = (unsigned)std::min<unsigned long long>((unsigned long long)sc.sm_count * per_sm, std::max<unsigned long long>(want, 1ull));
+    const size_t ovf = (size_t)grid * (TR_BLOCK / 32) * PL_S * PL_OVF;
+    if (sc.pool_overflow_n < ovf) {
+        if (sc.d_pool_overflow) cudaFree(sc.d_pool_overflow);
+        sc.d_pool_overflow = nullptr; sc.pool_overflow_n = 0;
+        VK_CUDA(cudaMalloc(&sc.d_pool_overflow, ovf * sizeof(uint2)));
+        sc.pool_overflow_n = ovf;
+    }
+    p.pool_overflow = sc.d_pool_overflow;
+    trace_pool2_kernel<STATS, PL_S, PL_STK><<<grid, TR_BLOCK, 0, st>>>(p);
+    sc.last_trace_was_pool = true;
+    count_launch();
+    return VKHRT_OK;
+}
 template <bool STATS>
 static int launch_pool(DeviceScene& sc, TraceParams& p, cudaStream_t st)
 {
+    if (tun().pool_version == 2) {
+        switch (tun().pool_cfg) {
+        case 1: return launch_pool2_t<STATS, 56, 8>(sc, p, st);
+        case 2: return launch_pool2_t<STATS, 64, 6>(sc, p, st);
+        default: return launch_pool2_t<STATS, 72, 4>(sc, p, st);
+        }
+    }
     // slots per warp x shared-memory stack window: 72 x 4 and 56 x 8 both fit 8 CTAs per SM (profiles/experiments/r01_pool_kernel.txt)
-    switch (env_int("VKHRT_POOL_CFG", 0)) {
+    switch (tun().pool_cfg) {
     case 1: return launch_pool_t<STATS, 56, 8>(sc, p, st);
     default: return launch_pool_t<STATS, 72, 4>(sc, p, st);
     }
@@ -973,18 +1421,18 @@ static int launch_trace(DeviceScene& sc, TraceParams& p, cudaStream_t st)
     tunables(p);
     sc.last_trace_was_pool = false;
     p.hits_aligned32 = (((uintptr_t)p.hits & 31u) == 0u ? 1u : 0u) | (((uintptr_t)p.hits_mirror & 31u) == 0u ? 2u : 0u);
-    if (env_int("VKHRT_STORE256", 1) == 0) p.hits_aligned32 = 0u;
+    if (tun().store256 == 0) p.hits_aligned32 = 0u;
     switch (sc.technique) {
     case VKHRT_TECHNIQUE_PHANTOM:
         // records that go straight to pinned host memory keep trace_kernel: its retiring lanes are pixel neighbours, which the
         // PCIe write path combines better (e2e 997 vs 819 Mrays/s on C2)
         // ... and small frames too: the pool needs several times its resident capacity (SMs x 32 warps x 56 slots = 265 k rays
         // on a B200) in rays to reach a steady state; below that it is all ramp-up and drain (C1: 639 vs 801 Mrays/s)
-        if (SRC == SRC_PRIMARY && !ANYHIT && g_pool && p.n_prims && (!STATS || g_pool_stats) && !(p.host_dest && env_int("VKHRT_POOL_HOST", 0) == 0) &&
-            (unsigned long long)(p.n_slots - p.slot_begin) >= (unsigned long long)g_pool_min_ratio * sc.sm_count * 32ull * 56ull)
+        if (SRC == SRC_PRIMARY && !ANYHIT && tun().pool && p.n_prims && (!STATS || tun().pool_stats) && !(p.host_dest && tun().pool_host == 0) &&
+            (unsigned long long)(p.n_slots - p.slot_begin) >= (unsigned long long)tun().pool_min_ratio * sc.sm_count * 32ull * 56ull)
             return launch_pool<STATS>(sc, p, st);
-        if (!STATS && SRC == SRC_PRIMARY && g_min_blocks == 7) return launch_trace_t<VKHRT_TECHNIQUE_PHANTOM, false, SRC_PRIMARY, false, 7>(sc, p, st);
-        if (!STATS && SRC == SRC_PRIMARY && g_min_blocks == 8) return launch_trace_t<VKHRT_TECHNIQUE_PHANTOM, false, SRC_PRIMARY, false, 8>(sc, p, st);
+        if (!STATS && SRC == SRC_PRIMARY && tun().min_blocks == 7) return launch_trace_t<VKHRT_TECHNIQUE_PHANTOM, false, SRC_PRIMARY, false, 7>(sc, p, st);
+        if (!STATS && SRC == SRC_PRIMARY && tun().min_blocks == 8) return launch_trace_t<VKHRT_TECHNIQUE_PHANTOM, false, SRC_PRIMARY, false, 8>(sc, p, st);
         return launch_trace_t<VKHRT_TECHNIQUE_PHANTOM, STATS, SRC, ANYHIT, TR_MIN_BLOCKS>(sc, p, st);
     case VKHRT_TECHNIQUE_LSS: return launch_trace_t<VKHRT_TECHNIQUE_LSS, STATS, SRC, ANYHIT, TR_MIN_BLOCKS>(sc, p, st);
     default: return launch_trace_t<VKHRT_TECHNIQUE_DOTS, STATS, SRC, ANYHIT, TR_MIN_BLOCKS>(sc, p, st);
@@ -1035,7 +1483,7 @@ int render_frame(DeviceScene& sc, const VkhrtFrameDesc& f, VkhrtHit* hits_out, u
     // PCIe (posted 16-byte writes, fully overlapped with the traversal) instead of a device->host copy after the
     // kernel.  When an image is wanted too, the records are also kept in HBM for the shading kernel.
     VkhrtHit* h_hits_mapped = nullptr;
-    if (host_out && want_hits && !stats && env_int("VKHRT_ZERO_COPY", 1)) {
+    if (host_out && want_hits && !stats && tun().zero_copy) {
         cudaPointerAttributes at;
         if (cudaPointerGetAttributes(&at, hits_out) == cudaSuccess && at.type == cudaMemoryTypeHost && at.devicePointer)
             h_hits_mapped = static_cast<VkhrtHit*>(at.devicePointer);
@@ -1047,10 +1495,9 @@ int render_frame(DeviceScene& sc, const VkhrtFrameDesc& f, VkhrtHit* hits_out, u
     if (want_hits || want_rgba) d_hits0 = direct_hits ? hits_out : sc.d_hits_scratch;
     // Phantom frames large enough for the pool kernel: line-wise delivery (records to HBM, complete 128-byte lines to the host)
     bool linewise = false;
-    // 128-byte lines (4 records) measured best: e2e 996 (64 B) / 1077 (128 B) / 1068 (256 B) / 1034 (512 B) Mrays/s on C2
-    const uint32_t line_shift = (uint32_t)std::min(5, std::max(1, env_int("VKHRT_LINE_SHIFT", 2)));
-    if (h_hits_mapped && !want_rgba && sc.technique == VKHRT_TECHNIQUE_PHANTOM && sc.n_leaves && env_int("VKHRT_POOL", 1) && env_int("VKHRT_LINEWISE", 1) &&
-        (((uintptr_t)h_hits_mapped) & ((32u << line_shift) - 1u)) == 0u && r.n_slots >= (unsigned long long)env_int("VKHRT_POOL_MIN_RATIO", 3) * sc.sm_count * 32ull * 56ull) {
+    const uint32_t line_shift = (uint32_t)tun().line_shift;
+    if (h_hits_mapped && !want_rgba && sc.technique == VKHRT_TECHNIQUE_PHANTOM && sc.n_leaves && tun().pool && tun().linewise &&
+        (((uintptr_t)h_hits_mapped) & ((32u << line_shift) - 1u)) == 0u && r.n_slots >= (unsigned long long)tun().pool_min_ratio * sc.sm_count * 32ull * 56ull) {
         if ((rc = grow(&sc.d_hits_scratch, &sc.hits_scratch_n, (size_t)r.n_out))) return rc;
         if ((rc = grow(&sc.d_line_cnt, &sc.line_cnt_n, (size_t)r.n_out / 2 + 1))) return rc;      // enough for the smallest line (2 records)
         linewise = true;
@@ -1084,7 +1531,7 @@ int render_frame(DeviceScene& sc, const VkhrtFrameDesc& f, VkhrtHit* hits_out, u
             p.line_cnt = sc.d_line_cnt; p.host_lines = h_lines; p.line_shift = line_shift;
             VK_CUDA(cudaMemsetAsync(sc.d_line_cnt, 0, (((size_t)r.n_out >> p.line_shift) + 1) * sizeof(uint32_t), st));
         }
-        VK_CUDA(cudaMemsetAsync(sc.d_counters, 0, sizeof(unsigned long long), st));
+        take_work_counter(sc, p);
         if (s == 0) VK_CUDA(cudaEventRecord(ev[7], st));
         rc = stats ? launch_trace<true, SRC_PRIMARY, false>(sc, p, st) : launch_trace<false, SRC_PRIMARY, false>(sc, p, st);
         if (rc) return rc;
@@ -1103,7 +1550,7 @@ int render_frame(DeviceScene& sc, const VkhrtFrameDesc& f, VkhrtHit* hits_out, u
             q.hits = nullptr; q.hits_mirror = nullptr;
             for (uint32_t a = 0; a < ao; ++a) {
                 q.ao_index = a;
-                VK_CUDA(cudaMemsetAsync(sc.d_counters, 0, sizeof(unsigned long long), st));
+                take_work_counter(sc, q);
                 rc = stats ? launch_trace<true, SRC_AO, true>(sc, q, st) : launch_trace<false, SRC_AO, true>(sc, q, st);
                 if (rc) return rc;
             }
@@ -1130,7 +1577,9 @@ int render_frame(DeviceScene& sc, const VkhrtFrameDesc& f, VkhrtHit* hits_out, u
         stats->nodes_visited = c[1]; stats->prims_tested = c[2]; stats->hits = c[3]; stats->phantom_iterations = c[4]; stats->rays = c[5];
         for (int k = 0; k < 4; ++k) { stats->sched_steps[k] = c[8 + k]; stats->sched_lanes[k] = c[12 + k]; }
     }
-    if (host_out) VK_CUDA(cudaStreamSynchronize(st));
+    // host outputs: the call returns when the copies have landed.  Device outputs on the scene's own stream (no caller
+    // stream): the caller has no handle to order against, so the call is synchronous too, like vkhrt_trace_rays.
+    if (host_out || !f.stream) VK_CUDA(cudaStreamSynchronize(st));
     VK_CUDA(cudaGetLastError());
     return VKHRT_OK;
 }
@@ -1152,7 +1601,7 @@ int trace_ray_buffer(DeviceScene& sc, const float* rays_dev, uint64_t n, VkhrtHi
         p.rays = reinterpret_cast<const float4*>(rays_dev) + 2 * first;
         p.hits = hits_dev + first;
         p.n_slots = (uint32_t)std::min<uint64_t>(chunk, n - first);
-        VK_CUDA(cudaMemsetAsync(sc.d_counters, 0, sizeof(unsigned long long), st));
+        take_work_counter(sc, p);
         int rc = any_hit ? launch_trace<false, SRC_BUFFER, true>(sc, p, st) : launch_trace<false, SRC_BUFFER, false>(sc, p, st);
         if (rc) return rc;
     }
@@ -1183,8 +1632,13 @@ int untile_buffer(const VkhrtFrameDesc& f, uint32_t world, const void* gathered,
     g.tile_first = 0; g.tile_stride = world;
     Resolved r;
     if (!resolve(g, r) || world == 0) { set_last_error("vkhrt_untile: bad frame description"); return VKHRT_ERR_INVALID_ARGUMENT; }
+    if (elem_bytes != 4 && elem_bytes != 32) { set_last_error("vkhrt_untile: elem_bytes must be 4 or 32"); return VKHRT_ERR_INVALID_ARGUMENT; }
+    if (world == 1) {
+        // a one-shard render is never compact (tile_stride 1 writes row-major, W*H elements): plain copy, as vkhrt_untile_host
+        VK_CUDA(cudaMemcpyAsync(row_major, gathered, (size_t)r.W * r.H * elem_bytes, cudaMemcpyDeviceToDevice, stream));
+        return VKHRT_OK;
+    }
     unsigned long long shard = (unsigned long long)r.n_local_tiles * r.T * r.T;
-    if (world == 1) shard = (unsigned long long)r.n_tiles * r.T * r.T;
     unsigned grid = (unsigned)(((unsigned long long)r.W * r.H + 255) / 256);
     if (elem_bytes == 4) untile_kernel<uint32_t><<<grid, 256, 0, stream>>>((const uint32_t*)gathered, (uint32_t*)row_major, r.W, r.H, r.T, r.tiles_x, world, shard);
     else if (elem_bytes == 32) untile_kernel<Elem32><<<grid, 256, 0, stream>>>((const Elem32*)gathered, (Elem32*)row_major, r.W, r.H, r.T, r.tiles_x, world, shard);
