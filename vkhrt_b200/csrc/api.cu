@@ -3,7 +3,9 @@
 #include "scene.h"
 #include <algorithm>
 #include <atomic>
+#include <condition_variable>
 #include <cstring>
+#include <functional>
 #include <cmath>
 #include <mutex>
 #include <new>
@@ -43,6 +45,8 @@ static void free_scene(DeviceScene* sc)
     cudaSetDevice(sc->device);
     cudaFree(sc->d_positions); cudaFree(sc->d_indices); cudaFree(sc->d_radius_pv); cudaFree(sc->d_curves); cudaFree(sc->d_env);
     cudaFree(sc->d_arena);       // nodes, sorted ids / keys, parents, refit flags, primA, primB
+    cudaFree(sc->d_multi_hits); cudaFree(sc->d_multi_rgba);
+    if (sc->multi_done) cudaEventDestroy(sc->multi_done);
     cudaFree(sc->d_counters); cudaFree(sc->d_hits_scratch); cudaFree(sc->d_accum); cudaFree(sc->d_rgba_scratch); cudaFree(sc->d_occluded); cudaFree(sc->d_pool_overflow); cudaFree(sc->d_line_cnt);
     if (sc->h_pinned) cudaFreeHost(sc->h_pinned);
     for (auto& e : sc->ev) if (e) cudaEventDestroy(e);
@@ -271,6 +275,96 @@ int vkhrt_untile_host(const VkhrtFrameDesc* frame, uint32_t world, const void* g
     return untile_host(*frame, world, shards.data(), (unsigned char*)row_major, elem_bytes);
 }
 
+// One frame on several GPUs from one process.  Two ways to assemble it, both without a CPU re-ordering pass:
+//   * hit records, page-locked caller buffer: every GPU's traversal kernel stores its records at their row-major position
+//     straight into the caller's buffer over its own PCIe link (the zero-copy / line-wise delivery of vkhrt_render);
+//   * everything else (pixels; records into pageable memory): scenes[0]'s GPU holds a full-frame buffer, the other GPUs store
+//     into it over NVLink (peer access, VkhrtFrameDesc::row_major_output: the kernels' own stores are the gather), and one
+//     copy brings it to the host.
+// Shards are launched by persistent worker threads (one per extra scene) so that no GPU waits for another one's launch.
+// Without peer access between the devices the shards are staged through pinned buffers and re-ordered on the host.
+}  // extern "C"
+namespace vkhrt {
+namespace {
+class Workers {
+public:
+    // run fn(0) .. fn(n-1): fn(0) on the calling thread, the others on persistent threads
+    void run(uint32_t n, const std::function<void(uint32_t)>& fn)
+    {
+        std::lock_guard<std::mutex> serial(call_);
+        while (threads_.size() + 1 < n) { const uint32_t id = (uint32_t)threads_.size() + 1; threads_.emplace_back([this, id] { loop(id); }); }
+        {
+            std::lock_guard<std::mutex> g(m_);
+            fn_ = &fn; n_ = n; pending_ = n - 1; ++generation_;
+        }
+        cv_.notify_all();
+        fn(0);
+        std::unique_lock<std::mutex> g(m_);
+        done_.wait(g, [this] { return pending_ == 0; });
+        fn_ = nullptr;
+    }
+    ~Workers()
+    {
+        { std::lock_guard<std::mutex> g(m_); quit_ = true; }
+        cv_.notify_all();
+        for (std::thread& t : threads_) t.join();
+    }
+private:
+    void loop(uint32_t id)
+    {
+        uint64_t seen = 0;
+        for (;;) {
+            const std::function<void(uint32_t)>* fn = nullptr;
+            {
+                std::unique_lock<std::mutex> g(m_);
+                cv_.wait(g, [&] { return quit_ || (generation_ != seen && id < n_); });
+                if (quit_) return;
+                seen = generation_; fn = fn_;
+            }
+            (*fn)(id);
+            { std::lock_guard<std::mutex> g(m_); if (--pending_ == 0) done_.notify_one(); }
+        }
+    }
+    std::mutex call_, m_;
+    std::condition_variable cv_, done_;
+    std::vector<std::thread> threads_;
+    const std::function<void(uint32_t)>* fn_ = nullptr;
+    uint32_t n_ = 0, pending_ = 0;
+    uint64_t generation_ = 0;
+    bool quit_ = false;
+};
+Workers& workers() { static Workers w; return w; }
+
+// can every scene's device store into scenes[0]'s device?  (enables peer access on first use)
+bool peer_ready(VkhrtScene* const* scenes, uint32_t n)
+{
+    const int d0 = scenes[0]->s.device;
+    for (uint32_t r = 1; r < n; ++r) {
+        const int d = scenes[r]->s.device;
+        if (d == d0) continue;
+        int can = 0;
+        if (cudaDeviceCanAccessPeer(&can, d, d0) != cudaSuccess || !can) { cudaGetLastError(); return false; }
+        if (cudaSetDevice(d) != cudaSuccess) { cudaGetLastError(); return false; }
+        const cudaError_t e = cudaDeviceEnablePeerAccess(d0, 0);
+        if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) { cudaGetLastError(); return false; }
+        cudaGetLastError();
+    }
+    return true;
+}
+template <typename T>
+int grow_buffer(T** p, size_t* have, size_t want)
+{
+    if (*have >= want) return VKHRT_OK;
+    if (*p) cudaFree(*p);
+    *p = nullptr; *have = 0;
+    VK_CUDA(cudaMalloc((void**)p, want * sizeof(T)));
+    *have = want;
+    return VKHRT_OK;
+}
+}  // namespace
+}  // namespace vkhrt
+extern "C" {
+
 int vkhrt_render_multi(VkhrtScene* const* scenes, uint32_t n_scenes, const VkhrtFrameDesc* frame, VkhrtHit* hits_out, uint8_t* rgba8_out)
 {
     if (!scenes || n_scenes == 0 || !frame) { set_last_error("null argument"); return VKHRT_ERR_INVALID_ARGUMENT; }
@@ -288,6 +382,56 @@ int vkhrt_render_multi(VkhrtScene* const* scenes, uint32_t n_scenes, const Vkhrt
     base.tile_stride = n_scenes;
     const uint64_t per_shard = frame_local_pixels(base);
     if (per_shard == 0) { set_last_error("vkhrt_render_multi: bad frame description"); return VKHRT_ERR_INVALID_ARGUMENT; }
+    const size_t n_full = (size_t)frame->width * frame->height;
+    init_tunables();                       // the environment switches are read once, before the worker threads launch anything
+    DeviceScene& s0 = scenes[0]->s;
+    std::vector<int> rc(n_scenes, VKHRT_OK);
+    std::vector<std::string> err(n_scenes);
+    auto first_error = [&]() -> int {
+        for (uint32_t r = 0; r < n_scenes; ++r)
+            if (rc[r] != VKHRT_OK) { set_last_error("shard " + std::to_string(r) + ": " + err[r]); return rc[r]; }
+        return VKHRT_OK;
+    };
+
+    if (peer_ready(scenes, n_scenes)) {
+        // records: straight into the caller's buffer when the kernels can store into it (page-locked), else via scenes[0]'s GPU
+        bool hits_zero_copy = false;
+        if (hits_out) {
+            cudaPointerAttributes at;
+            hits_zero_copy = cudaPointerGetAttributes(&at, hits_out) == cudaSuccess && at.type == cudaMemoryTypeHost && at.devicePointer != nullptr;
+            cudaGetLastError();
+        }
+        VK_CUDA(cudaSetDevice(s0.device));
+        if (hits_out && !hits_zero_copy) { int g = grow_buffer(&s0.d_multi_hits, &s0.multi_hits_n, n_full); if (g) return g; }
+        if (rgba8_out) { int g = grow_buffer(&s0.d_multi_rgba, &s0.multi_rgba_n, n_full * 4); if (g) return g; }
+        for (uint32_t r = 0; r < n_scenes; ++r)
+            if (!scenes[r]->s.multi_done) { VK_CUDA(cudaSetDevice(scenes[r]->s.device)); VK_CUDA(cudaEventCreateWithFlags(&scenes[r]->s.multi_done, cudaEventDisableTiming)); }
+        workers().run(n_scenes, [&](uint32_t r) {
+            DeviceScene& sc = scenes[r]->s;
+            VkhrtFrameDesc f = base;
+            f.tile_first = r;
+            f.row_major_output = 1;
+            RenderOpts o;
+            o.defer_sync = true;
+            o.hits_on_device = hits_out && !hits_zero_copy;
+            o.rgba_on_device = rgba8_out != nullptr;
+            rc[r] = render_frame(sc, f, hits_out ? (hits_zero_copy ? hits_out : s0.d_multi_hits) : nullptr, rgba8_out ? s0.d_multi_rgba : nullptr, nullptr, o);
+            if (rc[r] == VKHRT_OK && cudaEventRecord(sc.multi_done, sc.stream) != cudaSuccess) { rc[r] = VKHRT_ERR_CUDA; set_last_error("cudaEventRecord failed"); }
+            if (rc[r] != VKHRT_OK) err[r] = vkhrt_last_error();       // the error text is per thread: carry it to the caller's
+        });
+        // wait for every shard (also after a failure: nothing may still be writing into the buffers when this call returns)
+        for (uint32_t r = 0; r < n_scenes; ++r) { cudaSetDevice(scenes[r]->s.device); cudaStreamSynchronize(scenes[r]->s.stream); }
+        cudaGetLastError();
+        int e = first_error();
+        if (e) return e;
+        VK_CUDA(cudaSetDevice(s0.device));
+        if (hits_out && !hits_zero_copy) VK_CUDA(cudaMemcpyAsync(hits_out, s0.d_multi_hits, n_full * sizeof(VkhrtHit), cudaMemcpyDeviceToHost, s0.stream));
+        if (rgba8_out) VK_CUDA(cudaMemcpyAsync(rgba8_out, s0.d_multi_rgba, n_full * 4, cudaMemcpyDeviceToHost, s0.stream));
+        VK_CUDA(cudaStreamSynchronize(s0.stream));
+        return VKHRT_OK;
+    }
+
+    // no peer access between the devices: compact shards through host staging + re-ordering on the host
     std::vector<std::vector<unsigned char>> sh_hits(n_scenes), sh_rgba(n_scenes);
     try {
         for (uint32_t r = 0; r < n_scenes; ++r) {
@@ -295,20 +439,14 @@ int vkhrt_render_multi(VkhrtScene* const* scenes, uint32_t n_scenes, const Vkhrt
             if (rgba8_out) sh_rgba[r].resize((size_t)per_shard * 4);
         }
     } catch (const std::bad_alloc&) { set_last_error("out of host memory"); return VKHRT_ERR_OUT_OF_MEMORY; }
-    init_tunables();                       // the environment switches are read once, before the worker threads launch anything
-    std::vector<int> rc(n_scenes, VKHRT_OK);
-    std::vector<std::string> err(n_scenes);
-    std::vector<std::thread> workers;
-    for (uint32_t r = 0; r < n_scenes; ++r)
-        workers.emplace_back([&, r]() {
-            VkhrtFrameDesc f = base;
-            f.tile_first = r;
-            rc[r] = vkhrt_render(scenes[r], &f, hits_out ? (VkhrtHit*)sh_hits[r].data() : nullptr, rgba8_out ? sh_rgba[r].data() : nullptr);
-            if (rc[r] != VKHRT_OK) err[r] = vkhrt_last_error();       // the error text is per thread: carry it to the caller's
-        });
-    for (std::thread& w : workers) w.join();
-    for (uint32_t r = 0; r < n_scenes; ++r)
-        if (rc[r] != VKHRT_OK) { set_last_error("shard " + std::to_string(r) + ": " + err[r]); return rc[r]; }
+    workers().run(n_scenes, [&](uint32_t r) {
+        VkhrtFrameDesc f = base;
+        f.tile_first = r;
+        rc[r] = vkhrt_render(scenes[r], &f, hits_out ? (VkhrtHit*)sh_hits[r].data() : nullptr, rgba8_out ? sh_rgba[r].data() : nullptr);
+        if (rc[r] != VKHRT_OK) err[r] = vkhrt_last_error();
+    });
+    int e = first_error();
+    if (e) return e;
     std::vector<const unsigned char*> ptr(n_scenes);
     if (hits_out) {
         for (uint32_t r = 0; r < n_scenes; ++r) ptr[r] = sh_hits[r].data();

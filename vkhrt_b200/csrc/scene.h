@@ -58,6 +58,10 @@ struct DeviceScene {
     uint2* d_pool_overflow = nullptr; size_t pool_overflow_n = 0;   // trace_pool_kernel: stack entries beyond the shared-memory slots   // per pixel: occluded AO rays of the current sample
     uint8_t* d_rgba_scratch = nullptr; size_t rgba_scratch_n = 0;
     void* h_pinned = nullptr; size_t h_pinned_bytes = 0;   // staging for host outputs
+    // vkhrt_render_multi: full-frame buffers on the gathering GPU (scenes[0]'s device); the other GPUs store into them over NVLink
+    VkhrtHit* d_multi_hits = nullptr; size_t multi_hits_n = 0;
+    uint8_t* d_multi_rgba = nullptr; size_t multi_rgba_n = 0;
+    cudaEvent_t multi_done = nullptr;
 
     cudaStream_t stream = nullptr;
     cudaStream_t copy_stream = nullptr;
@@ -90,8 +94,13 @@ int apply_lod(DeviceScene& sc, uint32_t split_passes, uint32_t merge_passes, uin
 int export_lines(DeviceScene& sc, float* host_out, size_t out_floats);
 
 // trace.cu
-struct FrameParams;
-int render_frame(DeviceScene& sc, const VkhrtFrameDesc& f, VkhrtHit* hits_out, uint8_t* rgba_out, VkhrtTraceStats* stats);
+struct RenderOpts {
+    bool defer_sync = false;       // enqueue only; the caller synchronises sc.stream itself
+    bool hits_on_device = false;   // hits_out is a DEVICE pointer although frame.output_memory is HOST (vkhrt_render_multi)
+    bool rgba_on_device = false;   // same for rgba8_out
+    cudaStream_t stream = nullptr; // run on this stream instead of the scene's / the frame's
+};
+int render_frame(DeviceScene& sc, const VkhrtFrameDesc& f, VkhrtHit* hits_out, uint8_t* rgba_out, VkhrtTraceStats* stats, const RenderOpts& opts = RenderOpts());
 int trace_ray_buffer(DeviceScene& sc, const float* rays_dev, uint64_t n, VkhrtHit* hits_dev, bool any_hit, cudaStream_t stream);
 int generate_ray_buffer(const VkhrtFrameDesc& f, uint32_t sample, float* rays_dev, cudaStream_t stream);
 int untile_buffer(const VkhrtFrameDesc& f, uint32_t world, const void* gathered, void* row_major, uint32_t elem_bytes,

@@ -1450,44 +1450,52 @@ static int grow(T** p, size_t* have, size_t want)
     return VKHRT_OK;
 }
 
-int render_frame(DeviceScene& sc, const VkhrtFrameDesc& f, VkhrtHit* hits_out, uint8_t* rgba_out, VkhrtTraceStats* stats)
+int render_frame(DeviceScene& sc, const VkhrtFrameDesc& f, VkhrtHit* hits_out, uint8_t* rgba_out, VkhrtTraceStats* stats, const RenderOpts& opts)
 {
     VK_CUDA(cudaSetDevice(sc.device));
     Resolved r;
     if (!resolve(f, r)) { set_last_error("vkhrt_render: bad frame description (size, tile_size multiple of 8, tile_first < tile_stride)"); return VKHRT_ERR_INVALID_ARGUMENT; }
     if (f.miss_mode == VKHRT_MISS_ENVIRONMENT && !sc.d_env) { set_last_error("vkhrt_render: miss_mode ENVIRONMENT without vkhrt_scene_set_environment"); return VKHRT_ERR_INVALID_ARGUMENT; }
     if (f.miss_mode != VKHRT_MISS_CONSTANT && f.miss_mode != VKHRT_MISS_ENVIRONMENT) { set_last_error("vkhrt_render: unknown miss_mode"); return VKHRT_ERR_INVALID_ARGUMENT; }
-    const bool host_out = f.output_memory == VKHRT_MEM_HOST;
-    if (host_out && r.tile_stride > 1 && f.row_major_output) {
-        set_last_error("vkhrt_render: row_major_output with tile_stride > 1 writes into a frame buffer shared by all shards and needs device output memory");
-        return VKHRT_ERR_INVALID_ARGUMENT;
-    }
-    cudaStream_t st = (!host_out && f.stream) ? (cudaStream_t)f.stream : sc.stream;
+    const bool want_rgba = rgba_out != nullptr;
+    const bool want_hits = hits_out != nullptr;
+    // where each output lives (vkhrt_render_multi sends the two to different places: records to the caller's pinned host
+    // buffer, pixels to the gathering GPU's frame buffer)
+    const bool host_frame = f.output_memory == VKHRT_MEM_HOST;
+    const bool hits_host = want_hits && host_frame && !opts.hits_on_device;
+    const bool rgba_host = want_rgba && host_frame && !opts.rgba_on_device;
+    const bool any_host = hits_host || rgba_host;
+    // a shard that writes at row-major positions of a buffer shared with other shards may only touch its own pixels
+    const bool shared_frame = r.tile_stride > 1 && f.row_major_output;
+    cudaStream_t st = opts.stream ? opts.stream : ((!host_frame && f.stream) ? (cudaStream_t)f.stream : sc.stream);
     int rc;
 
     // device-side destinations: sample-0 hit records go to the caller's buffer when it is device memory,
     // otherwise to scratch[0, n_out); samples >= 1 (only traced when an image is wanted) use scratch[n_out, 2 n_out)
-    const bool want_rgba = rgba_out != nullptr;
-    const bool want_hits = hits_out != nullptr;
     const bool multi = r.spp > 1 && want_rgba;
     const uint32_t ao = want_rgba ? f.ao_samples : 0u;     // AO only changes the image
     // with AO the passes re-read the primary hit records: keep them in this GPU's HBM and mirror them to the caller's
     // buffer (which may be a peer GPU's frame buffer, row_major_output) instead of reading them back over NVLink
-    const bool direct_hits = !host_out && want_hits && ao == 0u;
-    VkhrtHit* d_hits_mirror = (!host_out && want_hits && ao != 0u) ? hits_out : nullptr;
+    const bool direct_hits = want_hits && !hits_host && ao == 0u;
+    VkhrtHit* d_hits_mirror = (want_hits && !hits_host && ao != 0u) ? hits_out : nullptr;
     bool direct_to_host = false;
     VkhrtHit* d_hits0 = nullptr;
     VkhrtHit* d_hits_other = nullptr;
     uint8_t* d_rgba = nullptr;
     // Host hit buffer in pinned (page-locked) memory: the traversal kernel stores each record straight into it over
-    // PCIe (posted 16-byte writes, fully overlapped with the traversal) instead of a device->host copy after the
+    // PCIe (posted writes, fully overlapped with the traversal) instead of a device->host copy after the
     // kernel.  When an image is wanted too, the records are also kept in HBM for the shading kernel.
     VkhrtHit* h_hits_mapped = nullptr;
-    if (host_out && want_hits && !stats && tun().zero_copy) {
+    if (hits_host && !stats && tun().zero_copy) {
         cudaPointerAttributes at;
         if (cudaPointerGetAttributes(&at, hits_out) == cudaSuccess && at.type == cudaMemoryTypeHost && at.devicePointer)
             h_hits_mapped = static_cast<VkhrtHit*>(at.devicePointer);
         cudaGetLastError();
+    }
+    if (shared_frame && ((hits_host && !h_hits_mapped) || rgba_host)) {
+        set_last_error("vkhrt_render: row_major_output with tile_stride > 1 writes into a frame buffer shared by all shards: device output memory, "
+                       "or (hit records only) a page-locked host buffer that the kernel can store into directly");
+        return VKHRT_ERR_INVALID_ARGUMENT;
     }
     if ((want_hits || want_rgba) && (!direct_hits || multi) && !(h_hits_mapped && !want_rgba)) {
         if ((rc = grow(&sc.d_hits_scratch, &sc.hits_scratch_n, (size_t)r.n_out * (multi ? 2 : 1)))) return rc;
@@ -1507,7 +1515,7 @@ int render_frame(DeviceScene& sc, const VkhrtFrameDesc& f, VkhrtHit* hits_out, u
     if (h_hits_mapped && !want_rgba) { d_hits0 = h_hits_mapped; h_hits_mapped = nullptr; direct_to_host = true; }   // single destination
     if (multi) d_hits_other = sc.d_hits_scratch + r.n_out;
     if (want_rgba) {
-        if (host_out) { if ((rc = grow(&sc.d_rgba_scratch, &sc.rgba_scratch_n, (size_t)r.n_out * 4))) return rc; d_rgba = sc.d_rgba_scratch; }
+        if (rgba_host) { if ((rc = grow(&sc.d_rgba_scratch, &sc.rgba_scratch_n, (size_t)r.n_out * 4))) return rc; d_rgba = sc.d_rgba_scratch; }
         else d_rgba = rgba_out;
         if (multi) { if ((rc = grow(&sc.d_accum, &sc.accum_n, (size_t)r.n_out))) return rc; }
         if (ao) { if ((rc = grow(&sc.d_occluded, &sc.occluded_n, (size_t)r.n_out))) return rc; }
@@ -1537,8 +1545,11 @@ int render_frame(DeviceScene& sc, const VkhrtFrameDesc& f, VkhrtHit* hits_out, u
         if (rc) return rc;
         if (s == 0) VK_CUDA(cudaEventRecord(ev[8], st));
         // line-wise delivery is a feature of the pool kernel: if the dispatch picked the lane-bound kernel after all, the records are
-        // in HBM only and go out with a plain copy
-        if (linewise && s == 0 && !sc.last_trace_was_pool) VK_CUDA(cudaMemcpyAsync(hits_out, d_hits0, (size_t)r.n_out * sizeof(VkhrtHit), cudaMemcpyDeviceToHost, st));
+        // in HBM only and go out with a plain copy (whole buffer: not possible for a shard of a shared frame)
+        if (linewise && s == 0 && !sc.last_trace_was_pool) {
+            if (shared_frame) { set_last_error("vkhrt_render: line-wise host delivery fell back to a whole-buffer copy on a shared frame"); return VKHRT_ERR_UNSUPPORTED; }
+            VK_CUDA(cudaMemcpyAsync(hits_out, d_hits0, (size_t)r.n_out * sizeof(VkhrtHit), cudaMemcpyDeviceToHost, st));
+        }
         if (ao) {
             // secondary rays: ao passes of one occlusion ray per hit pixel, spawned from the hit records inside the
             // traversal kernel's refill step (no ray buffer), terminate-on-first-hit
@@ -1565,10 +1576,8 @@ int render_frame(DeviceScene& sc, const VkhrtFrameDesc& f, VkhrtHit* hits_out, u
         if (s == 0) VK_CUDA(cudaEventRecord(ev[9], st));
     }
     VK_CUDA(cudaEventRecord(ev[10], st));
-    if (host_out) {
-        if (want_hits && !h_hits_mapped && !direct_to_host && !linewise) VK_CUDA(cudaMemcpyAsync(hits_out, d_hits0, (size_t)r.n_out * sizeof(VkhrtHit), cudaMemcpyDeviceToHost, st));
-        if (want_rgba) VK_CUDA(cudaMemcpyAsync(rgba_out, d_rgba, (size_t)r.n_out * 4, cudaMemcpyDeviceToHost, st));
-    }
+    if (hits_host && !h_hits_mapped && !direct_to_host && !linewise) VK_CUDA(cudaMemcpyAsync(hits_out, d_hits0, (size_t)r.n_out * sizeof(VkhrtHit), cudaMemcpyDeviceToHost, st));
+    if (rgba_host) VK_CUDA(cudaMemcpyAsync(rgba_out, d_rgba, (size_t)r.n_out * 4, cudaMemcpyDeviceToHost, st));
     VK_CUDA(cudaEventRecord(ev[11], st));
     if (stats) {
         unsigned long long c[16];
@@ -1579,7 +1588,8 @@ int render_frame(DeviceScene& sc, const VkhrtFrameDesc& f, VkhrtHit* hits_out, u
     }
     // host outputs: the call returns when the copies have landed.  Device outputs on the scene's own stream (no caller
     // stream): the caller has no handle to order against, so the call is synchronous too, like vkhrt_trace_rays.
-    if (host_out || !f.stream) VK_CUDA(cudaStreamSynchronize(st));
+    // opts.defer_sync: the caller (vkhrt_render_multi) waits for all its shards at once.
+    if (!opts.defer_sync && (any_host || host_frame || !f.stream)) VK_CUDA(cudaStreamSynchronize(st));
     VK_CUDA(cudaGetLastError());
     return VKHRT_OK;
 }
