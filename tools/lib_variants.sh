@@ -10,7 +10,7 @@ cp $L/libvkhrt_b200.so $L/libvkhrt_b200.so.default
 for v in "$@"; do
   cp $L/$v/libvkhrt_b200.so $L/libvkhrt_b200.so
   for wl in $wls; do
-    timeout 600 python bench.py --workload $wl --steps ${STEPS:-20} --warmup 5 --no-cpu-baseline > gpurun_out/${tag}_${v}_$wl.json 2> gpurun_out/${tag}_${v}_$wl.err
+    timeout 600 python bench.py --workload $wl --steps ${STEPS:-20} --warmup 5 --no-cpu-baseline --no-parity --no-strong-c5 > gpurun_out/${tag}_${v}_$wl.json 2> gpurun_out/${tag}_${v}_$wl.err
     python tools/variant_line.py "$v $wl" gpurun_out/${tag}_${v}_$wl.json
   done
 done

@@ -5,6 +5,6 @@ mkdir -p gpurun_out
 i=0
 for v in "$@"; do
   i=$((i+1))
-  env $v timeout 600 python bench.py --workload $wl --steps ${STEPS:-20} --warmup 5 --no-cpu-baseline > gpurun_out/${tag}_v$i.json 2> gpurun_out/${tag}_v$i.err
+  env $v timeout 600 python bench.py --workload $wl --steps ${STEPS:-20} --warmup 5 --no-cpu-baseline --no-parity --no-strong-c5 > gpurun_out/${tag}_v$i.json 2> gpurun_out/${tag}_v$i.err
   python tools/variant_line.py "$v" gpurun_out/${tag}_v$i.json
 done

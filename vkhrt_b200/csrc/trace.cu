@@ -798,8 +798,8 @@ struct PoolWarp2 {
                                        // every push costs more than one LDS)
 };
 
-template <bool STATS, int PL_S, int PL_STK>
-__global__ void __launch_bounds__(TR_BLOCK, PL_MINB) trace_pool2_kernel(const TraceParams p)
+template <bool STATS, int PL_S, int PL_STK, int MINB = PL_MINB>
+__global__ void __launch_bounds__(TR_BLOCK, MINB) trace_pool2_kernel(const TraceParams p)
 {
     __shared__ PoolWarp2<PL_S, PL_STK> sh_all[TR_BLOCK / 32];
     if (blockIdx.x == 0 && threadIdx.x == 0) *p.work_next = 0ull;
@@ -1377,12 +1377,12 @@ static int launch_pool_t(DeviceScene& sc, TraceParams& p, cudaStream_t st)
     count_launch();
     return VKHRT_OK;
 }
-template <bool STATS, int PL_S, int PL_STK>
+template <bool STATS, int PL_S, int PL_STK, int MINB = PL_MINB>
 static int launch_pool2_t(DeviceScene& sc, TraceParams& p, cudaStream_t st)
 {
     const int carve = tun().carveout;
-    if (carve >= 0) VK_CUDA(cudaFuncSetAttribute(trace_pool2_kernel<STATS, PL_S, PL_STK>, cudaFuncAttributePreferredSharedMemoryCarveout, carve));
-    int per_sm = blocks_per_sm(trace_pool2_kernel<STATS, PL_S, PL_STK>, sc.device);
+    if (carve >= 0) VK_CUDA(cudaFuncSetAttribute(trace_pool2_kernel<STATS, PL_S, PL_STK, MINB>, cudaFuncAttributePreferredSharedMemoryCarveout, carve));
+    int per_sm = blocks_per_sm(trace_pool2_kernel<STATS, PL_S, PL_STK, MINB>, sc.device);
     if (tun().blocks_per_sm > 0) per_sm = std::min(per_sm, tun().blocks_per_sm);
     unsigned long long want = ((unsigned long long)(p.n_slots - p.slot_begin) + TR_BLOCK - 1) / TR_BLOCK;
     unsigned grid = (unsigned)std::min<unsigned long long>((unsigned long long)sc.sm_count * per_sm, std::max<unsigned long long>(want, 1ull));
@@ -1394,7 +1394,7 @@ static int launch_pool2_t(DeviceScene& sc, TraceParams& p, cudaStream_t st)
         sc.pool_overflow_n = ovf;
     }
     p.pool_overflow = sc.d_pool_overflow;
-    trace_pool2_kernel<STATS, PL_S, PL_STK><<<grid, TR_BLOCK, 0, st>>>(p);
+    trace_pool2_kernel<STATS, PL_S, PL_STK, MINB><<<grid, TR_BLOCK, 0, st>>>(p);
     sc.last_trace_was_pool = true;
     count_launch();
     return VKHRT_OK;
@@ -1406,6 +1406,9 @@ static int launch_pool(DeviceScene& sc, TraceParams& p, cudaStream_t st)
         switch (tun().pool_cfg) {
         case 1: return launch_pool2_t<STATS, 56, 8>(sc, p, st);
         case 2: return launch_pool2_t<STATS, 64, 6>(sc, p, st);
+        case 3: return launch_pool2_t<STATS, 64, 4, 9>(sc, p, st);      // 9 CTAs / SM: 56 registers
+        case 4: return launch_pool2_t<STATS, 56, 4, 10>(sc, p, st);     // 10 CTAs / SM: 48 registers
+        case 5: return launch_pool2_t<STATS, 48, 4, 12>(sc, p, st);     // 12 CTAs / SM: 40 registers
         default: return launch_pool2_t<STATS, 72, 4>(sc, p, st);
         }
     }

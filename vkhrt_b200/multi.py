@@ -7,7 +7,9 @@ so the only communication is the final gather of the shards.  Rank r traces tile
   "peer"   (default on GPUs) the gathering rank's full-frame buffers are mapped into every rank (CUDA IPC) and each
            rank's traversal kernel stores its hit records / pixels straight to their row-major position over NVLink
            (VkhrtFrameDesc.row_major_output): the kernel's own stores are the gather, overlapped with the traversal;
-           a 4-byte NCCL all_reduce per frame is the completion signal.
+           a 4-byte NCCL all_reduce per frame is the completion signal.  There are TWO sets of frame buffers, used by
+           alternate frames: the tensors render() returns stay valid while the next frame is being rendered (no rank
+           can store into them before the frame after next), so the consumer needs no "I am done reading" signal.
   "gather" every rank writes a compact shard, all_gather (NCCL; gloo in the CPU tests) concatenates them rank-major,
            vkhrt_untile (CUDA) / untile_host (numpy mirror) restores row-major order.
 
@@ -102,11 +104,16 @@ class ShardedRenderer:
                 self.o_rgba = torch.empty((n_full, 4), dtype=torch.uint8, device=self.device)
         else:
             self.o_hits, self.o_rgba = self.d_hits, self.d_rgba
+        self.hits_ptr = self.d_hits.data_ptr()
+        self.rgba_ptr = self.d_rgba.data_ptr() if want_rgba else None
+
+    N_BUFFERS = 2      # peer mode: frame k lives in buffer set k % 2
 
     def _setup_peer(self, n_full):
         torch, dist = self.torch, self.dist
         dev = self.device.index
-        sizes = [n_full * 32] + ([n_full * 4] if self.want_rgba else [])
+        per_set = [n_full * 32] + ([n_full * 4] if self.want_rgba else [])
+        sizes = per_set * self.N_BUFFERS
         ok = 1
         handles = [None]
         if self.rank == self.gather_rank:
@@ -128,12 +135,16 @@ class ShardedRenderer:
         if int(flag.item()) == 0:
             self.close()
             raise RuntimeError("CUDA IPC mapping of the gathering rank's frame buffer failed on at least one rank")
-        self.hits_ptr = self._shared[0].ptr
-        self.rgba_ptr = self._shared[1].ptr if self.want_rgba else None
+        k = len(per_set)
+        self._frame_index = 0
+        self._hits_ptrs = [self._shared[b * k].ptr for b in range(self.N_BUFFERS)]
+        self._rgba_ptrs = [self._shared[b * k + 1].ptr if self.want_rgba else None for b in range(self.N_BUFFERS)]
         self._done = torch.zeros(1, dtype=torch.int32, device=self.device)
-        self.o_hits = torch.as_tensor(_DeviceView(self.hits_ptr, (n_full, 32)), device=self.device) if self.rank == self.gather_rank else None
-        if self.want_rgba and self.rank == self.gather_rank:
-            self.o_rgba = torch.as_tensor(_DeviceView(self.rgba_ptr, (n_full, 4)), device=self.device)
+        mine = self.rank == self.gather_rank
+        self._o_hits = [torch.as_tensor(_DeviceView(q, (n_full, 32)), device=self.device) if mine else None for q in self._hits_ptrs]
+        self._o_rgba = [torch.as_tensor(_DeviceView(q, (n_full, 4)), device=self.device) if (mine and self.want_rgba) else None for q in self._rgba_ptrs]
+        self.hits_ptr, self.rgba_ptr = self._hits_ptrs[0], self._rgba_ptrs[0]
+        self.o_hits, self.o_rgba = self._o_hits[0], self._o_rgba[0]
 
     def close(self):
         for sb in self._shared:
@@ -150,6 +161,15 @@ class ShardedRenderer:
         """Trace this rank's tiles and assemble the frame on the gathering rank.  Everything is enqueued on `stream`
         (a raw cudaStream_t that must be torch's current stream so the NCCL call orders after the kernel)."""
         if self.mode == "peer":
+            # Frame k goes to buffer set k % 2.  The all_reduce of frame k completes on a rank only after EVERY rank has enqueued
+            # its own (after its frame-k kernel), and a rank's frame-(k+1) kernel is ordered after its frame-k all_reduce; so
+            # when any rank starts storing frame k+2 into this set again, the gathering rank's stream is past frame k+1's
+            # all_reduce, i.e. past everything it enqueued to read frame k.  The returned tensors are therefore valid until the
+            # call after next (consume them on `stream`, or copy them, before rendering two more frames).
+            b = self._frame_index % self.N_BUFFERS
+            self._frame_index += 1
+            self.hits_ptr, self.rgba_ptr = self._hits_ptrs[b], self._rgba_ptrs[b]
+            self.o_hits, self.o_rgba = self._o_hits[b], self._o_rgba[b]
             self.scene.render_into(frame, self.hits_ptr, self.rgba_ptr)
             self.dist.all_reduce(self._done, group=self.group)       # stream-ordered "every shard has landed" signal
             return self.o_hits, self.o_rgba
@@ -161,3 +181,52 @@ class ShardedRenderer:
                 self.dist.all_gather_into_tensor(self.g_rgba, self.d_rgba, group=self.group)
                 _api.untile(self._full, self.world, self.g_rgba.data_ptr(), self.o_rgba.data_ptr(), 4, stream)
         return self.o_hits, self.o_rgba
+
+
+class SharedHostFrame:
+    """ONE page-locked host frame that every rank's GPU stores its hit records into (the N > 1 end-to-end path).
+
+    The gathering rank creates a POSIX shared-memory segment, every rank maps it and registers it with CUDA
+    (cudaHostRegister, portable + mapped).  vkhrt_render with output_memory = HOST, row_major_output = 1 then stores
+    each rank's records at their row-major position over that rank's own PCIe link (zero-copy / line-wise delivery,
+    DESIGN.md §6): after a barrier the gathering rank holds the assembled frame in host memory — no staging, no copy.
+    """
+
+    def __init__(self, n_records, group=None, gather_rank=0):
+        import torch
+        import torch.distributed as dist
+        from multiprocessing import shared_memory
+        self.torch, self.dist, self.group = torch, dist, group
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.nbytes = int(n_records) * 32
+        self.owner = self.rank == gather_rank
+        name = [None]
+        if self.owner:
+            self.shm = shared_memory.SharedMemory(create=True, size=self.nbytes)
+            name = [self.shm.name]
+        if self.world > 1:
+            dist.broadcast_object_list(name, src=gather_rank, group=group)
+        if not self.owner:
+            self.shm = shared_memory.SharedMemory(name=name[0])
+        self.array = np.frombuffer(self.shm.buf, dtype=np.uint8, count=self.nbytes)
+        self.ptr = self.array.ctypes.data
+        rc = torch.cuda.cudart().cudaHostRegister(self.ptr, self.nbytes, 1 | 2)      # cudaHostRegisterPortable | Mapped
+        if int(rc) != 0:
+            raise RuntimeError(f"cudaHostRegister of the shared host frame failed: {rc}")
+        self.registered = True
+
+    def hits(self):
+        return self.array.view(_api.HIT_DTYPE)
+
+    def close(self):
+        if getattr(self, "registered", False):
+            self.torch.cuda.cudart().cudaHostUnregister(self.ptr)
+            self.registered = False
+        self.array = None
+        try:
+            self.shm.close()
+            if self.owner:
+                self.shm.unlink()
+        except Exception:
+            pass
