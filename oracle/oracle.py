@@ -87,6 +87,8 @@ def lib():
         L.orc_ao_direction.argtypes = [fp, C.c_uint32, C.c_uint32, C.c_uint32, fp]
         L.orc_prhi.restype = C.c_int
         L.orc_prhi.argtypes = [fp, fp, fp, C.c_float, fp, fp, fp]
+        L.orc_prhi_taper.restype = C.c_int
+        L.orc_prhi_taper.argtypes = [fp, fp, fp, C.c_float, C.c_float, fp, fp, fp]
         L.orc_ray_cylinder.restype = C.c_int
         L.orc_ray_cylinder.argtypes = [fp, fp, fp, fp, C.c_float]
         L.orc_lss.restype = C.c_int
@@ -274,6 +276,15 @@ def prhi(ro, rd, curve, radius=0.02):
     t, u = C.c_float(), C.c_float()
     n = (C.c_float * 3)()
     it = lib().orc_prhi(pro, prd, pc, radius, C.byref(t), C.byref(u), n)
+    return float(t.value), float(u.value), np.array(list(n), np.float32), int(it)
+
+
+def prhi_taper(ro, rd, curve, r0, r1):
+    """Prhi with the radius running linearly from r0 (t = 0) to r1 (t = 1): cone.radius = r(t), cone.slant = r1 - r0"""
+    _, pro = _f(ro); _, prd = _f(rd); _, pc = _f(np.asarray(curve).reshape(12))
+    t, u = C.c_float(), C.c_float()
+    n = (C.c_float * 3)()
+    it = lib().orc_prhi_taper(pro, prd, pc, r0, r1, C.byref(t), C.byref(u), n)
     return float(t.value), float(u.value), np.array(list(n), np.float32), int(it)
 
 

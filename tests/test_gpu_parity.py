@@ -235,6 +235,41 @@ def test_lss_per_vertex_radius(V, O, small_groom):
         assert np.array_equal(ig, io)
 
 
+@pytest.mark.parametrize("tech", TECHS)
+def test_per_vertex_radius_all_techniques(V, O, small_groom, tech):
+    """north_star input contract: polyline strands with PER-VERTEX radius.  Taper 0.02 -> 0.005 along every strand:
+    Phantom = radius(t) + cone slant (cone.glsl:27), DOTS = per-end offsets, LSS = per-end sphere radii.
+    Primitives, BVH nodes, hit records, images and counters against the oracle; and a constant per-vertex array must give
+    exactly the default-radius scene."""
+    pos, idx = small_groom
+    W, H = 256, 160
+    vi, pi = default_camera(V, W, H)
+    taper = np.tile(np.linspace(0.02, 0.005, 17, dtype=np.float32), 2000)
+    with V.Scene(pos, idx, technique=tech, radius_per_vertex=taper) as sc:
+        sc.build()
+        orc = O.OracleScene(pos, idx, technique=tech, radius_per_vertex=taper)
+        assert np.array_equal(sc.primitives().view(np.uint32), orc.primitives().view(np.uint32))
+        assert sc.bvh()[0].tobytes() == orc.bvh()[0].tobytes()
+        for spp, ao in ((1, 0), (2, 2)):
+            hg, ig, sg = sc.render(V.make_frame(vi, pi, W, H, spp=spp, ao_samples=ao), stats=True)
+            ho, io, so = orc.render(O.make_frame(vi, pi, W, H, spp=spp, ao_samples=ao), stats=True)
+            assert (ho["flags"] & 1).sum() > 1000
+            assert_bit_identical(hg, ho)
+            assert np.array_equal(ig, io)
+            assert sg["nodes_visited"] == so["nodes_visited"] and sg["prims_tested"] == so["prims_tested"]
+        # thinner hair is hit less often than the default 0.02 everywhere
+        with V.Scene(pos, idx, technique=tech) as ref:
+            ref.build()
+            h_ref, i_ref, _ = ref.render(V.make_frame(vi, pi, W, H))
+        h_tap, _, _ = sc.render(V.make_frame(vi, pi, W, H))
+        assert (h_tap["flags"] & 1).sum() < (h_ref["flags"] & 1).sum()
+    const = np.full(pos.shape[0], 0.02, np.float32)
+    with V.Scene(pos, idx, technique=tech, radius_per_vertex=const) as sc:
+        sc.build()
+        hc, ic, _ = sc.render(V.make_frame(vi, pi, W, H))
+        assert hc.tobytes() == h_ref.tobytes() and np.array_equal(ic, i_ref)
+
+
 def test_stats_counters_equal_the_oracles(V, O, small_groom):
     """The warp scheduler only interleaves lanes; each ray's own sequence of node visits and candidate tests is the
     oracle's, so the traversal counters (the N_int / N_prim of the bytes-per-ray roofline) are IDENTICAL."""

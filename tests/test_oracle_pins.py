@@ -517,3 +517,50 @@ def test_oracle_build_is_thread_count_independent(O):
         env = dict(os.environ, OMP_NUM_THREADS=nt)
         outs.add(subprocess.check_output([sys.executable, "-c", code], env=env).decode().strip())
     assert len(outs) == 1, outs
+
+
+def test_tapered_prhi_constant_radius_is_the_reference_loop(O):
+    """Per-vertex radius: with r0 == r1 the tapered Prhi must return the constant-radius bits (cone.slant = 0, as the reference calls it)."""
+    rng = np.random.default_rng(7)
+    curve = np.array([[0, 0, 0], [1 / 3, 0.02, 0], [2 / 3, -0.02, 0.01], [1, 0, 0]], np.float32)
+    for _ in range(200):
+        o = np.array([rng.uniform(0, 1), rng.uniform(-0.03, 0.03), 20.0], np.float32)
+        d = np.array([rng.uniform(-0.01, 0.01), rng.uniform(-0.01, 0.01), -1.0], np.float32)
+        d /= np.linalg.norm(d).astype(np.float32)
+        a = O.prhi(o, d, curve, 0.02)
+        b = O.prhi_taper(o, d, curve, 0.02, 0.02)
+        assert np.float32(a[0]).tobytes() == np.float32(b[0]).tobytes() and np.float32(a[1]).tobytes() == np.float32(b[1]).tobytes()
+        assert a[2].tobytes() == b[2].tobytes() and a[3] == b[3]
+
+
+def test_tapered_prhi_vs_analytic_cone(O):
+    """Straight curve (0,0,0)->(1,0,0) with radius 0.02 -> 0.005: the surface is the cone |yz| = r(x) = 0.02 - 0.015 x.
+    fp64 analytic ray/cone roots are the pin (the reference only ever runs slant = 0)."""
+    curve = np.array([[0, 0, 0], [1 / 3, 0, 0], [2 / 3, 0, 0], [1, 0, 0]], np.float32)
+    r0, r1 = 0.02, 0.005
+    rng = np.random.default_rng(11)
+    hits = close = 0
+    for _ in range(600):
+        o = np.array([rng.uniform(0.05, 0.95), rng.uniform(-0.025, 0.025), 5.0], np.float64)
+        d = np.array([rng.uniform(-0.02, 0.02), rng.uniform(-0.002, 0.002), -1.0], np.float64)
+        d /= np.linalg.norm(d)
+        # |(y, z)(s)|^2 = r(x(s))^2, r(x) = r0 + (r1 - r0) x
+        k = r1 - r0
+        A = d[1] ** 2 + d[2] ** 2 - (k * d[0]) ** 2
+        B = 2 * (o[1] * d[1] + o[2] * d[2] - k * d[0] * (r0 + k * o[0]))
+        Cq = o[1] ** 2 + o[2] ** 2 - (r0 + k * o[0]) ** 2
+        disc = B * B - 4 * A * Cq
+        t_ref = None
+        if disc > 0:
+            s = (-B - np.sqrt(disc)) / (2 * A)
+            x = o[0] + s * d[0]
+            if 0.0 < x < 1.0 and s > 0:
+                t_ref = s
+        t, u, n, _ = O.prhi_taper(o.astype(np.float32), d.astype(np.float32), curve, r0, r1)
+        if t_ref is not None and disc > 1e-7:          # clear of grazing
+            hits += 1
+            if t > 0 and abs(t - t_ref) / t_ref < 1e-4:
+                close += 1
+                x = o[0] + t_ref * d[0]
+                assert abs(u - x) < 2e-3            # curve parameter == x on this curve (the cone's axial offset is second order)
+    assert hits > 100 and close >= 0.97 * hits, (hits, close)

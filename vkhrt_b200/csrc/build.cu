@@ -31,6 +31,12 @@ VK_DEV float3 load_pos(const MeshIn& m, uint32_t v) { return f3(m.pos[3 * v], m.
 VK_DEV bool same_point(float3 a, float3 b) { return a.x == b.x && a.y == b.y && a.z == b.z; }   // glm::vec3 ==
 
 struct Aabb { float3 lo, hi; };
+// radii at the two ends of segment i: per-vertex when given (north_star: "polyline strands with per-vertex radius in"), else the scene's
+VK_DEV void segment_radii(const MeshIn& m, uint32_t i, float* r0, float* r1)
+{
+    *r0 = m.rpv ? m.rpv[m.idx[2 * i]] : m.radius;
+    *r1 = m.rpv ? m.rpv[m.idx[2 * i + 1]] : m.radius;
+}
 
 // GenerateCurves (geometry_processor.cpp:123-156), tension 1, for segment i
 VK_DEV Bezier gen_curve(const MeshIn& m, uint32_t i)
@@ -112,10 +118,12 @@ VK_DEV TriPrim gen_tri(const MeshIn& m, uint32_t prim)
     float3 fwd = normalize3(e - s);
     float3 sv = perp_stark(fwd);
     float3 v = face ? cross3(fwd, sv) : sv;
-    float3 off = v * m.radius;
+    float r0, r1;
+    segment_radii(m, seg, &r0, &r1);
+    float3 offs = v * r0, offe = v * r1;
     TriPrim t;
-    if (k == 0) { t.v0 = s + off; t.v1 = e - off; t.v2 = e + off; }
-    else        { t.v0 = s + off; t.v1 = s - off; t.v2 = e - off; }
+    if (k == 0) { t.v0 = s + offs; t.v1 = e - offe; t.v2 = e + offe; }
+    else        { t.v0 = s + offs; t.v1 = s - offs; t.v2 = e - offe; }
     return t;
 }
 VK_DEV Aabb tri_box(const TriPrim& t)
@@ -168,14 +176,18 @@ VK_DEV Aabb strip_piece_box(const MeshIn& m, uint32_t seg, uint32_t piece)
 {
     float3 s = load_pos(m, m.idx[2 * seg]), e = load_pos(m, m.idx[2 * seg + 1]);
     float3 fwd = normalize3(e - s);
-    float3 sv = perp_stark(fwd);
-    float3 off0 = sv * m.radius, off1 = cross3(fwd, sv) * m.radius;
+    float3 sv = perp_stark(fwd), tv = cross3(fwd, sv);
     float a = (float)piece / (float)K, bb = (float)(piece + 1u) / (float)K;
+    float r0, r1;
+    segment_radii(m, seg, &r0, &r1);
+    float dr = r1 - r0;
+    float ra = r0 + dr * a, rb = r0 + dr * bb;       // the strip's edges are straight: its half-width is linear along the segment
     float3 se = e - s;
     float3 A = s + se * a, B = s + se * bb;
-    Aabb b; b.lo = A + off0; b.hi = b.lo;
-    grow_box(b, A - off0); grow_box(b, A + off1); grow_box(b, A - off1);
-    grow_box(b, B + off0); grow_box(b, B - off0); grow_box(b, B + off1); grow_box(b, B - off1);
+    float3 a0 = sv * ra, a1 = tv * ra, b0 = sv * rb, b1 = tv * rb;
+    Aabb b; b.lo = A + a0; b.hi = b.lo;
+    grow_box(b, A - a0); grow_box(b, A + a1); grow_box(b, A - a1);
+    grow_box(b, B + b0); grow_box(b, B - b0); grow_box(b, B + b1); grow_box(b, B - b1);
     return pad_box(b, piece_guard(b));
 }
 // piece `piece` of K equal parts of a linear swept sphere: the two end spheres of the part (radius is linear along the segment)
@@ -200,7 +212,11 @@ VK_DEV Aabb leaf_box(const MeshIn& m, uint32_t leaf)
 {
     constexpr uint32_t K = LeafSplit<TECH>::K;
     const uint32_t group = leaf / K, piece = leaf % K;
-    if (TECH == VKHRT_TECHNIQUE_PHANTOM) return curve_piece_box<(int)K>(gen_curve(m, group), piece, m.radius);
+    if (TECH == VKHRT_TECHNIQUE_PHANTOM) {
+        float r0, r1;
+        segment_radii(m, group, &r0, &r1);
+        return curve_piece_box<(int)K>(gen_curve(m, group), piece, fmaxf(r0, r1));       // the curve's larger end radius
+    }
     if (TECH == VKHRT_TECHNIQUE_LSS) return lss_piece_box<(int)K>(gen_lss(m, group), piece);
     if (K > 1) return strip_piece_box<(int)K>(m, group, piece);
     Aabb b = tri_box(gen_tri(m, 4u * group));
@@ -464,7 +480,7 @@ __global__ void __launch_bounds__(256) karras_kernel(const uint64_t* __restrict_
 // ------------------------------------------------------------------------------------------------
 template <int TECH>
 __global__ void __launch_bounds__(256) materialise_refit_kernel(MeshIn m, uint32_t n_prims, const uint32_t* __restrict__ sorted_ids,
-                                                                float4* __restrict__ primA, float4* __restrict__ primB,
+                                                                float4* __restrict__ primA, float4* __restrict__ primB, float2* __restrict__ primR,
                                                                 float* nodes_f32, const uint32_t* __restrict__ parent_internal,
                                                                 const uint32_t* __restrict__ parent_leaf, uint32_t* flags)
 {
@@ -476,12 +492,16 @@ __global__ void __launch_bounds__(256) materialise_refit_kernel(MeshIn m, uint32
     Aabb box;
     if (TECH == VKHRT_TECHNIQUE_PHANTOM) {
         Bezier c = gen_curve(m, prim);
-        box = curve_piece_box<(int)LeafSplit<TECH>::K>(c, leaf % LeafSplit<TECH>::K, m.radius);
-        float rmax = bezier_bound_radius(c, m.radius);
+        float r0, r1;
+        segment_radii(m, prim, &r0, &r1);
+        const float rbig = fmaxf(r0, r1);
+        box = curve_piece_box<(int)LeafSplit<TECH>::K>(c, leaf % LeafSplit<TECH>::K, rbig);
+        float rmax = bezier_bound_radius(c, rbig);
         primA[2 * (size_t)pos] = make_float4(c.p0.x, c.p0.y, c.p0.z, rmax);
         primA[2 * (size_t)pos + 1] = make_float4(c.p3.x, c.p3.y, c.p3.z, __uint_as_float(prim));
-        primB[2 * (size_t)pos] = make_float4(c.p1.x, c.p1.y, c.p1.z, bezier_quarter_chord_deviation(c) + bezier_convergence_slack(c, m.radius));
+        primB[2 * (size_t)pos] = make_float4(c.p1.x, c.p1.y, c.p1.z, bezier_quarter_chord_deviation(c) + bezier_convergence_slack(c, fminf(r0, r1)));
         primB[2 * (size_t)pos + 1] = make_float4(c.p2.x, c.p2.y, c.p2.z, 0.0f);
+        if (primR) primR[pos] = make_float2(r0, r1);
     } else if (TECH == VKHRT_TECHNIQUE_LSS) {
         LssPrim s = gen_lss(m, prim);
         box = lss_piece_box<(int)LeafSplit<TECH>::K>(s, leaf % LeafSplit<TECH>::K);
@@ -494,11 +514,21 @@ __global__ void __launch_bounds__(256) materialise_refit_kernel(MeshIn m, uint32
         float3 s = load_pos(m, m.idx[2 * prim]), e = load_pos(m, m.idx[2 * prim + 1]);
         float3 fwd = normalize3(e - s);
         float3 sv = perp_stark(fwd);
-        float3 off0 = sv * m.radius, off1 = cross3(fwd, sv) * m.radius;
+        float3 tv = cross3(fwd, sv);
         primA[4 * (size_t)pos] = make_float4(s.x, s.y, s.z, __uint_as_float(prim));
         primA[4 * (size_t)pos + 1] = make_float4(e.x, e.y, e.z, 0.0f);
-        primA[4 * (size_t)pos + 2] = make_float4(off0.x, off0.y, off0.z, 0.0f);
-        primA[4 * (size_t)pos + 3] = make_float4(off1.x, off1.y, off1.z, 0.0f);
+        if (m.rpv) {
+            // per-vertex radius: the record keeps the unit frame vectors and the two end radii; the kernel forms the offsets
+            // v * r0 / v * r1 with the one multiply gen_tri() performs
+            float r0, r1;
+            segment_radii(m, prim, &r0, &r1);
+            primA[4 * (size_t)pos + 2] = make_float4(sv.x, sv.y, sv.z, r0);
+            primA[4 * (size_t)pos + 3] = make_float4(tv.x, tv.y, tv.z, r1);
+        } else {
+            float3 off0 = sv * m.radius, off1 = tv * m.radius;
+            primA[4 * (size_t)pos + 2] = make_float4(off0.x, off0.y, off0.z, 0.0f);
+            primA[4 * (size_t)pos + 3] = make_float4(off1.x, off1.y, off1.z, 0.0f);
+        }
     }
     if (n_prims == 1) {   // single primitive: node 0 holds the same leaf in both slots
         float* nd = nodes_f32;
@@ -585,7 +615,8 @@ int build_scene(DeviceScene& sc, bool refit_only)
         auto up = [](size_t x) { return (x + 255) & ~(size_t)255; };
         const size_t o_nodes = 0, o_ids = o_nodes + up((size_t)sc.n_nodes * 64), o_morton = o_ids + up((size_t)n * 4), o_pint = o_morton + up((size_t)n * 8),
                      o_pleaf = o_pint + up((size_t)sc.n_nodes * 4), o_flags = o_pleaf + up((size_t)n * 4), o_primA = o_flags + up((size_t)sc.n_nodes * 4),
-                     o_primB = o_primA + up((size_t)n * primA_per * 16), total = o_primB + (tech == VKHRT_TECHNIQUE_PHANTOM ? up((size_t)n * 32) : 0);
+                     o_primB = o_primA + up((size_t)n * primA_per * 16), o_primR = o_primB + (tech == VKHRT_TECHNIQUE_PHANTOM ? up((size_t)n * 32) : 0),
+                     total = o_primR + ((tech == VKHRT_TECHNIQUE_PHANTOM && sc.d_radius_pv) ? up((size_t)n * 8) : 0);
         if (sc.arena_bytes < total) {
             if (sc.d_arena) cudaFree(sc.d_arena);
             sc.d_arena = nullptr; sc.arena_bytes = 0;
@@ -596,6 +627,7 @@ int build_scene(DeviceScene& sc, bool refit_only)
         sc.d_parent_internal = (uint32_t*)(sc.d_arena + o_pint); sc.d_parent_leaf = (uint32_t*)(sc.d_arena + o_pleaf);
         sc.d_refit_flags = (uint32_t*)(sc.d_arena + o_flags); sc.d_primA = (float4*)(sc.d_arena + o_primA);
         sc.d_primB = tech == VKHRT_TECHNIQUE_PHANTOM ? (float4*)(sc.d_arena + o_primB) : nullptr;
+        sc.d_primR = (tech == VKHRT_TECHNIQUE_PHANTOM && sc.d_radius_pv) ? (float2*)(sc.d_arena + o_primR) : nullptr;
 
         // ... and one for the build's scratch
         const uint32_t rs_blocks = cdiv(n, RS_TILE);
@@ -663,11 +695,11 @@ int build_scene(DeviceScene& sc, bool refit_only)
     VK_CUDA(cudaMemsetAsync(sc.d_refit_flags, 0, (size_t)sc.n_nodes * 4, st));
     const uint32_t g = cdiv(n, 256);
     if (tech == VKHRT_TECHNIQUE_PHANTOM)
-        materialise_refit_kernel<VKHRT_TECHNIQUE_PHANTOM><<<g, 256, 0, st>>>(m, n, sc.d_sorted_ids, sc.d_primA, sc.d_primB, (float*)sc.d_nodes, sc.d_parent_internal, sc.d_parent_leaf, sc.d_refit_flags);
+        materialise_refit_kernel<VKHRT_TECHNIQUE_PHANTOM><<<g, 256, 0, st>>>(m, n, sc.d_sorted_ids, sc.d_primA, sc.d_primB, sc.d_primR, (float*)sc.d_nodes, sc.d_parent_internal, sc.d_parent_leaf, sc.d_refit_flags);
     else if (tech == VKHRT_TECHNIQUE_LSS)
-        materialise_refit_kernel<VKHRT_TECHNIQUE_LSS><<<g, 256, 0, st>>>(m, n, sc.d_sorted_ids, sc.d_primA, sc.d_primB, (float*)sc.d_nodes, sc.d_parent_internal, sc.d_parent_leaf, sc.d_refit_flags);
+        materialise_refit_kernel<VKHRT_TECHNIQUE_LSS><<<g, 256, 0, st>>>(m, n, sc.d_sorted_ids, sc.d_primA, sc.d_primB, sc.d_primR, (float*)sc.d_nodes, sc.d_parent_internal, sc.d_parent_leaf, sc.d_refit_flags);
     else
-        materialise_refit_kernel<VKHRT_TECHNIQUE_DOTS><<<g, 256, 0, st>>>(m, n, sc.d_sorted_ids, sc.d_primA, sc.d_primB, (float*)sc.d_nodes, sc.d_parent_internal, sc.d_parent_leaf, sc.d_refit_flags);
+        materialise_refit_kernel<VKHRT_TECHNIQUE_DOTS><<<g, 256, 0, st>>>(m, n, sc.d_sorted_ids, sc.d_primA, sc.d_primB, sc.d_primR, (float*)sc.d_nodes, sc.d_parent_internal, sc.d_parent_leaf, sc.d_refit_flags);
     count_launch();
     VK_CUDA(cudaEventRecord(ev[5], st));
     VK_CUDA(cudaStreamSynchronize(st));

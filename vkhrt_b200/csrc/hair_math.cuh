@@ -242,6 +242,7 @@ struct MarchState {
     float t, told, dt1, dt2;
     float t_start;
     uint32_t it;         // bits 0..3: iteration i of this side; bit 4: side
+    float r0, dr;        // per-vertex radius (TAPER kernels only): radius(t) = r0 + t * dr, cone slant = dr
 };
 enum MarchResult { MARCH_CONTINUE = 0, MARCH_HIT = 1, MARCH_NOTHING = 2 };
 
@@ -264,12 +265,15 @@ VK_DEV void march_begin(MarchState& m, const RayFrame& fr, float3 o, const Bezie
 // A side is also left when the march has reached an exact fp32 fixed point (t + dt == t on the plain-step
 // branch): every later iteration of that side would recompute the very same state, so the outcome is
 // unchanged.
+// TAPER: the curve's radius runs linearly from r0 (t = 0) to r0 + dr (t = 1): cone.radius = r(t), cone.slant = dr/dt = dr, the taper
+// term of cone.glsl:27 (`drr = radius * slant`) that the reference's caller leaves at 0 (hair_intersection.rint:62).
+template <bool TAPER = false>
 VK_DEV int march_step(MarchState& m, float radius, float* t_hit, float* u_hit)
 {
     const uint32_t i = m.it & 15u;
     float3 centre = bezier_point(m.c, m.t);
     float3 axis = bezier_axis(m.c, m.t);
-    ConeStep cs = cone_step(centre, radius, axis, 0.0f);
+    ConeStep cs = TAPER ? cone_step(centre, fmaf(m.t, m.dr, m.r0), axis, m.dr) : cone_step(centre, radius, axis, 0.0f);
     if (cs.real && fabsf(cs.dt) < 5e-5f) {
         *t_hit = cs.s + centre.z;
         *u_hit = m.t;
@@ -381,6 +385,13 @@ VK_DEV void strip_triangle(float3 s, float3 e, float3 off, uint32_t k, float3* v
     *v0 = s + off;
     if (k == 0u) { *v1 = e - off; *v2 = e + off; }
     else         { *v1 = s - off; *v2 = e - off; }
+}
+// per-vertex radius: the offsets at the start / end vertices are v * r0 / v * r1
+VK_DEV void strip_triangle_taper(float3 s, float3 e, float3 offs, float3 offe, uint32_t k, float3* v0, float3* v1, float3* v2)
+{
+    *v0 = s + offs;
+    if (k == 0u) { *v1 = e - offe; *v2 = e + offe; }
+    else         { *v1 = s - offs; *v2 = e - offe; }
 }
 // Conservative strip reject (NOT in the reference; result-neutral by construction).  Every point of the four
 // triangles is (a point of the segment) + c * off_f with |c| <= 1 and |off_f| = r, so a ray that hits any of them

@@ -46,6 +46,10 @@ struct DeviceScene {
     //            primA[4p+2] = {v0*r, 0}, primA[4p+3] = {v1*r, 0}; the 12 strip vertices are start/end -+ these offsets
     float4* d_primA = nullptr;
     float4* d_primB = nullptr;
+    //   per-vertex radii (d_radius_pv != null): PHANTOM adds primR[p] = {r0, r1} of the curve's two ends; the DOTS record becomes
+    //   primA[4p+2] = {v0 (unit), r0}, primA[4p+3] = {v1 (unit), r1}; LSS already carries its radii
+    float2* d_primR = nullptr;
+    bool tapered() const { return d_radius_pv != nullptr && technique != VKHRT_TECHNIQUE_LSS; }
 
     // per-frame scratch (grown on demand)
     unsigned long long* d_counters = nullptr;   // [0], [6] alternating work counters (a launch zeroes the other one), [1..5] stats, [8..15] scheduler

@@ -26,6 +26,7 @@ struct TraceParams {
     const float4* nodes;
     const float4* primA;
     const float4* primB;
+    const float2* primR;            // per-vertex radius scenes (TAPER kernels): {r0, r1} per Phantom leaf position
     const uint32_t* sorted_ids;
     uint32_t n_prims;
     float radius;
@@ -130,7 +131,8 @@ enum : int { SRC_PRIMARY = 0,   // generated from the camera (ray_gen.rgen), fus
              SRC_AO = 2 };      // ambient-occlusion ray spawned from the pixel's primary hit record
 
 // ANYHIT: gl_RayFlagsTerminateOnFirstHitEXT — the ray retires on its first accepted hit (shadow / occlusion rays).
-template <int TECH, bool STATS, int SRC, bool ANYHIT, int MINB>
+// TAPER: the scene has per-vertex radii (Phantom: radius(t) linear along the curve, cone slant = r1 - r0; DOTS: per-end offsets)
+template <int TECH, bool STATS, int SRC, bool ANYHIT, int MINB, bool TAPER = false>
 __global__ void __launch_bounds__(TR_BLOCK, MINB) trace_kernel(const TraceParams p)
 {
     constexpr bool WAVEFRONT = SRC == SRC_BUFFER;
@@ -149,7 +151,7 @@ __global__ void __launch_bounds__(TR_BLOCK, MINB) trace_kernel(const TraceParams
     uint32_t last_group = PRIM_NONE;     // one-entry mailbox (VKHRT_MAILBOX_PHANTOM): the curve this ray tested last
     MarchState ms;
     ms.c.p0 = ms.c.p1 = ms.c.p2 = ms.c.p3 = f3(0, 0, 0);
-    ms.t = ms.told = ms.dt1 = ms.dt2 = ms.t_start = 0.0f; ms.it = 0u;
+    ms.t = ms.told = ms.dt1 = ms.dt2 = ms.t_start = 0.0f; ms.it = 0u; ms.r0 = ms.dr = 0.0f;
     uint32_t out_idx = 0, mpos = 0;
     int sp = 0;
     uint32_t cur = REF_NONE;
@@ -233,8 +235,10 @@ __global__ void __launch_bounds__(TR_BLOCK, MINB) trace_kernel(const TraceParams
                         // cylinder test (~2 per ray) is cheaper than keeping 9 registers alive through the node loop
                         march_begin(ms, make_ray_frame(d), o, w);
                         mpos = pos;
+                        float rfilter = p.radius;
+                        if (TAPER) { const float2 rr = __ldg(p.primR + pos); ms.r0 = rr.x; ms.dr = rr.y - rr.x; rfilter = fmaxf(rr.x, rr.y); }
                         // conservative filter (hair_math.cuh): skip marches that cannot report a hit
-                        state = quarter_chords_near_ray(ms.c, p.radius, b0.w) ? ST_MARCH : ST_POP;
+                        state = quarter_chords_near_ray(ms.c, rfilter, b0.w) ? ST_MARCH : ST_POP;
                     } else state = ST_POP;
                 } else if (TECH == VKHRT_TECHNIQUE_LSS) {
                     const float4 a0 = __ldg(p.primA + 2 * (size_t)pos), a1 = __ldg(p.primA + 2 * (size_t)pos + 1);
@@ -247,13 +251,16 @@ __global__ void __launch_bounds__(TR_BLOCK, MINB) trace_kernel(const TraceParams
                     const float4* rec = p.primA + 4 * (size_t)pos;
                     const float4 a0 = __ldg(rec), a1 = __ldg(rec + 1);
                     if (STATS) st_prims += 4;
-                    if (ray_near_strip_axis(o, d, xyz(a0), xyz(a1), p.radius)) {
-                        const float4 a2 = __ldg(rec + 2), a3 = __ldg(rec + 3);
+                    // per-vertex radius: the record's last two float4 are {v0 (unit), r0} {v1 (unit), r1}
+                    const float4 a2 = __ldg(rec + 2), a3 = __ldg(rec + 3);
+                    if (ray_near_strip_axis(o, d, xyz(a0), xyz(a1), TAPER ? fmaxf(a2.w, a3.w) : p.radius)) {
                         const uint32_t prim0 = __float_as_uint(a0.w) << 2;
 #pragma unroll 1
                         for (uint32_t k = 0; k < 4u; ++k) {
                             float3 v0, v1, v2;
-                            strip_triangle(xyz(a0), xyz(a1), (k & 2u) ? xyz(a3) : xyz(a2), k & 1u, &v0, &v1, &v2);
+                            const float3 fv = (k & 2u) ? xyz(a3) : xyz(a2);
+                            if (TAPER) strip_triangle_taper(xyz(a0), xyz(a1), fv * a2.w, fv * a3.w, k & 1u, &v0, &v1, &v2);
+                            else strip_triangle(xyz(a0), xyz(a1), fv, k & 1u, &v0, &v1, &v2);
                             float t, u;
                             if (tri_intersect(o, d, v0, v1, v2, k & 1u, &t, &u)) commit(t, u, prim0 + k, pos);
                             if (ANYHIT && best_prim != PRIM_NONE) break;
@@ -270,7 +277,7 @@ __global__ void __launch_bounds__(TR_BLOCK, MINB) trace_kernel(const TraceParams
                 if (state == ST_MARCH) {
                     if (STATS) st_iters++;
                     float t = 0.0f, u = 0.0f;
-                    const int r = march_step(ms, p.radius, &t, &u);
+                    const int r = march_step<TAPER>(ms, p.radius, &t, &u);
                     if (r != MARCH_CONTINUE) {
                         // hair_intersection.rint:146-148: report only tHit > 0
                         if (r == MARCH_HIT && t > 0.0f) commit(t, u, __float_as_uint(__ldg(p.primA + 2 * (size_t)mpos + 1).w), mpos);
@@ -306,7 +313,10 @@ __global__ void __launch_bounds__(TR_BLOCK, MINB) trace_kernel(const TraceParams
                         const float4* rec = p.primA + 4 * (size_t)best_pos;
                         const float4 a0 = __ldg(rec), a1 = __ldg(rec + 1), a2 = __ldg(rec + ((best_prim & 2u) ? 3 : 2));
                         float3 v0, v1, v2;
-                        strip_triangle(xyz(a0), xyz(a1), xyz(a2), best_prim & 1u, &v0, &v1, &v2);
+                        if (TAPER) {
+                            const float r0 = __ldg(rec + 2).w, r1 = __ldg(rec + 3).w;
+                            strip_triangle_taper(xyz(a0), xyz(a1), xyz(a2) * r0, xyz(a2) * r1, best_prim & 1u, &v0, &v1, &v2);
+                        } else strip_triangle(xyz(a0), xyz(a1), xyz(a2), best_prim & 1u, &v0, &v1, &v2);
                         n = tri_normal(d, v0, v1, v2);
                         seg = best_prim >> 2;
                     }
@@ -1262,7 +1272,7 @@ static void sample_offset(uint32_t s, float* sx, float* sy)
 
 static void fill_params(const DeviceScene& sc, const VkhrtFrameDesc& f, const Resolved& r, TraceParams& p)
 {
-    p.nodes = sc.d_nodes; p.primA = sc.d_primA; p.primB = sc.d_primB; p.sorted_ids = sc.d_sorted_ids;
+    p.nodes = sc.d_nodes; p.primA = sc.d_primA; p.primB = sc.d_primB; p.primR = sc.d_primR; p.sorted_ids = sc.d_sorted_ids;
     p.n_prims = sc.n_leaves; p.radius = sc.radius;
     memcpy(p.cam.vi, f.view_inverse, sizeof(p.cam.vi)); memcpy(p.cam.pi, f.proj_inverse, sizeof(p.cam.pi));
     p.W = r.W; p.H = r.H; p.sx = 0.5f; p.sy = 0.5f; p.tmin = r.tmin; p.tmax = r.tmax;
@@ -1343,15 +1353,15 @@ static void take_work_counter(DeviceScene& sc, TraceParams& p)
     sc.work_flip = !sc.work_flip;
 }
 
-template <int TECH, bool STATS, int SRC, bool ANYHIT, int MINB>
+template <int TECH, bool STATS, int SRC, bool ANYHIT, int MINB, bool TAPER = false>
 static int launch_trace_t(DeviceScene& sc, TraceParams& p, cudaStream_t st)
 {
-    int per_sm = blocks_per_sm(trace_kernel<TECH, STATS, SRC, ANYHIT, MINB>, sc.device);
+    int per_sm = blocks_per_sm(trace_kernel<TECH, STATS, SRC, ANYHIT, MINB, TAPER>, sc.device);
     tunables(p);
     if (tun().blocks_per_sm > 0) per_sm = std::min(per_sm, tun().blocks_per_sm);
     unsigned long long want = ((unsigned long long)(p.n_slots - p.slot_begin) + TR_BLOCK - 1) / TR_BLOCK;
     unsigned grid = (unsigned)std::min<unsigned long long>((unsigned long long)sc.sm_count * per_sm, std::max<unsigned long long>(want, 1ull));
-    trace_kernel<TECH, STATS, SRC, ANYHIT, MINB><<<grid, TR_BLOCK, 0, st>>>(p);
+    trace_kernel<TECH, STATS, SRC, ANYHIT, MINB, TAPER><<<grid, TR_BLOCK, 0, st>>>(p);
     count_launch();
     return VKHRT_OK;
 }
@@ -1425,6 +1435,11 @@ static int launch_trace(DeviceScene& sc, TraceParams& p, cudaStream_t st)
     sc.last_trace_was_pool = false;
     p.hits_aligned32 = (((uintptr_t)p.hits & 31u) == 0u ? 1u : 0u) | (((uintptr_t)p.hits_mirror & 31u) == 0u ? 2u : 0u);
     if (tun().store256 == 0) p.hits_aligned32 = 0u;
+    if (sc.tapered()) {
+        // per-vertex radii (Phantom, DOTS): the lane-bound kernel with the taper terms compiled in (LSS always carries its radii)
+        if (sc.technique == VKHRT_TECHNIQUE_PHANTOM) return launch_trace_t<VKHRT_TECHNIQUE_PHANTOM, STATS, SRC, ANYHIT, TR_MIN_BLOCKS, true>(sc, p, st);
+        return launch_trace_t<VKHRT_TECHNIQUE_DOTS, STATS, SRC, ANYHIT, TR_MIN_BLOCKS, true>(sc, p, st);
+    }
     switch (sc.technique) {
     case VKHRT_TECHNIQUE_PHANTOM:
         // records that go straight to pinned host memory keep trace_kernel: its retiring lanes are pixel neighbours, which the
@@ -1507,7 +1522,7 @@ int render_frame(DeviceScene& sc, const VkhrtFrameDesc& f, VkhrtHit* hits_out, u
     // Phantom frames large enough for the pool kernel: line-wise delivery (records to HBM, complete 128-byte lines to the host)
     bool linewise = false;
     const uint32_t line_shift = (uint32_t)tun().line_shift;
-    if (h_hits_mapped && !want_rgba && sc.technique == VKHRT_TECHNIQUE_PHANTOM && sc.n_leaves && tun().pool && tun().linewise &&
+    if (h_hits_mapped && !want_rgba && sc.technique == VKHRT_TECHNIQUE_PHANTOM && !sc.tapered() && sc.n_leaves && tun().pool && tun().linewise &&
         (((uintptr_t)h_hits_mapped) & ((32u << line_shift) - 1u)) == 0u && r.n_slots >= (unsigned long long)tun().pool_min_ratio * sc.sm_count * 32ull * 56ull) {
         if ((rc = grow(&sc.d_hits_scratch, &sc.hits_scratch_n, (size_t)r.n_out))) return rc;
         if ((rc = grow(&sc.d_line_cnt, &sc.line_cnt_n, (size_t)r.n_out / 2 + 1))) return rc;      // enough for the smallest line (2 records)
@@ -1603,7 +1618,7 @@ int trace_ray_buffer(DeviceScene& sc, const float* rays_dev, uint64_t n, VkhrtHi
     cudaStream_t st = stream ? stream : sc.stream;
     TraceParams p;
     memset(&p, 0, sizeof(p));
-    p.nodes = sc.d_nodes; p.primA = sc.d_primA; p.primB = sc.d_primB; p.sorted_ids = sc.d_sorted_ids;
+    p.nodes = sc.d_nodes; p.primA = sc.d_primA; p.primB = sc.d_primB; p.primR = sc.d_primR; p.sorted_ids = sc.d_sorted_ids;
     p.n_prims = sc.n_leaves; p.radius = sc.radius;
     p.counters = sc.d_counters;
     p.slot_begin = 0; p.hits_mirror = nullptr;
