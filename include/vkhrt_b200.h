@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define VKHRT_ABI_VERSION 4
+#define VKHRT_ABI_VERSION 5
 
 typedef enum VkhrtStatus {
     VKHRT_OK = 0,
@@ -92,7 +92,9 @@ typedef struct VkhrtSceneDesc {
     uint32_t        n_vertices;
     const uint32_t* line_indices;       /* n_segments * 2 vertex indices                           */
     uint32_t        n_segments;
-    const float*    radius_per_vertex;  /* nullable: n_vertices radii (LSS extension). NULL => `radius` */
+    const float*    radius_per_vertex;  /* nullable: n_vertices radii, linear along each segment.  PHANTOM: cone radius(t) and slant
+                                           (shaders/cone.glsl:27, which the reference's caller leaves at 0); LSS: end-sphere radii;
+                                           DOTS: per-end strip half-widths.  NULL => `radius` everywhere (the reference's 0.02)  */
     float           radius;             /* <= 0 => VKHRT_DEFAULT_RADIUS                            */
     int32_t         technique;          /* VkhrtTechnique                                          */
     int32_t         device;             /* CUDA device ordinal                                     */
@@ -121,7 +123,8 @@ typedef struct VkhrtFrameDesc {
                                        is written at its row-major position (only the tiles of this shard are
                                        touched).  All shards can then share one frame buffer, e.g. the gathering
                                        GPU's, mapped into every rank over NVLink (vkhrt_shared_buffer_*): the
-                                       traversal kernel's stores ARE the gather.  Device output memory only.   */
+                                       traversal kernel's stores ARE the gather.  Device output memory, or (hit
+                                       records only) a PAGE-LOCKED host buffer the kernels store into directly. */
     int32_t  output_memory;         /* VkhrtMemory of hits_out / rgba8_out                         */
     void*    stream;                /* cudaStream_t to run on (device outputs only); NULL => the
                                        scene's own stream                                         */
@@ -270,14 +273,27 @@ int  vkhrt_untile(const VkhrtFrameDesc* frame, uint32_t world, const void* gathe
                   uint32_t elem_bytes, void* stream);
 /* the same re-ordering on HOST buffers (plain loops, no device needed) */
 int  vkhrt_untile_host(const VkhrtFrameDesc* frame, uint32_t world, const void* gathered, void* row_major, uint32_t elem_bytes);
-/* One frame on several GPUs from ONE process (the shape of the reference's single executable).  scenes[r] is the
- * same geometry built on device r (deterministic build => identical BVHs; several scenes may also share a device).  The frame is cut
- * into tile_size^2 tiles dealt round-robin (scene r traces tiles r, r + n, ...; no exchange step), one host thread
- * per scene drives vkhrt_render on its shard, and the shards are re-ordered into the caller's row-major HOST buffers.  `frame` must
- * describe the whole frame (tile_stride <= 1) with output_memory = VKHRT_MEM_HOST; results are identical to vkhrt_render's.
- * The per-process path used by bench.py (one process per GPU, NVLink peer stores) is vkhrt_b200/multi.py. */
+/* One frame on several GPUs from ONE process (the shape of the reference's single executable, one queue: source/renderer.cpp:83-131;
+ * SURVEY.md §8(b)).  scenes[r] is the same geometry built on device r (deterministic build => identical BVHs; several scenes may
+ * also share a device).  The frame is cut into tile_size^2 tiles dealt round-robin (scene r traces tiles r, r + n, ...; no exchange
+ * step) and assembled without any CPU re-ordering: hit records go straight from every GPU's traversal kernel into
+ * the caller's buffer when it is page-locked (vkhrt_host_alloc), everything else (pixels; records into pageable memory) is stored
+ * by every GPU at its row-major position of a frame buffer on scenes[0]'s device over NVLink (peer access) and copied out once.
+ * Shards are launched by persistent worker threads.  `frame` must describe the whole frame (tile_stride <= 1) with
+ * output_memory = VKHRT_MEM_HOST; results are identical to vkhrt_render's.  Without peer access between the devices the shards
+ * are staged and re-ordered on the host.  The one-process-per-GPU path used by bench.py is vkhrt_b200/multi.py. */
 int  vkhrt_render_multi(VkhrtScene* const* scenes, uint32_t n_scenes, const VkhrtFrameDesc* frame, VkhrtHit* hits_out, uint8_t* rgba8_out);
 int  vkhrt_last_timing(const VkhrtScene* scene, VkhrtTiming* timing);
+
+/* ---- page-locked host output buffers --------------------------------------------------------------------------------
+ * Host memory every GPU of the box can store into directly (cudaHostAlloc, portable + mapped).  A hit-record buffer from here
+ * takes vkhrt_render's zero-copy path: the traversal kernel writes the records straight into it over PCIe instead of a
+ * device->host copy after the kernel, and vkhrt_render_multi lets every GPU deliver its own shard.  Any other
+ * page-locked memory (cudaHostAlloc / cudaHostRegister by the caller, torch pin_memory) is recognised just the same; plain
+ * malloc memory always works too, through a staging copy.  The reference's counterpart is its host-visible staging buffer
+ * (source/vk_common.cpp CreateBuffer with HOST_VISIBLE | HOST_COHERENT memory). */
+int  vkhrt_host_alloc(size_t bytes, void** out_ptr);
+int  vkhrt_host_free(void* ptr);
 
 /* ---- device buffers shareable between the per-GPU processes of one box (CUDA IPC over NVLink/PCIe) ---- */
 /* create: plain device allocation on `device` + a 64-byte handle another process can open.

@@ -92,7 +92,7 @@ ABI_SYMBOLS = [
     "vkhrt_scene_get_primitives", "vkhrt_scene_primitive_count", "vkhrt_scene_destroy",
     "vkhrt_render", "vkhrt_render_stats", "vkhrt_frame_local_pixels", "vkhrt_untile", "vkhrt_untile_host", "vkhrt_render_multi", "vkhrt_last_timing",
     "vkhrt_generate_rays", "vkhrt_trace_rays", "vkhrt_trace_rays_any_hit", "vkhrt_camera_matrices", "vkhrt_groom_generate",
-    "vkhrt_shared_buffer_create", "vkhrt_shared_buffer_open", "vkhrt_shared_buffer_close", "vkhrt_shared_buffer_destroy",
+    "vkhrt_host_alloc", "vkhrt_host_free", "vkhrt_shared_buffer_create", "vkhrt_shared_buffer_open", "vkhrt_shared_buffer_close", "vkhrt_shared_buffer_destroy",
     "vkhrt_scene_set_environment", "vkhrt_scene_apply_lod", "vkhrt_scene_segment_count", "vkhrt_scene_get_lines",
     "vkhrt_asset_load_lines", "vkhrt_asset_save_lines", "vkhrt_asset_free", "vkhrt_image_load_hdr", "vkhrt_image_save_hdr",
     "vkhrt_image_free", "vkhrt_image_save_png", "vkhrt_environment_generate",
@@ -164,7 +164,9 @@ def lib():
     L.vkhrt_image_save_png.argtypes = [C.c_char_p, C.c_void_p, C.c_uint32, C.c_uint32]
     L.vkhrt_environment_generate.argtypes = [C.c_uint32, C.c_uint32, C.c_void_p]
     L.vkhrt_environment_generate.restype = None
-    if L.vkhrt_abi_version() != 4:
+    L.vkhrt_host_alloc.argtypes = [C.c_size_t, C.POINTER(C.c_void_p)]
+    L.vkhrt_host_free.argtypes = [C.c_void_p]
+    if L.vkhrt_abi_version() != 5:
         raise ImportError("libvkhrt_b200.so ABI version mismatch")
     _lib = L
     return L
@@ -437,6 +439,28 @@ class Scene:
         t = Timing()
         _check(lib().vkhrt_last_timing(self._h, C.byref(t)), "vkhrt_last_timing")
         return t.as_dict()
+
+
+class HostBuffer:
+    """Page-locked host memory from vkhrt_host_alloc, viewed as a numpy array (`.array`): hit-record buffers from here take the
+    zero-copy path of vkhrt_render / vkhrt_render_multi."""
+
+    def __init__(self, shape, dtype):
+        self.dtype = np.dtype(dtype)
+        self.shape = tuple(shape) if isinstance(shape, (tuple, list)) else (int(shape),)
+        n = int(np.prod(self.shape)) * self.dtype.itemsize
+        p = C.c_void_p()
+        _check(lib().vkhrt_host_alloc(max(n, 1), C.byref(p)), "vkhrt_host_alloc")
+        self.ptr = p.value
+        self.array = np.frombuffer((C.c_uint8 * max(n, 1)).from_address(self.ptr), dtype=self.dtype, count=int(np.prod(self.shape))).reshape(self.shape)
+
+    def close(self):
+        if getattr(self, "ptr", None):
+            self.array = None
+            lib().vkhrt_host_free(self.ptr)
+            self.ptr = None
+
+    __del__ = close
 
 
 class SharedBuffer:

@@ -480,6 +480,23 @@ int vkhrt_last_timing(const VkhrtScene* scene, VkhrtTiming* timing)
     return VKHRT_OK;
 }
 
+int vkhrt_host_alloc(size_t bytes, void** out_ptr)
+{
+    if (!out_ptr || bytes == 0) { set_last_error("null argument"); return VKHRT_ERR_INVALID_ARGUMENT; }
+    *out_ptr = nullptr;
+    int rc = check_device(0);
+    if (rc) return rc;
+    VK_CUDA(cudaHostAlloc(out_ptr, bytes, cudaHostAllocPortable | cudaHostAllocMapped));
+    return VKHRT_OK;
+}
+
+int vkhrt_host_free(void* ptr)
+{
+    if (!ptr) return VKHRT_OK;
+    VK_CUDA(cudaFreeHost(ptr));
+    return VKHRT_OK;
+}
+
 int vkhrt_shared_buffer_create(int device, size_t bytes, void** dev_ptr_out, uint8_t handle_out[VKHRT_IPC_HANDLE_BYTES])
 {
     static_assert(sizeof(cudaIpcMemHandle_t) == VKHRT_IPC_HANDLE_BYTES, "IPC handle size");

@@ -20,6 +20,8 @@
 #include <cmath>
 #include <cstdint>
 #include <cstdio>
+#include <cstdlib>
+#include <new>
 #include <cstring>
 #include <fstream>
 #include <memory>
@@ -39,6 +41,44 @@ struct VkhrtError : std::runtime_error {
         : std::runtime_error(where + ": " + vkhrt_error_string(s) + " (" + std::to_string(s) + ") " + vkhrt_last_error()), status(s) {}
 };
 inline void Check(int status, const char* where) { if (status != VKHRT_OK) throw VkhrtError(status, where); }
+
+// Output buffer in page-locked host memory (vkhrt_host_alloc): what the reference keeps in HOST_VISIBLE staging memory.
+// Falls back to plain heap memory when the allocation is refused (then vkhrt_render stages the copy itself).
+template <typename T>
+class HostBuffer {
+public:
+    HostBuffer() = default;
+    HostBuffer(const HostBuffer&) = delete;
+    HostBuffer& operator=(const HostBuffer&) = delete;
+    ~HostBuffer() { release(); }
+    void resize(size_t n)
+    {
+        if (n == _n) return;
+        release();
+        if (n == 0) return;
+        void* p = nullptr;
+        if (vkhrt_host_alloc(n * sizeof(T), &p) == VKHRT_OK) { _p = static_cast<T*>(p); _pinned = true; }
+        else { _p = static_cast<T*>(std::malloc(n * sizeof(T))); _pinned = false; if (!_p) throw std::bad_alloc(); }
+        _n = n;
+    }
+    [[nodiscard]] T* data() { return _p; }
+    [[nodiscard]] const T* data() const { return _p; }
+    [[nodiscard]] size_t size() const { return _n; }
+    [[nodiscard]] bool empty() const { return _n == 0; }
+    [[nodiscard]] bool pinned() const { return _pinned; }
+    [[nodiscard]] const T& operator[](size_t i) const { return _p[i]; }
+    [[nodiscard]] const T* begin() const { return _p; }
+    [[nodiscard]] const T* end() const { return _p + _n; }
+private:
+    void release()
+    {
+        if (_p) { if (_pinned) vkhrt_host_free(_p); else std::free(_p); }
+        _p = nullptr; _n = 0; _pinned = false;
+    }
+    T* _p = nullptr;
+    size_t _n = 0;
+    bool _pinned = false;
+};
 
 struct vec3 { float x = 0, y = 0, z = 0; };
 
@@ -244,8 +284,8 @@ public:
                   "vkhrt_render_multi");
         }
     }
-    [[nodiscard]] const std::vector<VkhrtHit>& GetHits() const { return _hits; }
-    [[nodiscard]] const std::vector<uint8_t>& GetImage() const { return _image; }     // RGBA8, row-major, row 0 = top
+    [[nodiscard]] const HostBuffer<VkhrtHit>& GetHits() const { return _hits; }
+    [[nodiscard]] const HostBuffer<uint8_t>& GetImage() const { return _image; }     // RGBA8, row-major, row 0 = top
     [[nodiscard]] const RendererInitInfo& GetInitInfo() const { return _info; }
 
     bool WritePPM(const std::string& path) const
@@ -269,8 +309,8 @@ private:
     std::shared_ptr<FlyCamera> _flyCamera;
     std::vector<std::shared_ptr<Model>> _models;
     std::vector<std::shared_ptr<Model>> _replicas;
-    std::vector<VkhrtHit> _hits;
-    std::vector<uint8_t> _image;
+    HostBuffer<VkhrtHit> _hits;       // page-locked: the GPUs store hit records straight into it
+    HostBuffer<uint8_t> _image;
 };
 
 }  // namespace vkhrt_host
