@@ -397,7 +397,7 @@ def main():
         flush.zero_()
         step_device()
     barrier()
-    sampler = ClockSampler(local_rank) if rank == 0 else None
+    sampler = ClockSampler(local_rank) if (rank == 0 and not os.environ.get("VKHRT_BENCH_NO_SAMPLER")) else None
     evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     launches0 = V.launch_count()
     barrier()
@@ -441,11 +441,17 @@ def main():
         scene.render_into(fh, h_hits_ptr, h_rgba_ptr)
     barrier()
     t0 = time.time()
+    dbg = []
     for _ in range(args.steps):
         # camera matrices (the per-frame input, CameraUniformData) travel host->device as kernel parameters
+        ta = time.time()
         scene.render_into(fh, h_hits_ptr, h_rgba_ptr)   # blocks until this rank's records have landed in host memory
+        tb = time.time()
         if world > 1:
             dist.barrier()                               # the frame is complete when every rank's shard has landed
+        dbg.append((1e3 * (tb - ta), 1e3 * (time.time() - tb), scene.timing()["trace_ms"]) if os.environ.get("VKHRT_BENCH_DEBUG") else None)
+    if os.environ.get("VKHRT_BENCH_DEBUG"):
+        print(f"rank {rank} e2e frames (render ms, barrier ms, kernel ms):", [tuple(round(x, 2) for x in d) for d in dbg], file=sys.stderr)
     torch.cuda.synchronize()
     e2e_wall = time.time() - t0
     e2e_t = torch.tensor([e2e_wall], dtype=torch.float64, device=dev)

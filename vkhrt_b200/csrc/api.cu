@@ -44,6 +44,7 @@ static void free_scene(DeviceScene* sc)
     if (!sc) return;
     cudaSetDevice(sc->device);
     cudaFree(sc->d_positions); cudaFree(sc->d_indices); cudaFree(sc->d_radius_pv); cudaFree(sc->d_curves); cudaFree(sc->d_env);
+    cudaFree(sc->d_build_scratch);
     cudaFree(sc->d_arena);       // nodes, sorted ids / keys, parents, refit flags, primA, primB
     cudaFree(sc->d_multi_hits); cudaFree(sc->d_multi_rgba);
     if (sc->multi_done) cudaEventDestroy(sc->multi_done);

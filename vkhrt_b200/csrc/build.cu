@@ -299,74 +299,158 @@ __global__ void __launch_bounds__(256) morton_kernel(const float4* __restrict__ 
 }
 
 // ------------------------------------------------------------------------------------------------
-// LSD radix sort, 8-bit digits, stable, 64-bit keys + 32-bit values (hand-written; no CUB/Thrust).
-// Per pass: block histograms -> exclusive scan (digit-major) -> stable scatter with warp-match ranking.
+// Radix sort of (64-bit Morton key, 32-bit leaf id): LSD, 8-bit digits, stable, ONE read and ONE write of the data per
+// digit pass ("onesweep": Adinets & Merrill 2022; hand-written, no CUB / Thrust).
+//   os_histogram_kernel  one pass over the keys: the 256-bin histograms of all 8 digits at once
+//   os_scan_kernel       exclusive scan of each of the 8 histograms -> where every digit's run starts in the output
+//   os_pass_kernel       per digit: a CTA takes the next tile of 3072 keys (ticket counter: tiles start in order), ranks them
+//                        stably (warp-match ranking inside 256-key warp chunks, chunk prefixes per digit), learns where its
+//                        keys of each digit go by DECOUPLED LOOK-BACK over the previous tiles' per-digit counts (one 64-bit
+//                        status word per tile and digit = flag + count, so no fence is needed), regroups the tile by digit in
+//                        shared memory and writes each digit's run with consecutive threads.
+// The status words carry the pass number in their flag (2 pass + 1 = tile count, 2 pass + 2 = inclusive prefix), so one
+// buffer, zeroed once per sort, serves all passes.  8 x (12 B read + 12 B write) + 8 B per key instead of the 8 x (20 + 12) + 8
+// histogram/scan/scatter passes of round 1 (C2: 6.4 M keys in 1.21 ms = 5.3 Gkeys/s before).
 // ------------------------------------------------------------------------------------------------
-constexpr int RS_BLOCK = 256;
-constexpr int RS_IPT = 8;                       // items per thread
-constexpr int RS_TILE = RS_BLOCK * RS_IPT;      // 2048 keys per block
-constexpr int RS_WARPS = RS_BLOCK / 32;
+constexpr int OS_BLOCK = 384;
+constexpr int OS_IPT = 8;                       // keys per thread
+constexpr int OS_TILE = OS_BLOCK * OS_IPT;      // 3072 keys per tile (44 KB of static shared memory)
+constexpr int OS_WARPS = OS_BLOCK / 32;
+constexpr int OS_PASSES = 8;
 
-__global__ void __launch_bounds__(RS_BLOCK) rs_histogram_kernel(const uint64_t* __restrict__ keys, uint32_t n, int shift,
-                                                                uint32_t* __restrict__ hist, uint32_t n_blocks)
+__global__ void __launch_bounds__(512) os_histogram_kernel(const uint64_t* __restrict__ keys, uint32_t n, uint32_t* __restrict__ hist /* [8][256] */)
 {
-    __shared__ uint32_t sh[256];
-    sh[threadIdx.x] = 0;
+    __shared__ uint32_t sh[OS_PASSES][256];
+    for (int k = threadIdx.x; k < OS_PASSES * 256; k += blockDim.x) (&sh[0][0])[k] = 0;
     __syncthreads();
-    uint32_t base = blockIdx.x * RS_TILE;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const uint64_t k = keys[i];
 #pragma unroll
-    for (int r = 0; r < RS_IPT; ++r) {
-        uint32_t i = base + r * RS_BLOCK + threadIdx.x;
-        if (i < n) atomicAdd(&sh[(uint32_t)(keys[i] >> shift) & 255u], 1u);
+        for (int p = 0; p < OS_PASSES; ++p) atomicAdd(&sh[p][(uint32_t)(k >> (8 * p)) & 255u], 1u);
     }
     __syncthreads();
-    hist[threadIdx.x * n_blocks + blockIdx.x] = sh[threadIdx.x];
+    for (int k = threadIdx.x; k < OS_PASSES * 256; k += blockDim.x) { const uint32_t v = (&sh[0][0])[k]; if (v) atomicAdd(hist + k, v); }
 }
-
-__global__ void __launch_bounds__(RS_BLOCK) rs_scatter_kernel(const uint64_t* __restrict__ keys_in, const uint32_t* __restrict__ vals_in,
-                                                              uint64_t* __restrict__ keys_out, uint32_t* __restrict__ vals_out,
-                                                              uint32_t n, int shift, const uint32_t* __restrict__ scanned, uint32_t n_blocks)
+// in place: hist[p][d] -> number of keys whose digit p is smaller than d
+__global__ void __launch_bounds__(256) os_scan_kernel(uint32_t* __restrict__ hist)
 {
-    __shared__ uint32_t warp_cnt[RS_WARPS][256];
-    __shared__ uint32_t base[256];
-    const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    for (int k = threadIdx.x; k < RS_WARPS * 256; k += RS_BLOCK) (&warp_cnt[0][0])[k] = 0;
-    __syncthreads();
-
-    // warp w owns the contiguous range [tile + w*32*IPT, +32*IPT); round r = 32 consecutive keys
-    const uint32_t wbase = blockIdx.x * RS_TILE + w * (32 * RS_IPT);
-    uint64_t key[RS_IPT];
-    uint32_t val[RS_IPT], rank[RS_IPT];
+    __shared__ uint32_t wsum[8];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    for (int p = 0; p < OS_PASSES; ++p) {
+        const uint32_t v = hist[p * 256 + threadIdx.x];
+        uint32_t inc = v;
 #pragma unroll
-    for (int r = 0; r < RS_IPT; ++r) {
-        uint32_t i = wbase + r * 32 + lane;
-        bool ok = i < n;
+        for (int o = 1; o < 32; o <<= 1) { uint32_t t = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += t; }
+        if (lane == 31) wsum[w] = inc;
+        __syncthreads();
+        uint32_t base = 0;
+        for (int k = 0; k < w; ++k) base += wsum[k];
+        hist[p * 256 + threadIdx.x] = base + inc - v;
+        __syncthreads();
+    }
+}
+VK_DEV unsigned long long os_ld(const unsigned long long* p)
+{
+    unsigned long long v;
+    asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+VK_DEV void os_st(unsigned long long* p, unsigned long long v) { asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory"); }
+
+__global__ void __launch_bounds__(OS_BLOCK) os_pass_kernel(const uint64_t* __restrict__ keys_in, const uint32_t* __restrict__ vals_in,
+                                                           uint64_t* __restrict__ keys_out, uint32_t* __restrict__ vals_out, uint32_t n, int pass,
+                                                           const uint32_t* __restrict__ digit_start /* [256] of this pass */,
+                                                           unsigned long long* __restrict__ status /* [tiles][256] */, uint32_t* __restrict__ ticket /* [8] */)
+{
+    __shared__ uint16_t warp_cnt[OS_WARPS][256];   // keys of digit d in the chunks of the warps before w (after the prefix step)
+    __shared__ uint32_t dig_first[256];            // first position of digit d in the regrouped tile
+    __shared__ uint32_t dig_dst[256];              // global position of this tile's first key of digit d, minus dig_first[d]
+    __shared__ uint32_t scan_w[8];
+    __shared__ uint32_t s_tile;
+    __shared__ uint64_t s_key[OS_TILE];
+    __shared__ uint32_t s_val[OS_TILE];
+    const int tid = threadIdx.x, w = tid >> 5, lane = tid & 31;
+    const int shift = 8 * pass;
+    if (tid == 0) s_tile = atomicAdd(ticket + pass, 1u);
+    for (int k = tid; k < OS_WARPS * 256; k += OS_BLOCK) (&warp_cnt[0][0])[k] = 0;
+    __syncthreads();
+    const uint32_t tile = s_tile;
+    // warp w owns the contiguous chunk [tile * OS_TILE + w * 256, + 256); round r = 32 consecutive keys: ranks are stable
+    const uint32_t wbase = tile * OS_TILE + w * (32 * OS_IPT);
+    uint64_t key[OS_IPT];
+    uint32_t val[OS_IPT];
+    uint16_t rank[OS_IPT];
+#pragma unroll
+    for (int r = 0; r < OS_IPT; ++r) {
+        const uint32_t i = wbase + r * 32 + lane;
+        const bool ok = i < n;
         key[r] = ok ? keys_in[i] : ~0ull;
         val[r] = ok ? vals_in[i] : 0u;
-        uint32_t d = ok ? ((uint32_t)(key[r] >> shift) & 255u) : 256u;
-        uint32_t peers = __match_any_sync(0xffffffffu, d);
-        uint32_t pre = ok ? warp_cnt[w][d] : 0u;
+    }
+#pragma unroll
+    for (int r = 0; r < OS_IPT; ++r) {
+        const bool ok = wbase + r * 32 + lane < n;
+        const uint32_t d = ok ? ((uint32_t)(key[r] >> shift) & 255u) : 256u;
+        const uint32_t peers = __match_any_sync(0xffffffffu, d);
+        const uint32_t pre = ok ? warp_cnt[w][d] : 0u;
         __syncwarp();
-        if (ok && (peers & ((1u << lane) - 1u)) == 0u) warp_cnt[w][d] = pre + __popc(peers);
+        if (ok && (peers & ((1u << lane) - 1u)) == 0u) warp_cnt[w][d] = (uint16_t)(pre + __popc(peers));
         __syncwarp();
-        rank[r] = pre + __popc(peers & ((1u << lane) - 1u));
+        rank[r] = (uint16_t)(pre + __popc(peers & ((1u << lane) - 1u)));
     }
     __syncthreads();
-    {   // digit d = threadIdx.x: exclusive prefix over the warps of this block
-        uint32_t d = threadIdx.x, run = 0;
+    // digit d = tid (threads 0..255): prefix over the warps' chunks, tile count, look-back
+    uint32_t count = 0;
+    if (tid < 256) {
 #pragma unroll
-        for (int k = 0; k < RS_WARPS; ++k) { uint32_t c = warp_cnt[k][d]; warp_cnt[k][d] = run; run += c; }
-        base[d] = scanned[d * n_blocks + blockIdx.x];
+        for (int k = 0; k < OS_WARPS; ++k) { const uint32_t c = warp_cnt[k][tid]; warp_cnt[k][tid] = (uint16_t)count; count += c; }
+        const unsigned long long AGG = (unsigned long long)(2 * pass + 1) << 56, INC = (unsigned long long)(2 * pass + 2) << 56;
+        unsigned long long* mine = status + (size_t)tile * 256 + tid;
+        if (tile > 0) os_st(mine, AGG | count);
+        uint32_t excl = 0;
+        for (int t = (int)tile - 1; t >= 0; --t) {
+            unsigned long long sw;
+            do { sw = os_ld(status + (size_t)t * 256 + tid); } while ((sw >> 56) != (AGG >> 56) && (sw >> 56) != (INC >> 56));
+            excl += (uint32_t)sw;
+            if ((sw >> 56) == (INC >> 56)) break;
+        }
+        os_st(mine, INC | (unsigned long long)(excl + count));
+        // exclusive scan of the tile's digit counts -> where each digit starts in the regrouped tile
+        uint32_t inc = count;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { uint32_t t = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += t; }
+        if (lane == 31) scan_w[w] = inc;
+        dig_first[tid] = inc - count;                  // within the warp; the warp bases are added below
+        dig_dst[tid] = digit_start[tid] + excl;
     }
     __syncthreads();
+    if (tid < 256) {
+        uint32_t base = 0;
+        for (int k = 0; k < w; ++k) base += scan_w[k];
+        const uint32_t first = dig_first[tid] + base;
+        dig_first[tid] = first;
+        dig_dst[tid] -= first;
+    }
+    __syncthreads();
+    // regroup the tile by digit in shared memory ...
 #pragma unroll
-    for (int r = 0; r < RS_IPT; ++r) {
-        uint32_t i = wbase + r * 32 + lane;
-        if (i < n) {
-            uint32_t d = (uint32_t)(key[r] >> shift) & 255u;
-            uint32_t o = base[d] + warp_cnt[w][d] + rank[r];
-            keys_out[o] = key[r];
-            vals_out[o] = val[r];
+    for (int r = 0; r < OS_IPT; ++r) {
+        if (wbase + r * 32 + lane < n) {
+            const uint32_t d = (uint32_t)(key[r] >> shift) & 255u;
+            const uint32_t at = dig_first[d] + warp_cnt[w][d] + rank[r];
+            s_key[at] = key[r]; s_val[at] = val[r];
+        }
+    }
+    __syncthreads();
+    // ... and write every digit's run with consecutive threads
+    const uint32_t in_tile = min((uint32_t)OS_TILE, n - tile * OS_TILE);
+#pragma unroll
+    for (int r = 0; r < OS_IPT; ++r) {
+        const uint32_t at = r * OS_BLOCK + tid;
+        if (at < in_tile) {
+            const uint64_t k = s_key[at];
+            const uint32_t o = dig_dst[(uint32_t)(k >> shift) & 255u] + at;
+            keys_out[o] = k; vals_out[o] = s_val[at];
         }
     }
 }
@@ -441,9 +525,12 @@ VK_DEV int prefix_len(const uint64_t* __restrict__ m, int n, int i, int j)
     return __clzll((long long)(a ^ b));
 }
 
+// The bottom-up box pass works on tiles of REFIT_TILE consecutive (Morton-sorted) leaves, one CTA each: a node whose leaf range lies
+// inside one tile is only ever reached by threads of that CTA (node_local = 1) and is handled in shared memory.
+constexpr int REFIT_TILE_SHIFT = 9, REFIT_TILE = 1 << REFIT_TILE_SHIFT;
 __global__ void __launch_bounds__(256) karras_kernel(const uint64_t* __restrict__ morton, const uint32_t* __restrict__ sorted_ids, int n,
                                                      uint32_t* __restrict__ nodes_u32 /* 16 words per node */,
-                                                     uint32_t* __restrict__ parent_internal, uint32_t* __restrict__ parent_leaf)
+                                                     uint32_t* __restrict__ parent_internal, uint32_t* __restrict__ parent_leaf, uint8_t* __restrict__ node_local)
 {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n - 1) return;
@@ -463,6 +550,7 @@ __global__ void __launch_bounds__(256) karras_kernel(const uint64_t* __restrict_
     } while (t > 1);
     int gamma = i + s * d + min(d, 0);
     int lo = min(i, j), hi = max(i, j);
+    node_local[i] = (lo >> REFIT_TILE_SHIFT) == (hi >> REFIT_TILE_SHIFT) ? 1 : 0;
     uint32_t c0, c1, p0 = 0, p1 = 0;
     if (lo == gamma) { c0 = VKHRT_BVH_LEAF | (uint32_t)gamma; p0 = sorted_ids[gamma]; parent_leaf[gamma] = ((uint32_t)i << 1); }
     else { c0 = (uint32_t)gamma; parent_internal[gamma] = ((uint32_t)i << 1); }
@@ -479,13 +567,31 @@ __global__ void __launch_bounds__(256) karras_kernel(const uint64_t* __restrict_
 // boxes do not depend on arrival order.
 // ------------------------------------------------------------------------------------------------
 template <int TECH>
-__global__ void __launch_bounds__(256) materialise_refit_kernel(MeshIn m, uint32_t n_prims, const uint32_t* __restrict__ sorted_ids,
+__global__ void __launch_bounds__(REFIT_TILE) materialise_refit_kernel(MeshIn m, uint32_t n_prims, const uint32_t* __restrict__ sorted_ids,
                                                                 float4* __restrict__ primA, float4* __restrict__ primB, float2* __restrict__ primR,
                                                                 float* nodes_f32, const uint32_t* __restrict__ parent_internal,
-                                                                const uint32_t* __restrict__ parent_leaf, uint32_t* flags)
+                                                                const uint32_t* __restrict__ parent_leaf, uint32_t* flags,
+                                                                const uint8_t* __restrict__ node_local)
 {
-    uint32_t pos = blockIdx.x * blockDim.x + threadIdx.x;
-    if (pos >= n_prims) return;
+    // Everything the walk needs for the nodes INSIDE this CTA's tile of leaves lives in shared memory (index = node - tile base):
+    // the parent link and the "local" bit (loaded coalesced), an arrival counter, and both child boxes, which are written to the
+    // node records by the whole CTA at the end (12 of every 16 words, consecutive threads -> consecutive words).
+    __shared__ float s_box[REFIT_TILE][12];        // lo0 hi0 lo1 hi1 (the box words of VkhrtBvhNode, without the child / prim words)
+    __shared__ uint32_t s_arrived[REFIT_TILE];
+    __shared__ uint32_t s_parent[REFIT_TILE];
+    __shared__ uint8_t s_local[REFIT_TILE];
+    const uint32_t tile_base = blockIdx.x * REFIT_TILE;
+    {
+        const uint32_t node = tile_base + threadIdx.x;
+        const bool in = n_prims > 1 && node < n_prims - 1;
+        s_arrived[threadIdx.x] = 0u;
+        s_parent[threadIdx.x] = in ? parent_internal[node] : 0u;
+        s_local[threadIdx.x] = in ? node_local[node] : (uint8_t)0;
+    }
+    __syncthreads();
+    uint32_t pos = tile_base + threadIdx.x;
+    bool walking = pos < n_prims;
+    if (walking) {
     // the leaf's record is its GROUP's (a curve / LSS / strip reached through any of its pieces is tested whole); its box is the piece's
     const uint32_t leaf = sorted_ids[pos];
     const uint32_t prim = leaf / LeafSplit<TECH>::K;
@@ -539,23 +645,45 @@ __global__ void __launch_bounds__(256) materialise_refit_kernel(MeshIn m, uint32
         return;
     }
     uint32_t p = parent_leaf[pos];
-    for (;;) {
-        uint32_t node = p >> 1, slot = p & 1u;
+    while (walking) {
+        const uint32_t node = p >> 1, slot = p & 1u;
+        const uint32_t li = node - tile_base;                 // < REFIT_TILE exactly for the nodes indexed inside this tile
+        if (li < (uint32_t)REFIT_TILE && s_local[li]) {
+            // both children of this node come from threads of this CTA: ~50 cycles per level instead of a round trip to L2
+            float* mine = s_box[li] + 6 * slot;
+            mine[0] = box.lo.x; mine[1] = box.lo.y; mine[2] = box.lo.z; mine[3] = box.hi.x; mine[4] = box.hi.y; mine[5] = box.hi.z;
+            __threadfence_block();
+            if (atomicAdd(&s_arrived[li], 1u) == 0u) { walking = false; break; }         // first arrival: the sibling will carry on
+            __threadfence_block();
+            const volatile float* sib = s_box[li] + 6 * (1u - slot);
+            box.lo.x = fminf(box.lo.x, sib[0]); box.lo.y = fminf(box.lo.y, sib[1]); box.lo.z = fminf(box.lo.z, sib[2]);
+            box.hi.x = fmaxf(box.hi.x, sib[3]); box.hi.y = fmaxf(box.hi.y, sib[4]); box.hi.z = fmaxf(box.hi.z, sib[5]);
+            if (node == 0) { walking = false; break; }
+            p = s_parent[li];
+            continue;
+        }
+        // a node shared with other CTAs: publish my box in the parent's slot (L2 is the coherence point: .cg stores / loads), then
+        // ONE acq_rel atomic both releases it and, for the second arrival, acquires the sibling's
         float* nd = nodes_f32 + (size_t)node * 16 + 8 * slot;
-        // publish my box in the parent's slot (L2 is the coherence point: .cg stores / loads), then ONE acq_rel atomic both
-        // releases it and, for the second arrival, acquires the sibling's
         __stcg(reinterpret_cast<float2*>(nd), make_float2(box.lo.x, box.lo.y)); __stcg(nd + 2, box.lo.z);
         __stcg(reinterpret_cast<float2*>(nd + 4), make_float2(box.hi.x, box.hi.y)); __stcg(nd + 6, box.hi.z);
         uint32_t arrived;
         asm volatile("atom.acq_rel.gpu.global.add.u32 %0, [%1], 1;" : "=r"(arrived) : "l"(flags + node) : "memory");
-        if (arrived == 0u) return;                           // first arrival: the sibling will carry on
+        if (arrived == 0u) break;                            // first arrival: the sibling will carry on
         const float* sb = nodes_f32 + (size_t)node * 16 + 8 * (1u - slot);
         const float2 l01 = __ldcg(reinterpret_cast<const float2*>(sb)), h01 = __ldcg(reinterpret_cast<const float2*>(sb + 4));
         const float lz = __ldcg(sb + 2), hz = __ldcg(sb + 6);
         box.lo.x = fminf(box.lo.x, l01.x); box.lo.y = fminf(box.lo.y, l01.y); box.lo.z = fminf(box.lo.z, lz);
         box.hi.x = fmaxf(box.hi.x, h01.x); box.hi.y = fmaxf(box.hi.y, h01.y); box.hi.z = fmaxf(box.hi.z, hz);
-        if (node == 0) return;
-        p = parent_internal[node];
+        if (node == 0) break;
+        p = (li < (uint32_t)REFIT_TILE) ? s_parent[li] : parent_internal[node];
+    }
+    }   // if (walking)
+    __syncthreads();
+    // the tile's local nodes: box words 0-2, 4-6, 8-10, 12-14 of each 16-word record
+    for (uint32_t k = threadIdx.x; k < (uint32_t)REFIT_TILE * 16u; k += REFIT_TILE) {
+        const uint32_t li = k >> 4, wd = k & 15u;
+        if ((wd & 3u) != 3u && s_local[li]) nodes_f32[(size_t)(tile_base + li) * 16 + wd] = s_box[li][(wd >> 2) * 3 + (wd & 3u)];
     }
 }
 
@@ -608,7 +736,6 @@ int build_scene(DeviceScene& sc, bool refit_only)
     const size_t primA_per = tech == VKHRT_TECHNIQUE_DOTS ? 4 : 2;
 
     cudaEvent_t* ev = sc.ev;
-    VK_CUDA(cudaEventRecord(ev[0], st));
     if (!refit_only) {
         sc.n_nodes = n > 1 ? n - 1 : 1;
         // one allocation for everything the scene keeps (a cudaMalloc per array used to cost more than the build's kernels) ...
@@ -616,7 +743,8 @@ int build_scene(DeviceScene& sc, bool refit_only)
         const size_t o_nodes = 0, o_ids = o_nodes + up((size_t)sc.n_nodes * 64), o_morton = o_ids + up((size_t)n * 4), o_pint = o_morton + up((size_t)n * 8),
                      o_pleaf = o_pint + up((size_t)sc.n_nodes * 4), o_flags = o_pleaf + up((size_t)n * 4), o_primA = o_flags + up((size_t)sc.n_nodes * 4),
                      o_primB = o_primA + up((size_t)n * primA_per * 16), o_primR = o_primB + (tech == VKHRT_TECHNIQUE_PHANTOM ? up((size_t)n * 32) : 0),
-                     total = o_primR + ((tech == VKHRT_TECHNIQUE_PHANTOM && sc.d_radius_pv) ? up((size_t)n * 8) : 0);
+                     o_local = o_primR + ((tech == VKHRT_TECHNIQUE_PHANTOM && sc.d_radius_pv) ? up((size_t)n * 8) : 0),
+                     total = o_local + up((size_t)sc.n_nodes);
         if (sc.arena_bytes < total) {
             if (sc.d_arena) cudaFree(sc.d_arena);
             sc.d_arena = nullptr; sc.arena_bytes = 0;
@@ -628,19 +756,26 @@ int build_scene(DeviceScene& sc, bool refit_only)
         sc.d_refit_flags = (uint32_t*)(sc.d_arena + o_flags); sc.d_primA = (float4*)(sc.d_arena + o_primA);
         sc.d_primB = tech == VKHRT_TECHNIQUE_PHANTOM ? (float4*)(sc.d_arena + o_primB) : nullptr;
         sc.d_primR = (tech == VKHRT_TECHNIQUE_PHANTOM && sc.d_radius_pv) ? (float2*)(sc.d_arena + o_primR) : nullptr;
+        sc.d_node_local = (uint8_t*)(sc.d_arena + o_local);
 
-        // ... and one for the build's scratch
-        const uint32_t rs_blocks = cdiv(n, RS_TILE);
-        const uint32_t hist_n = rs_blocks * 256u;
+        // ... and one for the build's scratch, kept with the scene (a per-frame rebuild of a dynamic groom allocates nothing)
+        const uint32_t os_tiles = cdiv(n, OS_TILE);
         const size_t s_cent = 0, s_bounds = s_cent + up((size_t)n * 16), s_keys = s_bounds + 256, s_vals = s_keys + up((size_t)n * 8),
-                     s_hist = s_vals + up((size_t)n * 4), s_scan = s_hist + up((size_t)hist_n * 4), s_total = s_scan + up(scan_tmp_elems(hist_n) * 4);
-        unsigned char* d_scratch = nullptr;
-        auto free_scratch = [&]() { cudaFree(d_scratch); };
-#define VK_CUDA_S(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { set_last_error(std::string(#call) + ": " + cudaGetErrorString(e_)); free_scratch(); return e_ == cudaErrorMemoryAllocation ? VKHRT_ERR_OUT_OF_MEMORY : VKHRT_ERR_CUDA; } } while (0)
-        VK_CUDA_S(cudaMalloc((void**)&d_scratch, s_total));
+                     s_hist = s_vals + up((size_t)n * 4), s_ticket = s_hist + up(OS_PASSES * 256 * 4), s_status = s_ticket + 256,
+                     s_total = s_status + up((size_t)os_tiles * 256 * 8);
+        if (sc.build_scratch_bytes < s_total) {
+            if (sc.d_build_scratch) cudaFree(sc.d_build_scratch);
+            sc.d_build_scratch = nullptr; sc.build_scratch_bytes = 0;
+            VK_CUDA(cudaMalloc((void**)&sc.d_build_scratch, s_total));
+            sc.build_scratch_bytes = s_total;
+        }
+        unsigned char* d_scratch = sc.d_build_scratch;
+#define VK_CUDA_S(call) VK_CUDA(call)
         float4* d_cent = (float4*)(d_scratch + s_cent); uint32_t* d_bounds = (uint32_t*)(d_scratch + s_bounds);
         uint64_t* d_keys_alt = (uint64_t*)(d_scratch + s_keys); uint32_t* d_vals_alt = (uint32_t*)(d_scratch + s_vals);
-        uint32_t* d_hist = (uint32_t*)(d_scratch + s_hist); uint32_t* d_scan_tmp = (uint32_t*)(d_scratch + s_scan);
+        uint32_t* d_hist = (uint32_t*)(d_scratch + s_hist); uint32_t* d_ticket = (uint32_t*)(d_scratch + s_ticket);
+        unsigned long long* d_status = (unsigned long long*)(d_scratch + s_status);
+        VK_CUDA(cudaEventRecord(ev[0], st));            // the build proper starts here: allocations are not part of it
 
         // 1a centroids + bounds
         uint32_t init_bounds[6] = {0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0u, 0u, 0u};
@@ -657,15 +792,14 @@ int build_scene(DeviceScene& sc, bool refit_only)
         morton_kernel<<<g, 256, 0, st>>>(d_cent, n, d_bounds, keys[0], vals[0]);
         count_launch();
         VK_CUDA_S(cudaEventRecord(ev[2], st));
-        // 2 radix sort: 8 passes over the 63-bit key (even count => result lands back in keys[0]/vals[0])
+        // 2 onesweep radix sort: 8 digit passes over the 63-bit key (even count => the result lands back in keys[0]/vals[0])
+        VK_CUDA_S(cudaMemsetAsync(d_hist, 0, (size_t)(s_total - s_hist), st));          // histograms, tickets, status words
+        os_histogram_kernel<<<std::min<uint32_t>(cdiv(n, 512 * 8), (uint32_t)sc.sm_count * 4u), 512, 0, st>>>(keys[0], n, d_hist);
+        os_scan_kernel<<<1, 256, 0, st>>>(d_hist);
+        count_launch(2);
         int cur = 0;
-        for (int pass = 0; pass < 8; ++pass) {
-            int shift = pass * 8;
-            rs_histogram_kernel<<<rs_blocks, RS_BLOCK, 0, st>>>(keys[cur], n, shift, d_hist, rs_blocks);
-            count_launch();
-            int rc2 = exclusive_scan(d_hist, hist_n, d_scan_tmp, st);
-            if (rc2) { free_scratch(); return rc2; }
-            rs_scatter_kernel<<<rs_blocks, RS_BLOCK, 0, st>>>(keys[cur], vals[cur], keys[cur ^ 1], vals[cur ^ 1], n, shift, d_hist, rs_blocks);
+        for (int pass = 0; pass < OS_PASSES; ++pass) {
+            os_pass_kernel<<<os_tiles, OS_BLOCK, 0, st>>>(keys[cur], vals[cur], keys[cur ^ 1], vals[cur ^ 1], n, pass, d_hist + pass * 256, d_status, d_ticket);
             count_launch();
             cur ^= 1;
         }
@@ -674,36 +808,33 @@ int build_scene(DeviceScene& sc, bool refit_only)
         VK_CUDA_S(cudaMemsetAsync(sc.d_nodes, 0, (size_t)sc.n_nodes * 64, st));
         if (n > 1) {
             karras_kernel<<<cdiv(n - 1, 256), 256, 0, st>>>(sc.d_sorted_morton, sc.d_sorted_ids, (int)n, (uint32_t*)sc.d_nodes,
-                                                            sc.d_parent_internal, sc.d_parent_leaf);
+                                                            sc.d_parent_internal, sc.d_parent_leaf, sc.d_node_local);
         } else {
             single_node_kernel<<<1, 1, 0, st>>>((uint32_t*)sc.d_nodes, sc.d_sorted_ids);
         }
         count_launch();
         VK_CUDA_S(cudaEventRecord(ev[4], st));
-        uint32_t hb[6];
-        VK_CUDA_S(cudaMemcpyAsync(hb, d_bounds, sizeof(hb), cudaMemcpyDeviceToHost, st));
-        VK_CUDA_S(cudaStreamSynchronize(st));
-        VK_CUDA_S(cudaGetLastError());
-        for (int k = 0; k < 3; ++k) { sc.scene_lo[k] = ord2f_host(hb[k]); sc.scene_hi[k] = ord2f_host(hb[3 + k]); }
-        free_scratch();
+        VK_CUDA_S(cudaMemcpyAsync(sc.h_bounds, d_bounds, sizeof(sc.h_bounds), cudaMemcpyDeviceToHost, st));     // read after the final synchronise
 #undef VK_CUDA_S
     } else {
+        VK_CUDA(cudaEventRecord(ev[0], st));
         VK_CUDA(cudaEventRecord(ev[1], st)); VK_CUDA(cudaEventRecord(ev[2], st));
         VK_CUDA(cudaEventRecord(ev[3], st)); VK_CUDA(cudaEventRecord(ev[4], st));
     }
     // 4 materialise + refit
     VK_CUDA(cudaMemsetAsync(sc.d_refit_flags, 0, (size_t)sc.n_nodes * 4, st));
-    const uint32_t g = cdiv(n, 256);
+    const uint32_t g = cdiv(n, REFIT_TILE);
     if (tech == VKHRT_TECHNIQUE_PHANTOM)
-        materialise_refit_kernel<VKHRT_TECHNIQUE_PHANTOM><<<g, 256, 0, st>>>(m, n, sc.d_sorted_ids, sc.d_primA, sc.d_primB, sc.d_primR, (float*)sc.d_nodes, sc.d_parent_internal, sc.d_parent_leaf, sc.d_refit_flags);
+        materialise_refit_kernel<VKHRT_TECHNIQUE_PHANTOM><<<g, REFIT_TILE, 0, st>>>(m, n, sc.d_sorted_ids, sc.d_primA, sc.d_primB, sc.d_primR, (float*)sc.d_nodes, sc.d_parent_internal, sc.d_parent_leaf, sc.d_refit_flags, sc.d_node_local);
     else if (tech == VKHRT_TECHNIQUE_LSS)
-        materialise_refit_kernel<VKHRT_TECHNIQUE_LSS><<<g, 256, 0, st>>>(m, n, sc.d_sorted_ids, sc.d_primA, sc.d_primB, sc.d_primR, (float*)sc.d_nodes, sc.d_parent_internal, sc.d_parent_leaf, sc.d_refit_flags);
+        materialise_refit_kernel<VKHRT_TECHNIQUE_LSS><<<g, REFIT_TILE, 0, st>>>(m, n, sc.d_sorted_ids, sc.d_primA, sc.d_primB, sc.d_primR, (float*)sc.d_nodes, sc.d_parent_internal, sc.d_parent_leaf, sc.d_refit_flags, sc.d_node_local);
     else
-        materialise_refit_kernel<VKHRT_TECHNIQUE_DOTS><<<g, 256, 0, st>>>(m, n, sc.d_sorted_ids, sc.d_primA, sc.d_primB, sc.d_primR, (float*)sc.d_nodes, sc.d_parent_internal, sc.d_parent_leaf, sc.d_refit_flags);
+        materialise_refit_kernel<VKHRT_TECHNIQUE_DOTS><<<g, REFIT_TILE, 0, st>>>(m, n, sc.d_sorted_ids, sc.d_primA, sc.d_primB, sc.d_primR, (float*)sc.d_nodes, sc.d_parent_internal, sc.d_parent_leaf, sc.d_refit_flags, sc.d_node_local);
     count_launch();
     VK_CUDA(cudaEventRecord(ev[5], st));
     VK_CUDA(cudaStreamSynchronize(st));
     VK_CUDA(cudaGetLastError());
+    if (!refit_only) for (int k = 0; k < 3; ++k) { sc.scene_lo[k] = ord2f_host(sc.h_bounds[k]); sc.scene_hi[k] = ord2f_host(sc.h_bounds[3 + k]); }
     sc.timing.geometry_ms = ev_ms(ev[0], ev[1]);
     sc.timing.morton_ms = ev_ms(ev[1], ev[2]);
     sc.timing.sort_ms = ev_ms(ev[2], ev[3]);

@@ -37,7 +37,10 @@ struct DeviceScene {
     uint32_t* d_parent_internal = nullptr;  // n_nodes: (parent << 1) | slot
     uint32_t* d_parent_leaf = nullptr;      // n_leaves
     uint32_t* d_refit_flags = nullptr;      // n_nodes
+    uint8_t* d_node_local = nullptr;        // n_nodes: 1 = the node's leaf range lies inside one refit tile (handled in shared memory)
     float scene_lo[3] = {0, 0, 0}, scene_hi[3] = {0, 0, 0};
+    uint32_t h_bounds[6] = {};            // centroid bounds as ordered uints, copied back at the end of a build
+    unsigned char* d_build_scratch = nullptr; size_t build_scratch_bytes = 0;   // centroids, sort ping-pong, histograms, look-back status
 
     // primitives in Morton-sorted order
     //   PHANTOM: primA[2p] = {B0.xyz, rmax}, primA[2p+1] = {B3.xyz, bits(prim id)}; primB[2p] = {B1.xyz, quarter-chord deviation}, primB[2p+1] = {B2.xyz,0}

@@ -1522,7 +1522,8 @@ int render_frame(DeviceScene& sc, const VkhrtFrameDesc& f, VkhrtHit* hits_out, u
     // Phantom frames large enough for the pool kernel: line-wise delivery (records to HBM, complete 128-byte lines to the host)
     bool linewise = false;
     const uint32_t line_shift = (uint32_t)tun().line_shift;
-    if (h_hits_mapped && !want_rgba && sc.technique == VKHRT_TECHNIQUE_PHANTOM && !sc.tapered() && sc.n_leaves && tun().pool && tun().linewise &&
+    // (with an image the records stay in HBM for the shading kernel anyway, which is where line-wise delivery keeps them)
+    if (h_hits_mapped && sc.technique == VKHRT_TECHNIQUE_PHANTOM && !sc.tapered() && ao == 0u && sc.n_leaves && tun().pool && tun().linewise &&
         (((uintptr_t)h_hits_mapped) & ((32u << line_shift) - 1u)) == 0u && r.n_slots >= (unsigned long long)tun().pool_min_ratio * sc.sm_count * 32ull * 56ull) {
         if ((rc = grow(&sc.d_hits_scratch, &sc.hits_scratch_n, (size_t)r.n_out))) return rc;
         if ((rc = grow(&sc.d_line_cnt, &sc.line_cnt_n, (size_t)r.n_out / 2 + 1))) return rc;      // enough for the smallest line (2 records)
