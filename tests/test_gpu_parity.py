@@ -553,8 +553,8 @@ def test_render_multi_from_one_process(V, small_groom, tech):
 
 
 @pytest.mark.parametrize("env", [{"VKHRT_POOL_MIN_RATIO": "0"}, {"VKHRT_POOL_MIN_RATIO": "0", "VKHRT_POOL_CFG": "1"},
-                                 {"VKHRT_POOL_MIN_RATIO": "0", "VKHRT_POOL_CFG": "2"}, {"VKHRT_POOL_MIN_RATIO": "0", "VKHRT_POOL_V": "1"}, {"VKHRT_POOL": "0"}],
-                         ids=["pool-on-every-frame", "pool-56x8", "pool-64x6", "pool-round1-kernel", "lane-bound-only"])
+                                 {"VKHRT_POOL_MIN_RATIO": "0", "VKHRT_POOL_CFG": "2"}, {"VKHRT_POOL": "0"}],
+                         ids=["pool-on-every-frame", "pool-56x8", "pool-64x6", "lane-bound-only"])
 def test_both_traversal_kernels_pass_the_whole_suite(env):
     """Phantom primary rays have two traversal kernels: the per-warp ray pool (frames >= 3x its resident capacity) and the lane-bound
     kernel (everything else).  The library reads its switches once per process, so the whole parity file is re-run in a subprocess

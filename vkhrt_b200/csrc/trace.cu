@@ -405,383 +405,32 @@ __global__ void __launch_bounds__(TR_BLOCK, MINB) trace_kernel(const TraceParams
 //
 // trace_kernel ties a ray to a lane for its whole life, so a lane whose ray waits for a leaf test or a cone iteration is
 // dead weight in every node step (17 of 32 lanes active), and the leaf / march steps run with ~10 / ~9 lanes.  Here a
-// warp owns S ray SLOTS in shared memory (S = 64 = 2 per lane: origin, direction, 1/d, tcur, best hit, stack) and rays
-// move between queues of slot ids instead of waiting inside a lane:
+// warp owns S ray SLOTS in shared memory (direction, 1/d, tcur, best hit, a window of the stack) and rays move between
+// queues of slot ids instead of waiting inside a lane:
 //   READY  rays that want node steps     -> lanes pull them whenever they are free ("top-up"), traverse until the ray
 //                                           reaches a leaf (-> LEAF) or its stack runs empty (-> DONE)
-//   LEAF   rays standing at a leaf       -> batch of up to 32: the Prhi bounding-cylinder early-out; reject -> READY, pass -> CAND
+//   LEAF   rays standing at a leaf       -> batch of up to 32: the Prhi bounding-cylinder early-out; reject -> next stack entry, pass -> CAND
 //   CAND   rays with a candidate curve   -> set-up batch (ray-centric transform + quarter-chord filter) into the lanes'
-//                                           MARCH registers; reject -> READY.  A lane's march persists across phases and is a
+//                                           MARCH registers; reject -> next stack entry.  A lane's march persists across phases and is a
 //                                           different ray from the one the lane traverses; cone iterations run as a phase of
 //                                           their own while enough lanes hold one; a finished march commits into its ray's slot
-//                                           (one outstanding candidate per ray: no race) -> READY
+//                                           (one outstanding candidate per ray: no race) -> next stack entry
 //   DONE   finished rays                 -> batch: hit records written, slots refilled with new primary rays -> READY
 // Nothing is speculated: a ray's own sequence of node visits and candidate tests is exactly trace_kernel's (and the
 // oracle's), so hit records AND traversal counters are identical; only which lane executes which step changes.
 // Everything is warp-synchronous (queues are per warp), so there is no inter-warp protocol to get wrong.
+// The queues are LIFO stacks of slot ids: the most recently queued rays are served first, while the nodes and curves they
+// touched are still in L1 (a FIFO ring measured 4 % slower on C2); every queue drains when the warp runs out of other work.
 // ------------------------------------------------------------------------------------------------
-constexpr int PL_OVF = 96;             // spill entries per slot (Karras depth <= 64 + 32)
-constexpr uint32_t REF_POP = REF_NONE; // slot.cur marker: the ray resumes by popping its stack
+constexpr int PL_OVF = 96;             // stack entries per slot in the global spill area (Karras depth <= 64 + 32)
 constexpr int PL_MINB = 8;             // CTAs per SM the register allocation is held to
 enum : int { Q_READY = 0, Q_LEAF = 1, Q_CAND = 2, Q_DONE = 3, Q_FREE = 4 };
 
-// 87 bytes per slot with the default 72 x 4 configuration (119 with an 8-entry stack window).  The origin is the camera position for every primary ray (kernel parameter) and -(o/d) is rebuilt
-// from it when a lane pulls the ray, so a slot stores only d and 1/d; the best hit is (tcur, leaf position, u) — the
-// primitive id lives in the leaf record.
-// PL_S = ray slots per warp; PL_STK = shared-memory stack window per slot (a power of two: the TOP entries; older ones spill to global)
-template <int PL_S, int PL_STK>
-struct PoolWarp {
-    static_assert((PL_STK & (PL_STK - 1)) == 0, "the stack window is indexed with a mask");
-    uint2 stack[PL_STK][PL_S];         // ring: entry k of the stack sits at [k % PL_STK] while it is among the top PL_STK
-    float dir[6][PL_S];                // d.xyz, 1/d (rebuilding 1/d on every pull instead: -4 %)
-    float tcur[PL_S];
-    uint32_t cur[PL_S], best_pos[PL_S];
-    uint32_t last_group[VKHRT_MAILBOX_PHANTOM ? PL_S : 1];   // one-entry mailbox (VKHRT_MAILBOX_PHANTOM): the curve the ray tested last
-    float best_u[PL_S];
-    uint32_t out_idx[PL_S];
-    uint8_t sp[PL_S], spilled[PL_S];   // stack size, and how many of its bottom entries live in the global spill area
-    uint8_t q[5][PL_S];                // LIFO stacks of slot ids
-};
-
-template <bool STATS, int PL_S, int PL_STK>
-__global__ void __launch_bounds__(TR_BLOCK, PL_MINB) trace_pool_kernel(const TraceParams p)
-{
-    __shared__ PoolWarp<PL_S, PL_STK> sh_all[TR_BLOCK / 32];
-    if (blockIdx.x == 0 && threadIdx.x == 0) *p.work_next = 0ull;
-    const unsigned FULL = 0xffffffffu;
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const unsigned lt = (1u << lane) - 1u;
-    PoolWarp<PL_S, PL_STK>& sh = sh_all[warp];
-    uint2* const ovf_base = p.pool_overflow + ((size_t)(blockIdx.x * (TR_BLOCK / 32) + warp) * PL_S) * PL_OVF;
-    const float3 o = f3(p.cam.vi[12], p.cam.vi[13], p.cam.vi[14]);     // ray_gen.rgen:22: every primary ray starts at the camera
-
-    // the ray this lane traverses
-    bool has = false;
-    uint32_t slot = 0, cur = REF_POP, state = ST_POP;
-    int sp = 0, spilled = 0;
-    float3 id = f3(0, 0, 0), noid = f3(0, 0, 0);
-    float tcur = 0.0f;
-    // the candidate this lane marches (a different ray)
-    bool mhave = false;
-    MarchState ms;
-    ms.c.p0 = ms.c.p1 = ms.c.p2 = ms.c.p3 = f3(0, 0, 0);
-    ms.t = ms.told = ms.dt1 = ms.dt2 = ms.t_start = 0.0f; ms.it = 0u;
-    uint32_t m_slot = 0;
-    // queue fills (warp-uniform)
-    uint32_t nR = 0, nL = 0, nC = 0, nD = 0, nF = PL_S;
-    bool exhausted = false;
-    uint32_t st_nodes = 0, st_prims = 0, st_iters = 0, st_hits = 0, st_rays = 0;
-    uint32_t sc_steps[4] = {0, 0, 0, 0}, sc_lanes[4] = {0, 0, 0, 0};
-
-    for (int k = lane; k < PL_S; k += 32) sh.q[Q_FREE][k] = (uint8_t)k;
-    __syncwarp();
-
-    // the queues are LIFO stacks of slot ids: the most recently queued rays are served first, while the nodes and curves they
-    // touched are still in L1 (a FIFO ring measured 4 % slower: 1112 vs 1156 Mrays/s on C2); every queue drains when the warp
-    // runs out of other work, so nothing is left behind
-    auto enqueue = [&](int qi, uint32_t& n, bool pred, uint32_t s) {
-        const unsigned m = __ballot_sync(FULL, pred);
-        if (pred) sh.q[qi][n + __popc(m & lt)] = (uint8_t)s;
-        n += __popc(m);
-    };
-    auto dequeue = [&](int qi, uint32_t n, uint32_t k) -> uint32_t { return sh.q[qi][n - 1u - k]; };
-    // the shared-memory ring holds the top PL_STK entries; when it is full the OLDEST entry moves to the global spill area,
-    // and comes back only when everything above it has been popped
-    // Write one hit record per calling lane (`wrote`).  With line-wise host delivery the record goes to HBM, the lane counts it
-    // on its 128-byte line with a releasing atomic, and for every line that just became complete four lanes copy its four
-    // records to the host in one 256-bit store instruction = one 128-byte PCIe write (random 32-byte writes reach 12 GB/s,
-    // whole lines from adjacent lanes 44 GB/s: tools/micro/pcie_write.cu).  Called by all lanes of the warp.
-    auto emit = [&](bool wrote, uint32_t oi, float t, uint32_t seg, float u, float3 n, uint32_t prim, uint32_t flags) {
-        if (!p.line_cnt) { if (wrote) store_hit<false>(p, oi, t, seg, u, n, prim, flags); return; }      // warp-uniform
-        bool completes = false;
-        uint32_t line = 0;
-        if (wrote) {
-            store_hit<false>(p, oi, t, seg, u, n, prim, flags);
-            __threadfence();
-            line = oi >> p.line_shift;
-            uint32_t old;
-            asm volatile("atom.acq_rel.gpu.global.add.u32 %0, [%1], 1;" : "=r"(old) : "l"(p.line_cnt + line) : "memory");
-            completes = old + 1u == min(1u << p.line_shift, p.n_out - (line << p.line_shift));
-        }
-        unsigned m = __ballot_sync(FULL, completes);
-        while (m) {
-            // with r = 1 << line_shift records per line: lane L copies record L % r of the (L / r)-th completed line of this pass
-            const uint32_t src = __fns(m, 0, (lane >> p.line_shift) + 1);
-            const uint32_t ln = __shfl_sync(FULL, line, src & 31u);
-            const uint32_t rec = (ln << p.line_shift) + ((uint32_t)lane & ((1u << p.line_shift) - 1u));
-            if (src != 0xFFFFFFFFu && rec < p.n_out) {
-                uint32_t c;
-                asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(c) : "l"(p.line_cnt + ln) : "memory");
-                const float4* sp4 = reinterpret_cast<const float4*>(p.hits + rec);
-                const float4 x = __ldcg(sp4), y = __ldcg(sp4 + 1);
-                store_record(p.host_lines + rec, true, x, y);
-            }
-            for (uint32_t j = 0; j < (32u >> p.line_shift) && m; ++j) m &= m - 1u;
-        }
-    };
-    auto push = [&](uint32_t ref, float tn) {
-        const int rtop = sp & (PL_STK - 1);
-        // ring full: its oldest entry sits exactly where the new one goes
-        if (sp - spilled == PL_STK) { ovf_base[(size_t)slot * PL_OVF + spilled] = sh.stack[rtop][slot]; ++spilled; }
-        sh.stack[rtop][slot] = make_uint2(ref, __float_as_uint(tn));
-        ++sp;
-    };
-    auto pop_one = [&]() {
-        if (sp == 0) { state = ST_DONE; return; }
-        --sp;
-        const int rtop = sp & (PL_STK - 1);
-        uint2 e;
-        if (sp < spilled) { --spilled; e = ovf_base[(size_t)slot * PL_OVF + sp]; }
-        else e = sh.stack[rtop][slot];
-        if (__uint_as_float(e.y) <= tcur) { cur = e.x; state = (e.x & VKHRT_BVH_LEAF) ? ST_LEAF : ST_NODE; }
-    };
-
-    uint32_t nHave = 0, nM = 0;               // lanes holding a ray / a march (warp-uniform)
-    // free lanes pull READY rays
-    auto top_up = [&]() {
-        if (nR == 0u || nHave == 32u) return;
-        const unsigned idle = __ballot_sync(FULL, !has);
-        const uint32_t rank = __popc(idle & lt);
-        if (!has && rank < nR) {
-            slot = dequeue(Q_READY, nR, rank);
-            id = f3(sh.dir[3][slot], sh.dir[4][slot], sh.dir[5][slot]);
-            noid = f3(-(o.x * id.x), -(o.y * id.y), -(o.z * id.z));
-            tcur = sh.tcur[slot]; cur = sh.cur[slot]; sp = (int)sh.sp[slot]; spilled = (int)sh.spilled[slot];
-            state = cur == REF_POP ? ST_POP : ST_NODE;
-            has = true;
-        }
-        const uint32_t taken = min(nR, 32u - nHave);
-        nR -= taken; nHave += taken;
-        __syncwarp();
-    };
-
-    for (;;) {
-        top_up();
-        const uint32_t nRet = exhausted ? nD : nD + nF;
-        if ((nHave | nM | nR | nL | nC | nRet) == 0u) break;
-
-        // ---------------- scheduler ----------------
-        enum : int { PH_NODE, PH_LEAF, PH_SETUP, PH_MARCH, PH_RETIRE };
-        int phase;
-        if (!exhausted && nF >= 32u) phase = PH_RETIRE;                        // fill the pool first
-        else if (nHave >= p.pool_node_lanes) phase = PH_NODE;
-        else {
-            const uint32_t sS = min(nC, 32u - nM);
-            const uint32_t sR = min(nRet, 32u);
-            uint32_t best = nL; int bp = PH_LEAF;
-            if (sS > best) { best = sS; bp = PH_SETUP; }
-            if (nM > best || (nM == 32u)) { best = nM; bp = PH_MARCH; }
-            if (sR > best) { best = sR; bp = PH_RETIRE; }
-            if (best >= p.pool_batch_lanes) phase = bp;
-            else if (nHave >= p.pool_node_min) phase = PH_NODE;
-            else if (best > 0u) phase = bp;
-            else phase = PH_NODE;
-        }
-
-        if (phase == PH_NODE) {
-            // ---------------- internal nodes (same step as trace_kernel) ----------------
-            // stays here, re-filling free lanes from READY, for as long as enough lanes hold a ray
-            do {
-                uint32_t n0 = nHave, n1;
-                do {
-                    if (STATS) { sc_steps[0]++; sc_lanes[0] += __popc(__ballot_sync(FULL, has && state <= ST_POP)); }
-                    if (has) {
-                        if (state == ST_POP) pop_one();
-                        if (state == ST_NODE) {
-                            const float4* nd = p.nodes + 4 * (size_t)cur;
-                            const float4 q0 = __ldg(nd), q1 = __ldg(nd + 1), q2 = __ldg(nd + 2), q3 = __ldg(nd + 3);
-                            if (STATS) st_nodes++;
-                            float tn0, tn1;
-                            const bool h0 = slab_test(xyz(q0), xyz(q1), id, noid, p.tmin, tcur, &tn0);
-                            const bool h1 = slab_test(xyz(q2), xyz(q3), id, noid, p.tmin, tcur, &tn1);
-                            const uint32_t c0 = __float_as_uint(q0.w), c1 = __float_as_uint(q1.w);
-                            const bool both = h0 && h1;
-                            const bool second = both ? (tn1 < tn0) : h1;
-                            const uint32_t near_ref = second ? c1 : c0, far_ref = second ? c0 : c1;
-                            if (both) push(far_ref, second ? tn0 : tn1);
-                            if (h0 || h1) { cur = near_ref; if (near_ref & VKHRT_BVH_LEAF) state = ST_LEAF; }
-                            else state = ST_POP;
-                        }
-                    }
-                    n1 = __popc(__ballot_sync(FULL, has && state <= ST_POP));
-                } while (n1 * 8u >= n0 * p.pool_exit_eighths && n1 > 0u);
-                // rays that left the node state go to their queues; the lane is free again
-                const bool to_leaf = has && state == ST_LEAF, to_done = has && state == ST_DONE;
-                if (to_leaf) { sh.cur[slot] = cur; sh.sp[slot] = (uint8_t)sp; sh.spilled[slot] = (uint8_t)spilled; }
-                enqueue(Q_LEAF, nL, to_leaf, slot);
-                enqueue(Q_DONE, nD, to_done, slot);
-                if (to_leaf || to_done) has = false;
-                nHave = n1;
-                __syncwarp();
-                top_up();
-            } while (nHave >= p.pool_node_lanes);
-        } else if (phase == PH_LEAF) {
-            // ---------------- leaves: Prhi early-out (hair_intersection.rint:20-33, rmax precomputed) ----------------
-            const uint32_t n = min(nL, 32u);
-            const bool act = (uint32_t)lane < n;
-            if (STATS) { sc_steps[1]++; sc_lanes[1] += n; }
-            uint32_t s = 0;
-            bool pass = false;
-            if (act) {
-                s = dequeue(Q_LEAF, nL, (uint32_t)lane);
-                const float3 d = f3(sh.dir[0][s], sh.dir[1][s], sh.dir[2][s]);
-                const uint32_t pos = sh.cur[s] & 0x7FFFFFFFu;
-                const float4 a0 = __ldg(p.primA + 2 * (size_t)pos), a1 = __ldg(p.primA + 2 * (size_t)pos + 1);
-                // mailbox: another piece of the curve tested last gives the same answer; skipped and not counted
-                const bool again = VKHRT_MAILBOX_PHANTOM && __float_as_uint(a1.w) == sh.last_group[s];
-                if (VKHRT_MAILBOX_PHANTOM) sh.last_group[s] = __float_as_uint(a1.w);
-                if (STATS && !again) st_prims++;
-                pass = !again && ray_hits_cylinder(o, d, xyz(a0), xyz(a1), a0.w);
-                if (!pass) sh.cur[s] = REF_POP;
-            }
-            nL -= n;
-            __syncwarp();
-            enqueue(Q_CAND, nC, act && pass, s);
-            enqueue(Q_READY, nR, act && !pass, s);
-            __syncwarp();
-        } else if (phase == PH_SETUP) {
-            // ---------------- candidates: ray-centric transform + quarter-chord filter into free MARCH registers ----------------
-            const unsigned midle = __ballot_sync(FULL, !mhave);
-            const uint32_t rank = __popc(midle & lt);
-            const bool take = !mhave && rank < nC;
-            if (STATS) { sc_steps[1]++; sc_lanes[1] += __popc(__ballot_sync(FULL, take)); }
-            bool reject = false;
-            if (take) {
-                m_slot = dequeue(Q_CAND, nC, rank);
-                const float3 d = f3(sh.dir[0][m_slot], sh.dir[1][m_slot], sh.dir[2][m_slot]);
-                const uint32_t pos = sh.cur[m_slot] & 0x7FFFFFFFu;
-                const float4 a0 = __ldg(p.primA + 2 * (size_t)pos), a1 = __ldg(p.primA + 2 * (size_t)pos + 1);
-                const float4 b0 = __ldg(p.primB + 2 * (size_t)pos), b1 = __ldg(p.primB + 2 * (size_t)pos + 1);
-                Bezier w;
-                w.p0 = xyz(a0); w.p1 = xyz(b0); w.p2 = xyz(b1); w.p3 = xyz(a1);
-                march_begin(ms, make_ray_frame(d), o, w);
-                if (quarter_chords_near_ray(ms.c, p.radius, b0.w)) mhave = true;
-                else { reject = true; sh.cur[m_slot] = REF_POP; }
-            }
-            nC -= min(nC, (uint32_t)__popc(midle));
-            nM = __popc(__ballot_sync(FULL, mhave));
-            __syncwarp();
-            enqueue(Q_READY, nR, reject, m_slot);
-            __syncwarp();
-        } else if (phase == PH_MARCH) {
-            // ---------------- Phantom cone iterations (hair_intersection.rint:56-126) ----------------
-            uint32_t n0 = nM, n1;
-            do {
-                if (STATS) { sc_steps[2]++; sc_lanes[2] += __popc(__ballot_sync(FULL, mhave)); }
-                bool fin = false;
-                if (mhave) {
-                    if (STATS) st_iters++;
-                    float t = 0.0f, u = 0.0f;
-                    const int r = march_step(ms, p.radius, &t, &u);
-                    if (r != MARCH_CONTINUE) {
-                        mhave = false; fin = true;
-                        const uint32_t pos = sh.cur[m_slot] & 0x7FFFFFFFu;       // the slot still points at the candidate's leaf
-                        // hair_intersection.rint:146-148 (report only tHit > 0), reportIntersectionEXT interval, tie rule of `commit`
-                        if (r == MARCH_HIT && t > 0.0f && t >= p.tmin) {
-                            const float tc = sh.tcur[m_slot];
-                            bool take_it = t < tc;
-                            if (t == tc) {
-                                const uint32_t bpos = sh.best_pos[m_slot];
-                                const uint32_t prim = __float_as_uint(__ldg(p.primA + 2 * (size_t)pos + 1).w);
-                                take_it = bpos == PRIM_NONE || prim < __float_as_uint(__ldg(p.primA + 2 * (size_t)bpos + 1).w);
-                            }
-                            if (take_it) { sh.tcur[m_slot] = t; sh.best_pos[m_slot] = pos; sh.best_u[m_slot] = u; }
-                        }
-                        sh.cur[m_slot] = REF_POP;
-                    }
-                }
-                enqueue(Q_READY, nR, fin, m_slot);
-                n1 = __popc(__ballot_sync(FULL, mhave));
-            } while (n1 * 4u >= n0 * 3u && n1 > 0u);
-            nM = n1;
-            __syncwarp();
-        } else {
-            // ---------------- retire finished rays, refill their slots (and free ones) with new primary rays ----------------
-            const uint32_t n_d = min(nD, 32u);
-            const uint32_t n_f = exhausted ? 0u : min(nF, 32u - n_d);
-            const bool act_d = (uint32_t)lane < n_d, act_f = !act_d && (uint32_t)lane - n_d < n_f;
-            if (STATS) { sc_steps[3]++; sc_lanes[3] += n_d + n_f; }
-            uint32_t s = 0;
-            if (act_d) s = dequeue(Q_DONE, nD, (uint32_t)lane);
-            else if (act_f) s = dequeue(Q_FREE, nF, (uint32_t)lane - n_d);
-            nD -= n_d; nF -= n_f;
-            {
-                float rt = __int_as_float(0x7f800000), ru = 0.0f;
-                float3 rn = f3(0, 0, 0);
-                uint32_t rprim = PRIM_NONE, rseg = VKHRT_MISS_SEGMENT, rflags = 0u, oi = 0u;
-                if (act_d) {
-                    const uint32_t pos = sh.best_pos[s];
-                    oi = sh.out_idx[s];
-                    if (pos != PRIM_NONE) {
-                        // hair_intersection.rint:74-76 from the committed (t, u)
-                        rt = sh.tcur[s]; ru = sh.best_u[s];
-                        const float3 d = f3(sh.dir[0][s], sh.dir[1][s], sh.dir[2][s]);
-                        const float4 a0 = __ldg(p.primA + 2 * (size_t)pos), a1 = __ldg(p.primA + 2 * (size_t)pos + 1);
-                        const float4 b0 = __ldg(p.primB + 2 * (size_t)pos), b1 = __ldg(p.primB + 2 * (size_t)pos + 1);
-                        Bezier w;
-                        w.p0 = xyz(a0); w.p1 = xyz(b0); w.p2 = xyz(b1); w.p3 = xyz(a1);
-                        rprim = rseg = __float_as_uint(a1.w);
-                        rn = fnormalize3(fmadd3(rt, d, o) - bezier_point(w, ru));
-                        rflags = FLAG_HIT;
-                        if (STATS) st_hits++;
-                    }
-                }
-                emit(act_d, oi, rt, rseg, ru, rn, rprim, rflags);
-            }
-            const bool want = (act_d || act_f) && !exhausted;
-            const unsigned wm = __ballot_sync(FULL, want);
-            unsigned long long base = 0;
-            if (lane == 0 && wm) base = atomicAdd(p.work, (unsigned long long)__popc(wm));
-            base = __shfl_sync(FULL, base, 0);
-            bool fresh = false, padded = false;
-            uint32_t pad_idx = 0u;
-            if (want) {
-                const unsigned long long slot64 = p.slot_begin + base + (unsigned)__popc(wm & lt);
-                if (slot64 < (unsigned long long)p.n_slots) {
-                    const PixelRef q = slot_to_pixel(p, (uint32_t)slot64);
-                    if (q.valid) {
-                        float3 ro, d;
-                        primary_ray(p.cam, p.W, p.H, q.px, q.py, p.sx, p.sy, &ro, &d);
-                        sh.dir[0][s] = d.x; sh.dir[1][s] = d.y; sh.dir[2][s] = d.z;
-                        sh.dir[3][s] = safe_rcp(d.x); sh.dir[4][s] = safe_rcp(d.y); sh.dir[5][s] = safe_rcp(d.z);
-                        sh.tcur[s] = p.tmax; sh.cur[s] = 0u; sh.sp[s] = 0; sh.spilled[s] = 0;
-                        sh.best_pos[s] = PRIM_NONE; sh.best_u[s] = 0.0f; sh.out_idx[s] = q.out;
-                        if (VKHRT_MAILBOX_PHANTOM) sh.last_group[s] = PRIM_NONE;
-                        fresh = true;
-                        if (STATS) st_rays++;
-                    } else if (p.compact) { padded = true; pad_idx = q.out; }
-                }
-            }
-            if (p.compact) emit(padded, pad_idx, __int_as_float(0x7f800000), VKHRT_MISS_SEGMENT, 0.0f, f3(0, 0, 0), PRIM_NONE, FLAG_PADDING);
-            if (wm && p.slot_begin + base + (unsigned)__popc(wm) >= (unsigned long long)p.n_slots) exhausted = true;
-            __syncwarp();
-            enqueue(Q_READY, nR, fresh, s);
-            enqueue(Q_FREE, nF, (act_d || act_f) && !fresh, s);
-            __syncwarp();
-        }
-    }
-
-    if (STATS) {
-#pragma unroll
-        for (int k = 16; k > 0; k >>= 1) {
-            st_nodes += __shfl_xor_sync(FULL, st_nodes, k); st_prims += __shfl_xor_sync(FULL, st_prims, k);
-            st_iters += __shfl_xor_sync(FULL, st_iters, k); st_hits += __shfl_xor_sync(FULL, st_hits, k);
-            st_rays += __shfl_xor_sync(FULL, st_rays, k);
-        }
-        if (lane == 0) {
-            atomicAdd(p.counters + 1, (unsigned long long)st_nodes); atomicAdd(p.counters + 2, (unsigned long long)st_prims);
-            atomicAdd(p.counters + 3, (unsigned long long)st_hits); atomicAdd(p.counters + 4, (unsigned long long)st_iters);
-            atomicAdd(p.counters + 5, (unsigned long long)st_rays);
-            for (int k = 0; k < 4; ++k) { atomicAdd(p.counters + 8 + k, (unsigned long long)sc_steps[k]); atomicAdd(p.counters + 12 + k, (unsigned long long)sc_lanes[k]); }
-        }
-    }
-}
-
 // ------------------------------------------------------------------------------------------------
-// trace_pool2_kernel: the ray pool with a leaner node step (round 2).  Same queues, same scheduler, same per-ray sequence of
-// node visits and candidate tests as trace_pool_kernel (records AND counters identical); what changed is where the
-// instructions go (ncu source page of round 1: stack push / pop / spill 15.8 % of the warp instructions at 5-7 lanes, loop
-// control and state bookkeeping 8 %):
+// trace_pool_kernel.  Round 2 rewrote the node step of round 1's kernel (same queues, same scheduler, same per-ray sequence of
+// node visits and candidate tests: records AND counters identical); what changed is where the instructions go (ncu source
+// page of round 1: stack push / pop / spill 15.8 % of the warp instructions at 5-7 lanes, loop control and state
+// bookkeeping 8 %):
 //   * a lane's state lives in `cur` alone: internal node index | leaf ref (bit 31) | POP | DONE | IDLE;
 //   * WRITE-THROUGH stack: every push stores the entry both in the slot's shared-memory ring (the top PL_STK entries) and at
 //     its depth in the warp's global spill area ([depth][slot]: lanes of a warp at similar depths share lines, .cg = L2
@@ -794,7 +443,7 @@ __global__ void __launch_bounds__(TR_BLOCK, PL_MINB) trace_pool_kernel(const Tra
 constexpr uint32_t R2_POP = 0x7FFFFFFDu, R2_DONE = 0x7FFFFFFEu, R2_IDLE = 0x7FFFFFFFu;   // cur < R2_POP: internal node
 
 template <int PL_S, int PL_STK>
-struct PoolWarp2 {
+struct PoolWarp {
     uint2 stack[PL_STK][PL_S];         // ring: entry k of the stack sits at [k % PL_STK] while index k >= lo
     float dir[6][PL_S];                // d.xyz, 1/d
     float tcur[PL_S];
@@ -809,14 +458,14 @@ struct PoolWarp2 {
 };
 
 template <bool STATS, int PL_S, int PL_STK, int MINB = PL_MINB>
-__global__ void __launch_bounds__(TR_BLOCK, MINB) trace_pool2_kernel(const TraceParams p)
+__global__ void __launch_bounds__(TR_BLOCK, MINB) trace_pool_kernel(const TraceParams p)
 {
-    __shared__ PoolWarp2<PL_S, PL_STK> sh_all[TR_BLOCK / 32];
+    __shared__ PoolWarp<PL_S, PL_STK> sh_all[TR_BLOCK / 32];
     if (blockIdx.x == 0 && threadIdx.x == 0) *p.work_next = 0ull;
     const unsigned FULL = 0xffffffffu;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const unsigned lt = (1u << lane) - 1u;
-    PoolWarp2<PL_S, PL_STK>& sh = sh_all[warp];
+    PoolWarp<PL_S, PL_STK>& sh = sh_all[warp];
     // spill area of this warp: [depth][slot]
     if (lane == 0) sh.ovf = p.pool_overflow + (size_t)(blockIdx.x * (TR_BLOCK / 32) + (uint32_t)warp) * (size_t)(PL_S * PL_OVF);
     const float3 o = f3(p.cam.vi[12], p.cam.vi[13], p.cam.vi[14]);     // ray_gen.rgen:22: every primary ray starts at the camera
@@ -846,7 +495,13 @@ __global__ void __launch_bounds__(TR_BLOCK, MINB) trace_pool2_kernel(const Trace
         n += __popc(m);
     };
     auto dequeue = [&](int qi, uint32_t n, uint32_t k) -> uint32_t { return sh.q[qi][n - 1u - k]; };   // LIFO (see trace_pool_kernel)
-    // hit-record delivery: see trace_pool_kernel::emit
+    // Write one hit record per calling lane (`wrote`).  With line-wise host delivery the record goes to HBM, the lane counts it
+    // on its 128-byte line with a releasing atomic, and for every line that just became complete four lanes copy its four
+    // records to the host in one 256-bit store instruction = one 128-byte PCIe write (random 32-byte writes reach 12 GB/s,
+    // whole lines from adjacent lanes 44 GB/s: tools/micro/pcie_write.cu).  Called by all lanes of the warp.
+    // (Round 2 also tried counting the lines in shared memory — the four rays of a line always fetched by one warp, the
+    // counting slot held until its line completes: no global atomic, no device-wide fence — and measured it SLOWER, device 1244
+    // vs 1310 and e2e 1148 vs 1180 Mrays/s: refills in groups of four starve the pool and the extra state spills registers.)
     auto emit = [&](bool wrote, uint32_t oi, float t, uint32_t seg, float u, float3 n, uint32_t prim, uint32_t flags) {
         if (!p.line_cnt) { if (wrote) store_hit<false>(p, oi, t, seg, u, n, prim, flags); return; }      // warp-uniform
         bool completes = false;
@@ -1286,7 +941,6 @@ static void fill_params(const DeviceScene& sc, const VkhrtFrameDesc& f, const Re
 // initialisation); the defaults are the shipped configuration.
 struct Tunables {
     int refill_threshold, min_blocks, blocks_per_sm, w_node, w_leaf, w_march;
-    int pool_version;
     int pool, pool_stats, pool_min_ratio, pool_node_lanes, pool_batch_lanes, pool_node_min, pool_exit, pool_cfg, pool_host, carveout;
     int store256, zero_copy, linewise, line_shift;
 };
@@ -1301,7 +955,6 @@ static const Tunables& tun()
         x.w_node = env_int("VKHRT_W_NODE", 16);
         x.w_leaf = env_int("VKHRT_W_LEAF", 32);
         x.w_march = env_int("VKHRT_W_MARCH", 32);
-        x.pool_version = env_int("VKHRT_POOL_V", 2);             // 1 = round 1's trace_pool_kernel, 2 = trace_pool2_kernel
         x.pool = env_int("VKHRT_POOL", 1);                       // Phantom primary rays: trace_pool_kernel
         x.pool_stats = env_int("VKHRT_POOL_STATS", 1);           // scheduler statistics of the pool kernel instead of trace_kernel's
         x.pool_min_ratio = env_int("VKHRT_POOL_MIN_RATIO", 3);
@@ -1365,12 +1018,12 @@ static int launch_trace_t(DeviceScene& sc, TraceParams& p, cudaStream_t st)
     count_launch();
     return VKHRT_OK;
 }
-template <bool STATS, int PL_S, int PL_STK>
+template <bool STATS, int PL_S, int PL_STK, int MINB = PL_MINB>
 static int launch_pool_t(DeviceScene& sc, TraceParams& p, cudaStream_t st)
 {
     const int carve = tun().carveout;
-    if (carve >= 0) VK_CUDA(cudaFuncSetAttribute(trace_pool_kernel<STATS, PL_S, PL_STK>, cudaFuncAttributePreferredSharedMemoryCarveout, carve));
-    int per_sm = blocks_per_sm(trace_pool_kernel<STATS, PL_S, PL_STK>, sc.device);
+    if (carve >= 0) VK_CUDA(cudaFuncSetAttribute(trace_pool_kernel<STATS, PL_S, PL_STK, MINB>, cudaFuncAttributePreferredSharedMemoryCarveout, carve));
+    int per_sm = blocks_per_sm(trace_pool_kernel<STATS, PL_S, PL_STK, MINB>, sc.device);
     if (tun().blocks_per_sm > 0) per_sm = std::min(per_sm, tun().blocks_per_sm);
     unsigned long long want = ((unsigned long long)(p.n_slots - p.slot_begin) + TR_BLOCK - 1) / TR_BLOCK;
     unsigned grid = (unsigned)std::min<unsigned long long>((unsigned long long)sc.sm_count * per_sm, std::max<unsigned long long>(want, 1ull));
@@ -1382,29 +1035,7 @@ static int launch_pool_t(DeviceScene& sc, TraceParams& p, cudaStream_t st)
         sc.pool_overflow_n = ovf;
     }
     p.pool_overflow = sc.d_pool_overflow;
-    trace_pool_kernel<STATS, PL_S, PL_STK><<<grid, TR_BLOCK, 0, st>>>(p);
-    sc.last_trace_was_pool = true;
-    count_launch();
-    return VKHRT_OK;
-}
-template <bool STATS, int PL_S, int PL_STK, int MINB = PL_MINB>
-static int launch_pool2_t(DeviceScene& sc, TraceParams& p, cudaStream_t st)
-{
-    const int carve = tun().carveout;
-    if (carve >= 0) VK_CUDA(cudaFuncSetAttribute(trace_pool2_kernel<STATS, PL_S, PL_STK, MINB>, cudaFuncAttributePreferredSharedMemoryCarveout, carve));
-    int per_sm = blocks_per_sm(trace_pool2_kernel<STATS, PL_S, PL_STK, MINB>, sc.device);
-    if (tun().blocks_per_sm > 0) per_sm = std::min(per_sm, tun().blocks_per_sm);
-    unsigned long long want = ((unsigned long long)(p.n_slots - p.slot_begin) + TR_BLOCK - 1) / TR_BLOCK;
-    unsigned grid = (unsigned)std::min<unsigned long long>((unsigned long long)sc.sm_count * per_sm, std::max<unsigned long long>(want, 1ull));
-    const size_t ovf = (size_t)grid * (TR_BLOCK / 32) * PL_S * PL_OVF;
-    if (sc.pool_overflow_n < ovf) {
-        if (sc.d_pool_overflow) cudaFree(sc.d_pool_overflow);
-        sc.d_pool_overflow = nullptr; sc.pool_overflow_n = 0;
-        VK_CUDA(cudaMalloc(&sc.d_pool_overflow, ovf * sizeof(uint2)));
-        sc.pool_overflow_n = ovf;
-    }
-    p.pool_overflow = sc.d_pool_overflow;
-    trace_pool2_kernel<STATS, PL_S, PL_STK, MINB><<<grid, TR_BLOCK, 0, st>>>(p);
+    trace_pool_kernel<STATS, PL_S, PL_STK, MINB><<<grid, TR_BLOCK, 0, st>>>(p);
     sc.last_trace_was_pool = true;
     count_launch();
     return VKHRT_OK;
@@ -1412,19 +1043,11 @@ static int launch_pool2_t(DeviceScene& sc, TraceParams& p, cudaStream_t st)
 template <bool STATS>
 static int launch_pool(DeviceScene& sc, TraceParams& p, cudaStream_t st)
 {
-    if (tun().pool_version == 2) {
-        switch (tun().pool_cfg) {
-        case 1: return launch_pool2_t<STATS, 56, 8>(sc, p, st);
-        case 2: return launch_pool2_t<STATS, 64, 6>(sc, p, st);
-        case 3: return launch_pool2_t<STATS, 64, 4, 9>(sc, p, st);      // 9 CTAs / SM: 56 registers
-        case 4: return launch_pool2_t<STATS, 56, 4, 10>(sc, p, st);     // 10 CTAs / SM: 48 registers
-        case 5: return launch_pool2_t<STATS, 48, 4, 12>(sc, p, st);     // 12 CTAs / SM: 40 registers
-        default: return launch_pool2_t<STATS, 72, 4>(sc, p, st);
-        }
-    }
-    // slots per warp x shared-memory stack window: 72 x 4 and 56 x 8 both fit 8 CTAs per SM (profiles/experiments/r01_pool_kernel.txt)
+    // slots per warp x shared-memory stack window (profiles/experiments/r02_pool_kernel.txt): 72 x 4 measured best; 56 x 8 and 64 x 6
+    // trade slots for fewer spill reads (-0.5 % / -1 %); 9 / 10 / 12 CTAs per SM at 56 / 48 / 40 registers lose 3 / 16 / 22 %
     switch (tun().pool_cfg) {
     case 1: return launch_pool_t<STATS, 56, 8>(sc, p, st);
+    case 2: return launch_pool_t<STATS, 64, 6>(sc, p, st);
     default: return launch_pool_t<STATS, 72, 4>(sc, p, st);
     }
 }
