@@ -61,7 +61,10 @@ typedef enum VkhrtTechnique {
  * shaders/hair_closest_hit.rchit:21-24). */
 typedef enum VkhrtShadeMode {
     VKHRT_SHADE = 0,
-    VKHRT_SHADE_DEBUG_PRIMID = 1
+    VKHRT_SHADE_DEBUG_PRIMID = 1,
+    VKHRT_SHADE_MATERIAL = 2       /* Shade(normal) * albedo, albedo = material.albedoFactor [* albedo map]: the term
+                                      shaders/triangle_closest_hit.rchit:77-81 computes (and the reference then overwrites
+                                      with the debug colour); see vkhrt_scene_set_material */
 } VkhrtShadeMode;
 
 /* Colour of a ray that hits nothing.  ENVIRONMENT = shaders/miss.rmiss:17-38: equirectangular lookup of
@@ -319,6 +322,21 @@ int  vkhrt_trace_rays_any_hit(VkhrtScene* scene, const float* rays_device, uint6
  * NULL / 0x0 removes the map.  Frames select it with miss_mode = VKHRT_MISS_ENVIRONMENT. */
 int  vkhrt_scene_set_environment(VkhrtScene* scene, const float* rgba32f, uint32_t width, uint32_t height);
 
+/* ---- material: shaders/bindless.glsl:6-32 (Material), the fields the closest-hit shaders read ------------------------------
+ * ProcessMaterial (source/resources/model/model_loader.cpp:58-136) fills albedoFactor from the glTF base colour and
+ * albedoMap from the diffuse texture; triangle_closest_hit.rchit:77-81 forms albedo = albedoFactor * texture(albedoMap, texCoord).
+ * Hair primitives carry no texture coordinates (the DOTS vertices are written with zero UVs, geometry_processor.cpp:246-266;
+ * curves and LSS have none at all), so the lookup is the sampler's value at (0, 0): linear filter, repeat addressing
+ * (include/resources/gpu_resources.hpp:46-50) = the mean of the map's four corner texels, evaluated once per scene.
+ * Frames select the term with shade_mode = VKHRT_SHADE_MATERIAL: colour = Shade(normal) * albedo.rgb. */
+typedef struct VkhrtMaterial {
+    float        albedo_factor[4];       /* Material::albedoFactor                                         */
+    const float* albedo_map_rgba32f;     /* nullable (useAlbedoMap = false); width * height texels, row 0 first, HOST memory */
+    uint32_t     albedo_map_width, albedo_map_height;
+} VkhrtMaterial;
+/* NULL => the default material (albedo 1,1,1,1, no map) */
+int  vkhrt_scene_set_material(VkhrtScene* scene, const VkhrtMaterial* material);
+
 /* ---- strand level of detail on the device, before the build ------------------------------
  * The reference defines but never calls MergeLines / SplitLines / MergeCurvesFast
  * (source/resources/model/geometry_processor.cpp:69-104, 106-121, 158-197).  Applied in this order to the scene's
@@ -352,6 +370,9 @@ void vkhrt_asset_free(VkhrtLineAsset* asset);
 int  vkhrt_image_load_hdr(const char* path, float** rgba_out, uint32_t* width_out, uint32_t* height_out);
 int  vkhrt_image_save_hdr(const char* path, const float* rgba, uint32_t width, uint32_t height);
 void vkhrt_image_free(float* rgba);
+/* OpenEXR, scanline, uncompressed, four FLOAT channels (A, B, G, R): float images (environment maps, linear frames) for tools that
+ * read the reference's HDR inputs */
+int  vkhrt_image_save_exr(const char* path, const float* rgba, uint32_t width, uint32_t height);
 /* the frame the reference presents to its swap chain (source/renderer.cpp:222-231) as an 8-bit RGBA PNG */
 int  vkhrt_image_save_png(const char* path, const uint8_t* rgba8, uint32_t width, uint32_t height);
 /* procedural equirectangular sky, RGBA32F (the reference's .hdr asset is not in its repository) */

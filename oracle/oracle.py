@@ -63,6 +63,7 @@ def lib():
         L.orc_scene_create_lod.restype = C.c_void_p
         L.orc_scene_create_lod.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32, C.c_void_p, C.c_float, C.c_int, C.c_void_p]
         L.orc_scene_set_environment.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32]
+        L.orc_scene_set_material.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32]
         L.orc_scene_line_count.restype = C.c_uint32
         L.orc_scene_line_count.argtypes = [C.c_void_p]
         L.orc_scene_get_lines.argtypes = [C.c_void_p, C.c_void_p]
@@ -183,6 +184,15 @@ class OracleScene:
         e = np.ascontiguousarray(rgba, np.float32)
         assert e.ndim == 3 and e.shape[2] == 4
         lib().orc_scene_set_environment(self._h, e.ctypes.data, e.shape[1], e.shape[0])
+
+    def set_material(self, albedo_factor=(1.0, 1.0, 1.0, 1.0), albedo_map=None):
+        """Material::albedoFactor and an optional RGBA32F albedo map [h, w, 4] (frames use it with shade_mode = 2)"""
+        f = np.ascontiguousarray(albedo_factor, np.float32)
+        if albedo_map is None:
+            lib().orc_scene_set_material(self._h, f.ctypes.data, None, 0, 0)
+        else:
+            m = np.ascontiguousarray(albedo_map, np.float32)
+            lib().orc_scene_set_material(self._h, f.ctypes.data, m.ctypes.data, m.shape[1], m.shape[0])
 
     def environment_miss(self, d):
         a = _f(d); o = (C.c_float * 3)()

@@ -567,3 +567,77 @@ def test_oracle_lod_and_miss_shader_against_the_second_transcription(O, V):
         d = rng.normal(size=3)
         d /= np.linalg.norm(d)
         assert np.abs(sc.environment_miss(d.astype(np.float32)) - G.miss_shader(env, d)).max() < 2e-4
+
+
+def _read_exr_uncompressed(path):
+    """minimal reader for what vkhrt_image_save_exr writes: scanline, NO_COMPRESSION, FLOAT channels"""
+    import struct
+    b = open(path, "rb").read()
+    assert b[:4] == bytes([0x76, 0x2F, 0x31, 0x01]) and struct.unpack_from("<I", b, 4)[0] == 2
+    p = 8
+    attrs = {}
+    while b[p] != 0:
+        e = b.index(0, p); name = b[p:e].decode(); p = e + 1
+        e = b.index(0, p); typ = b[p:e].decode(); p = e + 1
+        size = struct.unpack_from("<i", b, p)[0]; p += 4
+        attrs[name] = (typ, b[p:p + size]); p += size
+    p += 1
+    chans = []
+    c = attrs["channels"][1]; q = 0
+    while c[q] != 0:
+        e = c.index(0, q); chans.append((c[q:e].decode(), struct.unpack_from("<i", c, e + 1)[0])); q = e + 1 + 16
+    assert attrs["compression"][1] == b"\x00" and attrs["lineOrder"][1] == b"\x00"
+    x0, y0, x1, y1 = struct.unpack("<4i", attrs["dataWindow"][1])
+    W, H = x1 - x0 + 1, y1 - y0 + 1
+    offs = struct.unpack_from("<%dQ" % H, b, p)
+    img = {}
+    for y in range(H):
+        yy, size = struct.unpack_from("<ii", b, offs[y])
+        assert yy == y and size == W * 4 * len(chans)
+        row = np.frombuffer(b, "<f4", W * len(chans), offs[y] + 8).reshape(len(chans), W)
+        for k, (nm, ty) in enumerate(chans):
+            assert ty == 2
+            img.setdefault(nm, np.zeros((H, W), np.float32))[y] = row[k]
+    return img, [n for n, _ in chans]
+
+
+def test_exr_writer_round_trip(V, tmp_path):
+    """vkhrt_image_save_exr: header attributes an OpenEXR reader requires, channels in alphabetical order, floats bit-exact"""
+    rng = np.random.default_rng(5)
+    img = rng.standard_normal((7, 13, 4)).astype(np.float32)
+    img[0, 0] = [np.inf, 0.0, -0.0, 1e-38]
+    path = str(tmp_path / "frame.exr")
+    V.save_exr(path, img)
+    planes, names = _read_exr_uncompressed(path)
+    assert names == ["A", "B", "G", "R"]
+    for k, nm in enumerate("RGBA"):
+        assert planes[nm].view(np.uint32).tolist() == img[:, :, k].view(np.uint32).tolist()
+    with pytest.raises(V.VkhrtError):
+        V.save_exr(str(tmp_path / "no" / "dir.exr"), img)
+
+
+def test_oracle_material_albedo_term(O):
+    """triangle_closest_hit.rchit:77-83: albedo = albedoFactor * texture(albedoMap, texCoord); hair has zero UVs, so the linear /
+    repeat sampler returns the mean of the four corner texels.  Shade(n) = abs(n.y) * (0.4, 0.2, 0.1) + 0.3."""
+    pos = np.array([[-1, 150, 0], [1, 150, 0]], np.float32)
+    idx = np.array([[0, 1]], np.uint32)
+    orc = O.OracleScene(pos, idx, technique=1)
+    vi, pi = O.camera_matrices(aspect=1.0)
+    tex = np.zeros((3, 5, 4), np.float32)
+    tex[0, 0] = [1, 0, 0, 1]; tex[0, 4] = [0, 1, 0, 1]; tex[2, 0] = [0, 0, 1, 1]; tex[2, 4] = [1, 1, 1, 1]
+    tex[1, 2] = [9, 9, 9, 9]                                   # interior texels are never touched at uv (0, 0)
+    orc.set_material((0.5, 1.0, 0.25, 1.0), tex)
+    W = H = 33
+    _, img, _ = orc.render(O.make_frame(vi, pi, W, H, shade_mode=2))
+    h, ref, _ = orc.render(O.make_frame(vi, pi, W, H, shade_mode=0))
+    c = (H // 2) * W + W // 2
+    assert h["flags"][c] & 1
+    ny = abs(float(h["ny"][c]))
+    shade = np.array([ny * 0.4 + 0.3, ny * 0.2 + 0.3, ny * 0.1 + 0.3])
+    albedo = np.array([0.5 * 0.5, 1.0 * 0.5, 0.25 * 0.5])       # corner mean = (0.5, 0.5, 0.5)
+    want = np.floor(np.clip(shade * albedo, 0, 1) * 255 + 0.5)
+    assert np.abs(img[c, :3].astype(np.float64) - want).max() <= 1
+    assert img[c, 3] == 255 and not np.array_equal(img, ref)
+    orc.set_material()                                          # default material: albedo 1 -> plain Shade()
+    _, img1, _ = orc.render(O.make_frame(vi, pi, W, H, shade_mode=2))
+    assert np.array_equal(img1, ref)

@@ -270,6 +270,31 @@ def test_per_vertex_radius_all_techniques(V, O, small_groom, tech):
         assert hc.tobytes() == h_ref.tobytes() and np.array_equal(ic, i_ref)
 
 
+@pytest.mark.parametrize("tech", TECHS)
+def test_material_albedo_shading(V, O, small_groom, tech):
+    """shade_mode MATERIAL: Shade(normal) * albedoFactor * texture(albedoMap, (0,0)) (triangle_closest_hit.rchit:77-83)"""
+    pos, idx = small_groom
+    W, H = 200, 120
+    vi, pi = default_camera(V, W, H)
+    rng = np.random.default_rng(3)
+    tex = rng.random((4, 6, 4)).astype(np.float32)
+    with V.Scene(pos, idx, technique=tech) as sc:
+        sc.build()
+        orc = O.OracleScene(pos, idx, technique=tech)
+        for factor, m in (((0.8, 0.5, 0.3, 1.0), None), ((1.0, 0.9, 0.7, 1.0), tex)):
+            sc.set_material(factor, m); orc.set_material(factor, m)
+            for spp in (1, 2):
+                hg, ig, _ = sc.render(V.make_frame(vi, pi, W, H, spp=spp, shade_mode=V.SHADE_MATERIAL, miss_rgb=(0.2, 0.1, 0.0)))
+                ho, io, _ = orc.render(O.make_frame(vi, pi, W, H, spp=spp, shade_mode=2, miss_rgb=(0.2, 0.1, 0.0)))
+                assert_bit_identical(hg, ho)
+                assert np.array_equal(ig, io)
+        _, plain, _ = sc.render(V.make_frame(vi, pi, W, H, shade_mode=V.SHADE))
+        assert not np.array_equal(plain, ig)
+        sc.set_material()
+        _, unit, _ = sc.render(V.make_frame(vi, pi, W, H, shade_mode=V.SHADE_MATERIAL))
+        assert np.array_equal(unit, plain)                       # the default material leaves Shade() unchanged
+
+
 def test_stats_counters_equal_the_oracles(V, O, small_groom):
     """The warp scheduler only interleaves lanes; each ray's own sequence of node visits and candidate tests is the
     oracle's, so the traversal counters (the N_int / N_prim of the bytes-per-ray roofline) are IDENTICAL."""

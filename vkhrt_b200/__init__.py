@@ -5,9 +5,9 @@ This package is the thin Python host binding used by tests and bench.py; it cont
 compute and no CPU fallback: importing `vkhrt_b200.api` without the built library raises.
 """
 from .api import (  # noqa: F401
-    PHANTOM, LSS, DOTS, SHADE, DEBUG_PRIMID, MEM_HOST, MEM_DEVICE, GROOM_STRAIGHT, GROOM_CURLY,
+    PHANTOM, LSS, DOTS, SHADE, DEBUG_PRIMID, SHADE_MATERIAL, MEM_HOST, MEM_DEVICE, GROOM_STRAIGHT, GROOM_CURLY,
     HIT_DTYPE, NODE_DTYPE, FLOATS_PER_PRIM, DEFAULT_SEED,
     VkhrtError, FrameDesc, Scene, FlyCamera, camera_matrices, generate_groom, make_frame,
     frame_local_pixels, device_count, launch_count, library_path, untile, untile_host, render_multi, lib, HostBuffer, SharedBuffer,
-    MISS_CONSTANT, MISS_ENVIRONMENT, load_lines, save_lines, load_hdr, save_hdr, save_png, generate_environment,
+    MISS_CONSTANT, MISS_ENVIRONMENT, load_lines, save_lines, load_hdr, save_hdr, save_png, save_exr, generate_environment,
 )

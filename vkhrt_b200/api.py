@@ -13,7 +13,7 @@ import os
 import numpy as np
 
 PHANTOM, LSS, DOTS = 0, 1, 2
-SHADE, DEBUG_PRIMID = 0, 1
+SHADE, DEBUG_PRIMID, SHADE_MATERIAL = 0, 1, 2
 MEM_HOST, MEM_DEVICE = 0, 1
 MISS_CONSTANT, MISS_ENVIRONMENT = 0, 1
 GROOM_STRAIGHT, GROOM_CURLY = 0, 1
@@ -58,6 +58,10 @@ class LineAsset(C.Structure):
                 ("n_segments", C.c_uint32), ("radius_per_vertex", C.c_void_p), ("n_strands", C.c_uint32)]
 
 
+class Material(C.Structure):
+    _fields_ = [("albedo_factor", C.c_float * 4), ("albedo_map_rgba32f", C.c_void_p), ("albedo_map_width", C.c_uint32), ("albedo_map_height", C.c_uint32)]
+
+
 class BvhView(C.Structure):
     _fields_ = [("n_primitives", C.c_uint32), ("n_nodes", C.c_uint32), ("nodes", C.c_void_p),
                 ("sorted_prim_ids", C.c_void_p), ("sorted_morton", C.c_void_p),
@@ -93,7 +97,7 @@ ABI_SYMBOLS = [
     "vkhrt_render", "vkhrt_render_stats", "vkhrt_frame_local_pixels", "vkhrt_untile", "vkhrt_untile_host", "vkhrt_render_multi", "vkhrt_last_timing",
     "vkhrt_generate_rays", "vkhrt_trace_rays", "vkhrt_trace_rays_any_hit", "vkhrt_camera_matrices", "vkhrt_groom_generate",
     "vkhrt_host_alloc", "vkhrt_host_free", "vkhrt_shared_buffer_create", "vkhrt_shared_buffer_open", "vkhrt_shared_buffer_close", "vkhrt_shared_buffer_destroy",
-    "vkhrt_scene_set_environment", "vkhrt_scene_apply_lod", "vkhrt_scene_segment_count", "vkhrt_scene_get_lines",
+    "vkhrt_scene_set_environment", "vkhrt_scene_set_material", "vkhrt_image_save_exr", "vkhrt_scene_apply_lod", "vkhrt_scene_segment_count", "vkhrt_scene_get_lines",
     "vkhrt_asset_load_lines", "vkhrt_asset_save_lines", "vkhrt_asset_free", "vkhrt_image_load_hdr", "vkhrt_image_save_hdr",
     "vkhrt_image_free", "vkhrt_image_save_png", "vkhrt_environment_generate",
 ]
@@ -149,6 +153,8 @@ def lib():
     L.vkhrt_shared_buffer_close.argtypes = [C.c_int, C.c_void_p]
     L.vkhrt_shared_buffer_destroy.argtypes = [C.c_int, C.c_void_p]
     L.vkhrt_scene_set_environment.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32]
+    L.vkhrt_scene_set_material.argtypes = [C.c_void_p, C.POINTER(Material)]
+    L.vkhrt_image_save_exr.argtypes = [C.c_char_p, C.c_void_p, C.c_uint32, C.c_uint32]
     L.vkhrt_scene_apply_lod.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32]
     L.vkhrt_scene_segment_count.restype = C.c_uint32
     L.vkhrt_scene_segment_count.argtypes = [C.c_void_p]
@@ -269,6 +275,12 @@ def save_hdr(path, rgba):
     _check(lib().vkhrt_image_save_hdr(os.fsencode(path), e.ctypes.data, e.shape[1], e.shape[0]), "vkhrt_image_save_hdr")
 
 
+def save_exr(path, rgba):
+    """float32 [h, w, 4] -> uncompressed scanline OpenEXR with FLOAT channels A, B, G, R"""
+    e = np.ascontiguousarray(rgba, np.float32)
+    _check(lib().vkhrt_image_save_exr(os.fsencode(path), e.ctypes.data, e.shape[1], e.shape[0]), "vkhrt_image_save_exr")
+
+
 def save_png(path, rgba8, width, height):
     img = np.ascontiguousarray(rgba8, np.uint8).reshape(height, width, 4)
     _check(lib().vkhrt_image_save_png(os.fsencode(path), img.ctypes.data, width, height), "vkhrt_image_save_png")
@@ -378,6 +390,19 @@ class Scene:
         if e.ndim != 3 or e.shape[2] != 4:
             raise ValueError("environment map must be [h, w, 4] float32")
         _check(lib().vkhrt_scene_set_environment(self._h, e.ctypes.data, e.shape[1], e.shape[0]), "vkhrt_scene_set_environment")
+        return self
+
+    def set_material(self, albedo_factor=(1.0, 1.0, 1.0, 1.0), albedo_map=None):
+        """Material::albedoFactor and an optional RGBA32F albedo map [h, w, 4]; frames use it with shade_mode = SHADE_MATERIAL"""
+        m = Material()
+        m.albedo_factor[:] = [float(x) for x in albedo_factor]
+        tex = None
+        if albedo_map is not None:
+            tex = np.ascontiguousarray(albedo_map, np.float32)
+            if tex.ndim != 3 or tex.shape[2] != 4:
+                raise ValueError("albedo map must be [h, w, 4] float32")
+            m.albedo_map_rgba32f, m.albedo_map_width, m.albedo_map_height = tex.ctypes.data, tex.shape[1], tex.shape[0]
+        _check(lib().vkhrt_scene_set_material(self._h, C.byref(m)), "vkhrt_scene_set_material")
         return self
 
     def build(self):

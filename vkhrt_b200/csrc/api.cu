@@ -218,6 +218,30 @@ int vkhrt_scene_set_environment(VkhrtScene* scene, const float* rgba32f, uint32_
     return VKHRT_OK;
 }
 
+int vkhrt_scene_set_material(VkhrtScene* scene, const VkhrtMaterial* material)
+{
+    if (!scene) { set_last_error("null scene"); return VKHRT_ERR_INVALID_ARGUMENT; }
+    DeviceScene& sc = scene->s;
+    float a[4] = {1.0f, 1.0f, 1.0f, 1.0f};
+    if (material) {
+        for (int k = 0; k < 4; ++k) a[k] = material->albedo_factor[k];
+        if (material->albedo_map_rgba32f) {
+            const uint32_t W = material->albedo_map_width, H = material->albedo_map_height;
+            if (!W || !H) { set_last_error("albedo map without a size"); return VKHRT_ERR_INVALID_ARGUMENT; }
+            // texture(albedoMap, vec2(0)): texel coordinate -0.5 -> texels W-1 | 0 and H-1 | 0 with weights 1/2 (linear, repeat)
+            const float* m = material->albedo_map_rgba32f;
+            const size_t i0 = W - 1, i1 = 0, j0 = H - 1, j1 = 0;
+            for (int k = 0; k < 4; ++k) {
+                const float t00 = m[4 * (j0 * W + i0) + k], t10 = m[4 * (j0 * W + i1) + k], t01 = m[4 * (j1 * W + i0) + k], t11 = m[4 * (j1 * W + i1) + k];
+                const float top = std::fmaf(0.5f, t10 - t00, t00), bot = std::fmaf(0.5f, t11 - t01, t01);
+                a[k] *= std::fmaf(0.5f, bot - top, top);
+            }
+        }
+    }
+    std::memcpy(sc.albedo, a, sizeof(a));
+    return VKHRT_OK;
+}
+
 void vkhrt_scene_destroy(VkhrtScene* scene)
 {
     if (scene) free_scene(reinterpret_cast<DeviceScene*>(scene));

@@ -424,6 +424,52 @@ int vkhrt_image_save_hdr(const char* path, const float* rgba, uint32_t width, ui
 
 void vkhrt_image_free(float* rgba) { std::free(rgba); }
 
+// OpenEXR 2.0 single-part scanline file, NO_COMPRESSION, four 32-bit FLOAT channels.  Channels are stored in alphabetical order
+// (A, B, G, R), one scanline per block, offsets table in front of the pixel data; everything little-endian.
+int vkhrt_image_save_exr(const char* path, const float* rgba, uint32_t width, uint32_t height)
+{
+    if (!path || !rgba || !width || !height) return fail(VKHRT_ERR_INVALID_ARGUMENT, "null argument");
+    std::vector<unsigned char> out;
+    auto put32 = [&](uint32_t v) { for (int k = 0; k < 4; ++k) out.push_back((unsigned char)(v >> (8 * k))); };
+    auto put64 = [&](uint64_t v) { for (int k = 0; k < 8; ++k) out.push_back((unsigned char)(v >> (8 * k))); };
+    auto putf = [&](float f) { uint32_t u; std::memcpy(&u, &f, 4); put32(u); };
+    auto puts = [&](const char* z) { while (*z) out.push_back((unsigned char)*z++); out.push_back(0); };
+    auto attr = [&](const char* name, const char* type, uint32_t size) { puts(name); puts(type); put32(size); };
+    put32(20000630u);                    // magic 76 2f 31 01
+    put32(2u);                           // version 2, no flags: scanline, single part
+    attr("channels", "chlist", 4 * 18 + 1);
+    for (const char* ch : {"A", "B", "G", "R"}) { puts(ch); put32(2u /* FLOAT */); put32(0u /* pLinear + reserved */); put32(1u); put32(1u); }
+    out.push_back(0);
+    attr("compression", "compression", 1); out.push_back(0);
+    attr("dataWindow", "box2i", 16); put32(0); put32(0); put32(width - 1); put32(height - 1);
+    attr("displayWindow", "box2i", 16); put32(0); put32(0); put32(width - 1); put32(height - 1);
+    attr("lineOrder", "lineOrder", 1); out.push_back(0);
+    attr("pixelAspectRatio", "float", 4); putf(1.0f);
+    attr("screenWindowCenter", "v2f", 8); putf(0.0f); putf(0.0f);
+    attr("screenWindowWidth", "float", 4); putf(1.0f);
+    out.push_back(0);                    // end of header
+    const uint64_t row_bytes = (uint64_t)width * 16, block = 8 + row_bytes;
+    const uint64_t first = out.size() + (uint64_t)height * 8;
+    for (uint32_t y = 0; y < height; ++y) put64(first + (uint64_t)y * block);
+    const size_t header = out.size();
+    out.resize(header + (size_t)(block * height));
+    unsigned char* q = out.data() + header;
+    static const int order[4] = {3, 2, 1, 0};           // A B G R from RGBA
+    for (uint32_t y = 0; y < height; ++y) {
+        const uint32_t yy = y, sz = (uint32_t)row_bytes;
+        std::memcpy(q, &yy, 4); std::memcpy(q + 4, &sz, 4); q += 8;
+        for (int c = 0; c < 4; ++c) {
+            const float* src = rgba + (size_t)y * width * 4 + order[c];
+            for (uint32_t x = 0; x < width; ++x) { std::memcpy(q, src + 4 * (size_t)x, 4); q += 4; }
+        }
+    }
+    FILE* f = std::fopen(path, "wb");
+    if (!f) return fail(VKHRT_ERR_IO, std::string("cannot open for writing: ") + path);
+    bool ok = std::fwrite(out.data(), 1, out.size(), f) == out.size();
+    ok = (std::fclose(f) == 0) && ok;
+    return ok ? VKHRT_OK : fail(VKHRT_ERR_IO, std::string("write failed: ") + path);
+}
+
 int vkhrt_image_save_png(const char* path, const uint8_t* rgba8, uint32_t width, uint32_t height)
 {
     if (!path || !rgba8 || !width || !height) return fail(VKHRT_ERR_INVALID_ARGUMENT, "null argument");

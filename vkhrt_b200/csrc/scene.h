@@ -25,6 +25,9 @@ struct DeviceScene {
     float lod_ms = 0.0f;
     bool lod_applied = false;          // the vertex list was rewritten by the LOD passes: refit with caller positions is refused
 
+    // material (bindless.glsl Material): albedoFactor * albedo map at texCoord (0,0), evaluated when the material is set
+    float albedo[4] = {1.0f, 1.0f, 1.0f, 1.0f};
+
     // environment map (RGBA32F, miss.rmiss)
     float4* d_env = nullptr;
     uint32_t env_w = 0, env_h = 0;

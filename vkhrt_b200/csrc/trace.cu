@@ -828,7 +828,7 @@ __global__ void __launch_bounds__(256) raygen_kernel(const TraceParams p, float4
 // ------------------------------------------------------------------------------------------------
 // One thread per ray slot of this shard (same slot -> pixel map as the traversal kernel), so that a shard only
 // ever touches the pixels it owns whatever the output layout is.
-__global__ void __launch_bounds__(256) shade_kernel(const TraceParams p, const VkhrtHit* __restrict__ hits, int mode, float3 miss,
+__global__ void __launch_bounds__(256) shade_kernel(const TraceParams p, const VkhrtHit* __restrict__ hits, int mode, float3 miss, float3 albedo,
                                                     float4* __restrict__ accum, uchar4* __restrict__ rgba, uint32_t sample, uint32_t spp,
                                                     const uint32_t* __restrict__ occluded, uint32_t ao_samples,
                                                     const float4* __restrict__ env, uint32_t env_w, uint32_t env_h)
@@ -847,6 +847,7 @@ __global__ void __launch_bounds__(256) shade_kernel(const TraceParams p, const V
     float3 c;
     if (flags & FLAG_HIT) {
         c = mode == VKHRT_SHADE_DEBUG_PRIMID ? debug_palette(__float_as_uint(h1.z)) : shade_normal(f3(h0.w, h1.x, h1.y));
+        if (mode == VKHRT_SHADE_MATERIAL) c = f3(c.x * albedo.x, c.y * albedo.y, c.z * albedo.z);     // triangle_closest_hit.rchit:77-83
         if (ao_samples) c = c * (1.0f - (float)occluded[i] / (float)ao_samples);    // unoccluded fraction of the AO rays
     } else if (env) {
         // miss.rmiss: the colour depends on the ray of THIS sample, regenerated here (ray_gen.rgen:16-24)
@@ -1211,7 +1212,7 @@ int render_frame(DeviceScene& sc, const VkhrtFrameDesc& f, VkhrtHit* hits_out, u
         if (s == 0) VK_CUDA(cudaEventRecord(ev[12], st));
         if (want_rgba) {
             const bool env = f.miss_mode == VKHRT_MISS_ENVIRONMENT && sc.d_env;
-            shade_kernel<<<(unsigned)((r.n_slots + 255) / 256), 256, 0, st>>>(p, p.hits, f.shade_mode, miss, sc.d_accum, (uchar4*)d_rgba, s, r.spp,
+            shade_kernel<<<(unsigned)((r.n_slots + 255) / 256), 256, 0, st>>>(p, p.hits, f.shade_mode, miss, make_float3(sc.albedo[0], sc.albedo[1], sc.albedo[2]), sc.d_accum, (uchar4*)d_rgba, s, r.spp,
                                                                               sc.d_occluded, ao, env ? sc.d_env : nullptr, sc.env_w, sc.env_h);
             count_launch();
         }
