@@ -571,7 +571,8 @@ __global__ void __launch_bounds__(REFIT_TILE) materialise_refit_kernel(MeshIn m,
                                                                 float4* __restrict__ primA, float4* __restrict__ primB, float2* __restrict__ primR,
                                                                 float* nodes_f32, const uint32_t* __restrict__ parent_internal,
                                                                 const uint32_t* __restrict__ parent_leaf, uint32_t* flags,
-                                                                const uint8_t* __restrict__ node_local)
+                                                                const uint8_t* __restrict__ node_local,
+                                                                float4* __restrict__ exits /* 2 per entry */, uint32_t* __restrict__ exit_count, uint32_t exit_cap)
 {
     // Everything the walk needs for the nodes INSIDE this CTA's tile of leaves lives in shared memory (index = node - tile base):
     // the parent link and the "local" bit (loaded coalesced), an arrival counter, and both child boxes, which are written to the
@@ -591,11 +592,13 @@ __global__ void __launch_bounds__(REFIT_TILE) materialise_refit_kernel(MeshIn m,
     __syncthreads();
     uint32_t pos = tile_base + threadIdx.x;
     bool walking = pos < n_prims;
+    Aabb box;
+    box.lo = box.hi = f3(0, 0, 0);
+    uint32_t p = 0;
     if (walking) {
     // the leaf's record is its GROUP's (a curve / LSS / strip reached through any of its pieces is tested whole); its box is the piece's
     const uint32_t leaf = sorted_ids[pos];
     const uint32_t prim = leaf / LeafSplit<TECH>::K;
-    Aabb box;
     if (TECH == VKHRT_TECHNIQUE_PHANTOM) {
         Bezier c = gen_curve(m, prim);
         float r0, r1;
@@ -644,26 +647,46 @@ __global__ void __launch_bounds__(REFIT_TILE) materialise_refit_kernel(MeshIn m,
         }
         return;
     }
-    uint32_t p = parent_leaf[pos];
+    // phase 1: up through the nodes inside this tile (shared memory only); a walker that reaches a node shared with other
+    // CTAs parks there (p, box) until the tile's boxes have been written out
+    p = parent_leaf[pos];
     while (walking) {
         const uint32_t node = p >> 1, slot = p & 1u;
         const uint32_t li = node - tile_base;                 // < REFIT_TILE exactly for the nodes indexed inside this tile
-        if (li < (uint32_t)REFIT_TILE && s_local[li]) {
-            // both children of this node come from threads of this CTA: ~50 cycles per level instead of a round trip to L2
-            float* mine = s_box[li] + 6 * slot;
-            mine[0] = box.lo.x; mine[1] = box.lo.y; mine[2] = box.lo.z; mine[3] = box.hi.x; mine[4] = box.hi.y; mine[5] = box.hi.z;
-            __threadfence_block();
-            if (atomicAdd(&s_arrived[li], 1u) == 0u) { walking = false; break; }         // first arrival: the sibling will carry on
-            __threadfence_block();
-            const volatile float* sib = s_box[li] + 6 * (1u - slot);
-            box.lo.x = fminf(box.lo.x, sib[0]); box.lo.y = fminf(box.lo.y, sib[1]); box.lo.z = fminf(box.lo.z, sib[2]);
-            box.hi.x = fmaxf(box.hi.x, sib[3]); box.hi.y = fmaxf(box.hi.y, sib[4]); box.hi.z = fmaxf(box.hi.z, sib[5]);
-            if (node == 0) { walking = false; break; }
-            p = s_parent[li];
-            continue;
+        if (!(li < (uint32_t)REFIT_TILE && s_local[li])) break;
+        // both children of this node come from threads of this CTA: ~50 cycles per level instead of a round trip to L2
+        float* mine = s_box[li] + 6 * slot;
+        mine[0] = box.lo.x; mine[1] = box.lo.y; mine[2] = box.lo.z; mine[3] = box.hi.x; mine[4] = box.hi.y; mine[5] = box.hi.z;
+        __threadfence_block();
+        if (atomicAdd(&s_arrived[li], 1u) == 0u) { walking = false; break; }         // first arrival: the sibling will carry on
+        __threadfence_block();
+        const volatile float* sib = s_box[li] + 6 * (1u - slot);
+        box.lo.x = fminf(box.lo.x, sib[0]); box.lo.y = fminf(box.lo.y, sib[1]); box.lo.z = fminf(box.lo.z, sib[2]);
+        box.hi.x = fmaxf(box.hi.x, sib[3]); box.hi.y = fmaxf(box.hi.y, sib[4]); box.hi.z = fmaxf(box.hi.z, sib[5]);
+        if (node == 0) { walking = false; break; }
+        p = s_parent[li];
+    }
+    }   // if (walking)
+    __syncthreads();
+    // the tile's local nodes: box words 0-2, 4-6, 8-10, 12-14 of each 16-word record, consecutive threads -> consecutive words
+    for (uint32_t k = threadIdx.x; k < (uint32_t)REFIT_TILE * 16u; k += REFIT_TILE) {
+        const uint32_t li = k >> 4, wd = k & 15u;
+        if ((wd & 3u) != 3u && s_local[li]) nodes_f32[(size_t)(tile_base + li) * 16 + wd] = s_box[li][(wd >> 2) * 3 + (wd & 3u)];
+    }
+    // phase 2: the few walkers that left the tile (a handful per CTA) go on through the nodes shared between CTAs in a kernel of
+    // their own (upper_refit_kernel), so that this CTA's 512 threads do not stay resident for one thread's chain of L2 round trips
+    if (walking) {
+        const uint32_t at = atomicAdd(exit_count, 1u);
+        if (at < exit_cap) {
+            exits[2 * (size_t)at] = make_float4(box.lo.x, box.lo.y, box.lo.z, __uint_as_float(p));
+            exits[2 * (size_t)at + 1] = make_float4(box.hi.x, box.hi.y, box.hi.z, 0.0f);
+            walking = false;
         }
-        // a node shared with other CTAs: publish my box in the parent's slot (L2 is the coherence point: .cg stores / loads), then
-        // ONE acq_rel atomic both releases it and, for the second arrival, acquires the sibling's
+    }
+    while (walking) {     // (list full: finish here)
+        const uint32_t node = p >> 1, slot = p & 1u;
+        // publish my box in the parent's slot (L2 is the coherence point: .cg stores / loads), then ONE acq_rel atomic both
+        // releases it and, for the second arrival, acquires the sibling's
         float* nd = nodes_f32 + (size_t)node * 16 + 8 * slot;
         __stcg(reinterpret_cast<float2*>(nd), make_float2(box.lo.x, box.lo.y)); __stcg(nd + 2, box.lo.z);
         __stcg(reinterpret_cast<float2*>(nd + 4), make_float2(box.hi.x, box.hi.y)); __stcg(nd + 6, box.hi.z);
@@ -676,14 +699,35 @@ __global__ void __launch_bounds__(REFIT_TILE) materialise_refit_kernel(MeshIn m,
         box.lo.x = fminf(box.lo.x, l01.x); box.lo.y = fminf(box.lo.y, l01.y); box.lo.z = fminf(box.lo.z, lz);
         box.hi.x = fmaxf(box.hi.x, h01.x); box.hi.y = fmaxf(box.hi.y, h01.y); box.hi.z = fmaxf(box.hi.z, hz);
         if (node == 0) break;
-        p = (li < (uint32_t)REFIT_TILE) ? s_parent[li] : parent_internal[node];
+        p = parent_internal[node];
     }
-    }   // if (walking)
-    __syncthreads();
-    // the tile's local nodes: box words 0-2, 4-6, 8-10, 12-14 of each 16-word record
-    for (uint32_t k = threadIdx.x; k < (uint32_t)REFIT_TILE * 16u; k += REFIT_TILE) {
-        const uint32_t li = k >> 4, wd = k & 15u;
-        if ((wd & 3u) != 3u && s_local[li]) nodes_f32[(size_t)(tile_base + li) * 16 + wd] = s_box[li][(wd >> 2) * 3 + (wd & 3u)];
+}
+
+// the walkers that left their tile: one thread each, up through the nodes shared between CTAs
+__global__ void __launch_bounds__(256) upper_refit_kernel(const float4* __restrict__ exits, const uint32_t* __restrict__ exit_count, uint32_t exit_cap,
+                                                          float* nodes_f32, const uint32_t* __restrict__ parent_internal, uint32_t* flags)
+{
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= min(*exit_count, exit_cap)) return;
+    const float4 e0 = exits[2 * (size_t)i], e1 = exits[2 * (size_t)i + 1];
+    Aabb box;
+    box.lo = xyz(e0); box.hi = xyz(e1);
+    uint32_t p = __float_as_uint(e0.w);
+    for (;;) {
+        const uint32_t node = p >> 1, slot = p & 1u;
+        float* nd = nodes_f32 + (size_t)node * 16 + 8 * slot;
+        __stcg(reinterpret_cast<float2*>(nd), make_float2(box.lo.x, box.lo.y)); __stcg(nd + 2, box.lo.z);
+        __stcg(reinterpret_cast<float2*>(nd + 4), make_float2(box.hi.x, box.hi.y)); __stcg(nd + 6, box.hi.z);
+        uint32_t arrived;
+        asm volatile("atom.acq_rel.gpu.global.add.u32 %0, [%1], 1;" : "=r"(arrived) : "l"(flags + node) : "memory");
+        if (arrived == 0u) return;
+        const float* sb = nodes_f32 + (size_t)node * 16 + 8 * (1u - slot);
+        const float2 l01 = __ldcg(reinterpret_cast<const float2*>(sb)), h01 = __ldcg(reinterpret_cast<const float2*>(sb + 4));
+        const float lz = __ldcg(sb + 2), hz = __ldcg(sb + 6);
+        box.lo.x = fminf(box.lo.x, l01.x); box.lo.y = fminf(box.lo.y, l01.y); box.lo.z = fminf(box.lo.z, lz);
+        box.hi.x = fmaxf(box.hi.x, h01.x); box.hi.y = fmaxf(box.hi.y, h01.y); box.hi.z = fmaxf(box.hi.z, hz);
+        if (node == 0) return;
+        p = parent_internal[node];
     }
 }
 
@@ -744,7 +788,8 @@ int build_scene(DeviceScene& sc, bool refit_only)
                      o_pleaf = o_pint + up((size_t)sc.n_nodes * 4), o_flags = o_pleaf + up((size_t)n * 4), o_primA = o_flags + up((size_t)sc.n_nodes * 4),
                      o_primB = o_primA + up((size_t)n * primA_per * 16), o_primR = o_primB + (tech == VKHRT_TECHNIQUE_PHANTOM ? up((size_t)n * 32) : 0),
                      o_local = o_primR + ((tech == VKHRT_TECHNIQUE_PHANTOM && sc.d_radius_pv) ? up((size_t)n * 8) : 0),
-                     total = o_local + up((size_t)sc.n_nodes);
+                     o_exits = o_local + up((size_t)sc.n_nodes), o_exit_count = o_exits + up(((size_t)n / 8 + 4096) * 32),
+                     total = o_exit_count + 256;
         if (sc.arena_bytes < total) {
             if (sc.d_arena) cudaFree(sc.d_arena);
             sc.d_arena = nullptr; sc.arena_bytes = 0;
@@ -757,6 +802,8 @@ int build_scene(DeviceScene& sc, bool refit_only)
         sc.d_primB = tech == VKHRT_TECHNIQUE_PHANTOM ? (float4*)(sc.d_arena + o_primB) : nullptr;
         sc.d_primR = (tech == VKHRT_TECHNIQUE_PHANTOM && sc.d_radius_pv) ? (float2*)(sc.d_arena + o_primR) : nullptr;
         sc.d_node_local = (uint8_t*)(sc.d_arena + o_local);
+        sc.d_refit_exits = (float4*)(sc.d_arena + o_exits); sc.d_refit_exit_count = (uint32_t*)(sc.d_arena + o_exit_count);
+        sc.refit_exit_cap = (uint32_t)std::min<size_t>((size_t)n / 8 + 4096, 0x7FFFFFFFu);
 
         // ... and one for the build's scratch, kept with the scene (a per-frame rebuild of a dynamic groom allocates nothing)
         const uint32_t os_tiles = cdiv(n, OS_TILE);
@@ -823,14 +870,17 @@ int build_scene(DeviceScene& sc, bool refit_only)
     }
     // 4 materialise + refit
     VK_CUDA(cudaMemsetAsync(sc.d_refit_flags, 0, (size_t)sc.n_nodes * 4, st));
+    VK_CUDA(cudaMemsetAsync(sc.d_refit_exit_count, 0, 4, st));
     const uint32_t g = cdiv(n, REFIT_TILE);
     if (tech == VKHRT_TECHNIQUE_PHANTOM)
-        materialise_refit_kernel<VKHRT_TECHNIQUE_PHANTOM><<<g, REFIT_TILE, 0, st>>>(m, n, sc.d_sorted_ids, sc.d_primA, sc.d_primB, sc.d_primR, (float*)sc.d_nodes, sc.d_parent_internal, sc.d_parent_leaf, sc.d_refit_flags, sc.d_node_local);
+        materialise_refit_kernel<VKHRT_TECHNIQUE_PHANTOM><<<g, REFIT_TILE, 0, st>>>(m, n, sc.d_sorted_ids, sc.d_primA, sc.d_primB, sc.d_primR, (float*)sc.d_nodes, sc.d_parent_internal, sc.d_parent_leaf, sc.d_refit_flags, sc.d_node_local, sc.d_refit_exits, sc.d_refit_exit_count, sc.refit_exit_cap);
     else if (tech == VKHRT_TECHNIQUE_LSS)
-        materialise_refit_kernel<VKHRT_TECHNIQUE_LSS><<<g, REFIT_TILE, 0, st>>>(m, n, sc.d_sorted_ids, sc.d_primA, sc.d_primB, sc.d_primR, (float*)sc.d_nodes, sc.d_parent_internal, sc.d_parent_leaf, sc.d_refit_flags, sc.d_node_local);
+        materialise_refit_kernel<VKHRT_TECHNIQUE_LSS><<<g, REFIT_TILE, 0, st>>>(m, n, sc.d_sorted_ids, sc.d_primA, sc.d_primB, sc.d_primR, (float*)sc.d_nodes, sc.d_parent_internal, sc.d_parent_leaf, sc.d_refit_flags, sc.d_node_local, sc.d_refit_exits, sc.d_refit_exit_count, sc.refit_exit_cap);
     else
-        materialise_refit_kernel<VKHRT_TECHNIQUE_DOTS><<<g, REFIT_TILE, 0, st>>>(m, n, sc.d_sorted_ids, sc.d_primA, sc.d_primB, sc.d_primR, (float*)sc.d_nodes, sc.d_parent_internal, sc.d_parent_leaf, sc.d_refit_flags, sc.d_node_local);
-    count_launch();
+        materialise_refit_kernel<VKHRT_TECHNIQUE_DOTS><<<g, REFIT_TILE, 0, st>>>(m, n, sc.d_sorted_ids, sc.d_primA, sc.d_primB, sc.d_primR, (float*)sc.d_nodes, sc.d_parent_internal, sc.d_parent_leaf, sc.d_refit_flags, sc.d_node_local, sc.d_refit_exits, sc.d_refit_exit_count, sc.refit_exit_cap);
+    // the walkers that left their tiles (their number is only known on the device: the grid covers the list's capacity, idle threads return at once)
+    if (n > 1) upper_refit_kernel<<<cdiv(sc.refit_exit_cap, 256), 256, 0, st>>>(sc.d_refit_exits, sc.d_refit_exit_count, sc.refit_exit_cap, (float*)sc.d_nodes, sc.d_parent_internal, sc.d_refit_flags);
+    count_launch(2);
     VK_CUDA(cudaEventRecord(ev[5], st));
     VK_CUDA(cudaStreamSynchronize(st));
     VK_CUDA(cudaGetLastError());

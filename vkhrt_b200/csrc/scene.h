@@ -40,6 +40,7 @@ struct DeviceScene {
     uint32_t* d_parent_internal = nullptr;  // n_nodes: (parent << 1) | slot
     uint32_t* d_parent_leaf = nullptr;      // n_leaves
     uint32_t* d_refit_flags = nullptr;      // n_nodes
+    float4* d_refit_exits = nullptr; uint32_t* d_refit_exit_count = nullptr; uint32_t refit_exit_cap = 0;   // walkers that leave their refit tile
     uint8_t* d_node_local = nullptr;        // n_nodes: 1 = the node's leaf range lies inside one refit tile (handled in shared memory)
     float scene_lo[3] = {0, 0, 0}, scene_hi[3] = {0, 0, 0};
     uint32_t h_bounds[6] = {};            // centroid bounds as ordered uints, copied back at the end of a build
