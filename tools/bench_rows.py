@@ -4,7 +4,7 @@ LBVH build, refit, strand LOD passes, shading with the constant / environment mi
 All times are CUDA-event times reported by the library (vkhrt_last_timing); bytes are ALGORITHMIC bytes per element
 (stated per row below), so GB/s can be read against the measured HBM peak in MEASURED_PEAKS.json.
 
-    python tools/bench_rows.py [--strands 100000] [--segments 32] [--reps 5] > profiles/r01_rows.json
+    python tools/bench_rows.py [--strands 100000] [--segments 32] [--reps 5] > profiles/r02_rows.json
 """
 import argparse
 import json
@@ -51,17 +51,20 @@ def main():
             return sc.timing()
     ts = [build_once() for _ in range(a.reps)]
     t = min(ts, key=lambda d: d["build_total_ms"])
-    rows.append(row("lbvh_build_total", t["build_total_ms"], n, 300, "curves",
-                    "gen+centroid 64 B, morton 28 B, 8 sort passes x 24 B, karras 24 B write, materialise+refit ~ 180 B"))
-    rows.append(row("lbvh_sort", t["sort_ms"], n, 8 * 24, "keys", "8 LSD passes x (12 B read + 12 B write); histogram pass re-reads 8 B"))
-    rows.append(row("lbvh_materialise_refit", t["refit_ms"], n, 64 + 64 + 64 + 16, "curves",
+    nl = 2 * n                       # BVH leaves: VKHRT_LEAF_SPLIT_PHANTOM = 2 pieces per curve
+    rows.append(row("lbvh_build_total", t["build_total_ms"], nl, 64 + 28 + 8 * 24 + 8 + 24 + 208, "leaves",
+                    "gen+centroid 64 B, morton 28 B, onesweep: 8 B histogram read + 8 passes x 24 B, karras 24 B write, materialise+refit 208 B"))
+    rows.append(row("lbvh_geometry_centroids", t["geometry_ms"], nl, 64, "leaves", "curve generation from 4 vertices through the index pairs, piece box, centroid out (16 B)"))
+    rows.append(row("lbvh_sort", t["sort_ms"], nl, 8 * 24 + 8, "keys", "onesweep: one histogram read (8 B) + 8 digit passes x (12 B read + 12 B write), decoupled look-back"))
+    rows.append(row("lbvh_karras", t["hierarchy_ms"], nl, 24 + 16, "leaves", "neighbour keys read (L1/L2), child refs + parents + local bit written"))
+    rows.append(row("lbvh_materialise_refit", t["refit_ms"], nl, 64 + 64 + 64 + 16, "leaves",
                     "4 vertices + indices in (~64 B), primA+primB out (64 B), node boxes written (64 B) and parents read (16 B)"))
     with V.Scene(pos, idx) as sc:
         sc.build()
         def refit():
             sc.refit(pos)
             return sc.timing()["refit_ms"]
-        rows.append(row("refit_only", best(refit), n, 64 + 64 + 64 + 16, "curves", "vkhrt_scene_refit: the materialise+refit kernel alone (H2D of the positions not included)"))
+        rows.append(row("refit_only", best(refit), nl, 64 + 64 + 64 + 16, "leaves", "vkhrt_scene_refit: materialise_refit_kernel + upper_refit_kernel (H2D of the positions not included)"))
 
         # --- shading rows at 1080p ---
         env = V.generate_environment(2048, 1024)

@@ -4,7 +4,7 @@ tag=$1; shift
 mkdir -p gpurun_out
 for w in ${*:-c1 c3 c4 c5}; do
   steps=10; [ $w = c5 ] && steps=2
-  timeout 900 python bench.py --workload $w --steps $steps --warmup 3 --no-cpu-baseline > gpurun_out/${tag}_$w.json 2> gpurun_out/${tag}_$w.err
+  timeout 900 python bench.py --workload $w --steps $steps --warmup 3 --no-strong-c5 $EXTRA > gpurun_out/${tag}_$w.json 2> gpurun_out/${tag}_$w.err
   echo "$w rc=$?"; python -c "
 import json,sys
 d=json.load(open('gpurun_out/${tag}_$w.json')); r=d['roofline']
