@@ -12,6 +12,10 @@
 #include <algorithm>
 #include <cmath>
 
+#ifndef VKHRT_LINE_PROTOCOL
+#define VKHRT_LINE_PROTOCOL 1      // line-wise host delivery: 0 = round 1 (fence + acq_rel count + acquire load), 1 = release-only count
+#endif
+
 namespace vkhrt {
 
 constexpr int TR_BLOCK = 128;          // 4 warps per CTA
@@ -508,10 +512,16 @@ __global__ void __launch_bounds__(TR_BLOCK, MINB) trace_pool_kernel(const TraceP
         uint32_t line = 0;
         if (wrote) {
             store_hit<false>(p, oi, t, seg, u, n, prim, flags);
-            __threadfence();
             line = oi >> p.line_shift;
             uint32_t old;
+#if VKHRT_LINE_PROTOCOL == 0
+            __threadfence();
             asm volatile("atom.acq_rel.gpu.global.add.u32 %0, [%1], 1;" : "=r"(old) : "l"(p.line_cnt + line) : "memory");
+#else
+            // RELEASE only: the count publishes this lane's record (one MEMBAR, no L1 invalidation).  Whoever sees the line's last
+            // count reads the records with ld.cg — L2 is the coherence point, so there is nothing in L1 to invalidate on that side.
+            asm volatile("atom.release.gpu.global.add.u32 %0, [%1], 1;" : "=r"(old) : "l"(p.line_cnt + line) : "memory");
+#endif
             completes = old + 1u == min(1u << p.line_shift, p.n_out - (line << p.line_shift));
         }
         unsigned m = __ballot_sync(FULL, completes);
@@ -520,8 +530,10 @@ __global__ void __launch_bounds__(TR_BLOCK, MINB) trace_pool_kernel(const TraceP
             const uint32_t ln = __shfl_sync(FULL, line, src & 31u);
             const uint32_t rec = (ln << p.line_shift) + ((uint32_t)lane & ((1u << p.line_shift) - 1u));
             if (src != 0xFFFFFFFFu && rec < p.n_out) {
+#if VKHRT_LINE_PROTOCOL == 0
                 uint32_t c;
                 asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(c) : "l"(p.line_cnt + ln) : "memory");
+#endif
                 const float4* sp4 = reinterpret_cast<const float4*>(p.hits + rec);
                 const float4 x = __ldcg(sp4), y = __ldcg(sp4 + 1);
                 store_record(p.host_lines + rec, true, x, y);
