@@ -42,8 +42,9 @@ class TraceStats(C.Structure):
 def build(force=False):
     src = os.path.join(_HERE, "vkhrt_oracle.cpp")
     hdr = os.path.join(_HERE, "..", "include", "vkhrt_b200.h")
+    incs = [os.path.join(_HERE, f) for f in ("vkhrt_oracle_studies_traversal.inc", "vkhrt_oracle_studies_api.inc")]
     if (force or not os.path.exists(_LIB_PATH)
-            or any(os.path.exists(p) and os.path.getmtime(p) > os.path.getmtime(_LIB_PATH) for p in (src, hdr))):
+            or any(os.path.exists(p) and os.path.getmtime(p) > os.path.getmtime(_LIB_PATH) for p in [src, hdr] + incs)):
         subprocess.check_call(["make", "-C", _HERE, "-B" if force else "-s", "all"] if force else ["make", "-s", "-C", _HERE, "all"])
     return _LIB_PATH
 

@@ -133,6 +133,45 @@ def test_tile_shards_and_untile(V, O, small_groom, world):
         assert np.array_equal(oi.cpu().numpy(), full_i)
 
 
+def test_untile_with_one_shard_is_a_plain_copy(V, small_groom):
+    """vkhrt_untile(world = 1): a one-shard render is never compact (tile_stride 1 writes row-major, W*H records), so the device
+    untile must be a plain copy like vkhrt_untile_host — on a frame whose size is not a multiple of the tile size (ADVICE r1:
+    the tiled index arithmetic scrambled the image and read past the W*H source)."""
+    import torch
+    pos, idx = small_groom
+    W, H, T = 203, 117, 32
+    vi, pi = default_camera(V, W, H)
+    with V.Scene(pos, idx, technique=V.LSS) as sc:
+        sc.build()
+        h, img, _ = sc.render(V.make_frame(vi, pi, W, H, tile_size=T))
+    f = V.make_frame(vi, pi, W, H, tile_size=T)
+    st = torch.cuda.current_stream().cuda_stream
+    for arr, elem in ((h.view(np.uint8).reshape(-1, 32), 32), (img, 4)):
+        src = torch.from_numpy(np.ascontiguousarray(arr)).cuda()              # exactly W*H elements: nothing to read beyond
+        dst = torch.zeros_like(src)
+        V.untile(f, 1, src.data_ptr(), dst.data_ptr(), elem, st)
+        torch.cuda.synchronize()
+        assert torch.equal(src, dst)
+        assert np.array_equal(V.untile_host(f, 1, arr.reshape(-1).view(V.HIT_DTYPE) if elem == 32 else arr).view(np.uint8).reshape(-1, elem), arr)
+
+
+def test_candidate_filter_is_neutral_for_thin_long_segments(V, O):
+    """The quarter-chord candidate filter (not in the reference) must never drop a hit Prhi reports.  Its bound has to cover the
+    convergence tolerance: an accepted hit lies sqrt(r^2 + (5e-5 |B'|)^2) from B(t), which matters when segments are long and thin
+    (length / radius beyond ~900).  Radius 0.001 and 0.0004 on 1.5-unit segments (L / r = 1500 and 3750), grazing rays
+    included by the dense frame; the oracle has no filter."""
+    pos, idx = V.generate_groom(3000, 4, V.GROOM_CURLY)          # 6 units of strand in 4 segments
+    W, H = 640, 400
+    vi, pi = default_camera(V, W, H)
+    for r in (0.001, 0.0004):
+        with V.Scene(pos, idx, technique=V.PHANTOM, radius=r) as sc:
+            sc.build()
+            hg, _, _ = sc.render(V.make_frame(vi, pi, W, H), rgba=False)
+        ho, _, _ = O.OracleScene(pos, idx, technique=0, radius=r).render(O.make_frame(vi, pi, W, H), rgba=False)
+        assert (ho["flags"] & 1).sum() > 500
+        assert_bit_identical(hg, ho)
+
+
 def test_device_outputs_and_wavefront_api(V, O, small_groom):
     import torch
     pos, idx = small_groom
