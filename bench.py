@@ -55,11 +55,11 @@ def frame_size(base_w, base_h, n):
     return w, h
 
 
-def workload_desc(name, n, w, h):
+def workload_desc(name, n, w, h, tile=64):
     s, g, style, _, _, tech, spp, rgba = WORKLOADS[name]
     return (f"{name}: synthetic {style} groom {s} strands x {g} segments ({s * g} segs), {tech} intersector, "
             f"{w}x{h} primary rays x {spp} spp, {'hit buffer + RGBA8' if rgba else 'hit buffer only'}"
-            + (f", 64x64 tiles round-robin over {n} GPUs" if n > 1 else ""))
+            + (f", {tile}x{tile} tiles round-robin over {n} GPUs" if n > 1 else ""))
 
 
 def peaks():
@@ -219,7 +219,9 @@ def strong_c5(V, torch, dist, world, rank, local_rank, dev, stream, steps, warmu
     del pos, idx
     scene.build()
     build_ms = scene.timing()["build_total_ms"]
-    sharded = ShardedRenderer(scene, W, H, tile=64, spp=spp, want_rgba=want_rgba, device=dev, mode="peer")
+    from vkhrt_b200.multi import TileSharding
+    T = TileSharding.balanced_tile(W, world, 64)       # 3840 / 64 = 60 tiles per row would give 2 / 4 ranks vertical stripes
+    sharded = ShardedRenderer(scene, W, H, tile=T, spp=spp, want_rgba=want_rgba, device=dev, mode="peer")
     fd = sharded.make_frame(vi, pi, stream.cuda_stream)
 
     def barrier():
@@ -291,7 +293,6 @@ def strong_c5(V, torch, dist, world, rank, local_rank, dev, stream, steps, warmu
             b.record(stream)
             torch.cuda.synchronize()
             single_ms = a.elapsed_time(b)
-            T = 64
             tiles = ((H + T - 1) // T) * ((W + T - 1) // T)
             same_h = bool(torch.equal(d_h, o_hits)); same_i = bool(torch.equal(d_i, o_rgba))
             same_host = bool(torch.equal(h_hits, d_h.cpu())) and bool(torch.equal(h_rgba, d_i.cpu()))
@@ -301,7 +302,7 @@ def strong_c5(V, torch, dist, world, rank, local_rank, dev, stream, steps, warmu
                          "single_gpu_ms": single_ms, "single_gpu_mrays": rays / (single_ms * 1e-3) / 1e6}
         dist.barrier()
     if rank == 0:
-        out = {"workload": workload_desc("c5", world, W, H), "scaling": "strong", "value": value, "unit": "Mrays/s",
+        out = {"workload": workload_desc("c5", world, W, H, T), "scaling": "strong", "tile": T, "value": value, "unit": "Mrays/s",
                "ms_per_frame": total_ms / steps, "frames_timed": steps, "rays_per_frame": rays, "build_ms": build_ms,
                "frame_ms_min_max_over_ranks": [float(lo.item()), float(hi.item())],
                "own_shard_ms_min_max_over_ranks": [float(own_lo.item()), float(own_hi.item())],
@@ -374,10 +375,10 @@ def main():
     n_leaves = scene.n_leaves
 
     # a non-default stream: the ABI treats a NULL stream handle as "use the scene's own stream"
-    from vkhrt_b200.multi import ShardedRenderer, SharedHostFrame
+    from vkhrt_b200.multi import ShardedRenderer, SharedHostFrame, TileSharding
     stream = torch.cuda.Stream(device=dev)
     torch.cuda.set_stream(stream)
-    T = 64
+    T = TileSharding.balanced_tile(W, world, 64)
     sharded = ShardedRenderer(scene, W, H, tile=T, spp=spp, want_rgba=want_rgba, device=dev, mode=args.gather)
     fd = sharded.make_frame(vi, pi, stream.cuda_stream)
     n_local = sharded.layout.shard_pixels
@@ -524,7 +525,7 @@ def main():
             "metric": "Mrays/s primary-ray hair hits", "value": value, "unit": "Mrays/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": total_ms / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": workload_desc(name, world, W, H), "rays_per_step": rays_per_step, "rays_per_gpu_per_step": rays_per_step // world,
+            "config": {"workload": workload_desc(name, world, W, H, T), "rays_per_step": rays_per_step, "rays_per_gpu_per_step": rays_per_step // world,
                        "l2": "256 MB flush between timed frames; scene is %.0f MB (%d BVH leaves: a 64-byte node and a %d-byte primitive record each)" % (n_leaves * (64 + LEAF_RECORD_BYTES[tech]) / 1e6, n_leaves, LEAF_RECORD_BYTES[tech]),
                        "seed": hex(V.DEFAULT_SEED), "build_ms": build_timing["build_total_ms"],
                        "traversal_kernel": ("value: trace_pool2_kernel (per-warp ray pool) for Phantom frames of >= 3x the pool's resident capacity, else "

@@ -39,6 +39,11 @@ struct TraceParams {
     uint32_t W, H;
     float sx, sy, tmin, tmax;
     uint32_t T, tiles_x, n_tiles, tile_first, tile_stride, compact;
+    // several samples of the frame in ONE launch (samples >= 1 of small or sharded frames, so that the persistent kernel does not
+    // ramp up and drain once per sample): slot = b * slots_per_sample + slot of the pixel, b-th sample offset (bsx, bsy)[b],
+    // record at hits[b * n_out + out].  n_batch <= 1: one sample, offset (sx, sy)
+    uint32_t n_batch, slots_per_sample;
+    float bsx[8], bsy[8];
     // ambient-occlusion mode (SRC_AO): rays are generated from the primary hit records
     const VkhrtHit* ao_hits;        // indexed like `hits`
     uint32_t* ao_occluded;          // per pixel: += 1 for every occluded AO ray (zeroed by the host before the passes)
@@ -363,11 +368,13 @@ __global__ void __launch_bounds__(TR_BLOCK, MINB) trace_kernel(const TraceParams
                             }
                         }
                     } else {
-                        const PixelRef q = slot_to_pixel(p, slot);
+                        uint32_t b = 0u, ls = slot;
+                        if (p.n_batch > 1u) { b = slot / p.slots_per_sample; ls = slot - b * p.slots_per_sample; }
+                        const PixelRef q = slot_to_pixel(p, ls);
                         valid = q.valid;
-                        out_idx = q.out;
+                        out_idx = q.out + b * p.n_out;
                         if (valid) {
-                            primary_ray(p.cam, p.W, p.H, q.px, q.py, p.sx, p.sy, &o, &d);
+                            primary_ray(p.cam, p.W, p.H, q.px, q.py, p.n_batch > 1u ? p.bsx[b] : p.sx, p.n_batch > 1u ? p.bsy[b] : p.sy, &o, &d);
                             tmin = p.tmin; tcur = p.tmax;
                         } else if (p.compact) {
                             store_hit(p, out_idx, __int_as_float(0x7f800000), VKHRT_MISS_SEGMENT, 0.0f, f3(0, 0, 0), PRIM_NONE, FLAG_PADDING);
@@ -779,10 +786,13 @@ __global__ void __launch_bounds__(TR_BLOCK, MINB) trace_pool_kernel(const TraceP
             if (want) {
                 const unsigned long long slot64 = p.slot_begin + base + (unsigned)__popc(wm & lt);
                 if (slot64 < (unsigned long long)p.n_slots) {
-                    const PixelRef q = slot_to_pixel(p, (uint32_t)slot64);
+                    uint32_t b = 0u, ls = (uint32_t)slot64;
+                    if (p.n_batch > 1u) { b = ls / p.slots_per_sample; ls -= b * p.slots_per_sample; }
+                    PixelRef q = slot_to_pixel(p, ls);
+                    q.out += b * p.n_out;
                     if (q.valid) {
                         float3 ro, d;
-                        primary_ray(p.cam, p.W, p.H, q.px, q.py, p.sx, p.sy, &ro, &d);
+                        primary_ray(p.cam, p.W, p.H, q.px, q.py, p.n_batch > 1u ? p.bsx[b] : p.sx, p.n_batch > 1u ? p.bsy[b] : p.sy, &ro, &d);
                         sh.dir[0][s] = d.x; sh.dir[1][s] = d.y; sh.dir[2][s] = d.z;
                         sh.dir[3][s] = safe_rcp(d.x); sh.dir[4][s] = safe_rcp(d.y); sh.dir[5][s] = safe_rcp(d.z);
                         sh.tcur[s] = p.tmax; sh.cur[s] = 0u; sh.sp[s] = 0; sh.lo[s] = 0;
@@ -946,7 +956,7 @@ static void fill_params(const DeviceScene& sc, const VkhrtFrameDesc& f, const Re
     p.W = r.W; p.H = r.H; p.sx = 0.5f; p.sy = 0.5f; p.tmin = r.tmin; p.tmax = r.tmax;
     p.T = r.T; p.tiles_x = r.tiles_x; p.n_tiles = r.n_tiles; p.tile_first = r.tile_first; p.tile_stride = r.tile_stride; p.compact = r.compact ? 1u : 0u;
     p.rays = nullptr; p.slot_begin = 0; p.n_slots = (uint32_t)r.n_slots; p.hits = nullptr; p.hits_mirror = nullptr; p.counters = sc.d_counters;
-    p.host_dest = 0u; p.hits_aligned32 = 0u; p.pool_overflow = nullptr; p.line_cnt = nullptr; p.host_lines = nullptr; p.n_out = (uint32_t)r.n_out; p.line_shift = 2u;
+    p.host_dest = 0u; p.hits_aligned32 = 0u; p.pool_overflow = nullptr; p.line_cnt = nullptr; p.host_lines = nullptr; p.n_out = (uint32_t)r.n_out; p.n_batch = 1u; p.slots_per_sample = (uint32_t)r.n_slots; p.line_shift = 2u;
     p.ao_hits = nullptr; p.ao_occluded = nullptr; p.ao_index = p.ao_sample = 0u; p.ao_distance = 0.0f; p.ao_bias = 0.0f;
 }
 
@@ -955,7 +965,7 @@ static void fill_params(const DeviceScene& sc, const VkhrtFrameDesc& f, const Re
 struct Tunables {
     int refill_threshold, min_blocks, blocks_per_sm, w_node, w_leaf, w_march;
     int pool, pool_stats, pool_min_ratio, pool_node_lanes, pool_batch_lanes, pool_node_min, pool_exit, pool_cfg, pool_host, carveout;
-    int store256, zero_copy, linewise, line_shift;
+    int store256, zero_copy, linewise, line_shift, sample_batch;
 };
 static int env_int(const char* name, int def) { const char* v = getenv(name); return v ? atoi(v) : def; }
 static const Tunables& tun()
@@ -981,6 +991,7 @@ static const Tunables& tun()
         x.store256 = env_int("VKHRT_STORE256", 1);
         x.zero_copy = env_int("VKHRT_ZERO_COPY", 1);
         x.linewise = env_int("VKHRT_LINEWISE", 1);
+        x.sample_batch = env_int("VKHRT_SAMPLE_BATCH", 1);     // 0 = one launch per sample (round 1)
         // 128-byte lines (4 records) measured best: e2e 996 (64 B) / 1077 (128 B) / 1068 (256 B) / 1034 (512 B) Mrays/s on C2
         x.line_shift = std::min(5, std::max(1, env_int("VKHRT_LINE_SHIFT", 2)));
         return x;
@@ -1151,8 +1162,15 @@ int render_frame(DeviceScene& sc, const VkhrtFrameDesc& f, VkhrtHit* hits_out, u
                        "or (hit records only) a page-locked host buffer that the kernel can store into directly");
         return VKHRT_ERR_INVALID_ARGUMENT;
     }
+    // samples per launch for the samples after the first (see the loop below): enough for ~6 M rays, at most 8, none with AO passes
+    uint32_t batch_k = 1u;
+    if (multi && ao == 0u && r.n_slots * 8ull < 0xFFFFFFFFull && tun().sample_batch) {
+        batch_k = (uint32_t)std::min<unsigned long long>(8ull, std::max<unsigned long long>(1ull, (6000000ull + r.n_slots - 1) / r.n_slots));
+        batch_k = std::min(batch_k, std::max(1u, r.spp - 1u));
+        if (r.n_out * (unsigned long long)batch_k >= 0xFFFFFFFFull) batch_k = 1u;          // 32-bit record indices inside the kernels
+    }
     if ((want_hits || want_rgba) && (!direct_hits || multi) && !(h_hits_mapped && !want_rgba)) {
-        if ((rc = grow(&sc.d_hits_scratch, &sc.hits_scratch_n, (size_t)r.n_out * (multi ? 2 : 1)))) return rc;
+        if ((rc = grow(&sc.d_hits_scratch, &sc.hits_scratch_n, (size_t)r.n_out * (multi ? 1 + batch_k : 1)))) return rc;
     }
     if (want_hits || want_rgba) d_hits0 = direct_hits ? hits_out : sc.d_hits_scratch;
     // Phantom frames large enough for the pool kernel: line-wise delivery (records to HBM, complete 128-byte lines to the host)
@@ -1184,8 +1202,14 @@ int render_frame(DeviceScene& sc, const VkhrtFrameDesc& f, VkhrtHit* hits_out, u
     if (stats) VK_CUDA(cudaMemsetAsync(sc.d_counters, 0, 16 * sizeof(unsigned long long), st));
     const uint32_t n_samples = (want_rgba || stats) ? r.spp : 1;    // hits only => sample 0 is all that is observable
 
-    for (uint32_t s = 0; s < n_samples; ++s) {
+    // samples >= 1 of a small frame or shard go several per launch (TraceParams::n_batch): the persistent kernels need a few
+    // million rays to reach a steady state, and a launch per sample pays ramp-up and drain 63 times on a 64-spp shard
+    const uint32_t batch_max = batch_k;
+    for (uint32_t s = 0; s < n_samples;) {
+        const uint32_t kb = (s == 0u) ? 1u : std::min(batch_max, n_samples - s);
         sample_offset(s, &p.sx, &p.sy);
+        p.n_batch = kb; p.slots_per_sample = (uint32_t)r.n_slots; p.n_slots = (uint32_t)(r.n_slots * kb);
+        for (uint32_t b = 0; b < kb; ++b) sample_offset(s + b, &p.bsx[b], &p.bsy[b]);
         p.hits = s == 0 ? d_hits0 : d_hits_other;
         p.hits_mirror = s == 0 ? (h_hits_mapped ? h_hits_mapped : d_hits_mirror) : nullptr;
         p.host_dest = (s == 0 && (direct_to_host || h_hits_mapped)) ? 1u : 0u;
@@ -1207,7 +1231,7 @@ int render_frame(DeviceScene& sc, const VkhrtFrameDesc& f, VkhrtHit* hits_out, u
         }
         if (ao) {
             // secondary rays: ao passes of one occlusion ray per hit pixel, spawned from the hit records inside the
-            // traversal kernel's refill step (no ray buffer), terminate-on-first-hit
+            // traversal kernel's refill step (no ray buffer), terminate-on-first-hit  (never batched: kb == 1)
             VK_CUDA(cudaMemsetAsync(sc.d_occluded, 0, (size_t)r.n_out * sizeof(uint32_t), st));
             TraceParams q = p;
             q.ao_hits = p.hits; q.ao_occluded = sc.d_occluded; q.ao_sample = s;
@@ -1223,12 +1247,19 @@ int render_frame(DeviceScene& sc, const VkhrtFrameDesc& f, VkhrtHit* hits_out, u
         }
         if (s == 0) VK_CUDA(cudaEventRecord(ev[12], st));
         if (want_rgba) {
+            // one shading pass per sample, in sample order (the fp32 accumulation order is part of the result)
             const bool env = f.miss_mode == VKHRT_MISS_ENVIRONMENT && sc.d_env;
-            shade_kernel<<<(unsigned)((r.n_slots + 255) / 256), 256, 0, st>>>(p, p.hits, f.shade_mode, miss, make_float3(sc.albedo[0], sc.albedo[1], sc.albedo[2]), sc.d_accum, (uchar4*)d_rgba, s, r.spp,
-                                                                              sc.d_occluded, ao, env ? sc.d_env : nullptr, sc.env_w, sc.env_h);
-            count_launch();
+            TraceParams ps = p;
+            ps.n_batch = 1u; ps.n_slots = (uint32_t)r.n_slots;
+            for (uint32_t b = 0; b < kb; ++b) {
+                ps.sx = p.bsx[b]; ps.sy = p.bsy[b];
+                shade_kernel<<<(unsigned)((r.n_slots + 255) / 256), 256, 0, st>>>(ps, p.hits + (size_t)b * r.n_out, f.shade_mode, miss, make_float3(sc.albedo[0], sc.albedo[1], sc.albedo[2]), sc.d_accum, (uchar4*)d_rgba, s + b, r.spp,
+                                                                                  sc.d_occluded, ao, env ? sc.d_env : nullptr, sc.env_w, sc.env_h);
+                count_launch();
+            }
         }
         if (s == 0) VK_CUDA(cudaEventRecord(ev[9], st));
+        s += kb;
     }
     VK_CUDA(cudaEventRecord(ev[10], st));
     if (hits_host && !h_hits_mapped && !direct_to_host && !linewise) VK_CUDA(cudaMemcpyAsync(hits_out, d_hits0, (size_t)r.n_out * sizeof(VkhrtHit), cudaMemcpyDeviceToHost, st));

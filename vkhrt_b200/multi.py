@@ -33,6 +33,20 @@ class TileSharding:
         self.n_local_tiles = (self.n_tiles + self.world - 1) // self.world   # same on every rank: shards gather evenly
         self.shard_pixels = self.n_local_tiles * tile * tile if world > 1 else self.width * self.height
 
+    @staticmethod
+    def balanced_tile(width, world, preferred=64):
+        """A tile size (multiple of 8, near `preferred`) whose tile count per image row is coprime with `world`.
+        Tiles are dealt round-robin over the row-major tile index; when the row length divides by `world` (e.g. 3840 / 64 = 60
+        tiles over 4 ranks) every rank gets VERTICAL STRIPES and the load follows the horizontal hair density; with a coprime row
+        length the pattern shifts from row to row (diagonal), which evens it out."""
+        from math import gcd
+        if world <= 1:
+            return preferred
+        for t in sorted(range(32, 129, 8), key=lambda t: abs(t - preferred)):
+            if gcd(-(-width // t) % world or world, world) == 1:
+                return t
+        return preferred
+
     def rank_of_tile(self, tile_index):
         return tile_index % self.world
 
