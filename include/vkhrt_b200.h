@@ -359,6 +359,8 @@ typedef struct VkhrtLineAsset {
     uint32_t  n_segments;
     float*    radius_per_vertex;  /* NULL unless the file carries a thickness array (.hair): thickness / 2 */
     uint32_t  n_strands;
+    float     base_color[4];      /* Material::albedoFactor as ProcessMaterial reads it (AI_MATKEY_BASE_COLOR, model_loader.cpp:96-99):
+                                     glTF pbrMetallicRoughness.baseColorFactor of the first line primitive's material; 1,1,1,1 if none */
 } VkhrtLineAsset;
 /* by extension: .obj (`v` + `l` polyline records), .hair (Cem Yuksel HAIR format), .gltf / .glb (glTF 2.0 line primitives: modes LINES,
  * LINE_LOOP, LINE_STRIP; external, base64 or GLB buffers; node transforms applied to the positions) — the format of the reference's own

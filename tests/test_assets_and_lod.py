@@ -641,3 +641,26 @@ def test_oracle_material_albedo_term(O):
     orc.set_material()                                          # default material: albedo 1 -> plain Shade()
     _, img1, _ = orc.render(O.make_frame(vi, pi, W, H, shade_mode=2))
     assert np.array_equal(img1, ref)
+
+
+def test_gltf_material_base_color(V, tmp_path):
+    """ProcessMaterial (model_loader.cpp:96-99): albedoFactor = the glTF base colour of the line primitive's material"""
+    import base64, json, struct
+    pos = np.array([[0, 0, 0], [1, 0, 0], [2, 1, 0]], np.float32)
+    idx = np.array([0, 1, 1, 2], np.uint32)
+    blob = pos.tobytes() + idx.tobytes()
+    doc = {"asset": {"version": "2.0"},
+           "buffers": [{"byteLength": len(blob), "uri": "data:application/octet-stream;base64," + base64.b64encode(blob).decode()}],
+           "bufferViews": [{"buffer": 0, "byteOffset": 0, "byteLength": 36}, {"buffer": 0, "byteOffset": 36, "byteLength": 16}],
+           "accessors": [{"bufferView": 0, "componentType": 5126, "count": 3, "type": "VEC3"}, {"bufferView": 1, "componentType": 5125, "count": 4, "type": "SCALAR"}],
+           "materials": [{"name": "unused"}, {"pbrMetallicRoughness": {"baseColorFactor": [0.25, 0.5, 0.75, 1.0]}}],
+           "meshes": [{"primitives": [{"mode": 1, "attributes": {"POSITION": 0}, "indices": 1, "material": 1}]}],
+           "nodes": [{"mesh": 0}], "scenes": [{"nodes": [0]}], "scene": 0}
+    p = tmp_path / "hair.gltf"
+    p.write_text(json.dumps(doc))
+    assert V.load_material(str(p)) == (0.25, 0.5, 0.75, 1.0)
+    doc["meshes"][0]["primitives"][0].pop("material")
+    p.write_text(json.dumps(doc))
+    assert V.load_material(str(p)) == (1.0, 1.0, 1.0, 1.0)
+    V.save_lines(str(tmp_path / "hair.obj"), pos, idx.reshape(-1, 2))
+    assert V.load_material(str(tmp_path / "hair.obj")) == (1.0, 1.0, 1.0, 1.0)

@@ -55,7 +55,7 @@ class FrameDesc(C.Structure):
 
 class LineAsset(C.Structure):
     _fields_ = [("positions_xyz", C.c_void_p), ("n_vertices", C.c_uint32), ("line_indices", C.c_void_p),
-                ("n_segments", C.c_uint32), ("radius_per_vertex", C.c_void_p), ("n_strands", C.c_uint32)]
+                ("n_segments", C.c_uint32), ("radius_per_vertex", C.c_void_p), ("n_strands", C.c_uint32), ("base_color", C.c_float * 4)]
 
 
 class Material(C.Structure):
@@ -234,6 +234,16 @@ def make_frame(view_inv, proj_inv, width, height, spp=1, shade_mode=SHADE, miss_
     f.stream = stream
     f.row_major_output = row_major_output
     return f
+
+
+def load_material(path):
+    """Material::albedoFactor of a line asset (glTF baseColorFactor of the first line primitive's material; 1,1,1,1 otherwise)"""
+    a = LineAsset()
+    _check(lib().vkhrt_asset_load_lines(os.fsencode(path), C.byref(a)), "vkhrt_asset_load_lines")
+    try:
+        return tuple(float(x) for x in a.base_color)
+    finally:
+        lib().vkhrt_asset_free(C.byref(a))
 
 
 def load_lines(path):

@@ -358,6 +358,7 @@ int vkhrt_asset_load_lines(const char* path, VkhrtLineAsset* out)
 {
     if (!path || !out) return fail(VKHRT_ERR_INVALID_ARGUMENT, "null argument");
     std::memset(out, 0, sizeof(*out));
+    for (int k = 0; k < 4; ++k) out->base_color[k] = 1.0f;                 // formats without materials (.obj polylines, .hair)
     std::vector<unsigned char> data;
     if (!read_file(path, data)) return fail(VKHRT_ERR_IO, std::string("cannot read ") + path);
     std::string p(path);

@@ -292,13 +292,24 @@ int view_accessor(Gltf& g, size_t ai, const char* want_type, AccessorView* v)
     return VKHRT_OK;
 }
 
-struct Builder { std::vector<float> pos; std::vector<uint32_t> idx; uint32_t strands = 0; };
+struct Builder { std::vector<float> pos; std::vector<uint32_t> idx; uint32_t strands = 0; float base_color[4] = {1, 1, 1, 1}; bool have_color = false; };
 
 int emit_primitive(Gltf& g, const JVal& prim, const M4& world, Builder& out)
 {
     size_t mode = 4;
     if (!as_size(prim.get("mode"), 4, &mode)) return fail(VKHRT_ERR_IO, "gltf: malformed primitive mode");
     if (mode < 1 || mode > 3) return VKHRT_OK;                            // not a line primitive
+    if (!out.have_color) {
+        // ProcessMaterial (model_loader.cpp:96-99): albedoFactor = AI_MATKEY_BASE_COLOR = pbrMetallicRoughness.baseColorFactor
+        out.have_color = true;
+        const JVal* mats = g.root.get("materials");
+        size_t mi;
+        if (mats && mats->type == JVal::ARR && prim.get("material") && as_index(prim.get("material"), mats->arr.size(), &mi))
+            if (const JVal* pbr = mats->arr[mi].get("pbrMetallicRoughness"))
+                if (const JVal* bc = pbr->get("baseColorFactor"))
+                    if (bc->type == JVal::ARR && bc->arr.size() == 4 && bc->arr[0].is_num() && bc->arr[1].is_num() && bc->arr[2].is_num() && bc->arr[3].is_num())
+                        for (int k = 0; k < 4; ++k) out.base_color[k] = (float)bc->arr[k].num;
+    }
     const JVal* attrs = prim.get("attributes");
     const JVal* accs = g.root.get("accessors");
     size_t pa;
@@ -459,6 +470,7 @@ int load_gltf(const std::string& path, const std::vector<unsigned char>& data, b
     out->positions_xyz = dup_array(b.pos);
     out->line_indices = dup_array(b.idx);
     out->radius_per_vertex = nullptr;
+    for (int k = 0; k < 4; ++k) out->base_color[k] = b.base_color[k];
     return VKHRT_OK;
 }
 

@@ -20,7 +20,7 @@ using namespace vkhrt_host;
 static void usage()
 {
     std::puts("usage: vkhrt_headless --model <file.gltf | file.glb | file.obj | file.hair | synthetic:<straight|curly>:<strands>:<segments>[:seed]>\n"
-              "                      [--technique phantom|lss|dots] [--size WxH] [--spp N] [--debug-primid]\n"
+              "                      [--technique phantom|lss|dots] [--size WxH] [--spp N] [--debug-primid | --material]\n"
               "                      [--frames N] [--ppm out.ppm] [--png out.png] [--hits out.bin] [--device D] [--gpus N]\n"
               "                      [--env procedural|file.hdr] [--ao N] [--lod split,merge,curve_merge]");
 }
@@ -40,6 +40,7 @@ int main(int argc, char** argv)
         else if (a == "--size") { if (std::sscanf(next(), "%ux%u", &info.width, &info.height) != 2) { usage(); return 2; } }
         else if (a == "--spp") info.spp = (uint32_t)std::atoi(next());
         else if (a == "--debug-primid") info.shadeMode = VKHRT_SHADE_DEBUG_PRIMID;
+        else if (a == "--material") info.shadeMode = VKHRT_SHADE_MATERIAL;     // Shade(normal) * the asset's albedo factor
         else if (a == "--frames") frames = std::atoi(next());
         else if (a == "--ppm") ppm = next();
         else if (a == "--png") png = next();

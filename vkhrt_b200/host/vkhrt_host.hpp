@@ -87,7 +87,8 @@ struct vec3 { float x = 0, y = 0, z = 0; };
 struct ModelCreation {
     std::vector<vec3> vertexBuffer {};          // Mesh::Vertex::position
     std::vector<uint32_t> indexBuffer {};       // pairs (start, end); strand joints repeat the vertex index
-    std::vector<float> radiusBuffer {};         // optional, one per vertex (LSS); empty => `radius`
+    std::vector<float> radiusBuffer {};         // optional, one per vertex (all techniques); empty => `radius`
+    float albedoFactor[4] { 1.0f, 1.0f, 1.0f, 1.0f };   // MaterialCreation::albedoFactor (ProcessMaterial, model_loader.cpp:96-99)
     float radius = VKHRT_DEFAULT_RADIUS;
     VkhrtTechnique technique = VKHRT_TECHNIQUE_LSS;   // the reference's own default when the LSS extension exists
     std::string sceneName {};
@@ -117,6 +118,9 @@ public:
         d.technique = creation.technique;
         d.device = device;
         Check(vkhrt_scene_create(&d, &_scene), "vkhrt_scene_create");
+        VkhrtMaterial mat {};
+        std::memcpy(mat.albedo_factor, creation.albedoFactor, sizeof(mat.albedo_factor));
+        vkhrt_scene_set_material(_scene, &mat);
         int rc = vkhrt_scene_apply_lod(_scene, creation.lineSplitPasses, creation.lineMergePasses, creation.curveMergePasses);
         if (rc == VKHRT_OK) rc = vkhrt_scene_build(_scene);
         if (rc != VKHRT_OK) { vkhrt_scene_destroy(_scene); _scene = nullptr; throw VkhrtError(rc, "vkhrt_scene_build"); }
@@ -175,6 +179,7 @@ public:
         if (a.n_vertices) std::memcpy(&out.vertexBuffer[0].x, a.positions_xyz, (size_t)a.n_vertices * 12);
         out.indexBuffer.assign(a.line_indices, a.line_indices + (size_t)a.n_segments * 2);
         if (a.radius_per_vertex) out.radiusBuffer.assign(a.radius_per_vertex, a.radius_per_vertex + a.n_vertices);
+        std::memcpy(out.albedoFactor, a.base_color, sizeof(out.albedoFactor));
         vkhrt_asset_free(&a);
         return !out.indexBuffer.empty();
     }
