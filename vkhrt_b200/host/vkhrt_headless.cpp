@@ -21,7 +21,7 @@ static void usage()
 {
     std::puts("usage: vkhrt_headless --model <file.gltf | file.glb | file.obj | file.hair | synthetic:<straight|curly>:<strands>:<segments>[:seed]>\n"
               "                      [--technique phantom|lss|dots] [--size WxH] [--spp N] [--debug-primid | --material]\n"
-              "                      [--frames N] [--ppm out.ppm] [--png out.png] [--hits out.bin] [--device D] [--gpus N]\n"
+              "                      [--frames N] [--no-image | --no-hits] [--ppm out.ppm] [--png out.png] [--hits out.bin] [--device D] [--gpus N]\n"
               "                      [--env procedural|file.hdr] [--ao N] [--lod split,merge,curve_merge]");
 }
 
@@ -41,6 +41,8 @@ int main(int argc, char** argv)
         else if (a == "--spp") info.spp = (uint32_t)std::atoi(next());
         else if (a == "--debug-primid") info.shadeMode = VKHRT_SHADE_DEBUG_PRIMID;
         else if (a == "--material") info.shadeMode = VKHRT_SHADE_MATERIAL;     // Shade(normal) * the asset's albedo factor
+        else if (a == "--no-image") info.wantImage = false;                   // hit records only (BASELINE configs[1])
+        else if (a == "--no-hits") info.wantHits = false;
         else if (a == "--frames") frames = std::atoi(next());
         else if (a == "--ppm") ppm = next();
         else if (a == "--png") png = next();

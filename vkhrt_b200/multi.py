@@ -223,6 +223,11 @@ class SharedHostFrame:
             dist.broadcast_object_list(name, src=gather_rank, group=group)
         if not self.owner:
             self.shm = shared_memory.SharedMemory(name=name[0])
+            try:        # Python < 3.13 registers attached segments with the resource tracker too: only the creator unlinks
+                from multiprocessing import resource_tracker
+                resource_tracker.unregister(self.shm._name, "shared_memory")
+            except Exception:
+                pass
         self.array = np.frombuffer(self.shm.buf, dtype=np.uint8, count=self.nbytes)
         self.ptr = self.array.ctypes.data
         rc = torch.cuda.cudart().cudaHostRegister(self.ptr, self.nbytes, 1 | 2)      # cudaHostRegisterPortable | Mapped
