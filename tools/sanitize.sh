@@ -25,6 +25,19 @@ with V.Scene(pos, idx) as sc:
     hh = torch.zeros((161 * 97, 32), dtype=torch.uint8).pin_memory()
     sc.render_into(V.make_frame(vi, pi, 161, 97, output_memory=V.MEM_HOST), hh.data_ptr(), None)
     print("pinned", int(hh.numpy().view(V.HIT_DTYPE)["flags"].sum()))
+# per-vertex radii (TAPER kernels), material shading, several samples per launch (spp 4 on a small frame)
+taper = np.tile(np.linspace(0.02, 0.005, 13, dtype=np.float32), 1500)
+for tech in (V.PHANTOM, V.DOTS):
+    with V.Scene(pos, idx, technique=tech, radius_per_vertex=taper) as sc:
+        sc.set_material((0.5, 0.6, 0.7, 1.0)).build()
+        h, img, _ = sc.render(V.make_frame(vi, pi, 160, 96, spp=4, shade_mode=V.SHADE_MATERIAL))
+        print("taper", tech, int((h["flags"] & 1).sum()), int(img[:, :3].sum()))
+# one process, two scene handles on one device: vkhrt_render_multi (peer path: shared frame buffers, persistent workers)
+scs = [V.Scene(pos, idx, technique=V.LSS).build() for _ in range(2)]
+h, img = V.render_multi(scs, V.make_frame(vi, pi, 160, 96, spp=2))
+print("multi", int((h["flags"] & 1).sum()))
+for s_ in scs:
+    s_.close()
 PY
 # VKHRT_POOL_MIN_RATIO=0: the Phantom frames above go through the per-warp ray-pool kernel as well as the lane-bound one
 for tool in memcheck racecheck; do
