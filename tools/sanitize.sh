@@ -42,7 +42,7 @@ PY
 # VKHRT_POOL_MIN_RATIO=0: the Phantom frames above go through the per-warp ray-pool kernel as well as the lane-bound one
 for tool in memcheck racecheck; do
   for pool in 3 0; do
-    VKHRT_POOL_MIN_RATIO=$pool timeout 900 compute-sanitizer --tool $tool --print-limit 5 python san_tmp.py > gpurun_out/sanitizer_${tool}_pool$pool.log 2>&1
+    VKHRT_POOL_MIN_RATIO=$pool timeout 900 compute-sanitizer --tool $tool --print-limit ${PRINT_LIMIT:-5} python san_tmp.py > gpurun_out/sanitizer_${tool}_pool$pool.log 2>&1
     echo "$tool (VKHRT_POOL_MIN_RATIO=$pool) rc=$?"; grep -E "ERROR SUMMARY|RACECHECK SUMMARY|hazard" gpurun_out/sanitizer_${tool}_pool$pool.log | tail -3
   done
 done
