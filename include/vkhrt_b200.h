@@ -265,6 +265,14 @@ void vkhrt_scene_destroy(VkhrtScene* scene);
 /* replaces source/renderer.cpp:156-166,189-195 and shaders/ray_gen.rgen:16-48.
  * hits_out: n_local_pixels records (nullable); rgba8_out: n_local_pixels*4 bytes (nullable). */
 int  vkhrt_render(VkhrtScene* scene, const VkhrtFrameDesc* frame, VkhrtHit* hits_out, uint8_t* rgba8_out);
+/* Frames in flight — Renderer::Render keeps MAX_FRAMES_IN_FLIGHT frames submitted and waits on the fence of the oldest one
+ * (source/renderer.cpp:85-97,119).  vkhrt_render_submit enqueues a frame and returns; its outputs (HOST memory, page-locked for the
+ * copy to be asynchronous: vkhrt_host_alloc) are complete when the matching vkhrt_render_wait returns.  Up to VKHRT_FRAMES_IN_FLIGHT
+ * frames may be outstanding per scene (a further submit first waits for the oldest); frames complete in submission order, one wait per
+ * submit.  While frame k's records cross PCIe on the copy engine, frame k+1 is already traversing.  Results are vkhrt_render's. */
+#define VKHRT_FRAMES_IN_FLIGHT 2
+int  vkhrt_render_submit(VkhrtScene* scene, const VkhrtFrameDesc* frame, VkhrtHit* hits_out, uint8_t* rgba8_out);
+int  vkhrt_render_wait(VkhrtScene* scene);      /* the oldest outstanding frame; VKHRT_ERR_INVALID_ARGUMENT when none is outstanding */
 /* same, and also returns the traversal counters (slower debug kernel variant) */
 int  vkhrt_render_stats(VkhrtScene* scene, const VkhrtFrameDesc* frame, VkhrtHit* hits_out,
                         uint8_t* rgba8_out, VkhrtTraceStats* stats);

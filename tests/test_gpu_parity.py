@@ -133,6 +133,41 @@ def test_tile_shards_and_untile(V, O, small_groom, world):
         assert np.array_equal(oi.cpu().numpy(), full_i)
 
 
+@pytest.mark.parametrize("tech,spp,rgba", [(0, 1, False), (1, 2, True), (2, 1, True)])
+def test_frames_in_flight(V, small_groom, tech, spp, rgba):
+    """vkhrt_render_submit / vkhrt_render_wait (Renderer::Render keeps frames in flight behind fences, renderer.cpp:85-119): a moving
+    camera, two page-locked output sets used alternately, at most 2 frames outstanding; every frame must equal the blocking call's."""
+    import torch
+    pos, idx = small_groom
+    W, H = 1280 if tech == 0 else 320, 720 if tech == 0 else 200          # the Phantom frame is large enough for the pool kernel
+    cams = [V.camera_matrices(position=(0.3 * k, 150.0 + 0.2 * k, 20.0 - 0.5 * k), yaw=-90.0 + 2 * k, aspect=float(np.float32(W) / np.float32(H))) for k in range(5)]
+    with V.Scene(pos, idx, technique=tech) as sc:
+        sc.build()
+        refs = [sc.render(V.make_frame(vi, pi, W, H, spp=spp), rgba=rgba) for vi, pi in cams]
+        hh = [torch.zeros((W * H, 32), dtype=torch.uint8).pin_memory() for _ in range(2)]
+        ii = [torch.zeros((W * H, 4), dtype=torch.uint8).pin_memory() for _ in range(2)]
+        got = []
+        for k, (vi, pi) in enumerate(cams):
+            if k >= 2:                      # frame k-2 used this buffer set: take its result before it is overwritten
+                sc.wait()
+                got.append((hh[k % 2].numpy().copy(), ii[k % 2].numpy().copy()))
+            sc.submit(V.make_frame(vi, pi, W, H, spp=spp, output_memory=V.MEM_HOST), hh[k % 2].data_ptr(), ii[k % 2].data_ptr() if rgba else None)
+        for k in (3, 4):
+            sc.wait()
+            got.append((hh[k % 2].numpy().copy(), ii[k % 2].numpy().copy()))
+        with pytest.raises(V.VkhrtError):
+            sc.wait()                       # nothing outstanding
+        for k, ((gh, gi), (rh, ri, _)) in enumerate(zip(got, refs)):
+            assert gh.reshape(-1).tobytes() == rh.tobytes(), k
+            if rgba:
+                assert np.array_equal(gi, ri), k
+        # three submits without a wait: the third waits for the first by itself; frames still complete in order
+        for k in range(3):
+            sc.submit(V.make_frame(cams[k][0], cams[k][1], W, H, spp=spp, output_memory=V.MEM_HOST), hh[k % 2].data_ptr(), None)
+        sc.wait(); sc.wait()
+        assert hh[1].numpy().reshape(-1).tobytes() == refs[1][0].tobytes() and hh[0].numpy().reshape(-1).tobytes() == refs[2][0].tobytes()
+
+
 def test_untile_with_one_shard_is_a_plain_copy(V, small_groom):
     """vkhrt_untile(world = 1): a one-shard render is never compact (tile_stride 1 writes row-major, W*H records), so the device
     untile must be a plain copy like vkhrt_untile_host — on a frame whose size is not a multiple of the tile size (ADVICE r1:

@@ -94,7 +94,7 @@ ABI_SYMBOLS = [
     "vkhrt_abi_version", "vkhrt_device_count", "vkhrt_error_string", "vkhrt_last_error", "vkhrt_launch_count",
     "vkhrt_scene_create", "vkhrt_scene_build", "vkhrt_scene_refit", "vkhrt_scene_get_bvh",
     "vkhrt_scene_get_primitives", "vkhrt_scene_primitive_count", "vkhrt_scene_destroy",
-    "vkhrt_render", "vkhrt_render_stats", "vkhrt_frame_local_pixels", "vkhrt_untile", "vkhrt_untile_host", "vkhrt_render_multi", "vkhrt_last_timing",
+    "vkhrt_render", "vkhrt_render_submit", "vkhrt_render_wait", "vkhrt_render_stats", "vkhrt_frame_local_pixels", "vkhrt_untile", "vkhrt_untile_host", "vkhrt_render_multi", "vkhrt_last_timing",
     "vkhrt_generate_rays", "vkhrt_trace_rays", "vkhrt_trace_rays_any_hit", "vkhrt_camera_matrices", "vkhrt_groom_generate",
     "vkhrt_host_alloc", "vkhrt_host_free", "vkhrt_shared_buffer_create", "vkhrt_shared_buffer_open", "vkhrt_shared_buffer_close", "vkhrt_shared_buffer_destroy",
     "vkhrt_scene_set_environment", "vkhrt_scene_set_material", "vkhrt_image_save_exr", "vkhrt_scene_apply_lod", "vkhrt_scene_segment_count", "vkhrt_scene_get_lines",
@@ -134,6 +134,8 @@ def lib():
     L.vkhrt_scene_destroy.argtypes = [C.c_void_p]
     L.vkhrt_scene_destroy.restype = None
     L.vkhrt_render.argtypes = [C.c_void_p, C.POINTER(FrameDesc), C.c_void_p, C.c_void_p]
+    L.vkhrt_render_submit.argtypes = [C.c_void_p, C.POINTER(FrameDesc), C.c_void_p, C.c_void_p]
+    L.vkhrt_render_wait.argtypes = [C.c_void_p]
     L.vkhrt_render_stats.argtypes = [C.c_void_p, C.POINTER(FrameDesc), C.c_void_p, C.c_void_p, C.POINTER(TraceStats)]
     L.vkhrt_frame_local_pixels.restype = C.c_uint64
     L.vkhrt_frame_local_pixels.argtypes = [C.POINTER(FrameDesc)]
@@ -457,6 +459,14 @@ class Scene:
     def render_into(self, frame, hits_ptr=None, rgba_ptr=None):
         """Raw-pointer render (host or device pointers per frame.output_memory)."""
         _check(lib().vkhrt_render(self._h, C.byref(frame), hits_ptr, rgba_ptr), "vkhrt_render")
+
+    def submit(self, frame, hits_ptr=None, rgba_ptr=None):
+        """vkhrt_render_submit: enqueue a frame into HOST buffers (page-locked for an asynchronous copy) and return; up to 2 in flight"""
+        _check(lib().vkhrt_render_submit(self._h, C.byref(frame), hits_ptr, rgba_ptr), "vkhrt_render_submit")
+
+    def wait(self):
+        """vkhrt_render_wait: the oldest outstanding frame's outputs are complete"""
+        _check(lib().vkhrt_render_wait(self._h), "vkhrt_render_wait")
 
     def render_stats_into(self, frame, hits_ptr=None, rgba_ptr=None):
         st = TraceStats()

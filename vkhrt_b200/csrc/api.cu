@@ -46,6 +46,7 @@ static void free_scene(DeviceScene* sc)
     cudaFree(sc->d_positions); cudaFree(sc->d_indices); cudaFree(sc->d_radius_pv); cudaFree(sc->d_curves); cudaFree(sc->d_env);
     cudaFree(sc->d_build_scratch);
     cudaFree(sc->d_arena);       // nodes, sorted ids / keys, parents, refit flags, primA, primB
+    for (auto& f : sc->fl) { cudaFree(f.d_hits); cudaFree(f.d_rgba); if (f.traced) cudaEventDestroy(f.traced); if (f.copied) cudaEventDestroy(f.copied); }
     cudaFree(sc->d_multi_hits); cudaFree(sc->d_multi_rgba);
     if (sc->multi_done) cudaEventDestroy(sc->multi_done);
     cudaFree(sc->d_counters); cudaFree(sc->d_hits_scratch); cudaFree(sc->d_accum); cudaFree(sc->d_rgba_scratch); cudaFree(sc->d_occluded); cudaFree(sc->d_pool_overflow); cudaFree(sc->d_line_cnt);
@@ -252,6 +253,56 @@ int vkhrt_render(VkhrtScene* scene, const VkhrtFrameDesc* frame, VkhrtHit* hits_
     if (!scene || !frame) { set_last_error("null argument"); return VKHRT_ERR_INVALID_ARGUMENT; }
     if (!scene->s.built) { set_last_error("render before build"); return VKHRT_ERR_NOT_BUILT; }
     return render_frame(scene->s, *frame, hits_out, rgba8_out, nullptr);
+}
+
+static int wait_oldest(DeviceScene& sc)
+{
+    DeviceScene::InFlight& f = sc.fl[sc.fl_head];
+    VK_CUDA(cudaSetDevice(sc.device));
+    VK_CUDA(cudaEventSynchronize(f.copied));
+    f.pending = false;
+    sc.fl_head = (sc.fl_head + 1u) % VKHRT_FRAMES_IN_FLIGHT;
+    sc.fl_count--;
+    return VKHRT_OK;
+}
+
+int vkhrt_render_submit(VkhrtScene* scene, const VkhrtFrameDesc* frame, VkhrtHit* hits_out, uint8_t* rgba8_out)
+{
+    if (!scene || !frame) { set_last_error("null argument"); return VKHRT_ERR_INVALID_ARGUMENT; }
+    DeviceScene& sc = scene->s;
+    if (!sc.built) { set_last_error("render before build"); return VKHRT_ERR_NOT_BUILT; }
+    if (frame->output_memory != VKHRT_MEM_HOST) { set_last_error("vkhrt_render_submit: host output buffers (device outputs are asynchronous through VkhrtFrameDesc::stream already)"); return VKHRT_ERR_INVALID_ARGUMENT; }
+    if (frame->tile_stride > 1 && frame->row_major_output) { set_last_error("vkhrt_render_submit: a shard of a shared frame cannot be copied out as a whole buffer"); return VKHRT_ERR_INVALID_ARGUMENT; }
+    const uint64_t n_out = frame_local_pixels(*frame);
+    if (n_out == 0) { set_last_error("vkhrt_render_submit: bad frame description"); return VKHRT_ERR_INVALID_ARGUMENT; }
+    int rc;
+    if (sc.fl_count == VKHRT_FRAMES_IN_FLIGHT && (rc = wait_oldest(sc))) return rc;       // back-pressure: the oldest frame's buffers are needed again
+    VK_CUDA(cudaSetDevice(sc.device));
+    DeviceScene::InFlight& f = sc.fl[(sc.fl_head + sc.fl_count) % VKHRT_FRAMES_IN_FLIGHT];
+    if (!f.traced) { VK_CUDA(cudaEventCreateWithFlags(&f.traced, cudaEventDisableTiming)); VK_CUDA(cudaEventCreateWithFlags(&f.copied, cudaEventDisableTiming)); }
+    if (hits_out && f.hits_n < n_out) { cudaFree(f.d_hits); f.d_hits = nullptr; f.hits_n = 0; VK_CUDA(cudaMalloc((void**)&f.d_hits, (size_t)n_out * sizeof(VkhrtHit))); f.hits_n = (size_t)n_out; }
+    if (rgba8_out && f.rgba_n < n_out * 4) { cudaFree(f.d_rgba); f.d_rgba = nullptr; f.rgba_n = 0; VK_CUDA(cudaMalloc((void**)&f.d_rgba, (size_t)n_out * 4)); f.rgba_n = (size_t)n_out * 4; }
+    // the traversal writes into this slot's device buffers (its previous copy has completed: the slot was waited for); the copy
+    // engine takes them to the host on its own stream, so the NEXT frame's kernels do not wait for the copy
+    RenderOpts o;
+    o.defer_sync = true; o.hits_on_device = true; o.rgba_on_device = true;
+    rc = render_frame(sc, *frame, hits_out ? f.d_hits : nullptr, rgba8_out ? f.d_rgba : nullptr, nullptr, o);
+    if (rc) return rc;
+    VK_CUDA(cudaEventRecord(f.traced, sc.stream));
+    VK_CUDA(cudaStreamWaitEvent(sc.copy_stream, f.traced, 0));
+    if (hits_out) VK_CUDA(cudaMemcpyAsync(hits_out, f.d_hits, (size_t)n_out * sizeof(VkhrtHit), cudaMemcpyDeviceToHost, sc.copy_stream));
+    if (rgba8_out) VK_CUDA(cudaMemcpyAsync(rgba8_out, f.d_rgba, (size_t)n_out * 4, cudaMemcpyDeviceToHost, sc.copy_stream));
+    VK_CUDA(cudaEventRecord(f.copied, sc.copy_stream));
+    f.pending = true;
+    sc.fl_count++;
+    return VKHRT_OK;
+}
+
+int vkhrt_render_wait(VkhrtScene* scene)
+{
+    if (!scene) { set_last_error("null scene"); return VKHRT_ERR_INVALID_ARGUMENT; }
+    if (scene->s.fl_count == 0) { set_last_error("vkhrt_render_wait: no frame is outstanding"); return VKHRT_ERR_INVALID_ARGUMENT; }
+    return wait_oldest(scene->s);
 }
 
 int vkhrt_render_stats(VkhrtScene* scene, const VkhrtFrameDesc* frame, VkhrtHit* hits_out, uint8_t* rgba8_out, VkhrtTraceStats* stats)

@@ -74,6 +74,15 @@ struct DeviceScene {
     uint8_t* d_multi_rgba = nullptr; size_t multi_rgba_n = 0;
     cudaEvent_t multi_done = nullptr;
 
+    // frames in flight (vkhrt_render_submit / _wait): per slot the device buffers the copy engine reads while the next frame traverses
+    struct InFlight {
+        VkhrtHit* d_hits = nullptr; size_t hits_n = 0;
+        uint8_t* d_rgba = nullptr; size_t rgba_n = 0;
+        cudaEvent_t traced = nullptr, copied = nullptr;
+        bool pending = false;
+    } fl[VKHRT_FRAMES_IN_FLIGHT];
+    uint32_t fl_head = 0, fl_count = 0;     // oldest outstanding slot, number outstanding
+
     cudaStream_t stream = nullptr;
     cudaStream_t copy_stream = nullptr;
     cudaEvent_t ev[16] = {};
