@@ -357,7 +357,10 @@ VK_DEV unsigned long long os_ld(const unsigned long long* p)
 }
 VK_DEV void os_st(unsigned long long* p, unsigned long long v) { asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory"); }
 
-__global__ void __launch_bounds__(OS_BLOCK) os_pass_kernel(const uint64_t* __restrict__ keys_in, const uint32_t* __restrict__ vals_in,
+#ifndef VKHRT_OS_MIN_BLOCKS
+#define VKHRT_OS_MIN_BLOCKS 4       // CTAs per SM the register allocation is held to: 2 (80 registers) / 3 (56) / 4 (40, 36 B spilled) sort C2 in 0.84 / 0.78 / 0.73 ms
+#endif
+__global__ void __launch_bounds__(OS_BLOCK, VKHRT_OS_MIN_BLOCKS) os_pass_kernel(const uint64_t* __restrict__ keys_in, const uint32_t* __restrict__ vals_in,
                                                            uint64_t* __restrict__ keys_out, uint32_t* __restrict__ vals_out, uint32_t n, int pass,
                                                            const uint32_t* __restrict__ digit_start /* [256] of this pass */,
                                                            unsigned long long* __restrict__ status /* [tiles][256] */, uint32_t* __restrict__ ticket /* [8] */)
