@@ -652,13 +652,14 @@ def test_render_multi_from_one_process(V, small_groom, tech):
 
 
 @pytest.mark.parametrize("env", [{"VKHRT_POOL_MIN_RATIO": "0"}, {"VKHRT_POOL_MIN_RATIO": "0", "VKHRT_POOL_CFG": "1"},
-                                 {"VKHRT_POOL_MIN_RATIO": "0", "VKHRT_POOL_CFG": "2"}, {"VKHRT_POOL": "0"}],
-                         ids=["pool-on-every-frame", "pool-56x8", "pool-64x6", "lane-bound-only"])
+                                 {"VKHRT_POOL_MIN_RATIO": "0", "VKHRT_POOL_CFG": "2"}, {"VKHRT_POOL": "0"},
+                                 {"VKHRT_POOL_MIN_RATIO": "0", "VKHRT_POOL_LSS": "1", "VKHRT_POOL_DOTS": "1"}],
+                         ids=["pool-on-every-frame", "pool-56x8", "pool-64x6", "lane-bound-only", "pool-for-lss-and-dots"])
 def test_both_traversal_kernels_pass_the_whole_suite(env):
     """Phantom primary rays have two traversal kernels: the per-warp ray pool (frames >= 3x its resident capacity) and the lane-bound
     kernel (everything else).  The library reads its switches once per process, so the whole parity file is re-run in a subprocess
     with the pool forced onto every frame size (tiny, ragged, sharded, empty ...) and with the pool switched off (full-size C2 on
-    the lane-bound kernel)."""
+    the lane-bound kernel).  The last variant sends LSS and DOTS primary rays through the pool kernel too (an opt-in switch: measured no faster)."""
     import os
     import subprocess
     import sys

@@ -459,7 +459,7 @@ struct PoolWarp {
     float dir[6][PL_S];                // d.xyz, 1/d
     float tcur[PL_S];
     uint32_t cur[PL_S], best_pos[PL_S];
-    uint32_t last_group[VKHRT_MAILBOX_PHANTOM ? PL_S : 1];
+    uint32_t last_group[PL_S];         // Phantom: the curve this ray tested last (one-entry mailbox); LSS / DOTS: primitive id of the best hit
     float best_u[PL_S];
     uint32_t out_idx[PL_S];
     uint8_t sp[PL_S], lo[PL_S];
@@ -468,9 +468,10 @@ struct PoolWarp {
                                        // every push costs more than one LDS)
 };
 
-template <bool STATS, int PL_S, int PL_STK, int MINB = PL_MINB>
+template <int TECH, bool STATS, int PL_S, int PL_STK, int MINB = PL_MINB>
 __global__ void __launch_bounds__(TR_BLOCK, MINB) trace_pool_kernel(const TraceParams p)
 {
+    constexpr bool PH = TECH == VKHRT_TECHNIQUE_PHANTOM;        // LSS / DOTS: the leaf batch runs the whole primitive test; no CAND / MARCH
     __shared__ PoolWarp<PL_S, PL_STK> sh_all[TR_BLOCK / 32];
     if (blockIdx.x == 0 && threadIdx.x == 0) *p.work_next = 0ull;
     const unsigned FULL = 0xffffffffu;
@@ -662,7 +663,7 @@ __global__ void __launch_bounds__(TR_BLOCK, MINB) trace_pool_kernel(const TraceP
                 top_up();
             } while (nHave >= p.pool_node_lanes);
         } else if (phase == PH_LEAF) {
-            // ---------------- leaves: Prhi early-out (hair_intersection.rint:20-33, rmax precomputed) ----------------
+            // ---------------- leaves: Phantom: Prhi early-out (hair_intersection.rint:20-33, rmax precomputed); LSS / DOTS: the primitive test ----------------
             const uint32_t n = min(nL, 32u);
             const bool act = (uint32_t)lane < n;
             if (STATS) { sc_steps[1]++; sc_lanes[1] += n; }
@@ -672,12 +673,41 @@ __global__ void __launch_bounds__(TR_BLOCK, MINB) trace_pool_kernel(const TraceP
                 s = dequeue(Q_LEAF, nL, (uint32_t)lane);
                 const float3 d = f3(sh.dir[0][s], sh.dir[1][s], sh.dir[2][s]);
                 const uint32_t pos = sh.cur[s] & 0x7FFFFFFFu;
-                const float4 a0 = __ldg(p.primA + 2 * (size_t)pos), a1 = __ldg(p.primA + 2 * (size_t)pos + 1);
-                // mailbox: another piece of the curve tested last gives the same answer; skipped and not counted
-                const bool again = VKHRT_MAILBOX_PHANTOM && __float_as_uint(a1.w) == sh.last_group[s];
-                if (VKHRT_MAILBOX_PHANTOM) sh.last_group[s] = __float_as_uint(a1.w);
-                if (STATS && !again) st_prims++;
-                pass = !again && ray_hits_cylinder(o, d, xyz(a0), xyz(a1), a0.w);
+                if (PH) {
+                    const float4 a0 = __ldg(p.primA + 2 * (size_t)pos), a1 = __ldg(p.primA + 2 * (size_t)pos + 1);
+                    // mailbox: another piece of the curve tested last gives the same answer; skipped and not counted
+                    const bool again = VKHRT_MAILBOX_PHANTOM && __float_as_uint(a1.w) == sh.last_group[s];
+                    if (VKHRT_MAILBOX_PHANTOM) sh.last_group[s] = __float_as_uint(a1.w);
+                    if (STATS && !again) st_prims++;
+                    pass = !again && ray_hits_cylinder(o, d, xyz(a0), xyz(a1), a0.w);
+                } else {
+                    // reportIntersectionEXT interval [tMin, tCurrent] + tie rule (smaller primitive id), as trace_kernel's `commit`
+                    auto commit = [&](float t, float u, uint32_t prim) {
+                        const float tc = sh.tcur[s];
+                        if (t >= p.tmin && (t < tc || (t == tc && prim < sh.last_group[s]))) { sh.tcur[s] = t; sh.last_group[s] = prim; sh.best_pos[s] = pos; sh.best_u[s] = u; }
+                    };
+                    if (TECH == VKHRT_TECHNIQUE_LSS) {
+                        const float4 a0 = __ldg(p.primA + 2 * (size_t)pos), a1 = __ldg(p.primA + 2 * (size_t)pos + 1);
+                        float t, u;
+                        if (STATS) st_prims++;
+                        if (lss_intersect<false>(o, d, xyz(a0), a0.w, xyz(a1), a1.w, &t, &u, nullptr)) commit(t, u, __ldg(p.sorted_ids + pos) / VKHRT_LEAF_SPLIT_LSS);
+                    } else {
+                        const float4* rec = p.primA + 4 * (size_t)pos;
+                        const float4 a0 = __ldg(rec), a1 = __ldg(rec + 1);
+                        if (STATS) st_prims += 4;
+                        if (ray_near_strip_axis(o, d, xyz(a0), xyz(a1), p.radius)) {
+                            const float4 a2 = __ldg(rec + 2), a3 = __ldg(rec + 3);
+                            const uint32_t prim0 = __float_as_uint(a0.w) << 2;
+#pragma unroll 1
+                            for (uint32_t k = 0; k < 4u; ++k) {
+                                float3 v0, v1, v2;
+                                strip_triangle(xyz(a0), xyz(a1), (k & 2u) ? xyz(a3) : xyz(a2), k & 1u, &v0, &v1, &v2);
+                                float t, u;
+                                if (tri_intersect(o, d, v0, v1, v2, k & 1u, &t, &u)) commit(t, u, prim0 + k);
+                            }
+                        }
+                    }
+                }
                 if (!pass) next = pop_parked(s);
             }
             nL -= n;
@@ -685,7 +715,7 @@ __global__ void __launch_bounds__(TR_BLOCK, MINB) trace_pool_kernel(const TraceP
             enqueue(Q_CAND, nC, act && pass, s);
             route(act && !pass, s, next);
             __syncwarp();
-        } else if (phase == PH_SETUP) {
+        } else if (PH && phase == PH_SETUP) {
             // ---------------- candidates: ray-centric transform + quarter-chord filter into free MARCH registers ----------------
             const unsigned midle = __ballot_sync(FULL, !mhave);
             const uint32_t rank = __popc(midle & lt);
@@ -710,7 +740,7 @@ __global__ void __launch_bounds__(TR_BLOCK, MINB) trace_pool_kernel(const TraceP
             __syncwarp();
             route(reject, m_slot, next);
             __syncwarp();
-        } else if (phase == PH_MARCH) {
+        } else if (PH && phase == PH_MARCH) {
             // ---------------- Phantom cone iterations (hair_intersection.rint:56-126) ----------------
             uint32_t n0 = nM, n1;
             do {
@@ -761,15 +791,30 @@ __global__ void __launch_bounds__(TR_BLOCK, MINB) trace_pool_kernel(const TraceP
                     const uint32_t pos = sh.best_pos[s];
                     oi = sh.out_idx[s];
                     if (pos != PRIM_NONE) {
-                        // hair_intersection.rint:74-76 from the committed (t, u)
                         rt = sh.tcur[s]; ru = sh.best_u[s];
                         const float3 d = f3(sh.dir[0][s], sh.dir[1][s], sh.dir[2][s]);
-                        const float4 a0 = __ldg(p.primA + 2 * (size_t)pos), a1 = __ldg(p.primA + 2 * (size_t)pos + 1);
-                        const float4 b0 = __ldg(p.primB + 2 * (size_t)pos), b1 = __ldg(p.primB + 2 * (size_t)pos + 1);
-                        Bezier w;
-                        w.p0 = xyz(a0); w.p1 = xyz(b0); w.p2 = xyz(b1); w.p3 = xyz(a1);
-                        rprim = rseg = __float_as_uint(a1.w);
-                        rn = fnormalize3(fmadd3(rt, d, o) - bezier_point(w, ru));
+                        if (PH) {
+                            // hair_intersection.rint:74-76 from the committed (t, u)
+                            const float4 a0 = __ldg(p.primA + 2 * (size_t)pos), a1 = __ldg(p.primA + 2 * (size_t)pos + 1);
+                            const float4 b0 = __ldg(p.primB + 2 * (size_t)pos), b1 = __ldg(p.primB + 2 * (size_t)pos + 1);
+                            Bezier w;
+                            w.p0 = xyz(a0); w.p1 = xyz(b0); w.p2 = xyz(b1); w.p3 = xyz(a1);
+                            rprim = rseg = __float_as_uint(a1.w);
+                            rn = fnormalize3(fmadd3(rt, d, o) - bezier_point(w, ru));
+                        } else if (TECH == VKHRT_TECHNIQUE_LSS) {
+                            const float4 a0 = __ldg(p.primA + 2 * (size_t)pos), a1 = __ldg(p.primA + 2 * (size_t)pos + 1);
+                            float t, u;
+                            lss_intersect<true>(o, d, xyz(a0), a0.w, xyz(a1), a1.w, &t, &u, &rn);
+                            rprim = rseg = sh.last_group[s];
+                        } else {
+                            rprim = sh.last_group[s];
+                            const float4* rec = p.primA + 4 * (size_t)pos;
+                            const float4 a0 = __ldg(rec), a1 = __ldg(rec + 1), a2 = __ldg(rec + ((rprim & 2u) ? 3 : 2));
+                            float3 v0, v1, v2;
+                            strip_triangle(xyz(a0), xyz(a1), xyz(a2), rprim & 1u, &v0, &v1, &v2);
+                            rn = tri_normal(d, v0, v1, v2);
+                            rseg = rprim >> 2;
+                        }
                         rflags = FLAG_HIT;
                         if (STATS) st_hits++;
                     }
@@ -797,7 +842,7 @@ __global__ void __launch_bounds__(TR_BLOCK, MINB) trace_pool_kernel(const TraceP
                         sh.dir[3][s] = safe_rcp(d.x); sh.dir[4][s] = safe_rcp(d.y); sh.dir[5][s] = safe_rcp(d.z);
                         sh.tcur[s] = p.tmax; sh.cur[s] = 0u; sh.sp[s] = 0; sh.lo[s] = 0;
                         sh.best_pos[s] = PRIM_NONE; sh.best_u[s] = 0.0f; sh.out_idx[s] = q.out;
-                        if (VKHRT_MAILBOX_PHANTOM) sh.last_group[s] = PRIM_NONE;
+                        sh.last_group[s] = PRIM_NONE;
                         fresh = true;
                         if (STATS) st_rays++;
                     } else if (p.compact) { padded = true; pad_idx = q.out; }
@@ -965,7 +1010,7 @@ static void fill_params(const DeviceScene& sc, const VkhrtFrameDesc& f, const Re
 struct Tunables {
     int refill_threshold, min_blocks, blocks_per_sm, w_node, w_leaf, w_march;
     int pool, pool_stats, pool_min_ratio, pool_node_lanes, pool_batch_lanes, pool_node_min, pool_exit, pool_cfg, pool_host, carveout;
-    int store256, zero_copy, linewise, line_shift, sample_batch;
+    int store256, zero_copy, linewise, line_shift, sample_batch, pool_lss, pool_dots;
 };
 static int env_int(const char* name, int def) { const char* v = getenv(name); return v ? atoi(v) : def; }
 static const Tunables& tun()
@@ -986,6 +1031,11 @@ static const Tunables& tun()
         x.pool_node_min = env_int("VKHRT_POOL_NODE_MIN", 8);
         x.pool_exit = env_int("VKHRT_POOL_EXIT", 6);
         x.pool_cfg = env_int("VKHRT_POOL_CFG", 0);
+        // LSS / DOTS primary rays through the pool kernel as well: records and counters identical, but measured no better (C3 1987 vs
+        // 2234 Mrays/s: 18 % fewer warp instructions, yet L1 hits 44 vs 59 % with 4608 instead of 2048 rays in flight per SM and
+        // long-scoreboard stalls double; C4 1059 vs 1040, e2e 996 vs 1020), so both default to the lane-bound kernel
+        x.pool_lss = env_int("VKHRT_POOL_LSS", 0);
+        x.pool_dots = env_int("VKHRT_POOL_DOTS", 0);
         x.pool_host = env_int("VKHRT_POOL_HOST", 0);
         x.carveout = env_int("VKHRT_CARVEOUT", -1);
         x.store256 = env_int("VKHRT_STORE256", 1);
@@ -1042,12 +1092,12 @@ static int launch_trace_t(DeviceScene& sc, TraceParams& p, cudaStream_t st)
     count_launch();
     return VKHRT_OK;
 }
-template <bool STATS, int PL_S, int PL_STK, int MINB = PL_MINB>
+template <int TECH, bool STATS, int PL_S, int PL_STK, int MINB = PL_MINB>
 static int launch_pool_t(DeviceScene& sc, TraceParams& p, cudaStream_t st)
 {
     const int carve = tun().carveout;
-    if (carve >= 0) VK_CUDA(cudaFuncSetAttribute(trace_pool_kernel<STATS, PL_S, PL_STK, MINB>, cudaFuncAttributePreferredSharedMemoryCarveout, carve));
-    int per_sm = blocks_per_sm(trace_pool_kernel<STATS, PL_S, PL_STK, MINB>, sc.device);
+    if (carve >= 0) VK_CUDA(cudaFuncSetAttribute(trace_pool_kernel<TECH, STATS, PL_S, PL_STK, MINB>, cudaFuncAttributePreferredSharedMemoryCarveout, carve));
+    int per_sm = blocks_per_sm(trace_pool_kernel<TECH, STATS, PL_S, PL_STK, MINB>, sc.device);
     if (tun().blocks_per_sm > 0) per_sm = std::min(per_sm, tun().blocks_per_sm);
     unsigned long long want = ((unsigned long long)(p.n_slots - p.slot_begin) + TR_BLOCK - 1) / TR_BLOCK;
     unsigned grid = (unsigned)std::min<unsigned long long>((unsigned long long)sc.sm_count * per_sm, std::max<unsigned long long>(want, 1ull));
@@ -1059,22 +1109,29 @@ static int launch_pool_t(DeviceScene& sc, TraceParams& p, cudaStream_t st)
         sc.pool_overflow_n = ovf;
     }
     p.pool_overflow = sc.d_pool_overflow;
-    trace_pool_kernel<STATS, PL_S, PL_STK, MINB><<<grid, TR_BLOCK, 0, st>>>(p);
+    trace_pool_kernel<TECH, STATS, PL_S, PL_STK, MINB><<<grid, TR_BLOCK, 0, st>>>(p);
     sc.last_trace_was_pool = true;
     count_launch();
     return VKHRT_OK;
 }
-template <bool STATS>
+template <int TECH, bool STATS>
 static int launch_pool(DeviceScene& sc, TraceParams& p, cudaStream_t st)
 {
     // slots per warp x shared-memory stack window (profiles/experiments/r02_pool_kernel.txt): 72 x 4 measured best; 56 x 8 and 64 x 6
     // trade slots for fewer spill reads (-0.5 % / -1 %); 9 / 10 / 12 CTAs per SM at 56 / 48 / 40 registers lose 3 / 16 / 22 %
     switch (tun().pool_cfg) {
-    case 1: return launch_pool_t<STATS, 56, 8>(sc, p, st);
-    case 2: return launch_pool_t<STATS, 64, 6>(sc, p, st);
-    default: return launch_pool_t<STATS, 72, 4>(sc, p, st);
+    case 1: return launch_pool_t<TECH, STATS, 56, 8>(sc, p, st);
+    case 2: return launch_pool_t<TECH, STATS, 64, 6>(sc, p, st);
+    default: return launch_pool_t<TECH, STATS, 72, 4>(sc, p, st);
     }
 }
+// does the per-warp ray-pool kernel serve this scene's primary rays? (uniform radius only; LSS / DOTS behind their switches)
+static bool pool_serves(const DeviceScene& sc)
+{
+    if (!tun().pool || sc.tapered()) return false;
+    return sc.technique == VKHRT_TECHNIQUE_PHANTOM || (sc.technique == VKHRT_TECHNIQUE_LSS && tun().pool_lss) || (sc.technique == VKHRT_TECHNIQUE_DOTS && tun().pool_dots);
+}
+
 template <bool STATS, int SRC, bool ANYHIT>
 static int launch_trace(DeviceScene& sc, TraceParams& p, cudaStream_t st)
 {
@@ -1095,12 +1152,20 @@ static int launch_trace(DeviceScene& sc, TraceParams& p, cudaStream_t st)
         // on a B200) in rays to reach a steady state; below that it is all ramp-up and drain (C1: 639 vs 801 Mrays/s)
         if (SRC == SRC_PRIMARY && !ANYHIT && tun().pool && p.n_prims && (!STATS || tun().pool_stats) && !(p.host_dest && tun().pool_host == 0) &&
             (unsigned long long)(p.n_slots - p.slot_begin) >= (unsigned long long)tun().pool_min_ratio * sc.sm_count * 32ull * 56ull)
-            return launch_pool<STATS>(sc, p, st);
+            return launch_pool<VKHRT_TECHNIQUE_PHANTOM, STATS>(sc, p, st);
         if (!STATS && SRC == SRC_PRIMARY && tun().min_blocks == 7) return launch_trace_t<VKHRT_TECHNIQUE_PHANTOM, false, SRC_PRIMARY, false, 7>(sc, p, st);
         if (!STATS && SRC == SRC_PRIMARY && tun().min_blocks == 8) return launch_trace_t<VKHRT_TECHNIQUE_PHANTOM, false, SRC_PRIMARY, false, 8>(sc, p, st);
         return launch_trace_t<VKHRT_TECHNIQUE_PHANTOM, STATS, SRC, ANYHIT, TR_MIN_BLOCKS>(sc, p, st);
-    case VKHRT_TECHNIQUE_LSS: return launch_trace_t<VKHRT_TECHNIQUE_LSS, STATS, SRC, ANYHIT, TR_MIN_BLOCKS>(sc, p, st);
-    default: return launch_trace_t<VKHRT_TECHNIQUE_DOTS, STATS, SRC, ANYHIT, TR_MIN_BLOCKS>(sc, p, st);
+    case VKHRT_TECHNIQUE_LSS:
+        if (SRC == SRC_PRIMARY && !ANYHIT && pool_serves(sc) && p.n_prims && (!STATS || tun().pool_stats) && !(p.host_dest && tun().pool_host == 0) &&
+            (unsigned long long)(p.n_slots - p.slot_begin) >= (unsigned long long)tun().pool_min_ratio * sc.sm_count * 32ull * 56ull)
+            return launch_pool<VKHRT_TECHNIQUE_LSS, STATS>(sc, p, st);
+        return launch_trace_t<VKHRT_TECHNIQUE_LSS, STATS, SRC, ANYHIT, TR_MIN_BLOCKS>(sc, p, st);
+    default:
+        if (SRC == SRC_PRIMARY && !ANYHIT && pool_serves(sc) && p.n_prims && (!STATS || tun().pool_stats) && !(p.host_dest && tun().pool_host == 0) &&
+            (unsigned long long)(p.n_slots - p.slot_begin) >= (unsigned long long)tun().pool_min_ratio * sc.sm_count * 32ull * 56ull)
+            return launch_pool<VKHRT_TECHNIQUE_DOTS, STATS>(sc, p, st);
+        return launch_trace_t<VKHRT_TECHNIQUE_DOTS, STATS, SRC, ANYHIT, TR_MIN_BLOCKS>(sc, p, st);
     }
 }
 
@@ -1177,7 +1242,7 @@ int render_frame(DeviceScene& sc, const VkhrtFrameDesc& f, VkhrtHit* hits_out, u
     bool linewise = false;
     const uint32_t line_shift = (uint32_t)tun().line_shift;
     // (with an image the records stay in HBM for the shading kernel anyway, which is where line-wise delivery keeps them)
-    if (h_hits_mapped && sc.technique == VKHRT_TECHNIQUE_PHANTOM && !sc.tapered() && ao == 0u && sc.n_leaves && tun().pool && tun().linewise &&
+    if (h_hits_mapped && pool_serves(sc) && ao == 0u && sc.n_leaves && tun().linewise &&
         (((uintptr_t)h_hits_mapped) & ((32u << line_shift) - 1u)) == 0u && r.n_slots >= (unsigned long long)tun().pool_min_ratio * sc.sm_count * 32ull * 56ull) {
         if ((rc = grow(&sc.d_hits_scratch, &sc.hits_scratch_n, (size_t)r.n_out))) return rc;
         if ((rc = grow(&sc.d_line_cnt, &sc.line_cnt_n, (size_t)r.n_out / 2 + 1))) return rc;      // enough for the smallest line (2 records)
