@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define VKHRT_ABI_VERSION 5
+#define VKHRT_ABI_VERSION 6
 
 typedef enum VkhrtStatus {
     VKHRT_OK = 0,
@@ -342,8 +342,27 @@ typedef struct VkhrtMaterial {
     const float* albedo_map_rgba32f;     /* nullable (useAlbedoMap = false); width * height texels, row 0 first, HOST memory */
     uint32_t     albedo_map_width, albedo_map_height;
 } VkhrtMaterial;
-/* NULL => the default material (albedo 1,1,1,1, no map) */
+/* NULL => the default material (albedo 1,1,1,1, no map); on a multi-mesh scene: every mesh's material */
 int  vkhrt_scene_set_material(VkhrtScene* scene, const VkhrtMaterial* material);
+
+/* ---- multi-mesh scenes --------------------------------------------------------------------------------------------------
+ * The reference loads several models, builds one BLAS per mesh / hair and one TLAS instance for each
+ * (source/renderer.cpp:33-41, 694-727; source/top_level_acceleration_structure.cpp:19-113: instanceCustomIndex = BLAS
+ * ordinal, identity-only transforms), and the closest-hit shaders find the mesh's material through
+ * geometryNodes[blasInstances[gl_InstanceCustomIndexEXT].firstGeometryIndex] (shaders/hair_closest_hit.rchit:17-18).
+ * Here the meshes' line lists are CONCATENATED into the scene's vertex / index arrays the way GenerateLines addresses them
+ * (firstVertex / firstIndex, source/resources/model/geometry_processor.cpp:45-67; node transforms applied by the loader) and ONE
+ * LBVH is built over all segments: instances are unique, so a flat hierarchy finds the same closest hit as TLAS -> BLAS with one
+ * traversal instead of two.  Mesh m owns segments [first_segment[m], first_segment[m + 1]) (the last one up to n_segments);
+ * first_segment[0] must be 0 and the list ascending (an empty mesh repeats its successor's value).  A hit record's `segment` is the
+ * scene-wide index; vkhrt_scene_mesh_of_segments maps it to the mesh (= gl_InstanceCustomIndexEXT), VKHRT_MISS_SEGMENT for a miss.
+ * shade_mode VKHRT_SHADE_MATERIAL uses the material of the mesh that owns the hit segment.  Strands must not span meshes
+ * (GenerateCurves looks at the neighbouring segment only when it shares a vertex, so concatenation keeps every curve as it was).
+ * Not combinable with vkhrt_scene_apply_lod (the passes renumber segments).  n_meshes = 0 returns to a single mesh. */
+int      vkhrt_scene_set_meshes(VkhrtScene* scene, const uint32_t* first_segment, uint32_t n_meshes);
+int      vkhrt_scene_set_mesh_material(VkhrtScene* scene, uint32_t mesh, const VkhrtMaterial* material);
+uint32_t vkhrt_scene_mesh_count(const VkhrtScene* scene);
+int      vkhrt_scene_mesh_of_segments(const VkhrtScene* scene, const uint32_t* segments, uint32_t* mesh_out, size_t n);
 
 /* ---- strand level of detail on the device, before the build ------------------------------
  * The reference defines but never calls MergeLines / SplitLines / MergeCurvesFast

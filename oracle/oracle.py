@@ -65,6 +65,10 @@ def lib():
         L.orc_scene_create_lod.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32, C.c_void_p, C.c_float, C.c_int, C.c_void_p]
         L.orc_scene_set_environment.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32]
         L.orc_scene_set_material.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32]
+        L.orc_scene_set_meshes.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32]
+        L.orc_scene_set_mesh_material.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32]
+        L.orc_scene_mesh_of_segment.argtypes = [C.c_void_p, C.c_uint32]
+        L.orc_scene_mesh_of_segment.restype = C.c_uint32
         L.orc_scene_line_count.restype = C.c_uint32
         L.orc_scene_line_count.argtypes = [C.c_void_p]
         L.orc_scene_get_lines.argtypes = [C.c_void_p, C.c_void_p]
@@ -194,6 +198,22 @@ class OracleScene:
         else:
             m = np.ascontiguousarray(albedo_map, np.float32)
             lib().orc_scene_set_material(self._h, f.ctypes.data, m.ctypes.data, m.shape[1], m.shape[0])
+
+    def set_meshes(self, first_segment):
+        """multi-mesh scene: mesh m = segments [first_segment[m], first_segment[m + 1])"""
+        fs = np.ascontiguousarray(first_segment, np.uint32).reshape(-1)
+        lib().orc_scene_set_meshes(self._h, fs.ctypes.data if fs.size else None, fs.size)
+
+    def set_mesh_material(self, mesh, albedo_factor=(1.0, 1.0, 1.0, 1.0), albedo_map=None):
+        f = np.ascontiguousarray(albedo_factor, np.float32)
+        if albedo_map is None:
+            lib().orc_scene_set_mesh_material(self._h, int(mesh), f.ctypes.data, None, 0, 0)
+        else:
+            m = np.ascontiguousarray(albedo_map, np.float32)
+            lib().orc_scene_set_mesh_material(self._h, int(mesh), f.ctypes.data, m.ctypes.data, m.shape[1], m.shape[0])
+
+    def mesh_of_segment(self, seg):
+        return int(lib().orc_scene_mesh_of_segment(self._h, int(seg)))
 
     def environment_miss(self, d):
         a = _f(d); o = (C.c_float * 3)()

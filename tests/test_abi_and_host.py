@@ -86,7 +86,7 @@ def test_header_is_plain_c(V):
 
 def test_error_strings_and_versions(V):
     L = V.lib()
-    assert L.vkhrt_abi_version() == 5
+    assert L.vkhrt_abi_version() == 6
     assert L.vkhrt_error_string(0) == b"ok"
     for code in range(-8, 0):
         assert L.vkhrt_error_string(code) not in (b"ok", b"unknown status")

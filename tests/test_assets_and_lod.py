@@ -643,6 +643,49 @@ def test_oracle_material_albedo_term(O):
     assert np.array_equal(img1, ref)
 
 
+def test_oracle_multi_mesh_scene(V, O):
+    """One BLAS per mesh + one TLAS instance each in the reference (renderer.cpp:694-727) = concatenated line lists under one hierarchy here:
+    the closest hit over the union is the nearer of the per-mesh closest hits, the hit segment names its mesh, and SHADE_MATERIAL
+    multiplies Shade(n) by THAT mesh's albedo (hair_closest_hit.rchit:17-18 -> geometryNodes[...].material)."""
+    a_pos = np.array([[-1, 150, 0], [1, 150, 0]], np.float32)                       # a horizontal hair through the image centre
+    b_pos = np.array([[-1, 151, 0], [0, 151, 0], [1, 151, 0]], np.float32)          # two segments above it
+    c_pos = np.array([[-1, 150, 5], [1, 150, 5]], np.float32)                       # in front of mesh 0: occludes it
+    idx1 = np.array([[0, 1]], np.uint32); idx2 = np.array([[0, 1], [1, 2]], np.uint32)
+    pos, idx, rad, first = V.merge_meshes([(a_pos, idx1), (b_pos, idx2), (c_pos, idx1)])
+    assert list(first) == [0, 1, 3] and idx.tolist() == [[0, 1], [2, 3], [3, 4], [5, 6]] and rad is None
+    vi, pi = O.camera_matrices(aspect=1.0)
+    W = H = 65
+    f0 = O.make_frame(vi, pi, W, H)
+    for tech in (0, 1, 2):
+        parts = [O.OracleScene(p, i, technique=tech, radius=0.2).render(f0)[0] for p, i in ((a_pos, idx1), (b_pos, idx2), (c_pos, idx1))]
+        orc = O.OracleScene(pos, idx, technique=tech, radius=0.2)
+        orc.set_meshes(first)
+        albedo = [(1.0, 0.5, 0.25, 1.0), (0.25, 1.0, 0.5, 1.0), (0.5, 0.25, 1.0, 1.0)]
+        for m, a in enumerate(albedo):
+            orc.set_mesh_material(m, a)
+        h, img, _ = orc.render(O.make_frame(vi, pi, W, H, shade_mode=2))
+        _, plain, _ = orc.render(O.make_frame(vi, pi, W, H, shade_mode=0))
+        t = np.stack([p["t"] for p in parts])                    # [3, rays]; +inf for a miss
+        nearest = t.argmin(axis=0)
+        hit = (h["flags"] & 1) != 0
+        assert np.array_equal(hit, np.isfinite(t.min(axis=0)))
+        assert np.array_equal(h["t"][hit], t.min(axis=0)[hit])                                    # union closest hit = nearest per-mesh hit
+        mesh = np.array([orc.mesh_of_segment(int(s_)) for s_ in h["segment"][hit]])
+        assert np.array_equal(mesh, nearest[hit])
+        assert 0 not in mesh and {1, 2} <= set(mesh.tolist())                                        # mesh 2 hides mesh 0 everywhere
+        local = h["segment"][hit] - first[mesh]                                                      # firstIndex-relative segment
+        assert np.array_equal(local, np.array([parts[m]["segment"][k] for m, k in zip(mesh, np.flatnonzero(hit))]))
+        for m in (1, 2):
+            k = np.flatnonzero(hit)[mesh == m][0]
+            ny = abs(float(h["ny"][k]))
+            shade = np.array([ny * 0.4 + 0.3, ny * 0.2 + 0.3, ny * 0.1 + 0.3])
+            want = np.floor(np.clip(shade * np.array(albedo[m][:3]), 0, 1) * 255 + 0.5)
+            assert np.abs(img[k, :3].astype(np.float64) - want).max() <= 1
+        orc.set_material()                                                                           # every mesh back to albedo 1
+        _, img1, _ = orc.render(O.make_frame(vi, pi, W, H, shade_mode=2))
+        assert np.array_equal(img1, plain)
+
+
 def test_gltf_material_base_color(V, tmp_path):
     """ProcessMaterial (model_loader.cpp:96-99): albedoFactor = the glTF base colour of the line primitive's material"""
     import base64, json, struct

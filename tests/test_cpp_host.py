@@ -125,3 +125,64 @@ def test_headless_hair_asset_lod_environment_png(V, O, tmp_path):
     assert data[37:41] == b"IDAT"
     raw = np.frombuffer(zlib.decompress(data[41:41 + n]), np.uint8).reshape(H, 1 + 4 * W)[:, 1:].reshape(-1, 4)
     assert np.abs(raw.astype(np.int32) - io.astype(np.int32)).max() <= 1
+
+
+MERGE_PROBE = r"""
+#include "vkhrt_host.hpp"
+#include <cstdio>
+using namespace vkhrt_host;
+int main(int argc, char** argv) {
+    std::vector<ModelCreation> parts(argc - 1);
+    for (int i = 1; i < argc; ++i) if (!ModelLoader::LoadModel(argv[i], parts[i - 1])) { std::puts("FAIL"); return 1; }
+    parts[0].radiusBuffer.assign(parts[0].vertexBuffer.size(), 0.01f);        // one part with per-vertex radii: the others get their constant
+    const ModelCreation m = MergeModels(parts);
+    std::printf("%zu %zu %zu\n", m.vertexBuffer.size(), m.indexBuffer.size() / 2, m.radiusBuffer.size());
+    for (uint32_t f : m.meshFirstSegment) std::printf("%u ", f);
+    std::printf("\n");
+    for (uint32_t i : m.indexBuffer) std::printf("%u ", i);
+    std::printf("\n%g %g\n", m.radiusBuffer.front(), m.radiusBuffer.back());
+    return 0;
+}
+"""
+
+
+def test_merge_models_concatenates_like_generate_lines(V, tmp_path):
+    """MergeModels: several models as one line list (firstVertex / firstIndex rebasing, geometry_processor.cpp:45-67), one mesh each"""
+    (tmp_path / "a.obj").write_text("v 0 0 0\nv 1 0 0\nv 2 1 0\nl 1 2 3\n")
+    (tmp_path / "b.obj").write_text("v 5 5 5\nv 6 5 5\nl 1 2\n")
+    src, exe = tmp_path / "merge.cpp", tmp_path / "merge"
+    src.write_text(MERGE_PROBE)
+    lib_dir = os.path.dirname(V.library_path())
+    subprocess.check_call(["/usr/bin/g++", "-std=c++17", "-Wall", "-Wextra", "-Werror", "-I", os.path.join(ROOT, "vkhrt_b200", "host"), str(src), "-o", str(exe),
+                           "-L", lib_dir, "-lvkhrt_b200", f"-Wl,-rpath,{lib_dir}"])
+    out = subprocess.run([str(exe), str(tmp_path / "a.obj"), str(tmp_path / "b.obj")], capture_output=True, text=True).stdout.split("\n")
+    assert out[0] == "5 3 5"
+    assert out[1].split() == ["0", "2"]
+    assert out[2].split() == ["0", "1", "1", "2", "3", "4"]
+    assert out[3] == "0.01 0.02"
+
+
+@pytest.mark.gpu
+def test_headless_multi_model_scene(V, O, tmp_path):
+    """`--model` twice = the reference's list of scene models (renderer.cpp:33-41) in ONE device scene: records equal the oracle's over the
+    concatenated line list, and the per-mesh ray counts equal the mesh lookup of the Python binding."""
+    W, H = 200, 120
+    p1, i1 = V.generate_groom(2000, 12, V.GROOM_CURLY)
+    p2, i2 = V.generate_groom(800, 6, V.GROOM_STRAIGHT, seed=3)
+    p2 = p2 + np.float32([5.0, 0.0, 0.0])
+    a, b, hits_path = tmp_path / "a.glb", tmp_path / "b.hair", tmp_path / "hits.bin"
+    V.save_lines(str(a), p1, i1); V.save_lines(str(b), p2, i2)
+    r = subprocess.run([EXE, "--model", str(a), "--model", str(b), "--technique", "phantom", "--size", f"{W}x{H}", "--hits", str(hits_path)],
+                       capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    l1 = V.load_lines(str(a)); l2 = V.load_lines(str(b))
+    pos, idx, _, first = V.merge_meshes([(l1[0], l1[1]), (l2[0], l2[1])])
+    vi, pi = V.camera_matrices(aspect=float(np.float32(W) / np.float32(H)))
+    ho, _, _ = O.OracleScene(pos, idx, technique=0).render(O.make_frame(vi, pi, W, H))
+    hits = np.fromfile(hits_path, dtype=V.HIT_DTYPE)
+    assert hits.tobytes() == ho.tobytes()
+    hit = (hits["flags"] & 1) != 0
+    mesh = np.searchsorted(first, hits["segment"][hit], side="right") - 1
+    lines = r.stdout.split("\n")
+    assert f"  mesh 0: {int((mesh == 0).sum())} rays" in lines and f"  mesh 1: {int((mesh == 1).sum())} rays" in lines
+    assert (mesh == 1).sum() > 0

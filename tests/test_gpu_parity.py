@@ -369,6 +369,62 @@ def test_material_albedo_shading(V, O, small_groom, tech):
         assert np.array_equal(unit, plain)                       # the default material leaves Shade() unchanged
 
 
+@pytest.mark.parametrize("tech", TECHS)
+def test_multi_mesh_scene(V, O, tech):
+    """Several meshes in one scene (the reference: one BLAS per mesh / hair, one TLAS instance each, renderer.cpp:694-727): the line lists are
+    concatenated (firstVertex / firstIndex, geometry_processor.cpp:45-67) under ONE LBVH.  Hit records equal the oracle's and those of the
+    same segments given as a single mesh; the record's segment maps back to its mesh (= gl_InstanceCustomIndexEXT); SHADE_MATERIAL uses
+    the material of the mesh that was hit."""
+    p1, i1 = V.generate_groom(700, 10, V.GROOM_CURLY)
+    p2, i2 = V.generate_groom(500, 7, V.GROOM_STRAIGHT, seed=11)
+    p3, i3 = V.generate_groom(300, 5, V.GROOM_CURLY, seed=5)
+    p2 = p2 + np.float32([4.0, -2.0, 1.0]); p3 = p3 + np.float32([-5.0, 1.0, 2.0])
+    pos, idx, rad, first = V.merge_meshes([(p1, i1), (p2, i2), (p3, i3)])
+    assert rad is None and list(first) == [0, len(i1), len(i1) + len(i2)]
+    W, H = 240, 150
+    vi, pi = default_camera(V, W, H)
+    mats = [((0.9, 0.4, 0.2, 1.0), None), ((0.2, 0.8, 0.5, 1.0), np.random.default_rng(1).random((3, 5, 4)).astype(np.float32)), ((0.5, 0.5, 1.0, 1.0), None)]
+    with V.Scene(pos, idx, technique=tech) as sc, V.Scene(pos, idx, technique=tech) as single:
+        sc.set_meshes(first).build()
+        single.build()
+        assert sc.n_meshes == 3 and single.n_meshes == 1
+        orc = O.OracleScene(pos, idx, technique=tech)
+        orc.set_meshes(first)
+        for m, (factor, tex) in enumerate(mats):
+            sc.set_mesh_material(m, factor, tex); orc.set_mesh_material(m, factor, tex)
+        for spp in (1, 3):
+            hg, ig, _ = sc.render(V.make_frame(vi, pi, W, H, spp=spp, shade_mode=V.SHADE_MATERIAL, miss_rgb=(0.1, 0.1, 0.2)))
+            ho, io, _ = orc.render(O.make_frame(vi, pi, W, H, spp=spp, shade_mode=2, miss_rgb=(0.1, 0.1, 0.2)))
+            assert_bit_identical(hg, ho)
+            assert np.array_equal(ig, io)
+        hs, _, _ = single.render(V.make_frame(vi, pi, W, H))
+        h1, _, _ = sc.render(V.make_frame(vi, pi, W, H))
+        assert_bit_identical(h1, hs)                                   # the mesh table changes no record
+        mesh = sc.mesh_of_segments(h1["segment"])
+        hit = (h1["flags"] & 1) != 0
+        assert np.all(mesh[~hit] == 0xFFFFFFFF)
+        want = np.searchsorted(first, h1["segment"][hit], side="right") - 1
+        assert np.array_equal(mesh[hit], want.astype(np.uint32))
+        assert set(np.unique(mesh[hit])) == {0, 1, 2}                  # the camera sees all three
+        assert all(orc.mesh_of_segment(int(s_)) == int(m_) for s_, m_ in zip(h1["segment"][hit][:200], mesh[hit][:200]))
+        # one material for the whole scene again
+        sc.set_material((0.3, 0.6, 0.9, 1.0)); single.set_material((0.3, 0.6, 0.9, 1.0))
+        _, ia, _ = sc.render(V.make_frame(vi, pi, W, H, shade_mode=V.SHADE_MATERIAL))
+        _, ib, _ = single.render(V.make_frame(vi, pi, W, H, shade_mode=V.SHADE_MATERIAL))
+        assert np.array_equal(ia, ib)
+        # the table must start at 0 and ascend; LOD passes renumber segments
+        with pytest.raises(V.VkhrtError):
+            sc.set_meshes([1, 5])
+        with pytest.raises(V.VkhrtError):
+            sc.set_meshes([0, 9, 3])
+        with pytest.raises(V.VkhrtError):
+            sc.set_mesh_material(7)
+    with V.Scene(pos, idx, technique=tech) as sc:
+        sc.set_meshes(first)
+        with pytest.raises(V.VkhrtError):
+            sc.apply_lod(1, 0, 0)
+
+
 def test_stats_counters_equal_the_oracles(V, O, small_groom):
     """The warp scheduler only interleaves lanes; each ray's own sequence of node visits and candidate tests is the
     oracle's, so the traversal counters (the N_int / N_prim of the bytes-per-ray roofline) are IDENTICAL."""

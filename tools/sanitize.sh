@@ -32,6 +32,14 @@ for tech in (V.PHANTOM, V.DOTS):
         sc.set_material((0.5, 0.6, 0.7, 1.0)).build()
         h, img, _ = sc.render(V.make_frame(vi, pi, 160, 96, spp=4, shade_mode=V.SHADE_MATERIAL))
         print("taper", tech, int((h["flags"] & 1).sum()), int(img[:, :3].sum()))
+# three meshes in one scene: per-mesh materials through the mesh table
+p2, i2 = V.generate_groom(400, 6, V.GROOM_STRAIGHT, seed=3)
+mp, mi, _, first = V.merge_meshes([(pos, idx), (p2 + np.float32([4, 0, 0]), i2), (p2 - np.float32([4, 0, 0]), i2)])
+with V.Scene(mp, mi) as sc:
+    sc.set_meshes(first).build()
+    sc.set_mesh_material(1, (0.2, 0.9, 0.4, 1.0)).set_mesh_material(2, (0.9, 0.2, 0.4, 1.0))
+    h, img, _ = sc.render(V.make_frame(vi, pi, 160, 96, spp=2, shade_mode=V.SHADE_MATERIAL))
+    print("meshes", np.bincount(sc.mesh_of_segments(h["segment"][(h["flags"] & 1) != 0]), minlength=3), int(img[:, :3].sum()))
 # one process, two scene handles on one device: vkhrt_render_multi (peer path: shared frame buffers, persistent workers)
 scs = [V.Scene(pos, idx, technique=V.LSS).build() for _ in range(2)]
 h, img = V.render_multi(scs, V.make_frame(vi, pi, 160, 96, spp=2))

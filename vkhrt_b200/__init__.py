@@ -9,5 +9,5 @@ from .api import (  # noqa: F401
     HIT_DTYPE, NODE_DTYPE, FLOATS_PER_PRIM, DEFAULT_SEED,
     VkhrtError, FrameDesc, Scene, FlyCamera, camera_matrices, generate_groom, make_frame,
     frame_local_pixels, device_count, launch_count, library_path, untile, untile_host, render_multi, lib, HostBuffer, SharedBuffer,
-    MISS_CONSTANT, MISS_ENVIRONMENT, load_lines, load_material, save_lines, load_hdr, save_hdr, save_png, save_exr, generate_environment,
+    MISS_CONSTANT, MISS_ENVIRONMENT, load_lines, load_material, save_lines, load_hdr, save_hdr, save_png, save_exr, generate_environment, merge_meshes,
 )

@@ -97,7 +97,7 @@ ABI_SYMBOLS = [
     "vkhrt_render", "vkhrt_render_submit", "vkhrt_render_wait", "vkhrt_render_stats", "vkhrt_frame_local_pixels", "vkhrt_untile", "vkhrt_untile_host", "vkhrt_render_multi", "vkhrt_last_timing",
     "vkhrt_generate_rays", "vkhrt_trace_rays", "vkhrt_trace_rays_any_hit", "vkhrt_camera_matrices", "vkhrt_groom_generate",
     "vkhrt_host_alloc", "vkhrt_host_free", "vkhrt_shared_buffer_create", "vkhrt_shared_buffer_open", "vkhrt_shared_buffer_close", "vkhrt_shared_buffer_destroy",
-    "vkhrt_scene_set_environment", "vkhrt_scene_set_material", "vkhrt_image_save_exr", "vkhrt_scene_apply_lod", "vkhrt_scene_segment_count", "vkhrt_scene_get_lines",
+    "vkhrt_scene_set_environment", "vkhrt_scene_set_material", "vkhrt_scene_set_meshes", "vkhrt_scene_set_mesh_material", "vkhrt_scene_mesh_count", "vkhrt_scene_mesh_of_segments", "vkhrt_image_save_exr", "vkhrt_scene_apply_lod", "vkhrt_scene_segment_count", "vkhrt_scene_get_lines",
     "vkhrt_asset_load_lines", "vkhrt_asset_save_lines", "vkhrt_asset_free", "vkhrt_image_load_hdr", "vkhrt_image_save_hdr",
     "vkhrt_image_free", "vkhrt_image_save_png", "vkhrt_environment_generate",
 ]
@@ -156,6 +156,11 @@ def lib():
     L.vkhrt_shared_buffer_destroy.argtypes = [C.c_int, C.c_void_p]
     L.vkhrt_scene_set_environment.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32]
     L.vkhrt_scene_set_material.argtypes = [C.c_void_p, C.POINTER(Material)]
+    L.vkhrt_scene_set_meshes.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32]
+    L.vkhrt_scene_set_mesh_material.argtypes = [C.c_void_p, C.c_uint32, C.POINTER(Material)]
+    L.vkhrt_scene_mesh_count.restype = C.c_uint32
+    L.vkhrt_scene_mesh_count.argtypes = [C.c_void_p]
+    L.vkhrt_scene_mesh_of_segments.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t]
     L.vkhrt_image_save_exr.argtypes = [C.c_char_p, C.c_void_p, C.c_uint32, C.c_uint32]
     L.vkhrt_scene_apply_lod.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32]
     L.vkhrt_scene_segment_count.restype = C.c_uint32
@@ -174,7 +179,7 @@ def lib():
     L.vkhrt_environment_generate.restype = None
     L.vkhrt_host_alloc.argtypes = [C.c_size_t, C.POINTER(C.c_void_p)]
     L.vkhrt_host_free.argtypes = [C.c_void_p]
-    if L.vkhrt_abi_version() != 5:
+    if L.vkhrt_abi_version() != 6:
         raise ImportError("libvkhrt_b200.so ABI version mismatch")
     _lib = L
     return L
@@ -298,6 +303,25 @@ def save_png(path, rgba8, width, height):
     _check(lib().vkhrt_image_save_png(os.fsencode(path), img.ctypes.data, width, height), "vkhrt_image_save_png")
 
 
+def merge_meshes(meshes):
+    """Concatenate line meshes [(positions [n, 3], indices [m, 2]) or (positions, indices, radius_per_vertex), ...] the way the reference's
+    GenerateLines addresses them (firstVertex / firstIndex, geometry_processor.cpp:45-67): returns positions, indices (rebased),
+    radius_per_vertex (None unless every mesh has one) and first_segment for Scene.set_meshes."""
+    pos, idx, rad, first = [], [], [], []
+    v0 = s0 = 0
+    for m in meshes:
+        p = np.ascontiguousarray(m[0], np.float32).reshape(-1, 3)
+        i = np.ascontiguousarray(m[1], np.uint32).reshape(-1, 2)
+        pos.append(p); idx.append(i + np.uint32(v0)); first.append(s0)
+        rad.append(None if len(m) < 3 or m[2] is None else np.ascontiguousarray(m[2], np.float32).reshape(-1))
+        v0 += p.shape[0]; s0 += i.shape[0]
+    if any(r is None for r in rad) and not all(r is None for r in rad):
+        raise ValueError("merge_meshes: radius_per_vertex for all meshes or for none")
+    radius = None if (not rad or rad[0] is None) else np.concatenate(rad)
+    return (np.concatenate(pos) if pos else np.zeros((0, 3), np.float32), np.concatenate(idx) if idx else np.zeros((0, 2), np.uint32),
+            radius, np.asarray(first, np.uint32))
+
+
 def generate_environment(width=512, height=256):
     """procedural equirectangular sky, float32 [h, w, 4] (the reference's .hdr asset is not in its repository)"""
     out = np.empty((height, width, 4), np.float32)
@@ -416,6 +440,35 @@ class Scene:
             m.albedo_map_rgba32f, m.albedo_map_width, m.albedo_map_height = tex.ctypes.data, tex.shape[1], tex.shape[0]
         _check(lib().vkhrt_scene_set_material(self._h, C.byref(m)), "vkhrt_scene_set_material")
         return self
+
+    def set_meshes(self, first_segment):
+        """Multi-mesh scene: mesh m owns segments [first_segment[m], first_segment[m + 1]) of the concatenated line list (see merge_meshes)"""
+        fs = np.ascontiguousarray(first_segment, np.uint32).reshape(-1)
+        _check(lib().vkhrt_scene_set_meshes(self._h, fs.ctypes.data if fs.size else None, fs.size), "vkhrt_scene_set_meshes")
+        return self
+
+    def set_mesh_material(self, mesh, albedo_factor=(1.0, 1.0, 1.0, 1.0), albedo_map=None):
+        m = Material()
+        m.albedo_factor[:] = [float(x) for x in albedo_factor]
+        tex = None
+        if albedo_map is not None:
+            tex = np.ascontiguousarray(albedo_map, np.float32)
+            if tex.ndim != 3 or tex.shape[2] != 4:
+                raise ValueError("albedo map must be [h, w, 4] float32")
+            m.albedo_map_rgba32f, m.albedo_map_width, m.albedo_map_height = tex.ctypes.data, tex.shape[1], tex.shape[0]
+        _check(lib().vkhrt_scene_set_mesh_material(self._h, int(mesh), C.byref(m)), "vkhrt_scene_set_mesh_material")
+        return self
+
+    @property
+    def n_meshes(self):
+        return int(lib().vkhrt_scene_mesh_count(self._h))
+
+    def mesh_of_segments(self, segments):
+        """the mesh (= gl_InstanceCustomIndexEXT of the reference's TLAS) owning each segment index of a hit record; 0xFFFFFFFF for a miss"""
+        seg = np.ascontiguousarray(segments, np.uint32)
+        out = np.empty(seg.shape, np.uint32)
+        _check(lib().vkhrt_scene_mesh_of_segments(self._h, seg.ctypes.data, out.ctypes.data, seg.size), "vkhrt_scene_mesh_of_segments")
+        return out
 
     def build(self):
         _check(lib().vkhrt_scene_build(self._h), "vkhrt_scene_build")

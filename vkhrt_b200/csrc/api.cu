@@ -43,7 +43,7 @@ static void free_scene(DeviceScene* sc)
 {
     if (!sc) return;
     cudaSetDevice(sc->device);
-    cudaFree(sc->d_positions); cudaFree(sc->d_indices); cudaFree(sc->d_radius_pv); cudaFree(sc->d_curves); cudaFree(sc->d_env);
+    cudaFree(sc->d_positions); cudaFree(sc->d_indices); cudaFree(sc->d_radius_pv); cudaFree(sc->d_curves); cudaFree(sc->d_env); cudaFree(sc->d_mesh_table);
     cudaFree(sc->d_build_scratch);
     cudaFree(sc->d_arena);       // nodes, sorted ids / keys, parents, refit flags, primA, primB
     for (auto& f : sc->fl) { cudaFree(f.d_hits); cudaFree(f.d_rgba); if (f.traced) cudaEventDestroy(f.traced); if (f.copied) cudaEventDestroy(f.copied); }
@@ -194,6 +194,7 @@ uint32_t vkhrt_scene_segment_count(const VkhrtScene* scene) { return scene ? sce
 int vkhrt_scene_apply_lod(VkhrtScene* scene, uint32_t line_split_passes, uint32_t line_merge_passes, uint32_t curve_merge_passes)
 {
     if (!scene) { set_last_error("null scene"); return VKHRT_ERR_INVALID_ARGUMENT; }
+    if (scene->s.mesh_first.size() > 1) { set_last_error("vkhrt_scene_apply_lod on a multi-mesh scene: the passes renumber segments across mesh boundaries"); return VKHRT_ERR_UNSUPPORTED; }
     return apply_lod(scene->s, line_split_passes, line_merge_passes, curve_merge_passes);
 }
 
@@ -219,27 +220,82 @@ int vkhrt_scene_set_environment(VkhrtScene* scene, const float* rgba32f, uint32_
     return VKHRT_OK;
 }
 
+// albedo = albedoFactor * texture(albedoMap, vec2(0)) (triangle_closest_hit.rchit:77-81 with the zero UVs of hair primitives)
+static int evaluate_albedo(const VkhrtMaterial* material, float a[4])
+{
+    a[0] = a[1] = a[2] = a[3] = 1.0f;
+    if (!material) return VKHRT_OK;
+    for (int k = 0; k < 4; ++k) a[k] = material->albedo_factor[k];
+    if (material->albedo_map_rgba32f) {
+        const uint32_t W = material->albedo_map_width, H = material->albedo_map_height;
+        if (!W || !H) { set_last_error("albedo map without a size"); return VKHRT_ERR_INVALID_ARGUMENT; }
+        // texture(albedoMap, vec2(0)): texel coordinate -0.5 -> texels W-1 | 0 and H-1 | 0 with weights 1/2 (linear, repeat)
+        const float* m = material->albedo_map_rgba32f;
+        const size_t i0 = W - 1, i1 = 0, j0 = H - 1, j1 = 0;
+        for (int k = 0; k < 4; ++k) {
+            const float t00 = m[4 * (j0 * W + i0) + k], t10 = m[4 * (j0 * W + i1) + k], t01 = m[4 * (j1 * W + i0) + k], t11 = m[4 * (j1 * W + i1) + k];
+            const float top = std::fmaf(0.5f, t10 - t00, t00), bot = std::fmaf(0.5f, t11 - t01, t01);
+            a[k] *= std::fmaf(0.5f, bot - top, top);
+        }
+    }
+    return VKHRT_OK;
+}
+
 int vkhrt_scene_set_material(VkhrtScene* scene, const VkhrtMaterial* material)
 {
     if (!scene) { set_last_error("null scene"); return VKHRT_ERR_INVALID_ARGUMENT; }
     DeviceScene& sc = scene->s;
-    float a[4] = {1.0f, 1.0f, 1.0f, 1.0f};
-    if (material) {
-        for (int k = 0; k < 4; ++k) a[k] = material->albedo_factor[k];
-        if (material->albedo_map_rgba32f) {
-            const uint32_t W = material->albedo_map_width, H = material->albedo_map_height;
-            if (!W || !H) { set_last_error("albedo map without a size"); return VKHRT_ERR_INVALID_ARGUMENT; }
-            // texture(albedoMap, vec2(0)): texel coordinate -0.5 -> texels W-1 | 0 and H-1 | 0 with weights 1/2 (linear, repeat)
-            const float* m = material->albedo_map_rgba32f;
-            const size_t i0 = W - 1, i1 = 0, j0 = H - 1, j1 = 0;
-            for (int k = 0; k < 4; ++k) {
-                const float t00 = m[4 * (j0 * W + i0) + k], t10 = m[4 * (j0 * W + i1) + k], t01 = m[4 * (j1 * W + i0) + k], t11 = m[4 * (j1 * W + i1) + k];
-                const float top = std::fmaf(0.5f, t10 - t00, t00), bot = std::fmaf(0.5f, t11 - t01, t01);
-                a[k] *= std::fmaf(0.5f, bot - top, top);
-            }
-        }
-    }
+    float a[4];
+    if (int rc = evaluate_albedo(material, a)) return rc;
     std::memcpy(sc.albedo, a, sizeof(a));
+    for (size_t m = 0; m < sc.mesh_first.size(); ++m) std::memcpy(&sc.mesh_albedo[4 * m], a, sizeof(a));     // every mesh
+    sc.mesh_table_dirty = !sc.mesh_first.empty();
+    return VKHRT_OK;
+}
+
+int vkhrt_scene_set_meshes(VkhrtScene* scene, const uint32_t* first_segment, uint32_t n_meshes)
+{
+    if (!scene) { set_last_error("null scene"); return VKHRT_ERR_INVALID_ARGUMENT; }
+    DeviceScene& sc = scene->s;
+    if (sc.lod_applied) { set_last_error("vkhrt_scene_set_meshes after vkhrt_scene_apply_lod: the segment numbering changed"); return VKHRT_ERR_UNSUPPORTED; }
+    if (n_meshes && !first_segment) { set_last_error("null first_segment"); return VKHRT_ERR_INVALID_ARGUMENT; }
+    for (uint32_t m = 0; m < n_meshes; ++m) {
+        const bool ok = m == 0 ? first_segment[0] == 0u : first_segment[m] >= first_segment[m - 1];
+        if (!ok || first_segment[m] > sc.n_segments) { set_last_error("vkhrt_scene_set_meshes: first_segment must start at 0, ascend and stay <= n_segments"); return VKHRT_ERR_INVALID_ARGUMENT; }
+    }
+    sc.mesh_first.assign(first_segment, first_segment + n_meshes);
+    sc.mesh_albedo.resize(4 * (size_t)n_meshes);
+    for (uint32_t m = 0; m < n_meshes; ++m) std::memcpy(&sc.mesh_albedo[4 * (size_t)m], sc.albedo, sizeof(sc.albedo));
+    sc.mesh_table_dirty = true;
+    return VKHRT_OK;
+}
+
+int vkhrt_scene_set_mesh_material(VkhrtScene* scene, uint32_t mesh, const VkhrtMaterial* material)
+{
+    if (!scene) { set_last_error("null scene"); return VKHRT_ERR_INVALID_ARGUMENT; }
+    DeviceScene& sc = scene->s;
+    if (mesh >= sc.mesh_first.size()) { set_last_error("vkhrt_scene_set_mesh_material: no such mesh (vkhrt_scene_set_meshes first)"); return VKHRT_ERR_INVALID_ARGUMENT; }
+    float a[4];
+    if (int rc = evaluate_albedo(material, a)) return rc;
+    std::memcpy(&sc.mesh_albedo[4 * (size_t)mesh], a, sizeof(a));
+    sc.mesh_table_dirty = true;
+    return VKHRT_OK;
+}
+
+uint32_t vkhrt_scene_mesh_count(const VkhrtScene* scene)
+{
+    if (!scene) return 0u;
+    return scene->s.mesh_first.empty() ? 1u : (uint32_t)scene->s.mesh_first.size();
+}
+
+int vkhrt_scene_mesh_of_segments(const VkhrtScene* scene, const uint32_t* segments, uint32_t* mesh_out, size_t n)
+{
+    if (!scene || (n && (!segments || !mesh_out))) { set_last_error("null argument"); return VKHRT_ERR_INVALID_ARGUMENT; }
+    const std::vector<uint32_t>& first = scene->s.mesh_first;
+    for (size_t i = 0; i < n; ++i) {
+        if (segments[i] >= scene->s.n_segments) { mesh_out[i] = VKHRT_MISS_SEGMENT; continue; }      // a miss record, or not a segment
+        mesh_out[i] = first.empty() ? 0u : (uint32_t)(std::upper_bound(first.begin(), first.end(), segments[i]) - first.begin()) - 1u;
+    }
     return VKHRT_OK;
 }
 

@@ -1,5 +1,6 @@
 // scene.h — internal (not part of the ABI): device-resident scene + launch helpers.
 #pragma once
+#include <vector>
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <string>
@@ -27,6 +28,11 @@ struct DeviceScene {
 
     // material (bindless.glsl Material): albedoFactor * albedo map at texCoord (0,0), evaluated when the material is set
     float albedo[4] = {1.0f, 1.0f, 1.0f, 1.0f};
+    // meshes (vkhrt_scene_set_meshes): mesh m owns segments [mesh_first[m], mesh_first[m + 1]); one LBVH over all of them.
+    // d_mesh_table[m] = {albedo.rgb, bits(first segment)}, uploaded when it changed; empty = one mesh with `albedo`
+    std::vector<uint32_t> mesh_first;
+    std::vector<float> mesh_albedo;    // 4 per mesh
+    float4* d_mesh_table = nullptr; bool mesh_table_dirty = false;
 
     // environment map (RGBA32F, miss.rmiss)
     float4* d_env = nullptr;

@@ -11,6 +11,7 @@
 #include "hair_math.cuh"
 #include <algorithm>
 #include <cmath>
+#include <cstring>
 
 #ifndef VKHRT_LINE_PROTOCOL
 #define VKHRT_LINE_PROTOCOL 1      // line-wise host delivery: 0 = round 1 (fence + acq_rel count + acquire load), 1 = release-only count
@@ -898,7 +899,8 @@ __global__ void __launch_bounds__(256) raygen_kernel(const TraceParams p, float4
 __global__ void __launch_bounds__(256) shade_kernel(const TraceParams p, const VkhrtHit* __restrict__ hits, int mode, float3 miss, float3 albedo,
                                                     float4* __restrict__ accum, uchar4* __restrict__ rgba, uint32_t sample, uint32_t spp,
                                                     const uint32_t* __restrict__ occluded, uint32_t ao_samples,
-                                                    const float4* __restrict__ env, uint32_t env_w, uint32_t env_h)
+                                                    const float4* __restrict__ env, uint32_t env_w, uint32_t env_h,
+                                                    const float4* __restrict__ meshes, uint32_t n_meshes)
 {
     const unsigned long long slot64 = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (slot64 >= p.n_slots) return;
@@ -914,7 +916,17 @@ __global__ void __launch_bounds__(256) shade_kernel(const TraceParams p, const V
     float3 c;
     if (flags & FLAG_HIT) {
         c = mode == VKHRT_SHADE_DEBUG_PRIMID ? debug_palette(__float_as_uint(h1.z)) : shade_normal(f3(h0.w, h1.x, h1.y));
-        if (mode == VKHRT_SHADE_MATERIAL) c = f3(c.x * albedo.x, c.y * albedo.y, c.z * albedo.z);     // triangle_closest_hit.rchit:77-83
+        if (mode == VKHRT_SHADE_MATERIAL) {                                          // triangle_closest_hit.rchit:72-83
+            if (n_meshes > 1u) {
+                // geometryNodes[blasInstances[gl_InstanceCustomIndexEXT].firstGeometryIndex].material: the mesh that owns the hit segment
+                const uint32_t seg = __float_as_uint(h0.y);
+                uint32_t lo = 0u, hi = n_meshes;                                     // last mesh whose first segment <= seg
+                while (hi - lo > 1u) { const uint32_t mid = (lo + hi) >> 1; if (__float_as_uint(__ldg(meshes + mid).w) <= seg) lo = mid; else hi = mid; }
+                const float4 m = __ldg(meshes + lo);
+                albedo = f3(m.x, m.y, m.z);
+            }
+            c = f3(c.x * albedo.x, c.y * albedo.y, c.z * albedo.z);
+        }
         if (ao_samples) c = c * (1.0f - (float)occluded[i] / (float)ao_samples);    // unoccluded fraction of the AO rays
     } else if (env) {
         // miss.rmiss: the colour depends on the ray of THIS sample, regenerated here (ray_gen.rgen:16-24)
@@ -1012,6 +1024,7 @@ struct Tunables {
     int pool, pool_stats, pool_min_ratio, pool_node_lanes, pool_batch_lanes, pool_node_min, pool_exit, pool_cfg, pool_host, carveout;
     int store256, zero_copy, linewise, line_shift, sample_batch, pool_lss, pool_dots;
 };
+static float bits_to_float(uint32_t u) { float f; std::memcpy(&f, &u, 4); return f; }
 static int env_int(const char* name, int def) { const char* v = getenv(name); return v ? atoi(v) : def; }
 static const Tunables& tun()
 {
@@ -1189,6 +1202,16 @@ int render_frame(DeviceScene& sc, const VkhrtFrameDesc& f, VkhrtHit* hits_out, u
     if (f.miss_mode != VKHRT_MISS_CONSTANT && f.miss_mode != VKHRT_MISS_ENVIRONMENT) { set_last_error("vkhrt_render: unknown miss_mode"); return VKHRT_ERR_INVALID_ARGUMENT; }
     const bool want_rgba = rgba_out != nullptr;
     const bool want_hits = hits_out != nullptr;
+    if (want_rgba && sc.mesh_table_dirty) {
+        // mesh table {albedo.rgb, first segment}: a few entries, uploaded when vkhrt_scene_set_meshes / _set_mesh_material changed it
+        const size_t n = sc.mesh_first.size();
+        std::vector<float4> t(n);
+        for (size_t m = 0; m < n; ++m) t[m] = make_float4(sc.mesh_albedo[4 * m], sc.mesh_albedo[4 * m + 1], sc.mesh_albedo[4 * m + 2], bits_to_float(sc.mesh_first[m]));
+        VK_CUDA(cudaStreamSynchronize(f.stream ? (cudaStream_t)f.stream : sc.stream));
+        cudaFree(sc.d_mesh_table); sc.d_mesh_table = nullptr;
+        if (n) { VK_CUDA(cudaMalloc(&sc.d_mesh_table, n * sizeof(float4))); VK_CUDA(cudaMemcpy(sc.d_mesh_table, t.data(), n * sizeof(float4), cudaMemcpyHostToDevice)); }
+        sc.mesh_table_dirty = false;
+    }
     // where each output lives (vkhrt_render_multi sends the two to different places: records to the caller's pinned host
     // buffer, pixels to the gathering GPU's frame buffer)
     const bool host_frame = f.output_memory == VKHRT_MEM_HOST;
@@ -1319,7 +1342,8 @@ int render_frame(DeviceScene& sc, const VkhrtFrameDesc& f, VkhrtHit* hits_out, u
             for (uint32_t b = 0; b < kb; ++b) {
                 ps.sx = p.bsx[b]; ps.sy = p.bsy[b];
                 shade_kernel<<<(unsigned)((r.n_slots + 255) / 256), 256, 0, st>>>(ps, p.hits + (size_t)b * r.n_out, f.shade_mode, miss, make_float3(sc.albedo[0], sc.albedo[1], sc.albedo[2]), sc.d_accum, (uchar4*)d_rgba, s + b, r.spp,
-                                                                                  sc.d_occluded, ao, env ? sc.d_env : nullptr, sc.env_w, sc.env_h);
+                                                                                  sc.d_occluded, ao, env ? sc.d_env : nullptr, sc.env_w, sc.env_h,
+                                                                                  sc.d_mesh_table, (uint32_t)sc.mesh_first.size());
                 count_launch();
             }
         }

@@ -19,7 +19,7 @@ using namespace vkhrt_host;
 
 static void usage()
 {
-    std::puts("usage: vkhrt_headless --model <file.gltf | file.glb | file.obj | file.hair | synthetic:<straight|curly>:<strands>:<segments>[:seed]>\n"
+    std::puts("usage: vkhrt_headless --model <file.gltf | file.glb | file.obj | file.hair | synthetic:<straight|curly>:<strands>:<segments>[:seed]>  (repeat --model for a multi-mesh scene)\n"
               "                      [--technique phantom|lss|dots] [--size WxH] [--spp N] [--debug-primid | --material]\n"
               "                      [--frames N] [--no-image | --no-hits] [--ppm out.ppm] [--png out.png] [--hits out.bin] [--device D] [--gpus N]\n"
               "                      [--env procedural|file.hdr] [--ao N] [--lod split,merge,curve_merge]");
@@ -28,6 +28,7 @@ static void usage()
 int main(int argc, char** argv)
 {
     std::string model = "synthetic:curly:10000:16", ppm, png, hits_path, technique = "lss";
+    std::vector<std::string> models;          // --model may repeat: the reference's scene is a list of models (renderer.cpp:33-41)
     unsigned lod[3] = {0, 0, 0};
     RendererInitInfo info;
     int frames = 1, device = 0, gpus = 1;
@@ -35,7 +36,7 @@ int main(int argc, char** argv)
         const std::string a = argv[i];
         auto next = [&]() -> const char* { if (i + 1 >= argc) { usage(); std::exit(2); } return argv[++i]; };
         if (a == "--help" || a == "-h") { usage(); return 0; }
-        else if (a == "--model") model = next();
+        else if (a == "--model") { model = next(); models.push_back(model); }
         else if (a == "--technique") technique = next();
         else if (a == "--size") { if (std::sscanf(next(), "%ux%u", &info.width, &info.height) != 2) { usage(); return 2; } }
         else if (a == "--spp") info.spp = (uint32_t)std::atoi(next());
@@ -58,8 +59,9 @@ int main(int argc, char** argv)
     try {
         ModelLoader loader(device);
         auto t0 = std::chrono::steady_clock::now();
-        std::shared_ptr<Model> m = loader.LoadFromFile(model, tech, lod[0], lod[1], lod[2]);
+        std::shared_ptr<Model> m = models.size() > 1 ? loader.LoadFromFiles(models, tech) : loader.LoadFromFile(model, tech, lod[0], lod[1], lod[2]);
         if (!m) return 1;
+        if (models.size() > 1) { model.clear(); for (const std::string& p : models) model += (model.empty() ? "" : " + ") + p; }
         const VkhrtTiming bt = m->Timing();
         std::printf("[MODEL LOADING] %s: %u primitives (%s), load+build %.1f ms wall, device build %.2f ms (sort %.2f, hierarchy %.2f, refit %.2f)\n",
                     model.c_str(), m->PrimitiveCount(), technique.c_str(),
@@ -71,7 +73,7 @@ int main(int argc, char** argv)
         Renderer renderer(info, camera);
         renderer.AddModel(m);
         for (int g = 1; g < gpus; ++g) {
-            std::shared_ptr<Model> r = ModelLoader(device + g).LoadFromFile(model, tech, lod[0], lod[1], lod[2]);
+            std::shared_ptr<Model> r = models.size() > 1 ? ModelLoader(device + g).LoadFromFiles(models, tech) : ModelLoader(device + g).LoadFromFile(model, tech, lod[0], lod[1], lod[2]);
             if (!r) return 1;
             renderer.AddReplica(r);
         }
@@ -86,6 +88,11 @@ int main(int argc, char** argv)
         size_t n_hit = 0;
         for (const VkhrtHit& h : renderer.GetHits()) n_hit += h.flags & 1u;
         std::printf("hits: %zu of %zu rays\n", n_hit, renderer.GetHits().size());
+        if (m->MeshCount() > 1) {
+            std::vector<size_t> per_mesh(m->MeshCount(), 0);
+            for (const VkhrtHit& h : renderer.GetHits()) if (h.flags & 1u) per_mesh[m->MeshOfSegment(h.segment)]++;
+            for (size_t k = 0; k < per_mesh.size(); ++k) std::printf("  mesh %zu: %zu rays\n", k, per_mesh[k]);
+        }
         if (!ppm.empty() && !renderer.WritePPM(ppm)) { std::fprintf(stderr, "[FILE] cannot write %s\n", ppm.c_str()); return 1; }
         if (!png.empty() && !renderer.WritePNG(png)) { std::fprintf(stderr, "[FILE] cannot write %s\n", png.c_str()); return 1; }
         if (!hits_path.empty()) {

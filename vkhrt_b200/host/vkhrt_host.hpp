@@ -29,6 +29,7 @@
 #include <stdexcept>
 #include <string>
 #include <string_view>
+#include <array>
 #include <vector>
 
 #include "../../include/vkhrt_b200.h"
@@ -95,7 +96,35 @@ struct ModelCreation {
     // strand level of detail, run on the device before the build (vkhrt_scene_apply_lod):
     // SplitLines / MergeLines / MergeCurvesFast of geometry_processor.cpp:69-197
     uint32_t lineSplitPasses = 0, lineMergePasses = 0, curveMergePasses = 0;
+    // several meshes in one model / scene (MergeModels): mesh m = segments [meshFirstSegment[m], meshFirstSegment[m + 1]) with its own
+    // albedo factor; empty = one mesh.  The reference keeps one BLAS per mesh under a TLAS (renderer.cpp:694-727).
+    std::vector<uint32_t> meshFirstSegment {};
+    std::vector<std::array<float, 4>> meshAlbedoFactor {};
 };
+
+// The scene of several models as ONE line list, addressed the way GenerateLines addresses a mesh inside the model's buffers
+// (firstVertex / firstIndex, geometry_processor.cpp:45-67).  Radii: per vertex as soon as one part has them (the others get their constant).
+inline ModelCreation MergeModels(const std::vector<ModelCreation>& parts)
+{
+    ModelCreation out;
+    if (parts.empty()) return out;
+    out.radius = parts[0].radius; out.technique = parts[0].technique;
+    bool anyRadii = false;
+    for (const ModelCreation& p : parts) anyRadii = anyRadii || !p.radiusBuffer.empty();
+    for (const ModelCreation& p : parts) {
+        const uint32_t firstVertex = (uint32_t)out.vertexBuffer.size();
+        out.meshFirstSegment.push_back((uint32_t)(out.indexBuffer.size() / 2));
+        out.meshAlbedoFactor.push_back({ p.albedoFactor[0], p.albedoFactor[1], p.albedoFactor[2], p.albedoFactor[3] });
+        out.vertexBuffer.insert(out.vertexBuffer.end(), p.vertexBuffer.begin(), p.vertexBuffer.end());
+        for (uint32_t i : p.indexBuffer) out.indexBuffer.push_back(firstVertex + i);
+        if (anyRadii) {
+            if (p.radiusBuffer.empty()) out.radiusBuffer.insert(out.radiusBuffer.end(), p.vertexBuffer.size(), p.radius);
+            else out.radiusBuffer.insert(out.radiusBuffer.end(), p.radiusBuffer.begin(), p.radiusBuffer.end());
+        }
+        out.sceneName += (out.sceneName.empty() ? "" : " + ") + p.sceneName;
+    }
+    return out;
+}
 
 // geometry_processor.hpp:4-7 — in the reference these run the generators on the host; here they only
 // select which generator the device build runs (build.cu), keeping the call sites identical.
@@ -121,7 +150,14 @@ public:
         VkhrtMaterial mat {};
         std::memcpy(mat.albedo_factor, creation.albedoFactor, sizeof(mat.albedo_factor));
         vkhrt_scene_set_material(_scene, &mat);
-        int rc = vkhrt_scene_apply_lod(_scene, creation.lineSplitPasses, creation.lineMergePasses, creation.curveMergePasses);
+        if (creation.meshFirstSegment.size() > 1) {
+            Check(vkhrt_scene_set_meshes(_scene, creation.meshFirstSegment.data(), (uint32_t)creation.meshFirstSegment.size()), "vkhrt_scene_set_meshes");
+            for (size_t m = 0; m < creation.meshAlbedoFactor.size(); ++m) {
+                std::memcpy(mat.albedo_factor, creation.meshAlbedoFactor[m].data(), sizeof(mat.albedo_factor));
+                Check(vkhrt_scene_set_mesh_material(_scene, (uint32_t)m, &mat), "vkhrt_scene_set_mesh_material");
+            }
+        }
+        int rc = (creation.lineSplitPasses | creation.lineMergePasses | creation.curveMergePasses) == 0u ? VKHRT_OK : vkhrt_scene_apply_lod(_scene, creation.lineSplitPasses, creation.lineMergePasses, creation.curveMergePasses);
         if (rc == VKHRT_OK) rc = vkhrt_scene_build(_scene);
         if (rc != VKHRT_OK) { vkhrt_scene_destroy(_scene); _scene = nullptr; throw VkhrtError(rc, "vkhrt_scene_build"); }
     }
@@ -131,6 +167,9 @@ public:
 
     void Refit(const std::vector<vec3>& positions) { Check(vkhrt_scene_refit(_scene, &positions[0].x), "vkhrt_scene_refit"); }
     [[nodiscard]] uint32_t PrimitiveCount() const { return vkhrt_scene_primitive_count(_scene); }
+    [[nodiscard]] uint32_t MeshCount() const { return vkhrt_scene_mesh_count(_scene); }
+    // gl_InstanceCustomIndexEXT of a hit record: the mesh that owns its segment
+    [[nodiscard]] uint32_t MeshOfSegment(uint32_t segment) const { uint32_t m = 0; Check(vkhrt_scene_mesh_of_segments(_scene, &segment, &m, 1), "vkhrt_scene_mesh_of_segments"); return m; }
     [[nodiscard]] VkhrtTechnique Technique() const { return _technique; }
     [[nodiscard]] VkhrtScene* Handle() const { return _scene; }
     [[nodiscard]] VkhrtTiming Timing() const { VkhrtTiming t {}; Check(vkhrt_last_timing(_scene, &t), "vkhrt_last_timing"); return t; }
@@ -153,6 +192,16 @@ public:
         if (!LoadModel(path, creation)) { std::fprintf(stderr, "[MODEL LOADING] Failed to load %.*s\n", (int)path.size(), path.data()); return nullptr; }
         creation.technique = technique;
         creation.lineSplitPasses = lineSplitPasses; creation.lineMergePasses = lineMergePasses; creation.curveMergePasses = curveMergePasses;
+        return ProcessModel(creation);
+    }
+    // The reference's scene is a LIST of models (renderer.cpp:33-41): all of them in one device scene, one mesh each
+    [[nodiscard]] std::shared_ptr<Model> LoadFromFiles(const std::vector<std::string>& paths, VkhrtTechnique technique = VKHRT_TECHNIQUE_LSS)
+    {
+        std::vector<ModelCreation> parts(paths.size());
+        for (size_t i = 0; i < paths.size(); ++i)
+            if (!LoadModel(paths[i], parts[i])) { std::fprintf(stderr, "[MODEL LOADING] Failed to load %s\n", paths[i].c_str()); return nullptr; }
+        ModelCreation creation = MergeModels(parts);
+        creation.technique = technique;
         return ProcessModel(creation);
     }
     [[nodiscard]] static bool LoadModel(std::string_view path, ModelCreation& out)
@@ -266,7 +315,7 @@ public:
     }
 
     // One frame: UpdateCameraResource + traceRaysKHR(width, height, 1) + read-back, blocking.
-    // (The reference TLAS holds several BLAS; this path renders one groom per Renderer, the first model.)
+    // (The reference TLAS holds several BLAS; here a scene of several meshes is ONE Model — ModelLoader::LoadFromFiles / MergeModels.)
     void Render()
     {
         if (_models.empty()) throw std::runtime_error("Renderer::Render: no model");
