@@ -47,16 +47,15 @@ VK_DEV Bezier gen_curve(const MeshIn& m, uint32_t i)
         b.p0 = f3(c[0], c[1], c[2]); b.p1 = f3(c[3], c[4], c[5]); b.p2 = f3(c[6], c[7], c[8]); b.p3 = f3(c[9], c[10], c[11]);
         return b;
     }
-    float3 s = load_pos(m, m.idx[2 * i]), e = load_pos(m, m.idx[2 * i + 1]);
-    float3 p0 = s, p3 = e;
-    if (i > 0) {
-        float3 pe = load_pos(m, m.idx[2 * (i - 1) + 1]);
-        if (same_point(pe, s)) p0 = load_pos(m, m.idx[2 * (i - 1)]);
-    }
-    if (i + 1 < m.n_segments) {
-        float3 ns = load_pos(m, m.idx[2 * (i + 1)]);
-        if (same_point(e, ns)) p3 = load_pos(m, m.idx[2 * (i + 1) + 1]);
-    }
+    // All index pairs first, then all six vertices, then the selection: two dependent round trips to memory instead of four (the
+    // neighbours' far vertices are fetched whether or not the strand continues; they are the next / previous thread's own vertices).
+    const uint2* pairs = reinterpret_cast<const uint2*>(m.idx);
+    const bool has_prev = i > 0, has_next = i + 1 < m.n_segments;
+    const uint2 ic = __ldg(pairs + i), ip = __ldg(pairs + (has_prev ? i - 1 : i)), in = __ldg(pairs + (has_next ? i + 1 : i));
+    const float3 s = load_pos(m, ic.x), e = load_pos(m, ic.y);
+    const float3 pe = load_pos(m, ip.y), pp = load_pos(m, ip.x), ns = load_pos(m, in.x), nn = load_pos(m, in.y);
+    const float3 p0 = (has_prev && same_point(pe, s)) ? pp : s;
+    const float3 p3 = (has_next && same_point(e, ns)) ? nn : e;
     const float k = 1.0f / 6.0f;
     Bezier c;
     c.p0 = s;
@@ -533,7 +532,8 @@ VK_DEV int prefix_len(const uint64_t* __restrict__ m, int n, int i, int j)
 constexpr int REFIT_TILE_SHIFT = 9, REFIT_TILE = 1 << REFIT_TILE_SHIFT;
 __global__ void __launch_bounds__(256) karras_kernel(const uint64_t* __restrict__ morton, const uint32_t* __restrict__ sorted_ids, int n,
                                                      uint32_t* __restrict__ nodes_u32 /* 16 words per node */,
-                                                     uint32_t* __restrict__ parent_internal, uint32_t* __restrict__ parent_leaf, uint8_t* __restrict__ node_local)
+                                                     uint32_t* __restrict__ parent_internal, uint32_t* __restrict__ parent_leaf, uint8_t* __restrict__ node_local,
+                                                     uint32_t* __restrict__ child0)
 {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n - 1) return;
@@ -553,14 +553,21 @@ __global__ void __launch_bounds__(256) karras_kernel(const uint64_t* __restrict_
     } while (t > 1);
     int gamma = i + s * d + min(d, 0);
     int lo = min(i, j), hi = max(i, j);
-    node_local[i] = (lo >> REFIT_TILE_SHIFT) == (hi >> REFIT_TILE_SHIFT) ? 1 : 0;
+    const bool local = (lo >> REFIT_TILE_SHIFT) == (hi >> REFIT_TILE_SHIFT);
     uint32_t c0, c1, p0 = 0, p1 = 0;
     if (lo == gamma) { c0 = VKHRT_BVH_LEAF | (uint32_t)gamma; p0 = sorted_ids[gamma]; parent_leaf[gamma] = ((uint32_t)i << 1); }
     else { c0 = (uint32_t)gamma; parent_internal[gamma] = ((uint32_t)i << 1); }
     if (hi == gamma + 1) { c1 = VKHRT_BVH_LEAF | (uint32_t)(gamma + 1); p1 = sorted_ids[gamma + 1]; parent_leaf[gamma + 1] = ((uint32_t)i << 1) | 1u; }
     else { c1 = (uint32_t)(gamma + 1); parent_internal[gamma + 1] = ((uint32_t)i << 1) | 1u; }
-    uint32_t* nd = nodes_u32 + (size_t)i * 16;
-    nd[3] = c0; nd[7] = c1; nd[11] = p0; nd[15] = p1;
+    // The four non-box words of a node follow from child0 and one bit (child1 = child0's position + 1; prim words = sorted_ids there).
+    // Nodes inside one refit tile get their WHOLE 64-byte record from materialise_refit_kernel (full 16-byte stores: scattering these four
+    // words here cost a read-modify-write of every 32-byte sector of the node array); only the few nodes shared between tiles are written here.
+    child0[i] = c0;
+    node_local[i] = (uint8_t)((local ? 1u : 0u) | ((c1 & VKHRT_BVH_LEAF) ? 2u : 0u));
+    if (!local) {
+        uint32_t* nd = nodes_u32 + (size_t)i * 16;
+        nd[3] = c0; nd[7] = c1; nd[11] = p0; nd[15] = p1;
+    }
     if (i == 0) parent_internal[0] = 0xFFFFFFFFu;
 }
 
@@ -570,11 +577,11 @@ __global__ void __launch_bounds__(256) karras_kernel(const uint64_t* __restrict_
 // boxes do not depend on arrival order.
 // ------------------------------------------------------------------------------------------------
 template <int TECH>
-__global__ void __launch_bounds__(REFIT_TILE) materialise_refit_kernel(MeshIn m, uint32_t n_prims, const uint32_t* __restrict__ sorted_ids,
+__global__ void __launch_bounds__(REFIT_TILE, TECH == VKHRT_TECHNIQUE_PHANTOM ? 2 : 4) materialise_refit_kernel(MeshIn m, uint32_t n_prims, const uint32_t* __restrict__ sorted_ids,
                                                                 float4* __restrict__ primA, float4* __restrict__ primB, float2* __restrict__ primR,
                                                                 float* nodes_f32, const uint32_t* __restrict__ parent_internal,
                                                                 const uint32_t* __restrict__ parent_leaf, uint32_t* flags,
-                                                                const uint8_t* __restrict__ node_local,
+                                                                const uint8_t* __restrict__ node_local, const uint32_t* __restrict__ child0,
                                                                 float4* __restrict__ exits /* 2 per entry */, uint32_t* __restrict__ exit_count, uint32_t exit_cap)
 {
     // Everything the walk needs for the nodes INSIDE this CTA's tile of leaves lives in shared memory (index = node - tile base):
@@ -583,24 +590,29 @@ __global__ void __launch_bounds__(REFIT_TILE) materialise_refit_kernel(MeshIn m,
     __shared__ float s_box[REFIT_TILE][12];        // lo0 hi0 lo1 hi1 (the box words of VkhrtBvhNode, without the child / prim words)
     __shared__ uint32_t s_arrived[REFIT_TILE];
     __shared__ uint32_t s_parent[REFIT_TILE];
-    __shared__ uint8_t s_local[REFIT_TILE];
+    __shared__ uint32_t s_child0[REFIT_TILE];      // child 0 of the node; child 1 sits one position further (bit 1 of s_local: it is a leaf)
+    __shared__ uint32_t s_leaf[REFIT_TILE];        // sorted_ids of the tile's leaves (the prim words of the node records)
+    __shared__ uint8_t s_local[REFIT_TILE];        // bit 0: the node's leaf range lies inside this tile
     const uint32_t tile_base = blockIdx.x * REFIT_TILE;
+    uint32_t p = 0;
     {
         const uint32_t node = tile_base + threadIdx.x;
         const bool in = n_prims > 1 && node < n_prims - 1;
         s_arrived[threadIdx.x] = 0u;
         s_parent[threadIdx.x] = in ? parent_internal[node] : 0u;
+        s_child0[threadIdx.x] = in ? child0[node] : 0u;
         s_local[threadIdx.x] = in ? node_local[node] : (uint8_t)0;
+        s_leaf[threadIdx.x] = node < n_prims ? sorted_ids[node] : 0u;
+        if (node < n_prims && n_prims > 1) p = parent_leaf[node];          // needed after the record's arithmetic: fetched with the rest
     }
     __syncthreads();
     uint32_t pos = tile_base + threadIdx.x;
     bool walking = pos < n_prims;
     Aabb box;
     box.lo = box.hi = f3(0, 0, 0);
-    uint32_t p = 0;
     if (walking) {
     // the leaf's record is its GROUP's (a curve / LSS / strip reached through any of its pieces is tested whole); its box is the piece's
-    const uint32_t leaf = sorted_ids[pos];
+    const uint32_t leaf = s_leaf[threadIdx.x];
     const uint32_t prim = leaf / LeafSplit<TECH>::K;
     if (TECH == VKHRT_TECHNIQUE_PHANTOM) {
         Bezier c = gen_curve(m, prim);
@@ -652,11 +664,10 @@ __global__ void __launch_bounds__(REFIT_TILE) materialise_refit_kernel(MeshIn m,
     }
     // phase 1: up through the nodes inside this tile (shared memory only); a walker that reaches a node shared with other
     // CTAs parks there (p, box) until the tile's boxes have been written out
-    p = parent_leaf[pos];
     while (walking) {
         const uint32_t node = p >> 1, slot = p & 1u;
         const uint32_t li = node - tile_base;                 // < REFIT_TILE exactly for the nodes indexed inside this tile
-        if (!(li < (uint32_t)REFIT_TILE && s_local[li])) break;
+        if (!(li < (uint32_t)REFIT_TILE && (s_local[li] & 1))) break;
         // both children of this node come from threads of this CTA: ~50 cycles per level instead of a round trip to L2
         float* mine = s_box[li] + 6 * slot;
         mine[0] = box.lo.x; mine[1] = box.lo.y; mine[2] = box.lo.z; mine[3] = box.hi.x; mine[4] = box.hi.y; mine[5] = box.hi.z;
@@ -671,10 +682,19 @@ __global__ void __launch_bounds__(REFIT_TILE) materialise_refit_kernel(MeshIn m,
     }
     }   // if (walking)
     __syncthreads();
-    // the tile's local nodes: box words 0-2, 4-6, 8-10, 12-14 of each 16-word record, consecutive threads -> consecutive words
-    for (uint32_t k = threadIdx.x; k < (uint32_t)REFIT_TILE * 16u; k += REFIT_TILE) {
-        const uint32_t li = k >> 4, wd = k & 15u;
-        if ((wd & 3u) != 3u && s_local[li]) nodes_f32[(size_t)(tile_base + li) * 16 + wd] = s_box[li][(wd >> 2) * 3 + (wd & 3u)];
+    // the tile's local nodes: whole records, one 16-byte store per thread and quarter record (consecutive threads -> consecutive addresses):
+    // {lo0, child0} {hi0, child1} {lo1, prim0} {hi1, prim1}
+    for (uint32_t k = threadIdx.x; k < (uint32_t)REFIT_TILE * 4u; k += REFIT_TILE) {
+        const uint32_t li = k >> 2, q = k & 3u;
+        const uint32_t fl = s_local[li];
+        if (fl & 1u) {
+            const uint32_t c0 = s_child0[li], g = (c0 & ~VKHRT_BVH_LEAF) - tile_base;        // child positions g, g + 1: inside the tile
+            const bool leaf1 = (fl & 2u) != 0u;
+            const uint32_t w = q == 0u ? c0 : (q == 1u ? ((c0 & ~VKHRT_BVH_LEAF) + 1u) | (leaf1 ? VKHRT_BVH_LEAF : 0u)
+                                                       : (q == 2u ? ((c0 & VKHRT_BVH_LEAF) ? s_leaf[g] : 0u) : (leaf1 ? s_leaf[g + 1u] : 0u)));
+            const float* b = s_box[li] + 3u * q;
+            reinterpret_cast<float4*>(nodes_f32)[(size_t)(tile_base + li) * 4 + q] = make_float4(b[0], b[1], b[2], __uint_as_float(w));
+        }
     }
     // phase 2: the few walkers that left the tile (a handful per CTA) go on through the nodes shared between CTAs in a kernel of
     // their own (upper_refit_kernel), so that this CTA's 512 threads do not stay resident for one thread's chain of L2 round trips
@@ -791,7 +811,7 @@ int build_scene(DeviceScene& sc, bool refit_only)
                      o_pleaf = o_pint + up((size_t)sc.n_nodes * 4), o_flags = o_pleaf + up((size_t)n * 4), o_primA = o_flags + up((size_t)sc.n_nodes * 4),
                      o_primB = o_primA + up((size_t)n * primA_per * 16), o_primR = o_primB + (tech == VKHRT_TECHNIQUE_PHANTOM ? up((size_t)n * 32) : 0),
                      o_local = o_primR + ((tech == VKHRT_TECHNIQUE_PHANTOM && sc.d_radius_pv) ? up((size_t)n * 8) : 0),
-                     o_exits = o_local + up((size_t)sc.n_nodes), o_exit_count = o_exits + up(((size_t)n / 8 + 4096) * 32),
+                     o_child0 = o_local + up((size_t)sc.n_nodes), o_exits = o_child0 + up((size_t)sc.n_nodes * 4), o_exit_count = o_exits + up(((size_t)n / 8 + 4096) * 32),
                      total = o_exit_count + 256;
         if (sc.arena_bytes < total) {
             if (sc.d_arena) cudaFree(sc.d_arena);
@@ -804,7 +824,7 @@ int build_scene(DeviceScene& sc, bool refit_only)
         sc.d_refit_flags = (uint32_t*)(sc.d_arena + o_flags); sc.d_primA = (float4*)(sc.d_arena + o_primA);
         sc.d_primB = tech == VKHRT_TECHNIQUE_PHANTOM ? (float4*)(sc.d_arena + o_primB) : nullptr;
         sc.d_primR = (tech == VKHRT_TECHNIQUE_PHANTOM && sc.d_radius_pv) ? (float2*)(sc.d_arena + o_primR) : nullptr;
-        sc.d_node_local = (uint8_t*)(sc.d_arena + o_local);
+        sc.d_node_local = (uint8_t*)(sc.d_arena + o_local); sc.d_child0 = (uint32_t*)(sc.d_arena + o_child0);
         sc.d_refit_exits = (float4*)(sc.d_arena + o_exits); sc.d_refit_exit_count = (uint32_t*)(sc.d_arena + o_exit_count);
         sc.refit_exit_cap = (uint32_t)std::min<size_t>((size_t)n / 8 + 4096, 0x7FFFFFFFu);
 
@@ -858,7 +878,7 @@ int build_scene(DeviceScene& sc, bool refit_only)
         VK_CUDA_S(cudaMemsetAsync(sc.d_nodes, 0, (size_t)sc.n_nodes * 64, st));
         if (n > 1) {
             karras_kernel<<<cdiv(n - 1, 256), 256, 0, st>>>(sc.d_sorted_morton, sc.d_sorted_ids, (int)n, (uint32_t*)sc.d_nodes,
-                                                            sc.d_parent_internal, sc.d_parent_leaf, sc.d_node_local);
+                                                            sc.d_parent_internal, sc.d_parent_leaf, sc.d_node_local, sc.d_child0);
         } else {
             single_node_kernel<<<1, 1, 0, st>>>((uint32_t*)sc.d_nodes, sc.d_sorted_ids);
         }
@@ -876,11 +896,11 @@ int build_scene(DeviceScene& sc, bool refit_only)
     VK_CUDA(cudaMemsetAsync(sc.d_refit_exit_count, 0, 4, st));
     const uint32_t g = cdiv(n, REFIT_TILE);
     if (tech == VKHRT_TECHNIQUE_PHANTOM)
-        materialise_refit_kernel<VKHRT_TECHNIQUE_PHANTOM><<<g, REFIT_TILE, 0, st>>>(m, n, sc.d_sorted_ids, sc.d_primA, sc.d_primB, sc.d_primR, (float*)sc.d_nodes, sc.d_parent_internal, sc.d_parent_leaf, sc.d_refit_flags, sc.d_node_local, sc.d_refit_exits, sc.d_refit_exit_count, sc.refit_exit_cap);
+        materialise_refit_kernel<VKHRT_TECHNIQUE_PHANTOM><<<g, REFIT_TILE, 0, st>>>(m, n, sc.d_sorted_ids, sc.d_primA, sc.d_primB, sc.d_primR, (float*)sc.d_nodes, sc.d_parent_internal, sc.d_parent_leaf, sc.d_refit_flags, sc.d_node_local, sc.d_child0, sc.d_refit_exits, sc.d_refit_exit_count, sc.refit_exit_cap);
     else if (tech == VKHRT_TECHNIQUE_LSS)
-        materialise_refit_kernel<VKHRT_TECHNIQUE_LSS><<<g, REFIT_TILE, 0, st>>>(m, n, sc.d_sorted_ids, sc.d_primA, sc.d_primB, sc.d_primR, (float*)sc.d_nodes, sc.d_parent_internal, sc.d_parent_leaf, sc.d_refit_flags, sc.d_node_local, sc.d_refit_exits, sc.d_refit_exit_count, sc.refit_exit_cap);
+        materialise_refit_kernel<VKHRT_TECHNIQUE_LSS><<<g, REFIT_TILE, 0, st>>>(m, n, sc.d_sorted_ids, sc.d_primA, sc.d_primB, sc.d_primR, (float*)sc.d_nodes, sc.d_parent_internal, sc.d_parent_leaf, sc.d_refit_flags, sc.d_node_local, sc.d_child0, sc.d_refit_exits, sc.d_refit_exit_count, sc.refit_exit_cap);
     else
-        materialise_refit_kernel<VKHRT_TECHNIQUE_DOTS><<<g, REFIT_TILE, 0, st>>>(m, n, sc.d_sorted_ids, sc.d_primA, sc.d_primB, sc.d_primR, (float*)sc.d_nodes, sc.d_parent_internal, sc.d_parent_leaf, sc.d_refit_flags, sc.d_node_local, sc.d_refit_exits, sc.d_refit_exit_count, sc.refit_exit_cap);
+        materialise_refit_kernel<VKHRT_TECHNIQUE_DOTS><<<g, REFIT_TILE, 0, st>>>(m, n, sc.d_sorted_ids, sc.d_primA, sc.d_primB, sc.d_primR, (float*)sc.d_nodes, sc.d_parent_internal, sc.d_parent_leaf, sc.d_refit_flags, sc.d_node_local, sc.d_child0, sc.d_refit_exits, sc.d_refit_exit_count, sc.refit_exit_cap);
     // the walkers that left their tiles (their number is only known on the device: the grid covers the list's capacity, idle threads return at once)
     if (n > 1) upper_refit_kernel<<<cdiv(sc.refit_exit_cap, 256), 256, 0, st>>>(sc.d_refit_exits, sc.d_refit_exit_count, sc.refit_exit_cap, (float*)sc.d_nodes, sc.d_parent_internal, sc.d_refit_flags);
     count_launch(2);

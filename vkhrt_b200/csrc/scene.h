@@ -47,7 +47,8 @@ struct DeviceScene {
     uint32_t* d_parent_leaf = nullptr;      // n_leaves
     uint32_t* d_refit_flags = nullptr;      // n_nodes
     float4* d_refit_exits = nullptr; uint32_t* d_refit_exit_count = nullptr; uint32_t refit_exit_cap = 0;   // walkers that leave their refit tile
-    uint8_t* d_node_local = nullptr;        // n_nodes: 1 = the node's leaf range lies inside one refit tile (handled in shared memory)
+    uint8_t* d_node_local = nullptr;        // n_nodes: bit 0 = the node's leaf range lies inside one refit tile (handled in shared memory), bit 1 = child 1 is a leaf
+    uint32_t* d_child0 = nullptr;           // n_nodes: child 0 (child 1 = its position + 1): the refit writes whole records of tile-local nodes
     float scene_lo[3] = {0, 0, 0}, scene_hi[3] = {0, 0, 0};
     uint32_t h_bounds[6] = {};            // centroid bounds as ordered uints, copied back at the end of a build
     unsigned char* d_build_scratch = nullptr; size_t build_scratch_bytes = 0;   // centroids, sort ping-pong, histograms, look-back status
