@@ -527,13 +527,16 @@ VK_DEV int prefix_len(const uint64_t* __restrict__ m, int n, int i, int j)
     return __clzll((long long)(a ^ b));
 }
 
-// The bottom-up box pass works on tiles of REFIT_TILE consecutive (Morton-sorted) leaves, one CTA each: a node whose leaf range lies
+// The bottom-up box pass works on tiles of RefitTile<TECH>::N consecutive (Morton-sorted) leaves, one CTA each: a node whose leaf range lies
 // inside one tile is only ever reached by threads of that CTA (node_local = 1) and is handled in shared memory.
-constexpr int REFIT_TILE_SHIFT = 9, REFIT_TILE = 1 << REFIT_TILE_SHIFT;
+// Tile size per technique (measured on the C2 groom, refit ms at 256 / 512 leaves per tile: Phantom 0.545 / 0.566 — its record arithmetic is long,
+// more and smaller CTAs overlap their phases better; LSS 0.358 / 0.354, DOTS 0.768 / 0.743 — short records, the deeper local walk wins).
+template <int TECH> struct RefitTile { static constexpr int SHIFT = TECH == VKHRT_TECHNIQUE_PHANTOM ? 8 : 9, N = 1 << SHIFT; };
+static int refit_tile_shift(int tech) { return tech == VKHRT_TECHNIQUE_PHANTOM ? RefitTile<VKHRT_TECHNIQUE_PHANTOM>::SHIFT : RefitTile<VKHRT_TECHNIQUE_LSS>::SHIFT; }
 __global__ void __launch_bounds__(256) karras_kernel(const uint64_t* __restrict__ morton, const uint32_t* __restrict__ sorted_ids, int n,
                                                      uint32_t* __restrict__ nodes_u32 /* 16 words per node */,
                                                      uint32_t* __restrict__ parent_internal, uint32_t* __restrict__ parent_leaf, uint8_t* __restrict__ node_local,
-                                                     uint32_t* __restrict__ child0)
+                                                     uint32_t* __restrict__ child0, int tile_shift)
 {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n - 1) return;
@@ -553,7 +556,7 @@ __global__ void __launch_bounds__(256) karras_kernel(const uint64_t* __restrict_
     } while (t > 1);
     int gamma = i + s * d + min(d, 0);
     int lo = min(i, j), hi = max(i, j);
-    const bool local = (lo >> REFIT_TILE_SHIFT) == (hi >> REFIT_TILE_SHIFT);
+    const bool local = (lo >> tile_shift) == (hi >> tile_shift);
     uint32_t c0, c1, p0 = 0, p1 = 0;
     if (lo == gamma) { c0 = VKHRT_BVH_LEAF | (uint32_t)gamma; p0 = sorted_ids[gamma]; parent_leaf[gamma] = ((uint32_t)i << 1); }
     else { c0 = (uint32_t)gamma; parent_internal[gamma] = ((uint32_t)i << 1); }
@@ -577,13 +580,14 @@ __global__ void __launch_bounds__(256) karras_kernel(const uint64_t* __restrict_
 // boxes do not depend on arrival order.
 // ------------------------------------------------------------------------------------------------
 template <int TECH>
-__global__ void __launch_bounds__(REFIT_TILE, TECH == VKHRT_TECHNIQUE_PHANTOM ? 2 : 4) materialise_refit_kernel(MeshIn m, uint32_t n_prims, const uint32_t* __restrict__ sorted_ids,
+__global__ void __launch_bounds__(RefitTile<TECH>::N, (TECH == VKHRT_TECHNIQUE_PHANTOM ? 1024 : 2048) / RefitTile<TECH>::N) materialise_refit_kernel(MeshIn m, uint32_t n_prims, const uint32_t* __restrict__ sorted_ids,
                                                                 float4* __restrict__ primA, float4* __restrict__ primB, float2* __restrict__ primR,
                                                                 float* nodes_f32, const uint32_t* __restrict__ parent_internal,
                                                                 const uint32_t* __restrict__ parent_leaf, uint32_t* flags,
                                                                 const uint8_t* __restrict__ node_local, const uint32_t* __restrict__ child0,
                                                                 float4* __restrict__ exits /* 2 per entry */, uint32_t* __restrict__ exit_count, uint32_t exit_cap)
 {
+    constexpr int REFIT_TILE = RefitTile<TECH>::N;
     // Everything the walk needs for the nodes INSIDE this CTA's tile of leaves lives in shared memory (index = node - tile base):
     // the parent link and the "local" bit (loaded coalesced), an arrival counter, and both child boxes, which are written to the
     // node records by the whole CTA at the end (12 of every 16 words, consecutive threads -> consecutive words).
@@ -716,6 +720,7 @@ __global__ void __launch_bounds__(REFIT_TILE, TECH == VKHRT_TECHNIQUE_PHANTOM ? 
         uint32_t arrived;
         asm volatile("atom.acq_rel.gpu.global.add.u32 %0, [%1], 1;" : "=r"(arrived) : "l"(flags + node) : "memory");
         if (arrived == 0u) break;                            // first arrival: the sibling will carry on
+        flags[node] = 0u;                                    // clean for the next pass
         const float* sb = nodes_f32 + (size_t)node * 16 + 8 * (1u - slot);
         const float2 l01 = __ldcg(reinterpret_cast<const float2*>(sb)), h01 = __ldcg(reinterpret_cast<const float2*>(sb + 4));
         const float lz = __ldcg(sb + 2), hz = __ldcg(sb + 6);
@@ -738,19 +743,21 @@ __global__ void __launch_bounds__(256) upper_refit_kernel(const float4* __restri
     uint32_t p = __float_as_uint(e0.w);
     for (;;) {
         const uint32_t node = p >> 1, slot = p & 1u;
+        const uint32_t up = __ldg(parent_internal + node);     // fetched while the stores and the atomic are in flight (used only by the second arrival)
         float* nd = nodes_f32 + (size_t)node * 16 + 8 * slot;
         __stcg(reinterpret_cast<float2*>(nd), make_float2(box.lo.x, box.lo.y)); __stcg(nd + 2, box.lo.z);
         __stcg(reinterpret_cast<float2*>(nd + 4), make_float2(box.hi.x, box.hi.y)); __stcg(nd + 6, box.hi.z);
         uint32_t arrived;
         asm volatile("atom.acq_rel.gpu.global.add.u32 %0, [%1], 1;" : "=r"(arrived) : "l"(flags + node) : "memory");
         if (arrived == 0u) return;
+        flags[node] = 0u;                                      // both children are in: the counter is clean for the next pass (no memset per refit)
         const float* sb = nodes_f32 + (size_t)node * 16 + 8 * (1u - slot);
         const float2 l01 = __ldcg(reinterpret_cast<const float2*>(sb)), h01 = __ldcg(reinterpret_cast<const float2*>(sb + 4));
         const float lz = __ldcg(sb + 2), hz = __ldcg(sb + 6);
         box.lo.x = fminf(box.lo.x, l01.x); box.lo.y = fminf(box.lo.y, l01.y); box.lo.z = fminf(box.lo.z, lz);
         box.hi.x = fmaxf(box.hi.x, h01.x); box.hi.y = fmaxf(box.hi.y, h01.y); box.hi.z = fmaxf(box.hi.z, hz);
         if (node == 0) return;
-        p = parent_internal[node];
+        p = up;
     }
 }
 
@@ -878,7 +885,7 @@ int build_scene(DeviceScene& sc, bool refit_only)
         VK_CUDA_S(cudaMemsetAsync(sc.d_nodes, 0, (size_t)sc.n_nodes * 64, st));
         if (n > 1) {
             karras_kernel<<<cdiv(n - 1, 256), 256, 0, st>>>(sc.d_sorted_morton, sc.d_sorted_ids, (int)n, (uint32_t*)sc.d_nodes,
-                                                            sc.d_parent_internal, sc.d_parent_leaf, sc.d_node_local, sc.d_child0);
+                                                            sc.d_parent_internal, sc.d_parent_leaf, sc.d_node_local, sc.d_child0, refit_tile_shift(tech));
         } else {
             single_node_kernel<<<1, 1, 0, st>>>((uint32_t*)sc.d_nodes, sc.d_sorted_ids);
         }
@@ -891,16 +898,16 @@ int build_scene(DeviceScene& sc, bool refit_only)
         VK_CUDA(cudaEventRecord(ev[1], st)); VK_CUDA(cudaEventRecord(ev[2], st));
         VK_CUDA(cudaEventRecord(ev[3], st)); VK_CUDA(cudaEventRecord(ev[4], st));
     }
-    // 4 materialise + refit
-    VK_CUDA(cudaMemsetAsync(sc.d_refit_flags, 0, (size_t)sc.n_nodes * 4, st));
+    // 4 materialise + refit (the arrival counters of the nodes shared between tiles clean themselves: zeroed once per build)
+    if (!refit_only) VK_CUDA(cudaMemsetAsync(sc.d_refit_flags, 0, (size_t)sc.n_nodes * 4, st));
     VK_CUDA(cudaMemsetAsync(sc.d_refit_exit_count, 0, 4, st));
-    const uint32_t g = cdiv(n, REFIT_TILE);
+    const uint32_t g = cdiv(n, 1u << refit_tile_shift(tech));
     if (tech == VKHRT_TECHNIQUE_PHANTOM)
-        materialise_refit_kernel<VKHRT_TECHNIQUE_PHANTOM><<<g, REFIT_TILE, 0, st>>>(m, n, sc.d_sorted_ids, sc.d_primA, sc.d_primB, sc.d_primR, (float*)sc.d_nodes, sc.d_parent_internal, sc.d_parent_leaf, sc.d_refit_flags, sc.d_node_local, sc.d_child0, sc.d_refit_exits, sc.d_refit_exit_count, sc.refit_exit_cap);
+        materialise_refit_kernel<VKHRT_TECHNIQUE_PHANTOM><<<g, RefitTile<VKHRT_TECHNIQUE_PHANTOM>::N, 0, st>>>(m, n, sc.d_sorted_ids, sc.d_primA, sc.d_primB, sc.d_primR, (float*)sc.d_nodes, sc.d_parent_internal, sc.d_parent_leaf, sc.d_refit_flags, sc.d_node_local, sc.d_child0, sc.d_refit_exits, sc.d_refit_exit_count, sc.refit_exit_cap);
     else if (tech == VKHRT_TECHNIQUE_LSS)
-        materialise_refit_kernel<VKHRT_TECHNIQUE_LSS><<<g, REFIT_TILE, 0, st>>>(m, n, sc.d_sorted_ids, sc.d_primA, sc.d_primB, sc.d_primR, (float*)sc.d_nodes, sc.d_parent_internal, sc.d_parent_leaf, sc.d_refit_flags, sc.d_node_local, sc.d_child0, sc.d_refit_exits, sc.d_refit_exit_count, sc.refit_exit_cap);
+        materialise_refit_kernel<VKHRT_TECHNIQUE_LSS><<<g, RefitTile<VKHRT_TECHNIQUE_LSS>::N, 0, st>>>(m, n, sc.d_sorted_ids, sc.d_primA, sc.d_primB, sc.d_primR, (float*)sc.d_nodes, sc.d_parent_internal, sc.d_parent_leaf, sc.d_refit_flags, sc.d_node_local, sc.d_child0, sc.d_refit_exits, sc.d_refit_exit_count, sc.refit_exit_cap);
     else
-        materialise_refit_kernel<VKHRT_TECHNIQUE_DOTS><<<g, REFIT_TILE, 0, st>>>(m, n, sc.d_sorted_ids, sc.d_primA, sc.d_primB, sc.d_primR, (float*)sc.d_nodes, sc.d_parent_internal, sc.d_parent_leaf, sc.d_refit_flags, sc.d_node_local, sc.d_child0, sc.d_refit_exits, sc.d_refit_exit_count, sc.refit_exit_cap);
+        materialise_refit_kernel<VKHRT_TECHNIQUE_DOTS><<<g, RefitTile<VKHRT_TECHNIQUE_DOTS>::N, 0, st>>>(m, n, sc.d_sorted_ids, sc.d_primA, sc.d_primB, sc.d_primR, (float*)sc.d_nodes, sc.d_parent_internal, sc.d_parent_leaf, sc.d_refit_flags, sc.d_node_local, sc.d_child0, sc.d_refit_exits, sc.d_refit_exit_count, sc.refit_exit_cap);
     // the walkers that left their tiles (their number is only known on the device: the grid covers the list's capacity, idle threads return at once)
     if (n > 1) upper_refit_kernel<<<cdiv(sc.refit_exit_cap, 256), 256, 0, st>>>(sc.d_refit_exits, sc.d_refit_exit_count, sc.refit_exit_cap, (float*)sc.d_nodes, sc.d_parent_internal, sc.d_refit_flags);
     count_launch(2);

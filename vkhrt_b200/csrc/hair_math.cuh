@@ -97,14 +97,14 @@ VK_DEV float bezier_bound_radius(const Bezier& c, float radius)
 // r + dev (+ rounding slack) from ALL four projected quarter-chords, the march cannot report anything and
 // is skipped.  bezier_quarter_chord_deviation() (= sagitta/16 of the whole curve) is evaluated once per curve
 // by the build kernel.
-VK_DEV float point_segment_distance(float3 p, float3 a, float3 b)
+VK_DEV float point_segment_distance2(float3 p, float3 a, float3 b)      // squared
 {
     float3 e = b - a, q = p - a;
     float ee = fdot3(e, e);
     float t = fminf(fmaxf(fdot3(q, e), 0.0f), ee);
     float s = ee > 0.0f ? t / ee : 0.0f;
     float3 r = q - s * e;
-    return sqrtf(fdot3(r, r));
+    return fdot3(r, r);
 }
 // de Casteljau split of a cubic at t = 1/2
 VK_DEV void bezier_split(const Bezier& c, Bezier& l, Bezier& r)
@@ -115,9 +115,11 @@ VK_DEV void bezier_split(const Bezier& c, Bezier& l, Bezier& r)
     l.p0 = c.p0; l.p1 = q01; l.p2 = r0; l.p3 = m;
     r.p0 = m; r.p1 = r1; r.p2 = q23; r.p3 = c.p3;
 }
-VK_DEV float bezier_chord_deviation(const Bezier& c)      // max distance of the curve from its chord SEGMENT (hull bound)
+// max distance of the curve from its chord SEGMENT (hull bound), SQUARED.  The oracle takes the maximum of the eight distances; sqrtf is
+// monotone (and correctly rounded), so the root of the largest square is bit-for-bit the largest root: one sqrtf per curve instead of eight.
+VK_DEV float bezier_chord_deviation2(const Bezier& c)
 {
-    return fmaxf(point_segment_distance(c.p1, c.p0, c.p3), point_segment_distance(c.p2, c.p0, c.p3));
+    return fmaxf(point_segment_distance2(c.p1, c.p0, c.p3), point_segment_distance2(c.p2, c.p0, c.p3));
 }
 // An accepted Prhi hit h lies sqrt(r^2 + (dt |B'(t)|)^2) from B(t) with |dt| < 5e-5 (hair_intersection.rint:67), i.e. up to
 // (5e-5 max|B'|)^2 / (2 r) farther than r.  max|B'| <= 3 max|p[i+1] - p[i]| (hull of the derivative's control points).  For hair-like
@@ -135,10 +137,10 @@ VK_DEV float bezier_quarter_chord_deviation(const Bezier& c)
     Bezier l, r, a, b;
     bezier_split(c, l, r);
     bezier_split(l, a, b);
-    float dv = fmaxf(bezier_chord_deviation(a), bezier_chord_deviation(b));
+    float dv2 = fmaxf(bezier_chord_deviation2(a), bezier_chord_deviation2(b));
     bezier_split(r, a, b);
-    dv = fmaxf(dv, fmaxf(bezier_chord_deviation(a), bezier_chord_deviation(b)));
-    return dv * 1.001f + 1e-7f;      // the bound must stay conservative under fp32 rounding
+    dv2 = fmaxf(dv2, fmaxf(bezier_chord_deviation2(a), bezier_chord_deviation2(b)));
+    return sqrtf(dv2) * 1.001f + 1e-7f;      // the bound must stay conservative under fp32 rounding
 }
 // is the origin farther than sqrt(b2) from the 2-D segment [a, b]?  Division-free: compares d^2 * |e|^2 with b2 * |e|^2.
 // Any NaN makes the comparison false (= "not farther").
