@@ -360,6 +360,7 @@ def main():
         raise SystemExit("bench.py needs a CUDA device: vkhrt_b200 has no CPU path")
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    os.environ.setdefault("NCCL_DEBUG", "WARN")       # keeps NCCL's version banner off stdout: rank 0 prints ONE line
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
 
