@@ -425,6 +425,35 @@ def test_multi_mesh_scene(V, O, tech):
             sc.apply_lod(1, 0, 0)
 
 
+def test_multi_mesh_with_per_vertex_radii_and_refit(V, O):
+    """meshes with their own per-vertex radii (merge_meshes concatenates them), then a refit of the whole scene: records and the per-mesh
+    albedo image stay equal to the oracle's"""
+    p1, i1 = V.generate_groom(500, 9, V.GROOM_CURLY)
+    p2, i2 = V.generate_groom(400, 6, V.GROOM_CURLY, seed=21)
+    p2 = p2 + np.float32([3.0, 1.0, 0.0])
+    r1 = np.tile(np.linspace(0.03, 0.008, 10, dtype=np.float32), 500)
+    r2 = np.full(p2.shape[0], 0.015, np.float32)
+    pos, idx, rad, first = V.merge_meshes([(p1, i1, r1), (p2, i2, r2)])
+    assert rad.shape[0] == pos.shape[0]
+    with pytest.raises(ValueError):
+        V.merge_meshes([(p1, i1, r1), (p2, i2)])
+    W, H = 200, 128
+    vi, pi = default_camera(V, W, H)
+    for tech in TECHS:
+        with V.Scene(pos, idx, technique=tech, radius_per_vertex=rad) as sc:
+            sc.set_meshes(first).set_mesh_material(0, (1.0, 0.6, 0.3, 1.0)).set_mesh_material(1, (0.3, 0.6, 1.0, 1.0)).build()
+            moved = pos + np.float32([0.05, -0.02, 0.03])
+            sc.refit(moved)
+            orc = O.OracleScene(moved, idx, technique=tech, radius_per_vertex=rad)
+            orc.set_meshes(first); orc.set_mesh_material(0, (1.0, 0.6, 0.3, 1.0)); orc.set_mesh_material(1, (0.3, 0.6, 1.0, 1.0))
+            hg, ig, _ = sc.render(V.make_frame(vi, pi, W, H, spp=2, shade_mode=V.SHADE_MATERIAL))
+            ho, io, _ = orc.render(O.make_frame(vi, pi, W, H, spp=2, shade_mode=2))
+            assert_bit_identical(hg, ho)
+            assert np.array_equal(ig, io)
+            hit = (hg["flags"] & 1) != 0
+            assert set(np.unique(sc.mesh_of_segments(hg["segment"][hit]))) == {0, 1}
+
+
 def test_stats_counters_equal_the_oracles(V, O, small_groom):
     """The warp scheduler only interleaves lanes; each ray's own sequence of node visits and candidate tests is the
     oracle's, so the traversal counters (the N_int / N_prim of the bytes-per-ray roofline) are IDENTICAL."""
@@ -709,13 +738,14 @@ def test_render_multi_from_one_process(V, small_groom, tech):
 
 @pytest.mark.parametrize("env", [{"VKHRT_POOL_MIN_RATIO": "0"}, {"VKHRT_POOL_MIN_RATIO": "0", "VKHRT_POOL_CFG": "1"},
                                  {"VKHRT_POOL_MIN_RATIO": "0", "VKHRT_POOL_CFG": "2"}, {"VKHRT_POOL": "0"},
-                                 {"VKHRT_POOL_MIN_RATIO": "0", "VKHRT_POOL_LSS": "1", "VKHRT_POOL_DOTS": "1"}],
-                         ids=["pool-on-every-frame", "pool-56x8", "pool-64x6", "lane-bound-only", "pool-for-lss-and-dots"])
+                                 {"VKHRT_POOL_MIN_RATIO": "0", "VKHRT_POOL_LSS": "1", "VKHRT_POOL_DOTS": "1"}, {"VKHRT_REFIT_EXIT_CAP": "16"}],
+                         ids=["pool-on-every-frame", "pool-56x8", "pool-64x6", "lane-bound-only", "pool-for-lss-and-dots", "refit-exit-list-overflows"])
 def test_both_traversal_kernels_pass_the_whole_suite(env):
     """Phantom primary rays have two traversal kernels: the per-warp ray pool (frames >= 3x its resident capacity) and the lane-bound
     kernel (everything else).  The library reads its switches once per process, so the whole parity file is re-run in a subprocess
     with the pool forced onto every frame size (tiny, ragged, sharded, empty ...) and with the pool switched off (full-size C2 on
-    the lane-bound kernel).  The last variant sends LSS and DOTS primary rays through the pool kernel too (an opt-in switch: measured no faster)."""
+    the lane-bound kernel).  One variant sends LSS and DOTS primary rays through the pool kernel too (an opt-in switch: measured no faster); the last one shrinks the
+    refit's exit list to 16 entries, so that nearly every walker that leaves its tile finishes inside materialise_refit_kernel (the overflow path)."""
     import os
     import subprocess
     import sys

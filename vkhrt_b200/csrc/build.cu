@@ -834,6 +834,10 @@ int build_scene(DeviceScene& sc, bool refit_only)
         sc.d_node_local = (uint8_t*)(sc.d_arena + o_local); sc.d_child0 = (uint32_t*)(sc.d_arena + o_child0);
         sc.d_refit_exits = (float4*)(sc.d_arena + o_exits); sc.d_refit_exit_count = (uint32_t*)(sc.d_arena + o_exit_count);
         sc.refit_exit_cap = (uint32_t)std::min<size_t>((size_t)n / 8 + 4096, 0x7FFFFFFFu);
+        // test switch (read once): a tiny exit list makes the walkers that do not fit finish inside materialise_refit_kernel, the path a
+        // scene with more tile exits than the list holds would take
+        static const int cap_override = [] { const char* v = getenv("VKHRT_REFIT_EXIT_CAP"); return v ? atoi(v) : 0; }();
+        if (cap_override > 0) sc.refit_exit_cap = std::min<uint32_t>(sc.refit_exit_cap, (uint32_t)cap_override);
 
         // ... and one for the build's scratch, kept with the scene (a per-frame rebuild of a dynamic groom allocates nothing)
         const uint32_t os_tiles = cdiv(n, OS_TILE);
