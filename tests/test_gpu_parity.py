@@ -518,15 +518,20 @@ def test_pinned_host_buffers_zero_copy_path(V, small_groom, tech):
     vi, pi = default_camera(V, W, H)
     with V.Scene(pos, idx, technique=tech) as sc:
         sc.build()
-        href, iref, _ = sc.render(V.make_frame(vi, pi, W, H, spp=2))
-        for want_rgba in (False, True):
-            hh = torch.zeros((W * H, 32), dtype=torch.uint8).pin_memory()
-            hi = torch.zeros((W * H, 4), dtype=torch.uint8).pin_memory()
-            f = V.make_frame(vi, pi, W, H, spp=2, output_memory=V.MEM_HOST)
-            sc.render_into(f, hh.data_ptr(), hi.data_ptr() if want_rgba else None)      # blocks until complete
-            assert np.array_equal(hh.numpy().reshape(-1), href.view(np.uint8))
-            if want_rgba:
-                assert np.array_equal(hi.numpy(), iref)
+        # spp 1 with an image: records mirrored by the kernel (HBM copy for the shading pass); spp > 1 with an image: the records of
+        # sample 0 leave on the copy engine while the other samples are traced
+        for spp in (1, 2, 5):
+            href, iref, _ = sc.render(V.make_frame(vi, pi, W, H, spp=spp))
+            for want_rgba in (False, True):
+                hh = torch.zeros((W * H, 32), dtype=torch.uint8).pin_memory()
+                hi = torch.zeros((W * H, 4), dtype=torch.uint8).pin_memory()
+                f = V.make_frame(vi, pi, W, H, spp=spp, output_memory=V.MEM_HOST)
+                for _ in range(2):                                                              # twice: the scratch buffers are reused
+                    hh.zero_()
+                    sc.render_into(f, hh.data_ptr(), hi.data_ptr() if want_rgba else None)      # blocks until complete
+                    assert np.array_equal(hh.numpy().reshape(-1), href.view(np.uint8))
+                    if want_rgba:
+                        assert np.array_equal(hi.numpy(), iref)
 
 
 @pytest.mark.parametrize("W,H,shard", [(201, 121, None), (333, 77, None), (200, 120, (1, 3)), (1920, 1080, None), (1928, 1083, (0, 2))])

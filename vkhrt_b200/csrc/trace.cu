@@ -1022,7 +1022,7 @@ static void fill_params(const DeviceScene& sc, const VkhrtFrameDesc& f, const Re
 struct Tunables {
     int refill_threshold, min_blocks, blocks_per_sm, w_node, w_leaf, w_march;
     int pool, pool_stats, pool_min_ratio, pool_node_lanes, pool_batch_lanes, pool_node_min, pool_exit, pool_cfg, pool_host, carveout;
-    int store256, zero_copy, linewise, line_shift, sample_batch, pool_lss, pool_dots;
+    int store256, zero_copy, linewise, line_shift, sample_batch, pool_lss, pool_dots, early_copy;
 };
 static float bits_to_float(uint32_t u) { float f; std::memcpy(&f, &u, 4); return f; }
 static int env_int(const char* name, int def) { const char* v = getenv(name); return v ? atoi(v) : def; }
@@ -1054,6 +1054,7 @@ static const Tunables& tun()
         x.store256 = env_int("VKHRT_STORE256", 1);
         x.zero_copy = env_int("VKHRT_ZERO_COPY", 1);
         x.linewise = env_int("VKHRT_LINEWISE", 1);
+        x.early_copy = env_int("VKHRT_EARLY_COPY", 1);       // multi-sample frames: sample-0 records leave on the copy engine under the other samples
         x.sample_batch = env_int("VKHRT_SAMPLE_BATCH", 1);     // 0 = one launch per sample (round 1)
         // 128-byte lines (4 records) measured best: e2e 996 (64 B) / 1077 (128 B) / 1068 (256 B) / 1034 (512 B) Mrays/s on C2
         x.line_shift = std::min(5, std::max(1, env_int("VKHRT_LINE_SHIFT", 2)));
@@ -1273,6 +1274,11 @@ int render_frame(DeviceScene& sc, const VkhrtFrameDesc& f, VkhrtHit* hits_out, u
     }
     VkhrtHit* h_lines = nullptr;
     if (linewise) { h_lines = h_hits_mapped; d_hits0 = sc.d_hits_scratch; h_hits_mapped = nullptr; }
+    // Several samples per pixel and a page-locked record buffer: the records belong to sample 0, so instead of mirroring every record
+    // over PCIe from inside the sample-0 kernel (which then runs at the link's pace: C3 2.1 ms instead of 0.93) they stay in HBM and
+    // the copy engine takes them out while the other samples are traced.
+    bool early_copy = false;
+    if (h_hits_mapped && multi && !shared_frame && tun().early_copy) { early_copy = true; h_hits_mapped = nullptr; }
     if (h_hits_mapped && !want_rgba) { d_hits0 = h_hits_mapped; h_hits_mapped = nullptr; direct_to_host = true; }   // single destination
     if (multi) d_hits_other = sc.d_hits_scratch + r.n_out;
     if (want_rgba) {
@@ -1334,6 +1340,12 @@ int render_frame(DeviceScene& sc, const VkhrtFrameDesc& f, VkhrtHit* hits_out, u
             }
         }
         if (s == 0) VK_CUDA(cudaEventRecord(ev[12], st));
+        if (s == 0 && early_copy) {
+            VK_CUDA(cudaEventRecord(ev[13], st));
+            VK_CUDA(cudaStreamWaitEvent(sc.copy_stream, ev[13], 0));
+            VK_CUDA(cudaMemcpyAsync(hits_out, d_hits0, (size_t)r.n_out * sizeof(VkhrtHit), cudaMemcpyDeviceToHost, sc.copy_stream));
+            VK_CUDA(cudaEventRecord(ev[14], sc.copy_stream));
+        }
         if (want_rgba) {
             // one shading pass per sample, in sample order (the fp32 accumulation order is part of the result)
             const bool env = f.miss_mode == VKHRT_MISS_ENVIRONMENT && sc.d_env;
@@ -1351,7 +1363,8 @@ int render_frame(DeviceScene& sc, const VkhrtFrameDesc& f, VkhrtHit* hits_out, u
         s += kb;
     }
     VK_CUDA(cudaEventRecord(ev[10], st));
-    if (hits_host && !h_hits_mapped && !direct_to_host && !linewise) VK_CUDA(cudaMemcpyAsync(hits_out, d_hits0, (size_t)r.n_out * sizeof(VkhrtHit), cudaMemcpyDeviceToHost, st));
+    if (early_copy) VK_CUDA(cudaStreamWaitEvent(st, ev[14], 0));          // the frame is complete on `st` when the records have landed too
+    else if (hits_host && !h_hits_mapped && !direct_to_host && !linewise) VK_CUDA(cudaMemcpyAsync(hits_out, d_hits0, (size_t)r.n_out * sizeof(VkhrtHit), cudaMemcpyDeviceToHost, st));
     if (rgba_host) VK_CUDA(cudaMemcpyAsync(rgba_out, d_rgba, (size_t)r.n_out * 4, cudaMemcpyDeviceToHost, st));
     VK_CUDA(cudaEventRecord(ev[11], st));
     if (stats) {
