@@ -551,7 +551,7 @@ def main():
             "config": {"workload": workload_desc(name, world, W, H, T), "rays_per_step": rays_per_step, "rays_per_gpu_per_step": rays_per_step // world,
                        "l2": "256 MB flush between timed frames; scene is %.0f MB (%d BVH leaves: a 64-byte node and a %d-byte primitive record each)" % (n_leaves * (64 + LEAF_RECORD_BYTES[tech]) / 1e6, n_leaves, LEAF_RECORD_BYTES[tech]),
                        "seed": hex(V.DEFAULT_SEED), "build_ms": build_timing["build_total_ms"],
-                       "traversal_kernel": ("value: trace_pool2_kernel (per-warp ray pool) for Phantom frames of >= 3x the pool's resident capacity, else "
+                       "traversal_kernel": ("value: trace_pool_kernel (per-warp ray pool) for Phantom frames of >= 3x the pool's resident capacity, else "
                                             "trace_kernel (lane-bound); e2e: the same kernel delivering complete 128-byte lines of records to the page-locked host buffer"),
                        "frame_assembly": {"single": "one GPU", "peer": "traversal kernels store hit records straight into rank 0's frame buffer over NVLink (CUDA IPC peer mapping, two alternating buffer sets), 4-byte NCCL all_reduce as completion signal",
                                           "gather": "NCCL all_gather of compact shards + untile kernel"}[sharded.mode]},

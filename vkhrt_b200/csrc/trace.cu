@@ -433,6 +433,9 @@ __global__ void __launch_bounds__(TR_BLOCK, MINB) trace_kernel(const TraceParams
 // Everything is warp-synchronous (queues are per warp), so there is no inter-warp protocol to get wrong.
 // The queues are LIFO stacks of slot ids: the most recently queued rays are served first, while the nodes and curves they
 // touched are still in L1 (a FIFO ring measured 4 % slower on C2); every queue drains when the warp runs out of other work.
+// The kernel is templated on the technique: for LSS / DOTS the LEAF batch runs the whole primitive test and the CAND / MARCH stages
+// compile away.  Parity holds, but those two measure no faster than trace_kernel (profiles/experiments/r02_pool_kernel.txt §8), so only
+// Phantom frames are dispatched here by default (VKHRT_POOL_LSS / VKHRT_POOL_DOTS opt in).
 // ------------------------------------------------------------------------------------------------
 constexpr int PL_OVF = 96;             // stack entries per slot in the global spill area (Karras depth <= 64 + 32)
 constexpr int PL_MINB = 8;             // CTAs per SM the register allocation is held to
