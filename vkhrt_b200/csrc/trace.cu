@@ -304,7 +304,8 @@ __global__ void __launch_bounds__(TR_BLOCK, MINB) trace_kernel(const TraceParams
                 have_ray = false;
                 if (SRC == SRC_AO) {
                     // one owner per pixel and pass: a plain read-modify-write is enough
-                    if (best_prim != PRIM_NONE) { p.ao_occluded[out_idx] += 1u; if (STATS) st_hits++; }
+                    // one owner per pixel and pass; with several passes in one launch (n_batch > 1) a pixel's rays are in flight together
+                    if (best_prim != PRIM_NONE) { if (p.n_batch > 1u) atomicAdd(p.ao_occluded + out_idx, 1u); else p.ao_occluded[out_idx] += 1u; if (STATS) st_hits++; }
                 } else if (best_prim != PRIM_NONE) {
                     float3 n;
                     uint32_t seg = best_prim;
@@ -352,7 +353,10 @@ __global__ void __launch_bounds__(TR_BLOCK, MINB) trace_kernel(const TraceParams
                         o = f3(r0.x, r0.y, r0.z); tmin = r0.w; d = f3(r1.x, r1.y, r1.z); tcur = r1.w;
                         out_idx = slot;
                     } else if (SRC == SRC_AO) {
-                        const PixelRef q = slot_to_pixel(p, slot);
+                        // several AO passes per launch: slot = pass * slots_per_sample + pixel slot
+                        uint32_t a_idx = p.ao_index, ls = slot;
+                        if (p.n_batch > 1u) { const uint32_t b = slot / p.slots_per_sample; ls = slot - b * p.slots_per_sample; a_idx += b; }
+                        const PixelRef q = slot_to_pixel(p, ls);
                         valid = q.valid;
                         out_idx = q.out;
                         if (valid) {
@@ -364,7 +368,7 @@ __global__ void __launch_bounds__(TR_BLOCK, MINB) trace_kernel(const TraceParams
                                 primary_ray(p.cam, p.W, p.H, q.px, q.py, p.sx, p.sy, &po, &pd);
                                 const float3 n = f3(h0.w, h1.x, h1.y);
                                 o = fmadd3(p.ao_bias, n, fmadd3(h0.x, pd, po));
-                                d = ao_direction(n, q.py * p.W + q.px, p.ao_sample, p.ao_index);
+                                d = ao_direction(n, q.py * p.W + q.px, p.ao_sample, a_idx);
                                 tmin = VKHRT_AO_T_MIN; tcur = p.ao_distance;
                             }
                         }
@@ -1335,11 +1339,17 @@ int render_frame(DeviceScene& sc, const VkhrtFrameDesc& f, VkhrtHit* hits_out, u
             q.ao_distance = f.ao_distance > 0.0f ? f.ao_distance : VKHRT_DEFAULT_AO_DISTANCE;
             q.ao_bias = f.ao_bias > 0.0f ? f.ao_bias : 0.25f * sc.radius;
             q.hits = nullptr; q.hits_mirror = nullptr;
-            for (uint32_t a = 0; a < ao; ++a) {
+            // the passes of a sample go up to 8 to a launch (the persistent kernel ramps up and drains once instead of `ao` times);
+            // the occlusion counts are integer sums, so the order the rays finish in cannot change them
+            const uint32_t ao_batch = (tun().sample_batch && r.n_slots * 8ull < 0xFFFFFFFFull) ? 8u : 1u;
+            for (uint32_t a = 0; a < ao;) {
+                const uint32_t ka = std::min(ao_batch, ao - a);
                 q.ao_index = a;
+                q.n_batch = ka; q.slots_per_sample = (uint32_t)r.n_slots; q.n_slots = (uint32_t)(r.n_slots * ka);
                 take_work_counter(sc, q);
                 rc = stats ? launch_trace<true, SRC_AO, true>(sc, q, st) : launch_trace<false, SRC_AO, true>(sc, q, st);
                 if (rc) return rc;
+                a += ka;
             }
         }
         if (s == 0) VK_CUDA(cudaEventRecord(ev[12], st));
