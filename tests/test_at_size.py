@@ -21,13 +21,13 @@ def host_gb():
         return 0.0
 
 
-def check(V, O, pos, idx, tech, W, H, spp, rgba, shade_mode=0):
+def check(V, O, pos, idx, tech, W, H, spp, rgba, shade_mode=0, radius_per_vertex=None):
     vi, pi = default_camera(V, W, H)
     sub = stratified_pixels(W, H, N_CHECK)
-    with V.Scene(pos, idx, technique=tech) as sc:
+    with V.Scene(pos, idx, technique=tech, radius_per_vertex=radius_per_vertex) as sc:
         sc.build()
         hg, ig, _ = sc.render(V.make_frame(vi, pi, W, H, spp=spp, shade_mode=shade_mode), rgba=rgba)
-    orc = O.OracleScene(pos, idx, technique=tech)
+    orc = O.OracleScene(pos, idx, technique=tech, radius_per_vertex=radius_per_vertex)
     ho, io, _ = orc.render(O.make_frame(vi, pi, W, H, spp=spp, shade_mode=shade_mode), rgba=rgba, pixel_subset=sub)
     orc.close()
     k = sub.astype(np.int64)
@@ -49,6 +49,13 @@ def groom_c2(V):
 def test_config2_phantom_at_size(V, O, groom_c2):
     """BASELINE configs[1]: curly 100k x 32 (3.2 M curves), 1920x1080, Phantom, hit buffer."""
     check(V, O, *groom_c2, V.PHANTOM, 1920, 1080, 1, False)
+
+
+def test_config2_groom_with_per_vertex_radii_at_size(V, O, groom_c2):
+    """The C2 groom with tapered strands (radius 0.02 at the root -> 0.005 at the tip, north_star's "per-vertex radius in"), 1920x1080, Phantom:
+    a frame of this size goes through the ray-pool kernel with the taper terms (radius(t), cone slant) in its set-up and march stages."""
+    rad = np.tile(np.linspace(0.02, 0.005, 33, dtype=np.float32), 100000)
+    check(V, O, *groom_c2, V.PHANTOM, 1920, 1080, 1, False, radius_per_vertex=rad)
 
 
 def test_config3_lss_at_size(V, O, groom_c2):

@@ -476,7 +476,7 @@ struct PoolWarp {
                                        // every push costs more than one LDS)
 };
 
-template <int TECH, bool STATS, int PL_S, int PL_STK, int MINB = PL_MINB>
+template <int TECH, bool STATS, int PL_S, int PL_STK, int MINB = PL_MINB, bool TAPER = false>
 __global__ void __launch_bounds__(TR_BLOCK, MINB) trace_pool_kernel(const TraceParams p)
 {
     constexpr bool PH = TECH == VKHRT_TECHNIQUE_PHANTOM;        // LSS / DOTS: the leaf batch runs the whole primitive test; no CAND / MARCH
@@ -499,7 +499,7 @@ __global__ void __launch_bounds__(TR_BLOCK, MINB) trace_pool_kernel(const TraceP
     bool mhave = false;
     MarchState ms;
     ms.c.p0 = ms.c.p1 = ms.c.p2 = ms.c.p3 = f3(0, 0, 0);
-    ms.t = ms.told = ms.dt1 = ms.dt2 = ms.t_start = 0.0f; ms.it = 0u;
+    ms.t = ms.told = ms.dt1 = ms.dt2 = ms.t_start = 0.0f; ms.it = 0u; ms.r0 = ms.dr = 0.0f;
     uint32_t m_slot = 0;
     uint32_t nR = 0, nL = 0, nC = 0, nD = 0, nF = PL_S;      // queue fills (warp-uniform)
     bool exhausted = false;
@@ -740,7 +740,9 @@ __global__ void __launch_bounds__(TR_BLOCK, MINB) trace_pool_kernel(const TraceP
                 Bezier w;
                 w.p0 = xyz(a0); w.p1 = xyz(b0); w.p2 = xyz(b1); w.p3 = xyz(a1);
                 march_begin(ms, make_ray_frame(d), o, w);
-                if (quarter_chords_near_ray(ms.c, p.radius, b0.w)) mhave = true;
+                float rfilter = p.radius;
+                if (TAPER) { const float2 rr = __ldg(p.primR + pos); ms.r0 = rr.x; ms.dr = rr.y - rr.x; rfilter = fmaxf(rr.x, rr.y); }   // per-vertex radii (§4.10)
+                if (quarter_chords_near_ray(ms.c, rfilter, b0.w)) mhave = true;
                 else { reject = true; next = pop_parked(m_slot); }
             }
             nC -= min(nC, (uint32_t)__popc(midle));
@@ -758,7 +760,7 @@ __global__ void __launch_bounds__(TR_BLOCK, MINB) trace_pool_kernel(const TraceP
                 if (mhave) {
                     if (STATS) st_iters++;
                     float t = 0.0f, u = 0.0f;
-                    const int r = march_step(ms, p.radius, &t, &u);
+                    const int r = march_step<TAPER>(ms, p.radius, &t, &u);
                     if (r != MARCH_CONTINUE) {
                         mhave = false; fin = true;
                         const uint32_t pos = sh.cur[m_slot] & 0x7FFFFFFFu;       // the slot still points at the candidate's leaf
@@ -1029,7 +1031,7 @@ static void fill_params(const DeviceScene& sc, const VkhrtFrameDesc& f, const Re
 struct Tunables {
     int refill_threshold, min_blocks, blocks_per_sm, w_node, w_leaf, w_march;
     int pool, pool_stats, pool_min_ratio, pool_node_lanes, pool_batch_lanes, pool_node_min, pool_exit, pool_cfg, pool_host, carveout;
-    int store256, zero_copy, linewise, line_shift, sample_batch, pool_lss, pool_dots, early_copy;
+    int store256, zero_copy, linewise, line_shift, sample_batch, pool_lss, pool_dots, early_copy, pool_taper;
 };
 static float bits_to_float(uint32_t u) { float f; std::memcpy(&f, &u, 4); return f; }
 static int env_int(const char* name, int def) { const char* v = getenv(name); return v ? atoi(v) : def; }
@@ -1056,6 +1058,7 @@ static const Tunables& tun()
         // long-scoreboard stalls double; C4 1059 vs 1040, e2e 996 vs 1020), so both default to the lane-bound kernel
         x.pool_lss = env_int("VKHRT_POOL_LSS", 0);
         x.pool_dots = env_int("VKHRT_POOL_DOTS", 0);
+        x.pool_taper = env_int("VKHRT_POOL_TAPER", 1);          // Phantom scenes with per-vertex radii through the pool kernel too
         x.pool_host = env_int("VKHRT_POOL_HOST", 0);
         x.carveout = env_int("VKHRT_CARVEOUT", -1);
         x.store256 = env_int("VKHRT_STORE256", 1);
@@ -1113,12 +1116,12 @@ static int launch_trace_t(DeviceScene& sc, TraceParams& p, cudaStream_t st)
     count_launch();
     return VKHRT_OK;
 }
-template <int TECH, bool STATS, int PL_S, int PL_STK, int MINB = PL_MINB>
+template <int TECH, bool STATS, int PL_S, int PL_STK, int MINB = PL_MINB, bool TAPER = false>
 static int launch_pool_t(DeviceScene& sc, TraceParams& p, cudaStream_t st)
 {
     const int carve = tun().carveout;
-    if (carve >= 0) VK_CUDA(cudaFuncSetAttribute(trace_pool_kernel<TECH, STATS, PL_S, PL_STK, MINB>, cudaFuncAttributePreferredSharedMemoryCarveout, carve));
-    int per_sm = blocks_per_sm(trace_pool_kernel<TECH, STATS, PL_S, PL_STK, MINB>, sc.device);
+    if (carve >= 0) VK_CUDA(cudaFuncSetAttribute(trace_pool_kernel<TECH, STATS, PL_S, PL_STK, MINB, TAPER>, cudaFuncAttributePreferredSharedMemoryCarveout, carve));
+    int per_sm = blocks_per_sm(trace_pool_kernel<TECH, STATS, PL_S, PL_STK, MINB, TAPER>, sc.device);
     if (tun().blocks_per_sm > 0) per_sm = std::min(per_sm, tun().blocks_per_sm);
     unsigned long long want = ((unsigned long long)(p.n_slots - p.slot_begin) + TR_BLOCK - 1) / TR_BLOCK;
     unsigned grid = (unsigned)std::min<unsigned long long>((unsigned long long)sc.sm_count * per_sm, std::max<unsigned long long>(want, 1ull));
@@ -1130,26 +1133,30 @@ static int launch_pool_t(DeviceScene& sc, TraceParams& p, cudaStream_t st)
         sc.pool_overflow_n = ovf;
     }
     p.pool_overflow = sc.d_pool_overflow;
-    trace_pool_kernel<TECH, STATS, PL_S, PL_STK, MINB><<<grid, TR_BLOCK, 0, st>>>(p);
+    trace_pool_kernel<TECH, STATS, PL_S, PL_STK, MINB, TAPER><<<grid, TR_BLOCK, 0, st>>>(p);
     sc.last_trace_was_pool = true;
     count_launch();
     return VKHRT_OK;
 }
-template <int TECH, bool STATS>
+template <int TECH, bool STATS, bool TAPER = false>
 static int launch_pool(DeviceScene& sc, TraceParams& p, cudaStream_t st)
 {
     // slots per warp x shared-memory stack window (profiles/experiments/r02_pool_kernel.txt): 72 x 4 measured best; 56 x 8 and 64 x 6
     // trade slots for fewer spill reads (-0.5 % / -1 %); 9 / 10 / 12 CTAs per SM at 56 / 48 / 40 registers lose 3 / 16 / 22 %
-    switch (tun().pool_cfg) {
-    case 1: return launch_pool_t<TECH, STATS, 56, 8>(sc, p, st);
-    case 2: return launch_pool_t<TECH, STATS, 64, 6>(sc, p, st);
-    default: return launch_pool_t<TECH, STATS, 72, 4>(sc, p, st);
+    if constexpr (TAPER) return launch_pool_t<TECH, STATS, 72, 4, PL_MINB, true>(sc, p, st);          // the experiment configurations are not instantiated for tapered scenes
+    else {
+        switch (tun().pool_cfg) {
+        case 1: return launch_pool_t<TECH, STATS, 56, 8>(sc, p, st);
+        case 2: return launch_pool_t<TECH, STATS, 64, 6>(sc, p, st);
+        default: return launch_pool_t<TECH, STATS, 72, 4>(sc, p, st);
+        }
     }
 }
 // does the per-warp ray-pool kernel serve this scene's primary rays? (uniform radius only; LSS / DOTS behind their switches)
 static bool pool_serves(const DeviceScene& sc)
 {
-    if (!tun().pool || sc.tapered()) return false;
+    if (!tun().pool) return false;
+    if (sc.tapered()) return sc.technique == VKHRT_TECHNIQUE_PHANTOM && tun().pool_taper;      // per-vertex radii: Phantom only
     return sc.technique == VKHRT_TECHNIQUE_PHANTOM || (sc.technique == VKHRT_TECHNIQUE_LSS && tun().pool_lss) || (sc.technique == VKHRT_TECHNIQUE_DOTS && tun().pool_dots);
 }
 
@@ -1162,7 +1169,13 @@ static int launch_trace(DeviceScene& sc, TraceParams& p, cudaStream_t st)
     if (tun().store256 == 0) p.hits_aligned32 = 0u;
     if (sc.tapered()) {
         // per-vertex radii (Phantom, DOTS): the lane-bound kernel with the taper terms compiled in (LSS always carries its radii)
-        if (sc.technique == VKHRT_TECHNIQUE_PHANTOM) return launch_trace_t<VKHRT_TECHNIQUE_PHANTOM, STATS, SRC, ANYHIT, TR_MIN_BLOCKS, true>(sc, p, st);
+        if (sc.technique == VKHRT_TECHNIQUE_PHANTOM) {
+            // primary rays of large frames: the pool kernel with the taper terms (radius(t), cone slant) in its set-up and march stages
+            if (SRC == SRC_PRIMARY && !ANYHIT && pool_serves(sc) && p.n_prims && (!STATS || tun().pool_stats) && !(p.host_dest && tun().pool_host == 0) &&
+                (unsigned long long)(p.n_slots - p.slot_begin) >= (unsigned long long)tun().pool_min_ratio * sc.sm_count * 32ull * 56ull)
+                return launch_pool<VKHRT_TECHNIQUE_PHANTOM, STATS, true>(sc, p, st);
+            return launch_trace_t<VKHRT_TECHNIQUE_PHANTOM, STATS, SRC, ANYHIT, TR_MIN_BLOCKS, true>(sc, p, st);
+        }
         return launch_trace_t<VKHRT_TECHNIQUE_DOTS, STATS, SRC, ANYHIT, TR_MIN_BLOCKS, true>(sc, p, st);
     }
     switch (sc.technique) {
