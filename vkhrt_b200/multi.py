@@ -15,6 +15,8 @@ so the only communication is the final gather of the shards.  Rank r traces tile
 
 The reference has no multi-GPU code at all (single graphics queue, source/vulkan_context.cpp:287-288).
 """
+import os
+
 import numpy as np
 
 from . import api as _api
@@ -209,26 +211,35 @@ class SharedHostFrame:
     def __init__(self, n_records, group=None, gather_rank=0):
         import torch
         import torch.distributed as dist
-        from multiprocessing import shared_memory
+        import _posixshmem      # shm_open / shm_unlink as multiprocessing.shared_memory uses them, without its resource tracker: the
+        import mmap             # tracker of Python < 3.13 also adopts ATTACHED segments and unlinks (or double-unregisters) them at exit
+        import secrets
         self.torch, self.dist, self.group = torch, dist, group
         self.rank = dist.get_rank(group) if dist.is_initialized() else 0
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
         self.nbytes = int(n_records) * 32
         self.owner = self.rank == gather_rank
+        self._unlink = _posixshmem.shm_unlink
         name = [None]
         if self.owner:
-            self.shm = shared_memory.SharedMemory(create=True, size=self.nbytes)
-            name = [self.shm.name]
+            self.name = "/vkhrt_frame_%d_%s" % (os.getpid(), secrets.token_hex(4))
+            fd = _posixshmem.shm_open(self.name, os.O_CREAT | os.O_EXCL | os.O_RDWR, mode=0o600)
+            try:
+                os.ftruncate(fd, max(self.nbytes, 1))
+                self.map = mmap.mmap(fd, max(self.nbytes, 1))
+            finally:
+                os.close(fd)
+            name = [self.name]
         if self.world > 1:
             dist.broadcast_object_list(name, src=gather_rank, group=group)
         if not self.owner:
-            self.shm = shared_memory.SharedMemory(name=name[0])
-            try:        # Python < 3.13 registers attached segments with the resource tracker too: only the creator unlinks
-                from multiprocessing import resource_tracker
-                resource_tracker.unregister(self.shm._name, "shared_memory")
-            except Exception:
-                pass
-        self.array = np.frombuffer(self.shm.buf, dtype=np.uint8, count=self.nbytes)
+            self.name = name[0]
+            fd = _posixshmem.shm_open(self.name, os.O_RDWR, mode=0o600)
+            try:
+                self.map = mmap.mmap(fd, max(self.nbytes, 1))
+            finally:
+                os.close(fd)
+        self.array = np.frombuffer(self.map, dtype=np.uint8, count=self.nbytes)
         self.ptr = self.array.ctypes.data
         rc = torch.cuda.cudart().cudaHostRegister(self.ptr, self.nbytes, 1 | 2)      # cudaHostRegisterPortable | Mapped
         if int(rc) != 0:
@@ -244,8 +255,12 @@ class SharedHostFrame:
             self.registered = False
         self.array = None
         try:
-            self.shm.close()
-            if self.owner:
-                self.shm.unlink()
-        except Exception:
-            pass
+            self.map.close()
+        except (BufferError, ValueError):
+            pass                    # a view handed out by hits() is still alive: the mapping goes with the process
+        if self.owner and getattr(self, "name", None):
+            try:
+                self._unlink(self.name)
+            except OSError:
+                pass
+            self.name = None
