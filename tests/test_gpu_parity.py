@@ -757,6 +757,7 @@ def test_both_traversal_kernels_pass_the_whole_suite(env):
     if os.environ.get("VKHRT_NESTED"):
         pytest.skip("nested run")
     e = dict(os.environ, VKHRT_NESTED="1", **env)
-    r = subprocess.run([sys.executable, "-m", "pytest", os.path.abspath(__file__), "-m", "gpu", "-x", "-q", "-p", "no:cacheprovider"],
+    here = os.path.dirname(os.path.abspath(__file__))
+    r = subprocess.run([sys.executable, "-m", "pytest", os.path.abspath(__file__), os.path.join(here, "test_random_scenes.py"), "-m", "gpu", "-x", "-q", "-p", "no:cacheprovider"],
                        env=e, capture_output=True, text=True, cwd=os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
