@@ -92,6 +92,21 @@ def test_random_small_scenes(V, O, tech, degenerate):
                     h2, i2, _ = sc.render(V.make_frame(vi, pi, W, H, **kw))
                     o2, oi2, _ = orc.render(O.make_frame(vi, pi, W, H, **kw))
                     assert same_records(h2, o2) and np.array_equal(i2, oi2), where
+            if seed % 6 == 1:
+                # secondary rays: 2 ambient-occlusion rays per hit pixel and sample (any-hit traversal spawned from the hit records)
+                ha, ia, _ = sc.render(V.make_frame(vi, pi, W, H, spp=spp, ao_samples=2))
+                oa, oia, _ = orc.render(O.make_frame(vi, pi, W, H, spp=spp, ao_samples=2))
+                assert same_records(ha, oa) and np.array_equal(ia, oia), where
             n_hits += int((ho["flags"] & 1).sum())
             orc.close()
+            if seed % 5 == 2:
+                # refit on moved vertices == a fresh oracle scene on them (same topology is kept; boxes and records follow the vertices)
+                moved = (pos + np.random.default_rng(seed).normal(scale=0.01, size=pos.shape)).astype(np.float32)
+                sc.refit(moved)
+                orc2 = O.OracleScene(moved, idx, technique=tech, radius=radius, radius_per_vertex=rpv)
+                hr, _, _ = sc.render(V.make_frame(vi, pi, W, H), rgba=False)
+                orr, _, _ = orc2.render(O.make_frame(vi, pi, W, H), rgba=False)
+                assert same_floats(sc.primitives(), orc2.primitives()), where
+                assert same_records(hr, orr), where
+                orc2.close()
     assert n_hits > 6000          # the cameras do look at the strands
