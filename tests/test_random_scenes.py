@@ -123,3 +123,44 @@ def test_random_small_scenes(V, O, tech, degenerate):
                 assert same_records(hl, hol) and np.array_equal(il, iol), where + f" lod {lod}"
                 ol.close()
     assert n_hits > 6000          # the cameras do look at the strands
+
+
+@pytest.mark.parametrize("tech", TECHS)
+def test_random_rays_through_the_wavefront_api(V, O, tech):
+    """vkhrt_trace_rays / _any_hit on rays a camera never makes: exactly axis-aligned directions (zero components: the slab test's
+    1/0 guard), rays that start inside a hair, rays pointing away, empty and tiny [tmin, tmax] intervals (unit directions only:
+    RayCylinderIntersect assumes them) — closest-hit and first-hit records equal the oracle's bit for bit."""
+    import torch
+    n = 6000
+    for seed in (0, 3, 5, 8):
+        pos, idx, radius, rpv, _ = random_scene(seed, degenerate=False)
+        rng = np.random.default_rng(77 + seed)
+        tgt = pos[rng.integers(0, pos.shape[0], n)] + rng.normal(0, 0.05, (n, 3))
+        o = tgt + rng.normal(0, 1, (n, 3)) * rng.choice([0.01, 0.5, 6.0], size=(n, 1))          # inside / near / far
+        d = tgt - o
+        d /= np.maximum(np.linalg.norm(d, axis=1, keepdims=True), 1e-20)
+        axis = rng.integers(0, 3, n)
+        aligned = rng.random(n) < 0.3                                                             # exactly axis-aligned rays
+        d[aligned] = 0.0
+        d[aligned, axis[aligned]] = rng.choice([-1.0, 1.0], size=int(aligned.sum()))
+        planar = (~aligned) & (rng.random(n) < 0.2)                                               # one zero component
+        d[planar, axis[planar]] = 0.0
+        d[planar] /= np.maximum(np.linalg.norm(d[planar], axis=1, keepdims=True), 1e-20)
+        o[aligned | planar] = tgt[aligned | planar] - 3.0 * d[aligned | planar] + rng.normal(0, 0.02, (int((aligned | planar).sum()), 3))
+        tmin = rng.choice([0.0, 1e-3, 0.5], size=(n, 1))
+        tmax = rng.choice([1e4, 5.0, 0.4, -1.0], size=(n, 1), p=[0.6, 0.2, 0.1, 0.1])               # incl. empty intervals
+        rays = np.concatenate([o, tmin, d, tmax], axis=1).astype(np.float32)
+        with V.Scene(pos, idx, technique=tech, radius=radius, radius_per_vertex=rpv) as sc:
+            sc.build()
+            orc = O.OracleScene(pos, idx, technique=tech, radius=radius, radius_per_vertex=rpv)
+            dr = torch.from_numpy(rays).cuda()
+            dh = torch.zeros((n, 32), dtype=torch.uint8, device="cuda")
+            st = torch.cuda.current_stream().cuda_stream
+            for any_hit in (False, True):
+                sc.trace_rays(dr.data_ptr(), n, dh.data_ptr(), st, any_hit=any_hit)
+                torch.cuda.synchronize()
+                ho = orc.trace_rays(rays, any_hit=any_hit)
+                hg = dh.cpu().numpy().reshape(-1).view(V.HIT_DTYPE)
+                assert (ho["flags"] & 1).sum() > 300, (seed, any_hit)
+                assert same_records(hg, ho), f"seed {seed} tech {tech} any_hit={any_hit}"
+            orc.close()
