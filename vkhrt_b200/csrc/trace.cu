@@ -1152,7 +1152,7 @@ static int launch_pool(DeviceScene& sc, TraceParams& p, cudaStream_t st)
         }
     }
 }
-// does the per-warp ray-pool kernel serve this scene's primary rays? (uniform radius only; LSS / DOTS behind their switches)
+// does the per-warp ray-pool kernel serve this scene's primary rays? (Phantom, with or without per-vertex radii; LSS / DOTS behind their switches)
 static bool pool_serves(const DeviceScene& sc)
 {
     if (!tun().pool) return false;
