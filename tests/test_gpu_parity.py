@@ -412,6 +412,13 @@ def test_multi_mesh_scene(V, O, tech):
         _, ia, _ = sc.render(V.make_frame(vi, pi, W, H, shade_mode=V.SHADE_MATERIAL))
         _, ib, _ = single.render(V.make_frame(vi, pi, W, H, shade_mode=V.SHADE_MATERIAL))
         assert np.array_equal(ia, ib)
+        # a table of ONE mesh: its material is the scene's
+        sc.set_meshes([0]).set_mesh_material(0, (0.7, 0.2, 0.9, 1.0)); single.set_material((0.7, 0.2, 0.9, 1.0))
+        orc.set_meshes([0]); orc.set_mesh_material(0, (0.7, 0.2, 0.9, 1.0))
+        _, ia, _ = sc.render(V.make_frame(vi, pi, W, H, shade_mode=V.SHADE_MATERIAL))
+        _, ib, _ = single.render(V.make_frame(vi, pi, W, H, shade_mode=V.SHADE_MATERIAL))
+        _, ic, _ = orc.render(O.make_frame(vi, pi, W, H, shade_mode=2))
+        assert sc.n_meshes == 1 and np.array_equal(ia, ib) and np.array_equal(ia, ic)
         # the table must start at 0 and ascend; LOD passes renumber segments
         with pytest.raises(V.VkhrtError):
             sc.set_meshes([1, 5])

@@ -278,6 +278,7 @@ int vkhrt_scene_set_mesh_material(VkhrtScene* scene, uint32_t mesh, const VkhrtM
     float a[4];
     if (int rc = evaluate_albedo(material, a)) return rc;
     std::memcpy(&sc.mesh_albedo[4 * (size_t)mesh], a, sizeof(a));
+    if (sc.mesh_first.size() == 1) std::memcpy(sc.albedo, a, sizeof(a));          // a table of one mesh is the scene's material
     sc.mesh_table_dirty = true;
     return VKHRT_OK;
 }
