@@ -519,12 +519,13 @@ static size_t scan_tmp_elems(uint32_t n)
 // Karras 2012 hierarchy over the sorted keys. Internal node i in [0, n-2], root = 0.
 // delta(i,j) = common-prefix length of the 64-bit keys, ties broken by the sorted position.
 // ------------------------------------------------------------------------------------------------
-VK_DEV int prefix_len(const uint64_t* __restrict__ m, int n, int i, int j)
+// `a` = m[i], loaded once by the caller (every search of node i compares against the same key)
+VK_DEV int prefix_len(const uint64_t* __restrict__ m, int n, int i, uint64_t a, int j)
 {
-    if (j < 0 || j >= n) return -1;
-    uint64_t a = m[i], b = m[j];
-    if (a == b) return 64 + __clz((uint32_t)i ^ (uint32_t)j);
-    return __clzll((long long)(a ^ b));
+    if ((unsigned)j >= (unsigned)n) return -1;
+    const uint64_t x = a ^ __ldg(m + j);
+    if (x == 0ull) return 64 + __clz((uint32_t)i ^ (uint32_t)j);
+    return __clzll((long long)x);
 }
 
 // The bottom-up box pass works on tiles of RefitTile<TECH>::N consecutive (Morton-sorted) leaves, one CTA each: a node whose leaf range lies
@@ -540,19 +541,20 @@ __global__ void __launch_bounds__(256) karras_kernel(const uint64_t* __restrict_
 {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n - 1) return;
-    int d = (prefix_len(morton, n, i, i + 1) - prefix_len(morton, n, i, i - 1)) >= 0 ? 1 : -1;
-    int dmin = prefix_len(morton, n, i, i - d);
+    const uint64_t key_i = __ldg(morton + i);
+    int d = (prefix_len(morton, n, i, key_i, i + 1) - prefix_len(morton, n, i, key_i, i - 1)) >= 0 ? 1 : -1;
+    int dmin = prefix_len(morton, n, i, key_i, i - d);
     int lmax = 2;
-    while (prefix_len(morton, n, i, i + lmax * d) > dmin) lmax *= 2;
+    while (prefix_len(morton, n, i, key_i, i + lmax * d) > dmin) lmax *= 2;
     int l = 0;
     for (int t = lmax / 2; t >= 1; t /= 2)
-        if (prefix_len(morton, n, i, i + (l + t) * d) > dmin) l += t;
+        if (prefix_len(morton, n, i, key_i, i + (l + t) * d) > dmin) l += t;
     int j = i + l * d;
-    int dnode = prefix_len(morton, n, i, j);
+    int dnode = prefix_len(morton, n, i, key_i, j);
     int s = 0, t = l;
     do {
         t = (t + 1) >> 1;
-        if (prefix_len(morton, n, i, i + (s + t) * d) > dnode) s += t;
+        if (prefix_len(morton, n, i, key_i, i + (s + t) * d) > dnode) s += t;
     } while (t > 1);
     int gamma = i + s * d + min(d, 0);
     int lo = min(i, j), hi = max(i, j);
