@@ -3,12 +3,15 @@
 nodes, hit records and the 2-spp image, bit for bit.  The second sweep adds DEGENERATE input (zero-length segments, repeated points), where
 both sides run the same fp32 operations into the same infinities / NaNs: floats are compared with NaN == NaN (the payload of a NaN is the one
 thing an x86 host and the GPU do not share)."""
+import os
+
 import numpy as np
 import pytest
 
 pytestmark = pytest.mark.gpu
 
 TECHS = [0, 1, 2]
+N_SEEDS = 16 if os.environ.get("VKHRT_NESTED") else 48      # the nested re-runs of the suite (other kernel variants) take a shorter sweep
 
 
 def random_scene(seed, degenerate):
@@ -65,7 +68,7 @@ def same_records(hg, ho):
 def test_random_small_scenes(V, O, tech, degenerate):
     W, H = 96, 64
     n_hits = 0
-    for seed in range(48):
+    for seed in range(N_SEEDS):
         pos, idx, radius, rpv, cam = random_scene(seed, degenerate)
         vi, pi = V.camera_matrices(position=cam, aspect=float(np.float32(W) / np.float32(H)))
         with V.Scene(pos, idx, technique=tech, radius=radius, radius_per_vertex=rpv) as sc:
@@ -122,7 +125,7 @@ def test_random_small_scenes(V, O, tech, degenerate):
                 hol, iol, _ = ol.render(O.make_frame(vi, pi, W, H))
                 assert same_records(hl, hol) and np.array_equal(il, iol), where + f" lod {lod}"
                 ol.close()
-    assert n_hits > 6000          # the cameras do look at the strands
+    assert n_hits > 125 * N_SEEDS          # the cameras do look at the strands
 
 
 @pytest.mark.parametrize("tech", TECHS)
