@@ -461,10 +461,11 @@ enum : int { Q_READY = 0, Q_LEAF = 1, Q_CAND = 2, Q_DONE = 3, Q_FREE = 4 };
 // ------------------------------------------------------------------------------------------------
 constexpr uint32_t R2_POP = 0x7FFFFFFDu, R2_DONE = 0x7FFFFFFEu, R2_IDLE = 0x7FFFFFFFu;   // cur < R2_POP: internal node
 
-template <int PL_S, int PL_STK>
+template <int PL_S, int PL_STK, bool ORG = false>
 struct PoolWarp {
     uint2 stack[PL_STK][PL_S];         // ring: entry k of the stack sits at [k % PL_STK] while index k >= lo
     float dir[6][PL_S];                // d.xyz, 1/d
+    float org[ORG ? 3 : 1][ORG ? PL_S : 1];   // ray origin, only for rays that do not start at the camera (ambient-occlusion rays)
     float tcur[PL_S];
     uint32_t cur[PL_S], best_pos[PL_S];
     uint32_t last_group[PL_S];         // Phantom: the curve this ray tested last (one-entry mailbox); LSS / DOTS: primitive id of the best hit
@@ -476,19 +477,24 @@ struct PoolWarp {
                                        // every push costs more than one LDS)
 };
 
-template <int TECH, bool STATS, int PL_S, int PL_STK, int MINB = PL_MINB, bool TAPER = false>
+// AO = the rays are ambient-occlusion rays spawned from the primary hit records (SRC_AO of trace_kernel: origin per slot, first accepted
+// hit ends the ray, result = the pixel's occlusion count); Phantom only.
+template <int TECH, bool STATS, int PL_S, int PL_STK, int MINB = PL_MINB, bool TAPER = false, bool AO = false>
 __global__ void __launch_bounds__(TR_BLOCK, MINB) trace_pool_kernel(const TraceParams p)
 {
     constexpr bool PH = TECH == VKHRT_TECHNIQUE_PHANTOM;        // LSS / DOTS: the leaf batch runs the whole primitive test; no CAND / MARCH
-    __shared__ PoolWarp<PL_S, PL_STK> sh_all[TR_BLOCK / 32];
+    static_assert(!AO || PH, "the ambient-occlusion variant of the pool kernel is Phantom only");
+    __shared__ PoolWarp<PL_S, PL_STK, AO> sh_all[TR_BLOCK / 32];
     if (blockIdx.x == 0 && threadIdx.x == 0) *p.work_next = 0ull;
     const unsigned FULL = 0xffffffffu;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const unsigned lt = (1u << lane) - 1u;
-    PoolWarp<PL_S, PL_STK>& sh = sh_all[warp];
+    PoolWarp<PL_S, PL_STK, AO>& sh = sh_all[warp];
     // spill area of this warp: [depth][slot]
     if (lane == 0) sh.ovf = p.pool_overflow + (size_t)(blockIdx.x * (TR_BLOCK / 32) + (uint32_t)warp) * (size_t)(PL_S * PL_OVF);
-    const float3 o = f3(p.cam.vi[12], p.cam.vi[13], p.cam.vi[14]);     // ray_gen.rgen:22: every primary ray starts at the camera
+    const float3 cam_o = f3(p.cam.vi[12], p.cam.vi[13], p.cam.vi[14]);     // ray_gen.rgen:22: every primary ray starts at the camera
+    auto org = [&](uint32_t s) -> float3 { return AO ? f3(sh.org[0][s], sh.org[1][s], sh.org[2][s]) : cam_o; };
+    const float ray_tmin = AO ? VKHRT_AO_T_MIN : p.tmin;
 
     // the ray this lane traverses (cur == R2_IDLE: none)
     uint32_t slot = 0, cur = R2_IDLE;
@@ -603,6 +609,7 @@ __global__ void __launch_bounds__(TR_BLOCK, MINB) trace_pool_kernel(const TraceP
         if (cur == R2_IDLE && rank < nR) {
             slot = dequeue(Q_READY, nR, rank);
             id = f3(sh.dir[3][slot], sh.dir[4][slot], sh.dir[5][slot]);
+            const float3 o = org(slot);
             noid = f3(-(o.x * id.x), -(o.y * id.y), -(o.z * id.z));
             tcur = sh.tcur[slot]; cur = sh.cur[slot]; sp = sh.sp[slot]; lo = sh.lo[slot];
         }
@@ -648,8 +655,8 @@ __global__ void __launch_bounds__(TR_BLOCK, MINB) trace_pool_kernel(const TraceP
                         const float4 q0 = __ldg(nd), q1 = __ldg(nd + 1), q2 = __ldg(nd + 2), q3 = __ldg(nd + 3);
                         if (STATS) st_nodes++;
                         float tn0, tn1;
-                        const bool h0 = slab_test(xyz(q0), xyz(q1), id, noid, p.tmin, tcur, &tn0);
-                        const bool h1 = slab_test(xyz(q2), xyz(q3), id, noid, p.tmin, tcur, &tn1);
+                        const bool h0 = slab_test(xyz(q0), xyz(q1), id, noid, ray_tmin, tcur, &tn0);
+                        const bool h1 = slab_test(xyz(q2), xyz(q3), id, noid, ray_tmin, tcur, &tn1);
                         const uint32_t c0 = __float_as_uint(q0.w), c1 = __float_as_uint(q1.w);
                         both = h0 && h1;
                         const bool second = both ? (tn1 < tn0) : h1;
@@ -680,6 +687,7 @@ __global__ void __launch_bounds__(TR_BLOCK, MINB) trace_pool_kernel(const TraceP
             if (act) {
                 s = dequeue(Q_LEAF, nL, (uint32_t)lane);
                 const float3 d = f3(sh.dir[0][s], sh.dir[1][s], sh.dir[2][s]);
+                const float3 o = org(s);
                 const uint32_t pos = sh.cur[s] & 0x7FFFFFFFu;
                 if (PH) {
                     const float4 a0 = __ldg(p.primA + 2 * (size_t)pos), a1 = __ldg(p.primA + 2 * (size_t)pos + 1);
@@ -692,7 +700,7 @@ __global__ void __launch_bounds__(TR_BLOCK, MINB) trace_pool_kernel(const TraceP
                     // reportIntersectionEXT interval [tMin, tCurrent] + tie rule (smaller primitive id), as trace_kernel's `commit`
                     auto commit = [&](float t, float u, uint32_t prim) {
                         const float tc = sh.tcur[s];
-                        if (t >= p.tmin && (t < tc || (t == tc && prim < sh.last_group[s]))) { sh.tcur[s] = t; sh.last_group[s] = prim; sh.best_pos[s] = pos; sh.best_u[s] = u; }
+                        if (t >= ray_tmin && (t < tc || (t == tc && prim < sh.last_group[s]))) { sh.tcur[s] = t; sh.last_group[s] = prim; sh.best_pos[s] = pos; sh.best_u[s] = u; }
                     };
                     if (TECH == VKHRT_TECHNIQUE_LSS) {
                         const float4 a0 = __ldg(p.primA + 2 * (size_t)pos), a1 = __ldg(p.primA + 2 * (size_t)pos + 1);
@@ -739,7 +747,7 @@ __global__ void __launch_bounds__(TR_BLOCK, MINB) trace_pool_kernel(const TraceP
                 const float4 b0 = __ldg(p.primB + 2 * (size_t)pos), b1 = __ldg(p.primB + 2 * (size_t)pos + 1);
                 Bezier w;
                 w.p0 = xyz(a0); w.p1 = xyz(b0); w.p2 = xyz(b1); w.p3 = xyz(a1);
-                march_begin(ms, make_ray_frame(d), o, w);
+                march_begin(ms, make_ray_frame(d), org(m_slot), w);
                 float rfilter = p.radius;
                 if (TAPER) { const float2 rr = __ldg(p.primR + pos); ms.r0 = rr.x; ms.dr = rr.y - rr.x; rfilter = fmaxf(rr.x, rr.y); }   // per-vertex radii (§4.10)
                 if (quarter_chords_near_ray(ms.c, rfilter, b0.w)) mhave = true;
@@ -765,7 +773,8 @@ __global__ void __launch_bounds__(TR_BLOCK, MINB) trace_pool_kernel(const TraceP
                         mhave = false; fin = true;
                         const uint32_t pos = sh.cur[m_slot] & 0x7FFFFFFFu;       // the slot still points at the candidate's leaf
                         // hair_intersection.rint:146-148 (report only tHit > 0), reportIntersectionEXT interval, tie rule of `commit`
-                        if (r == MARCH_HIT && t > 0.0f && t >= p.tmin) {
+                        bool took = false;
+                        if (r == MARCH_HIT && t > 0.0f && t >= ray_tmin) {
                             const float tc = sh.tcur[m_slot];
                             bool take_it = t < tc;
                             if (t == tc) {
@@ -773,9 +782,10 @@ __global__ void __launch_bounds__(TR_BLOCK, MINB) trace_pool_kernel(const TraceP
                                 const uint32_t prim = __float_as_uint(__ldg(p.primA + 2 * (size_t)pos + 1).w);
                                 take_it = bpos == PRIM_NONE || prim < __float_as_uint(__ldg(p.primA + 2 * (size_t)bpos + 1).w);
                             }
-                            if (take_it) { sh.tcur[m_slot] = t; sh.best_pos[m_slot] = pos; sh.best_u[m_slot] = u; }
+                            if (take_it) { sh.tcur[m_slot] = t; sh.best_pos[m_slot] = pos; sh.best_u[m_slot] = u; took = true; }
                         }
-                        next = pop_parked(m_slot);          // culls against the hit just committed
+                        // gl_RayFlagsTerminateOnFirstHitEXT (occlusion rays): the first accepted hit ends the ray
+                        next = (AO && took) ? R2_DONE : pop_parked(m_slot);          // (the pop culls against the hit just committed)
                     }
                 }
                 route(fin, m_slot, next);
@@ -797,12 +807,16 @@ __global__ void __launch_bounds__(TR_BLOCK, MINB) trace_pool_kernel(const TraceP
                 float rt = __int_as_float(0x7f800000), ru = 0.0f;
                 float3 rn = f3(0, 0, 0);
                 uint32_t rprim = PRIM_NONE, rseg = VKHRT_MISS_SEGMENT, rflags = 0u, oi = 0u;
-                if (act_d) {
+                if (AO) {
+                    // one more occluded ray for the pixel; several passes of a pixel can be in flight together (n_batch > 1): integer atomic
+                    if (act_d && sh.best_pos[s] != PRIM_NONE) { atomicAdd(p.ao_occluded + sh.out_idx[s], 1u); if (STATS) st_hits++; }
+                } else if (act_d) {
                     const uint32_t pos = sh.best_pos[s];
                     oi = sh.out_idx[s];
                     if (pos != PRIM_NONE) {
                         rt = sh.tcur[s]; ru = sh.best_u[s];
                         const float3 d = f3(sh.dir[0][s], sh.dir[1][s], sh.dir[2][s]);
+                        const float3 o = cam_o;
                         if (PH) {
                             // hair_intersection.rint:74-76 from the committed (t, u)
                             const float4 a0 = __ldg(p.primA + 2 * (size_t)pos), a1 = __ldg(p.primA + 2 * (size_t)pos + 1);
@@ -829,7 +843,7 @@ __global__ void __launch_bounds__(TR_BLOCK, MINB) trace_pool_kernel(const TraceP
                         if (STATS) st_hits++;
                     }
                 }
-                emit(act_d, oi, rt, rseg, ru, rn, rprim, rflags);
+                if (!AO) emit(act_d, oi, rt, rseg, ru, rn, rprim, rflags);
             }
             const bool want = (act_d || act_f) && !exhausted;
             const unsigned wm = __ballot_sync(FULL, want);
@@ -840,6 +854,33 @@ __global__ void __launch_bounds__(TR_BLOCK, MINB) trace_pool_kernel(const TraceP
             uint32_t pad_idx = 0u;
             if (want) {
                 const unsigned long long slot64 = p.slot_begin + base + (unsigned)__popc(wm & lt);
+                if (AO) {
+                    if (slot64 < (unsigned long long)p.n_slots) {
+                        // an occlusion ray of pass a_idx from the pixel's primary hit record (the refill step of trace_kernel<.., SRC_AO>)
+                        uint32_t a_idx = p.ao_index, ls = (uint32_t)slot64;
+                        if (p.n_batch > 1u) { const uint32_t b = ls / p.slots_per_sample; ls -= b * p.slots_per_sample; a_idx += b; }
+                        const PixelRef q = slot_to_pixel(p, ls);
+                        if (q.valid) {
+                            const float4* h = reinterpret_cast<const float4*>(p.ao_hits + q.out);
+                            const float4 h0 = __ldg(h), h1 = __ldg(h + 1);
+                            if (__float_as_uint(h1.w) & FLAG_HIT) {                 // a miss pixel spawns nothing
+                                float3 po, pd;
+                                primary_ray(p.cam, p.W, p.H, q.px, q.py, p.sx, p.sy, &po, &pd);
+                                const float3 n = f3(h0.w, h1.x, h1.y);
+                                const float3 ro = fmadd3(p.ao_bias, n, fmadd3(h0.x, pd, po));
+                                const float3 d = ao_direction(n, q.py * p.W + q.px, p.ao_sample, a_idx);
+                                sh.org[0][s] = ro.x; sh.org[1][s] = ro.y; sh.org[2][s] = ro.z;
+                                sh.dir[0][s] = d.x; sh.dir[1][s] = d.y; sh.dir[2][s] = d.z;
+                                sh.dir[3][s] = safe_rcp(d.x); sh.dir[4][s] = safe_rcp(d.y); sh.dir[5][s] = safe_rcp(d.z);
+                                sh.tcur[s] = p.ao_distance; sh.cur[s] = 0u; sh.sp[s] = 0; sh.lo[s] = 0;
+                                sh.best_pos[s] = PRIM_NONE; sh.best_u[s] = 0.0f; sh.out_idx[s] = q.out;
+                                sh.last_group[s] = PRIM_NONE;
+                                fresh = true;
+                                if (STATS) st_rays++;
+                            }
+                        }
+                    }
+                } else
                 if (slot64 < (unsigned long long)p.n_slots) {
                     uint32_t b = 0u, ls = (uint32_t)slot64;
                     if (p.n_batch > 1u) { b = ls / p.slots_per_sample; ls -= b * p.slots_per_sample; }
@@ -858,7 +899,7 @@ __global__ void __launch_bounds__(TR_BLOCK, MINB) trace_pool_kernel(const TraceP
                     } else if (p.compact) { padded = true; pad_idx = q.out; }
                 }
             }
-            if (p.compact) emit(padded, pad_idx, __int_as_float(0x7f800000), VKHRT_MISS_SEGMENT, 0.0f, f3(0, 0, 0), PRIM_NONE, FLAG_PADDING);
+            if (!AO && p.compact) emit(padded, pad_idx, __int_as_float(0x7f800000), VKHRT_MISS_SEGMENT, 0.0f, f3(0, 0, 0), PRIM_NONE, FLAG_PADDING);
             if (wm && p.slot_begin + base + (unsigned)__popc(wm) >= (unsigned long long)p.n_slots) exhausted = true;
             __syncwarp();
             enqueue(Q_READY, nR, fresh, s);
@@ -1031,7 +1072,7 @@ static void fill_params(const DeviceScene& sc, const VkhrtFrameDesc& f, const Re
 struct Tunables {
     int refill_threshold, min_blocks, blocks_per_sm, w_node, w_leaf, w_march;
     int pool, pool_stats, pool_min_ratio, pool_node_lanes, pool_batch_lanes, pool_node_min, pool_exit, pool_cfg, pool_host, carveout;
-    int store256, zero_copy, linewise, line_shift, sample_batch, pool_lss, pool_dots, early_copy, pool_taper;
+    int store256, zero_copy, linewise, line_shift, sample_batch, pool_lss, pool_dots, early_copy, pool_taper, pool_ao;
 };
 static float bits_to_float(uint32_t u) { float f; std::memcpy(&f, &u, 4); return f; }
 static int env_int(const char* name, int def) { const char* v = getenv(name); return v ? atoi(v) : def; }
@@ -1058,6 +1099,7 @@ static const Tunables& tun()
         // long-scoreboard stalls double; C4 1059 vs 1040, e2e 996 vs 1020), so both default to the lane-bound kernel
         x.pool_lss = env_int("VKHRT_POOL_LSS", 0);
         x.pool_dots = env_int("VKHRT_POOL_DOTS", 0);
+        x.pool_ao = env_int("VKHRT_POOL_AO", 1);                // ambient-occlusion passes of Phantom scenes through the pool kernel
         x.pool_taper = env_int("VKHRT_POOL_TAPER", 1);          // Phantom scenes with per-vertex radii through the pool kernel too
         x.pool_host = env_int("VKHRT_POOL_HOST", 0);
         x.carveout = env_int("VKHRT_CARVEOUT", -1);
@@ -1116,12 +1158,12 @@ static int launch_trace_t(DeviceScene& sc, TraceParams& p, cudaStream_t st)
     count_launch();
     return VKHRT_OK;
 }
-template <int TECH, bool STATS, int PL_S, int PL_STK, int MINB = PL_MINB, bool TAPER = false>
+template <int TECH, bool STATS, int PL_S, int PL_STK, int MINB = PL_MINB, bool TAPER = false, bool AO = false>
 static int launch_pool_t(DeviceScene& sc, TraceParams& p, cudaStream_t st)
 {
     const int carve = tun().carveout;
-    if (carve >= 0) VK_CUDA(cudaFuncSetAttribute(trace_pool_kernel<TECH, STATS, PL_S, PL_STK, MINB, TAPER>, cudaFuncAttributePreferredSharedMemoryCarveout, carve));
-    int per_sm = blocks_per_sm(trace_pool_kernel<TECH, STATS, PL_S, PL_STK, MINB, TAPER>, sc.device);
+    if (carve >= 0) VK_CUDA(cudaFuncSetAttribute(trace_pool_kernel<TECH, STATS, PL_S, PL_STK, MINB, TAPER, AO>, cudaFuncAttributePreferredSharedMemoryCarveout, carve));
+    int per_sm = blocks_per_sm(trace_pool_kernel<TECH, STATS, PL_S, PL_STK, MINB, TAPER, AO>, sc.device);
     if (tun().blocks_per_sm > 0) per_sm = std::min(per_sm, tun().blocks_per_sm);
     unsigned long long want = ((unsigned long long)(p.n_slots - p.slot_begin) + TR_BLOCK - 1) / TR_BLOCK;
     unsigned grid = (unsigned)std::min<unsigned long long>((unsigned long long)sc.sm_count * per_sm, std::max<unsigned long long>(want, 1ull));
@@ -1133,7 +1175,7 @@ static int launch_pool_t(DeviceScene& sc, TraceParams& p, cudaStream_t st)
         sc.pool_overflow_n = ovf;
     }
     p.pool_overflow = sc.d_pool_overflow;
-    trace_pool_kernel<TECH, STATS, PL_S, PL_STK, MINB, TAPER><<<grid, TR_BLOCK, 0, st>>>(p);
+    trace_pool_kernel<TECH, STATS, PL_S, PL_STK, MINB, TAPER, AO><<<grid, TR_BLOCK, 0, st>>>(p);
     sc.last_trace_was_pool = true;
     count_launch();
     return VKHRT_OK;
@@ -1152,6 +1194,13 @@ static int launch_pool(DeviceScene& sc, TraceParams& p, cudaStream_t st)
         }
     }
 }
+// ambient-occlusion passes through the pool kernel: 64 slots per warp (a slot also carries the ray's origin)
+template <bool STATS, bool TAPER>
+static int launch_pool_ao(DeviceScene& sc, TraceParams& p, cudaStream_t st)
+{
+    return launch_pool_t<VKHRT_TECHNIQUE_PHANTOM, STATS, 64, 4, PL_MINB, TAPER, true>(sc, p, st);
+}
+
 // does the per-warp ray-pool kernel serve this scene's primary rays? (Phantom, with or without per-vertex radii; LSS / DOTS behind their switches)
 static bool pool_serves(const DeviceScene& sc)
 {
@@ -1167,6 +1216,10 @@ static int launch_trace(DeviceScene& sc, TraceParams& p, cudaStream_t st)
     sc.last_trace_was_pool = false;
     p.hits_aligned32 = (((uintptr_t)p.hits & 31u) == 0u ? 1u : 0u) | (((uintptr_t)p.hits_mirror & 31u) == 0u ? 2u : 0u);
     if (tun().store256 == 0) p.hits_aligned32 = 0u;
+    // occlusion rays of a Phantom scene, enough of them to fill the pool: the pool kernel's ambient-occlusion variant
+    if (SRC == SRC_AO && ANYHIT && sc.technique == VKHRT_TECHNIQUE_PHANTOM && tun().pool && tun().pool_ao && p.n_prims && (!STATS || tun().pool_stats) &&
+        (unsigned long long)(p.n_slots - p.slot_begin) >= (unsigned long long)tun().pool_min_ratio * sc.sm_count * 32ull * 56ull)
+        return sc.tapered() ? launch_pool_ao<STATS, true>(sc, p, st) : launch_pool_ao<STATS, false>(sc, p, st);
     if (sc.tapered()) {
         // per-vertex radii (Phantom, DOTS): the lane-bound kernel with the taper terms compiled in (LSS always carries its radii)
         if (sc.technique == VKHRT_TECHNIQUE_PHANTOM) {
