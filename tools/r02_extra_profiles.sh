@@ -22,6 +22,8 @@ else:
         for k in range(4): sc.render_into(f, d.data_ptr(), None)
         torch.cuda.synchronize()
 PY
-timeout 600 ncu --set full --clock-control none --import-source on -k regex:"trace_kernel" -s 2 -c 1 -f -o gpurun_out/r02_ao python extra_tmp.py ao > gpurun_out/r02_ao.log 2>&1; echo "ao rc=$?"
+# the AO passes of a Phantom frame run in the pool kernel's AO variant (64 slots); VKHRT_POOL_AO=0 gives the lane-bound kernel for comparison
+timeout 600 ncu --set full --clock-control none --import-source on --kernel-name-base demangled -k regex:"trace_pool_kernel.*int.64" -s 2 -c 1 -f -o gpurun_out/r02_ao_pool python extra_tmp.py ao > gpurun_out/r02_ao_pool.log 2>&1; echo "ao pool rc=$?"
+VKHRT_POOL_AO=0 timeout 600 ncu --set full --clock-control none --import-source on -k regex:"trace_kernel" -s 2 -c 1 -f -o gpurun_out/r02_ao python extra_tmp.py ao > gpurun_out/r02_ao.log 2>&1; echo "ao rc=$?"
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:"trace_pool_kernel" -s 2 -c 1 -f -o gpurun_out/r02_taper python extra_tmp.py taper > gpurun_out/r02_taper.log 2>&1; echo "taper rc=$?"
 rm -f extra_tmp.py
