@@ -186,3 +186,17 @@ def test_headless_multi_model_scene(V, O, tmp_path):
     lines = r.stdout.split("\n")
     assert f"  mesh 0: {int((mesh == 0).sum())} rays" in lines and f"  mesh 1: {int((mesh == 1).sum())} rays" in lines
     assert (mesh == 1).sum() > 0
+
+
+@pytest.mark.gpu
+def test_headless_frames_in_flight(V, tmp_path):
+    """`--in-flight`: the reference's frame loop (renderer.cpp:85-119: MAX_FRAMES_IN_FLIGHT frames submitted, the oldest waited on) through
+    Renderer::Submit / Wait -> vkhrt_render_submit / _wait.  The last frame's records equal the blocking path's."""
+    W, H = 320, 200
+    a, b = tmp_path / "blocking.bin", tmp_path / "inflight.bin"
+    common = ["--model", "synthetic:curly:3000:16", "--technique", "phantom", "--size", f"{W}x{H}", "--no-image"]
+    r1 = subprocess.run([EXE, *common, "--frames", "2", "--hits", str(a)], capture_output=True, text=True)
+    r2 = subprocess.run([EXE, *common, "--frames", "7", "--in-flight", "--hits", str(b)], capture_output=True, text=True)
+    assert r1.returncode == 0 and r2.returncode == 0, r1.stderr + r2.stderr
+    assert "7 frames, 2 in flight" in r2.stdout
+    assert a.read_bytes() == b.read_bytes() and len(a.read_bytes()) == W * H * 32

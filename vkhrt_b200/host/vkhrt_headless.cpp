@@ -21,7 +21,7 @@ static void usage()
 {
     std::puts("usage: vkhrt_headless --model <file.gltf | file.glb | file.obj | file.hair | synthetic:<straight|curly>:<strands>:<segments>[:seed]>  (repeat --model for a multi-mesh scene)\n"
               "                      [--technique phantom|lss|dots] [--size WxH] [--spp N] [--debug-primid | --material]\n"
-              "                      [--frames N] [--no-image | --no-hits] [--ppm out.ppm] [--png out.png] [--hits out.bin] [--device D] [--gpus N]\n"
+              "                      [--frames N] [--in-flight] [--no-image | --no-hits] [--ppm out.ppm] [--png out.png] [--hits out.bin] [--device D] [--gpus N]\n"
               "                      [--env procedural|file.hdr] [--ao N] [--lod split,merge,curve_merge]");
 }
 
@@ -32,6 +32,7 @@ int main(int argc, char** argv)
     unsigned lod[3] = {0, 0, 0};
     RendererInitInfo info;
     int frames = 1, device = 0, gpus = 1;
+    bool inFlight = false;
     for (int i = 1; i < argc; ++i) {
         const std::string a = argv[i];
         auto next = [&]() -> const char* { if (i + 1 >= argc) { usage(); std::exit(2); } return argv[++i]; };
@@ -45,6 +46,7 @@ int main(int argc, char** argv)
         else if (a == "--no-image") info.wantImage = false;                   // hit records only (BASELINE configs[1])
         else if (a == "--no-hits") info.wantHits = false;
         else if (a == "--frames") frames = std::atoi(next());
+        else if (a == "--in-flight") inFlight = true;                        // keep VKHRT_FRAMES_IN_FLIGHT frames submitted (renderer.cpp:85-119)
         else if (a == "--ppm") ppm = next();
         else if (a == "--png") png = next();
         else if (a == "--env") info.environmentMap = next();
@@ -76,6 +78,31 @@ int main(int argc, char** argv)
             std::shared_ptr<Model> r = models.size() > 1 ? ModelLoader(device + g).LoadFromFiles(models, tech) : ModelLoader(device + g).LoadFromFile(model, tech, lod[0], lod[1], lod[2]);
             if (!r) return 1;
             renderer.AddReplica(r);
+        }
+        if (inFlight) {
+            // the reference's frame loop: submit, and wait for the oldest frame once VKHRT_FRAMES_IN_FLIGHT are outstanding
+            for (int k = 0; k < VKHRT_FRAMES_IN_FLIGHT; ++k) renderer.Submit();      // untimed: the page-locked buffer sets are allocated here
+            for (int k = 0; k < VKHRT_FRAMES_IN_FLIGHT; ++k) renderer.Wait();
+            auto t0 = std::chrono::steady_clock::now();
+            int last = 0, outstanding = 0;
+            for (int f = 0; f < frames; ++f) {
+                if (outstanding == VKHRT_FRAMES_IN_FLIGHT) { last = renderer.Wait(); --outstanding; }
+                renderer.Submit(); ++outstanding;
+            }
+            while (outstanding-- > 0) last = renderer.Wait();
+            const double wall = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+            std::printf("%d frames, %d in flight: %.3f ms per frame wall  (%.1f Mrays/s end to end)\n", frames, VKHRT_FRAMES_IN_FLIGHT, wall / frames,
+                        (double)info.width * info.height * info.spp * frames / (wall * 1e3));
+            size_t n_hit = 0;
+            for (const VkhrtHit& h : renderer.GetFlightHits(last)) n_hit += h.flags & 1u;
+            std::printf("hits: %zu of %zu rays\n", n_hit, renderer.GetFlightHits(last).size());
+            if (!hits_path.empty()) {
+                std::FILE* fp = std::fopen(hits_path.c_str(), "wb");
+                if (!fp) { std::fprintf(stderr, "[FILE] cannot write %s\n", hits_path.c_str()); return 1; }
+                std::fwrite(renderer.GetFlightHits(last).data(), sizeof(VkhrtHit), renderer.GetFlightHits(last).size(), fp);
+                std::fclose(fp);
+            }
+            return 0;
         }
         for (int f = 0; f < frames; ++f) {
             auto f0 = std::chrono::steady_clock::now();

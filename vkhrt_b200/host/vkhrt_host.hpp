@@ -319,13 +319,7 @@ public:
     void Render()
     {
         if (_models.empty()) throw std::runtime_error("Renderer::Render: no model");
-        VkhrtFrameDesc f {};
-        _flyCamera->CameraUniformData(f.view_inverse, f.proj_inverse);
-        f.width = _info.width; f.height = _info.height; f.spp = _info.spp; f.shade_mode = _info.shadeMode;
-        std::memcpy(f.miss_rgb, _info.missColor, sizeof(f.miss_rgb));
-        f.output_memory = VKHRT_MEM_HOST;
-        f.miss_mode = _env.empty() ? VKHRT_MISS_CONSTANT : VKHRT_MISS_ENVIRONMENT;
-        f.ao_samples = _info.aoSamples;
+        VkhrtFrameDesc f = FrameDesc();
         const size_t n = (size_t)_info.width * _info.height;
         if (_info.wantHits) _hits.resize(n);
         if (_info.wantImage) _image.resize(n * 4);
@@ -338,6 +332,30 @@ public:
                   "vkhrt_render_multi");
         }
     }
+    // Frames in flight (renderer.cpp:85-97,119: MAX_FRAMES_IN_FLIGHT frames submitted, the fence of the oldest waited on): Submit() enqueues
+    // a frame into buffer set (frame % VKHRT_FRAMES_IN_FLIGHT) and returns; Wait() completes the oldest one and returns its buffer index.
+    // While frame k's records cross PCIe on the copy engine, frame k+1 is already traversing.  One model, no replicas.
+    void Submit()
+    {
+        if (_models.empty()) throw std::runtime_error("Renderer::Submit: no model");
+        if (!_replicas.empty()) throw std::runtime_error("Renderer::Submit: frames in flight are a single-GPU path");
+        VkhrtFrameDesc f = FrameDesc();
+        const size_t n = (size_t)_info.width * _info.height;
+        const int k = (int)(_submitted % VKHRT_FRAMES_IN_FLIGHT);
+        if (_info.wantHits) _flightHits[k].resize(n);
+        if (_info.wantImage) _flightImage[k].resize(n * 4);
+        Check(vkhrt_render_submit(_models[0]->Handle(), &f, _info.wantHits ? _flightHits[k].data() : nullptr, _info.wantImage ? _flightImage[k].data() : nullptr),
+              "vkhrt_render_submit");
+        ++_submitted;
+    }
+    int Wait()
+    {
+        if (_waited == _submitted) throw std::runtime_error("Renderer::Wait: no frame outstanding");
+        Check(vkhrt_render_wait(_models[0]->Handle()), "vkhrt_render_wait");
+        return (int)(_waited++ % VKHRT_FRAMES_IN_FLIGHT);
+    }
+    [[nodiscard]] const HostBuffer<VkhrtHit>& GetFlightHits(int k) const { return _flightHits[k]; }
+    [[nodiscard]] const HostBuffer<uint8_t>& GetFlightImage(int k) const { return _flightImage[k]; }
     [[nodiscard]] const HostBuffer<VkhrtHit>& GetHits() const { return _hits; }
     [[nodiscard]] const HostBuffer<uint8_t>& GetImage() const { return _image; }     // RGBA8, row-major, row 0 = top
     [[nodiscard]] const RendererInitInfo& GetInitInfo() const { return _info; }
@@ -357,6 +375,21 @@ public:
     }
 
 private:
+    // UpdateCameraResource (renderer.cpp:189-195) + the launch size of traceRaysKHR
+    [[nodiscard]] VkhrtFrameDesc FrameDesc() const
+    {
+        VkhrtFrameDesc f {};
+        _flyCamera->CameraUniformData(f.view_inverse, f.proj_inverse);
+        f.width = _info.width; f.height = _info.height; f.spp = _info.spp; f.shade_mode = _info.shadeMode;
+        std::memcpy(f.miss_rgb, _info.missColor, sizeof(f.miss_rgb));
+        f.output_memory = VKHRT_MEM_HOST;
+        f.miss_mode = _env.empty() ? VKHRT_MISS_CONSTANT : VKHRT_MISS_ENVIRONMENT;
+        f.ao_samples = _info.aoSamples;
+        return f;
+    }
+    HostBuffer<VkhrtHit> _flightHits[VKHRT_FRAMES_IN_FLIGHT];
+    HostBuffer<uint8_t> _flightImage[VKHRT_FRAMES_IN_FLIGHT];
+    uint64_t _submitted = 0, _waited = 0;
     RendererInitInfo _info;
     std::vector<float> _env;
     uint32_t _envW = 0, _envH = 0;
